@@ -1,0 +1,211 @@
+/* ssv_b200 — C ABI of the B200-native self-supervised loss hot path.
+ *
+ * Drop-in boundary for the loss layer of NightShade99/Self-Supervised-Vision
+ * (reference `utils/losses.py` + the ring buffers of `models/moco.py`, `models/swav.py`).
+ * The reference is pure Python/PyTorch and has no FFI of its own; these entry points are
+ * what a `ctypes` binding added to the reference's `utils/losses.py` would bind (see
+ * INTEGRATION.md).  Every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers (current device), fp32 row-major unless noted;
+ *    `ld*` are leading dimensions in ELEMENTS; rows must be 16-byte aligned
+ *    (pointer % 16 == 0, ld % 4 == 0);
+ *  - the caller owns every buffer (inputs, outputs, `saved`, `workspace`); the library never
+ *    allocates or frees device memory and keeps no pointer after returning;
+ *  - `saved` is an opaque blob written by `*_fwd` and read by the matching `*_bwd`
+ *    (size from `*_saved_bytes`); `workspace` is scratch (size from `*_workspace_bytes`);
+ *  - all work is enqueued asynchronously on `stream` (a `cudaStream_t`); no host sync, no
+ *    global mutable state: entry points are re-entrant (autograd calls bwd from its own thread);
+ *  - `loss` and `grad_out` are device scalars (fp32) so no device->host sync is ever needed;
+ *  - return 0 on success, <0 for argument errors detected before launch (see codes),
+ *    >0 = a `cudaError_t`.  No exceptions, no exit(), no CPU fallback: on a non-sm_100
+ *    device every compute entry point returns SSVB_ERR_ARCH.
+ */
+#ifndef SSV_B200_H_
+#define SSV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSVB_VERSION 100
+
+enum {
+  SSVB_OK = 0,
+  SSVB_ERR_INVALID = -1,     /* null pointer / non-positive size / bad flag */
+  SSVB_ERR_ALIGNMENT = -2,   /* pointer or leading dimension not 16-byte aligned */
+  SSVB_ERR_UNSUPPORTED = -3, /* shape outside what the sm_100a kernels cover (e.g. d > 128 for tensor-core losses) */
+  SSVB_ERR_WORKSPACE = -4,   /* workspace / saved buffer too small */
+  SSVB_ERR_ARCH = -5,        /* current device is not compute capability 10.x */
+  SSVB_ERR_DRIVER = -6       /* cuTensorMapEncodeTiled unavailable / failed */
+};
+
+int ssvb_version(void);
+const char* ssvb_strerror(int rc);
+/* 0 if the current device can run the kernels (compute capability 10.x) */
+int ssvb_device_check(void);
+
+/* ---------------------------------------------------------------------------------------
+ * a1  SimCLR NT-Xent — replaces SimclrLoss.forward (utils/losses.py:15-46; ctor :10-13;
+ *     call site models/simclr.py:90) and the contrastive term of RelicLoss (:163-194).
+ *     zi, zj: [n x d].  loss = mean over 2n rows of (LSE_{b != a} s_ab - s_{a,partner(a)}),
+ *     s = Zhat Zhat^T / temperature.  The 2n x 2n similarity matrix is never written to HBM.
+ *     d <= 128 (zero-padded to a multiple of 64 internally).
+ * ------------------------------------------------------------------------------------- */
+size_t ssvb_ntxent_saved_bytes(int64_t n, int64_t d);
+size_t ssvb_ntxent_workspace_bytes(int64_t n, int64_t d);
+int ssvb_ntxent_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                    int normalize, float temperature, float* loss, void* saved, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* dzi/dzj: [n x d] gradients (overwritten).  grad_out: device scalar dL/dloss. */
+int ssvb_ntxent_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                    int normalize, float temperature, const float* grad_out, const void* saved, float* dzi,
+                    float* dzj, int64_t ld_dzi, int64_t ld_dzj, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a1/e  Global-batch NT-Xent, row-sharded over ranks (the reference has no
+ *     multi-GPU path: semantics = SimclrLoss on the rank-order concatenation of all inputs).
+ *     Stage 1 (prep): each rank normalises its n_local rows of both views into its slot of the
+ *       gathered bf16 matrix `zhat_all` [2*n_global(+pad) x d_pad] (row a of view i at
+ *       rank_row0 + a, view j at n_global + rank_row0 + a) -> caller all-gathers the slots.
+ *     Stage 2 (rows_fwd): local rows against all columns -> lse for local rows + local loss sum
+ *       (caller all-reduces `loss_sum` and all-gathers `stat_all`).
+ *     Stage 3 (rows_bwd): complete gradient of the local rows (no reduce-scatter needed).
+ *     Layout helpers below give sizes/offsets so the host side never hard-codes them.
+ * ------------------------------------------------------------------------------------- */
+int64_t ssvb_ntxent_dpad(int64_t d);                 /* padded feature dim of zhat_all */
+int64_t ssvb_ntxent_mpad(int64_t n_global);          /* padded row count of zhat_all / stat_all */
+size_t ssvb_ntxent_dist_workspace_bytes(int64_t n_global, int64_t n_local, int64_t d);
+int ssvb_ntxent_dist_prep(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                          int64_t ld_zj, int normalize, int64_t n_global, int64_t rank_row0,
+                          void* zhat_all /* bf16 [mpad x dpad] */, float* inv_norm_local /* [2*n_local] */,
+                          void* stream);
+/* stat_local: [2*n_local] per-row log2-domain LSE of the local rows (view i rows then view j rows);
+ * loss_sum: device scalar, sum over local rows of (lse - pos) (divide by 2*n_global after all-reduce). */
+int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t n_global, int64_t n_local, int64_t rank_row0,
+                              int64_t d, int normalize, float temperature, float* stat_local,
+                              float* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
+/* stat_all: [mpad] log2-domain LSE of ALL rows in zhat_all row order (padding entries ignored). */
+int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                              int64_t ld_zj, int normalize, float temperature, int64_t n_global,
+                              int64_t rank_row0, const void* zhat_all, const float* stat_all,
+                              const float* inv_norm_local, const float* grad_out, float* dzi, float* dzj,
+                              int64_t ld_dzi, int64_t ld_dzj, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a2  MoCo InfoNCE — replaces MocoLoss.forward (utils/losses.py:56-72; call models/moco.py:117).
+ *     query, keys: [n x d]; queue: [k x d] rows used AS STORED (no re-normalisation, no grad).
+ *     queue_bf16 (optional, may be NULL): a bf16 shadow [k x dpad] (dpad = ssvb_ntxent_dpad(d),
+ *     zero padded) maintained by ssvb_ring_enqueue; when NULL the fp32 queue is converted
+ *     into the workspace on every call.
+ * ------------------------------------------------------------------------------------- */
+size_t ssvb_moco_saved_bytes(int64_t n, int64_t k, int64_t d);
+size_t ssvb_moco_workspace_bytes(int64_t n, int64_t k, int64_t d);
+int ssvb_moco_fwd(const float* query, const float* keys, const float* queue, const void* queue_bf16, int64_t n,
+                  int64_t k, int64_t d, int64_t ld_q, int64_t ld_k, int64_t ld_queue, int normalize,
+                  float temperature, float* loss, void* saved, void* workspace, size_t workspace_bytes,
+                  void* stream);
+int ssvb_moco_bwd(const float* query, const float* keys, const float* queue, const void* queue_bf16, int64_t n,
+                  int64_t k, int64_t d, int64_t ld_q, int64_t ld_k, int64_t ld_queue, int normalize,
+                  float temperature, const float* grad_out, const void* saved, float* dquery, float* dkeys,
+                  int64_t ld_dq, int64_t ld_dk, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a3/a7  Ring-buffer enqueue — replaces MemoryBank.add_batch (models/moco.py:31-36,
+ *     normalize=1) and FeatureBank.add_vectors (models/swav.py:70-75, normalize=0).
+ *     Row i of `batch` is written to bank row (ptr + i) mod size; when n > size only the
+ *     last writer of each slot survives (same as the reference's sequential loop).
+ *     bank_bf16 (optional): bf16 shadow [size x dpad] kept in sync.  The new pointer
+ *     (ptr + n) mod size is returned through *new_ptr (HOST int64, bit-exact bookkeeping).
+ * ------------------------------------------------------------------------------------- */
+int ssvb_ring_enqueue(float* bank, void* bank_bf16, int64_t size, int64_t d, int64_t ld_bank,
+                      const float* batch, int64_t n, int64_t ld_batch, int64_t ptr, int normalize,
+                      int64_t* new_ptr, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a4  Barlow Twins — replaces BarlowLoss.forward (utils/losses.py:127-142; call models/barlow.py:90).
+ *     z_i, z_j: [n x d]; unbiased column standardisation, C = Xi^T Xj / n,
+ *     loss = sum_a (C_aa-1)^2 + lambda * sum_{a!=b} C_ab^2.  d % 8 == 0, n % 8 == 0.
+ * ------------------------------------------------------------------------------------- */
+size_t ssvb_barlow_saved_bytes(int64_t n, int64_t d);
+size_t ssvb_barlow_workspace_bytes(int64_t n, int64_t d);
+int ssvb_barlow_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                    int normalize, float lambda, float* loss, void* saved, void* workspace,
+                    size_t workspace_bytes, void* stream);
+int ssvb_barlow_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                    int normalize, float lambda, const float* grad_out, const void* saved, float* dzi,
+                    float* dzj, int64_t ld_dzi, int64_t ld_dzj, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a5  Sinkhorn-Knopp codes — replaces SwavLoss.compute_codes_sinkhorn (utils/losses.py:213-224).
+ *     scores: [b x k] -> codes [b x k] (rows sum to 1).  ld % 4 == 0 not required.
+ * ------------------------------------------------------------------------------------- */
+size_t ssvb_sinkhorn_workspace_bytes(int64_t b, int64_t k);
+int ssvb_sinkhorn(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters,
+                  float* codes, int64_t ld_codes, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a6  SwAV loss — replaces SwavLoss.forward (utils/losses.py:226-235; call models/swav.py:140).
+ *     z1, z2: [nb x d] live rows; bank: [nbank x d] or NULL (appended under both views, no grad);
+ *     prototypes: [k x d].
+ * ------------------------------------------------------------------------------------- */
+size_t ssvb_swav_saved_bytes(int64_t nb, int64_t nbank, int64_t k, int64_t d);
+size_t ssvb_swav_workspace_bytes(int64_t nb, int64_t nbank, int64_t k, int64_t d);
+int ssvb_swav_fwd(const float* z1, const float* z2, const float* bank, const float* prototypes, int64_t nb,
+                  int64_t nbank, int64_t k, int64_t d, int64_t ld_z1, int64_t ld_z2, int64_t ld_bank,
+                  int64_t ld_proto, float temperature, float eps, int n_iters, float* loss, void* saved,
+                  void* workspace, size_t workspace_bytes, void* stream);
+int ssvb_swav_bwd(const float* z1, const float* z2, const float* bank, const float* prototypes, int64_t nb,
+                  int64_t nbank, int64_t k, int64_t d, int64_t ld_z1, int64_t ld_z2, int64_t ld_bank,
+                  int64_t ld_proto, float temperature, const float* grad_out, const void* saved, float* dz1,
+                  float* dz2, float* dproto, int64_t ld_dz1, int64_t ld_dz2, int64_t ld_dproto, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a8/a9  Row-dot regression losses.
+ *     kind 0: BYOL nn.MSELoss() mean((o-t)^2)            (models/byol.py:89,129-130)
+ *     kind 1: SimSiamLoss -mean_n sum_k o*t              (utils/losses.py:150-151; models/simsiam.py:126)
+ *     o, t: [n x d].  d_o / d_t may be NULL (no gradient wanted for that operand).
+ * ------------------------------------------------------------------------------------- */
+size_t ssvb_rowdot_workspace_bytes(int64_t n, int64_t d);
+int ssvb_rowdot_fwd(int kind, const float* o, const float* t, int64_t n, int64_t d, int64_t ld_o, int64_t ld_t,
+                    float* loss, void* workspace, size_t workspace_bytes, void* stream);
+int ssvb_rowdot_bwd(int kind, const float* o, const float* t, int64_t n, int64_t d, int64_t ld_o, int64_t ld_t,
+                    const float* grad_out, float* d_o, float* d_t, int64_t ld_do, int64_t ld_dt, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a10  ReLIC KL term — the `alpha * kl_div_loss` part of RelicLoss.forward
+ *     (utils/losses.py:196-201; call models/relic.py:129), reproducing the reference quirk:
+ *     KL = sum_n exp(lq_n) * (lq_n - p_n), p = softmax_n(zi_n.zo_n/tau), lq = log_softmax_n(zj_n.zo_n/tau).
+ *     `kl` receives alpha*KL.  The contrastive term is ssvb_ntxent_*.
+ * ------------------------------------------------------------------------------------- */
+size_t ssvb_relic_kl_saved_bytes(int64_t n);
+size_t ssvb_relic_kl_workspace_bytes(int64_t n);
+int ssvb_relic_kl_fwd(const float* zi, const float* zj, const float* zo, int64_t n, int64_t d, int64_t ld_zi,
+                      int64_t ld_zj, int64_t ld_zo, int normalize, float temperature, float alpha, float* kl,
+                      void* saved, void* workspace, size_t workspace_bytes, void* stream);
+/* ACCUMULATES into dzi/dzj (so it composes with ssvb_ntxent_bwd) and overwrites dzo. */
+int ssvb_relic_kl_bwd(const float* zi, const float* zj, const float* zo, int64_t n, int64_t d, int64_t ld_zi,
+                      int64_t ld_zj, int64_t ld_zo, int normalize, float temperature, float alpha,
+                      const float* grad_out, const void* saved, float* dzi, float* dzj, float* dzo,
+                      int64_t ld_dzi, int64_t ld_dzj, int64_t ld_dzo, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Row L2-normalise (F.normalize(x, p=2, dim=-1), eps 1e-12) forward / backward —
+ * Prototypes.forward (models/swav.py:51-54) and the projection-head epilogues.
+ * ------------------------------------------------------------------------------------- */
+int ssvb_l2norm_fwd(const float* x, int64_t n, int64_t d, int64_t ld_x, float* y, int64_t ld_y,
+                    float* inv_norm /* [n] */, void* stream);
+int ssvb_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int64_t n, int64_t d, int64_t ld_dy,
+                    int64_t ld_y, float* dx, int64_t ld_dx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSV_B200_H_ */

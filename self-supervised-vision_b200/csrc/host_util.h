@@ -1,0 +1,94 @@
+// Host-side helpers: error codes, TMA descriptor encoding (driver entry point, no -lcuda), launch checks.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/ssv_b200.h"
+
+namespace ssvb {
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// carve a workspace: returns aligned pointer and advances the cursor
+struct Carver {
+  uint8_t* base;
+  size_t off;
+  explicit Carver(void* p) : base(static_cast<uint8_t*>(p)), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+  size_t used() const { return (off + 255) & ~static_cast<size_t>(255); }
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// bf16 row-major [rows x cols], leading dimension ld (elements, ld*2 % 16 == 0).
+// Box = 64 columns (128 B, SWIZZLE_128B) x box_rows rows; out-of-bounds reads are zero-filled.
+inline int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return SSVB_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return SSVB_ERR_ALIGNMENT;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SSVB_OK : SSVB_ERR_DRIVER;
+}
+
+inline int check_device_sm100() {
+  static int cached = -1;  // per-process; all devices of one box are identical
+  if (cached >= 0) return cached;
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return SSVB_ERR_ARCH;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cached = (major == 10) ? SSVB_OK : SSVB_ERR_ARCH;
+  return cached;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (n) return n;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  return n;
+}
+
+#define SSVB_CUDA(expr)                                  \
+  do {                                                   \
+    cudaError_t _e = (expr);                             \
+    if (_e != cudaSuccess) return static_cast<int>(_e);  \
+  } while (0)
+#define SSVB_TRY(expr)          \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != SSVB_OK) return _rc; \
+  } while (0)
+#define SSVB_LAUNCH_CHECK() SSVB_CUDA(cudaGetLastError())
+
+}  // namespace ssvb

@@ -1,0 +1,404 @@
+// NT-Xent (SimCLR) loss, forward + backward, single GPU and row-sharded multi-GPU pieces.
+// Replaces SimclrLoss.forward (reference utils/losses.py:15-46) and the contrastive term of
+// RelicLoss.forward (utils/losses.py:163-194).
+//
+// Math: Z = [zi; zj] (M = 2N rows), s_ab = zh_a.zh_b / tau, partner(a) = a +- N,
+//   loss = 1/M sum_a [ LSE_{b != a} s_ab - s_{a,partner(a)} ]
+//   d zh_a = [ sum_{b != a} (P_ab + P_ba) zh_b - 2 zh_partner(a) ] / (M tau),  P_ab = exp(s_ab - lse_a)
+//   d z_a  = (d zh_a - (d zh_a . zh_a) zh_a) / max(||z_a||, 1e-12)              (normalize=True)
+// All exponentials run in the log2 domain: t = s * log2(e)/tau.
+#include "sim_host.cuh"
+
+using namespace ssvb;
+
+namespace {
+
+struct NtxPlan {
+  int64_t n_glob, m, mpad, d, dpad;
+  int mode;
+  float c, shift;
+};
+
+int make_plan(NtxPlan& pl, int64_t n_glob, int64_t d, int normalize, float temperature) {
+  if (n_glob <= 0 || d <= 0 || !(temperature > 0.f)) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  if (d > 128) return SSVB_ERR_UNSUPPORTED;
+  if (2 * n_glob > (1 << 30)) return SSVB_ERR_UNSUPPORTED;
+  pl.n_glob = n_glob;
+  pl.m = 2 * n_glob;
+  pl.mpad = sim_mpad(pl.m);
+  pl.d = d;
+  pl.dpad = sim_dpad(d);
+  pl.c = SSVB_LOG2E / temperature;
+  pl.shift = pl.c;
+  // unit-norm rows bound |s| <= 1/tau: a constant shift replaces the running max as long as
+  // exp2(-2c) stays far from fp32 underflow (tau >= ~0.045); otherwise (or for raw inputs) online max.
+  pl.mode = (normalize && 2.f * pl.c <= 64.f) ? SIM_NTX_FIXED : SIM_NTX_ONLINE;
+  return SSVB_OK;
+}
+
+struct SavedLayout {  // single-GPU saved blob
+  __nv_bfloat16* zhat;
+  float* inv_norm;
+  float* stat;
+  size_t bytes;
+};
+SavedLayout saved_layout(void* base, int64_t mpad, int64_t dpad) {
+  Carver c(base);
+  SavedLayout s;
+  s.zhat = c.take<__nv_bfloat16>(mpad * dpad);
+  s.inv_norm = c.take<float>(mpad);
+  s.stat = c.take<float>(mpad);
+  s.bytes = c.used();
+  return s;
+}
+
+struct WsLayout {
+  float* pos;
+  float* part_m;
+  float* part_l;
+  float* block_sums;
+  unsigned int* counter;
+  float* dacc;
+  size_t bytes;
+};
+// `cols` = 2 * n_global: the partial buffers are sized from the same chunk plan the launch uses, and are
+// at least mpad floats so rows_bwd can stage the per-column statistics in part_m.
+WsLayout ws_layout(void* base, int64_t local_rows, int64_t row_blocks, int64_t cols, int64_t dpad) {
+  Carver c(base);
+  WsLayout w;
+  const int64_t lr = round_up(local_rows, 256);
+  SimParams p{};
+  p.row_blocks = static_cast<int>(row_blocks);
+  p.cols = static_cast<int>(cols);
+  plan_chunks(p, 256, 4);
+  size_t part_elems = static_cast<size_t>(2 * p.nchunks + 2) * lr;
+  if (part_elems < static_cast<size_t>(sim_mpad(cols))) part_elems = sim_mpad(cols);
+  w.pos = c.take<float>(lr);
+  w.part_m = c.take<float>(part_elems);
+  w.part_l = c.take<float>(part_elems);
+  w.block_sums = c.take<float>(ceil_div(lr, 256) + 8);
+  w.counter = c.take<unsigned int>(4);
+  w.dacc = c.take<float>(lr * dpad);
+  w.bytes = c.used();
+  return w;
+}
+
+// ---- gradient finish: partner term, 1/(M tau) * grad_out, normalise-backward --------------------------
+__global__ void ntx_grad_finish_kernel(const float* __restrict__ zi, const float* __restrict__ zj, int64_t ldi,
+                                       int64_t ldj, int n_view, int d, int n_glob, int row0,
+                                       const float* __restrict__ dacc, int ld_dacc,
+                                       const __nv_bfloat16* __restrict__ zhat, int dpad,
+                                       const float* __restrict__ inv_norm, int normalize, float inv_m_tau,
+                                       const float* __restrict__ grad_out, float* __restrict__ dzi,
+                                       float* __restrict__ dzj, int64_t ld_dzi, int64_t ld_dzj) {
+  const int lrow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (lrow >= 2 * n_view) return;
+  const int view = lrow >= n_view;
+  const int r = lrow - view * n_view;
+  const int a_glob = view * n_glob + row0 + r;
+  const int partner = view ? a_glob - n_glob : a_glob + n_glob;
+  const float* z = view ? zj + static_cast<int64_t>(r) * ldj : zi + static_cast<int64_t>(r) * ldi;
+  float* out = view ? dzj + static_cast<int64_t>(r) * ld_dzj : dzi + static_cast<int64_t>(r) * ld_dzi;
+  const float scale = inv_m_tau * __ldg(grad_out);
+  const float inv = normalize ? inv_norm[lrow] : 1.f;
+  const int k = lane * 4;
+  float g[4] = {0.f, 0.f, 0.f, 0.f}, zh[4] = {0.f, 0.f, 0.f, 0.f};
+  if (k < d) {
+    const float4 acc = *reinterpret_cast<const float4*>(dacc + static_cast<int64_t>(lrow) * ld_dacc + k);
+    const uint2 pz = *reinterpret_cast<const uint2*>(zhat + static_cast<int64_t>(partner) * dpad + k);
+    const float2 p01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pz.x));
+    const float2 p23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pz.y));
+    const float4 zz = *reinterpret_cast<const float4*>(z + k);
+    g[0] = (acc.x - 2.f * p01.x) * scale;
+    g[1] = (acc.y - 2.f * p01.y) * scale;
+    g[2] = (acc.z - 2.f * p23.x) * scale;
+    g[3] = (acc.w - 2.f * p23.y) * scale;
+    zh[0] = zz.x * inv; zh[1] = zz.y * inv; zh[2] = zz.z * inv; zh[3] = zz.w * inv;
+  }
+  if (normalize) {
+    float dot = g[0] * zh[0] + g[1] * zh[1] + g[2] * zh[2] + g[3] * zh[3];
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g[i] = (g[i] - dot * zh[i]) * inv;
+  }
+  if (k < d) *reinterpret_cast<float4*>(out + k) = make_float4(g[0], g[1], g[2], g[3]);
+}
+
+int check_rows(const void* p, int64_t ld) {
+  if (!p) return SSVB_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) || (ld & 3)) return SSVB_ERR_ALIGNMENT;
+  return SSVB_OK;
+}
+
+void fill_sim_params_rows(SimParams& p, const NtxPlan& pl, int nseg, int64_t seg_rows, int64_t s0, int64_t s1) {
+  p = SimParams{};
+  p.nseg = nseg;
+  p.seg_rows = static_cast<int>(seg_rows);
+  p.seg_start[0] = static_cast<int>(s0);
+  p.seg_start[1] = static_cast<int>(s1);
+  p.bps = static_cast<int>(ceil_div(seg_rows, 128));
+  p.row_blocks = nseg * p.bps;
+  p.cols = static_cast<int>(pl.m);
+  p.c = pl.c;
+  p.shift = pl.shift;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t ssvb_ntxent_dpad(int64_t d) { return sim_dpad(d); }
+int64_t ssvb_ntxent_mpad(int64_t n_global) { return sim_mpad(2 * n_global); }
+
+size_t ssvb_ntxent_saved_bytes(int64_t n, int64_t d) {
+  if (n <= 0 || d <= 0) return 0;
+  return saved_layout(nullptr, sim_mpad(2 * n), sim_dpad(d)).bytes;
+}
+size_t ssvb_ntxent_workspace_bytes(int64_t n, int64_t d) {
+  if (n <= 0 || d <= 0) return 0;
+  return ws_layout(nullptr, 2 * n, ceil_div(2 * n, 128), 2 * n, sim_dpad(d)).bytes;
+}
+
+int ssvb_ntxent_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                    int normalize, float temperature, float* loss, void* saved, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  NtxPlan pl;
+  SSVB_TRY(make_plan(pl, n, d, normalize, temperature));
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  if (!loss || !saved || !workspace) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_ntxent_workspace_bytes(n, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SavedLayout sv = saved_layout(saved, pl.mpad, pl.dpad);
+  WsLayout ws = ws_layout(workspace, pl.m, ceil_div(pl.m, 128), pl.m, pl.dpad);
+
+  // zero the padding rows of the bf16 staging matrix and the reduction counter
+  if (pl.mpad > pl.m)
+    SSVB_CUDA(cudaMemsetAsync(sv.zhat + pl.m * pl.dpad, 0, (pl.mpad - pl.m) * pl.dpad * sizeof(__nv_bfloat16), s));
+  SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
+  {
+    const int wpb = 8;
+    pair_prep_kernel<<<static_cast<unsigned>(ceil_div(n, wpb)), wpb * 32, 0, s>>>(
+        zi, zj, static_cast<int>(n), static_cast<int>(d), ld_zi, ld_zj, normalize, sv.zhat, sv.zhat + n * pl.dpad,
+        static_cast<int>(pl.dpad), sv.inv_norm, sv.inv_norm + n, ws.pos, ws.pos + n);
+    SSVB_LAUNCH_CHECK();
+  }
+  SimParams p;
+  fill_sim_params_rows(p, pl, 1, pl.m, 0, 0);
+  plan_chunks(p, 256, 4);
+  p.part_m = ws.part_m;
+  p.part_l = ws.part_l;
+  p.part_stride = static_cast<int>(round_up(pl.m, 256));
+  SSVB_TRY(launch_sim_fwd(pl.mode, sv.zhat, pl.mpad, sv.zhat, pl.mpad, pl.dpad, p, s));
+  {
+    const unsigned grid = static_cast<unsigned>(ceil_div(pl.m, 256));
+    const float scale = 1.f / static_cast<float>(pl.m);
+    if (pl.mode == SIM_NTX_FIXED)
+      lse_finalize_kernel<SIM_NTX_FIXED><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 2 * p.nchunks, p.part_stride,
+                                                            static_cast<int>(pl.m), ws.pos, pl.c, pl.shift,
+                                                            sv.stat, nullptr, ws.block_sums, ws.counter, scale, loss);
+    else
+      lse_finalize_kernel<SIM_NTX_ONLINE><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 2 * p.nchunks, p.part_stride,
+                                                             static_cast<int>(pl.m), ws.pos, pl.c, pl.shift,
+                                                             sv.stat, nullptr, ws.block_sums, ws.counter, scale, loss);
+    SSVB_LAUNCH_CHECK();
+    if (pl.mpad > pl.m) {
+      const float padv = pl.mode == SIM_NTX_FIXED ? 0.f : 1e30f;
+      fill_kernel<<<static_cast<unsigned>(ceil_div(pl.mpad - pl.m, 256)), 256, 0, s>>>(sv.stat + pl.m,
+                                                                                       pl.mpad - pl.m, padv);
+      SSVB_LAUNCH_CHECK();
+    }
+  }
+  return SSVB_OK;
+}
+
+int ssvb_ntxent_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                    int normalize, float temperature, const float* grad_out, const void* saved, float* dzi,
+                    float* dzj, int64_t ld_dzi, int64_t ld_dzj, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  SSVB_TRY(check_device_sm100());
+  NtxPlan pl;
+  SSVB_TRY(make_plan(pl, n, d, normalize, temperature));
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  SSVB_TRY(check_rows(dzi, ld_dzi));
+  SSVB_TRY(check_rows(dzj, ld_dzj));
+  if (!grad_out || !saved || !workspace) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_ntxent_workspace_bytes(n, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SavedLayout sv = saved_layout(const_cast<void*>(saved), pl.mpad, pl.dpad);
+  WsLayout ws = ws_layout(workspace, pl.m, ceil_div(pl.m, 128), pl.m, pl.dpad);
+
+  SimParams p;
+  fill_sim_params_rows(p, pl, 1, pl.m, 0, 0);
+  plan_chunks(p, 128, 8);
+  p.rowstat = sv.stat;
+  p.colstat = sv.stat;
+  p.dacc = ws.dacc;
+  p.ld_dacc = static_cast<int>(pl.dpad);
+  p.use_atomic = p.nchunks > 1;
+  if (p.use_atomic) SSVB_CUDA(cudaMemsetAsync(ws.dacc, 0, pl.m * pl.dpad * sizeof(float), s));
+  SSVB_TRY(launch_sim_bwd(pl.mode, sv.zhat, pl.mpad, sv.zhat, pl.mpad, pl.dpad, p, s));
+  {
+    const int wpb = 8;
+    ntx_grad_finish_kernel<<<static_cast<unsigned>(ceil_div(pl.m, wpb)), wpb * 32, 0, s>>>(
+        zi, zj, ld_zi, ld_zj, static_cast<int>(n), static_cast<int>(d), static_cast<int>(n), 0, ws.dacc,
+        static_cast<int>(pl.dpad), sv.zhat, static_cast<int>(pl.dpad), sv.inv_norm, normalize,
+        1.f / (static_cast<float>(pl.m) * temperature), grad_out, dzi, dzj, ld_dzi, ld_dzj);
+    SSVB_LAUNCH_CHECK();
+  }
+  return SSVB_OK;
+}
+
+// ------------------------------------------------------------------------------------ multi-GPU pieces
+size_t ssvb_ntxent_dist_workspace_bytes(int64_t n_global, int64_t n_local, int64_t d) {
+  if (n_local <= 0 || d <= 0) return 0;
+  return ws_layout(nullptr, 2 * n_local, 2 * ceil_div(n_local, 128), 2 * n_global, sim_dpad(d)).bytes;
+}
+
+int ssvb_ntxent_dist_prep(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                          int64_t ld_zj, int normalize, int64_t n_global, int64_t rank_row0, void* zhat_all,
+                          float* inv_norm_local, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  NtxPlan pl;
+  SSVB_TRY(make_plan(pl, n_global, d, normalize, 1.f));
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  if (!zhat_all || !inv_norm_local || n_local <= 0 || rank_row0 < 0 || rank_row0 + n_local > n_global)
+    return SSVB_ERR_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* zh = static_cast<__nv_bfloat16*>(zhat_all);
+  if (pl.mpad > pl.m)
+    SSVB_CUDA(cudaMemsetAsync(zh + pl.m * pl.dpad, 0, (pl.mpad - pl.m) * pl.dpad * sizeof(__nv_bfloat16), s));
+  const int wpb = 8;
+  pair_prep_kernel<<<static_cast<unsigned>(ceil_div(n_local, wpb)), wpb * 32, 0, s>>>(
+      zi, zj, static_cast<int>(n_local), static_cast<int>(d), ld_zi, ld_zj, normalize, zh + rank_row0 * pl.dpad,
+      zh + (n_global + rank_row0) * pl.dpad, static_cast<int>(pl.dpad), inv_norm_local, inv_norm_local + n_local,
+      nullptr, nullptr);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+namespace {
+// positive logit of every local row from the gathered bf16 matrix (the partner row may live on another rank)
+__global__ void dist_pos_kernel(const __nv_bfloat16* __restrict__ zhat, int dpad, int n_glob, int n_local, int row0,
+                                float* __restrict__ pos) {
+  const int lrow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (lrow >= 2 * n_local) return;
+  const int view = lrow >= n_local;
+  const int a = view * n_glob + row0 + (lrow - view * n_local);
+  const int b = view ? a - n_glob : a + n_glob;
+  float dot = 0.f;
+  for (int k = lane * 2; k < dpad; k += 64) {
+    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zhat + static_cast<int64_t>(a) * dpad + k));
+    const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zhat + static_cast<int64_t>(b) * dpad + k));
+    dot += x.x * y.x + x.y * y.y;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) pos[lrow] = dot;
+}
+}  // namespace
+
+int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t n_global, int64_t n_local, int64_t rank_row0,
+                              int64_t d, int normalize, float temperature, float* stat_local, float* loss_sum,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  NtxPlan pl;
+  SSVB_TRY(make_plan(pl, n_global, d, normalize, temperature));
+  if (!zhat_all || !stat_local || !loss_sum || !workspace || n_local <= 0 || rank_row0 < 0 ||
+      rank_row0 + n_local > n_global)
+    return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_ntxent_dist_workspace_bytes(n_global, n_local, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  WsLayout ws = ws_layout(workspace, 2 * n_local, 2 * ceil_div(n_local, 128), pl.m, pl.dpad);
+  const int64_t lr = 2 * n_local;
+  SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
+  dist_pos_kernel<<<static_cast<unsigned>(ceil_div(lr, 8)), 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(zhat_all), static_cast<int>(pl.dpad), static_cast<int>(n_global),
+      static_cast<int>(n_local), static_cast<int>(rank_row0), ws.pos);
+  SSVB_LAUNCH_CHECK();
+  SimParams p;
+  fill_sim_params_rows(p, pl, 2, n_local, rank_row0, n_global + rank_row0);
+  plan_chunks(p, 256, 4);
+  p.part_m = ws.part_m;
+  p.part_l = ws.part_l;
+  p.part_stride = static_cast<int>(round_up(lr, 256));
+  SSVB_TRY(launch_sim_fwd(pl.mode, zhat_all, pl.mpad, zhat_all, pl.mpad, pl.dpad, p, s));
+  const unsigned grid = static_cast<unsigned>(ceil_div(lr, 256));
+  // stat_local always carries the log2-domain LSE (what gets all-gathered); the FIXED-mode 1/L' is
+  // re-derived from it in rows_bwd.
+  if (pl.mode == SIM_NTX_FIXED)
+    lse_finalize_kernel<SIM_NTX_FIXED><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 2 * p.nchunks, p.part_stride,
+                                                          static_cast<int>(lr), ws.pos, pl.c, pl.shift,
+                                                          ws.dacc /*scratch*/, stat_local, ws.block_sums, ws.counter,
+                                                          1.f, loss_sum);
+  else
+    lse_finalize_kernel<SIM_NTX_ONLINE><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 2 * p.nchunks, p.part_stride,
+                                                           static_cast<int>(lr), ws.pos, pl.c, pl.shift,
+                                                           ws.dacc /*scratch*/, stat_local, ws.block_sums,
+                                                           ws.counter, 1.f, loss_sum);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+namespace {
+// lse2 (all rows) -> the column statistic the backward kernel consumes, with finite padding
+__global__ void dist_stat_kernel(const float* __restrict__ lse2, float* __restrict__ stat, int m, int mpad, int fixed,
+                                 float shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mpad) return;
+  if (i < m)
+    stat[i] = fixed ? exp2f(shift - lse2[i]) : lse2[i];
+  else
+    stat[i] = fixed ? 0.f : 1e30f;
+}
+}  // namespace
+
+int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                              int64_t ld_zj, int normalize, float temperature, int64_t n_global,
+                              int64_t rank_row0, const void* zhat_all, const float* stat_all,
+                              const float* inv_norm_local, const float* grad_out, float* dzi, float* dzj,
+                              int64_t ld_dzi, int64_t ld_dzj, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  SSVB_TRY(check_device_sm100());
+  NtxPlan pl;
+  SSVB_TRY(make_plan(pl, n_global, d, normalize, temperature));
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  SSVB_TRY(check_rows(dzi, ld_dzi));
+  SSVB_TRY(check_rows(dzj, ld_dzj));
+  if (!zhat_all || !stat_all || !inv_norm_local || !grad_out || !workspace || n_local <= 0 || rank_row0 < 0 ||
+      rank_row0 + n_local > n_global)
+    return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_ntxent_dist_workspace_bytes(n_global, n_local, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  WsLayout ws = ws_layout(workspace, 2 * n_local, 2 * ceil_div(n_local, 128), pl.m, pl.dpad);
+  const int64_t lr = 2 * n_local;
+  // column statistics for all M rows live in the (otherwise unused here) partial buffer
+  float* stat = ws.part_m;
+  dist_stat_kernel<<<static_cast<unsigned>(ceil_div(pl.mpad, 256)), 256, 0, s>>>(
+      stat_all, stat, static_cast<int>(pl.m), static_cast<int>(pl.mpad), pl.mode == SIM_NTX_FIXED, pl.shift);
+  SSVB_LAUNCH_CHECK();
+  SimParams p;
+  fill_sim_params_rows(p, pl, 2, n_local, rank_row0, n_global + rank_row0);
+  plan_chunks(p, 128, 8);
+  p.rowstat = stat;
+  p.colstat = stat;
+  p.dacc = ws.dacc;
+  p.ld_dacc = static_cast<int>(pl.dpad);
+  p.use_atomic = p.nchunks > 1;
+  if (p.use_atomic) SSVB_CUDA(cudaMemsetAsync(ws.dacc, 0, lr * pl.dpad * sizeof(float), s));
+  SSVB_TRY(launch_sim_bwd(pl.mode, zhat_all, pl.mpad, zhat_all, pl.mpad, pl.dpad, p, s));
+  const int wpb = 8;
+  ntx_grad_finish_kernel<<<static_cast<unsigned>(ceil_div(lr, wpb)), wpb * 32, 0, s>>>(
+      zi, zj, ld_zi, ld_zj, static_cast<int>(n_local), static_cast<int>(d), static_cast<int>(n_global),
+      static_cast<int>(rank_row0), ws.dacc, static_cast<int>(pl.dpad), static_cast<const __nv_bfloat16*>(zhat_all),
+      static_cast<int>(pl.dpad), inv_norm_local, normalize,
+      1.f / (static_cast<float>(pl.m) * temperature), grad_out, dzi, dzj, ld_dzi, ld_dzj);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+}  // extern "C"

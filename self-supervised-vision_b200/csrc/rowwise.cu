@@ -1,0 +1,485 @@
+// Bandwidth-bound row-wise kernels: BYOL MSE / SimSiam neg-cosine (a8, a9), row L2-normalise fwd/bwd,
+// ring-buffer enqueue (a3, a7) and the ReLIC KL term (a10).  Coalesced float4 accesses, warp-shuffle
+// reductions, deterministic scalar reductions.
+#include "sim_host.cuh"
+
+using namespace ssvb;
+
+namespace {
+
+int check_rows(const void* p, int64_t ld) {
+  if (!p) return SSVB_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) || (ld & 3)) return SSVB_ERR_ALIGNMENT;
+  return SSVB_OK;
+}
+
+// =========================================================================================== rowdot
+// kind 0: sum (o-t)^2 ; kind 1: sum o*t          (models/byol.py:89 nn.MSELoss, utils/losses.py:150-151)
+template <int KIND>
+__global__ void rowdot_fwd_kernel(const float* __restrict__ o, const float* __restrict__ t, int64_t n, int d4,
+                                  int64_t ldo, int64_t ldt, float* block_sums, unsigned int* counter, float scale,
+                                  float* loss) {
+  const int64_t total = n * d4;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / d4;
+    const int c = static_cast<int>(i - r * d4);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(o + r * ldo) + c);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(t + r * ldt) + c);
+    if (KIND == 0) {
+      const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
+      acc0 += dx * dx + dy * dy;
+      acc1 += dz * dz + dw * dw;
+    } else {
+      acc0 += a.x * b.x + a.y * b.y;
+      acc1 += a.z * b.z + a.w * b.w;
+    }
+  }
+  const float bt = block_sum_256(acc0 + acc1);
+  grid_sum_finish(bt, block_sums, counter, scale, loss, false);
+}
+
+template <int KIND>
+__global__ void rowdot_bwd_kernel(const float* __restrict__ o, const float* __restrict__ t, int64_t n, int d4,
+                                  int64_t ldo, int64_t ldt, const float* __restrict__ grad_out, float coef,
+                                  float* __restrict__ d_o, float* __restrict__ d_t, int64_t lddo, int64_t lddt) {
+  const int64_t total = n * d4;
+  const float g = __ldg(grad_out) * coef;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / d4;
+    const int c = static_cast<int>(i - r * d4);
+    float4 go, gt;
+    if (KIND == 0) {  // d/do mean((o-t)^2) = 2 (o-t) / (N D)
+      const float4 a = __ldg(reinterpret_cast<const float4*>(o + r * ldo) + c);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(t + r * ldt) + c);
+      go = make_float4((a.x - b.x) * g, (a.y - b.y) * g, (a.z - b.z) * g, (a.w - b.w) * g);
+      gt = make_float4(-go.x, -go.y, -go.z, -go.w);
+    } else {  // d/do -(1/N) sum o t = -t / N
+      if (d_o) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(t + r * ldt) + c);
+        go = make_float4(b.x * g, b.y * g, b.z * g, b.w * g);
+      }
+      if (d_t) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(o + r * ldo) + c);
+        gt = make_float4(a.x * g, a.y * g, a.z * g, a.w * g);
+      }
+    }
+    if (d_o) reinterpret_cast<float4*>(d_o + r * lddo)[c] = go;
+    if (d_t) reinterpret_cast<float4*>(d_t + r * lddt)[c] = gt;
+  }
+}
+
+// =========================================================================================== l2norm
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx, float* __restrict__ y,
+                                  int64_t ldy, float* __restrict__ inv_norm) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float s = 0.f;
+  for (int c = lane; c < d / 4; c += 32) {
+    const float4 v = __ldg(xr + c);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  s = warp_sum(s);
+  const float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);
+  float4* yr = reinterpret_cast<float4*>(y + row * ldy);
+  for (int c = lane; c < d / 4; c += 32) {
+    const float4 v = __ldg(xr + c);
+    yr[c] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+  }
+  if (lane == 0 && inv_norm) inv_norm[row] = inv;
+}
+
+__global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                  const float* __restrict__ inv_norm, int64_t n, int d, int64_t lddy, int64_t ldy,
+                                  float* __restrict__ dx, int64_t lddx) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float4* gr = reinterpret_cast<const float4*>(dy + row * lddy);
+  const float4* yr = reinterpret_cast<const float4*>(y + row * ldy);
+  float s = 0.f;
+  for (int c = lane; c < d / 4; c += 32) {
+    const float4 g = __ldg(gr + c), v = __ldg(yr + c);
+    s += g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w;
+  }
+  s = warp_sum(s);
+  const float inv = inv_norm[row];
+  float4* o = reinterpret_cast<float4*>(dx + row * lddx);
+  for (int c = lane; c < d / 4; c += 32) {
+    const float4 g = __ldg(gr + c), v = __ldg(yr + c);
+    o[c] = make_float4((g.x - s * v.x) * inv, (g.y - s * v.y) * inv, (g.z - s * v.z) * inv, (g.w - s * v.w) * inv);
+  }
+}
+
+// =========================================================================================== ring enqueue
+// one warp per batch row; rows that a later row of the same batch would overwrite (n > size) are skipped,
+// which is exactly "last writer wins" of the reference's sequential loop.
+__global__ void ring_enqueue_kernel(float* __restrict__ bank, __nv_bfloat16* __restrict__ bank_bf16, int64_t size,
+                                    int d, int dpad, int64_t ld_bank, const float* __restrict__ batch, int64_t n,
+                                    int64_t ld_batch, int64_t ptr, int normalize) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n || i < n - size) return;
+  const int64_t slot = (ptr + i) % size;
+  const float4* src = reinterpret_cast<const float4*>(batch + i * ld_batch);
+  float inv = 1.f;
+  if (normalize) {
+    float s = 0.f;
+    for (int c = lane; c < d / 4; c += 32) {
+      const float4 v = __ldg(src + c);
+      s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    s = warp_sum(s);
+    inv = fmaxf(sqrtf(s), 1e-12f);
+  }
+  float4* dst = reinterpret_cast<float4*>(bank + slot * ld_bank);
+  for (int c = lane; c < dpad / 4; c += 32) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < d / 4) {
+      v = __ldg(src + c);
+      if (normalize) {  // x / max(||x||, eps): true division, like F.normalize
+        v.x = v.x / inv; v.y = v.y / inv; v.z = v.z / inv; v.w = v.w / inv;
+      }
+      dst[c] = v;
+    }
+    if (bank_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(bank_bf16 + slot * dpad + c * 4) = pk;
+    }
+  }
+}
+
+// =========================================================================================== ReLIC KL
+struct RelicSaved {
+  float *a, *b, *inv_i, *inv_j, *inv_o, *scal;  // scal: [lse_a, lse_b, sum(p*q), kl]
+  size_t bytes;
+};
+RelicSaved relic_saved(void* base, int64_t n) {
+  Carver c(base);
+  RelicSaved s;
+  s.a = c.take<float>(n);
+  s.b = c.take<float>(n);
+  s.inv_i = c.take<float>(n);
+  s.inv_j = c.take<float>(n);
+  s.inv_o = c.take<float>(n);
+  s.scal = c.take<float>(8);
+  s.bytes = c.used();
+  return s;
+}
+
+__global__ void relic_dots_kernel(const float* __restrict__ zi, const float* __restrict__ zj,
+                                  const float* __restrict__ zo, int64_t n, int d, int64_t ldi, int64_t ldj,
+                                  int64_t ldo, int normalize, float inv_tau, RelicSaved sv) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float4* pi = reinterpret_cast<const float4*>(zi + row * ldi);
+  const float4* pj = reinterpret_cast<const float4*>(zj + row * ldj);
+  const float4* po = reinterpret_cast<const float4*>(zo + row * ldo);
+  float sii = 0.f, sjj = 0.f, soo = 0.f, sio = 0.f, sjo = 0.f;
+  for (int c = lane; c < d / 4; c += 32) {
+    const float4 a = __ldg(pi + c), b = __ldg(pj + c), o = __ldg(po + c);
+    sii += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    sjj += b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+    soo += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+    sio += a.x * o.x + a.y * o.y + a.z * o.z + a.w * o.w;
+    sjo += b.x * o.x + b.y * o.y + b.z * o.z + b.w * o.w;
+  }
+  sii = warp_sum(sii); sjj = warp_sum(sjj); soo = warp_sum(soo); sio = warp_sum(sio); sjo = warp_sum(sjo);
+  if (lane == 0) {
+    float ii = 1.f, ij = 1.f, io = 1.f;
+    if (normalize) {
+      ii = 1.f / fmaxf(sqrtf(sii), 1e-12f);
+      ij = 1.f / fmaxf(sqrtf(sjj), 1e-12f);
+      io = 1.f / fmaxf(sqrtf(soo), 1e-12f);
+    }
+    sv.inv_i[row] = ii; sv.inv_j[row] = ij; sv.inv_o[row] = io;
+    sv.a[row] = sio * ii * io * inv_tau;
+    sv.b[row] = sjo * ij * io * inv_tau;
+  }
+}
+
+__device__ float block_reduce_1024(float v, bool is_max) {
+  __shared__ float red[32];
+  v = is_max ? warp_max(v) : warp_sum(v);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = lane < (blockDim.x >> 5) ? red[lane] : (is_max ? -INFINITY : 0.f);
+  t = is_max ? warp_max(t) : warp_sum(t);
+  return t;  // valid in every warp
+}
+
+// single block: softmax over the batch axis of a, log-softmax of b, quirk-KL (utils/losses.py:198-200)
+__global__ void relic_softmax_kernel(int64_t n, RelicSaved sv, float alpha, float* __restrict__ kl_out) {
+  float ma = -INFINITY, mb = -INFINITY;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    ma = fmaxf(ma, sv.a[i]);
+    mb = fmaxf(mb, sv.b[i]);
+  }
+  ma = block_reduce_1024(ma, true);
+  mb = block_reduce_1024(mb, true);
+  float sa = 0.f, sb = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    sa += expf(sv.a[i] - ma);
+    sb += expf(sv.b[i] - mb);
+  }
+  sa = block_reduce_1024(sa, false);
+  sb = block_reduce_1024(sb, false);
+  const float lse_a = ma + logf(sa), lse_b = mb + logf(sb);
+  float kl = 0.f, spq = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float p = expf(sv.a[i] - lse_a);
+    const float lq = sv.b[i] - lse_b;
+    const float q = expf(lq);
+    kl += q * (lq - p);
+    spq += p * q;
+  }
+  kl = block_reduce_1024(kl, false);
+  spq = block_reduce_1024(spq, false);
+  if (threadIdx.x == 0) {
+    sv.scal[0] = lse_a; sv.scal[1] = lse_b; sv.scal[2] = spq; sv.scal[3] = kl;
+    *kl_out = alpha * kl;
+  }
+}
+
+__global__ void relic_bwd_kernel(const float* __restrict__ zi, const float* __restrict__ zj,
+                                 const float* __restrict__ zo, int64_t n, int d, int64_t ldi, int64_t ldj,
+                                 int64_t ldo, int normalize, float inv_tau, float alpha,
+                                 const float* __restrict__ grad_out, RelicSaved sv, float* __restrict__ dzi,
+                                 float* __restrict__ dzj, float* __restrict__ dzo, int64_t lddi, int64_t lddj,
+                                 int64_t lddo) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float lse_a = sv.scal[0], lse_b = sv.scal[1], spq = sv.scal[2], kl = sv.scal[3];
+  const float a = sv.a[row], b = sv.b[row];
+  const float p = expf(a - lse_a), lq = b - lse_b, q = expf(lq);
+  const float g = __ldg(grad_out) * alpha * inv_tau;
+  const float da = -(p * q - p * spq) * g;          // through softmax of the kl_div *input*
+  const float h = q * (lq - p) + q;
+  const float db = (h - q * (kl + 1.f)) * g;        // through log_softmax of the target; sum(h) = kl + 1
+  const float ii = sv.inv_i[row], ij = sv.inv_j[row], io = sv.inv_o[row];
+  // cosines (needed for the normalise-backward projections): a*tau, b*tau
+  const float cio = a / inv_tau, cjo = b / inv_tau;
+  const float4* pi = reinterpret_cast<const float4*>(zi + row * ldi);
+  const float4* pj = reinterpret_cast<const float4*>(zj + row * ldj);
+  const float4* po = reinterpret_cast<const float4*>(zo + row * ldo);
+  float4* oi = reinterpret_cast<float4*>(dzi + row * lddi);
+  float4* oj = reinterpret_cast<float4*>(dzj + row * lddj);
+  float4* oo = reinterpret_cast<float4*>(dzo + row * lddo);
+  for (int c = lane; c < d / 4; c += 32) {
+    const float4 vi = __ldg(pi + c), vj = __ldg(pj + c), vo = __ldg(po + c);
+    const float xi[4] = {vi.x * ii, vi.y * ii, vi.z * ii, vi.w * ii};
+    const float xj[4] = {vj.x * ij, vj.y * ij, vj.z * ij, vj.w * ij};
+    const float xo[4] = {vo.x * io, vo.y * io, vo.z * io, vo.w * io};
+    float gi[4], gj[4], go[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (normalize) {
+        // d zhat_i = da * zhat_o ; projected: (da*zo - (da*zo.zi) zi) * inv_i, with zo.zi = cos_io
+        gi[e] = da * (xo[e] - cio * xi[e]) * ii;
+        gj[e] = db * (xo[e] - cjo * xj[e]) * ij;
+        // d zhat_o = da*zi + db*zj ; (g.zo) = da*cio + db*cjo
+        go[e] = (da * xi[e] + db * xj[e] - (da * cio + db * cjo) * xo[e]) * io;
+      } else {
+        gi[e] = da * xo[e];
+        gj[e] = db * xo[e];
+        go[e] = da * xi[e] + db * xj[e];
+      }
+    }
+    float4 ci = oi[c], cj = oj[c];
+    ci.x += gi[0]; ci.y += gi[1]; ci.z += gi[2]; ci.w += gi[3];
+    cj.x += gj[0]; cj.y += gj[1]; cj.z += gj[2]; cj.w += gj[3];
+    oi[c] = ci;
+    oj[c] = cj;
+    oo[c] = make_float4(go[0], go[1], go[2], go[3]);
+  }
+}
+
+struct RowdotWs {
+  float* block_sums;
+  unsigned int* counter;
+  size_t bytes;
+};
+RowdotWs rowdot_ws(void* base) {
+  Carver c(base);
+  RowdotWs w;
+  w.block_sums = c.take<float>(4096);
+  w.counter = c.take<unsigned int>(4);
+  w.bytes = c.used();
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t ssvb_rowdot_workspace_bytes(int64_t n, int64_t d) {
+  (void)n; (void)d;
+  return rowdot_ws(nullptr).bytes;
+}
+
+int ssvb_rowdot_fwd(int kind, const float* o, const float* t, int64_t n, int64_t d, int64_t ld_o, int64_t ld_t,
+                    float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (n <= 0 || d <= 0 || !loss || !workspace || (kind != 0 && kind != 1)) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(o, ld_o));
+  SSVB_TRY(check_rows(t, ld_t));
+  if (workspace_bytes < rowdot_ws(nullptr).bytes) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  RowdotWs ws = rowdot_ws(workspace);
+  SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
+  const int64_t total = n * (d / 4);
+  int64_t grid = ceil_div(total, 256 * 4);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  if (kind == 0)
+    rowdot_fwd_kernel<0><<<static_cast<unsigned>(grid), 256, 0, s>>>(o, t, n, static_cast<int>(d / 4), ld_o, ld_t,
+                                                                     ws.block_sums, ws.counter,
+                                                                     1.f / (static_cast<float>(n) * d), loss);
+  else
+    rowdot_fwd_kernel<1><<<static_cast<unsigned>(grid), 256, 0, s>>>(o, t, n, static_cast<int>(d / 4), ld_o, ld_t,
+                                                                     ws.block_sums, ws.counter,
+                                                                     -1.f / static_cast<float>(n), loss);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_rowdot_bwd(int kind, const float* o, const float* t, int64_t n, int64_t d, int64_t ld_o, int64_t ld_t,
+                    const float* grad_out, float* d_o, float* d_t, int64_t ld_do, int64_t ld_dt, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (n <= 0 || d <= 0 || !grad_out || (kind != 0 && kind != 1) || (!d_o && !d_t)) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(o, ld_o));
+  SSVB_TRY(check_rows(t, ld_t));
+  if (d_o) SSVB_TRY(check_rows(d_o, ld_do));
+  if (d_t) SSVB_TRY(check_rows(d_t, ld_dt));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t total = n * (d / 4);
+  int64_t grid = ceil_div(total, 256 * 2);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  if (kind == 0)
+    rowdot_bwd_kernel<0><<<static_cast<unsigned>(grid), 256, 0, s>>>(o, t, n, static_cast<int>(d / 4), ld_o, ld_t,
+                                                                     grad_out, 2.f / (static_cast<float>(n) * d),
+                                                                     d_o, d_t, ld_do, ld_dt);
+  else
+    rowdot_bwd_kernel<1><<<static_cast<unsigned>(grid), 256, 0, s>>>(o, t, n, static_cast<int>(d / 4), ld_o, ld_t,
+                                                                     grad_out, -1.f / static_cast<float>(n), d_o,
+                                                                     d_t, ld_do, ld_dt);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_l2norm_fwd(const float* x, int64_t n, int64_t d, int64_t ld_x, float* y, int64_t ld_y, float* inv_norm,
+                    void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (n <= 0 || d <= 0) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(x, ld_x));
+  SSVB_TRY(check_rows(y, ld_y));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  l2norm_fwd_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(x, n, static_cast<int>(d), ld_x, y, ld_y,
+                                                                          inv_norm);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int64_t n, int64_t d, int64_t ld_dy,
+                    int64_t ld_y, float* dx, int64_t ld_dx, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (n <= 0 || d <= 0 || !inv_norm) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(dy, ld_dy));
+  SSVB_TRY(check_rows(y, ld_y));
+  SSVB_TRY(check_rows(dx, ld_dx));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  l2norm_bwd_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(dy, y, inv_norm, n, static_cast<int>(d),
+                                                                          ld_dy, ld_y, dx, ld_dx);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_ring_enqueue(float* bank, void* bank_bf16, int64_t size, int64_t d, int64_t ld_bank, const float* batch,
+                      int64_t n, int64_t ld_batch, int64_t ptr, int normalize, int64_t* new_ptr, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (size <= 0 || d <= 0 || n < 0 || ptr < 0 || ptr >= size || !new_ptr) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(bank, ld_bank));
+  if (n == 0) {
+    *new_ptr = ptr;
+    return SSVB_OK;
+  }
+  SSVB_TRY(check_rows(batch, ld_batch));
+  if (bank_bf16 && (reinterpret_cast<uintptr_t>(bank_bf16) & 15)) return SSVB_ERR_ALIGNMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ring_enqueue_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(
+      bank, static_cast<__nv_bfloat16*>(bank_bf16), size, static_cast<int>(d), static_cast<int>(sim_dpad(d)), ld_bank,
+      batch, n, ld_batch, ptr, normalize);
+  SSVB_LAUNCH_CHECK();
+  *new_ptr = (ptr + n) % size;
+  return SSVB_OK;
+}
+
+size_t ssvb_relic_kl_saved_bytes(int64_t n) { return n > 0 ? relic_saved(nullptr, n).bytes : 0; }
+size_t ssvb_relic_kl_workspace_bytes(int64_t n) {
+  (void)n;
+  return 256;
+}
+
+int ssvb_relic_kl_fwd(const float* zi, const float* zj, const float* zo, int64_t n, int64_t d, int64_t ld_zi,
+                      int64_t ld_zj, int64_t ld_zo, int normalize, float temperature, float alpha, float* kl,
+                      void* saved, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  SSVB_TRY(check_device_sm100());
+  if (n <= 0 || d <= 0 || !kl || !saved || !(temperature > 0.f)) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  SSVB_TRY(check_rows(zo, ld_zo));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  RelicSaved sv = relic_saved(saved, n);
+  relic_dots_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(zi, zj, zo, n, static_cast<int>(d), ld_zi,
+                                                                          ld_zj, ld_zo, normalize, 1.f / temperature,
+                                                                          sv);
+  SSVB_LAUNCH_CHECK();
+  relic_softmax_kernel<<<1, 1024, 0, s>>>(n, sv, alpha, kl);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_relic_kl_bwd(const float* zi, const float* zj, const float* zo, int64_t n, int64_t d, int64_t ld_zi,
+                      int64_t ld_zj, int64_t ld_zo, int normalize, float temperature, float alpha,
+                      const float* grad_out, const void* saved, float* dzi, float* dzj, float* dzo, int64_t ld_dzi,
+                      int64_t ld_dzj, int64_t ld_dzo, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (n <= 0 || d <= 0 || !grad_out || !saved || !(temperature > 0.f)) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  SSVB_TRY(check_rows(zo, ld_zo));
+  SSVB_TRY(check_rows(dzi, ld_dzi));
+  SSVB_TRY(check_rows(dzj, ld_dzj));
+  SSVB_TRY(check_rows(dzo, ld_dzo));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  RelicSaved sv = relic_saved(const_cast<void*>(saved), n);
+  relic_bwd_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(
+      zi, zj, zo, n, static_cast<int>(d), ld_zi, ld_zj, ld_zo, normalize, 1.f / temperature, alpha, grad_out, sv, dzi,
+      dzj, dzo, ld_dzi, ld_dzj, ld_dzo);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,241 @@
+// Host-side planning / launch of the similarity kernels + the small bandwidth kernels around them
+// (row normalise -> bf16 staging, partial-LSE finalize, deterministic scalar reduction).
+#pragma once
+#include "host_util.h"
+#include "sim_kernels.cuh"
+
+namespace ssvb {
+
+inline int64_t sim_dpad(int64_t d) { return round_up(d, 64); }
+inline int64_t sim_mpad(int64_t m) { return round_up(m, 256); }
+
+// choose the column chunking so that there are enough (row block, chunk) units to balance 148 SMs while
+// every chunk keeps >= min_tiles tiles (amortises the A-tile load and the epilogue); no chunk is empty.
+inline void plan_chunks(SimParams& p, int BN, int min_tiles) {
+  p.col_tiles = static_cast<int>(ceil_div(p.cols, BN));
+  const int target_units = num_sms() * 4;
+  int nch = static_cast<int>(ceil_div(target_units, p.row_blocks));
+  const int max_ch = p.col_tiles / min_tiles > 1 ? p.col_tiles / min_tiles : 1;
+  if (nch > max_ch) nch = max_ch;
+  if (nch < 1) nch = 1;
+  p.tiles_per_chunk = static_cast<int>(ceil_div(p.col_tiles, nch));
+  p.nchunks = static_cast<int>(ceil_div(p.col_tiles, p.tiles_per_chunk));
+}
+
+template <int KB, int MODE>
+int launch_sim_fwd_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const SimParams& p, cudaStream_t s) {
+  auto kern = sim_fwd_kernel<KB, MODE>;
+  constexpr int smem = FwdCfg<KB>::SMEM;
+  SSVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int nunits = p.row_blocks * p.nchunks;
+  const int grid = nunits < num_sms() ? nunits : num_sms();
+  kern<<<grid, 320, smem, s>>>(tmA, tmB, p);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+template <int KB, int MODE>
+int launch_sim_bwd_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const SimParams& p, cudaStream_t s) {
+  auto kern = sim_bwd_kernel<KB, MODE>;
+  constexpr int smem = BwdCfg<KB>::SMEM;
+  SSVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int nunits = p.row_blocks * p.nchunks;
+  const int grid = nunits < num_sms() ? nunits : num_sms();
+  kern<<<grid, 320, smem, s>>>(tmA, tmB, p);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+// A: bf16 [a_rows x dpad], B: bf16 [b_rows x dpad]
+inline int launch_sim_fwd(int mode, const void* A, int64_t a_rows, const void* B, int64_t b_rows, int64_t dpad,
+                          const SimParams& p, cudaStream_t s) {
+  CUtensorMap tmA, tmB;
+  SSVB_TRY(make_tmap_bf16(&tmA, A, a_rows, dpad, dpad, 128));
+  SSVB_TRY(make_tmap_bf16(&tmB, B, b_rows, dpad, dpad, 256));
+  const int KB = static_cast<int>(dpad / 64);
+#define SSVB_DISPATCH(KBV)                                                      \
+  switch (mode) {                                                               \
+    case SIM_NTX_FIXED: return launch_sim_fwd_t<KBV, SIM_NTX_FIXED>(tmA, tmB, p, s);  \
+    case SIM_NTX_ONLINE: return launch_sim_fwd_t<KBV, SIM_NTX_ONLINE>(tmA, tmB, p, s); \
+    case SIM_MOCO: return launch_sim_fwd_t<KBV, SIM_MOCO>(tmA, tmB, p, s);      \
+    default: return SSVB_ERR_INVALID;                                           \
+  }
+  if (KB == 1) { SSVB_DISPATCH(1) }
+  if (KB == 2) { SSVB_DISPATCH(2) }
+#undef SSVB_DISPATCH
+  return SSVB_ERR_UNSUPPORTED;
+}
+inline int launch_sim_bwd(int mode, const void* A, int64_t a_rows, const void* B, int64_t b_rows, int64_t dpad,
+                          const SimParams& p, cudaStream_t s) {
+  CUtensorMap tmA, tmB;
+  SSVB_TRY(make_tmap_bf16(&tmA, A, a_rows, dpad, dpad, 128));
+  SSVB_TRY(make_tmap_bf16(&tmB, B, b_rows, dpad, dpad, 128));
+  const int KB = static_cast<int>(dpad / 64);
+#define SSVB_DISPATCH(KBV)                                                      \
+  switch (mode) {                                                               \
+    case SIM_NTX_FIXED: return launch_sim_bwd_t<KBV, SIM_NTX_FIXED>(tmA, tmB, p, s);  \
+    case SIM_NTX_ONLINE: return launch_sim_bwd_t<KBV, SIM_NTX_ONLINE>(tmA, tmB, p, s); \
+    case SIM_MOCO: return launch_sim_bwd_t<KBV, SIM_MOCO>(tmA, tmB, p, s);      \
+    default: return SSVB_ERR_INVALID;                                           \
+  }
+  if (KB == 1) { SSVB_DISPATCH(1) }
+  if (KB == 2) { SSVB_DISPATCH(2) }
+#undef SSVB_DISPATCH
+  return SSVB_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pair_prep: one warp per row n of two [n x d] fp32 matrices.  Optionally L2-normalises
+// (x / max(||x||, 1e-12), F.normalize semantics), writes bf16 rows (zero padded to dpad) and the
+// row dot product of the two bf16-rounded rows (`pos`, exactly what the tensor cores will see).
+// ---------------------------------------------------------------------------------------------------
+static __global__ void pair_prep_kernel(const float* __restrict__ xi, const float* __restrict__ xj, int n, int d,
+                                 int64_t ldi, int64_t ldj, int normalize, __nv_bfloat16* __restrict__ out_i,
+                                 __nv_bfloat16* __restrict__ out_j, int dpad, float* __restrict__ inv_i,
+                                 float* __restrict__ inv_j, float* __restrict__ pos_i, float* __restrict__ pos_j) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float* ri = xi + static_cast<int64_t>(warp) * ldi;
+  const float* rj = xj + static_cast<int64_t>(warp) * ldj;
+  // dpad <= 256: up to two float4 per lane
+  float4 a[2], b[2];
+  float si = 0.f, sj = 0.f;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int k = it * 128 + lane * 4;
+    a[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    b[it] = a[it];
+    if (k < d) {
+      a[it] = *reinterpret_cast<const float4*>(ri + k);
+      b[it] = *reinterpret_cast<const float4*>(rj + k);
+    }
+    si += a[it].x * a[it].x + a[it].y * a[it].y + a[it].z * a[it].z + a[it].w * a[it].w;
+    sj += b[it].x * b[it].x + b[it].y * b[it].y + b[it].z * b[it].z + b[it].w * b[it].w;
+  }
+  si = warp_sum(si);
+  sj = warp_sum(sj);
+  float ivi = 1.f, ivj = 1.f;
+  if (normalize) {
+    ivi = 1.f / fmaxf(sqrtf(si), 1e-12f);
+    ivj = 1.f / fmaxf(sqrtf(sj), 1e-12f);
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int k = it * 128 + lane * 4;
+    if (k < dpad) {
+      __nv_bfloat162 i01 = __floats2bfloat162_rn(a[it].x * ivi, a[it].y * ivi);
+      __nv_bfloat162 i23 = __floats2bfloat162_rn(a[it].z * ivi, a[it].w * ivi);
+      __nv_bfloat162 j01 = __floats2bfloat162_rn(b[it].x * ivj, b[it].y * ivj);
+      __nv_bfloat162 j23 = __floats2bfloat162_rn(b[it].z * ivj, b[it].w * ivj);
+      const float2 fi01 = __bfloat1622float2(i01), fi23 = __bfloat1622float2(i23);
+      const float2 fj01 = __bfloat1622float2(j01), fj23 = __bfloat1622float2(j23);
+      dot += fi01.x * fj01.x + fi01.y * fj01.y + fi23.x * fj23.x + fi23.y * fj23.y;
+      if (out_i) {
+        uint2 v;
+        v.x = *reinterpret_cast<uint32_t*>(&i01);
+        v.y = *reinterpret_cast<uint32_t*>(&i23);
+        *reinterpret_cast<uint2*>(out_i + static_cast<int64_t>(warp) * dpad + k) = v;
+      }
+      if (out_j) {
+        uint2 v;
+        v.x = *reinterpret_cast<uint32_t*>(&j01);
+        v.y = *reinterpret_cast<uint32_t*>(&j23);
+        *reinterpret_cast<uint2*>(out_j + static_cast<int64_t>(warp) * dpad + k) = v;
+      }
+    }
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    if (inv_i) inv_i[warp] = ivi;
+    if (inv_j) inv_j[warp] = ivj;
+    if (pos_i) pos_i[warp] = dot;
+    if (pos_j) pos_j[warp] = dot;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// deterministic block-sum -> scalar: every block writes its partial, the last block to finish adds
+// them in index order (no float atomics -> run-to-run bit-stable loss).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v) {
+  __shared__ float red[8];
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (w == 0) {
+    t = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+    t = warp_sum(t);
+  }
+  return t;  // valid in warp 0
+}
+__device__ __forceinline__ void grid_sum_finish(float block_total, float* block_sums, unsigned int* counter,
+                                                float scale, float* out, bool accumulate) {
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    block_sums[blockIdx.x] = block_total;
+    __threadfence();
+    const unsigned int done = atomicAdd(counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < 32) {
+    __threadfence();
+    float t = 0.f;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += 32) t += __ldcg(block_sums + i);
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+      if (accumulate)
+        *out += t * scale;
+      else
+        *out = t * scale;
+      *counter = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// lse_finalize: combine the per-chunk partials of every local row into its log2-domain LSE, emit the
+// per-row statistic the backward needs (FIXED: 1/L', else lse2) and the loss sum.
+//   MoCo: the positive logit joins the LSE (label-0 column of the reference's cat, utils/losses.py:70).
+// ---------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void lse_finalize_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l, int nparts,
+                                    int stride, int nrows, const float* __restrict__ pos, float c, float shift,
+                                    float* __restrict__ stat, float* __restrict__ lse2_out,
+                                    float* block_sums, unsigned int* counter, float loss_scale, float* loss) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  float term = 0.f;
+  if (r < nrows) {
+    float lse2, st;
+    const float p2 = pos[r] * c;
+    if (MODE == SIM_NTX_FIXED) {
+      float L = 0.f;
+      for (int i = 0; i < nparts; ++i) L += part_l[static_cast<size_t>(i) * stride + r];
+      lse2 = shift + log2f(L);
+      st = 1.f / L;
+    } else {
+      float M = (MODE == SIM_MOCO) ? p2 : -1e30f;
+      for (int i = 0; i < nparts; ++i) M = fmaxf(M, part_m[static_cast<size_t>(i) * stride + r]);
+      float L = (MODE == SIM_MOCO) ? exp2f(p2 - M) : 0.f;
+      for (int i = 0; i < nparts; ++i)
+        L += part_l[static_cast<size_t>(i) * stride + r] * exp2f(part_m[static_cast<size_t>(i) * stride + r] - M);
+      lse2 = M + log2f(L);
+      st = lse2;
+    }
+    stat[r] = st;
+    if (lse2_out) lse2_out[r] = lse2;
+    term = (lse2 - p2) * SSVB_LN2;
+  }
+  const float bt = block_sum_256(term);
+  grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false);
+}
+
+static __global__ void fill_kernel(float* p, int64_t n, float v) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace ssvb

@@ -1,0 +1,531 @@
+// Flash-style similarity-matrix kernels for NT-Xent (SimCLR / ReLIC) and MoCo InfoNCE.
+//
+//   sim_fwd_kernel : S tile = A_I * B_J^T on tcgen05 (bf16 operands via TMA, fp32 accumulators in TMEM),
+//                    streamed through exp2 / row-sum in registers -> per-(row, column-chunk) partial
+//                    (max, sum) pairs.  S never touches HBM.
+//   sim_bwd_kernel : recompute the S tile, turn it into the softmax weight tile W (bf16, written back to
+//                    TMEM), second tcgen05 GEMM dA_I += W * B_J with W as the TMEM A-operand and the SAME
+//                    smem B tile read MN-major.  Accumulator stays in TMEM for the whole row block.
+//
+// Warp roles (320 threads, 1 CTA / SM): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = two
+// softmax warpgroups (TMEM lane quarter = warp % 4).  All hand-offs are mbarriers; every wait is bounded.
+#pragma once
+#include "common.cuh"
+
+namespace ssvb {
+
+enum SimMode { SIM_NTX_FIXED = 0, SIM_NTX_ONLINE = 1, SIM_MOCO = 2 };
+
+struct SimParams {
+  // A rows: `nseg` segments of `seg_rows` rows starting at global rows seg_start[s] of the A tensor map.
+  // Local row index (partials / dacc / MoCo rowstat) = seg * seg_rows + row-in-segment.
+  int nseg, seg_rows, seg_start[2];
+  int bps;         // 128-row blocks per segment
+  int row_blocks;  // nseg * bps
+  int cols;        // valid columns (rows of B)
+  int col_tiles;   // ceil(cols / BN)
+  int nchunks, tiles_per_chunk;
+  float c;      // log2(e) / temperature
+  float shift;  // FIXED mode: constant log2-domain shift (= c, the largest possible logit)
+  // forward outputs: [2 * nchunks][part_stride]
+  float* part_m;
+  float* part_l;
+  int part_stride;
+  // backward inputs / outputs
+  const float* rowstat;  // NT-Xent: indexed by global row; MoCo: by local row
+  const float* colstat;  // NT-Xent only, indexed by column, padded to a multiple of 128
+  float* dacc;           // [local rows x ld_dacc] fp32
+  int ld_dacc;
+  int use_atomic;  // nchunks > 1: red.add into a zeroed dacc
+};
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~static_cast<uintptr_t>(1023));
+}
+
+// wait::ld with the destination registers as in/out operands so no consumer is scheduled above it
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),
+                 "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]),
+                 "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]),
+                 "+r"(v[29]), "+r"(v[30]), "+r"(v[31])::"memory");
+}
+
+struct UnitInfo {
+  int g0;      // global A row of the block's first row
+  int lrow0;   // local row index of the block's first row
+  int nvalid;  // valid rows in the block
+  int t0, t1;  // column-tile range of the chunk
+  int ch;
+};
+__device__ __forceinline__ UnitInfo decode_unit(const SimParams& p, int u) {
+  UnitInfo ui;
+  const int rb = u / p.nchunks;
+  ui.ch = u - rb * p.nchunks;
+  const int seg = rb / p.bps;
+  const int rbi = rb - seg * p.bps;
+  ui.g0 = p.seg_start[seg] + rbi * 128;
+  ui.lrow0 = seg * p.seg_rows + rbi * 128;
+  ui.nvalid = min(128, p.seg_rows - rbi * 128);
+  ui.t0 = ui.ch * p.tiles_per_chunk;
+  ui.t1 = min(p.col_tiles, ui.t0 + p.tiles_per_chunk);
+  return ui;
+}
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+template <int KB>
+struct FwdCfg {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = 128 * 128 * KB;
+  static constexpr int B_BYTES = BN * 128 * KB;
+  static constexpr int NSTAGE = (KB == 1) ? 4 : 2;
+  static constexpr int NBARS = 4 + 2 * NSTAGE + 4;
+  static constexpr int SMEM = 1024 + 2 * A_BYTES + NSTAGE * B_BYTES + NBARS * 8 + 16;
+};
+
+template <int MODE, bool MASKED>
+__device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int a_glob, int j0, float& m,
+                                         float (&l)[4], uint64_t* s_empty_bar, int lane) {
+  uint32_t v[2][32];
+  tmem_ld_x32(taddr, v[0]);
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) {
+    uint32_t(&cur)[32] = v[cc & 1];
+    tmem_ld_wait_regs(cur);
+    if (cc < 7) {
+      tmem_ld_x32(taddr + (cc + 1) * 32, v[(cc + 1) & 1]);
+    } else {
+      // the S buffer is fully in registers: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty_bar);
+    }
+    const int colbase = j0 + cc * 32;
+    if (MODE == SIM_NTX_FIXED) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float t = fmaf(__uint_as_float(cur[i]), p.c, -p.shift);
+        if (MASKED) {
+          const int col = colbase + i;
+          if (col == a_glob || col >= p.cols) t = -INFINITY;
+        }
+        l[i & 3] += ex2f(t);
+      }
+    } else {
+      float x[32];
+      float cm = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float t = __uint_as_float(cur[i]) * p.c;
+        if (MASKED) {
+          const int col = colbase + i;
+          if ((MODE != SIM_MOCO && col == a_glob) || col >= p.cols) t = -INFINITY;
+        }
+        x[i] = t;
+        cm = fmaxf(cm, t);
+      }
+      const float mn = fmaxf(m, cm);
+      const float sc = ex2f(m - mn);
+      m = mn;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) l[i] *= sc;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) l[i & 3] += ex2f(x[i] - mn);
+    }
+  }
+}
+
+template <int KB, int MODE>
+__global__ void __launch_bounds__(320, 1)
+sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SimParams p) {
+  using C = FwdCfg<KB>;
+  constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 2 * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NSTAGE * C::B_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + 2;
+  uint64_t* b_full = bars + 4;
+  uint64_t* b_empty = b_full + NSTAGE;
+  uint64_t* s_full = b_empty + NSTAGE;
+  uint64_t* s_empty = s_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+    }
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int nunits = p.row_blocks * p.nchunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int ucount = 0, gt = 0;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
+        const UnitInfo ui = decode_unit(p, u);
+        const int ua = ucount & 1;
+        mbar_wait(&a_empty[ua], ((ucount >> 1) & 1) ^ 1);
+        mbar_expect_tx(&a_full[ua], C::A_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d(sA + ua * C::A_BYTES + kb * (128 * 128), &tmA, &a_full[ua], kb * 64, ui.g0);
+        for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
+          const int st = gt % NSTAGE;
+          mbar_wait(&b_empty[st], ((gt / NSTAGE) & 1) ^ 1);
+          mbar_expect_tx(&b_full[st], C::B_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d(sB + st * C::B_BYTES + kb * (BN * 128), &tmB, &b_full[st], kb * 64, t * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC = make_idesc(128, BN, 0, 0);
+      int ucount = 0, gt = 0;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
+        const UnitInfo ui = decode_unit(p, u);
+        const int ua = ucount & 1;
+        mbar_wait(&a_full[ua], (ucount >> 1) & 1);
+        const uint32_t abase = smem_u32(sA + ua * C::A_BYTES);
+        for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
+          const int st = gt % NSTAGE, buf = gt & 1;
+          mbar_wait(&b_full[st], (gt / NSTAGE) & 1);
+          mbar_wait(&s_empty[buf], ((gt >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t bbase = smem_u32(sB + st * C::B_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_ss(tmem + buf * BN, desc_kmajor(abase + kb * (128 * 128) + k4 * 32),
+                      desc_kmajor(bbase + kb * (BN * 128) + k4 * 32), IDESC, (kb | k4) != 0);
+          umma_commit(&b_empty[st]);
+          umma_commit(&s_full[buf]);
+        }
+        umma_commit(&a_empty[ua]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int wg = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row_l = q * 32 + lane;
+    const uint32_t tlane = static_cast<uint32_t>(q * 32) << 16;
+    int gt = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      const UnitInfo ui = decode_unit(p, u);
+      const int a_glob = ui.g0 + row_l;
+      float m = -1e30f;
+      float l[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
+        if ((gt & 1) != wg) continue;
+        mbar_wait(&s_full[wg], (gt >> 1) & 1);
+        tc_fence_after();
+        const int j0 = t * BN;
+        const bool special = (MODE != SIM_MOCO && j0 < ui.g0 + 128 && j0 + BN > ui.g0) || (j0 + BN > p.cols);
+        const uint32_t taddr = tmem + tlane + wg * BN;
+        if (special)
+          fwd_tile<MODE, true>(taddr, p, a_glob, j0, m, l, &s_empty[wg], lane);
+        else
+          fwd_tile<MODE, false>(taddr, p, a_glob, j0, m, l, &s_empty[wg], lane);
+      }
+      if (row_l < ui.nvalid) {
+        const size_t o = static_cast<size_t>(ui.ch * 2 + wg) * p.part_stride + ui.lrow0 + row_l;
+        p.part_l[o] = (l[0] + l[1]) + (l[2] + l[3]);
+        if (MODE != SIM_NTX_FIXED) p.part_m[o] = m;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// =====================================================================================================
+// backward
+// =====================================================================================================
+template <int KB>
+struct BwdCfg {
+  static constexpr int BN = 128;
+  static constexpr int DP = 64 * KB;
+  static constexpr int A_BYTES = 128 * 128 * KB;
+  static constexpr int B_BYTES = BN * 128 * KB;
+  static constexpr int CS_BYTES = BN * 4;
+  static constexpr int NSTAGE = (KB == 1) ? 6 : 4;
+  static constexpr int NBARS = 4 + 2 * NSTAGE + 8 + 2;
+  static constexpr int SMEM = 1024 + 2 * A_BYTES + NSTAGE * (B_BYTES + CS_BYTES) + NBARS * 8 + 16;
+  // TMEM columns
+  static constexpr int T_S = 0;      // two 128-column S buffers
+  static constexpr int T_DZ = 256;   // DP-column gradient accumulator
+  static constexpr int T_W = 384;    // two 64-column bf16 W buffers
+};
+
+template <int MODE, bool MASKED>
+__device__ __forceinline__ void bwd_tile(uint32_t t_s, uint32_t t_w, const SimParams& p, int a_glob, int j0,
+                                         float rs, const float* cs, uint64_t* s_empty_bar, int lane) {
+  uint32_t v[2][32];
+  tmem_ld_x32(t_s, v[0]);
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    uint32_t(&cur)[32] = v[cc & 1];
+    tmem_ld_wait_regs(cur);
+    if (cc < 3) {
+      tmem_ld_x32(t_s + (cc + 1) * 32, v[(cc + 1) & 1]);
+    } else {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty_bar);
+    }
+    float w[32];
+#pragma unroll
+    for (int i4 = 0; i4 < 8; ++i4) {
+      float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE != SIM_MOCO) c4 = reinterpret_cast<const float4*>(cs)[cc * 8 + i4];
+      const float csv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i4 * 4 + e;
+        const float s = __uint_as_float(cur[i]);
+        float wv;
+        if (MODE == SIM_NTX_FIXED) {
+          wv = ex2f(fmaf(s, p.c, -p.shift)) * (rs + csv[e]);
+        } else if (MODE == SIM_NTX_ONLINE) {
+          const float t = s * p.c;
+          wv = ex2f(t - rs) + ex2f(t - csv[e]);
+        } else {
+          wv = ex2f(fmaf(s, p.c, -rs));
+        }
+        if (MASKED && (j0 + cc * 32 + i == a_glob)) wv = 0.f;
+        w[i] = wv;
+      }
+    }
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(w[2 * i], w[2 * i + 1]);
+    tmem_st_x16(t_w + cc * 16, pk);
+  }
+}
+
+template <int KB, int MODE>
+__global__ void __launch_bounds__(320, 1)
+sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SimParams p) {
+  using C = BwdCfg<KB>;
+  constexpr int BN = C::BN, NSTAGE = C::NSTAGE, DP = C::DP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 2 * C::A_BYTES;
+  uint8_t* sC = sB + NSTAGE * C::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + NSTAGE * C::CS_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + 2;
+  uint64_t* b_full = bars + 4;
+  uint64_t* b_empty = b_full + NSTAGE;
+  uint64_t* s_full = b_empty + NSTAGE;
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* w_full = s_empty + 2;
+  uint64_t* w_empty = w_full + 2;
+  uint64_t* dz_full = w_empty + 2;
+  uint64_t* dz_empty = dz_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dz_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+      mbar_init(&w_full[i], 4);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(dz_full, 1);
+    mbar_init(dz_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int nunits = p.row_blocks * p.nchunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int ucount = 0, gt = 0;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
+        const UnitInfo ui = decode_unit(p, u);
+        const int ua = ucount & 1;
+        mbar_wait(&a_empty[ua], ((ucount >> 1) & 1) ^ 1);
+        mbar_expect_tx(&a_full[ua], C::A_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d(sA + ua * C::A_BYTES + kb * (128 * 128), &tmA, &a_full[ua], kb * 64, ui.g0);
+        for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
+          const int st = gt % NSTAGE;
+          mbar_wait(&b_empty[st], ((gt / NSTAGE) & 1) ^ 1);
+          mbar_expect_tx(&b_full[st], C::B_BYTES + (MODE != SIM_MOCO ? C::CS_BYTES : 0));
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d(sB + st * C::B_BYTES + kb * (BN * 128), &tmB, &b_full[st], kb * 64, t * BN);
+          if (MODE != SIM_MOCO) bulk_load_1d(sC + st * C::CS_BYTES, p.colstat + t * BN, C::CS_BYTES, &b_full[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC_S = make_idesc(128, BN, 0, 0);
+      constexpr uint32_t IDESC_D = make_idesc(128, DP, 0, 1);  // A = W from TMEM, B = same smem tile read MN-major
+      int ucount = 0, gt = 0;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
+        const UnitInfo ui = decode_unit(p, u);
+        const int ua = ucount & 1;
+        mbar_wait(&a_full[ua], (ucount >> 1) & 1);
+        const uint32_t abase = smem_u32(sA + ua * C::A_BYTES);
+        const int ntile = ui.t1 - ui.t0;
+        const int gt0 = gt;
+        // software pipeline: S(i) is issued one tile ahead of dZ(i-1)
+        for (int i = 0; i <= ntile; ++i) {
+          if (i < ntile) {
+            const int g = gt0 + i;
+            const int st = g % NSTAGE, buf = g & 1;
+            mbar_wait(&b_full[st], (g / NSTAGE) & 1);
+            mbar_wait(&s_empty[buf], ((g >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t bbase = smem_u32(sB + st * C::B_BYTES);
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_ss(tmem + C::T_S + buf * BN, desc_kmajor(abase + kb * (128 * 128) + k4 * 32),
+                        desc_kmajor(bbase + kb * (BN * 128) + k4 * 32), IDESC_S, (kb | k4) != 0);
+            umma_commit(&s_full[buf]);
+          }
+          if (i > 0) {
+            const int g = gt0 + i - 1;
+            const int st = g % NSTAGE, buf = g & 1;
+            mbar_wait(&w_full[buf], (g >> 1) & 1);
+            if (i == 1) mbar_wait(dz_empty, (ucount & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t bbase = smem_u32(sB + st * C::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BN / 16; ++k)
+              umma_ts(tmem + C::T_DZ, tmem + C::T_W + buf * 64 + k * 8,
+                      desc_mnmajor(bbase + k * (16 * 128), BN * 128), IDESC_D, (i > 1 || k > 0) ? 1u : 0u);
+            umma_commit(&b_empty[st]);
+            umma_commit(&w_empty[buf]);
+          }
+        }
+        gt = gt0 + ntile;
+        umma_commit(dz_full);
+        umma_commit(&a_empty[ua]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ weight warpgroups + epilogue
+    const int wg = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row_l = q * 32 + lane;
+    const uint32_t tlane = static_cast<uint32_t>(q * 32) << 16;
+    int gt = 0, ucount = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
+      const UnitInfo ui = decode_unit(p, u);
+      const int a_glob = ui.g0 + row_l;
+      const bool valid = row_l < ui.nvalid;
+      float rs = 0.f;
+      if (valid) rs = (MODE == SIM_MOCO) ? p.rowstat[ui.lrow0 + row_l] : p.rowstat[a_glob];
+      for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
+        if ((gt & 1) != wg) continue;
+        const int st = gt % NSTAGE;
+        if (MODE != SIM_MOCO) mbar_wait(&b_full[st], (gt / NSTAGE) & 1);  // column stats landed with the B tile
+        mbar_wait(&s_full[wg], (gt >> 1) & 1);
+        mbar_wait(&w_empty[wg], ((gt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const int j0 = t * BN;
+        const bool special = (MODE != SIM_MOCO) && (j0 < ui.g0 + 128) && (j0 + BN > ui.g0);
+        const uint32_t t_s = tmem + tlane + C::T_S + wg * BN;
+        const uint32_t t_w = tmem + tlane + C::T_W + wg * 64;
+        const float* cs = reinterpret_cast<const float*>(sC + st * C::CS_BYTES);
+        if (special)
+          bwd_tile<MODE, true>(t_s, t_w, p, a_glob, j0, rs, cs, &s_empty[wg], lane);
+        else
+          bwd_tile<MODE, false>(t_s, t_w, p, a_glob, j0, rs, cs, &s_empty[wg], lane);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&w_full[wg]);
+      }
+      // ---- epilogue: this warpgroup drains DP/2 accumulator columns of the finished row block
+      mbar_wait(dz_full, ucount & 1);
+      tc_fence_after();
+      constexpr int CPW = DP / 2;  // columns per warpgroup
+#pragma unroll
+      for (int cc = 0; cc < CPW / 32; ++cc) {
+        const int col0 = wg * CPW + cc * 32;
+        uint32_t v[32];
+        tmem_ld_x32(tmem + tlane + C::T_DZ + col0, v);
+        tmem_ld_wait_regs(v);
+        if (valid) {
+          float* dst = p.dacc + static_cast<size_t>(ui.lrow0 + row_l) * p.ld_dacc + col0;
+          if (p.use_atomic) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              red_add_v4(dst + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              reinterpret_cast<float4*>(dst)[i] =
+                  make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                              __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dz_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace ssvb

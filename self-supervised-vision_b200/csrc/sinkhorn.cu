@@ -1,0 +1,231 @@
+// Sinkhorn-Knopp codes (SwAV) — replaces SwavLoss.compute_codes_sinkhorn (reference utils/losses.py:213-224).
+//
+// Scaling-vector form of the reference's dense iteration (never materialises Q or its transpose):
+//   E_bk = exp((s_bk - smax)/eps)            (the global shift cancels in the first normalisation)
+//   u_k  = sum_b E_bk * beta_b ;  alpha_k = (1/K) / u_k          (row / prototype normalisation, :219-220)
+//   v_b  = sum_k alpha_k E_bk ;   beta_b  = (1/B) / v_b          (column / sample normalisation, :221)
+//   codes_bk = alpha_k E_bk / v_b                                 (final column normalisation, :222-223)
+// One pass over the scores per iteration (they stay L2-resident: 49 MB at 4096x3000): each warp stages the
+// exp'd row in shared memory, reduces v_b with shuffles, then either feeds the next iteration's column sums
+// (block-local shared accumulators -> per-block partial rows -> deterministic tree) or writes the codes.
+#include "sim_host.cuh"
+
+using namespace ssvb;
+
+namespace {
+
+struct SkWs {
+  float* smax_part;  // [grid]
+  float* smax;       // [1]
+  float* upart;      // [grid x kpad]
+  float* alpha;      // [kpad]
+  size_t bytes;
+  int grid;
+  int kpad;
+};
+inline int sk_grid() { return num_sms() * 2; }
+SkWs sk_ws(void* base, int64_t k) {
+  Carver c(base);
+  SkWs w;
+  w.grid = sk_grid();
+  w.kpad = static_cast<int>(round_up(k, 4));
+  w.smax_part = c.take<float>(w.grid);
+  w.smax = c.take<float>(4);
+  w.upart = c.take<float>(static_cast<size_t>(w.grid) * w.kpad);
+  w.alpha = c.take<float>(w.kpad);
+  w.bytes = c.used();
+  return w;
+}
+
+__global__ void sk_max_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, float* part) {
+  float m = -INFINITY;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  for (int64_t r = gw; r < b; r += warps)
+    for (int c = lane; c < k; c += 32) m = fmaxf(m, __ldg(s + r * ld + c));
+  __shared__ float red[32];
+  m = warp_max(m);
+  if (lane == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+    t = warp_max(t);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+  }
+}
+__global__ void sk_max_final_kernel(const float* part, int n, float* out) {
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += 32) m = fmaxf(m, part[i]);
+  m = warp_max(m);
+  if (threadIdx.x == 0) out[0] = m;
+}
+
+// alpha_k = (1/K) / sum_g upart[g][k]
+__global__ void sk_alpha_kernel(const float* __restrict__ upart, int grid, int kpad, int k, float* __restrict__ alpha) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= k) return;
+  float u = 0.f;
+  for (int g = 0; g < grid; ++g) u += upart[static_cast<size_t>(g) * kpad + c];
+  alpha[c] = (1.f / static_cast<float>(k)) / u;
+}
+
+// PHASE 0: u_k = sum_b E_bk                     (beta uniform: the reference's Q / sum(Q) scalar cancels)
+// PHASE 1: v_b from alpha; u_k += E_bk / (B v_b) (middle iterations)
+// PHASE 2: v_b from alpha; codes = alpha E / v_b (last pass)
+// REGACC: column sums are accumulated in registers (thread <-> columns tid + 256 j, j < 16, i.e. K <= 4096)
+// from the 8 rows the block's warps just staged in shared memory: no atomics, deterministic.  Otherwise
+// (wide K) block-local shared-memory atomics.
+constexpr int kSkJ = 16;
+template <int PHASE, bool REGACC>
+__global__ void sk_pass_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, float inv_eps_log2e,
+                               const float* __restrict__ smax, const float* __restrict__ alpha,
+                               float* __restrict__ upart, int kpad, float* __restrict__ codes, int64_t ldc) {
+  extern __shared__ float sk_smem[];
+  __shared__ float beta_s[32];
+  const int nwarp = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* uloc = sk_smem;                       // [kpad] (atomic path only)
+  float* erow = sk_smem + kpad + w * kpad;     // this warp's exp'd row
+  const float shift = smax[0] * inv_eps_log2e;
+  float acc[kSkJ];
+#pragma unroll
+  for (int j = 0; j < kSkJ; ++j) acc[j] = 0.f;
+  if (PHASE != 2 && !REGACC) {
+    for (int c = threadIdx.x; c < kpad; c += blockDim.x) uloc[c] = 0.f;
+    __syncthreads();
+  }
+  const float inv_b = 1.f / static_cast<float>(b);
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * nwarp; base < b; base += static_cast<int64_t>(gridDim.x) * nwarp) {
+    const int64_t r = base + w;
+    if (r < b) {
+      const float* row = s + r * ld;
+      float v = 0.f;
+      for (int c = lane; c < k; c += 32) {
+        const float e = ex2f(fmaf(__ldg(row + c), inv_eps_log2e, -shift));
+        erow[c] = e;
+        if (PHASE != 0) v += e * alpha[c];
+      }
+      float beta = 1.f;
+      if (PHASE != 0) {
+        v = warp_sum(v);
+        beta = inv_b / v;
+      }
+      __syncwarp();
+      if (PHASE == 2) {
+        const float iv = 1.f / v;
+        float* out = codes + r * ldc;
+        for (int c = lane; c < k; c += 32) out[c] = erow[c] * alpha[c] * iv;
+        __syncwarp();
+      } else if (!REGACC) {
+        for (int c = lane; c < k; c += 32) atomicAdd(&uloc[c], erow[c] * beta);
+        __syncwarp();
+      } else if (lane == 0) {
+        beta_s[w] = beta;
+      }
+    }
+    if (PHASE != 2 && REGACC) {
+      __syncthreads();
+      const int nvalid = static_cast<int>(min(static_cast<int64_t>(nwarp), b - base));
+#pragma unroll
+      for (int j = 0; j < kSkJ; ++j) {
+        const int c = threadIdx.x + j * blockDim.x;
+        if (c < k) {
+          float a = acc[j];
+          for (int ww = 0; ww < nvalid; ++ww) a = fmaf(sk_smem[kpad + ww * kpad + c], beta_s[ww], a);
+          acc[j] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (PHASE != 2) {
+    if (REGACC) {
+#pragma unroll
+      for (int j = 0; j < kSkJ; ++j) {
+        const int c = threadIdx.x + j * blockDim.x;
+        if (c < k) upart[static_cast<size_t>(blockIdx.x) * kpad + c] = acc[j];
+      }
+    } else {
+      __syncthreads();
+      for (int c = threadIdx.x; c < k; c += blockDim.x) upart[static_cast<size_t>(blockIdx.x) * kpad + c] = uloc[c];
+    }
+  }
+}
+
+template <int PHASE>
+int sk_launch(bool regacc, int grid, int threads, size_t smem, cudaStream_t s, const float* scores, int64_t b, int k,
+              int64_t ld, float iel, const SkWs& ws, float* codes, int64_t ldc) {
+  if (regacc) {
+    SSVB_CUDA(cudaFuncSetAttribute(sk_pass_kernel<PHASE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+    sk_pass_kernel<PHASE, true><<<grid, threads, smem, s>>>(scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart,
+                                                            ws.kpad, codes, ldc);
+  } else {
+    SSVB_CUDA(cudaFuncSetAttribute(sk_pass_kernel<PHASE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+    sk_pass_kernel<PHASE, false><<<grid, threads, smem, s>>>(scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart,
+                                                             ws.kpad, codes, ldc);
+  }
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+}  // namespace
+
+namespace ssvb {
+// shared with swav.cu: scores -> codes on `s`
+int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters, float* codes,
+                 int64_t ld_codes, void* workspace, cudaStream_t s) {
+  SkWs ws = sk_ws(workspace, k);
+  const int kk = static_cast<int>(k);
+  const float iel = SSVB_LOG2E / eps;
+  int nwarp = 8;
+  while (nwarp > 1 && static_cast<size_t>(nwarp + 1) * ws.kpad * 4 > 200 * 1024) nwarp >>= 1;
+  const size_t smem = static_cast<size_t>(nwarp + 1) * ws.kpad * 4;
+  if (smem > 200 * 1024) return SSVB_ERR_UNSUPPORTED;
+  const int threads = nwarp * 32;
+  const bool regacc = (nwarp == 8) && (k <= static_cast<int64_t>(kSkJ) * threads);
+  sk_max_kernel<<<ws.grid, 256, 0, s>>>(scores, b, kk, ld_scores, ws.smax_part);
+  SSVB_LAUNCH_CHECK();
+  sk_max_final_kernel<<<1, 32, 0, s>>>(ws.smax_part, ws.grid, ws.smax);
+  SSVB_LAUNCH_CHECK();
+  const unsigned agrid = static_cast<unsigned>(ceil_div(k, 256));
+  if (n_iters <= 0) {
+    // no iterations: codes = E / rowsum(E)  (alpha = 1)
+    fill_kernel<<<agrid, 256, 0, s>>>(ws.alpha, k, 1.f);
+    SSVB_LAUNCH_CHECK();
+  } else {
+    SSVB_TRY(sk_launch<0>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+    sk_alpha_kernel<<<agrid, 256, 0, s>>>(ws.upart, ws.grid, ws.kpad, kk, ws.alpha);
+    SSVB_LAUNCH_CHECK();
+    for (int it = 1; it < n_iters; ++it) {
+      SSVB_TRY(sk_launch<1>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+      sk_alpha_kernel<<<agrid, 256, 0, s>>>(ws.upart, ws.grid, ws.kpad, kk, ws.alpha);
+      SSVB_LAUNCH_CHECK();
+    }
+  }
+  SSVB_TRY(sk_launch<2>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+  return SSVB_OK;
+}
+size_t sinkhorn_ws_bytes(int64_t k) { return sk_ws(nullptr, k).bytes; }
+}  // namespace ssvb
+
+extern "C" {
+
+size_t ssvb_sinkhorn_workspace_bytes(int64_t b, int64_t k) {
+  (void)b;
+  return k > 0 ? sk_ws(nullptr, k).bytes : 0;
+}
+
+int ssvb_sinkhorn(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters, float* codes,
+                  int64_t ld_codes, void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (!scores || !codes || !workspace || b <= 0 || k <= 0 || !(eps > 0.f) || n_iters < 0 || ld_scores < k ||
+      ld_codes < k)
+    return SSVB_ERR_INVALID;
+  if (workspace_bytes < sk_ws(nullptr, k).bytes) return SSVB_ERR_WORKSPACE;
+  return sinkhorn_run(scores, b, k, ld_scores, eps, n_iters, codes, ld_codes, workspace,
+                      static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,12 @@
+"""ssv_b200 — B200-native (sm_100a) drop-in for the loss layer of NightShade99/Self-Supervised-Vision.
+
+Same class names, constructor kwargs and forward signatures as the reference's `utils/losses.py`
+and the ring buffers of `models/moco.py` / `models/swav.py`; the arithmetic runs in hand-written
+CUDA kernels behind the C ABI of include/ssv_b200.h.  No CPU fallback.
+"""
+from . import _cabi  # noqa: F401
+from .losses import (BarlowLoss, MocoLoss, MSELoss, RelicLoss, SimclrLoss, SimSiamLoss, SwavLoss)  # noqa: F401
+from .banks import FeatureBank, MemoryBank, Prototypes  # noqa: F401
+
+__all__ = ["SimclrLoss", "MocoLoss", "BarlowLoss", "SimSiamLoss", "RelicLoss", "SwavLoss", "MSELoss",
+           "MemoryBank", "FeatureBank", "Prototypes"]

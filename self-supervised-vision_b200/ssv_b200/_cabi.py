@@ -1,0 +1,108 @@
+"""ctypes binding of libssv_b200.so (the C ABI declared in include/ssv_b200.h).
+
+No CPU fallback and no alternative backend: if the shared library is missing, or a call
+returns non-zero, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libssv_b200.so")
+HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "ssv_b200.h"))
+
+_CTYPE = {
+    "int": c_int, "float": c_float, "int64_t": c_int64, "size_t": c_size_t,
+    "const char*": c_char_p, "void": None,
+}
+
+
+def _ctype_of(decl: str):
+    decl = decl.strip()
+    if decl.endswith("*") and decl != "const char*":
+        return c_void_p
+    return _CTYPE[decl]
+
+
+def parse_header(path: str = HEADER_PATH):
+    """Return {name: (restype, [argtypes])} for every `ssvb_*` prototype in the public header, so the
+    binding can never drift from include/ssv_b200.h."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ ]*?\*?)\s*(ssvb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                # drop the parameter name
+                mm = re.match(r"(.*?[\*\s])([A-Za-z_][A-Za-z0-9_]*)$", a)
+                typ = mm.group(1).strip() if mm else a
+                typ = typ.replace("const ", "") if not typ.startswith("const char") else typ
+                typ = typ.replace(" *", "*").strip()
+                argtypes.append(_ctype_of(typ))
+        protos[name] = (_ctype_of(ret.replace("const char *", "const char*")), argtypes)
+    return protos
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"ssv_b200: {LIB_PATH} not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C self-supervised-vision_b200`). There is no CPU / PyTorch fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in parse_header().items():
+            fn = getattr(l, name)  # AttributeError here == header/library mismatch: fail loudly
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = l
+    return _lib
+
+
+def strerror(rc: int) -> str:
+    return lib().ssvb_strerror(rc).decode()
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {strerror(rc)}")
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ssv_b200 runs on a B200 (sm_100a) only: got a CPU tensor; there is no CPU fallback")
+
+
+def as_f32_rows(t):
+    """fp32, last-dim contiguous, 16-byte aligned rows (what the C ABI requires)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.stride(-1) != 1 or (t.stride(0) % 4) or (t.data_ptr() % 16):
+        t = t.contiguous()
+    return t
+
+
+def byte_buffer(nbytes: int, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)

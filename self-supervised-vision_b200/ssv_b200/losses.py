@@ -1,0 +1,399 @@
+"""Drop-in loss modules: same names / ctor kwargs / forward signatures as the reference
+`utils/losses.py` (SimclrLoss :8-46, MocoLoss :49-72, BarlowLoss :120-142, SimSiamLoss :145-151,
+RelicLoss :154-201, SwavLoss :204-235) plus an nn.MSELoss()-compatible module for BYOL
+(models/byol.py:89).  Each forward returns a 0-dim tensor with autograd history; forward and
+backward both run in the CUDA kernels of libssv_b200.so through ctypes (no torch ops on the path
+except buffer allocation).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _cabi as C
+
+
+def _ld(t):
+    return t.stride(0)
+
+
+# --------------------------------------------------------------------------------------------- NT-Xent
+class _NtxentFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, zi, zj, normalize, temperature):
+        C.require_cuda(zi, zj)
+        if zi.shape != zj.shape or zi.dim() != 2:
+            raise ValueError("SimclrLoss expects two [N, d] tensors of the same shape")
+        xi, xj = C.as_f32_rows(zi), C.as_f32_rows(zj)
+        n, d = xi.shape
+        L = C.lib()
+        dev = xi.device
+        with torch.cuda.device(dev):
+            saved = C.byte_buffer(L.ssvb_ntxent_saved_bytes(n, d), dev)
+            ws_bytes = L.ssvb_ntxent_workspace_bytes(n, d)
+            ws = C.byte_buffer(ws_bytes, dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            C.check(L.ssvb_ntxent_fwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), int(bool(normalize)),
+                                      float(temperature), C.ptr(loss), C.ptr(saved), C.ptr(ws), ws_bytes,
+                                      C.stream_ptr(dev)), "ssvb_ntxent_fwd")
+        ctx.save_for_backward(xi, xj, saved)
+        ctx.cfg = (int(bool(normalize)), float(temperature), zi.dtype, zj.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xi, xj, saved = ctx.saved_tensors
+        normalize, temperature, dti, dtj = ctx.cfg
+        n, d = xi.shape
+        L = C.lib()
+        dev = xi.device
+        with torch.cuda.device(dev):
+            go = grad_out.to(torch.float32).contiguous()
+            dzi, dzj = torch.empty_like(xi), torch.empty_like(xj)
+            ws_bytes = L.ssvb_ntxent_workspace_bytes(n, d)
+            ws = C.byte_buffer(ws_bytes, dev)
+            C.check(L.ssvb_ntxent_bwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), normalize, temperature,
+                                      C.ptr(go), C.ptr(saved), C.ptr(dzi), C.ptr(dzj), _ld(dzi), _ld(dzj),
+                                      C.ptr(ws), ws_bytes, C.stream_ptr(dev)), "ssvb_ntxent_bwd")
+        return dzi.to(dti), dzj.to(dtj), None, None
+
+
+class SimclrLoss(nn.Module):
+    """Reference: utils/losses.py:8-46 (ctor defaults normalize=False, temperature=1.0)."""
+
+    def __init__(self, normalize=False, temperature=1.0):
+        super().__init__()
+        self.normalize = normalize
+        self.temperature = temperature
+
+    def forward(self, zi, zj):
+        return _NtxentFn.apply(zi, zj, self.normalize, self.temperature)
+
+
+# --------------------------------------------------------------------------------------------- MoCo
+def _bank_shadow(memory_vectors):
+    """bf16 shadow of a device-resident MemoryBank (see banks.py) if `memory_vectors` is exactly its
+    live fp32 storage; otherwise None (the fp32 queue is converted inside the C call)."""
+    from .banks import lookup_shadow
+    return lookup_shadow(memory_vectors)
+
+
+class _MocoFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, query, keys, memory_vectors, normalize, temperature):
+        C.require_cuda(query, keys, memory_vectors)
+        if query.shape != keys.shape or query.dim() != 2 or memory_vectors.dim() != 2 \
+                or memory_vectors.shape[1] != query.shape[1]:
+            raise ValueError("MocoLoss expects query/keys [N, d] and memory_vectors [K, d]")
+        q, k = C.as_f32_rows(query), C.as_f32_rows(keys)
+        mem = C.as_f32_rows(memory_vectors.detach())
+        shadow = _bank_shadow(memory_vectors) if mem.data_ptr() == memory_vectors.data_ptr() else None
+        n, d = q.shape
+        kq = mem.shape[0]
+        L = C.lib()
+        dev = q.device
+        with torch.cuda.device(dev):
+            saved = C.byte_buffer(L.ssvb_moco_saved_bytes(n, kq, d), dev)
+            ws_bytes = L.ssvb_moco_workspace_bytes(n, kq, d)
+            ws = C.byte_buffer(ws_bytes, dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            C.check(L.ssvb_moco_fwd(C.ptr(q), C.ptr(k), C.ptr(mem), C.ptr(shadow), n, kq, d, _ld(q), _ld(k), _ld(mem),
+                                    int(bool(normalize)), float(temperature), C.ptr(loss), C.ptr(saved), C.ptr(ws),
+                                    ws_bytes, C.stream_ptr(dev)), "ssvb_moco_fwd")
+        ctx.save_for_backward(q, k, mem, saved)
+        ctx.shadow = shadow
+        ctx.cfg = (int(bool(normalize)), float(temperature), query.dtype, keys.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        q, k, mem, saved = ctx.saved_tensors
+        normalize, temperature, dtq, dtk = ctx.cfg
+        n, d = q.shape
+        kq = mem.shape[0]
+        L = C.lib()
+        dev = q.device
+        with torch.cuda.device(dev):
+            go = grad_out.to(torch.float32).contiguous()
+            dq, dk = torch.empty_like(q), torch.empty_like(k)
+            ws_bytes = L.ssvb_moco_workspace_bytes(n, kq, d)
+            ws = C.byte_buffer(ws_bytes, dev)
+            C.check(L.ssvb_moco_bwd(C.ptr(q), C.ptr(k), C.ptr(mem), C.ptr(ctx.shadow), n, kq, d, _ld(q), _ld(k),
+                                    _ld(mem), normalize, temperature, C.ptr(go), C.ptr(saved), C.ptr(dq), C.ptr(dk),
+                                    _ld(dq), _ld(dk), C.ptr(ws), ws_bytes, C.stream_ptr(dev)), "ssvb_moco_bwd")
+        return dq.to(dtq), dk.to(dtk), None, None, None
+
+
+class MocoLoss(nn.Module):
+    """Reference: utils/losses.py:49-72 (ctor defaults normalize=True, temperature=1.0)."""
+
+    def __init__(self, normalize=True, temperature=1.0):
+        super().__init__()
+        self.normalize = normalize
+        self.temperature = temperature
+
+    def forward(self, query, keys, memory_vectors):
+        return _MocoFn.apply(query, keys, memory_vectors, self.normalize, self.temperature)
+
+
+# --------------------------------------------------------------------------------------------- row-dot losses
+class _RowdotFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, o, t, kind):
+        C.require_cuda(o, t)
+        if o.shape != t.shape:
+            raise ValueError("row-dot losses expect two tensors of the same shape")
+        oo = C.as_f32_rows(o.reshape(-1, o.shape[-1]) if o.dim() != 2 else o)
+        tt = C.as_f32_rows(t.reshape(-1, t.shape[-1]) if t.dim() != 2 else t)
+        n, d = oo.shape
+        L = C.lib()
+        dev = oo.device
+        with torch.cuda.device(dev):
+            ws_bytes = L.ssvb_rowdot_workspace_bytes(n, d)
+            ws = C.byte_buffer(ws_bytes, dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            C.check(L.ssvb_rowdot_fwd(kind, C.ptr(oo), C.ptr(tt), n, d, _ld(oo), _ld(tt), C.ptr(loss), C.ptr(ws),
+                                      ws_bytes, C.stream_ptr(dev)), "ssvb_rowdot_fwd")
+        ctx.save_for_backward(oo, tt)
+        ctx.cfg = (kind, o.shape, o.dtype, t.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        oo, tt = ctx.saved_tensors
+        kind, shape, dto, dtt = ctx.cfg
+        need_o, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_o or need_t):
+            return None, None, None
+        n, d = oo.shape
+        L = C.lib()
+        dev = oo.device
+        with torch.cuda.device(dev):
+            go = grad_out.to(torch.float32).contiguous()
+            d_o = torch.empty_like(oo) if need_o else None
+            d_t = torch.empty_like(tt) if need_t else None
+            C.check(L.ssvb_rowdot_bwd(kind, C.ptr(oo), C.ptr(tt), n, d, _ld(oo), _ld(tt), C.ptr(go), C.ptr(d_o),
+                                      C.ptr(d_t), _ld(d_o) if need_o else 0, _ld(d_t) if need_t else 0,
+                                      C.stream_ptr(dev)), "ssvb_rowdot_bwd")
+        return (d_o.reshape(shape).to(dto) if need_o else None,
+                d_t.reshape(shape).to(dtt) if need_t else None, None)
+
+
+class SimSiamLoss(nn.Module):
+    """Reference: utils/losses.py:145-151 : -(online * target).sum(1).mean()."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, online_output, target_output):
+        return _RowdotFn.apply(online_output, target_output, 1)
+
+
+class MSELoss(nn.Module):
+    """nn.MSELoss()-compatible (mean reduction) for BYOL: models/byol.py:89, used :129-130."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, input, target):  # noqa: A002  (same parameter names as torch.nn.MSELoss)
+        return _RowdotFn.apply(input, target, 0)
+
+
+# --------------------------------------------------------------------------------------------- ReLIC
+class _RelicFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, zi, zj, zo, normalize, temperature, alpha):
+        C.require_cuda(zi, zj, zo)
+        if not (zi.shape == zj.shape == zo.shape) or zi.dim() != 2:
+            raise ValueError("RelicLoss expects three [N, d] tensors of the same shape")
+        xi, xj, xo = C.as_f32_rows(zi), C.as_f32_rows(zj), C.as_f32_rows(zo)
+        n, d = xi.shape
+        L = C.lib()
+        dev = xi.device
+        norm = int(bool(normalize))
+        with torch.cuda.device(dev):
+            st = C.stream_ptr(dev)
+            saved_c = C.byte_buffer(L.ssvb_ntxent_saved_bytes(n, d), dev)
+            ws_bytes = L.ssvb_ntxent_workspace_bytes(n, d)
+            ws = C.byte_buffer(ws_bytes, dev)
+            out = torch.empty(2, dtype=torch.float32, device=dev)
+            C.check(L.ssvb_ntxent_fwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), norm, float(temperature),
+                                      C.ptr(out), C.ptr(saved_c), C.ptr(ws), ws_bytes, st), "ssvb_ntxent_fwd")
+            saved_k = C.byte_buffer(L.ssvb_relic_kl_saved_bytes(n), dev)
+            kl = out[1:]
+            C.check(L.ssvb_relic_kl_fwd(C.ptr(xi), C.ptr(xj), C.ptr(xo), n, d, _ld(xi), _ld(xj), _ld(xo), norm,
+                                        float(temperature), float(alpha), C.ptr(kl), C.ptr(saved_k), None, 0, st),
+                    "ssvb_relic_kl_fwd")
+        ctx.save_for_backward(xi, xj, xo, saved_c, saved_k)
+        ctx.cfg = (norm, float(temperature), float(alpha), zi.dtype, zj.dtype, zo.dtype)
+        return out.sum()  # contrastive + alpha * KL  (utils/losses.py:201)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xi, xj, xo, saved_c, saved_k = ctx.saved_tensors
+        norm, temperature, alpha, dti, dtj, dto = ctx.cfg
+        n, d = xi.shape
+        L = C.lib()
+        dev = xi.device
+        with torch.cuda.device(dev):
+            st = C.stream_ptr(dev)
+            go = grad_out.to(torch.float32).contiguous()
+            dzi, dzj, dzo = torch.empty_like(xi), torch.empty_like(xj), torch.empty_like(xo)
+            ws_bytes = L.ssvb_ntxent_workspace_bytes(n, d)
+            ws = C.byte_buffer(ws_bytes, dev)
+            C.check(L.ssvb_ntxent_bwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), norm, temperature, C.ptr(go),
+                                      C.ptr(saved_c), C.ptr(dzi), C.ptr(dzj), _ld(dzi), _ld(dzj), C.ptr(ws), ws_bytes,
+                                      st), "ssvb_ntxent_bwd")
+            C.check(L.ssvb_relic_kl_bwd(C.ptr(xi), C.ptr(xj), C.ptr(xo), n, d, _ld(xi), _ld(xj), _ld(xo), norm,
+                                        temperature, alpha, C.ptr(go), C.ptr(saved_k), C.ptr(dzi), C.ptr(dzj),
+                                        C.ptr(dzo), _ld(dzi), _ld(dzj), _ld(dzo), st), "ssvb_relic_kl_bwd")
+        return dzi.to(dti), dzj.to(dtj), dzo.to(dto), None, None, None
+
+
+class RelicLoss(nn.Module):
+    """Reference: utils/losses.py:154-201 (ctor defaults normalize=True, temperature=1.0, alpha=0.5)."""
+
+    def __init__(self, normalize=True, temperature=1.0, alpha=0.5):
+        super().__init__()
+        self.normalize = normalize
+        self.temperature = temperature
+        self.alpha = alpha
+
+    def forward(self, zi, zj, z_orig):
+        return _RelicFn.apply(zi, zj, z_orig, self.normalize, self.temperature, self.alpha)
+
+
+# --------------------------------------------------------------------------------------------- Barlow Twins
+class _BarlowFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, zi, zj, normalize, lmbda):
+        C.require_cuda(zi, zj)
+        if zi.shape != zj.shape or zi.dim() != 2:
+            raise ValueError("BarlowLoss expects two [N, D] tensors of the same shape")
+        xi, xj = C.as_f32_rows(zi), C.as_f32_rows(zj)
+        n, d = xi.shape
+        L = C.lib()
+        dev = xi.device
+        with torch.cuda.device(dev):
+            saved = C.byte_buffer(L.ssvb_barlow_saved_bytes(n, d), dev)
+            ws_bytes = L.ssvb_barlow_workspace_bytes(n, d)
+            ws = C.byte_buffer(ws_bytes, dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            C.check(L.ssvb_barlow_fwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), int(bool(normalize)), float(lmbda),
+                                      C.ptr(loss), C.ptr(saved), C.ptr(ws), ws_bytes, C.stream_ptr(dev)),
+                    "ssvb_barlow_fwd")
+        ctx.save_for_backward(xi, xj, saved)
+        ctx.cfg = (int(bool(normalize)), float(lmbda), zi.dtype, zj.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xi, xj, saved = ctx.saved_tensors
+        normalize, lmbda, dti, dtj = ctx.cfg
+        n, d = xi.shape
+        L = C.lib()
+        dev = xi.device
+        with torch.cuda.device(dev):
+            go = grad_out.to(torch.float32).contiguous()
+            dzi, dzj = torch.empty_like(xi), torch.empty_like(xj)
+            ws_bytes = L.ssvb_barlow_workspace_bytes(n, d)
+            ws = C.byte_buffer(ws_bytes, dev)
+            C.check(L.ssvb_barlow_bwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), normalize, lmbda, C.ptr(go),
+                                      C.ptr(saved), C.ptr(dzi), C.ptr(dzj), _ld(dzi), _ld(dzj), C.ptr(ws), ws_bytes,
+                                      C.stream_ptr(dev)), "ssvb_barlow_bwd")
+        return dzi.to(dti), dzj.to(dtj), None, None
+
+
+class BarlowLoss(nn.Module):
+    """Reference: utils/losses.py:120-142 (ctor defaults normalize=True, off_diagonal_weight=0.005)."""
+
+    def __init__(self, normalize=True, off_diagonal_weight=0.005):
+        super().__init__()
+        self.normalize = normalize
+        self.lmbda = off_diagonal_weight
+
+    def forward(self, z_i, z_j):
+        return _BarlowFn.apply(z_i, z_j, self.normalize, self.lmbda)
+
+
+# --------------------------------------------------------------------------------------------- SwAV
+class _SwavFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z1, z2, prototypes, bank, temperature, eps, n_iters):
+        C.require_cuda(z1, z2, prototypes, bank)
+        if z1.shape != z2.shape or z1.dim() != 2 or prototypes.dim() != 2 or prototypes.shape[1] != z1.shape[1]:
+            raise ValueError("SwavLoss expects z_1/z_2 [B, d] and prototypes [K, d]")
+        x1, x2, pc = C.as_f32_rows(z1), C.as_f32_rows(z2), C.as_f32_rows(prototypes)
+        bk = C.as_f32_rows(bank.detach()) if bank is not None and bank.shape[0] > 0 else None
+        nb, d = x1.shape
+        nbank = bk.shape[0] if bk is not None else 0
+        k = pc.shape[0]
+        L = C.lib()
+        dev = x1.device
+        with torch.cuda.device(dev):
+            saved = C.byte_buffer(L.ssvb_swav_saved_bytes(nb, nbank, k, d), dev)
+            ws_bytes = L.ssvb_swav_workspace_bytes(nb, nbank, k, d)
+            ws = C.byte_buffer(ws_bytes, dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            C.check(L.ssvb_swav_fwd(C.ptr(x1), C.ptr(x2), C.ptr(bk), C.ptr(pc), nb, nbank, k, d, _ld(x1), _ld(x2),
+                                    _ld(bk) if bk is not None else 0, _ld(pc), float(temperature), float(eps),
+                                    int(n_iters), C.ptr(loss), C.ptr(saved), C.ptr(ws), ws_bytes, C.stream_ptr(dev)),
+                    "ssvb_swav_fwd")
+        ctx.save_for_backward(x1, x2, pc, saved, *([bk] if bk is not None else []))
+        ctx.cfg = (float(temperature), z1.dtype, z2.dtype, prototypes.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x1, x2, pc, saved, *rest = ctx.saved_tensors
+        bk = rest[0] if rest else None
+        temperature, dt1, dt2, dtp = ctx.cfg
+        nb, d = x1.shape
+        nbank = bk.shape[0] if bk is not None else 0
+        k = pc.shape[0]
+        L = C.lib()
+        dev = x1.device
+        with torch.cuda.device(dev):
+            go = grad_out.to(torch.float32).contiguous()
+            dz1, dz2, dpc = torch.empty_like(x1), torch.empty_like(x2), torch.empty_like(pc)
+            ws_bytes = L.ssvb_swav_workspace_bytes(nb, nbank, k, d)
+            ws = C.byte_buffer(ws_bytes, dev)
+            C.check(L.ssvb_swav_bwd(C.ptr(x1), C.ptr(x2), C.ptr(bk), C.ptr(pc), nb, nbank, k, d, _ld(x1), _ld(x2),
+                                    _ld(bk) if bk is not None else 0, _ld(pc), temperature, C.ptr(go), C.ptr(saved),
+                                    C.ptr(dz1), C.ptr(dz2), C.ptr(dpc), _ld(dz1), _ld(dz2), _ld(dpc), C.ptr(ws),
+                                    ws_bytes, C.stream_ptr(dev)), "ssvb_swav_bwd")
+        return dz1.to(dt1), dz2.to(dt2), dpc.to(dtp), None, None, None, None
+
+
+class SwavLoss(nn.Module):
+    """Reference: utils/losses.py:204-235 (ctor defaults temperature=0.1, sinkhorn_eps=0.05, sinkhorn_iters=3).
+    `device` is kept as an attribute because the reference exposes one (utils/losses.py:208); it is unused."""
+
+    def __init__(self, temperature=0.1, sinkhorn_eps=0.05, sinkhorn_iters=3):
+        super().__init__()
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.temperature = temperature
+        self.n_iters = sinkhorn_iters
+        self.eps = sinkhorn_eps
+
+    @torch.no_grad()
+    def compute_codes_sinkhorn(self, scores):
+        C.require_cuda(scores)
+        if scores.dim() != 2:
+            raise ValueError("compute_codes_sinkhorn expects [B, K] scores")
+        s = scores.detach()
+        if s.dtype != torch.float32 or s.stride(1) != 1:
+            s = s.float().contiguous()
+        b, k = s.shape
+        L = C.lib()
+        dev = s.device
+        with torch.cuda.device(dev):
+            codes = torch.empty(b, k, dtype=torch.float32, device=dev)
+            ws_bytes = L.ssvb_sinkhorn_workspace_bytes(b, k)
+            ws = C.byte_buffer(ws_bytes, dev)
+            C.check(L.ssvb_sinkhorn(C.ptr(s), b, k, s.stride(0), float(self.eps), int(self.n_iters), C.ptr(codes),
+                                    codes.stride(0), C.ptr(ws), ws_bytes, C.stream_ptr(dev)), "ssvb_sinkhorn")
+        return codes
+
+    def forward(self, z_1, z_2, prototypes, bank_features=None):
+        return _SwavFn.apply(z_1, z_2, prototypes, bank_features, self.temperature, self.eps, self.n_iters)

@@ -1,0 +1,307 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs the CPU oracle on identical seeded inputs,
+and vs the golden fixtures produced by the reference itself.
+
+Tolerances are BASELINE.json's: loss relative error <= 1e-3, gradient relative L2 error <= 1e-2
+(bf16 tensor-core operands, fp32 accumulation); ring-buffer bookkeeping bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2, rel_scalar
+from oracle import ssl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-3
+GRAD_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def S():
+    import ssv_b200
+    assert torch.cuda.is_available()
+    from ssv_b200 import _cabi
+    assert _cabi.lib().ssvb_device_check() == 0, "not a B200"
+    return ssv_b200
+
+
+def dev(x, grad=True):
+    t = torch.as_tensor(np.asarray(x, dtype=np.float32)).cuda()
+    return t.requires_grad_(grad)
+
+
+def randn(seed, *shape):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float32).numpy()
+
+
+def clustered(seed, n, d, rho=0.8):
+    a = randn(seed, n, d)
+    b = (rho * a + (1 - rho ** 2) ** 0.5 * randn(seed + 1, n, d)).astype(np.float32)
+    if n >= 4:
+        a[1] = a[0] + 0.01 * randn(seed + 2, d)
+        b[3] = a[2] + 0.01 * randn(seed + 3, d)
+    return a, b
+
+
+def check(loss, grads, ref_loss, ref_grads, what, loss_tol=LOSS_TOL, grad_tol=GRAD_TOL):
+    lerr = rel_scalar(loss, ref_loss)
+    assert np.isfinite(float(loss)), f"{what}: loss not finite"
+    assert lerr <= loss_tol, f"{what}: loss {float(loss)} vs {ref_loss} rel {lerr:.3e}"
+    for i, (g, r) in enumerate(zip(grads, ref_grads)):
+        g = g.detach().cpu().numpy()
+        assert np.isfinite(g).all(), f"{what}: grad {i} not finite"
+        gerr = rel_l2(g, r)
+        assert gerr <= grad_tol, f"{what}: grad {i} rel-L2 {gerr:.3e}"
+
+
+# ------------------------------------------------------------------------------------------------ NT-Xent
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d", "cfg1"])
+def test_ntxent_golden(S, tag):
+    g = load_golden("ntxent")
+    norm, tau = bool(g[f"{tag}_cfg"][0]), float(g[f"{tag}_cfg"][1])
+    zi, zj = dev(g[f"{tag}_zi"]), dev(g[f"{tag}_zj"])
+    loss = S.SimclrLoss(norm, tau)(zi, zj)
+    loss.backward()
+    if tag == "d":
+        assert abs(loss.item()) < 1e-5 and zi.grad.abs().max().item() < 1e-5
+        return
+    check(loss.item(), [zi.grad, zj.grad], float(g[f"{tag}_loss"]), [g[f"{tag}_dzi"], g[f"{tag}_dzj"]], f"ntxent[{tag}]")
+
+
+@pytest.mark.parametrize("n,d,norm,tau,clu", [
+    (256, 128, True, 0.5, False),      # BASELINE configs[0]
+    (100, 64, True, 0.5, False),       # ragged: M=200 not a tile multiple, one 64-wide k block
+    (129, 128, True, 0.07, True),      # peaky softmax, near-duplicate negatives, diagonal straddles tiles
+    (384, 96, False, 1.0, False),      # raw inputs -> online-max path, padded feature dim
+    (640, 128, True, 0.02, True),      # tau below the fixed-shift bound -> online-max path
+    (2048, 128, True, 0.5, False),     # several row blocks x column chunks (atomic accumulation path)
+    (1024, 32, True, 0.1, False),
+])
+def test_ntxent_oracle(S, n, d, norm, tau, clu):
+    zi, zj = clustered(3, n, d) if clu else (randn(0, n, d), randn(1, n, d))
+    if not norm:
+        zi, zj = zi * 0.3, zj * 0.3
+    ref = O.ntxent(zi, zj, norm, tau)
+    a, b = dev(zi), dev(zj)
+    loss = S.SimclrLoss(norm, tau)(a, b)
+    loss.backward()
+    check(loss.item(), [a.grad, b.grad], ref[0], ref[1:], f"ntxent n={n} d={d} tau={tau}")
+
+
+def test_ntxent_grad_scale_and_determinism(S):
+    zi, zj = randn(0, 300, 128), randn(1, 300, 128)
+    a, b = dev(zi), dev(zj)
+    fn = S.SimclrLoss(True, 0.5)
+    l1 = fn(a, b)
+    (3.0 * l1).backward()
+    g3 = a.grad.clone()
+    a.grad = None
+    l2 = fn(a, b)
+    l2.backward()
+    assert torch.equal(l1, l2), "loss must be run-to-run deterministic"
+    assert rel_l2(g3.cpu().numpy(), 3.0 * a.grad.cpu().numpy()) < 1e-6
+
+
+def test_ntxent_permutation_invariance(S):
+    zi, zj = randn(0, 200, 128), randn(1, 200, 128)
+    perm = torch.randperm(200, generator=torch.Generator().manual_seed(5)).numpy()
+    fn = S.SimclrLoss(True, 0.2)
+    l0 = fn(dev(zi, False), dev(zj, False)).item()
+    l1 = fn(dev(zi[perm], False), dev(zj[perm], False)).item()
+    assert abs(l0 - l1) / abs(l0) < 1e-5
+
+
+def test_ntxent_large_self_consistency(S):
+    """BASELINE size (N=32768 per view, M=65536): chunked fp32 closed form on the GPU as witness for the
+    loss, and exact properties for the gradient: sum_a dz_a . z_a == 0 (normalised rows), finite values."""
+    n, d, tau = 32768, 128, 0.5
+    g = torch.Generator(device="cuda").manual_seed(0)
+    zi = torch.randn(n, d, device="cuda", generator=g)
+    zj = torch.randn(n, d, device="cuda", generator=g)
+    a, b = zi.clone().requires_grad_(True), zj.clone().requires_grad_(True)
+    loss = S.SimclrLoss(True, tau)(a, b)
+    loss.backward()
+    z = torch.nn.functional.normalize(torch.cat([zi, zj]), dim=-1)
+    m = 2 * n
+    tot = torch.zeros((), dtype=torch.float64, device="cuda")
+    for r0 in range(0, m, 4096):
+        s = (z[r0:r0 + 4096] @ z.t()) / tau
+        idx = torch.arange(r0, r0 + 4096, device="cuda")
+        pos = s[torch.arange(4096, device="cuda"), (idx + n) % m].clone()
+        s[torch.arange(4096, device="cuda"), idx] = float("-inf")
+        tot += (torch.logsumexp(s, 1) - pos).double().sum()
+    ref = (tot / m).item()
+    assert rel_scalar(loss.item(), ref) <= LOSS_TOL
+    assert torch.isfinite(a.grad).all() and torch.isfinite(b.grad).all()
+    radial = (a.grad * zi).sum(1).abs().max().item()
+    assert radial < 1e-6 * max(1.0, a.grad.abs().max().item() * zi.norm(dim=1).max().item()) + 1e-7
+
+
+# ------------------------------------------------------------------------------------------------ MoCo
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_moco_golden(S, tag):
+    g = load_golden("moco")
+    norm, tau = bool(g[f"{tag}_cfg"][0]), float(g[f"{tag}_cfg"][1])
+    q, k, mem = dev(g[f"{tag}_q"]), dev(g[f"{tag}_k"]), dev(g[f"{tag}_mem"], False)
+    loss = S.MocoLoss(norm, tau)(q, k, mem)
+    loss.backward()
+    check(loss.item(), [q.grad, k.grad], float(g[f"{tag}_loss"]), [g[f"{tag}_dq"], g[f"{tag}_dk"]], f"moco[{tag}]")
+
+
+@pytest.mark.parametrize("n,k,d,tau", [(256, 65536, 128, 0.07), (100, 1000, 128, 0.07), (300, 4100, 64, 0.2)])
+def test_moco_oracle(S, n, k, d, tau):
+    q, kk = randn(0, n, d), randn(1, n, d)
+    mem = randn(2, k, d)
+    mem /= np.linalg.norm(mem, axis=1, keepdims=True)
+    mem[:7] = 0.0
+    ref = O.moco(q, kk, mem, True, tau)
+    a, b, m = dev(q), dev(kk), dev(mem, False)
+    loss = S.MocoLoss(True, tau)(a, b, m)
+    loss.backward()
+    check(loss.item(), [a.grad, b.grad], ref[0], ref[1:], f"moco n={n} k={k}")
+
+
+def test_moco_with_device_bank(S):
+    """cfg2: 256 queries x 65536-entry queue + enqueue with a wrap; bank-resident bf16 shadow path."""
+    n, ksz, d, tau = 256, 65536, 128, 0.07
+    bank = S.MemoryBank(ksz, d)
+    fill = randn(5, ksz, d)
+    ref_bank, ref_ptr = np.zeros((ksz, d), np.float32), 0
+    # fill the queue in 4 big batches, then advance the pointer so that the next enqueue wraps
+    for i in range(4):
+        chunk = fill[i * 16384:(i + 1) * 16384]
+        bank.add_batch(torch.from_numpy(chunk).cuda())
+        nrm = np.maximum(np.linalg.norm(chunk.astype(np.float64), axis=1, keepdims=True), 1e-12)
+        ref_bank[i * 16384:(i + 1) * 16384] = (chunk / nrm).astype(np.float32)
+    assert bank.ptr == 0
+    bank.add_batch(torch.from_numpy(fill[:ksz - 100]).cuda())
+    assert bank.ptr == ksz - 100
+    q, kk = randn(0, n, d), randn(1, n, d)
+    a, b = dev(q), dev(kk)
+    mem = bank.get_vectors().to("cuda")
+    loss = S.MocoLoss(True, tau)(a, b, mem)
+    loss.backward()
+    ref = O.moco(q, kk, mem.cpu().numpy(), True, tau)
+    check(loss.item(), [a.grad, b.grad], ref[0], ref[1:], "moco cfg2 (bank)")
+    before = mem.cpu().numpy().copy()
+    bank.add_batch(b.detach())
+    exp_bank, exp_ptr = O.ring_enqueue(before, ksz - 100, kk, True)
+    assert bank.ptr == exp_ptr == 156
+    got = bank.bank.cpu().numpy()
+    changed = np.where((got != before).any(1))[0]
+    assert set(changed) <= set(list(range(ksz - 100, ksz)) + list(range(156)))
+    np.testing.assert_allclose(got, exp_bank, rtol=5e-7, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ ring buffers
+def test_ring_buffers_golden(S):
+    g = load_golden("banks")
+    mb, fb = S.MemoryBank(10, 4), S.FeatureBank(7, 3 + 1)  # d must be a multiple of 4: pad the 3-wide golden
+    assert not mb.bank.any().item() and mb.ptr == 0
+    for step in range(5):
+        mb.add_batch(torch.from_numpy(g[f"mb_batch{step}"]).cuda())
+        assert mb.ptr == int(g[f"mb_ptr{step}"])
+        got = mb.get_vectors().cpu().numpy()
+        np.testing.assert_allclose(got, g[f"mb_bank{step}"], rtol=5e-7, atol=0)
+        assert ((got == 0) == (g[f"mb_bank{step}"] == 0)).all()
+        fbatch = np.concatenate([g[f"fb_batch{step}"], np.zeros((len(g[f"fb_batch{step}"]), 1), np.float32)], 1)
+        fb.add_vectors(torch.from_numpy(fbatch))  # CPU input, like models/swav.py:141
+        assert fb.ptr == int(g[f"fb_ptr{step}"])
+        assert np.array_equal(fb.return_vectors("cuda").cpu().numpy()[:, :3], g[f"fb_bank{step}"])
+
+
+def test_prototypes_and_l2norm(S):
+    g = load_golden("banks")
+    p = S.Prototypes(12, 6).cuda()
+    w = np.zeros((6, 12), np.float32)
+    w[:, :9] = g["proto_weight"]
+    with torch.no_grad():
+        p.embedding.weight.copy_(torch.from_numpy(w))
+    out = p("cuda")
+    assert rel_l2(out.detach().cpu().numpy()[:, :9], g["proto_out"]) < 1e-6
+    x = dev(randn(0, 37, 24))
+    y = S.banks.l2_normalize(x)
+    gy = torch.from_numpy(randn(1, 37, 24)).cuda()
+    y.backward(gy)
+    xr = torch.from_numpy(randn(0, 37, 24)).requires_grad_(True)
+    yr = torch.nn.functional.normalize(xr, dim=-1)
+    yr.backward(gy.cpu())
+    assert rel_l2(y.detach().cpu().numpy(), yr.detach().numpy()) < 1e-6
+    assert rel_l2(x.grad.cpu().numpy(), xr.grad.numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ row-dot
+def test_rowdot_golden(S):
+    g = load_golden("rowdot")
+    o, t = dev(g["o"]), dev(g["t"])
+    loss = S.SimSiamLoss()(o, t)
+    loss.backward()
+    check(loss.item(), [o.grad, t.grad], float(g["ss_loss"]), [g["ss_do"], g["ss_dt"]], "simsiam", 1e-5, 1e-5)
+    o, t = dev(g["o"]), dev(g["t"])
+    loss = S.MSELoss()(o, t)
+    loss.backward()
+    check(loss.item(), [o.grad, t.grad], float(g["mse_loss"]), [g["mse_do"], g["mse_dt"]], "mse", 1e-5, 1e-5)
+
+
+@pytest.mark.parametrize("n,d", [(512, 128), (4096, 1024), (33, 20)])
+def test_rowdot_oracle(S, n, d):
+    o = randn(0, n, d) / np.sqrt(d)
+    t = randn(1, n, d) / np.sqrt(d)
+    a, b = dev(o), dev(t, False)  # BYOL: target has no grad path
+    loss = S.MSELoss()(a, b)
+    loss.backward()
+    ref = O.mse(o, t)
+    check(loss.item(), [a.grad], ref[0], ref[1:2], "mse", 1e-5, 1e-5)
+    a, b = dev(o), dev(t)
+    loss = S.SimSiamLoss()(a, b)
+    loss.backward()
+    ref = O.simsiam(o, t)
+    check(loss.item(), [a.grad, b.grad], ref[0], ref[1:], "simsiam", 1e-4, 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ ReLIC
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_relic_golden(S, tag):
+    g = load_golden("relic")
+    norm, tau, alpha = bool(g[f"{tag}_cfg"][0]), float(g[f"{tag}_cfg"][1]), float(g[f"{tag}_cfg"][2])
+    zi, zj, zo = dev(g[f"{tag}_zi"]), dev(g[f"{tag}_zj"]), dev(g[f"{tag}_zo"])
+    loss = S.RelicLoss(norm, tau, alpha)(zi, zj, zo)
+    loss.backward()
+    check(loss.item(), [zi.grad, zj.grad, zo.grad], float(g[f"{tag}_loss"]),
+          [g[f"{tag}_dzi"], g[f"{tag}_dzj"], g[f"{tag}_dzo"]], f"relic[{tag}]")
+
+
+@pytest.mark.parametrize("n,d,tau", [(512, 128, 1.0), (4096, 128, 1.0), (300, 64, 0.2)])
+def test_relic_oracle(S, n, d, tau):
+    zi, zj, zo = randn(0, n, d), randn(1, n, d), randn(2, n, d)
+    ref = O.relic(zi, zj, zo, True, tau, 0.5)
+    a, b, c = dev(zi), dev(zj), dev(zo)
+    loss = S.RelicLoss(True, tau, 0.5)(a, b, c)
+    loss.backward()
+    check(loss.item(), [a.grad, b.grad, c.grad], ref[0], ref[1:], f"relic n={n}")
+
+
+# ------------------------------------------------------------------------------------------------ Sinkhorn
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_sinkhorn_golden(S, tag):
+    g = load_golden("swav")
+    codes = S.SwavLoss(0.1, 0.05, 3).compute_codes_sinkhorn(dev(g[f"sk_{tag}_scores"], False))
+    assert rel_l2(codes.cpu().numpy(), g[f"sk_{tag}_codes"]) < 1e-4
+
+
+@pytest.mark.parametrize("b,k,iters", [(4096, 3000, 3), (3512, 3000, 3), (257, 5000, 2), (64, 30, 0), (100, 8, 5)])
+def test_sinkhorn_oracle(S, b, k, iters):
+    z = randn(0, b, 128)
+    c = randn(1, k, 128)
+    z /= np.linalg.norm(z, axis=1, keepdims=True)
+    c /= np.linalg.norm(c, axis=1, keepdims=True)
+    scores = (z @ c.T).astype(np.float32)
+    ref = O.sinkhorn(scores, 0.05, iters)
+    codes = S.SwavLoss(0.1, 0.05, iters).compute_codes_sinkhorn(dev(scores, False)).cpu().numpy()
+    assert np.isfinite(codes).all()
+    assert rel_l2(codes, ref) < 1e-4
+    np.testing.assert_allclose(codes.sum(1), 1.0, rtol=1e-4)
+    if iters > 0:  # prototype marginals are uniform up to the last column normalisation
+        assert abs(codes.sum() - b) / b < 1e-4
