@@ -67,32 +67,34 @@ int ssvb_ntxent_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
                     void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * a1/e  Global-batch NT-Xent, row-sharded over ranks (the reference has no
- *     multi-GPU path: semantics = SimclrLoss on the rank-order concatenation of all inputs).
- *     Stage 1 (prep): each rank normalises its n_local rows of both views into its slot of the
- *       gathered bf16 matrix `zhat_all` [2*n_global(+pad) x d_pad] (row a of view i at
- *       rank_row0 + a, view j at n_global + rank_row0 + a) -> caller all-gathers the slots.
- *     Stage 2 (rows_fwd): local rows against all columns -> lse for local rows + local loss sum
- *       (caller all-reduces `loss_sum` and all-gathers `stat_all`).
- *     Stage 3 (rows_bwd): complete gradient of the local rows (no reduce-scatter needed).
- *     Layout helpers below give sizes/offsets so the host side never hard-codes them.
+ * a1/e  Global-batch NT-Xent, row-sharded over `world` ranks (the reference has no
+ *     multi-GPU path: semantics = SimclrLoss on the concatenation of all ranks' inputs, each rank
+ *     receiving the gradient rows of its own inputs).  Every rank holds n_local rows per view.
+ *     The gathered matrices are RANK-MAJOR: global row of (rank r, view v, row i) = r*2L + v*L + i
+ *     (L = n_local), so each rank owns one contiguous slot and a single all-gather fills the rest;
+ *     NT-Xent is invariant to this row permutation (the positive partner is a +- L, same rank).
+ *     Stage 1 (prep):     normalise the local rows of both views into this rank's slot of `zhat_all`
+ *                         (bf16 [mpad x dpad], mpad = ssvb_ntxent_mpad(world*L)) + local positives.
+ *                         -> caller all-gathers the slots (2L*dpad bf16 per rank).
+ *     Stage 2 (rows_fwd): local rows against ALL columns -> log2-domain LSE of the local rows
+ *                         (`stat_local`, [2L]) + local loss sum (caller all-reduces `loss_sum` and
+ *                         divides by 2*world*L; all-gathers stat_local into stat_all [world*2L]).
+ *     Stage 3 (rows_bwd): complete gradient of the local rows; no reduce-scatter of gradients is
+ *                         needed because W_ab = P_ab + P_ba is computable from s_ab, lse_a, lse_b.
  * ------------------------------------------------------------------------------------- */
 int64_t ssvb_ntxent_dpad(int64_t d);                 /* padded feature dim of zhat_all */
-int64_t ssvb_ntxent_mpad(int64_t n_global);          /* padded row count of zhat_all / stat_all */
-size_t ssvb_ntxent_dist_workspace_bytes(int64_t n_global, int64_t n_local, int64_t d);
+int64_t ssvb_ntxent_mpad(int64_t n_global);          /* padded row count of zhat_all (n_global = world*L) */
+size_t ssvb_ntxent_dist_workspace_bytes(int64_t world, int64_t n_local, int64_t d);
 int ssvb_ntxent_dist_prep(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
-                          int64_t ld_zj, int normalize, int64_t n_global, int64_t rank_row0,
-                          void* zhat_all /* bf16 [mpad x dpad] */, float* inv_norm_local /* [2*n_local] */,
-                          void* stream);
-/* stat_local: [2*n_local] per-row log2-domain LSE of the local rows (view i rows then view j rows);
- * loss_sum: device scalar, sum over local rows of (lse - pos) (divide by 2*n_global after all-reduce). */
-int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t n_global, int64_t n_local, int64_t rank_row0,
-                              int64_t d, int normalize, float temperature, float* stat_local,
+                          int64_t ld_zj, int normalize, int64_t world, int64_t rank,
+                          void* zhat_all /* bf16 [mpad x dpad] */, float* inv_norm_local /* [2L] */,
+                          float* pos_local /* [2L] */, void* stream);
+int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
+                              int normalize, float temperature, const float* pos_local, float* stat_local,
                               float* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
-/* stat_all: [mpad] log2-domain LSE of ALL rows in zhat_all row order (padding entries ignored). */
 int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
-                              int64_t ld_zj, int normalize, float temperature, int64_t n_global,
-                              int64_t rank_row0, const void* zhat_all, const float* stat_all,
+                              int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
+                              const void* zhat_all, const float* stat_all /* [world*2L] */,
                               const float* inv_norm_local, const float* grad_out, float* dzi, float* dzj,
                               int64_t ld_dzi, int64_t ld_dzj, void* workspace, size_t workspace_bytes,
                               void* stream);
@@ -204,6 +206,17 @@ int ssvb_l2norm_fwd(const float* x, int64_t n, int64_t d, int64_t ld_x, float* y
                     float* inv_norm /* [n] */, void* stream);
 int ssvb_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int64_t n, int64_t d, int64_t ld_dy,
                     int64_t ld_y, float* dx, int64_t ld_dx, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py only; OFF by default, not on the loss path).
+ *   ssvb_launch_count: number of kernels this library has launched (reset != 0 zeroes it).
+ *   ssvb_profile_enable(1): record a CUDA-event pair around every tensor-core kernel launch, on
+ *   the stream it is launched on; ssvb_profile_summary(kind, &ms, &n) sums them
+ *   (kind 0 = sim_fwd_kernel, 1 = sim_bwd_kernel, 2 = gemm kernels).
+ * ------------------------------------------------------------------------------------- */
+long long ssvb_launch_count(int reset);
+int ssvb_profile_enable(int on);
+int ssvb_profile_summary(int kind, double* total_ms, long long* count);
 
 #ifdef __cplusplus
 }

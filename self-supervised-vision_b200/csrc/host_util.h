@@ -4,10 +4,18 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/ssv_b200.h"
 
 namespace ssvb {
+
+// profiling hooks (defined in core.cu; off by default, used by bench.py only)
+enum ProfKind { PROF_SIM_FWD = 0, PROF_SIM_BWD = 1, PROF_GEMM = 2, PROF_NKINDS = 3 };
+void count_launch();
+int prof_begin(int kind, cudaStream_t s);  // returns a record slot or -1
+void prof_end(int slot, cudaStream_t s);
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
@@ -56,6 +64,18 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+    // the driver call needs a context bound to THIS thread; autograd's backward thread may not have touched the
+    // runtime yet.  cudaFree(0) binds the primary context of the current device, then retry once.
+    cudaFree(nullptr);
+    r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS && getenv("SSVB_DEBUG"))
+    fprintf(stderr, "[ssv_b200] cuTensorMapEncodeTiled -> %d (ptr=%p rows=%lld cols=%lld ld=%lld box_rows=%d)\n",
+            static_cast<int>(r), ptr, static_cast<long long>(rows), static_cast<long long>(cols),
+            static_cast<long long>(ld), box_rows);
   return r == CUDA_SUCCESS ? SSVB_OK : SSVB_ERR_DRIVER;
 }
 
@@ -89,6 +109,10 @@ inline int num_sms() {
     int _rc = (expr);           \
     if (_rc != SSVB_OK) return _rc; \
   } while (0)
-#define SSVB_LAUNCH_CHECK() SSVB_CUDA(cudaGetLastError())
+#define SSVB_LAUNCH_CHECK()          \
+  do {                               \
+    ::ssvb::count_launch();          \
+    SSVB_CUDA(cudaGetLastError());   \
+  } while (0)
 
 }  // namespace ssvb

@@ -86,7 +86,7 @@ WsLayout ws_layout(void* base, int64_t local_rows, int64_t row_blocks, int64_t c
 
 // ---- gradient finish: partner term, 1/(M tau) * grad_out, normalise-backward --------------------------
 __global__ void ntx_grad_finish_kernel(const float* __restrict__ zi, const float* __restrict__ zj, int64_t ldi,
-                                       int64_t ldj, int n_view, int d, int n_glob, int row0,
+                                       int64_t ldj, int n_view, int d, int row0,
                                        const float* __restrict__ dacc, int ld_dacc,
                                        const __nv_bfloat16* __restrict__ zhat, int dpad,
                                        const float* __restrict__ inv_norm, int normalize, float inv_m_tau,
@@ -96,8 +96,8 @@ __global__ void ntx_grad_finish_kernel(const float* __restrict__ zi, const float
   if (lrow >= 2 * n_view) return;
   const int view = lrow >= n_view;
   const int r = lrow - view * n_view;
-  const int a_glob = view * n_glob + row0 + r;
-  const int partner = view ? a_glob - n_glob : a_glob + n_glob;
+  const int a_glob = row0 + lrow;  // rank-major layout: [rank][view][row]
+  const int partner = view ? a_glob - n_view : a_glob + n_view;
   const float* z = view ? zj + static_cast<int64_t>(r) * ldj : zi + static_cast<int64_t>(r) * ldi;
   float* out = view ? dzj + static_cast<int64_t>(r) * ld_dzj : dzi + static_cast<int64_t>(r) * ld_dzi;
   const float scale = inv_m_tau * __ldg(grad_out);
@@ -244,7 +244,7 @@ int ssvb_ntxent_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   {
     const int wpb = 8;
     ntx_grad_finish_kernel<<<static_cast<unsigned>(ceil_div(pl.m, wpb)), wpb * 32, 0, s>>>(
-        zi, zj, ld_zi, ld_zj, static_cast<int>(n), static_cast<int>(d), static_cast<int>(n), 0, ws.dacc,
+        zi, zj, ld_zi, ld_zj, static_cast<int>(n), static_cast<int>(d), 0, ws.dacc,
         static_cast<int>(pl.dpad), sv.zhat, static_cast<int>(pl.dpad), sv.inv_norm, normalize,
         1.f / (static_cast<float>(pl.m) * temperature), grad_out, dzi, dzj, ld_dzi, ld_dzj);
     SSVB_LAUNCH_CHECK();
@@ -253,74 +253,60 @@ int ssvb_ntxent_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
 }
 
 // ------------------------------------------------------------------------------------ multi-GPU pieces
-size_t ssvb_ntxent_dist_workspace_bytes(int64_t n_global, int64_t n_local, int64_t d) {
-  if (n_local <= 0 || d <= 0) return 0;
-  return ws_layout(nullptr, 2 * n_local, 2 * ceil_div(n_local, 128), 2 * n_global, sim_dpad(d)).bytes;
+// Gathered layout is RANK-MAJOR: global row of (rank r, view v, local row i) = r*2L + v*L + i with L = n_local,
+// so every rank owns ONE contiguous slot of zhat_all / stat_all (a single all-gather each) and the positive
+// partner of a row is always on the same rank (a +- L).  NT-Xent is invariant to this row permutation.
+size_t ssvb_ntxent_dist_workspace_bytes(int64_t world, int64_t n_local, int64_t d) {
+  if (world <= 0 || n_local <= 0 || d <= 0) return 0;
+  return ws_layout(nullptr, 2 * n_local, ceil_div(2 * n_local, 128), 2 * n_local * world, sim_dpad(d)).bytes;
 }
 
+namespace {
+int dist_check(int64_t world, int64_t rank, int64_t n_local) {
+  if (world <= 0 || rank < 0 || rank >= world || n_local <= 0) return SSVB_ERR_INVALID;
+  return SSVB_OK;
+}
+}  // namespace
+
 int ssvb_ntxent_dist_prep(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
-                          int64_t ld_zj, int normalize, int64_t n_global, int64_t rank_row0, void* zhat_all,
-                          float* inv_norm_local, void* stream) {
+                          int64_t ld_zj, int normalize, int64_t world, int64_t rank, void* zhat_all,
+                          float* inv_norm_local, float* pos_local, void* stream) {
   SSVB_TRY(check_device_sm100());
+  SSVB_TRY(dist_check(world, rank, n_local));
   NtxPlan pl;
-  SSVB_TRY(make_plan(pl, n_global, d, normalize, 1.f));
+  SSVB_TRY(make_plan(pl, n_local * world, d, normalize, 1.f));
   SSVB_TRY(check_rows(zi, ld_zi));
   SSVB_TRY(check_rows(zj, ld_zj));
-  if (!zhat_all || !inv_norm_local || n_local <= 0 || rank_row0 < 0 || rank_row0 + n_local > n_global)
-    return SSVB_ERR_INVALID;
+  if (!zhat_all || !inv_norm_local || !pos_local) return SSVB_ERR_INVALID;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* zh = static_cast<__nv_bfloat16*>(zhat_all);
   if (pl.mpad > pl.m)
     SSVB_CUDA(cudaMemsetAsync(zh + pl.m * pl.dpad, 0, (pl.mpad - pl.m) * pl.dpad * sizeof(__nv_bfloat16), s));
+  const int64_t row0 = rank * 2 * n_local;
   const int wpb = 8;
   pair_prep_kernel<<<static_cast<unsigned>(ceil_div(n_local, wpb)), wpb * 32, 0, s>>>(
-      zi, zj, static_cast<int>(n_local), static_cast<int>(d), ld_zi, ld_zj, normalize, zh + rank_row0 * pl.dpad,
-      zh + (n_global + rank_row0) * pl.dpad, static_cast<int>(pl.dpad), inv_norm_local, inv_norm_local + n_local,
-      nullptr, nullptr);
+      zi, zj, static_cast<int>(n_local), static_cast<int>(d), ld_zi, ld_zj, normalize, zh + row0 * pl.dpad,
+      zh + (row0 + n_local) * pl.dpad, static_cast<int>(pl.dpad), inv_norm_local, inv_norm_local + n_local,
+      pos_local, pos_local + n_local);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
 
-namespace {
-// positive logit of every local row from the gathered bf16 matrix (the partner row may live on another rank)
-__global__ void dist_pos_kernel(const __nv_bfloat16* __restrict__ zhat, int dpad, int n_glob, int n_local, int row0,
-                                float* __restrict__ pos) {
-  const int lrow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (lrow >= 2 * n_local) return;
-  const int view = lrow >= n_local;
-  const int a = view * n_glob + row0 + (lrow - view * n_local);
-  const int b = view ? a - n_glob : a + n_glob;
-  float dot = 0.f;
-  for (int k = lane * 2; k < dpad; k += 64) {
-    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zhat + static_cast<int64_t>(a) * dpad + k));
-    const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zhat + static_cast<int64_t>(b) * dpad + k));
-    dot += x.x * y.x + x.y * y.y;
-  }
-  dot = warp_sum(dot);
-  if (lane == 0) pos[lrow] = dot;
-}
-}  // namespace
-
-int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t n_global, int64_t n_local, int64_t rank_row0,
-                              int64_t d, int normalize, float temperature, float* stat_local, float* loss_sum,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
+                              int normalize, float temperature, const float* pos_local, float* stat_local,
+                              float* loss_sum, void* workspace, size_t workspace_bytes, void* stream) {
   SSVB_TRY(check_device_sm100());
+  SSVB_TRY(dist_check(world, rank, n_local));
   NtxPlan pl;
-  SSVB_TRY(make_plan(pl, n_global, d, normalize, temperature));
-  if (!zhat_all || !stat_local || !loss_sum || !workspace || n_local <= 0 || rank_row0 < 0 ||
-      rank_row0 + n_local > n_global)
-    return SSVB_ERR_INVALID;
-  if (workspace_bytes < ssvb_ntxent_dist_workspace_bytes(n_global, n_local, d)) return SSVB_ERR_WORKSPACE;
+  SSVB_TRY(make_plan(pl, n_local * world, d, normalize, temperature));
+  if (!zhat_all || !pos_local || !stat_local || !loss_sum || !workspace) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_ntxent_dist_workspace_bytes(world, n_local, d)) return SSVB_ERR_WORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  WsLayout ws = ws_layout(workspace, 2 * n_local, 2 * ceil_div(n_local, 128), pl.m, pl.dpad);
   const int64_t lr = 2 * n_local;
+  WsLayout ws = ws_layout(workspace, lr, ceil_div(lr, 128), pl.m, pl.dpad);
   SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
-  dist_pos_kernel<<<static_cast<unsigned>(ceil_div(lr, 8)), 256, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(zhat_all), static_cast<int>(pl.dpad), static_cast<int>(n_global),
-      static_cast<int>(n_local), static_cast<int>(rank_row0), ws.pos);
-  SSVB_LAUNCH_CHECK();
   SimParams p;
-  fill_sim_params_rows(p, pl, 2, n_local, rank_row0, n_global + rank_row0);
+  fill_sim_params_rows(p, pl, 1, lr, rank * lr, 0);
   plan_chunks(p, 256, 4);
   p.part_m = ws.part_m;
   p.part_l = ws.part_l;
@@ -331,12 +317,12 @@ int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t n_global, int64_t n_
   // re-derived from it in rows_bwd.
   if (pl.mode == SIM_NTX_FIXED)
     lse_finalize_kernel<SIM_NTX_FIXED><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 2 * p.nchunks, p.part_stride,
-                                                          static_cast<int>(lr), ws.pos, pl.c, pl.shift,
+                                                          static_cast<int>(lr), pos_local, pl.c, pl.shift,
                                                           ws.dacc /*scratch*/, stat_local, ws.block_sums, ws.counter,
                                                           1.f, loss_sum);
   else
     lse_finalize_kernel<SIM_NTX_ONLINE><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 2 * p.nchunks, p.part_stride,
-                                                           static_cast<int>(lr), ws.pos, pl.c, pl.shift,
+                                                           static_cast<int>(lr), pos_local, pl.c, pl.shift,
                                                            ws.dacc /*scratch*/, stat_local, ws.block_sums,
                                                            ws.counter, 1.f, loss_sum);
   SSVB_LAUNCH_CHECK();
@@ -357,32 +343,30 @@ __global__ void dist_stat_kernel(const float* __restrict__ lse2, float* __restri
 }  // namespace
 
 int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
-                              int64_t ld_zj, int normalize, float temperature, int64_t n_global,
-                              int64_t rank_row0, const void* zhat_all, const float* stat_all,
-                              const float* inv_norm_local, const float* grad_out, float* dzi, float* dzj,
-                              int64_t ld_dzi, int64_t ld_dzj, void* workspace, size_t workspace_bytes,
-                              void* stream) {
+                              int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
+                              const void* zhat_all, const float* stat_all, const float* inv_norm_local,
+                              const float* grad_out, float* dzi, float* dzj, int64_t ld_dzi, int64_t ld_dzj,
+                              void* workspace, size_t workspace_bytes, void* stream) {
   SSVB_TRY(check_device_sm100());
+  SSVB_TRY(dist_check(world, rank, n_local));
   NtxPlan pl;
-  SSVB_TRY(make_plan(pl, n_global, d, normalize, temperature));
+  SSVB_TRY(make_plan(pl, n_local * world, d, normalize, temperature));
   SSVB_TRY(check_rows(zi, ld_zi));
   SSVB_TRY(check_rows(zj, ld_zj));
   SSVB_TRY(check_rows(dzi, ld_dzi));
   SSVB_TRY(check_rows(dzj, ld_dzj));
-  if (!zhat_all || !stat_all || !inv_norm_local || !grad_out || !workspace || n_local <= 0 || rank_row0 < 0 ||
-      rank_row0 + n_local > n_global)
-    return SSVB_ERR_INVALID;
-  if (workspace_bytes < ssvb_ntxent_dist_workspace_bytes(n_global, n_local, d)) return SSVB_ERR_WORKSPACE;
+  if (!zhat_all || !stat_all || !inv_norm_local || !grad_out || !workspace) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_ntxent_dist_workspace_bytes(world, n_local, d)) return SSVB_ERR_WORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  WsLayout ws = ws_layout(workspace, 2 * n_local, 2 * ceil_div(n_local, 128), pl.m, pl.dpad);
   const int64_t lr = 2 * n_local;
+  WsLayout ws = ws_layout(workspace, lr, ceil_div(lr, 128), pl.m, pl.dpad);
   // column statistics for all M rows live in the (otherwise unused here) partial buffer
   float* stat = ws.part_m;
   dist_stat_kernel<<<static_cast<unsigned>(ceil_div(pl.mpad, 256)), 256, 0, s>>>(
       stat_all, stat, static_cast<int>(pl.m), static_cast<int>(pl.mpad), pl.mode == SIM_NTX_FIXED, pl.shift);
   SSVB_LAUNCH_CHECK();
   SimParams p;
-  fill_sim_params_rows(p, pl, 2, n_local, rank_row0, n_global + rank_row0);
+  fill_sim_params_rows(p, pl, 1, lr, rank * lr, 0);
   plan_chunks(p, 128, 8);
   p.rowstat = stat;
   p.colstat = stat;
@@ -393,10 +377,9 @@ int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local,
   SSVB_TRY(launch_sim_bwd(pl.mode, zhat_all, pl.mpad, zhat_all, pl.mpad, pl.dpad, p, s));
   const int wpb = 8;
   ntx_grad_finish_kernel<<<static_cast<unsigned>(ceil_div(lr, wpb)), wpb * 32, 0, s>>>(
-      zi, zj, ld_zi, ld_zj, static_cast<int>(n_local), static_cast<int>(d), static_cast<int>(n_global),
-      static_cast<int>(rank_row0), ws.dacc, static_cast<int>(pl.dpad), static_cast<const __nv_bfloat16*>(zhat_all),
-      static_cast<int>(pl.dpad), inv_norm_local, normalize,
-      1.f / (static_cast<float>(pl.m) * temperature), grad_out, dzi, dzj, ld_dzi, ld_dzj);
+      zi, zj, ld_zi, ld_zj, static_cast<int>(n_local), static_cast<int>(d), static_cast<int>(rank * lr), ws.dacc,
+      static_cast<int>(pl.dpad), static_cast<const __nv_bfloat16*>(zhat_all), static_cast<int>(pl.dpad),
+      inv_norm_local, normalize, 1.f / (static_cast<float>(pl.m) * temperature), grad_out, dzi, dzj, ld_dzi, ld_dzj);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }

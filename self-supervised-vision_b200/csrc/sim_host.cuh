@@ -29,7 +29,9 @@ int launch_sim_fwd_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const SimPa
   SSVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int nunits = p.row_blocks * p.nchunks;
   const int grid = nunits < num_sms() ? nunits : num_sms();
+  const int slot = prof_begin(PROF_SIM_FWD, s);
   kern<<<grid, 320, smem, s>>>(tmA, tmB, p);
+  prof_end(slot, s);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
@@ -40,7 +42,9 @@ int launch_sim_bwd_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const SimPa
   SSVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int nunits = p.row_blocks * p.nchunks;
   const int grid = nunits < num_sms() ? nunits : num_sms();
+  const int slot = prof_begin(PROF_SIM_BWD, s);
   kern<<<grid, 320, smem, s>>>(tmA, tmB, p);
+  prof_end(slot, s);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }

@@ -18,7 +18,7 @@ HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "ssv_b
 
 _CTYPE = {
     "int": c_int, "float": c_float, "int64_t": c_int64, "size_t": c_size_t,
-    "const char*": c_char_p, "void": None,
+    "const char*": c_char_p, "void": None, "long long": ctypes.c_longlong, "double": ctypes.c_double,
 }
 
 

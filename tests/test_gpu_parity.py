@@ -214,13 +214,14 @@ def test_ring_buffers_golden(S):
 
 def test_prototypes_and_l2norm(S):
     g = load_golden("banks")
-    p = S.Prototypes(12, 6).cuda()
-    w = np.zeros((6, 12), np.float32)
-    w[:, :9] = g["proto_weight"]
+    pw = g["proto_weight"]                      # RefPrototypes(hidden_dim=6, prototype_size=9): weight [9 x 6]
+    p = S.Prototypes(8, pw.shape[0]).cuda()     # feature dim padded 6 -> 8 (rows must be 16-byte multiples)
+    w = np.zeros((pw.shape[0], 8), np.float32)
+    w[:, :pw.shape[1]] = pw
     with torch.no_grad():
         p.embedding.weight.copy_(torch.from_numpy(w))
     out = p("cuda")
-    assert rel_l2(out.detach().cpu().numpy()[:, :9], g["proto_out"]) < 1e-6
+    assert rel_l2(out.detach().cpu().numpy()[:, :pw.shape[1]], g["proto_out"]) < 1e-6
     x = dev(randn(0, 37, 24))
     y = S.banks.l2_normalize(x)
     gy = torch.from_numpy(randn(1, 37, 24)).cuda()
