@@ -1,0 +1,333 @@
+// Barlow Twins loss, forward + backward — replaces BarlowLoss.forward (reference utils/losses.py:127-142,
+// call site models/barlow.py:90).
+//
+//   x~ = (x - mean_0) / std_0 (UNBIASED std, :136-137);  C = Xi~^T Xj~ / N (:138)
+//   loss = sum_a (C_aa - 1)^2 + lambda * sum_{a != b} C_ab^2 (:139-142)
+//   dC_aa = 2 (C_aa - 1), dC_ab = 2 lambda C_ab;  dXi~ = Xj~ dC^T / N;  dXj~ = Xi~ dC / N
+//   dx = (dx~ - mean_0(dx~) - x~ * sum_0(dx~ . x~) / (N-1)) / std        [+ row-normalise backward if normalize]
+//
+// Kernels: column statistics (shifted single pass) -> standardise to bf16 -> tcgen05 GEMM with both operands
+// consumed MN-major in place (no transposed copies) and a fused epilogue that reduces the loss and emits dC in
+// bf16 (the D x D fp32 matrix never reaches HBM) -> two tcgen05 GEMMs for the backward -> column reductions +
+// standardise-backward.
+#include "gemm_host.cuh"
+
+using namespace ssvb;
+
+namespace {
+
+constexpr int kColsPerBlock = 32;
+constexpr int kRowSplit = 8;  // row stripes per column group (fills the SMs at D = 4096..8192)
+constexpr int kMaxGemmCtas = 160;
+
+struct BarlowSaved {
+  __nv_bfloat16 *xi, *xj;  // standardised operands [n x d]
+  __nv_bfloat16* dC;       // [d x d]
+  float *mean_i, *rstd_i, *mean_j, *rstd_j;  // [d]
+  float *inv_i, *inv_j;                      // [n] row 1/norm (normalize=1)
+  size_t bytes;
+};
+BarlowSaved barlow_saved(void* base, int64_t n, int64_t d) {
+  Carver c(base);
+  BarlowSaved s;
+  s.xi = c.take<__nv_bfloat16>(n * d);
+  s.xj = c.take<__nv_bfloat16>(n * d);
+  s.dC = c.take<__nv_bfloat16>(d * d);
+  s.mean_i = c.take<float>(d);
+  s.rstd_i = c.take<float>(d);
+  s.mean_j = c.take<float>(d);
+  s.rstd_j = c.take<float>(d);
+  s.inv_i = c.take<float>(n);
+  s.inv_j = c.take<float>(n);
+  s.bytes = c.used();
+  return s;
+}
+struct BarlowWs {
+  float* colpart;        // [2 views][kRowSplit][2][d]
+  float* loss_partials;  // [kMaxGemmCtas]
+  float *dti, *dtj;      // backward: [n x d] fp32 each
+  float* colred;         // [2 views][2][d]  (mean of dT, sum(dT x~)/(n-1))
+  size_t bytes;
+};
+BarlowWs barlow_ws(void* base, int64_t n, int64_t d) {
+  Carver c(base);
+  BarlowWs w;
+  w.colpart = c.take<float>(2 * kRowSplit * 2 * d);
+  w.loss_partials = c.take<float>(kMaxGemmCtas);
+  w.dti = c.take<float>(n * d);
+  w.dtj = c.take<float>(n * d);
+  w.colred = c.take<float>(4 * d);
+  w.bytes = c.used();
+  return w;
+}
+
+// row 1/max(||x||, eps): one warp per row
+__global__ void row_invnorm_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld, float* __restrict__ inv) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ld);
+  float s = 0.f;
+  for (int c = lane; c < d / 4; c += 32) {
+    const float4 v = __ldg(xr + c);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  s = warp_sum(s);
+  if (lane == 0) inv[row] = 1.f / fmaxf(sqrtf(s), 1e-12f);
+}
+
+// Column partial sums over a row stripe.  MODE 0 (stats): f = v - v0, g = (v - v0)^2 with v0 = value of row 0
+// (shift against cancellation).  MODE 1 (backward): f = dT, g = dT * x~.
+// block (32, 8): threadIdx.x <-> column (coalesced 128-byte row segments), threadIdx.y <-> row phase.
+template <int MODE>
+__global__ void col_partials_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row,
+                                    const float* __restrict__ dt, int64_t lddt, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, int64_t n, int d, float* __restrict__ part) {
+  const int col = blockIdx.x * kColsPerBlock + threadIdx.x;
+  const int stripe = blockIdx.y;
+  const int64_t rows_per = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = stripe * rows_per, r1 = min(n, r0 + rows_per);
+  float s1 = 0.f, s2 = 0.f;
+  if (col < d) {
+    float v0 = 0.f, mu = 0.f, rs = 0.f;
+    if (MODE == 0) v0 = x[col] * (inv_row ? inv_row[0] : 1.f);
+    if (MODE == 1) { mu = mean[col]; rs = rstd[col]; }
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      const float v = x[r * ldx + col] * (inv_row ? inv_row[r] : 1.f);
+      if (MODE == 0) {
+        const float t = v - v0;
+        s1 += t;
+        s2 = fmaf(t, t, s2);
+      } else {
+        const float g = dt[r * lddt + col];
+        s1 += g;
+        s2 = fmaf(g, (v - mu) * rs, s2);
+      }
+    }
+  }
+  __shared__ float sh1[8][kColsPerBlock + 1], sh2[8][kColsPerBlock + 1];
+  sh1[threadIdx.y][threadIdx.x] = s1;
+  sh2[threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < d) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += sh1[i][threadIdx.x]; b += sh2[i][threadIdx.x]; }
+    part[(static_cast<int64_t>(stripe) * 2 + 0) * d + col] = a;
+    part[(static_cast<int64_t>(stripe) * 2 + 1) * d + col] = b;
+  }
+}
+
+// MODE 0: mean, 1/std (unbiased)   MODE 1: mean_0(dT), sum_0(dT x~)/(n-1)
+template <int MODE>
+__global__ void col_finalize_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ x,
+                                    const float* __restrict__ inv_row, int64_t n, int d, float* __restrict__ out0,
+                                    float* __restrict__ out1) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= d) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < nsplit; ++i) {
+    s1 += part[(static_cast<int64_t>(i) * 2 + 0) * d + col];
+    s2 += part[(static_cast<int64_t>(i) * 2 + 1) * d + col];
+  }
+  const float fn = static_cast<float>(n);
+  if (MODE == 0) {
+    const float v0 = x[col] * (inv_row ? inv_row[0] : 1.f);
+    const float var = (s2 - s1 * s1 / fn) / (fn - 1.f);
+    out0[col] = v0 + s1 / fn;
+    out1[col] = rsqrtf(var);
+  } else {
+    out0[col] = s1 / fn;
+    out1[col] = s2 / (fn - 1.f);
+  }
+}
+
+// x~ = (x * inv_row - mean) * rstd  -> bf16 [n x d]
+__global__ void standardize_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row,
+                                   const float* __restrict__ mean, const float* __restrict__ rstd, int64_t n, int d4,
+                                   __nv_bfloat16* __restrict__ out, int64_t ldo) {
+  const int64_t total = n * d4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / d4;
+    const int c = static_cast<int>(i - r * d4);
+    const float sc = inv_row ? inv_row[r] : 1.f;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ldx) + c);
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + c);
+    const float4 rs = __ldg(reinterpret_cast<const float4*>(rstd) + c);
+    __nv_bfloat162 lo = __floats2bfloat162_rn((v.x * sc - mu.x) * rs.x, (v.y * sc - mu.y) * rs.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn((v.z * sc - mu.z) * rs.z, (v.w * sc - mu.w) * rs.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + r * ldo + 4 * c) = pk;
+  }
+}
+
+// one block per row: dx^ = (dT - m1 - x~ m2) * rstd * grad_out, then (optionally) the row-normalise backward
+__global__ void barlow_finish_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const float* __restrict__ dt, int64_t lddt, const float* __restrict__ m1,
+                                     const float* __restrict__ m2, int d, const float* __restrict__ grad_out,
+                                     float* __restrict__ dx, int64_t lddx) {
+  const int64_t r = blockIdx.x;
+  const float go = __ldg(grad_out);
+  const float sc = inv_row ? inv_row[r] : 1.f;
+  __shared__ float red[32];
+  float dot = 0.f;
+  if (inv_row) {
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      const float xh = x[r * ldx + c] * sc;
+      const float rs = rstd[c];
+      const float g = (dt[r * lddt + c] - m1[c] - (xh - mean[c]) * rs * m2[c]) * rs * go;
+      dot = fmaf(g, xh, dot);
+    }
+    dot = warp_sum(dot);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    float t = (threadIdx.x & 31) < (blockDim.x >> 5) ? red[threadIdx.x & 31] : 0.f;
+    dot = warp_sum(t);
+  }
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float xh = x[r * ldx + c] * sc;
+    const float rs = rstd[c];
+    float g = (dt[r * lddt + c] - m1[c] - (xh - mean[c]) * rs * m2[c]) * rs * go;
+    if (inv_row) g = (g - dot * xh) * sc;
+    dx[r * lddx + c] = g;
+  }
+}
+
+int check_rows(const void* p, int64_t ld) {
+  if (!p) return SSVB_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) || (ld & 3)) return SSVB_ERR_ALIGNMENT;
+  return SSVB_OK;
+}
+int check_shape(int64_t n, int64_t d) {
+  if (n < 2 || d <= 0) return SSVB_ERR_INVALID;
+  if (d % 8) return SSVB_ERR_ALIGNMENT;  // bf16 rows of x~ [n x d] and dC [d x d] must be 16-byte multiples
+  if (n > (1 << 30) || d > (1 << 20)) return SSVB_ERR_UNSUPPORTED;
+  return SSVB_OK;
+}
+
+int stats_and_standardize(const float* x, int64_t ld, int normalize, int64_t n, int64_t d, float* inv_row, float* mean,
+                          float* rstd, __nv_bfloat16* xt, float* colpart, cudaStream_t s) {
+  const float* inv = nullptr;
+  if (normalize) {
+    row_invnorm_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(x, n, static_cast<int>(d), ld, inv_row);
+    SSVB_LAUNCH_CHECK();
+    inv = inv_row;
+  }
+  dim3 grid(static_cast<unsigned>(ceil_div(d, kColsPerBlock)), kRowSplit), block(32, 8);
+  col_partials_kernel<0><<<grid, block, 0, s>>>(x, ld, inv, nullptr, 0, nullptr, nullptr, n, static_cast<int>(d), colpart);
+  SSVB_LAUNCH_CHECK();
+  col_finalize_kernel<0><<<static_cast<unsigned>(ceil_div(d, 256)), 256, 0, s>>>(colpart, kRowSplit, x, inv, n,
+                                                                                 static_cast<int>(d), mean, rstd);
+  SSVB_LAUNCH_CHECK();
+  const int64_t total = n * (d / 4);
+  int64_t g = ceil_div(total, 256 * 4);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  standardize_kernel<<<static_cast<unsigned>(g), 256, 0, s>>>(x, ld, inv, mean, rstd, n, static_cast<int>(d / 4), xt, d);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t ssvb_barlow_saved_bytes(int64_t n, int64_t d) {
+  if (n <= 0 || d <= 0) return 0;
+  return barlow_saved(nullptr, n, d).bytes;
+}
+size_t ssvb_barlow_workspace_bytes(int64_t n, int64_t d) {
+  if (n <= 0 || d <= 0) return 0;
+  return barlow_ws(nullptr, n, d).bytes;
+}
+
+int ssvb_barlow_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                    int normalize, float lambda, float* loss, void* saved, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(check_shape(n, d));
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  if (!loss || !saved || !workspace) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_barlow_workspace_bytes(n, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BarlowSaved sv = barlow_saved(saved, n, d);
+  BarlowWs ws = barlow_ws(workspace, n, d);
+  SSVB_TRY(stats_and_standardize(zi, ld_zi, normalize, n, d, sv.inv_i, sv.mean_i, sv.rstd_i, sv.xi, ws.colpart, s));
+  SSVB_TRY(stats_and_standardize(zj, ld_zj, normalize, n, d, sv.inv_j, sv.mean_j, sv.rstd_j, sv.xj,
+                                 ws.colpart + kRowSplit * 2 * d, s));
+  // C = Xi~^T Xj~ / n : contraction over the batch axis, both operands MN-major in place
+  GemmParams p{};
+  p.M = static_cast<int>(d);
+  p.N = static_cast<int>(d);
+  p.K = static_cast<int>(n);
+  p.alpha = 1.f / static_cast<float>(n);
+  p.lambda = lambda;
+  p.dC = sv.dC;
+  p.ld_dc = d;
+  p.loss_partials = ws.loss_partials;
+  SSVB_CUDA(cudaMemsetAsync(ws.loss_partials, 0, kMaxGemmCtas * sizeof(float), s));
+  SSVB_TRY(launch_gemm({sv.xi, d, true}, {sv.xj, d, true}, p, 256, EPI_BARLOW, kMaxGemmCtas, s));
+  sum_partials_kernel<<<1, 256, 0, s>>>(ws.loss_partials, kMaxGemmCtas, 1.f, loss);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_barlow_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                    int normalize, float lambda, const float* grad_out, const void* saved, float* dzi, float* dzj,
+                    int64_t ld_dzi, int64_t ld_dzj, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)lambda;
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(check_shape(n, d));
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  SSVB_TRY(check_rows(dzi, ld_dzi));
+  SSVB_TRY(check_rows(dzj, ld_dzj));
+  if (!grad_out || !saved || !workspace) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_barlow_workspace_bytes(n, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BarlowSaved sv = barlow_saved(const_cast<void*>(saved), n, d);
+  BarlowWs ws = barlow_ws(workspace, n, d);
+
+  GemmParams p{};
+  p.M = static_cast<int>(n);
+  p.N = static_cast<int>(d);
+  p.K = static_cast<int>(d);
+  p.alpha = 1.f / static_cast<float>(n);
+  p.ldc = d;
+  // dTi[n, a] = sum_b Xj~[n, b] dC[a, b]          (A K-major, B = dC rows K-major)
+  p.out = ws.dti;
+  SSVB_TRY(launch_gemm({sv.xj, d, false}, {sv.dC, d, false}, p, 256, EPI_STORE_F32, 0, s));
+  // dTj[n, b] = sum_a Xi~[n, a] dC[a, b]          (A K-major, B = dC consumed MN-major)
+  p.out = ws.dtj;
+  SSVB_TRY(launch_gemm({sv.xi, d, false}, {sv.dC, d, true}, p, 256, EPI_STORE_F32, 0, s));
+
+  dim3 grid(static_cast<unsigned>(ceil_div(d, kColsPerBlock)), kRowSplit), block(32, 8);
+  const float* inv_i = normalize ? sv.inv_i : nullptr;
+  const float* inv_j = normalize ? sv.inv_j : nullptr;
+  float* part_i = ws.colpart;
+  float* part_j = ws.colpart + kRowSplit * 2 * d;
+  col_partials_kernel<1><<<grid, block, 0, s>>>(zi, ld_zi, inv_i, ws.dti, d, sv.mean_i, sv.rstd_i, n, static_cast<int>(d), part_i);
+  SSVB_LAUNCH_CHECK();
+  col_partials_kernel<1><<<grid, block, 0, s>>>(zj, ld_zj, inv_j, ws.dtj, d, sv.mean_j, sv.rstd_j, n, static_cast<int>(d), part_j);
+  SSVB_LAUNCH_CHECK();
+  const unsigned fgrid = static_cast<unsigned>(ceil_div(d, 256));
+  col_finalize_kernel<1><<<fgrid, 256, 0, s>>>(part_i, kRowSplit, nullptr, nullptr, n, static_cast<int>(d), ws.colred, ws.colred + d);
+  SSVB_LAUNCH_CHECK();
+  col_finalize_kernel<1><<<fgrid, 256, 0, s>>>(part_j, kRowSplit, nullptr, nullptr, n, static_cast<int>(d), ws.colred + 2 * d, ws.colred + 3 * d);
+  SSVB_LAUNCH_CHECK();
+  barlow_finish_kernel<<<static_cast<unsigned>(n), 256, 0, s>>>(zi, ld_zi, inv_i, sv.mean_i, sv.rstd_i, ws.dti, d, ws.colred,
+                                                              ws.colred + d, static_cast<int>(d), grad_out, dzi, ld_dzi);
+  SSVB_LAUNCH_CHECK();
+  barlow_finish_kernel<<<static_cast<unsigned>(n), 256, 0, s>>>(zj, ld_zj, inv_j, sv.mean_j, sv.rstd_j, ws.dtj, d,
+                                                              ws.colred + 2 * d, ws.colred + 3 * d, static_cast<int>(d),
+                                                              grad_out, dzj, ld_dzj);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,288 @@
+// SwAV loss, forward + backward — replaces SwavLoss.forward (reference utils/losses.py:226-235, call site
+// models/swav.py:140).
+//
+//   rows of both views = live batch rows followed by the bank rows (:227-229)
+//   scores_v = z_v C^T (:231);  q_v = sinkhorn(scores_v) (no grad, :232);  p_v = log_softmax(scores_v / T) (:233)
+//   loss = -1/2 mean_rows( sum_k q_1 p_2 + sum_k q_2 p_1 ) (:234)
+//   dscores_2 = -(q_1 - softmax(s_2/T) * sum_k q_1) / (2 B' T), likewise 1 <-> 2
+//   dz_v = dscores_v C (live rows only);  dC = dscores_1^T z_1 + dscores_2^T z_2
+//
+// Both views are stacked ([Z1; Z2], 2B' rows) so each contraction is ONE tcgen05 GEMM launch: scores (K-major x
+// K-major), dz (B = prototypes consumed MN-major), dC (both operands MN-major, contraction over the 2B' rows).
+// dscores are produced in forward (bf16) by the row-wise cross-entropy kernel and reused by both backward GEMMs.
+#include "gemm_host.cuh"
+
+namespace ssvb {
+int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters, float* codes,
+                 int64_t ld_codes, void* workspace, cudaStream_t s);
+size_t sinkhorn_ws_bytes(int64_t k);
+}  // namespace ssvb
+
+using namespace ssvb;
+
+namespace {
+
+struct SwavDims {
+  int64_t nb, nbank, bp, k, d, dpad, kp4, kp8;
+};
+SwavDims dims(int64_t nb, int64_t nbank, int64_t k, int64_t d) {
+  SwavDims s;
+  s.nb = nb; s.nbank = nbank; s.bp = nb + nbank; s.k = k; s.d = d;
+  s.dpad = round_up(d, 8);
+  s.kp4 = round_up(k, 4);
+  s.kp8 = round_up(k, 8);
+  return s;
+}
+struct SwavSaved {
+  __nv_bfloat16* z;   // [2B' x dpad]  (view 1 rows, then view 2 rows)
+  __nv_bfloat16* c;   // [K x dpad]
+  __nv_bfloat16* ds;  // [2B' x kp8]
+  size_t bytes;
+};
+SwavSaved swav_saved(void* base, const SwavDims& m) {
+  Carver c(base);
+  SwavSaved s;
+  s.z = c.take<__nv_bfloat16>(2 * m.bp * m.dpad);
+  s.c = c.take<__nv_bfloat16>(m.k * m.dpad);
+  s.ds = c.take<__nv_bfloat16>(2 * m.bp * m.kp8);
+  s.bytes = c.used();
+  return s;
+}
+struct SwavWs {
+  float* scores;  // [2B' x kp4]
+  float* codes;   // [2B' x kp4]
+  float* loss_part;  // [B']
+  float* dz;      // backward: [2B' x dpad] fp32
+  float* dc;      // backward: [K x dpad] fp32
+  void* sk;       // sinkhorn workspace
+  size_t bytes;
+};
+SwavWs swav_ws(void* base, const SwavDims& m) {
+  Carver c(base);
+  SwavWs w;
+  w.scores = c.take<float>(2 * m.bp * m.kp4);
+  w.codes = c.take<float>(2 * m.bp * m.kp4);
+  w.loss_part = c.take<float>(m.bp);
+  w.dz = c.take<float>(2 * m.bp * m.dpad);
+  w.dc = c.take<float>(m.k * m.dpad);
+  w.sk = c.take<uint8_t>(sinkhorn_ws_bytes(m.k));
+  w.bytes = c.used();
+  return w;
+}
+
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* red) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = lane < (blockDim.x >> 5) ? red[lane] : (is_max ? -INFINITY : 0.f);
+  return is_max ? warp_max(t) : warp_sum(t);
+}
+
+// one block per sample row r (of B'): both views' cross-entropy terms and dscores.
+__global__ void swav_ce_kernel(const float* __restrict__ scores, const float* __restrict__ codes, int64_t bp, int k,
+                               int64_t ld, float inv_t, float coef /* 1/(2 B' T) */, float* __restrict__ loss_part,
+                               __nv_bfloat16* __restrict__ ds, int64_t ldds) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x;
+  const float* s1 = scores + r * ld;
+  const float* s2 = scores + (bp + r) * ld;
+  const float* q1 = codes + r * ld;
+  const float* q2 = codes + (bp + r) * ld;
+  float m1 = -INFINITY, m2 = -INFINITY;
+  for (int c = threadIdx.x; c < k; c += blockDim.x) {
+    m1 = fmaxf(m1, s1[c]);
+    m2 = fmaxf(m2, s2[c]);
+  }
+  m1 = block_reduce(m1, true, red) * inv_t;
+  m2 = block_reduce(m2, true, red) * inv_t;
+  float e1 = 0.f, e2 = 0.f, a12 = 0.f, a21 = 0.f, sq1 = 0.f, sq2 = 0.f;
+  for (int c = threadIdx.x; c < k; c += blockDim.x) {
+    const float t1 = s1[c] * inv_t, t2 = s2[c] * inv_t;
+    e1 += __expf(t1 - m1);
+    e2 += __expf(t2 - m2);
+    const float a = q1[c], b = q2[c];
+    a12 = fmaf(a, t2, a12);  // sum q1 * (s2/T)
+    a21 = fmaf(b, t1, a21);
+    sq1 += a;
+    sq2 += b;
+  }
+  e1 = block_reduce(e1, false, red);
+  e2 = block_reduce(e2, false, red);
+  a12 = block_reduce(a12, false, red);
+  a21 = block_reduce(a21, false, red);
+  sq1 = block_reduce(sq1, false, red);
+  sq2 = block_reduce(sq2, false, red);
+  const float lse1 = m1 + __logf(e1), lse2 = m2 + __logf(e2);
+  // sum_k q1 p2 = sum q1 (t2 - lse2) ; per-row loss term -1/2 (.. + ..)
+  if (threadIdx.x == 0) loss_part[r] = -0.5f * ((a12 - sq1 * lse2) + (a21 - sq2 * lse1));
+  __nv_bfloat16* d1 = ds + r * ldds;
+  __nv_bfloat16* d2 = ds + (bp + r) * ldds;
+  for (int c = threadIdx.x; c < ldds; c += blockDim.x) {
+    float g1 = 0.f, g2 = 0.f;
+    if (c < k) {
+      g1 = -(q2[c] - __expf(s1[c] * inv_t - lse1) * sq2) * coef;  // d loss / d s1
+      g2 = -(q1[c] - __expf(s2[c] * inv_t - lse2) * sq1) * coef;  // d loss / d s2
+    }
+    d1[c] = __float2bfloat16_rn(g1);
+    d2[c] = __float2bfloat16_rn(g2);
+  }
+}
+
+// out[r, c] = go * in[r, c]  (+ optionally go * in2[r, c]) for c < d
+__global__ void scale_rows_kernel(const float* __restrict__ in, int64_t ldi, int64_t rows, int d,
+                                  const float* __restrict__ grad_out, float* __restrict__ out, int64_t ldo) {
+  const float go = __ldg(grad_out);
+  const int64_t total = rows * d;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / d;
+    const int c = static_cast<int>(i - r * d);
+    out[r * ldo + c] = in[r * ldi + c] * go;
+  }
+}
+
+int check_rows(const void* p, int64_t ld) {
+  if (!p) return SSVB_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) || (ld & 3)) return SSVB_ERR_ALIGNMENT;
+  return SSVB_OK;
+}
+int check_shape(int64_t nb, int64_t nbank, int64_t k, int64_t d, float temperature) {
+  if (nb <= 0 || nbank < 0 || k <= 0 || d <= 0 || !(temperature > 0.f)) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  if (2 * (nb + nbank) > (1 << 30) || k > (1 << 24)) return SSVB_ERR_UNSUPPORTED;
+  return SSVB_OK;
+}
+unsigned grid_for(int64_t total, int per_block) {
+  int64_t g = ceil_div(total, per_block);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t ssvb_swav_saved_bytes(int64_t nb, int64_t nbank, int64_t k, int64_t d) {
+  if (nb <= 0 || nbank < 0 || k <= 0 || d <= 0) return 0;
+  return swav_saved(nullptr, dims(nb, nbank, k, d)).bytes;
+}
+size_t ssvb_swav_workspace_bytes(int64_t nb, int64_t nbank, int64_t k, int64_t d) {
+  if (nb <= 0 || nbank < 0 || k <= 0 || d <= 0) return 0;
+  return swav_ws(nullptr, dims(nb, nbank, k, d)).bytes;
+}
+
+int ssvb_swav_fwd(const float* z1, const float* z2, const float* bank, const float* prototypes, int64_t nb,
+                  int64_t nbank, int64_t k, int64_t d, int64_t ld_z1, int64_t ld_z2, int64_t ld_bank,
+                  int64_t ld_proto, float temperature, float eps, int n_iters, float* loss, void* saved,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(check_shape(nb, nbank, k, d, temperature));
+  SSVB_TRY(check_rows(z1, ld_z1));
+  SSVB_TRY(check_rows(z2, ld_z2));
+  SSVB_TRY(check_rows(prototypes, ld_proto));
+  if (nbank > 0) SSVB_TRY(check_rows(bank, ld_bank));
+  if (!loss || !saved || !workspace || !(eps > 0.f) || n_iters < 0) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_swav_workspace_bytes(nb, nbank, k, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const SwavDims m = dims(nb, nbank, k, d);
+  SwavSaved sv = swav_saved(saved, m);
+  SwavWs ws = swav_ws(workspace, m);
+  const int di = static_cast<int>(d), dp = static_cast<int>(m.dpad);
+
+  // stage [Z1; Z2] (each = live rows then bank rows) and the prototypes as bf16
+  rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(nb, 8)), 256, 0, s>>>(z1, nb, di, ld_z1, dp, nullptr, sv.z);
+  SSVB_LAUNCH_CHECK();
+  rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(nb, 8)), 256, 0, s>>>(z2, nb, di, ld_z2, dp, nullptr,
+                                                                             sv.z + m.bp * m.dpad);
+  SSVB_LAUNCH_CHECK();
+  if (nbank > 0) {
+    rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(nbank, 8)), 256, 0, s>>>(bank, nbank, di, ld_bank, dp, nullptr,
+                                                                                  sv.z + nb * m.dpad);
+    SSVB_LAUNCH_CHECK();
+    SSVB_CUDA(cudaMemcpyAsync(sv.z + (m.bp + nb) * m.dpad, sv.z + nb * m.dpad, nbank * m.dpad * sizeof(__nv_bfloat16),
+                              cudaMemcpyDeviceToDevice, s));
+  }
+  rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(k, 8)), 256, 0, s>>>(prototypes, k, di, ld_proto, dp, nullptr, sv.c);
+  SSVB_LAUNCH_CHECK();
+
+  // scores[2B' x K] = [Z1; Z2] C^T
+  GemmParams p{};
+  p.M = static_cast<int>(2 * m.bp);
+  p.N = static_cast<int>(k);
+  p.K = static_cast<int>(m.dpad);
+  p.alpha = 1.f;
+  p.out = ws.scores;
+  p.ldc = m.kp4;
+  SSVB_TRY(launch_gemm({sv.z, m.dpad, false}, {sv.c, m.dpad, false}, p, 256, EPI_STORE_F32, 0, s));
+  // codes per view (Sinkhorn normalises over the B' rows of ONE view)
+  SSVB_TRY(sinkhorn_run(ws.scores, m.bp, k, m.kp4, eps, n_iters, ws.codes, m.kp4, ws.sk, s));
+  SSVB_TRY(sinkhorn_run(ws.scores + m.bp * m.kp4, m.bp, k, m.kp4, eps, n_iters, ws.codes + m.bp * m.kp4, m.kp4, ws.sk, s));
+  swav_ce_kernel<<<static_cast<unsigned>(m.bp), 256, 0, s>>>(ws.scores, ws.codes, m.bp, static_cast<int>(k), m.kp4,
+                                                           1.f / temperature,
+                                                           0.5f / (static_cast<float>(m.bp) * temperature),
+                                                           ws.loss_part, sv.ds, m.kp8);
+  SSVB_LAUNCH_CHECK();
+  sum_partials_kernel<<<1, 1024, 0, s>>>(ws.loss_part, static_cast<int>(m.bp), 1.f / static_cast<float>(m.bp), loss);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_swav_bwd(const float* z1, const float* z2, const float* bank, const float* prototypes, int64_t nb,
+                  int64_t nbank, int64_t k, int64_t d, int64_t ld_z1, int64_t ld_z2, int64_t ld_bank,
+                  int64_t ld_proto, float temperature, const float* grad_out, const void* saved, float* dz1,
+                  float* dz2, float* dproto, int64_t ld_dz1, int64_t ld_dz2, int64_t ld_dproto, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  (void)z1; (void)z2; (void)bank; (void)prototypes; (void)ld_z1; (void)ld_z2; (void)ld_bank; (void)ld_proto;
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(check_shape(nb, nbank, k, d, temperature));
+  if (dz1) SSVB_TRY(check_rows(dz1, ld_dz1));
+  if (dz2) SSVB_TRY(check_rows(dz2, ld_dz2));
+  if (dproto) SSVB_TRY(check_rows(dproto, ld_dproto));
+  if (!grad_out || !saved || !workspace) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_swav_workspace_bytes(nb, nbank, k, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const SwavDims m = dims(nb, nbank, k, d);
+  SwavSaved sv = swav_saved(const_cast<void*>(saved), m);
+  SwavWs ws = swav_ws(workspace, m);
+  const int di = static_cast<int>(d);
+
+  if (dz1 || dz2) {
+    // dz[2B' x d] = ds[2B' x K] C[K x d]        (A K-major, B = prototypes consumed MN-major)
+    GemmParams p{};
+    p.M = static_cast<int>(2 * m.bp);
+    p.N = static_cast<int>(m.dpad);
+    p.K = static_cast<int>(k);
+    p.alpha = 1.f;
+    p.out = ws.dz;
+    p.ldc = m.dpad;
+    SSVB_TRY(launch_gemm({sv.ds, m.kp8, false}, {sv.c, m.dpad, true}, p, 128, EPI_STORE_F32, 0, s));
+    if (dz1) {
+      scale_rows_kernel<<<grid_for(nb * d, 256), 256, 0, s>>>(ws.dz, m.dpad, nb, di, grad_out, dz1, ld_dz1);
+      SSVB_LAUNCH_CHECK();
+    }
+    if (dz2) {
+      scale_rows_kernel<<<grid_for(nb * d, 256), 256, 0, s>>>(ws.dz + m.bp * m.dpad, m.dpad, nb, di, grad_out, dz2, ld_dz2);
+      SSVB_LAUNCH_CHECK();
+    }
+  }
+  if (dproto) {
+    // dC[K x d] = ds^T [K x 2B'] [Z1; Z2] [2B' x d]   (both operands MN-major, contraction over the stacked rows)
+    GemmParams p{};
+    p.M = static_cast<int>(k);
+    p.N = static_cast<int>(m.dpad);
+    p.K = static_cast<int>(2 * m.bp);
+    p.alpha = 1.f;
+    p.out = ws.dc;
+    p.ldc = m.dpad;
+    SSVB_TRY(launch_gemm({sv.ds, m.kp8, true}, {sv.z, m.dpad, true}, p, 128, EPI_STORE_F32, 0, s));
+    scale_rows_kernel<<<grid_for(k * d, 256), 256, 0, s>>>(ws.dc, m.dpad, k, di, grad_out, dproto, ld_dproto);
+    SSVB_LAUNCH_CHECK();
+  }
+  return SSVB_OK;
+}
+
+}  // extern "C"

@@ -306,3 +306,73 @@ def test_sinkhorn_oracle(S, b, k, iters):
     np.testing.assert_allclose(codes.sum(1), 1.0, rtol=1e-4)
     if iters > 0:  # prototype marginals are uniform up to the last column normalisation
         assert abs(codes.sum() - b) / b < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ Barlow Twins
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_barlow_golden(S, tag):
+    g = load_golden("barlow")
+    norm, lm = bool(g[f"{tag}_cfg"][0]), float(g[f"{tag}_cfg"][1])
+    zi, zj = dev(g[f"{tag}_zi"]), dev(g[f"{tag}_zj"])
+    loss = S.BarlowLoss(norm, lm)(zi, zj)
+    loss.backward()
+    check(loss.item(), [zi.grad, zj.grad], float(g[f"{tag}_loss"]), [g[f"{tag}_dzi"], g[f"{tag}_dzj"]], f"barlow[{tag}]")
+
+
+def barlow_inputs(n, d, corr=0.7):
+    g = torch.Generator().manual_seed(7)
+    sig = (torch.rand(d, generator=g) * 1.5 + 0.5).numpy()
+    mu = torch.randn(d, generator=g).numpy()
+    zi = randn(0, n, d) * sig + mu
+    zj = corr * zi + (1 - corr) * (randn(1, n, d) * sig + mu)
+    return zi.astype(np.float32), zj.astype(np.float32)
+
+
+@pytest.mark.parametrize("n,d,norm", [(512, 4096, False), (256, 1000, False), (200, 264, True), (2048, 8192, False)])
+def test_barlow_oracle(S, n, d, norm):
+    zi, zj = barlow_inputs(n, d)
+    a, b = dev(zi), dev(zj)
+    loss = S.BarlowLoss(norm, 0.005)(a, b)
+    loss.backward()
+    if n * d * d > 3e10:   # cfg3 (2048 x 8192): fp64 oracle on CPU takes too long; chunked fp32 torch witness on GPU
+        with torch.no_grad():
+            xi = torch.from_numpy(zi).cuda().double()
+            xj = torch.from_numpy(zj).cuda().double()
+        xi.requires_grad_(True); xj.requires_grad_(True)
+        ti = (xi - xi.mean(0)) / xi.std(0)
+        tj = (xj - xj.mean(0)) / xj.std(0)
+        c = ti.t() @ tj / n
+        eye = torch.eye(d, device="cuda", dtype=torch.float64)
+        ref_loss = (((c - eye) ** 2) * (0.005 + (1 - 0.005) * eye)).sum()
+        ref_loss.backward()
+        ref = (ref_loss.item(), xi.grad.cpu().numpy(), xj.grad.cpu().numpy())
+    else:
+        ref = O.barlow(zi, zj, norm, 0.005)
+    check(loss.item(), [a.grad, b.grad], ref[0], ref[1:], f"barlow n={n} d={d}")
+
+
+# ------------------------------------------------------------------------------------------------ SwAV
+@pytest.mark.parametrize("tag", ["nobank", "bank", "c"])
+def test_swav_golden(S, tag):
+    g = load_golden("swav")
+    z1, z2, c = dev(g[f"sw_{tag}_z1"]), dev(g[f"sw_{tag}_z2"]), dev(g[f"sw_{tag}_c"])
+    bank = dev(g[f"sw_{tag}_bank"], False) if f"sw_{tag}_bank" in g else None
+    loss = S.SwavLoss(0.1, 0.05, 3)(z1, z2, c, bank)
+    loss.backward()
+    check(loss.item(), [z1.grad, z2.grad, c.grad], float(g[f"sw_{tag}_loss"]),
+          [g[f"sw_{tag}_dz1"], g[f"sw_{tag}_dz2"], g[f"sw_{tag}_dc"]], f"swav[{tag}]")
+
+
+@pytest.mark.parametrize("nb,nbank,k,d", [(512, 3000, 3000, 128), (300, 0, 100, 64), (64, 70, 1000, 32)])
+def test_swav_oracle(S, nb, nbank, k, d):
+    def unit(x):
+        return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+    z1 = unit(randn(0, nb, d))
+    z2 = unit(0.6 * z1 + 0.4 * randn(1, nb, d))
+    c = unit(randn(2, k, d))
+    bank = unit(randn(3, nbank, d)) if nbank else None
+    ref = O.swav(z1, z2, c, bank, 0.1, 0.05, 3)
+    a, b, p = dev(z1), dev(z2), dev(c)
+    loss = S.SwavLoss(0.1, 0.05, 3)(a, b, p, dev(bank, False) if nbank else None)
+    loss.backward()
+    check(loss.item(), [a.grad, b.grad, p.grad], ref[0], ref[1:], f"swav nb={nb} k={k}")
