@@ -9,16 +9,30 @@ namespace ssvb {
 inline int64_t sim_dpad(int64_t d) { return round_up(d, 64); }
 inline int64_t sim_mpad(int64_t m) { return round_up(m, 256); }
 
-// choose the column chunking so that there are enough (row block, chunk) units to balance 148 SMs while
-// every chunk keeps >= min_tiles tiles (amortises the A-tile load and the epilogue); no chunk is empty.
+// Choose the column chunking: (row block, chunk) units are statically strided over one CTA per SM, so the number
+// of units should fill whole waves of `num_sms()` CTAs (tail effect) while every chunk keeps >= min_tiles tiles
+// (amortises the A-tile load, the partial write / the accumulator drain).  No chunk is ever empty.
 inline void plan_chunks(SimParams& p, int BN, int min_tiles) {
   p.col_tiles = static_cast<int>(ceil_div(p.cols, BN));
-  const int target_units = num_sms() * 4;
-  int nch = static_cast<int>(ceil_div(target_units, p.row_blocks));
+  const int sms = num_sms();
   const int max_ch = p.col_tiles / min_tiles > 1 ? p.col_tiles / min_tiles : 1;
-  if (nch > max_ch) nch = max_ch;
-  if (nch < 1) nch = 1;
-  p.tiles_per_chunk = static_cast<int>(ceil_div(p.col_tiles, nch));
+  int best = 1;
+  double best_score = -1.0;
+  for (int nch = 1; nch <= max_ch && nch <= 256; ++nch) {
+    const int tpc = static_cast<int>(ceil_div(p.col_tiles, nch));
+    const int real = static_cast<int>(ceil_div(p.col_tiles, tpc));
+    if (real != nch) continue;  // would leave an empty chunk
+    const int64_t units = static_cast<int64_t>(p.row_blocks) * nch;
+    const int64_t waves = ceil_div(units, sms);
+    // wave efficiency in tiles (the last chunk of a row block may be shorter), minus a small per-chunk overhead
+    const double eff = static_cast<double>(p.row_blocks) * p.col_tiles / (static_cast<double>(waves) * sms * tpc);
+    const double score = eff - 0.002 * nch;
+    if (score > best_score) {
+      best_score = score;
+      best = nch;
+    }
+  }
+  p.tiles_per_chunk = static_cast<int>(ceil_div(p.col_tiles, best));
   p.nchunks = static_cast<int>(ceil_div(p.col_tiles, p.tiles_per_chunk));
 }
 
