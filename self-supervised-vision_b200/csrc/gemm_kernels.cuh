@@ -91,14 +91,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int ntiles = p.tiles_m * p.tiles_n;
   const int nkb = (p.K + C::BK - 1) / C::BK;
 
+  // producer / issuer loops run on the whole warp (uniform operands stay in uniform registers); elect_one() issues
   if (warp == 0) {
-    if (lane == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int st = it % NSTAGE;
-          mbar_wait(&empty[st], ((it / NSTAGE) & 1) ^ 1);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int st = it % NSTAGE;
+        mbar_wait(&empty[st], ((it / NSTAGE) & 1) ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full[st], C::A_BYTES + C::B_BYTES);
           uint8_t* a = sA + st * C::A_BYTES;
           uint8_t* b = sB + st * C::B_BYTES;
@@ -117,20 +118,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_load_2d(b, &tmB, &full[st], kb * C::BK, tn * BN);
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t IDESC = make_idesc(C::BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      int it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-        const int ab = tcount & 1;
-        mbar_wait(&acc_empty[ab], ((tcount >> 1) & 1) ^ 1);
+    constexpr uint32_t IDESC = make_idesc(C::BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    int it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int ab = tcount & 1;
+      mbar_wait(&acc_empty[ab], ((tcount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int st = it % NSTAGE;
+        mbar_wait(&full[st], (it / NSTAGE) & 1);
         tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int st = it % NSTAGE;
-          mbar_wait(&full[st], (it / NSTAGE) & 1);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t abase = smem_u32(sA + st * C::A_BYTES), bbase = smem_u32(sB + st * C::B_BYTES);
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
@@ -139,8 +141,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             umma_ss(tmem + ab * BN, ad, bd, IDESC, (kb | k4) != 0);
           }
           umma_commit(&empty[st]);
+          if (kb == nkb - 1) umma_commit(&acc_full[ab]);
         }
-        umma_commit(&acc_full[ab]);
+        __syncwarp();
       }
     }
   } else {

@@ -33,7 +33,8 @@ struct SimParams {
   int part_stride;
   // backward inputs / outputs
   const float* rowstat;  // NT-Xent: indexed by global row; MoCo: by local row
-  const float* colstat;  // NT-Xent only, indexed by column, padded to a multiple of 128
+  const float* colstat;       // NT-Xent ONLINE: fp32 lse2 per column, padded to a multiple of 128
+  const uint16_t* colstat16;  // NT-Xent FIXED: bf16 1/L' per column, padded to a multiple of 128
   float* dacc;           // [local rows x ld_dacc] fp32
   int ld_dacc;
   int use_atomic;  // nchunks > 1: red.add into a zeroed dacc
@@ -74,6 +75,17 @@ __device__ __forceinline__ UnitInfo decode_unit(const SimParams& p, int u) {
   return ui;
 }
 
+__device__ __forceinline__ float ex2_poly3(float x);
+// ---- timing-experiment knobs (tests/ab_bench.sh): each one REMOVES a piece of work, results become wrong ----
+#ifdef SSVB_DBG_NOEXP
+#define SSVB_EX2(x) (x)
+#else
+#define SSVB_EX2(x) ex2f(x)
+#endif
+#ifndef SSVB_POLY_MOD_FWD
+#define SSVB_POLY_MOD_FWD 3
+#endif
+
 // =====================================================================================================
 // forward
 // =====================================================================================================
@@ -82,22 +94,31 @@ struct FwdCfg {
   static constexpr int BN = 256;
   static constexpr int A_BYTES = 128 * 128 * KB;
   static constexpr int B_BYTES = BN * 128 * KB;
-  static constexpr int NSTAGE = (KB == 1) ? 4 : 2;
+  static constexpr int NSTAGE = (KB == 1) ? 6 : 3;  // deep enough to cover the TMA latency of a 64 KB tile
   static constexpr int NBARS = 4 + 2 * NSTAGE + 4;
-  static constexpr int SMEM = 1024 + 2 * A_BYTES + NSTAGE * B_BYTES + NBARS * 8 + 16;
+  static constexpr int SMEM = 1024 + A_BYTES + NSTAGE * B_BYTES + NBARS * 8 + 16;
 };
 
 template <int MODE, bool MASKED>
 __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int a_glob, int j0, float& m,
                                          float (&l)[4], uint64_t* s_empty_bar, int lane) {
   uint32_t v[2][32];
+#ifndef SSVB_DBG_NOLD
   tmem_ld_x32(taddr, v[0]);
+#else
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { v[0][i] = __float_as_uint(1e-3f * (i + lane)); v[1][i] = __float_as_uint(2e-3f * (i + lane)); }
+#endif
 #pragma unroll
   for (int cc = 0; cc < 8; ++cc) {
     uint32_t(&cur)[32] = v[cc & 1];
+#ifndef SSVB_DBG_NOLD
     tmem_ld_wait_regs(cur);
+#endif
     if (cc < 7) {
+#ifndef SSVB_DBG_NOLD
       tmem_ld_x32(taddr + (cc + 1) * 32, v[(cc + 1) & 1]);
+#endif
     } else {
       // the S buffer is fully in registers: hand it back to the MMA warp
       tc_fence_before();
@@ -113,7 +134,8 @@ __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int
           const int col = colbase + i;
           if (col == a_glob || col >= p.cols) t = -INFINITY;
         }
-        l[i & 3] += ex2f(t);
+        const bool poly = !MASKED && SSVB_POLY_MOD_FWD > 0 && (i % (SSVB_POLY_MOD_FWD > 0 ? SSVB_POLY_MOD_FWD : 1)) == 1;
+        l[i & 3] += poly ? ex2_poly3(t) : SSVB_EX2(t);
       }
     } else {
       float x[32];
@@ -139,15 +161,17 @@ __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int
   }
 }
 
+// 384 threads: warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps} shrinks to 40 registers/thread so that the two
+// softmax warpgroups (warps 4..11, TMEM lane quarter = warp % 4) can grow to 232.
 template <int KB, int MODE>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SimParams p) {
   using C = FwdCfg<KB>;
   constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + 2 * C::A_BYTES;
+  uint8_t* sB = smem + C::A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NSTAGE * C::B_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + 2;
@@ -182,59 +206,69 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem = *tmem_slot;
   const int nunits = p.row_blocks * p.nchunks;
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  // Producer / issuer loops are executed by the WHOLE warp (warp-uniform control flow and operands, so the TMA /
+  // UMMA operands stay in uniform registers); only the issue instructions sit behind elect_one().
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int ucount = 0, gt = 0;
-      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
-        const UnitInfo ui = decode_unit(p, u);
-        const int ua = ucount & 1;
-        mbar_wait(&a_empty[ua], ((ucount >> 1) & 1) ^ 1);
-        mbar_expect_tx(&a_full[ua], C::A_BYTES);
+    int ucount = 0, gt = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
+      const UnitInfo ui = decode_unit(p, u);
+      mbar_wait(&a_empty[0], (ucount & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&a_full[0], C::A_BYTES);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(sA + ua * C::A_BYTES + kb * (128 * 128), &tmA, &a_full[ua], kb * 64, ui.g0);
-        for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
-          const int st = gt % NSTAGE;
-          mbar_wait(&b_empty[st], ((gt / NSTAGE) & 1) ^ 1);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * (128 * 128), &tmA, &a_full[0], kb * 64, ui.g0);
+      }
+      __syncwarp();
+      for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
+        const int st = gt % NSTAGE;
+        mbar_wait(&b_empty[st], ((gt / NSTAGE) & 1) ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&b_full[st], C::B_BYTES);
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb)
             tma_load_2d(sB + st * C::B_BYTES + kb * (BN * 128), &tmB, &b_full[st], kb * 64, t * BN);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t IDESC = make_idesc(128, BN, 0, 0);
-      int ucount = 0, gt = 0;
-      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
-        const UnitInfo ui = decode_unit(p, u);
-        const int ua = ucount & 1;
-        mbar_wait(&a_full[ua], (ucount >> 1) & 1);
-        const uint32_t abase = smem_u32(sA + ua * C::A_BYTES);
-        for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
-          const int st = gt % NSTAGE, buf = gt & 1;
-          mbar_wait(&b_full[st], (gt / NSTAGE) & 1);
-          mbar_wait(&s_empty[buf], ((gt >> 1) & 1) ^ 1);
-          tc_fence_after();
+    constexpr uint32_t IDESC = make_idesc(128, BN, 0, 0);
+    const uint32_t abase = smem_u32(sA);
+    int ucount = 0, gt = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
+      const UnitInfo ui = decode_unit(p, u);
+      mbar_wait(&a_full[0], ucount & 1);
+      for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
+        const int st = gt % NSTAGE, buf = gt & 1;
+        mbar_wait(&b_full[st], (gt / NSTAGE) & 1);
+        mbar_wait(&s_empty[buf], ((gt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
           const uint32_t bbase = smem_u32(sB + st * C::B_BYTES);
+#ifndef SSVB_DBG_FWD_NOS
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)
               umma_ss(tmem + buf * BN, desc_kmajor(abase + kb * (128 * 128) + k4 * 32),
                       desc_kmajor(bbase + kb * (BN * 128) + k4 * 32), IDESC, (kb | k4) != 0);
+#endif
           umma_commit(&b_empty[st]);
           umma_commit(&s_full[buf]);
+          if (t == ui.t1 - 1) umma_commit(&a_empty[0]);
         }
-        umma_commit(&a_empty[ua]);
+        __syncwarp();
       }
     }
+  }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
-    const int wg = (warp - 2) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int wg = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row_l = q * 32 + lane;
     const uint32_t tlane = static_cast<uint32_t>(q * 32) << 16;
@@ -271,51 +305,80 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // =====================================================================================================
 // backward
 // =====================================================================================================
+// TMEM plan (512 columns): S0 @0, S1 @128 (fp32 similarity tiles), dZ @256 (DP-column gradient accumulator),
+// W0 @384, W1 @448 (bf16 weight tiles, the TMEM A-operand of the second GEMM).
+// Decoupling: a weight warpgroup pulls its WHOLE S tile into registers first and hands the S buffer straight back,
+// and the MMA thread never blocks on a single barrier — it polls "next S issuable" and "next dZ issuable" and issues
+// whichever is ready — so the similarity GEMM of tile t+2 runs while W(t) is still being computed and the
+// W -> dZ latency is off the critical path of the exp warps.
 template <int KB>
 struct BwdCfg {
   static constexpr int BN = 128;
   static constexpr int DP = 64 * KB;
   static constexpr int A_BYTES = 128 * 128 * KB;
   static constexpr int B_BYTES = BN * 128 * KB;
-  static constexpr int CS_BYTES = BN * 4;
-  static constexpr int NSTAGE = (KB == 1) ? 6 : 4;
-  static constexpr int NBARS = 4 + 2 * NSTAGE + 8 + 2;
-  static constexpr int SMEM = 1024 + 2 * A_BYTES + NSTAGE * (B_BYTES + CS_BYTES) + NBARS * 8 + 16;
-  // TMEM columns
-  static constexpr int T_S = 0;      // two 128-column S buffers
-  static constexpr int T_DZ = 256;   // DP-column gradient accumulator
-  static constexpr int T_W = 384;    // two 64-column bf16 W buffers
+  static constexpr int CS_BYTES = BN * 4;  // per-stage room for the column statistics (fp32; FIXED mode sends bf16 = half)
+  static constexpr int NSTAGE = (KB == 1) ? 8 : 5;
+  static constexpr int NBARS = 2 + 2 * NSTAGE + 8 + 2;
+  static constexpr int SMEM = 1024 + A_BYTES + NSTAGE * (B_BYTES + CS_BYTES) + NBARS * 8 + 16;
+  static constexpr int T_S = 0;
+  static constexpr int T_DZ = 256;
+  static constexpr int T_W = 384;
 };
 
+// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax, max rel. error 7.5e-5): takes a share of the
+// exponentials off the 16-op/clk MUFU unit, which is what bounds the forward kernel at d = 128.  Valid for x > -126.
+__device__ __forceinline__ float ex2_poly3(float x) {
+  const float magic = 12582912.f;  // 1.5 * 2^23: x + magic rounds x to the nearest integer in the low mantissa bits
+  const float r = x + magic;
+  const float f = x - (r - magic);  // f in [-0.5, 0.5]
+  float p = fmaf(f, 5.517166745e-2f, 2.426111221e-1f);
+  p = fmaf(p, f, 6.932609858e-1f);
+  p = fmaf(p, f, 9.999280736e-1f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+#ifndef SSVB_POLY_MOD_BWD
+#define SSVB_POLY_MOD_BWD 0  // share of backward exponentials on the polynomial path (measured: no gain, off)
+#endif
+
 template <int MODE, bool MASKED>
-__device__ __forceinline__ void bwd_tile(uint32_t t_s, uint32_t t_w, const SimParams& p, int a_glob, int j0,
-                                         float rs, const float* cs, uint64_t* s_empty_bar, int lane) {
-  uint32_t v[2][32];
-  tmem_ld_x32(t_s, v[0]);
+__device__ __forceinline__ void bwd_weights(const uint32_t (&sv)[4][32], uint32_t (&pkall)[4][16], const SimParams& p,
+                                            int a_glob, int j0, float rs, const void* cs) {
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
-    uint32_t(&cur)[32] = v[cc & 1];
-    tmem_ld_wait_regs(cur);
-    if (cc < 3) {
-      tmem_ld_x32(t_s + (cc + 1) * 32, v[(cc + 1) & 1]);
-    } else {
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty_bar);
+    uint32_t(&pk)[16] = pkall[cc];
+#pragma unroll
+    // FIXED mode: the column factor 1/L'_b is multiplicative, bf16 (2^-9 relative) is enough and halves the
+    // broadcast shared-memory reads (one wavefront per 4 bytes per warp: the dominant smem consumer otherwise).
+    uint4 c8[4];
+    if (MODE == SIM_NTX_FIXED) {
+#pragma unroll
+      for (int i8 = 0; i8 < 4; ++i8) c8[i8] = reinterpret_cast<const uint4*>(cs)[cc * 4 + i8];
     }
-    float w[32];
 #pragma unroll
     for (int i4 = 0; i4 < 8; ++i4) {
-      float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (MODE != SIM_MOCO) c4 = reinterpret_cast<const float4*>(cs)[cc * 8 + i4];
-      const float csv[4] = {c4.x, c4.y, c4.z, c4.w};
+      float csv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (MODE == SIM_NTX_FIXED) {
+        const uint4 cu = c8[i4 >> 1];
+        const uint32_t u0 = (i4 & 1) ? cu.z : cu.x, u1 = (i4 & 1) ? cu.w : cu.y;
+        csv[0] = __uint_as_float(u0 << 16);          // bf16 pair -> fp32: low half << 16,
+        csv[1] = __uint_as_float(u0 & 0xffff0000u);  //                    high half masked
+        csv[2] = __uint_as_float(u1 << 16);
+        csv[3] = __uint_as_float(u1 & 0xffff0000u);
+      } else if (MODE == SIM_NTX_ONLINE) {
+        const float4 c4 = reinterpret_cast<const float4*>(cs)[cc * 8 + i4];
+        csv[0] = c4.x; csv[1] = c4.y; csv[2] = c4.z; csv[3] = c4.w;
+      }
+      float w[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int i = i4 * 4 + e;
-        const float s = __uint_as_float(cur[i]);
+        const float s = __uint_as_float(sv[cc][i]);
         float wv;
         if (MODE == SIM_NTX_FIXED) {
-          wv = ex2f(fmaf(s, p.c, -p.shift)) * (rs + csv[e]);
+          const float x = fmaf(s, p.c, -p.shift);
+          const bool poly = !MASKED && SSVB_POLY_MOD_BWD > 0 && (i % (SSVB_POLY_MOD_BWD > 0 ? SSVB_POLY_MOD_BWD : 1)) == 1;
+          wv = (poly ? ex2_poly3(x) : SSVB_EX2(x)) * (rs + csv[e]);
         } else if (MODE == SIM_NTX_ONLINE) {
           const float t = s * p.c;
           wv = ex2f(t - rs) + ex2f(t - csv[e]);
@@ -323,30 +386,30 @@ __device__ __forceinline__ void bwd_tile(uint32_t t_s, uint32_t t_w, const SimPa
           wv = ex2f(fmaf(s, p.c, -rs));
         }
         if (MASKED && (j0 + cc * 32 + i == a_glob)) wv = 0.f;
-        w[i] = wv;
+        w[e] = wv;
       }
+      pk[i4 * 2] = pack_bf16x2(w[0], w[1]);
+      pk[i4 * 2 + 1] = pack_bf16x2(w[2], w[3]);
     }
-    uint32_t pk[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(w[2 * i], w[2 * i + 1]);
-    tmem_st_x16(t_w + cc * 16, pk);
   }
 }
 
+// 384 threads: warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps} at 40 registers/thread; warps 4..11 = two weight
+// warpgroups at 232 registers/thread (a whole 128-column S row lives in registers).
 template <int KB, int MODE>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SimParams p) {
   using C = BwdCfg<KB>;
   constexpr int BN = C::BN, NSTAGE = C::NSTAGE, DP = C::DP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + 2 * C::A_BYTES;
+  uint8_t* sB = smem + C::A_BYTES;
   uint8_t* sC = sB + NSTAGE * C::B_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sC + NSTAGE * C::CS_BYTES);
   uint64_t* a_full = bars;
-  uint64_t* a_empty = bars + 2;
-  uint64_t* b_full = bars + 4;
+  uint64_t* a_empty = bars + 1;
+  uint64_t* b_full = bars + 2;
   uint64_t* b_empty = b_full + NSTAGE;
   uint64_t* s_full = b_empty + NSTAGE;
   uint64_t* s_empty = s_full + 2;
@@ -362,9 +425,9 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 4);
       mbar_init(&w_full[i], 4);
@@ -385,82 +448,113 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem = *tmem_slot;
   const int nunits = p.row_blocks * p.nchunks;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer (whole warp, elect_one issues)
       int ucount = 0, gt = 0;
       for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
         const UnitInfo ui = decode_unit(p, u);
-        const int ua = ucount & 1;
-        mbar_wait(&a_empty[ua], ((ucount >> 1) & 1) ^ 1);
-        mbar_expect_tx(&a_full[ua], C::A_BYTES);
+        mbar_wait(a_empty, (ucount & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(a_full, C::A_BYTES);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(sA + ua * C::A_BYTES + kb * (128 * 128), &tmA, &a_full[ua], kb * 64, ui.g0);
+          for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * (128 * 128), &tmA, a_full, kb * 64, ui.g0);
+        }
+        __syncwarp();
         for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
           const int st = gt % NSTAGE;
           mbar_wait(&b_empty[st], ((gt / NSTAGE) & 1) ^ 1);
-          mbar_expect_tx(&b_full[st], C::B_BYTES + (MODE != SIM_MOCO ? C::CS_BYTES : 0));
+          if (elect_one()) {
+            constexpr int CSB = (MODE == SIM_NTX_FIXED) ? BN * 2 : (MODE == SIM_NTX_ONLINE ? BN * 4 : 0);
+            mbar_expect_tx(&b_full[st], C::B_BYTES + CSB);
 #pragma unroll
-          for (int kb = 0; kb < KB; ++kb)
-            tma_load_2d(sB + st * C::B_BYTES + kb * (BN * 128), &tmB, &b_full[st], kb * 64, t * BN);
-          if (MODE != SIM_MOCO) bulk_load_1d(sC + st * C::CS_BYTES, p.colstat + t * BN, C::CS_BYTES, &b_full[st]);
+            for (int kb = 0; kb < KB; ++kb)
+              tma_load_2d(sB + st * C::B_BYTES + kb * (BN * 128), &tmB, &b_full[st], kb * 64, t * BN);
+            if (MODE == SIM_NTX_FIXED) bulk_load_1d(sC + st * C::CS_BYTES, p.colstat16 + t * BN, CSB, &b_full[st]);
+            if (MODE == SIM_NTX_ONLINE) bulk_load_1d(sC + st * C::CS_BYTES, p.colstat + t * BN, CSB, &b_full[st]);
+          }
+          __syncwarp();
         }
       }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer: whole warp polls (votes keep the
+      // control flow warp-uniform), one elected lane issues; never blocks on a single barrier
       constexpr uint32_t IDESC_S = make_idesc(128, BN, 0, 0);
       constexpr uint32_t IDESC_D = make_idesc(128, DP, 0, 1);  // A = W from TMEM, B = same smem tile read MN-major
+      const uint32_t abase = smem_u32(sA);
       int ucount = 0, gt = 0;
       for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
         const UnitInfo ui = decode_unit(p, u);
-        const int ua = ucount & 1;
-        mbar_wait(&a_full[ua], (ucount >> 1) & 1);
-        const uint32_t abase = smem_u32(sA + ua * C::A_BYTES);
         const int ntile = ui.t1 - ui.t0;
         const int gt0 = gt;
-        // software pipeline: S(i) is issued one tile ahead of dZ(i-1)
-        for (int i = 0; i <= ntile; ++i) {
-          if (i < ntile) {
-            const int g = gt0 + i;
+        mbar_wait(a_full, ucount & 1);
+        int ns = 0, nd = 0;
+        long long t_idle = 0;
+        while (nd < ntile) {
+          bool progressed = false;
+          if (ns < ntile) {
+            const int g = gt0 + ns;
             const int st = g % NSTAGE, buf = g & 1;
-            mbar_wait(&b_full[st], (g / NSTAGE) & 1);
-            mbar_wait(&s_empty[buf], ((g >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t bbase = smem_u32(sB + st * C::B_BYTES);
+            const bool ok = mbar_test_wait(&b_full[st], (g / NSTAGE) & 1) && mbar_test_wait(&s_empty[buf], ((g >> 1) & 1) ^ 1);
+            if (__all_sync(0xffffffffu, ok)) {
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t bbase = smem_u32(sB + st * C::B_BYTES);
+#ifndef SSVB_DBG_NOS
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb)
+                for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                umma_ss(tmem + C::T_S + buf * BN, desc_kmajor(abase + kb * (128 * 128) + k4 * 32),
-                        desc_kmajor(bbase + kb * (BN * 128) + k4 * 32), IDESC_S, (kb | k4) != 0);
-            umma_commit(&s_full[buf]);
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    umma_ss(tmem + C::T_S + buf * BN, desc_kmajor(abase + kb * (128 * 128) + k4 * 32),
+                            desc_kmajor(bbase + kb * (BN * 128) + k4 * 32), IDESC_S, (kb | k4) != 0);
+#endif
+                umma_commit(&s_full[buf]);
+                if (ns == ntile - 1) umma_commit(a_empty);  // last reader of this unit's A tile
+              }
+              __syncwarp();
+              ++ns;
+              progressed = true;
+            }
           }
-          if (i > 0) {
-            const int g = gt0 + i - 1;
+          if (nd < ns) {
+            const int g = gt0 + nd;
             const int st = g % NSTAGE, buf = g & 1;
-            mbar_wait(&w_full[buf], (g >> 1) & 1);
-            if (i == 1) mbar_wait(dz_empty, (ucount & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t bbase = smem_u32(sB + st * C::B_BYTES);
+            const bool ok = mbar_test_wait(&w_full[buf], (g >> 1) & 1) &&
+                            (nd > 0 || mbar_test_wait(dz_empty, (ucount & 1) ^ 1));
+            if (__all_sync(0xffffffffu, ok)) {
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t bbase = smem_u32(sB + st * C::B_BYTES);
+#ifndef SSVB_DBG_NOD
 #pragma unroll
-            for (int k = 0; k < BN / 16; ++k)
-              umma_ts(tmem + C::T_DZ, tmem + C::T_W + buf * 64 + k * 8,
-                      desc_mnmajor(bbase + k * (16 * 128), BN * 128), IDESC_D, (i > 1 || k > 0) ? 1u : 0u);
-            umma_commit(&b_empty[st]);
-            umma_commit(&w_empty[buf]);
+                for (int k = 0; k < BN / 16; ++k)
+                  umma_ts(tmem + C::T_DZ, tmem + C::T_W + buf * 64 + k * 8,
+                          desc_mnmajor(bbase + k * (16 * 128), BN * 128), IDESC_D, (nd > 0 || k > 0) ? 1u : 0u);
+#endif
+                umma_commit(&b_empty[st]);
+                umma_commit(&w_empty[buf]);
+                if (nd == ntile - 1) umma_commit(dz_full);
+              }
+              __syncwarp();
+              ++nd;
+              progressed = true;
+            }
+          }
+          if (progressed) {
+            t_idle = 0;
+          } else {
+            if (t_idle == 0) t_idle = clock64();
+            else if (clock64() - t_idle > 4000000000LL) __trap();
           }
         }
         gt = gt0 + ntile;
-        umma_commit(dz_full);
-        umma_commit(&a_empty[ua]);
       }
     }
   } else {
     // ------------------------------------------------------------------ weight warpgroups + epilogue
-    const int wg = (warp - 2) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int wg = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row_l = q * 32 + lane;
     const uint32_t tlane = static_cast<uint32_t>(q * 32) << 16;
@@ -476,17 +570,39 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int st = gt % NSTAGE;
         if (MODE != SIM_MOCO) mbar_wait(&b_full[st], (gt / NSTAGE) & 1);  // column stats landed with the B tile
         mbar_wait(&s_full[wg], (gt >> 1) & 1);
-        mbar_wait(&w_empty[wg], ((gt >> 1) & 1) ^ 1);
         tc_fence_after();
+        const uint32_t t_s = tmem + tlane + C::T_S + wg * BN;
+        uint32_t sv[4][32];
+#ifndef SSVB_DBG_NOLD
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) tmem_ld_x32(t_s + cc * 32, sv[cc]);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) tmem_ld_wait_regs(sv[cc]);
+#else
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[cc][i] = __float_as_uint(1e-3f * (i + cc + lane));
+#endif
+        // the whole S tile is in registers: give the buffer back so S(t+2) can be issued right away
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[wg]);
         const int j0 = t * BN;
         const bool special = (MODE != SIM_MOCO) && (j0 < ui.g0 + 128) && (j0 + BN > ui.g0);
-        const uint32_t t_s = tmem + tlane + C::T_S + wg * BN;
         const uint32_t t_w = tmem + tlane + C::T_W + wg * 64;
-        const float* cs = reinterpret_cast<const float*>(sC + st * C::CS_BYTES);
+        const void* cs = sC + st * C::CS_BYTES;
+        // all 128 weights of this row are computed and packed in registers BEFORE waiting for the W buffer, so the
+        // dZ GEMM of tile t-2 (which still reads that buffer) stays off this warp's critical path
+        uint32_t pk[4][16];
         if (special)
-          bwd_tile<MODE, true>(t_s, t_w, p, a_glob, j0, rs, cs, &s_empty[wg], lane);
+          bwd_weights<MODE, true>(sv, pk, p, a_glob, j0, rs, cs);
         else
-          bwd_tile<MODE, false>(t_s, t_w, p, a_glob, j0, rs, cs, &s_empty[wg], lane);
+          bwd_weights<MODE, false>(sv, pk, p, a_glob, j0, rs, cs);
+        mbar_wait(&w_empty[wg], ((gt >> 1) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) tmem_st_x16(t_w + cc * 16, pk[cc]);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();

@@ -13,7 +13,8 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libssv_b200.so")
+# SSVB_LIB selects an A/B tuning build (e.g. libssv_b200_x.so) for experiments; default is the product build
+LIB_PATH = os.path.join(_HERE, os.environ.get("SSVB_LIB", "libssv_b200.so"))
 HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "ssv_b200.h"))
 
 _CTYPE = {
