@@ -33,11 +33,11 @@ struct SimParams {
   int part_stride;
   // backward inputs / outputs
   const float* rowstat;  // NT-Xent: indexed by global row; MoCo: by local row
-  const float* colstat;       // NT-Xent ONLINE: fp32 lse2 per column, padded to a multiple of 128
-  const uint16_t* colstat16;  // NT-Xent FIXED: bf16 1/L' per column, padded to a multiple of 128
+  const float* colstat;  // NT-Xent: fp32 column statistic (FIXED: 1/L', ONLINE: lse2), padded to a multiple of 128
   float* dacc;           // [local rows x ld_dacc] fp32
   int ld_dacc;
   int use_atomic;  // nchunks > 1: red.add into a zeroed dacc
+  unsigned long long* dbg;  // SSVB_DBG_TIMING builds only
 };
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -103,6 +103,7 @@ template <int MODE, bool MASKED>
 __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int a_glob, int j0, float& m,
                                          float (&l)[4], uint64_t* s_empty_bar, int lane) {
   uint32_t v[2][32];
+  unsigned long long l2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};  // packed row-sum accumulators
 #ifndef SSVB_DBG_NOLD
   tmem_ld_x32(taddr, v[0]);
 #else
@@ -126,7 +127,22 @@ __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int
       if (lane == 0) mbar_arrive(s_empty_bar);
     }
     const int colbase = j0 + cc * 32;
-    if (MODE == SIM_NTX_FIXED) {
+    if (MODE == SIM_NTX_FIXED && !MASKED) {
+      // packed scale/shift FFMA and packed row-sum FADD: 2 issue slots per element instead of 3
+      const unsigned long long c2 = pack_f32x2(p.c, p.c), ns2 = pack_f32x2(-p.shift, -p.shift);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const unsigned long long x2 =
+            fma_f32x2(pack_f32x2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), c2, ns2);
+        float x0, x1;
+        unpack_f32x2(x2, x0, x1);
+        const bool p0 = SSVB_POLY_MOD_FWD > 0 && ((2 * i) % (SSVB_POLY_MOD_FWD > 0 ? SSVB_POLY_MOD_FWD : 1)) == 1;
+        const bool p1 = SSVB_POLY_MOD_FWD > 0 && ((2 * i + 1) % (SSVB_POLY_MOD_FWD > 0 ? SSVB_POLY_MOD_FWD : 1)) == 1;
+        const float e0 = p0 ? ex2_poly3(x0) : SSVB_EX2(x0);
+        const float e1 = p1 ? ex2_poly3(x1) : SSVB_EX2(x1);
+        l2[i & 1] = add_f32x2(l2[i & 1], pack_f32x2(e0, e1));
+      }
+    } else if (MODE == SIM_NTX_FIXED) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float t = fmaf(__uint_as_float(cur[i]), p.c, -p.shift);
@@ -159,7 +175,14 @@ __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int
       for (int i = 0; i < 32; ++i) l[i & 3] += ex2f(x[i] - mn);
     }
   }
+  if (MODE == SIM_NTX_FIXED && !MASKED) {
+    float a0, a1, b0, b1;
+    unpack_f32x2(l2[0], a0, a1);
+    unpack_f32x2(l2[1], b0, b1);
+    l[0] += a0; l[1] += a1; l[2] += b0; l[3] += b1;
+  }
 }
+
 
 // 384 threads: warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps} shrinks to 40 registers/thread so that the two
 // softmax warpgroups (warps 4..11, TMEM lane quarter = warp % 4) can grow to 232.
@@ -311,13 +334,23 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // and the MMA thread never blocks on a single barrier — it polls "next S issuable" and "next dZ issuable" and issues
 // whichever is ready — so the similarity GEMM of tile t+2 runs while W(t) is still being computed and the
 // W -> dZ latency is off the critical path of the exp warps.
+// phase timing (timing experiments only): block 0, first lane of the first math warp / of the MMA warp accumulate
+// clock64 deltas per phase into p.dbg[0..15]
+#ifdef SSVB_DBG_TIMING
+#define SSVB_T0() long long _t_prev = clock64()
+#define SSVB_TP(slot) do { const long long _t_now = clock64(); _t_acc[slot] += _t_now - _t_prev; _t_prev = _t_now; } while (0)
+#else
+#define SSVB_T0() do {} while (0)
+#define SSVB_TP(slot) do {} while (0)
+#endif
+
 template <int KB>
 struct BwdCfg {
   static constexpr int BN = 128;
   static constexpr int DP = 64 * KB;
   static constexpr int A_BYTES = 128 * 128 * KB;
   static constexpr int B_BYTES = BN * 128 * KB;
-  static constexpr int CS_BYTES = BN * 4;  // per-stage room for the column statistics (fp32; FIXED mode sends bf16 = half)
+  static constexpr int CS_BYTES = BN * 4;  // per-stage column statistics (fp32)
   static constexpr int NSTAGE = (KB == 1) ? 8 : 5;
   static constexpr int NBARS = 2 + 2 * NSTAGE + 8 + 2;
   static constexpr int SMEM = 1024 + A_BYTES + NSTAGE * (B_BYTES + CS_BYTES) + NBARS * 8 + 16;
@@ -341,63 +374,77 @@ __device__ __forceinline__ float ex2_poly3(float x) {
 #define SSVB_POLY_MOD_BWD 0  // share of backward exponentials on the polynomial path (measured: no gain, off)
 #endif
 
+// weights of 32 consecutive columns [cb, cb+32) of one row: sv = S values, pk = packed bf16 pairs out
 template <int MODE, bool MASKED>
-__device__ __forceinline__ void bwd_weights(const uint32_t (&sv)[4][32], uint32_t (&pkall)[4][16], const SimParams& p,
-                                            int a_glob, int j0, float rs, const void* cs) {
+__device__ __forceinline__ void bwd_weights32(const uint32_t (&sv)[32], uint32_t (&pk)[16], const SimParams& p,
+                                              int a_glob, int colbase, float rs, const void* cs32) {
+#ifndef SSVB_BWD_SCALAR_MATH
+  if (MODE == SIM_NTX_FIXED && !MASKED) {
+    // issue-bound loop: packed fp32 arithmetic (two elements per FFMA2 / FADD2 / FMUL2), one MUFU per element, one
+    // pack per pair -> 3 issue slots per element instead of 5.  Column factors arrive as fp32 pairs (LDS.128 = 2 pairs).
+    const unsigned long long c2 = pack_f32x2(p.c, p.c), ns2 = pack_f32x2(-p.shift, -p.shift), rs2 = pack_f32x2(rs, rs);
+    const ulonglong2* cw = reinterpret_cast<const ulonglong2*>(cs32);
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    uint32_t(&pk)[16] = pkall[cc];
+    for (int i2 = 0; i2 < 8; ++i2) {
+      const ulonglong2 cu = cw[i2];  // column factors of 4 consecutive columns
 #pragma unroll
-    // FIXED mode: the column factor 1/L'_b is multiplicative, bf16 (2^-9 relative) is enough and halves the
-    // broadcast shared-memory reads (one wavefront per 4 bytes per warp: the dominant smem consumer otherwise).
-    uint4 c8[4];
-    if (MODE == SIM_NTX_FIXED) {
-#pragma unroll
-      for (int i8 = 0; i8 < 4; ++i8) c8[i8] = reinterpret_cast<const uint4*>(cs)[cc * 4 + i8];
+      for (int e = 0; e < 2; ++e) {
+        const int i = i2 * 2 + e;  // pair index: columns 2i, 2i+1
+        const unsigned long long x2 =
+            fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, ns2);
+        float x0, x1;
+        unpack_f32x2(x2, x0, x1);
+        // a share of the exponentials runs as a polynomial on the FMA pipe (MUFU is the binding pipe of this loop)
+        const bool q0 = SSVB_POLY_MOD_BWD > 0 && ((2 * i) % (SSVB_POLY_MOD_BWD > 0 ? SSVB_POLY_MOD_BWD : 1)) == 1;
+        const bool q1 = SSVB_POLY_MOD_BWD > 0 && ((2 * i + 1) % (SSVB_POLY_MOD_BWD > 0 ? SSVB_POLY_MOD_BWD : 1)) == 1;
+        const float e0 = q0 ? ex2_poly3(x0) : SSVB_EX2(x0);
+        const float e1 = q1 ? ex2_poly3(x1) : SSVB_EX2(x1);
+        const unsigned long long w2 = mul_f32x2(pack_f32x2(e0, e1), add_f32x2(rs2, e ? cu.y : cu.x));
+        float w0, w1;
+        unpack_f32x2(w2, w0, w1);
+        pk[i] = pack_bf16x2(w0, w1);
+      }
     }
+    return;
+  }
+#endif
 #pragma unroll
-    for (int i4 = 0; i4 < 8; ++i4) {
-      float csv[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i4 = 0; i4 < 8; ++i4) {
+    float csv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MODE != SIM_MOCO) {
+      const float4 c4 = reinterpret_cast<const float4*>(cs32)[i4];
+      csv[0] = c4.x; csv[1] = c4.y; csv[2] = c4.z; csv[3] = c4.w;
+    }
+    float w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = i4 * 4 + e;
+      const float s = __uint_as_float(sv[i]);
+      float wv;
       if (MODE == SIM_NTX_FIXED) {
-        const uint4 cu = c8[i4 >> 1];
-        const uint32_t u0 = (i4 & 1) ? cu.z : cu.x, u1 = (i4 & 1) ? cu.w : cu.y;
-        csv[0] = __uint_as_float(u0 << 16);          // bf16 pair -> fp32: low half << 16,
-        csv[1] = __uint_as_float(u0 & 0xffff0000u);  //                    high half masked
-        csv[2] = __uint_as_float(u1 << 16);
-        csv[3] = __uint_as_float(u1 & 0xffff0000u);
+        const float x = fmaf(s, p.c, -p.shift);
+        const bool poly = !MASKED && SSVB_POLY_MOD_BWD > 0 && (i % (SSVB_POLY_MOD_BWD > 0 ? SSVB_POLY_MOD_BWD : 1)) == 1;
+        wv = (poly ? ex2_poly3(x) : SSVB_EX2(x)) * (rs + csv[e]);
       } else if (MODE == SIM_NTX_ONLINE) {
-        const float4 c4 = reinterpret_cast<const float4*>(cs)[cc * 8 + i4];
-        csv[0] = c4.x; csv[1] = c4.y; csv[2] = c4.z; csv[3] = c4.w;
+        const float t = s * p.c;
+        wv = ex2f(t - rs) + ex2f(t - csv[e]);
+      } else {
+        wv = ex2f(fmaf(s, p.c, -rs));
       }
-      float w[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = i4 * 4 + e;
-        const float s = __uint_as_float(sv[cc][i]);
-        float wv;
-        if (MODE == SIM_NTX_FIXED) {
-          const float x = fmaf(s, p.c, -p.shift);
-          const bool poly = !MASKED && SSVB_POLY_MOD_BWD > 0 && (i % (SSVB_POLY_MOD_BWD > 0 ? SSVB_POLY_MOD_BWD : 1)) == 1;
-          wv = (poly ? ex2_poly3(x) : SSVB_EX2(x)) * (rs + csv[e]);
-        } else if (MODE == SIM_NTX_ONLINE) {
-          const float t = s * p.c;
-          wv = ex2f(t - rs) + ex2f(t - csv[e]);
-        } else {
-          wv = ex2f(fmaf(s, p.c, -rs));
-        }
-        if (MASKED && (j0 + cc * 32 + i == a_glob)) wv = 0.f;
-        w[e] = wv;
-      }
-      pk[i4 * 2] = pack_bf16x2(w[0], w[1]);
-      pk[i4 * 2 + 1] = pack_bf16x2(w[2], w[3]);
+      if (MASKED && (colbase + i == a_glob)) wv = 0.f;
+      w[e] = wv;
     }
+    pk[i4 * 2] = pack_bf16x2(w[0], w[1]);
+    pk[i4 * 2 + 1] = pack_bf16x2(w[2], w[3]);
   }
 }
 
-// 384 threads: warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps} at 40 registers/thread; warps 4..11 = two weight
-// warpgroups at 232 registers/thread (a whole 128-column S row lives in registers).
+// 640 threads: warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps} at 40 registers/thread; warps 4..19 = FOUR weight
+// warpgroups.  Tile t is processed by the warpgroup pair (t & 1); within the pair each warpgroup owns one 64-column
+// half of the 128 x 128 tile (thread = row, TMEM lane quarter = warp % 4).  Four resident math warps per scheduler
+// (instead of two) hide the TMEM-load / barrier / MUFU latencies of each other.
 template <int KB, int MODE>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(640, 1)
 sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SimParams p) {
   using C = BwdCfg<KB>;
   constexpr int BN = C::BN, NSTAGE = C::NSTAGE, DP = C::DP;
@@ -429,8 +476,8 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(a_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
-      mbar_init(&w_full[i], 4);
+      mbar_init(&s_empty[i], 8);
+      mbar_init(&w_full[i], 8);
       mbar_init(&w_empty[i], 1);
     }
     for (int i = 0; i < NSTAGE; ++i) {
@@ -438,7 +485,7 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&b_empty[i], 1);
     }
     mbar_init(dz_full, 1);
-    mbar_init(dz_empty, 8);
+    mbar_init(dz_empty, 16);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -466,13 +513,12 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int st = gt % NSTAGE;
           mbar_wait(&b_empty[st], ((gt / NSTAGE) & 1) ^ 1);
           if (elect_one()) {
-            constexpr int CSB = (MODE == SIM_NTX_FIXED) ? BN * 2 : (MODE == SIM_NTX_ONLINE ? BN * 4 : 0);
+            constexpr int CSB = (MODE != SIM_MOCO) ? BN * 4 : 0;
             mbar_expect_tx(&b_full[st], C::B_BYTES + CSB);
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
               tma_load_2d(sB + st * C::B_BYTES + kb * (BN * 128), &tmB, &b_full[st], kb * 64, t * BN);
-            if (MODE == SIM_NTX_FIXED) bulk_load_1d(sC + st * C::CS_BYTES, p.colstat16 + t * BN, CSB, &b_full[st]);
-            if (MODE == SIM_NTX_ONLINE) bulk_load_1d(sC + st * C::CS_BYTES, p.colstat + t * BN, CSB, &b_full[st]);
+            if (MODE != SIM_MOCO) bulk_load_1d(sC + st * C::CS_BYTES, p.colstat + t * BN, CSB, &b_full[st]);
           }
           __syncwarp();
         }
@@ -484,6 +530,9 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t IDESC_D = make_idesc(128, DP, 0, 1);  // A = W from TMEM, B = same smem tile read MN-major
       const uint32_t abase = smem_u32(sA);
       int ucount = 0, gt = 0;
+#ifdef SSVB_DBG_TIMING
+      long long _m_acc[2] = {0, 0};
+#endif
       for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
         const UnitInfo ui = decode_unit(p, u);
         const int ntile = ui.t1 - ui.t0;
@@ -491,6 +540,9 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(a_full, ucount & 1);
         int ns = 0, nd = 0;
         long long t_idle = 0;
+#ifdef SSVB_DBG_TIMING
+        long long _m_t = clock64();
+#endif
         while (nd < ntile) {
           bool progressed = false;
           if (ns < ntile) {
@@ -546,19 +598,32 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             if (t_idle == 0) t_idle = clock64();
             else if (clock64() - t_idle > 4000000000LL) __trap();
+            __nanosleep(40);
           }
+#ifdef SSVB_DBG_TIMING
+          { const long long n = clock64(); _m_acc[progressed ? 0 : 1] += n - _m_t; _m_t = n; }
+#endif
         }
         gt = gt0 + ntile;
       }
+#ifdef SSVB_DBG_TIMING
+      if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8] = _m_acc[0]; p.dbg[9] = _m_acc[1]; }
+#endif
     }
   } else {
     // ------------------------------------------------------------------ weight warpgroups + epilogue
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int wg = (warp - 4) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int wgi = (warp - 4) >> 2;  // 0..3
+    const int pair = wgi >> 1;        // which tiles (parity) / which S and W buffer
+    const int half = wgi & 1;         // which 64-column half of the tile
     const int q = warp & 3;
     const int row_l = q * 32 + lane;
     const uint32_t tlane = static_cast<uint32_t>(q * 32) << 16;
     int gt = 0, ucount = 0;
+#ifdef SSVB_DBG_TIMING
+    long long _t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    SSVB_T0();
     for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
       const UnitInfo ui = decode_unit(p, u);
       const int a_glob = ui.g0 + row_l;
@@ -566,55 +631,63 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float rs = 0.f;
       if (valid) rs = (MODE == SIM_MOCO) ? p.rowstat[ui.lrow0 + row_l] : p.rowstat[a_glob];
       for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
-        if ((gt & 1) != wg) continue;
+        if ((gt & 1) != pair) continue;
         const int st = gt % NSTAGE;
+        SSVB_TP(0);  // loop overhead / other
         if (MODE != SIM_MOCO) mbar_wait(&b_full[st], (gt / NSTAGE) & 1);  // column stats landed with the B tile
-        mbar_wait(&s_full[wg], (gt >> 1) & 1);
+        SSVB_TP(1);  // wait b_full
+        mbar_wait(&s_full[pair], (gt >> 1) & 1);
         tc_fence_after();
-        const uint32_t t_s = tmem + tlane + C::T_S + wg * BN;
-        uint32_t sv[4][32];
+        SSVB_TP(2);  // wait s_full
+        const uint32_t t_s = tmem + tlane + C::T_S + pair * BN + half * 64;
+        uint32_t sv[2][32];
 #ifndef SSVB_DBG_NOLD
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) tmem_ld_x32(t_s + cc * 32, sv[cc]);
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) tmem_ld_wait_regs(sv[cc]);
+        tmem_ld_x32(t_s, sv[0]);
+        tmem_ld_x32(t_s + 32, sv[1]);
+        tmem_ld_wait_regs(sv[0]);
+        tmem_ld_wait_regs(sv[1]);
 #else
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sv[cc][i] = __float_as_uint(1e-3f * (i + cc + lane));
+        for (int i = 0; i < 32; ++i) { sv[0][i] = __float_as_uint(1e-3f * (i + lane)); sv[1][i] = sv[0][i]; }
 #endif
-        // the whole S tile is in registers: give the buffer back so S(t+2) can be issued right away
+        // this half of the S tile is in registers: give the buffer back so S(t+2) can be issued right away
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[wg]);
-        const int j0 = t * BN;
-        const bool special = (MODE != SIM_MOCO) && (j0 < ui.g0 + 128) && (j0 + BN > ui.g0);
-        const uint32_t t_w = tmem + tlane + C::T_W + wg * 64;
-        const void* cs = sC + st * C::CS_BYTES;
-        // all 128 weights of this row are computed and packed in registers BEFORE waiting for the W buffer, so the
-        // dZ GEMM of tile t-2 (which still reads that buffer) stays off this warp's critical path
-        uint32_t pk[4][16];
+        if (lane == 0) mbar_arrive(&s_empty[pair]);
+        SSVB_TP(3);  // tmem loads + release
+        const int j0 = t * BN + half * 64;
+        const bool special = (MODE != SIM_MOCO) && (j0 < ui.g0 + 128) && (j0 + 64 > ui.g0);
+        const uint32_t t_w = tmem + tlane + C::T_W + pair * 64 + half * 32;
+        const uint8_t* cs = sC + st * C::CS_BYTES + half * 64 * 4;
+        constexpr int CSTEP = 32 * 4;
+        // first 32 weights are computed before waiting for the W buffer (dZ GEMM of tile t-2 may still read it)
+        uint32_t pk[16];
         if (special)
-          bwd_weights<MODE, true>(sv, pk, p, a_glob, j0, rs, cs);
+          bwd_weights32<MODE, true>(sv[0], pk, p, a_glob, j0, rs, cs);
         else
-          bwd_weights<MODE, false>(sv, pk, p, a_glob, j0, rs, cs);
-        mbar_wait(&w_empty[wg], ((gt >> 1) & 1) ^ 1);
+          bwd_weights32<MODE, false>(sv[0], pk, p, a_glob, j0, rs, cs);
+        SSVB_TP(4);  // first 32 weights
+        mbar_wait(&w_empty[pair], ((gt >> 1) & 1) ^ 1);
         tc_fence_after();
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) tmem_st_x16(t_w + cc * 16, pk[cc]);
+        SSVB_TP(5);  // wait w_empty
+        tmem_st_x16(t_w, pk);
+        if (special)
+          bwd_weights32<MODE, true>(sv[1], pk, p, a_glob, j0 + 32, rs, cs + CSTEP);
+        else
+          bwd_weights32<MODE, false>(sv[1], pk, p, a_glob, j0 + 32, rs, cs + CSTEP);
+        tmem_st_x16(t_w + 16, pk);
+        SSVB_TP(6);  // second 32 weights + stores issued
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&w_full[wg]);
+        if (lane == 0) mbar_arrive(&w_full[pair]);
+        SSVB_TP(7);  // st drain + arrive
       }
-      // ---- epilogue: this warpgroup drains DP/2 accumulator columns of the finished row block
+      // ---- epilogue: the four warpgroups drain DP/4 accumulator columns each (DP = 64: only two of them have work)
       mbar_wait(dz_full, ucount & 1);
       tc_fence_after();
-      constexpr int CPW = DP / 2;  // columns per warpgroup
-#pragma unroll
-      for (int cc = 0; cc < CPW / 32; ++cc) {
-        const int col0 = wg * CPW + cc * 32;
+      if (DP == 128 || wgi < 2) {
+        const int col0 = wgi * 32;
         uint32_t v[32];
         tmem_ld_x32(tmem + tlane + C::T_DZ + col0, v);
         tmem_ld_wait_regs(v);
@@ -638,6 +711,10 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(dz_empty);
     }
+#ifdef SSVB_DBG_TIMING
+    if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0)
+      for (int i = 0; i < 8; ++i) p.dbg[i] = static_cast<unsigned long long>(_t_acc[i]);
+#endif
   }
   tc_fence_before();
   __syncthreads();
