@@ -64,9 +64,16 @@ __global__ void sk_max_final_kernel(const float* part, int n, float* out) {
 __global__ void sk_alpha_kernel(const float* __restrict__ upart, int grid, int kpad, int k, float* __restrict__ alpha) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= k) return;
-  float u = 0.f;
-  for (int g = 0; g < grid; ++g) u += upart[static_cast<size_t>(g) * kpad + c];
-  alpha[c] = (1.f / static_cast<float>(k)) / u;
+  float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;  // fixed summation order, 4 loads in flight
+  int g = 0;
+  for (; g + 4 <= grid; g += 4) {
+    u0 += upart[static_cast<size_t>(g) * kpad + c];
+    u1 += upart[static_cast<size_t>(g + 1) * kpad + c];
+    u2 += upart[static_cast<size_t>(g + 2) * kpad + c];
+    u3 += upart[static_cast<size_t>(g + 3) * kpad + c];
+  }
+  for (; g < grid; ++g) u0 += upart[static_cast<size_t>(g) * kpad + c];
+  alpha[c] = (1.f / static_cast<float>(k)) / ((u0 + u1) + (u2 + u3));
 }
 
 // PHASE 0: u_k = sum_b E_bk                     (beta uniform: the reference's Q / sum(Q) scalar cancels)
@@ -152,6 +159,102 @@ __global__ void sk_pass_kernel(const float* __restrict__ s, int64_t b, int k, in
   }
 }
 
+// Fast path (K <= 3072, K % 4 == 0, 16-byte aligned rows): one warp per row, the whole row lives in registers
+// (24 float4 per lane, all loads issued up front -> 12 KB in flight per warp), column sums accumulate in registers
+// across the rows of a warp and are combined across the 8 warps of the block in a fixed order through shared memory.
+constexpr int kSkNV = 24;
+template <int PHASE>
+__global__ void __launch_bounds__(256, 1)
+sk_rowreg_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, float inv_eps_log2e,
+                 const float* __restrict__ smax, const float* __restrict__ alpha, float* __restrict__ upart, int kpad,
+                 float* __restrict__ codes, int64_t ldc) {
+  extern __shared__ float sk_smem[];  // [kpad] alpha, then (PHASE != 2) [8][kpad] per-warp column sums
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int k4 = k >> 2;
+  float* alpha_s = sk_smem;
+  if (PHASE != 0) {
+    for (int c = threadIdx.x; c < k; c += blockDim.x) alpha_s[c] = alpha[c];
+    __syncthreads();
+  }
+  const float shift = smax[0] * inv_eps_log2e;
+  const float inv_b = 1.f / static_cast<float>(b);
+  float4 acc[kSkNV];
+#pragma unroll
+  for (int j = 0; j < kSkNV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * nwarp + w; r < b; r += static_cast<int64_t>(gridDim.x) * nwarp) {
+    const float4* row = reinterpret_cast<const float4*>(s + r * ld);
+    float4 e[kSkNV];
+#pragma unroll
+    for (int j = 0; j < kSkNV; ++j) {
+      const int c4 = lane + 32 * j;
+      e[j] = (c4 < k4) ? __ldg(row + c4) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < kSkNV; ++j) {
+      e[j].x = ex2f(fmaf(e[j].x, inv_eps_log2e, -shift));
+      e[j].y = ex2f(fmaf(e[j].y, inv_eps_log2e, -shift));
+      e[j].z = ex2f(fmaf(e[j].z, inv_eps_log2e, -shift));
+      e[j].w = ex2f(fmaf(e[j].w, inv_eps_log2e, -shift));
+      if (PHASE != 0) {
+        const int c4 = lane + 32 * j;
+        if (c4 < k4) {
+          const float4 a = reinterpret_cast<const float4*>(alpha_s)[c4];
+          v += (e[j].x * a.x + e[j].y * a.y) + (e[j].z * a.z + e[j].w * a.w);
+        }
+      }
+    }
+    if (PHASE == 0) {
+#pragma unroll
+      for (int j = 0; j < kSkNV; ++j) { acc[j].x += e[j].x; acc[j].y += e[j].y; acc[j].z += e[j].z; acc[j].w += e[j].w; }
+    } else {
+      v = warp_sum(v);
+      if (PHASE == 1) {
+        const float beta = inv_b / v;
+#pragma unroll
+        for (int j = 0; j < kSkNV; ++j) {
+          acc[j].x = fmaf(e[j].x, beta, acc[j].x); acc[j].y = fmaf(e[j].y, beta, acc[j].y);
+          acc[j].z = fmaf(e[j].z, beta, acc[j].z); acc[j].w = fmaf(e[j].w, beta, acc[j].w);
+        }
+      } else {
+        const float iv = 1.f / v;
+        float4* out = reinterpret_cast<float4*>(codes + r * ldc);
+#pragma unroll
+        for (int j = 0; j < kSkNV; ++j) {
+          const int c4 = lane + 32 * j;
+          if (c4 < k4) {
+            const float4 a = reinterpret_cast<const float4*>(alpha_s)[c4];
+            out[c4] = make_float4(e[j].x * a.x * iv, e[j].y * a.y * iv, e[j].z * a.z * iv, e[j].w * a.w * iv);
+          }
+        }
+      }
+    }
+  }
+  if (PHASE != 2) {
+    float* mine = sk_smem + kpad + w * kpad;
+#pragma unroll
+    for (int j = 0; j < kSkNV; ++j) {
+      const int c4 = lane + 32 * j;
+      if (c4 < k4) reinterpret_cast<float4*>(mine)[c4] = acc[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < k; c += blockDim.x) {
+      float t = 0.f;
+      for (int ww = 0; ww < nwarp; ++ww) t += sk_smem[kpad + ww * kpad + c];
+      upart[static_cast<size_t>(blockIdx.x) * kpad + c] = t;
+    }
+  }
+}
+
+template <int PHASE>
+int sk_launch_fast(int grid, size_t smem, cudaStream_t s, const float* scores, int64_t b, int k, int64_t ld, float iel,
+                   const SkWs& ws, float* codes, int64_t ldc) {
+  SSVB_CUDA(cudaFuncSetAttribute(sk_rowreg_kernel<PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  sk_rowreg_kernel<PHASE><<<grid, 256, smem, s>>>(scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart, ws.kpad, codes, ldc);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
 template <int PHASE>
 int sk_launch(bool regacc, int grid, int threads, size_t smem, cudaStream_t s, const float* scores, int64_t b, int k,
               int64_t ld, float iel, const SkWs& ws, float* codes, int64_t ldc) {
@@ -185,26 +288,33 @@ int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, f
   if (smem > 200 * 1024) return SSVB_ERR_UNSUPPORTED;
   const int threads = nwarp * 32;
   const bool regacc = (nwarp == 8) && (k <= static_cast<int64_t>(kSkJ) * threads);
+  const bool fast = (k % 4 == 0) && (k <= 128 * kSkNV) && (ld_scores % 4 == 0) && (ld_codes % 4 == 0) &&
+                    !(reinterpret_cast<uintptr_t>(scores) & 15) && !(reinterpret_cast<uintptr_t>(codes) & 15);
+  const size_t smem_fast = static_cast<size_t>(9) * ws.kpad * 4;
+  const int fgrid = num_sms();  // one 8-warp CTA per SM; partial rows [fgrid x kpad]
   sk_max_kernel<<<ws.grid, 256, 0, s>>>(scores, b, kk, ld_scores, ws.smax_part);
   SSVB_LAUNCH_CHECK();
   sk_max_final_kernel<<<1, 32, 0, s>>>(ws.smax_part, ws.grid, ws.smax);
   SSVB_LAUNCH_CHECK();
-  const unsigned agrid = static_cast<unsigned>(ceil_div(k, 256));
+  const unsigned agrid = static_cast<unsigned>(ceil_div(k, 256));  // (alpha / fill kernels: 256 columns per CTA)
   if (n_iters <= 0) {
     // no iterations: codes = E / rowsum(E)  (alpha = 1)
     fill_kernel<<<agrid, 256, 0, s>>>(ws.alpha, k, 1.f);
     SSVB_LAUNCH_CHECK();
   } else {
-    SSVB_TRY(sk_launch<0>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
-    sk_alpha_kernel<<<agrid, 256, 0, s>>>(ws.upart, ws.grid, ws.kpad, kk, ws.alpha);
+    if (fast) SSVB_TRY(sk_launch_fast<0>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+    else SSVB_TRY(sk_launch<0>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+    sk_alpha_kernel<<<agrid, 256, 0, s>>>(ws.upart, fast ? fgrid : ws.grid, ws.kpad, kk, ws.alpha);
     SSVB_LAUNCH_CHECK();
     for (int it = 1; it < n_iters; ++it) {
-      SSVB_TRY(sk_launch<1>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
-      sk_alpha_kernel<<<agrid, 256, 0, s>>>(ws.upart, ws.grid, ws.kpad, kk, ws.alpha);
+      if (fast) SSVB_TRY(sk_launch_fast<1>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+      else SSVB_TRY(sk_launch<1>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+      sk_alpha_kernel<<<agrid, 256, 0, s>>>(ws.upart, fast ? fgrid : ws.grid, ws.kpad, kk, ws.alpha);
       SSVB_LAUNCH_CHECK();
     }
   }
-  SSVB_TRY(sk_launch<2>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+  if (fast) SSVB_TRY(sk_launch_fast<2>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+  else SSVB_TRY(sk_launch<2>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
   return SSVB_OK;
 }
 size_t sinkhorn_ws_bytes(int64_t k) { return sk_ws(nullptr, k).bytes; }
