@@ -76,9 +76,11 @@ int ssvb_ntxent_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
  *     Stage 1 (prep):     normalise the local rows of both views into this rank's slot of `zhat_all`
  *                         (bf16 [mpad x dpad], mpad = ssvb_ntxent_mpad(world*L)) + local positives.
  *                         -> caller all-gathers the slots (2L*dpad bf16 per rank).
- *     Stage 2 (rows_fwd): local rows against ALL columns -> log2-domain LSE of the local rows
- *                         (`stat_local`, [2L]) + local loss sum (caller all-reduces `loss_sum` and
- *                         divides by 2*world*L; all-gathers stat_local into stat_all [world*2L]).
+ *     Stage 2 (rows_fwd): local rows against ALL columns -> `stat_local` [2][2L]: the log2-domain LSE of
+ *                         the local rows, then their per-row loss terms (lse - pos, natural log); also the
+ *                         local loss sum.  ONE all-gather of stat_local into stat_all [world][2][2L] gives
+ *                         every rank both the column statistics for backward and (summing the term halves,
+ *                         divided by 2*world*L) the global loss - no separate all-reduce.
  *     Stage 3 (rows_bwd): complete gradient of the local rows; no reduce-scatter of gradients is
  *                         needed because W_ab = P_ab + P_ba is computable from s_ab, lse_a, lse_b.
  * ------------------------------------------------------------------------------------- */
@@ -92,9 +94,22 @@ int ssvb_ntxent_dist_prep(const float* zi, const float* zj, int64_t n_local, int
 int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
                               int normalize, float temperature, const float* pos_local, float* stat_local,
                               float* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
+/* Fused compute + all-gather over NVLink peer memory (no NCCL on the data path): `peer_zhat` / `peer_stat` are
+ * DEVICE arrays of `world` peer-mapped base pointers (every rank's gathered buffer, e.g. torch symmetric memory).
+ * prep_push stores each normalised bf16 row into this rank's slot of EVERY rank's zhat buffer; rows_fwd_push stores
+ * this rank's [lse | term] block into slot `rank` of every rank's [world][2][2L] buffer.  The caller separates the
+ * stages with a barrier on the same peer group.  dist_loss sums the gathered per-row terms into the global loss. */
+int ssvb_ntxent_dist_prep_push(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                               int64_t ld_zj, int normalize, int64_t world, int64_t rank, void* const* peer_zhat,
+                               float* inv_norm_local, float* pos_local, void* stream);
+int ssvb_ntxent_dist_rows_fwd_push(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
+                                   int normalize, float temperature, const float* pos_local,
+                                   void* const* peer_stat, float* loss_sum, void* workspace,
+                                   size_t workspace_bytes, void* stream);
+int ssvb_ntxent_dist_loss(const float* stat_all, int64_t world, int64_t n_local, float* loss, void* stream);
 int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
                               int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
-                              const void* zhat_all, const float* stat_all /* [world*2L] */,
+                              const void* zhat_all, const float* stat_all /* [world][2][2L] */,
                               const float* inv_norm_local, const float* grad_out, float* dzi, float* dzj,
                               int64_t ld_dzi, int64_t ld_dzj, void* workspace, size_t workspace_bytes,
                               void* stream);

@@ -295,19 +295,44 @@ int ssvb_ntxent_dist_prep(const float* zi, const float* zj, int64_t n_local, int
   return SSVB_OK;
 }
 
+namespace {
+int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d, int normalize,
+                  float temperature, const float* pos_local, float* stat_local, float* const* peer_stat,
+                  float* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
+}
 int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
                               int normalize, float temperature, const float* pos_local, float* stat_local,
                               float* loss_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!stat_local) return SSVB_ERR_INVALID;
+  return rows_fwd_impl(zhat_all, world, rank, n_local, d, normalize, temperature, pos_local, stat_local, nullptr,
+                       loss_sum, workspace, workspace_bytes, stream);
+}
+int ssvb_ntxent_dist_rows_fwd_push(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
+                                   int normalize, float temperature, const float* pos_local,
+                                   void* const* peer_stat, float* loss_sum, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  if (!peer_stat) return SSVB_ERR_INVALID;
+  return rows_fwd_impl(zhat_all, world, rank, n_local, d, normalize, temperature, pos_local, nullptr,
+                       reinterpret_cast<float* const*>(peer_stat), loss_sum, workspace, workspace_bytes, stream);
+}
+namespace {
+int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d, int normalize,
+                  float temperature, const float* pos_local, float* stat_local, float* const* peer_stat,
+                  float* loss_sum, void* workspace, size_t workspace_bytes, void* stream) {
   SSVB_TRY(check_device_sm100());
   SSVB_TRY(dist_check(world, rank, n_local));
   NtxPlan pl;
   SSVB_TRY(make_plan(pl, n_local * world, d, normalize, temperature));
-  if (!zhat_all || !pos_local || !stat_local || !loss_sum || !workspace) return SSVB_ERR_INVALID;
+  if (!zhat_all || !pos_local || !loss_sum || !workspace) return SSVB_ERR_INVALID;
   if (workspace_bytes < ssvb_ntxent_dist_workspace_bytes(world, n_local, d)) return SSVB_ERR_WORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t lr = 2 * n_local;
   WsLayout ws = ws_layout(workspace, lr, ceil_div(lr, 128), pl.m, pl.dpad);
   SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
+  // local outputs either go to the caller's [2][2L] block or (push mode) into slot `rank` of every peer's buffer
+  float* lse_out = stat_local;
+  float* term_out = stat_local ? stat_local + lr : nullptr;
+  const size_t peer_off = static_cast<size_t>(rank) * 2 * lr;
   SimParams p;
   fill_sim_params_rows(p, pl, 1, lr, rank * lr, 0);
   plan_chunks(p, 256, 4);
@@ -321,27 +346,86 @@ int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t world, int64_t rank,
   if (pl.mode == SIM_NTX_FIXED)
     lse_finalize_kernel<SIM_NTX_FIXED><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 2 * p.nchunks, p.part_stride,
                                                           static_cast<int>(lr), pos_local, pl.c, pl.shift,
-                                                          ws.dacc /*scratch*/, stat_local, ws.block_sums, ws.counter,
-                                                          1.f, loss_sum);
+                                                          ws.dacc /*scratch*/, lse_out, ws.block_sums, ws.counter,
+                                                          1.f, loss_sum, term_out, peer_stat, static_cast<int>(world),
+                                                          peer_off);
   else
     lse_finalize_kernel<SIM_NTX_ONLINE><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 2 * p.nchunks, p.part_stride,
                                                            static_cast<int>(lr), pos_local, pl.c, pl.shift,
-                                                           ws.dacc /*scratch*/, stat_local, ws.block_sums,
-                                                           ws.counter, 1.f, loss_sum);
+                                                           ws.dacc /*scratch*/, lse_out, ws.block_sums,
+                                                           ws.counter, 1.f, loss_sum, term_out, peer_stat,
+                                                           static_cast<int>(world), peer_off);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+}  // namespace
+
+// Fused normalise + all-gather: like dist_prep, but every bf16 row goes to the same slot of EVERY rank's gathered
+// matrix through `peer_zhat` (a DEVICE array of `world` peer-mapped base pointers, e.g. torch symmetric memory).
+int ssvb_ntxent_dist_prep_push(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                               int64_t ld_zj, int normalize, int64_t world, int64_t rank, void* const* peer_zhat,
+                               float* inv_norm_local, float* pos_local, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(dist_check(world, rank, n_local));
+  NtxPlan pl;
+  SSVB_TRY(make_plan(pl, n_local * world, d, normalize, 1.f));
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  if (!peer_zhat || !inv_norm_local || !pos_local) return SSVB_ERR_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t row0 = rank * 2 * n_local;
+  pair_prep_push_kernel<<<static_cast<unsigned>(ceil_div(n_local, 8)), 256, 0, s>>>(
+      zi, zj, static_cast<int>(n_local), static_cast<int>(d), ld_zi, ld_zj, normalize, peer_zhat,
+      static_cast<int>(world), row0, row0 + n_local, static_cast<int>(pl.dpad), inv_norm_local,
+      inv_norm_local + n_local, pos_local, pos_local + n_local);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+// global loss from the gathered per-row terms: loss = sum(stat_all[:, 1, :]) / (2 * world * L); fixed order
+namespace {
+__global__ void dist_loss_kernel(const float* __restrict__ g, int world, int lr, float scale, float* __restrict__ out) {
+  __shared__ float red[32];
+  float v = 0.f;
+  const int total = world * lr;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int r = i / lr;
+    v += g[static_cast<size_t>(r) * 2 * lr + lr + (i - r * lr)];
+  }
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) out[0] = t * scale;
+  }
+}
+}  // namespace
+int ssvb_ntxent_dist_loss(const float* stat_all, int64_t world, int64_t n_local, float* loss, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (!stat_all || !loss || world <= 0 || n_local <= 0) return SSVB_ERR_INVALID;
+  dist_loss_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      stat_all, static_cast<int>(world), static_cast<int>(2 * n_local), 1.f / static_cast<float>(2 * world * n_local),
+      loss);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
 
 namespace {
 // lse2 (all rows) -> the column statistic the backward kernel consumes, with finite padding
-__global__ void dist_stat_kernel(const float* __restrict__ lse2, float* __restrict__ stat, int m, int mpad, int fixed,
-                                 float shift) {
+// gathered layout: [world][2][2L] (per rank: 2L lse2 values, then 2L per-row loss terms)
+__global__ void dist_stat_kernel(const float* __restrict__ gathered, float* __restrict__ stat, int m, int mpad, int lr,
+                                 int fixed, float shift) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= mpad) return;
-  if (i < m)
-    stat[i] = fixed ? exp2f(shift - lse2[i]) : lse2[i];
-  else
+  if (i < m) {
+    const int r = i / lr;
+    const float l2 = gathered[static_cast<size_t>(r) * 2 * lr + (i - r * lr)];
+    stat[i] = fixed ? exp2f(shift - l2) : l2;
+  } else {
     stat[i] = fixed ? 0.f : 1e30f;
+  }
 }
 }  // namespace
 
@@ -366,7 +450,7 @@ int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local,
   // column statistics for all M rows live in the (otherwise unused here) partial buffer
   float* stat = ws.part_m;
   dist_stat_kernel<<<static_cast<unsigned>(ceil_div(pl.mpad, 256)), 256, 0, s>>>(
-      stat_all, stat, static_cast<int>(pl.m), static_cast<int>(pl.mpad), pl.mode == SIM_NTX_FIXED, pl.shift);
+      stat_all, stat, static_cast<int>(pl.m), static_cast<int>(pl.mpad), static_cast<int>(lr), pl.mode == SIM_NTX_FIXED, pl.shift);
   SSVB_LAUNCH_CHECK();
 
   SimParams p;

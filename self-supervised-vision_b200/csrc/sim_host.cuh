@@ -171,6 +171,50 @@ static __global__ void pair_prep_kernel(const float* __restrict__ xi, const floa
   }
 }
 
+// pair_prep + fused all-gather: every bf16 row is stored into the same slot of EVERY rank's gathered matrix through
+// peer-mapped pointers (NVLink stores), so no separate collective is needed (a barrier publishes the data).
+static __global__ void pair_prep_push_kernel(const float* __restrict__ xi, const float* __restrict__ xj, int n, int d,
+                                             int64_t ldi, int64_t ldj, int normalize, void* const* __restrict__ peers,
+                                             int world, int64_t row_i, int64_t row_j, int dpad,
+                                             float* __restrict__ inv_i, float* __restrict__ inv_j,
+                                             float* __restrict__ pos_i, float* __restrict__ pos_j) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float* ri = xi + static_cast<int64_t>(warp) * ldi;
+  const float* rj = xj + static_cast<int64_t>(warp) * ldj;
+  const int k = lane * 4;  // dpad <= 128: one float4 per lane
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (k < d) {
+    a = *reinterpret_cast<const float4*>(ri + k);
+    b = *reinterpret_cast<const float4*>(rj + k);
+  }
+  float si = warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w);
+  float sj = warp_sum(b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w);
+  float ivi = 1.f, ivj = 1.f;
+  if (normalize) {
+    ivi = 1.f / fmaxf(sqrtf(si), 1e-12f);
+    ivj = 1.f / fmaxf(sqrtf(sj), 1e-12f);
+  }
+  __nv_bfloat162 i01 = __floats2bfloat162_rn(a.x * ivi, a.y * ivi), i23 = __floats2bfloat162_rn(a.z * ivi, a.w * ivi);
+  __nv_bfloat162 j01 = __floats2bfloat162_rn(b.x * ivj, b.y * ivj), j23 = __floats2bfloat162_rn(b.z * ivj, b.w * ivj);
+  const float2 fi01 = __bfloat1622float2(i01), fi23 = __bfloat1622float2(i23);
+  const float2 fj01 = __bfloat1622float2(j01), fj23 = __bfloat1622float2(j23);
+  float dot = warp_sum(fi01.x * fj01.x + fi01.y * fj01.y + fi23.x * fj23.x + fi23.y * fj23.y);
+  if (k < dpad) {
+    uint2 vi, vj;
+    vi.x = *reinterpret_cast<uint32_t*>(&i01); vi.y = *reinterpret_cast<uint32_t*>(&i23);
+    vj.x = *reinterpret_cast<uint32_t*>(&j01); vj.y = *reinterpret_cast<uint32_t*>(&j23);
+    for (int pr = 0; pr < world; ++pr) {
+      __nv_bfloat16* base = static_cast<__nv_bfloat16*>(peers[pr]);
+      *reinterpret_cast<uint2*>(base + (row_i + warp) * dpad + k) = vi;
+      *reinterpret_cast<uint2*>(base + (row_j + warp) * dpad + k) = vj;
+    }
+  }
+  if (lane == 0) {
+    inv_i[warp] = ivi; inv_j[warp] = ivj; pos_i[warp] = dot; pos_j[warp] = dot;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // deterministic block-sum -> scalar: every block writes its partial, the last block to finish adds
 // them in index order (no float atomics -> run-to-run bit-stable loss).
@@ -223,7 +267,9 @@ template <int MODE>
 __global__ void lse_finalize_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l, int nparts,
                                     int stride, int nrows, const float* __restrict__ pos, float c, float shift,
                                     float* __restrict__ stat, float* __restrict__ lse2_out,
-                                    float* block_sums, unsigned int* counter, float loss_scale, float* loss) {
+                                    float* block_sums, unsigned int* counter, float loss_scale, float* loss,
+                                    float* __restrict__ term_out = nullptr, float* const* __restrict__ peer_stat = nullptr,
+                                    int world = 0, size_t peer_off = 0) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   float term = 0.f;
   if (r < nrows) {
@@ -246,6 +292,14 @@ __global__ void lse_finalize_kernel(const float* __restrict__ part_m, const floa
     stat[r] = st;
     if (lse2_out) lse2_out[r] = lse2;
     term = (lse2 - p2) * SSVB_LN2;
+    if (term_out) term_out[r] = term;
+    if (peer_stat) {  // fused all-gather: store this rank's [lse2 | term] block straight into every peer's buffer
+      for (int pr = 0; pr < world; ++pr) {
+        float* dst = peer_stat[pr] + peer_off;
+        dst[r] = lse2;
+        dst[nrows + r] = term;
+      }
+    }
   }
   const float bt = block_sum_256(term);
   grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false);

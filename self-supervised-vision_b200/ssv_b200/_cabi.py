@@ -52,6 +52,8 @@ def parse_header(path: str = HEADER_PATH):
     return protos
 
 
+c_void_p = ctypes.c_void_p  # re-exported for callers that pass raw device addresses
+
 _lib = None
 
 

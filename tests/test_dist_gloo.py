@@ -42,8 +42,10 @@ class EmulatedStages:
         idx = torch.arange(lr)
         s[idx, rank * lr + idx] = float("-inf")
         lse = torch.logsumexp(s, 1)
-        stat_local.copy_(lse.float())
-        loss_sum.copy_((lse - pos_local.double() / temperature).sum().float())
+        term = lse - pos_local.double() / temperature
+        stat_local[0].copy_(lse.float())     # stat_local: [2][2L] = LSE, then per-row loss terms
+        stat_local[1].copy_(term.float())
+        loss_sum.copy_(term.sum().float())
 
     def rows_bwd(self, zi, zj, normalize, temperature, world, rank, zhat_all, stat_all, inv_local, grad_out, dzi, dzj):
         n = zi.shape[0]
@@ -52,7 +54,8 @@ class EmulatedStages:
         z = zhat_all.double()
         zl = z[rank * lr:(rank + 1) * lr]
         s = zl @ z.t() / temperature
-        w = torch.exp(s - stat_all.double()[rank * lr:(rank + 1) * lr, None]) + torch.exp(s - stat_all.double()[None, :])
+        lse_all = stat_all.double()[:, 0, :].reshape(-1)   # gathered layout [world][2][2L]
+        w = torch.exp(s - lse_all[rank * lr:(rank + 1) * lr, None]) + torch.exp(s - lse_all[None, :])
         idx = torch.arange(lr)
         w[idx, rank * lr + idx] = 0.0
         partner = rank * lr + (idx + n) % lr

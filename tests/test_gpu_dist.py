@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, n_local, d, normalize, tau, out):
+def _worker(rank, world, port, n_local, d, normalize, tau, out, transport="auto"):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "self-supervised-vision_b200")]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -24,16 +24,20 @@ def _worker(rank, world, port, n_local, d, normalize, tau, out):
     zj = torch.randn(n_local, d, generator=g)
     a = zi.cuda().requires_grad_(True)
     b = zj.cuda().requires_grad_(True)
-    loss = DistributedSimclrLoss(normalize, tau)(a, b)
-    loss.backward()
+    fn = DistributedSimclrLoss(normalize, tau, transport=transport)
+    for _ in range(3):  # several steps: exercises the double-buffered peer transport
+        a.grad = None; b.grad = None
+        loss = fn(a, b)
+        loss.backward()
     torch.cuda.synchronize()
     out[rank] = (loss.item(), a.grad.cpu().numpy(), b.grad.cpu().numpy(), zi.numpy(), zj.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
 @pytest.mark.parametrize("n_local,d,normalize,tau", [(192, 128, True, 0.5), (1000, 64, True, 0.07), (256, 128, True, 0.02)])
-def test_dist_ntxent_vs_oracle(n_local, d, normalize, tau):
+def test_dist_ntxent_vs_oracle(n_local, d, normalize, tau, transport):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     from oracle import ssl_oracle as O
@@ -41,7 +45,7 @@ def test_dist_ntxent_vs_oracle(n_local, d, normalize, tau):
     mgr = mp.Manager()
     out = mgr.dict()
     port = 29700 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(world, port, n_local, d, normalize, tau, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n_local, d, normalize, tau, out, transport), nprocs=world, join=True)
     zi = np.concatenate([out[r][3] for r in range(world)])
     zj = np.concatenate([out[r][4] for r in range(world)])
     ref_loss, ref_dzi, ref_dzj = O.ntxent(zi, zj, normalize, tau)
