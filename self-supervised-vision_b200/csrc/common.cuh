@@ -31,6 +31,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// 16-bit staging format of the similarity operands: fp16 when the rows are L2-normalised (|x| <= 1: three more
+// mantissa bits than bf16 and it allows fp16 accumulators), bf16 for raw inputs (range safety).
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v, bool f16) {
+  if (f16) {
+    float lo, hi;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n"
+        : "=f"(lo), "=f"(hi) : "r"(v));
+    return make_float2(lo, hi);
+  }
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -197,8 +217,10 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo_by
 }
 
 // 32-bit instruction descriptor: bf16 x bf16 -> fp32, dense.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+// ab_fmt: operand format of A and B (1 = bf16, 0 = fp16); accumulator fp32 (c_format bits [4,6) = 1).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, int ab_fmt = 1) {
+  return (1u << 4) | (static_cast<uint32_t>(ab_fmt) << 7) | (static_cast<uint32_t>(ab_fmt) << 10) |
+         (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }

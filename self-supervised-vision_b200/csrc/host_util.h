@@ -53,7 +53,8 @@ inline PFN_encodeTiled get_encode_fn() {
 
 // bf16 row-major [rows x cols], leading dimension ld (elements, ld*2 % 16 == 0).
 // Box = 64 columns (128 B, SWIZZLE_128B) x box_rows rows; out-of-bounds reads are zero-filled.
-inline int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+inline int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                          bool fp16 = false) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return SSVB_ERR_DRIVER;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return SSVB_ERR_ALIGNMENT;
@@ -61,14 +62,15 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  const CUtensorMapDataType dt = fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
     // the driver call needs a context bound to THIS thread; autograd's backward thread may not have touched the
     // runtime yet.  cudaFree(0) binds the primary context of the current device, then retry once.
     cudaFree(nullptr);
-    r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    r = fn(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }

@@ -185,7 +185,7 @@ int ssvb_moco_fwd(const float* query, const float* keys, const float* queue, con
   if (npad > n) SSVB_CUDA(cudaMemsetAsync(sv.qhat + n * dpad, 0, (npad - n) * dpad * sizeof(__nv_bfloat16), s));
   SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
   pair_prep_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(
-      query, keys, static_cast<int>(n), static_cast<int>(d), ld_q, ld_k, normalize, sv.qhat, nullptr,
+      query, keys, static_cast<int>(n), static_cast<int>(d), ld_q, ld_k, normalize, 0, sv.qhat, nullptr,
       static_cast<int>(dpad), sv.inv_q, sv.inv_k, sv.pos, nullptr);
   SSVB_LAUNCH_CHECK();
   const __nv_bfloat16* qb = nullptr;

@@ -16,6 +16,7 @@ namespace {
 struct NtxPlan {
   int64_t n_glob, m, mpad, d, dpad;
   int mode;
+  int normalize;
   float c, shift;
 };
 
@@ -29,6 +30,7 @@ int make_plan(NtxPlan& pl, int64_t n_glob, int64_t d, int normalize, float tempe
   pl.mpad = sim_mpad(pl.m);
   pl.d = d;
   pl.dpad = sim_dpad(d);
+  pl.normalize = normalize ? 1 : 0;
   pl.c = SSVB_LOG2E / temperature;
   pl.shift = pl.c;
   // unit-norm rows bound |s| <= 1/tau: a constant shift replaces the running max as long as
@@ -107,8 +109,7 @@ __global__ void ntx_grad_finish_kernel(const float* __restrict__ zi, const float
   if (k < d) {
     const float4 acc = *reinterpret_cast<const float4*>(dacc + static_cast<int64_t>(lrow) * ld_dacc + k);
     const uint2 pz = *reinterpret_cast<const uint2*>(zhat + static_cast<int64_t>(partner) * dpad + k);
-    const float2 p01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pz.x));
-    const float2 p23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pz.y));
+    const float2 p01 = unpack_h2(pz.x, normalize != 0), p23 = unpack_h2(pz.y, normalize != 0);  // fp16 iff normalised
     const float4 zz = *reinterpret_cast<const float4*>(z + k);
     g[0] = (acc.x - 2.f * p01.x) * scale;
     g[1] = (acc.y - 2.f * p01.y) * scale;
@@ -133,6 +134,7 @@ int check_rows(const void* p, int64_t ld) {
 
 void fill_sim_params_rows(SimParams& p, const NtxPlan& pl, int nseg, int64_t seg_rows, int64_t s0, int64_t s1) {
   p = SimParams{};
+  p.opf16 = pl.normalize ? 1 : 0;  // fp16 staging for unit-norm rows (3 more mantissa bits than bf16), bf16 otherwise
   p.nseg = nseg;
   p.seg_rows = static_cast<int>(seg_rows);
   p.seg_start[0] = static_cast<int>(s0);
@@ -181,7 +183,8 @@ int ssvb_ntxent_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   {
     const int wpb = 8;
     pair_prep_kernel<<<static_cast<unsigned>(ceil_div(n, wpb)), wpb * 32, 0, s>>>(
-        zi, zj, static_cast<int>(n), static_cast<int>(d), ld_zi, ld_zj, normalize, sv.zhat, sv.zhat + n * pl.dpad,
+        zi, zj, static_cast<int>(n), static_cast<int>(d), ld_zi, ld_zj, normalize, normalize ? 1 : 0, sv.zhat,
+        sv.zhat + n * pl.dpad,
         static_cast<int>(pl.dpad), sv.inv_norm, sv.inv_norm + n, ws.pos, ws.pos + n);
     SSVB_LAUNCH_CHECK();
   }
@@ -288,7 +291,8 @@ int ssvb_ntxent_dist_prep(const float* zi, const float* zj, int64_t n_local, int
   const int64_t row0 = rank * 2 * n_local;
   const int wpb = 8;
   pair_prep_kernel<<<static_cast<unsigned>(ceil_div(n_local, wpb)), wpb * 32, 0, s>>>(
-      zi, zj, static_cast<int>(n_local), static_cast<int>(d), ld_zi, ld_zj, normalize, zh + row0 * pl.dpad,
+      zi, zj, static_cast<int>(n_local), static_cast<int>(d), ld_zi, ld_zj, normalize, normalize ? 1 : 0,
+      zh + row0 * pl.dpad,
       zh + (row0 + n_local) * pl.dpad, static_cast<int>(pl.dpad), inv_norm_local, inv_norm_local + n_local,
       pos_local, pos_local + n_local);
   SSVB_LAUNCH_CHECK();
@@ -375,7 +379,7 @@ int ssvb_ntxent_dist_prep_push(const float* zi, const float* zj, int64_t n_local
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t row0 = rank * 2 * n_local;
   pair_prep_push_kernel<<<static_cast<unsigned>(ceil_div(n_local, 8)), 256, 0, s>>>(
-      zi, zj, static_cast<int>(n_local), static_cast<int>(d), ld_zi, ld_zj, normalize, peer_zhat,
+      zi, zj, static_cast<int>(n_local), static_cast<int>(d), ld_zi, ld_zj, normalize, normalize ? 1 : 0, peer_zhat,
       static_cast<int>(world), row0, row0 + n_local, static_cast<int>(pl.dpad), inv_norm_local,
       inv_norm_local + n_local, pos_local, pos_local + n_local);
   SSVB_LAUNCH_CHECK();

@@ -36,9 +36,9 @@ inline void plan_chunks(SimParams& p, int BN, int min_tiles) {
   p.nchunks = static_cast<int>(ceil_div(p.col_tiles, p.tiles_per_chunk));
 }
 
-template <int KB, int MODE>
+template <int KB, int MODE, bool OPF16 = false>
 int launch_sim_fwd_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const SimParams& p, cudaStream_t s) {
-  auto kern = sim_fwd_kernel<KB, MODE>;
+  auto kern = sim_fwd_kernel<KB, MODE, OPF16>;
   constexpr int smem = FwdCfg<KB>::SMEM;
   SSVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int nunits = p.row_blocks * p.nchunks;
@@ -49,9 +49,9 @@ int launch_sim_fwd_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const SimPa
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
-template <int KB, int MODE>
+template <int KB, int MODE, bool OPF16 = false>
 int launch_sim_bwd_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const SimParams& p, cudaStream_t s) {
-  auto kern = sim_bwd_kernel<KB, MODE>;
+  auto kern = sim_bwd_kernel<KB, MODE, OPF16>;
   constexpr int smem = BwdCfg<KB>::SMEM;
   SSVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int nunits = p.row_blocks * p.nchunks;
@@ -67,13 +67,17 @@ int launch_sim_bwd_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const SimPa
 inline int launch_sim_fwd(int mode, const void* A, int64_t a_rows, const void* B, int64_t b_rows, int64_t dpad,
                           const SimParams& p, cudaStream_t s) {
   CUtensorMap tmA, tmB;
-  SSVB_TRY(make_tmap_bf16(&tmA, A, a_rows, dpad, dpad, 128));
-  SSVB_TRY(make_tmap_bf16(&tmB, B, b_rows, dpad, dpad, 256));
+  SSVB_TRY(make_tmap_bf16(&tmA, A, a_rows, dpad, dpad, 128, p.opf16 != 0));
+  SSVB_TRY(make_tmap_bf16(&tmB, B, b_rows, dpad, dpad, 256, p.opf16 != 0));
   const int KB = static_cast<int>(dpad / 64);
 #define SSVB_DISPATCH(KBV)                                                      \
   switch (mode) {                                                               \
-    case SIM_NTX_FIXED: return launch_sim_fwd_t<KBV, SIM_NTX_FIXED>(tmA, tmB, p, s);  \
-    case SIM_NTX_ONLINE: return launch_sim_fwd_t<KBV, SIM_NTX_ONLINE>(tmA, tmB, p, s); \
+    case SIM_NTX_FIXED:                                                         \
+      if (p.opf16) return launch_sim_fwd_t<KBV, SIM_NTX_FIXED, true>(tmA, tmB, p, s);                   \
+      return launch_sim_fwd_t<KBV, SIM_NTX_FIXED, false>(tmA, tmB, p, s);                               \
+    case SIM_NTX_ONLINE:                                                        \
+      if (p.opf16) return launch_sim_fwd_t<KBV, SIM_NTX_ONLINE, true>(tmA, tmB, p, s);                  \
+      return launch_sim_fwd_t<KBV, SIM_NTX_ONLINE, false>(tmA, tmB, p, s);                              \
     case SIM_MOCO: return launch_sim_fwd_t<KBV, SIM_MOCO>(tmA, tmB, p, s);      \
     default: return SSVB_ERR_INVALID;                                           \
   }
@@ -85,13 +89,17 @@ inline int launch_sim_fwd(int mode, const void* A, int64_t a_rows, const void* B
 inline int launch_sim_bwd(int mode, const void* A, int64_t a_rows, const void* B, int64_t b_rows, int64_t dpad,
                           const SimParams& p, cudaStream_t s) {
   CUtensorMap tmA, tmB;
-  SSVB_TRY(make_tmap_bf16(&tmA, A, a_rows, dpad, dpad, 128));
-  SSVB_TRY(make_tmap_bf16(&tmB, B, b_rows, dpad, dpad, 128));
+  SSVB_TRY(make_tmap_bf16(&tmA, A, a_rows, dpad, dpad, 128, p.opf16 != 0));
+  SSVB_TRY(make_tmap_bf16(&tmB, B, b_rows, dpad, dpad, 128, p.opf16 != 0));
   const int KB = static_cast<int>(dpad / 64);
 #define SSVB_DISPATCH(KBV)                                                      \
   switch (mode) {                                                               \
-    case SIM_NTX_FIXED: return launch_sim_bwd_t<KBV, SIM_NTX_FIXED>(tmA, tmB, p, s);  \
-    case SIM_NTX_ONLINE: return launch_sim_bwd_t<KBV, SIM_NTX_ONLINE>(tmA, tmB, p, s); \
+    case SIM_NTX_FIXED:                                                         \
+      if (p.opf16) return launch_sim_bwd_t<KBV, SIM_NTX_FIXED, true>(tmA, tmB, p, s);  \
+      return launch_sim_bwd_t<KBV, SIM_NTX_FIXED, false>(tmA, tmB, p, s);              \
+    case SIM_NTX_ONLINE:                                                        \
+      if (p.opf16) return launch_sim_bwd_t<KBV, SIM_NTX_ONLINE, true>(tmA, tmB, p, s); \
+      return launch_sim_bwd_t<KBV, SIM_NTX_ONLINE, false>(tmA, tmB, p, s);             \
     case SIM_MOCO: return launch_sim_bwd_t<KBV, SIM_MOCO>(tmA, tmB, p, s);      \
     default: return SSVB_ERR_INVALID;                                           \
   }
@@ -107,7 +115,7 @@ inline int launch_sim_bwd(int mode, const void* A, int64_t a_rows, const void* B
 // row dot product of the two bf16-rounded rows (`pos`, exactly what the tensor cores will see).
 // ---------------------------------------------------------------------------------------------------
 static __global__ void pair_prep_kernel(const float* __restrict__ xi, const float* __restrict__ xj, int n, int d,
-                                 int64_t ldi, int64_t ldj, int normalize, __nv_bfloat16* __restrict__ out_i,
+                                 int64_t ldi, int64_t ldj, int normalize, int f16, __nv_bfloat16* __restrict__ out_i,
                                  __nv_bfloat16* __restrict__ out_j, int dpad, float* __restrict__ inv_i,
                                  float* __restrict__ inv_j, float* __restrict__ pos_i, float* __restrict__ pos_j) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -141,25 +149,16 @@ static __global__ void pair_prep_kernel(const float* __restrict__ xi, const floa
   for (int it = 0; it < 2; ++it) {
     const int k = it * 128 + lane * 4;
     if (k < dpad) {
-      __nv_bfloat162 i01 = __floats2bfloat162_rn(a[it].x * ivi, a[it].y * ivi);
-      __nv_bfloat162 i23 = __floats2bfloat162_rn(a[it].z * ivi, a[it].w * ivi);
-      __nv_bfloat162 j01 = __floats2bfloat162_rn(b[it].x * ivj, b[it].y * ivj);
-      __nv_bfloat162 j23 = __floats2bfloat162_rn(b[it].z * ivj, b[it].w * ivj);
-      const float2 fi01 = __bfloat1622float2(i01), fi23 = __bfloat1622float2(i23);
-      const float2 fj01 = __bfloat1622float2(j01), fj23 = __bfloat1622float2(j23);
+      uint2 vi, vj;
+      vi.x = f16 ? pack_f16x2(a[it].x * ivi, a[it].y * ivi) : pack_bf16x2(a[it].x * ivi, a[it].y * ivi);
+      vi.y = f16 ? pack_f16x2(a[it].z * ivi, a[it].w * ivi) : pack_bf16x2(a[it].z * ivi, a[it].w * ivi);
+      vj.x = f16 ? pack_f16x2(b[it].x * ivj, b[it].y * ivj) : pack_bf16x2(b[it].x * ivj, b[it].y * ivj);
+      vj.y = f16 ? pack_f16x2(b[it].z * ivj, b[it].w * ivj) : pack_bf16x2(b[it].z * ivj, b[it].w * ivj);
+      const float2 fi01 = unpack_h2(vi.x, f16), fi23 = unpack_h2(vi.y, f16);
+      const float2 fj01 = unpack_h2(vj.x, f16), fj23 = unpack_h2(vj.y, f16);
       dot += fi01.x * fj01.x + fi01.y * fj01.y + fi23.x * fj23.x + fi23.y * fj23.y;
-      if (out_i) {
-        uint2 v;
-        v.x = *reinterpret_cast<uint32_t*>(&i01);
-        v.y = *reinterpret_cast<uint32_t*>(&i23);
-        *reinterpret_cast<uint2*>(out_i + static_cast<int64_t>(warp) * dpad + k) = v;
-      }
-      if (out_j) {
-        uint2 v;
-        v.x = *reinterpret_cast<uint32_t*>(&j01);
-        v.y = *reinterpret_cast<uint32_t*>(&j23);
-        *reinterpret_cast<uint2*>(out_j + static_cast<int64_t>(warp) * dpad + k) = v;
-      }
+      if (out_i) *reinterpret_cast<uint2*>(out_i + static_cast<int64_t>(warp) * dpad + k) = vi;
+      if (out_j) *reinterpret_cast<uint2*>(out_j + static_cast<int64_t>(warp) * dpad + k) = vj;
     }
   }
   dot = warp_sum(dot);
@@ -174,7 +173,8 @@ static __global__ void pair_prep_kernel(const float* __restrict__ xi, const floa
 // pair_prep + fused all-gather: every bf16 row is stored into the same slot of EVERY rank's gathered matrix through
 // peer-mapped pointers (NVLink stores), so no separate collective is needed (a barrier publishes the data).
 static __global__ void pair_prep_push_kernel(const float* __restrict__ xi, const float* __restrict__ xj, int n, int d,
-                                             int64_t ldi, int64_t ldj, int normalize, void* const* __restrict__ peers,
+                                             int64_t ldi, int64_t ldj, int normalize, int f16,
+                                             void* const* __restrict__ peers,
                                              int world, int64_t row_i, int64_t row_j, int dpad,
                                              float* __restrict__ inv_i, float* __restrict__ inv_j,
                                              float* __restrict__ pos_i, float* __restrict__ pos_j) {
@@ -195,15 +195,15 @@ static __global__ void pair_prep_push_kernel(const float* __restrict__ xi, const
     ivi = 1.f / fmaxf(sqrtf(si), 1e-12f);
     ivj = 1.f / fmaxf(sqrtf(sj), 1e-12f);
   }
-  __nv_bfloat162 i01 = __floats2bfloat162_rn(a.x * ivi, a.y * ivi), i23 = __floats2bfloat162_rn(a.z * ivi, a.w * ivi);
-  __nv_bfloat162 j01 = __floats2bfloat162_rn(b.x * ivj, b.y * ivj), j23 = __floats2bfloat162_rn(b.z * ivj, b.w * ivj);
-  const float2 fi01 = __bfloat1622float2(i01), fi23 = __bfloat1622float2(i23);
-  const float2 fj01 = __bfloat1622float2(j01), fj23 = __bfloat1622float2(j23);
+  uint2 vi, vj;
+  vi.x = f16 ? pack_f16x2(a.x * ivi, a.y * ivi) : pack_bf16x2(a.x * ivi, a.y * ivi);
+  vi.y = f16 ? pack_f16x2(a.z * ivi, a.w * ivi) : pack_bf16x2(a.z * ivi, a.w * ivi);
+  vj.x = f16 ? pack_f16x2(b.x * ivj, b.y * ivj) : pack_bf16x2(b.x * ivj, b.y * ivj);
+  vj.y = f16 ? pack_f16x2(b.z * ivj, b.w * ivj) : pack_bf16x2(b.z * ivj, b.w * ivj);
+  const float2 fi01 = unpack_h2(vi.x, f16), fi23 = unpack_h2(vi.y, f16);
+  const float2 fj01 = unpack_h2(vj.x, f16), fj23 = unpack_h2(vj.y, f16);
   float dot = warp_sum(fi01.x * fj01.x + fi01.y * fj01.y + fi23.x * fj23.x + fi23.y * fj23.y);
   if (k < dpad) {
-    uint2 vi, vj;
-    vi.x = *reinterpret_cast<uint32_t*>(&i01); vi.y = *reinterpret_cast<uint32_t*>(&i23);
-    vj.x = *reinterpret_cast<uint32_t*>(&j01); vj.y = *reinterpret_cast<uint32_t*>(&j23);
     for (int pr = 0; pr < world; ++pr) {
       __nv_bfloat16* base = static_cast<__nv_bfloat16*>(peers[pr]);
       *reinterpret_cast<uint2*>(base + (row_i + warp) * dpad + k) = vi;

@@ -38,6 +38,7 @@ struct SimParams {
   int ld_dacc;
   int use_atomic;  // nchunks > 1: red.add into a zeroed dacc
   unsigned long long* dbg;  // SSVB_DBG_TIMING builds only
+  int opf16;  // similarity operands staged as fp16 (normalised rows) instead of bf16
 };
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -186,7 +187,7 @@ __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int
 
 // 384 threads: warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps} shrinks to 40 registers/thread so that the two
 // softmax warpgroups (warps 4..11, TMEM lane quarter = warp % 4) can grow to 232.
-template <int KB, int MODE>
+template <int KB, int MODE, bool OPF16 = false>
 __global__ void __launch_bounds__(384, 1)
 sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SimParams p) {
   using C = FwdCfg<KB>;
@@ -259,7 +260,7 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t IDESC = make_idesc(128, BN, 0, 0);
+    constexpr uint32_t IDESC = make_idesc(128, BN, 0, 0, OPF16 ? 0 : 1);
     const uint32_t abase = smem_u32(sA);
     int ucount = 0, gt = 0;
     for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
@@ -375,7 +376,7 @@ __device__ __forceinline__ float ex2_poly3(float x) {
 #endif
 
 // weights of 32 consecutive columns [cb, cb+32) of one row: sv = S values, pk = packed bf16 pairs out
-template <int MODE, bool MASKED>
+template <int MODE, bool MASKED, bool OPF16>
 __device__ __forceinline__ void bwd_weights32(const uint32_t (&sv)[32], uint32_t (&pk)[16], const SimParams& p,
                                               int a_glob, int colbase, float rs, const void* cs32) {
 #ifndef SSVB_BWD_SCALAR_MATH
@@ -402,7 +403,7 @@ __device__ __forceinline__ void bwd_weights32(const uint32_t (&sv)[32], uint32_t
         const unsigned long long w2 = mul_f32x2(pack_f32x2(e0, e1), add_f32x2(rs2, e ? cu.y : cu.x));
         float w0, w1;
         unpack_f32x2(w2, w0, w1);
-        pk[i] = pack_bf16x2(w0, w1);
+        pk[i] = pack_h2<OPF16>(w0, w1);
       }
     }
     return;
@@ -434,8 +435,8 @@ __device__ __forceinline__ void bwd_weights32(const uint32_t (&sv)[32], uint32_t
       if (MASKED && (colbase + i == a_glob)) wv = 0.f;
       w[e] = wv;
     }
-    pk[i4 * 2] = pack_bf16x2(w[0], w[1]);
-    pk[i4 * 2 + 1] = pack_bf16x2(w[2], w[3]);
+    pk[i4 * 2] = pack_h2<OPF16>(w[0], w[1]);
+    pk[i4 * 2 + 1] = pack_h2<OPF16>(w[2], w[3]);
   }
 }
 
@@ -443,7 +444,7 @@ __device__ __forceinline__ void bwd_weights32(const uint32_t (&sv)[32], uint32_t
 // warpgroups.  Tile t is processed by the warpgroup pair (t & 1); within the pair each warpgroup owns one 64-column
 // half of the 128 x 128 tile (thread = row, TMEM lane quarter = warp % 4).  Four resident math warps per scheduler
 // (instead of two) hide the TMEM-load / barrier / MUFU latencies of each other.
-template <int KB, int MODE>
+template <int KB, int MODE, bool OPF16 = false>
 __global__ void __launch_bounds__(640, 1)
 sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SimParams p) {
   using C = BwdCfg<KB>;
@@ -526,8 +527,8 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
       // ---------------------------------------------------------------- MMA issuer: whole warp polls (votes keep the
       // control flow warp-uniform), one elected lane issues; never blocks on a single barrier
-      constexpr uint32_t IDESC_S = make_idesc(128, BN, 0, 0);
-      constexpr uint32_t IDESC_D = make_idesc(128, DP, 0, 1);  // A = W from TMEM, B = same smem tile read MN-major
+      constexpr uint32_t IDESC_S = make_idesc(128, BN, 0, 0, OPF16 ? 0 : 1);
+      constexpr uint32_t IDESC_D = make_idesc(128, DP, 0, 1, OPF16 ? 0 : 1);  // A = W from TMEM, B = same smem tile read MN-major
       const uint32_t abase = smem_u32(sA);
       int ucount = 0, gt = 0;
 #ifdef SSVB_DBG_TIMING
@@ -663,18 +664,18 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // first 32 weights are computed before waiting for the W buffer (dZ GEMM of tile t-2 may still read it)
         uint32_t pk[16];
         if (special)
-          bwd_weights32<MODE, true>(sv[0], pk, p, a_glob, j0, rs, cs);
+          bwd_weights32<MODE, true, OPF16>(sv[0], pk, p, a_glob, j0, rs, cs);
         else
-          bwd_weights32<MODE, false>(sv[0], pk, p, a_glob, j0, rs, cs);
+          bwd_weights32<MODE, false, OPF16>(sv[0], pk, p, a_glob, j0, rs, cs);
         SSVB_TP(4);  // first 32 weights
         mbar_wait(&w_empty[pair], ((gt >> 1) & 1) ^ 1);
         tc_fence_after();
         SSVB_TP(5);  // wait w_empty
         tmem_st_x16(t_w, pk);
         if (special)
-          bwd_weights32<MODE, true>(sv[1], pk, p, a_glob, j0 + 32, rs, cs + CSTEP);
+          bwd_weights32<MODE, true, OPF16>(sv[1], pk, p, a_glob, j0 + 32, rs, cs + CSTEP);
         else
-          bwd_weights32<MODE, false>(sv[1], pk, p, a_glob, j0 + 32, rs, cs + CSTEP);
+          bwd_weights32<MODE, false, OPF16>(sv[1], pk, p, a_glob, j0 + 32, rs, cs + CSTEP);
         tmem_st_x16(t_w + 16, pk);
         SSVB_TP(6);  // second 32 weights + stores issued
         tmem_st_wait();
