@@ -635,8 +635,9 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if ((gt & 1) != pair) continue;
         const int st = gt % NSTAGE;
         SSVB_TP(0);  // loop overhead / other
-        if (MODE != SIM_MOCO) mbar_wait(&b_full[st], (gt / NSTAGE) & 1);  // column stats landed with the B tile
-        SSVB_TP(1);  // wait b_full
+        // no separate wait on b_full: S(t) was issued only after the MMA warp observed b_full[st], so observing
+        // s_full(t) also orders this warp after the TMA / bulk-copy writes of the B tile and its column statistics
+        SSVB_TP(1);
         mbar_wait(&s_full[pair], (gt >> 1) & 1);
         tc_fence_after();
         SSVB_TP(2);  // wait s_full
@@ -661,23 +662,23 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t t_w = tmem + tlane + C::T_W + pair * 64 + half * 32;
         const uint8_t* cs = sC + st * C::CS_BYTES + half * 64 * 4;
         constexpr int CSTEP = 32 * 4;
-        // first 32 weights are computed before waiting for the W buffer (dZ GEMM of tile t-2 may still read it)
-        uint32_t pk[16];
-        if (special)
-          bwd_weights32<MODE, true, OPF16>(sv[0], pk, p, a_glob, j0, rs, cs);
-        else
-          bwd_weights32<MODE, false, OPF16>(sv[0], pk, p, a_glob, j0, rs, cs);
-        SSVB_TP(4);  // first 32 weights
+        // all 64 weights are computed and packed before waiting for the W buffer (the dZ GEMM of tile t-2 may still
+        // be reading it): that wait is off the critical path unless the tensor pipe is the bottleneck
+        uint32_t pk[2][16];
+        if (special) {
+          bwd_weights32<MODE, true, OPF16>(sv[0], pk[0], p, a_glob, j0, rs, cs);
+          bwd_weights32<MODE, true, OPF16>(sv[1], pk[1], p, a_glob, j0 + 32, rs, cs + CSTEP);
+        } else {
+          bwd_weights32<MODE, false, OPF16>(sv[0], pk[0], p, a_glob, j0, rs, cs);
+          bwd_weights32<MODE, false, OPF16>(sv[1], pk[1], p, a_glob, j0 + 32, rs, cs + CSTEP);
+        }
+        SSVB_TP(4);  // 64 weights
         mbar_wait(&w_empty[pair], ((gt >> 1) & 1) ^ 1);
         tc_fence_after();
         SSVB_TP(5);  // wait w_empty
-        tmem_st_x16(t_w, pk);
-        if (special)
-          bwd_weights32<MODE, true, OPF16>(sv[1], pk, p, a_glob, j0 + 32, rs, cs + CSTEP);
-        else
-          bwd_weights32<MODE, false, OPF16>(sv[1], pk, p, a_glob, j0 + 32, rs, cs + CSTEP);
-        tmem_st_x16(t_w + 16, pk);
-        SSVB_TP(6);  // second 32 weights + stores issued
+        tmem_st_x16(t_w, pk[0]);
+        tmem_st_x16(t_w + 16, pk[1]);
+        SSVB_TP(6);  // stores issued
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
