@@ -74,7 +74,7 @@ WsLayout ws_layout(void* base, int64_t local_rows, int64_t row_blocks, int64_t c
   p.row_blocks = static_cast<int>(row_blocks);
   p.cols = static_cast<int>(cols);
   plan_chunks(p, 256, 4);
-  size_t part_elems = static_cast<size_t>(2 * p.nchunks + 2) * lr;
+  size_t part_elems = static_cast<size_t>(4 * p.nchunks + 2) * lr;
   if (part_elems < static_cast<size_t>(sim_mpad(cols))) part_elems = sim_mpad(cols);
   w.pos = c.take<float>(lr);
   w.part_m = c.take<float>(part_elems);
@@ -194,16 +194,19 @@ int ssvb_ntxent_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   p.part_m = ws.part_m;
   p.part_l = ws.part_l;
   p.part_stride = static_cast<int>(round_up(pl.m, 256));
+#ifdef SSVB_DBG_TIMING
+  if (const char* e = getenv("SSVB_DBG_PTR")) p.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
+#endif
   SSVB_TRY(launch_sim_fwd(pl.mode, sv.zhat, pl.mpad, sv.zhat, pl.mpad, pl.dpad, p, s));
   {
     const unsigned grid = static_cast<unsigned>(ceil_div(pl.m, 256));
     const float scale = 1.f / static_cast<float>(pl.m);
     if (pl.mode == SIM_NTX_FIXED)
-      lse_finalize_kernel<SIM_NTX_FIXED><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 2 * p.nchunks, p.part_stride,
+      lse_finalize_kernel<SIM_NTX_FIXED><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride,
                                                             static_cast<int>(pl.m), ws.pos, pl.c, pl.shift,
                                                             sv.stat, nullptr, ws.block_sums, ws.counter, scale, loss);
     else
-      lse_finalize_kernel<SIM_NTX_ONLINE><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 2 * p.nchunks, p.part_stride,
+      lse_finalize_kernel<SIM_NTX_ONLINE><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride,
                                                              static_cast<int>(pl.m), ws.pos, pl.c, pl.shift,
                                                              sv.stat, nullptr, ws.block_sums, ws.counter, scale, loss);
     SSVB_LAUNCH_CHECK();
@@ -348,13 +351,13 @@ int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_l
   // stat_local always carries the log2-domain LSE (what gets all-gathered); the FIXED-mode 1/L' is
   // re-derived from it in rows_bwd.
   if (pl.mode == SIM_NTX_FIXED)
-    lse_finalize_kernel<SIM_NTX_FIXED><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 2 * p.nchunks, p.part_stride,
+    lse_finalize_kernel<SIM_NTX_FIXED><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride,
                                                           static_cast<int>(lr), pos_local, pl.c, pl.shift,
                                                           ws.dacc /*scratch*/, lse_out, ws.block_sums, ws.counter,
                                                           1.f, loss_sum, term_out, peer_stat, static_cast<int>(world),
                                                           peer_off);
   else
-    lse_finalize_kernel<SIM_NTX_ONLINE><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 2 * p.nchunks, p.part_stride,
+    lse_finalize_kernel<SIM_NTX_ONLINE><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride,
                                                            static_cast<int>(lr), pos_local, pl.c, pl.shift,
                                                            ws.dacc /*scratch*/, lse_out, ws.block_sums,
                                                            ws.counter, 1.f, loss_sum, term_out, peer_stat,

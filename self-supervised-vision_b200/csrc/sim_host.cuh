@@ -44,7 +44,7 @@ int launch_sim_fwd_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const SimPa
   const int nunits = p.row_blocks * p.nchunks;
   const int grid = nunits < num_sms() ? nunits : num_sms();
   const int slot = prof_begin(PROF_SIM_FWD, s);
-  kern<<<grid, 384, smem, s>>>(tmA, tmB, p);
+  kern<<<grid, 640, smem, s>>>(tmA, tmB, p);
   prof_end(slot, s);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;

@@ -27,7 +27,7 @@ struct SimParams {
   int nchunks, tiles_per_chunk;
   float c;      // log2(e) / temperature
   float shift;  // FIXED mode: constant log2-domain shift (= c, the largest possible logit)
-  // forward outputs: [2 * nchunks][part_stride]
+  // forward outputs: [4 * nchunks][part_stride] (one partial per softmax warpgroup and column chunk)
   float* part_m;
   float* part_l;
   int part_stride;
@@ -76,6 +76,16 @@ __device__ __forceinline__ UnitInfo decode_unit(const SimParams& p, int u) {
   return ui;
 }
 
+// phase timing (timing experiments only): block 0, first lane of the first math warp / of the MMA warp accumulate
+// clock64 deltas per phase into p.dbg[0..15]
+#ifdef SSVB_DBG_TIMING
+#define SSVB_T0() long long _t_prev = clock64()
+#define SSVB_TP(slot) do { const long long _t_now = clock64(); _t_acc[slot] += _t_now - _t_prev; _t_prev = _t_now; } while (0)
+#else
+#define SSVB_T0() do {} while (0)
+#define SSVB_TP(slot) do {} while (0)
+#endif
+
 __device__ __forceinline__ float ex2_poly3(float x);
 // ---- timing-experiment knobs (tests/ab_bench.sh): each one REMOVES a piece of work, results become wrong ----
 #ifdef SSVB_DBG_NOEXP
@@ -102,7 +112,11 @@ struct FwdCfg {
 
 template <int MODE, bool MASKED>
 __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int a_glob, int j0, float& m,
-                                         float (&l)[4], uint64_t* s_empty_bar, int lane) {
+                                         float (&l)[4], uint64_t* s_empty_bar, int lane
+#ifdef SSVB_DBG_TIMING
+                                         , long long (&_t_acc)[8], long long& _t_prev
+#endif
+                                         ) {
   uint32_t v[2][32];
   unsigned long long l2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};  // packed row-sum accumulators
 #ifndef SSVB_DBG_NOLD
@@ -112,12 +126,14 @@ __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int
   for (int i = 0; i < 32; ++i) { v[0][i] = __float_as_uint(1e-3f * (i + lane)); v[1][i] = __float_as_uint(2e-3f * (i + lane)); }
 #endif
 #pragma unroll
-  for (int cc = 0; cc < 8; ++cc) {
+  for (int cc = 0; cc < 4; ++cc) {
     uint32_t(&cur)[32] = v[cc & 1];
+    SSVB_TP(3);  // exp / sum work of the previous chunk
 #ifndef SSVB_DBG_NOLD
     tmem_ld_wait_regs(cur);
 #endif
-    if (cc < 7) {
+    SSVB_TP(2);  // waiting for the TMEM load
+    if (cc < 3) {
 #ifndef SSVB_DBG_NOLD
       tmem_ld_x32(taddr + (cc + 1) * 32, v[(cc + 1) & 1]);
 #endif
@@ -185,10 +201,12 @@ __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int
 }
 
 
-// 384 threads: warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps} shrinks to 40 registers/thread so that the two
-// softmax warpgroups (warps 4..11, TMEM lane quarter = warp % 4) can grow to 232.
+// 640 threads: warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps} shrinks to 40 registers/thread; warps 4..19 are
+// FOUR softmax warpgroups (TMEM lane quarter = warp % 4): tile t belongs to the warpgroup pair (t & 1) (= its S
+// buffer), and within the pair each warpgroup streams one 128-column half.  Four math warps per scheduler keep the
+// MUFU and FMA pipes (polynomial exp2) busy at the same time.
 template <int KB, int MODE, bool OPF16 = false>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(640, 1)
 sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SimParams p) {
   using C = FwdCfg<KB>;
   constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
@@ -215,7 +233,7 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&s_empty[i], 8);
     }
     for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(&b_full[i], 1);
@@ -291,35 +309,54 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int wg = (warp - 4) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int wgi = (warp - 4) >> 2;  // 0..3
+    const int pair = wgi >> 1, half = wgi & 1;
     const int q = warp & 3;
     const int row_l = q * 32 + lane;
     const uint32_t tlane = static_cast<uint32_t>(q * 32) << 16;
     int gt = 0;
+#ifdef SSVB_DBG_TIMING
+    long long _t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    SSVB_T0();
     for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
       const UnitInfo ui = decode_unit(p, u);
       const int a_glob = ui.g0 + row_l;
       float m = -1e30f;
       float l[4] = {0.f, 0.f, 0.f, 0.f};
       for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
-        if ((gt & 1) != wg) continue;
-        mbar_wait(&s_full[wg], (gt >> 1) & 1);
+        if ((gt & 1) != pair) continue;
+        const int buf = pair;
+        SSVB_TP(0);  // loop / other
+        mbar_wait(&s_full[buf], (gt >> 1) & 1);
         tc_fence_after();
-        const int j0 = t * BN;
-        const bool special = (MODE != SIM_MOCO && j0 < ui.g0 + 128 && j0 + BN > ui.g0) || (j0 + BN > p.cols);
-        const uint32_t taddr = tmem + tlane + wg * BN;
+        SSVB_TP(1);  // wait s_full
+        const int j0 = t * BN + half * 128;
+        const bool special = (MODE != SIM_MOCO && j0 < ui.g0 + 128 && j0 + 128 > ui.g0) || (j0 + 128 > p.cols);
+        const uint32_t taddr = tmem + tlane + buf * BN + half * 128;
+#ifdef SSVB_DBG_TIMING
         if (special)
-          fwd_tile<MODE, true>(taddr, p, a_glob, j0, m, l, &s_empty[wg], lane);
+          fwd_tile<MODE, true>(taddr, p, a_glob, j0, m, l, &s_empty[buf], lane, _t_acc, _t_prev);
         else
-          fwd_tile<MODE, false>(taddr, p, a_glob, j0, m, l, &s_empty[wg], lane);
+          fwd_tile<MODE, false>(taddr, p, a_glob, j0, m, l, &s_empty[buf], lane, _t_acc, _t_prev);
+#else
+        if (special)
+          fwd_tile<MODE, true>(taddr, p, a_glob, j0, m, l, &s_empty[buf], lane);
+        else
+          fwd_tile<MODE, false>(taddr, p, a_glob, j0, m, l, &s_empty[buf], lane);
+#endif
       }
       if (row_l < ui.nvalid) {
-        const size_t o = static_cast<size_t>(ui.ch * 2 + wg) * p.part_stride + ui.lrow0 + row_l;
+        const size_t o = static_cast<size_t>(ui.ch * 4 + wgi) * p.part_stride + ui.lrow0 + row_l;
         p.part_l[o] = (l[0] + l[1]) + (l[2] + l[3]);
         if (MODE != SIM_NTX_FIXED) p.part_m[o] = m;
       }
     }
+#ifdef SSVB_DBG_TIMING
+    if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0)
+      for (int i = 0; i < 8; ++i) p.dbg[16 + i] = static_cast<unsigned long long>(_t_acc[i]);
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -335,16 +372,6 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // and the MMA thread never blocks on a single barrier — it polls "next S issuable" and "next dZ issuable" and issues
 // whichever is ready — so the similarity GEMM of tile t+2 runs while W(t) is still being computed and the
 // W -> dZ latency is off the critical path of the exp warps.
-// phase timing (timing experiments only): block 0, first lane of the first math warp / of the MMA warp accumulate
-// clock64 deltas per phase into p.dbg[0..15]
-#ifdef SSVB_DBG_TIMING
-#define SSVB_T0() long long _t_prev = clock64()
-#define SSVB_TP(slot) do { const long long _t_now = clock64(); _t_acc[slot] += _t_now - _t_prev; _t_prev = _t_now; } while (0)
-#else
-#define SSVB_T0() do {} while (0)
-#define SSVB_TP(slot) do {} while (0)
-#endif
-
 template <int KB>
 struct BwdCfg {
   static constexpr int BN = 128;
