@@ -58,7 +58,7 @@ MocoWs moco_ws(void* base, int64_t n, int64_t k, int64_t dpad) {
   w.queue_bf16 = c.take<__nv_bfloat16>(k * dpad);
   w.part_m = c.take<float>(static_cast<size_t>(4 * p.nchunks) * npad);
   w.part_l = c.take<float>(static_cast<size_t>(4 * p.nchunks) * npad);
-  w.block_sums = c.take<float>(ceil_div(npad, 256) + 8);
+  w.block_sums = c.take<float>(ceil_div(npad, 8) + 8);
   w.counter = c.take<unsigned int>(4);
   w.dacc = c.take<float>(npad * dpad);
   w.bytes = c.used();
@@ -197,9 +197,9 @@ int ssvb_moco_fwd(const float* query, const float* keys, const float* queue, con
   p.part_l = ws.part_l;
   p.part_stride = static_cast<int>(npad);
   SSVB_TRY(launch_sim_fwd(SIM_MOCO, sv.qhat, npad, qb, k, dpad, p, s));
-  lse_finalize_kernel<SIM_MOCO><<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, s>>>(
-      ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride, static_cast<int>(n), sv.pos, c, 0.f, sv.lse2, nullptr,
-      ws.block_sums, ws.counter, 1.f / static_cast<float>(n), loss);
+  lse_finalize_wide_kernel<SIM_MOCO><<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(
+      ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride, static_cast<int>(n), sv.pos, c, sv.lse2, ws.block_sums,
+      ws.counter, 1.f / static_cast<float>(n), loss);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }

@@ -305,6 +305,35 @@ __global__ void lse_finalize_kernel(const float* __restrict__ part_m, const floa
   grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false);
 }
 
+// Same combine for MANY partials per row (MoCo: the queue axis is split into up to 128 chunks x 4 warpgroups):
+// one warp per row, lanes stride over the partials, shuffle max / sum; 8 rows per block.
+template <int MODE>
+__global__ void lse_finalize_wide_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
+                                         int nparts, int stride, int nrows, const float* __restrict__ pos, float c,
+                                         float* __restrict__ stat, float* block_sums, unsigned int* counter,
+                                         float loss_scale, float* loss) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  float term = 0.f;
+  if (r < nrows) {
+    const float p2 = pos[r] * c;
+    float M = (MODE == SIM_MOCO) ? p2 : -1e30f;
+    for (int i = lane; i < nparts; i += 32) M = fmaxf(M, part_m[static_cast<size_t>(i) * stride + r]);
+    M = warp_max(M);
+    float L = 0.f;
+    for (int i = lane; i < nparts; i += 32)
+      L += part_l[static_cast<size_t>(i) * stride + r] * exp2f(part_m[static_cast<size_t>(i) * stride + r] - M);
+    L = warp_sum(L);
+    if (MODE == SIM_MOCO) L += exp2f(p2 - M);
+    const float lse2 = M + log2f(L);
+    if (lane == 0) {
+      stat[r] = lse2;
+      term = (lse2 - p2) * SSVB_LN2;
+    }
+  }
+  const float bt = block_sum_256(term);
+  grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false);
+}
+
 static __global__ void fill_kernel(float* p, int64_t n, float v) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

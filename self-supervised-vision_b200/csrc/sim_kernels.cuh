@@ -552,91 +552,62 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     } else if (warp == 1) {
-      // ---------------------------------------------------------------- MMA issuer: whole warp polls (votes keep the
-      // control flow warp-uniform), one elected lane issues; never blocks on a single barrier
+      // ---------------------------------------------------------------- S-GEMM issuer (whole warp, elect_one issues).
+      // The two GEMMs have their own issuer warps: a tile needs 16 tcgen05.mma of only 64 tensor-cycles each, and one
+      // thread cannot issue them (plus commits and barrier waits) fast enough to keep the pipe full.
       constexpr uint32_t IDESC_S = make_idesc(128, BN, 0, 0, OPF16 ? 0 : 1);
-      constexpr uint32_t IDESC_D = make_idesc(128, DP, 0, 1, OPF16 ? 0 : 1);  // A = W from TMEM, B = same smem tile read MN-major
       const uint32_t abase = smem_u32(sA);
       int ucount = 0, gt = 0;
-#ifdef SSVB_DBG_TIMING
-      long long _m_acc[2] = {0, 0};
-#endif
       for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
         const UnitInfo ui = decode_unit(p, u);
-        const int ntile = ui.t1 - ui.t0;
-        const int gt0 = gt;
         mbar_wait(a_full, ucount & 1);
-        int ns = 0, nd = 0;
-        long long t_idle = 0;
-#ifdef SSVB_DBG_TIMING
-        long long _m_t = clock64();
-#endif
-        while (nd < ntile) {
-          bool progressed = false;
-          if (ns < ntile) {
-            const int g = gt0 + ns;
-            const int st = g % NSTAGE, buf = g & 1;
-            const bool ok = mbar_test_wait(&b_full[st], (g / NSTAGE) & 1) && mbar_test_wait(&s_empty[buf], ((g >> 1) & 1) ^ 1);
-            if (__all_sync(0xffffffffu, ok)) {
-              tc_fence_after();
-              if (elect_one()) {
-                const uint32_t bbase = smem_u32(sB + st * C::B_BYTES);
+        for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
+          const int st = gt % NSTAGE, buf = gt & 1;
+          mbar_wait(&b_full[st], (gt / NSTAGE) & 1);
+          mbar_wait(&s_empty[buf], ((gt >> 1) & 1) ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t bbase = smem_u32(sB + st * C::B_BYTES);
 #ifndef SSVB_DBG_NOS
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb)
+            for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-                  for (int k4 = 0; k4 < 4; ++k4)
-                    umma_ss(tmem + C::T_S + buf * BN, desc_kmajor(abase + kb * (128 * 128) + k4 * 32),
-                            desc_kmajor(bbase + kb * (BN * 128) + k4 * 32), IDESC_S, (kb | k4) != 0);
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_ss(tmem + C::T_S + buf * BN, desc_kmajor(abase + kb * (128 * 128) + k4 * 32),
+                        desc_kmajor(bbase + kb * (BN * 128) + k4 * 32), IDESC_S, (kb | k4) != 0);
 #endif
-                umma_commit(&s_full[buf]);
-                if (ns == ntile - 1) umma_commit(a_empty);  // last reader of this unit's A tile
-              }
-              __syncwarp();
-              ++ns;
-              progressed = true;
-            }
+            umma_commit(&s_full[buf]);
+            if (t == ui.t1 - 1) umma_commit(a_empty);  // last reader of this unit's A tile
           }
-          if (nd < ns) {
-            const int g = gt0 + nd;
-            const int st = g % NSTAGE, buf = g & 1;
-            const bool ok = mbar_test_wait(&w_full[buf], (g >> 1) & 1) &&
-                            (nd > 0 || mbar_test_wait(dz_empty, (ucount & 1) ^ 1));
-            if (__all_sync(0xffffffffu, ok)) {
-              tc_fence_after();
-              if (elect_one()) {
-                const uint32_t bbase = smem_u32(sB + st * C::B_BYTES);
+          __syncwarp();
+        }
+      }
+    } else if (warp == 2) {
+      // ---------------------------------------------------------------- dZ-GEMM issuer
+      constexpr uint32_t IDESC_D = make_idesc(128, DP, 0, 1, OPF16 ? 0 : 1);  // A = W from TMEM, B = smem tile MN-major
+      int ucount = 0, gt = 0;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++ucount) {
+        const UnitInfo ui = decode_unit(p, u);
+        mbar_wait(dz_empty, (ucount & 1) ^ 1);
+        for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
+          const int st = gt % NSTAGE, buf = gt & 1;
+          mbar_wait(&w_full[buf], (gt >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t bbase = smem_u32(sB + st * C::B_BYTES);
 #ifndef SSVB_DBG_NOD
 #pragma unroll
-                for (int k = 0; k < BN / 16; ++k)
-                  umma_ts(tmem + C::T_DZ, tmem + C::T_W + buf * 64 + k * 8,
-                          desc_mnmajor(bbase + k * (16 * 128), BN * 128), IDESC_D, (nd > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BN / 16; ++k)
+              umma_ts(tmem + C::T_DZ, tmem + C::T_W + buf * 64 + k * 8, desc_mnmajor(bbase + k * (16 * 128), BN * 128),
+                      IDESC_D, (t > ui.t0 || k > 0) ? 1u : 0u);
 #endif
-                umma_commit(&b_empty[st]);
-                umma_commit(&w_empty[buf]);
-                if (nd == ntile - 1) umma_commit(dz_full);
-              }
-              __syncwarp();
-              ++nd;
-              progressed = true;
-            }
+            umma_commit(&b_empty[st]);
+            umma_commit(&w_empty[buf]);
+            if (t == ui.t1 - 1) umma_commit(dz_full);
           }
-          if (progressed) {
-            t_idle = 0;
-          } else {
-            if (t_idle == 0) t_idle = clock64();
-            else if (clock64() - t_idle > 4000000000LL) __trap();
-            __nanosleep(40);
-          }
-#ifdef SSVB_DBG_TIMING
-          { const long long n = clock64(); _m_acc[progressed ? 0 : 1] += n - _m_t; _m_t = n; }
-#endif
+          __syncwarp();
         }
-        gt = gt0 + ntile;
       }
-#ifdef SSVB_DBG_TIMING
-      if (p.dbg && blockIdx.x == 0 && lane == 0) { p.dbg[8] = _m_acc[0]; p.dbg[9] = _m_acc[1]; }
-#endif
     }
   } else {
     // ------------------------------------------------------------------ weight warpgroups + epilogue
