@@ -109,3 +109,56 @@ def as_f32_rows(t):
 
 def byte_buffer(nbytes: int, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ---- host-overhead helpers: the small losses are launch-bound, every microsecond of Python per call shows -------
+_WS = {}
+
+
+def workspace(tag: str, nbytes: int, device):
+    """Scratch buffer reused across calls of one op on one (device, stream): work is stream-ordered, so the next call
+    on the same stream may overwrite it.  (`saved` blobs that must survive until backward are NOT taken from here.)"""
+    key = (tag, device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+_SIZES = {}
+
+
+def cached_size(fn_name: str, *args) -> int:
+    """Memoised `*_saved_bytes` / `*_workspace_bytes` queries (pure functions of the shape)."""
+    key = (fn_name,) + args
+    v = _SIZES.get(key)
+    if v is None:
+        v = int(getattr(lib(), fn_name)(*args))
+        _SIZES[key] = v
+    return v
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def on_device(device):
+    """`torch.cuda.device(device)` only when it is not already current (the context manager costs ~10 us)."""
+    if torch.cuda.current_device() == device.index:
+        return _NULL
+    return torch.cuda.device(device)
+
+
+def f32_scalar(t):
+    """grad_output as a contiguous fp32 device scalar without redundant ops."""
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t
+    return t.to(torch.float32).contiguous()

@@ -31,10 +31,10 @@ class CudaStages:
     """The product path: hand-written kernels behind the C ABI."""
 
     def dpad(self, d):
-        return int(C.lib().ssvb_ntxent_dpad(d))
+        return C.cached_size("ssvb_ntxent_dpad", d)
 
     def mpad(self, n_global):
-        return int(C.lib().ssvb_ntxent_mpad(n_global))
+        return C.cached_size("ssvb_ntxent_mpad", n_global)
 
     def prep(self, zi, zj, normalize, world, rank, zhat_all, inv_local, pos_local):
         n, d = zi.shape
@@ -45,8 +45,8 @@ class CudaStages:
     def rows_fwd(self, zhat_all, world, rank, n_local, d, normalize, temperature, pos_local, stat_local, loss_sum):
         L = C.lib()
         dev = zhat_all.device
-        ws_bytes = L.ssvb_ntxent_dist_workspace_bytes(world, n_local, d)
-        ws = C.byte_buffer(ws_bytes, dev)
+        ws_bytes = C.cached_size("ssvb_ntxent_dist_workspace_bytes", world, n_local, d)
+        ws = C.workspace("ntxent_dist", ws_bytes, dev)
         C.check(L.ssvb_ntxent_dist_rows_fwd(C.ptr(zhat_all), world, rank, n_local, d, normalize, temperature,
                                             C.ptr(pos_local), C.ptr(stat_local), C.ptr(loss_sum), C.ptr(ws), ws_bytes,
                                             C.stream_ptr(dev)), "ssvb_ntxent_dist_rows_fwd")
@@ -55,8 +55,8 @@ class CudaStages:
         L = C.lib()
         n, d = zi.shape
         dev = zi.device
-        ws_bytes = L.ssvb_ntxent_dist_workspace_bytes(world, n, d)
-        ws = C.byte_buffer(ws_bytes, dev)
+        ws_bytes = C.cached_size("ssvb_ntxent_dist_workspace_bytes", world, n, d)
+        ws = C.workspace("ntxent_dist", ws_bytes, dev)
         C.check(L.ssvb_ntxent_dist_rows_bwd(C.ptr(zi), C.ptr(zj), n, d, zi.stride(0), zj.stride(0), normalize,
                                             temperature, world, rank, C.ptr(zhat_all), C.ptr(stat_all), C.ptr(inv_local),
                                             C.ptr(grad_out), C.ptr(dzi), C.ptr(dzj), dzi.stride(0), dzj.stride(0),
@@ -73,8 +73,8 @@ class CudaStages:
     def rows_fwd_push(self, zhat_all, world, rank, n_local, d, normalize, temperature, pos_local, peer_stat_dev, loss_sum):
         L = C.lib()
         dev = zhat_all.device
-        ws_bytes = L.ssvb_ntxent_dist_workspace_bytes(world, n_local, d)
-        ws = C.byte_buffer(ws_bytes, dev)
+        ws_bytes = C.cached_size("ssvb_ntxent_dist_workspace_bytes", world, n_local, d)
+        ws = C.workspace("ntxent_dist", ws_bytes, dev)
         C.check(L.ssvb_ntxent_dist_rows_fwd_push(C.ptr(zhat_all), world, rank, n_local, d, normalize, temperature,
                                                  C.ptr(pos_local), C.c_void_p(peer_stat_dev), C.ptr(loss_sum), C.ptr(ws),
                                                  ws_bytes, C.stream_ptr(dev)), "ssvb_ntxent_dist_rows_fwd_push")
@@ -147,7 +147,7 @@ class _NtxentDistFn(torch.autograd.Function):
         n, d = xi.shape
         dev = xi.device
         m = 2 * n * world
-        mpad, dpad = stages.mpad(n * world), stages.dpad(d)
+        mpad, dpad = stages.mpad(n * world), stages.dpad(d)  # (memoised for the CUDA stages)
         norm = int(bool(normalize))
         inv_local = torch.empty(2 * n, dtype=torch.float32, device=dev)
         pos_local = torch.empty(2 * n, dtype=torch.float32, device=dev)
@@ -198,7 +198,7 @@ class _NtxentDistFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         xi, xj, zhat_all, stat_all, inv_local = ctx.saved_tensors
         norm, temperature, world, rank, stages, dti, dtj = ctx.cfg
-        go = grad_out.to(torch.float32).contiguous()
+        go = C.f32_scalar(grad_out)
         dzi, dzj = torch.empty_like(xi), torch.empty_like(xj)
         stages.rows_bwd(xi, xj, norm, temperature, world, rank, zhat_all, stat_all, inv_local, go, dzi, dzj)
         return dzi.to(dti), dzj.to(dtj), None, None, None, None, None

@@ -28,10 +28,10 @@ class _NtxentFn(torch.autograd.Function):
         n, d = xi.shape
         L = C.lib()
         dev = xi.device
-        with torch.cuda.device(dev):
-            saved = C.byte_buffer(L.ssvb_ntxent_saved_bytes(n, d), dev)
-            ws_bytes = L.ssvb_ntxent_workspace_bytes(n, d)
-            ws = C.byte_buffer(ws_bytes, dev)
+        with C.on_device(dev):
+            saved = C.byte_buffer(C.cached_size("ssvb_ntxent_saved_bytes", n, d), dev)
+            ws_bytes = C.cached_size("ssvb_ntxent_workspace_bytes", n, d)
+            ws = C.workspace("ntxent", ws_bytes, dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             C.check(L.ssvb_ntxent_fwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), int(bool(normalize)),
                                       float(temperature), C.ptr(loss), C.ptr(saved), C.ptr(ws), ws_bytes,
@@ -47,11 +47,11 @@ class _NtxentFn(torch.autograd.Function):
         n, d = xi.shape
         L = C.lib()
         dev = xi.device
-        with torch.cuda.device(dev):
-            go = grad_out.to(torch.float32).contiguous()
+        with C.on_device(dev):
+            go = C.f32_scalar(grad_out)
             dzi, dzj = torch.empty_like(xi), torch.empty_like(xj)
-            ws_bytes = L.ssvb_ntxent_workspace_bytes(n, d)
-            ws = C.byte_buffer(ws_bytes, dev)
+            ws_bytes = C.cached_size("ssvb_ntxent_workspace_bytes", n, d)
+            ws = C.workspace("ntxent", ws_bytes, dev)
             C.check(L.ssvb_ntxent_bwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), normalize, temperature,
                                       C.ptr(go), C.ptr(saved), C.ptr(dzi), C.ptr(dzj), _ld(dzi), _ld(dzj),
                                       C.ptr(ws), ws_bytes, C.stream_ptr(dev)), "ssvb_ntxent_bwd")
@@ -92,10 +92,10 @@ class _MocoFn(torch.autograd.Function):
         kq = mem.shape[0]
         L = C.lib()
         dev = q.device
-        with torch.cuda.device(dev):
-            saved = C.byte_buffer(L.ssvb_moco_saved_bytes(n, kq, d), dev)
-            ws_bytes = L.ssvb_moco_workspace_bytes(n, kq, d)
-            ws = C.byte_buffer(ws_bytes, dev)
+        with C.on_device(dev):
+            saved = C.byte_buffer(C.cached_size("ssvb_moco_saved_bytes", n, kq, d), dev)
+            ws_bytes = C.cached_size("ssvb_moco_workspace_bytes", n, kq, d)
+            ws = C.workspace("moco", ws_bytes, dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             C.check(L.ssvb_moco_fwd(C.ptr(q), C.ptr(k), C.ptr(mem), C.ptr(shadow), n, kq, d, _ld(q), _ld(k), _ld(mem),
                                     int(bool(normalize)), float(temperature), C.ptr(loss), C.ptr(saved), C.ptr(ws),
@@ -113,11 +113,11 @@ class _MocoFn(torch.autograd.Function):
         kq = mem.shape[0]
         L = C.lib()
         dev = q.device
-        with torch.cuda.device(dev):
-            go = grad_out.to(torch.float32).contiguous()
+        with C.on_device(dev):
+            go = C.f32_scalar(grad_out)
             dq, dk = torch.empty_like(q), torch.empty_like(k)
-            ws_bytes = L.ssvb_moco_workspace_bytes(n, kq, d)
-            ws = C.byte_buffer(ws_bytes, dev)
+            ws_bytes = C.cached_size("ssvb_moco_workspace_bytes", n, kq, d)
+            ws = C.workspace("moco", ws_bytes, dev)
             C.check(L.ssvb_moco_bwd(C.ptr(q), C.ptr(k), C.ptr(mem), C.ptr(ctx.shadow), n, kq, d, _ld(q), _ld(k),
                                     _ld(mem), normalize, temperature, C.ptr(go), C.ptr(saved), C.ptr(dq), C.ptr(dk),
                                     _ld(dq), _ld(dk), C.ptr(ws), ws_bytes, C.stream_ptr(dev)), "ssvb_moco_bwd")
@@ -148,9 +148,9 @@ class _RowdotFn(torch.autograd.Function):
         n, d = oo.shape
         L = C.lib()
         dev = oo.device
-        with torch.cuda.device(dev):
-            ws_bytes = L.ssvb_rowdot_workspace_bytes(n, d)
-            ws = C.byte_buffer(ws_bytes, dev)
+        with C.on_device(dev):
+            ws_bytes = C.cached_size("ssvb_rowdot_workspace_bytes", n, d)
+            ws = C.workspace("rowdot", ws_bytes, dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             C.check(L.ssvb_rowdot_fwd(kind, C.ptr(oo), C.ptr(tt), n, d, _ld(oo), _ld(tt), C.ptr(loss), C.ptr(ws),
                                       ws_bytes, C.stream_ptr(dev)), "ssvb_rowdot_fwd")
@@ -168,8 +168,8 @@ class _RowdotFn(torch.autograd.Function):
         n, d = oo.shape
         L = C.lib()
         dev = oo.device
-        with torch.cuda.device(dev):
-            go = grad_out.to(torch.float32).contiguous()
+        with C.on_device(dev):
+            go = C.f32_scalar(grad_out)
             d_o = torch.empty_like(oo) if need_o else None
             d_t = torch.empty_like(tt) if need_t else None
             C.check(L.ssvb_rowdot_bwd(kind, C.ptr(oo), C.ptr(tt), n, d, _ld(oo), _ld(tt), C.ptr(go), C.ptr(d_o),
@@ -211,15 +211,15 @@ class _RelicFn(torch.autograd.Function):
         L = C.lib()
         dev = xi.device
         norm = int(bool(normalize))
-        with torch.cuda.device(dev):
+        with C.on_device(dev):
             st = C.stream_ptr(dev)
-            saved_c = C.byte_buffer(L.ssvb_ntxent_saved_bytes(n, d), dev)
-            ws_bytes = L.ssvb_ntxent_workspace_bytes(n, d)
-            ws = C.byte_buffer(ws_bytes, dev)
+            saved_c = C.byte_buffer(C.cached_size("ssvb_ntxent_saved_bytes", n, d), dev)
+            ws_bytes = C.cached_size("ssvb_ntxent_workspace_bytes", n, d)
+            ws = C.workspace("ntxent", ws_bytes, dev)
             out = torch.empty(2, dtype=torch.float32, device=dev)
             C.check(L.ssvb_ntxent_fwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), norm, float(temperature),
                                       C.ptr(out), C.ptr(saved_c), C.ptr(ws), ws_bytes, st), "ssvb_ntxent_fwd")
-            saved_k = C.byte_buffer(L.ssvb_relic_kl_saved_bytes(n), dev)
+            saved_k = C.byte_buffer(C.cached_size("ssvb_relic_kl_saved_bytes", n), dev)
             kl = out[1:]
             C.check(L.ssvb_relic_kl_fwd(C.ptr(xi), C.ptr(xj), C.ptr(xo), n, d, _ld(xi), _ld(xj), _ld(xo), norm,
                                         float(temperature), float(alpha), C.ptr(kl), C.ptr(saved_k), None, 0, st),
@@ -235,12 +235,12 @@ class _RelicFn(torch.autograd.Function):
         n, d = xi.shape
         L = C.lib()
         dev = xi.device
-        with torch.cuda.device(dev):
+        with C.on_device(dev):
             st = C.stream_ptr(dev)
-            go = grad_out.to(torch.float32).contiguous()
+            go = C.f32_scalar(grad_out)
             dzi, dzj, dzo = torch.empty_like(xi), torch.empty_like(xj), torch.empty_like(xo)
-            ws_bytes = L.ssvb_ntxent_workspace_bytes(n, d)
-            ws = C.byte_buffer(ws_bytes, dev)
+            ws_bytes = C.cached_size("ssvb_ntxent_workspace_bytes", n, d)
+            ws = C.workspace("ntxent", ws_bytes, dev)
             C.check(L.ssvb_ntxent_bwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), norm, temperature, C.ptr(go),
                                       C.ptr(saved_c), C.ptr(dzi), C.ptr(dzj), _ld(dzi), _ld(dzj), C.ptr(ws), ws_bytes,
                                       st), "ssvb_ntxent_bwd")
@@ -274,10 +274,10 @@ class _BarlowFn(torch.autograd.Function):
         n, d = xi.shape
         L = C.lib()
         dev = xi.device
-        with torch.cuda.device(dev):
-            saved = C.byte_buffer(L.ssvb_barlow_saved_bytes(n, d), dev)
-            ws_bytes = L.ssvb_barlow_workspace_bytes(n, d)
-            ws = C.byte_buffer(ws_bytes, dev)
+        with C.on_device(dev):
+            saved = C.byte_buffer(C.cached_size("ssvb_barlow_saved_bytes", n, d), dev)
+            ws_bytes = C.cached_size("ssvb_barlow_workspace_bytes", n, d)
+            ws = C.workspace("barlow", ws_bytes, dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             C.check(L.ssvb_barlow_fwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), int(bool(normalize)), float(lmbda),
                                       C.ptr(loss), C.ptr(saved), C.ptr(ws), ws_bytes, C.stream_ptr(dev)),
@@ -293,11 +293,11 @@ class _BarlowFn(torch.autograd.Function):
         n, d = xi.shape
         L = C.lib()
         dev = xi.device
-        with torch.cuda.device(dev):
-            go = grad_out.to(torch.float32).contiguous()
+        with C.on_device(dev):
+            go = C.f32_scalar(grad_out)
             dzi, dzj = torch.empty_like(xi), torch.empty_like(xj)
-            ws_bytes = L.ssvb_barlow_workspace_bytes(n, d)
-            ws = C.byte_buffer(ws_bytes, dev)
+            ws_bytes = C.cached_size("ssvb_barlow_workspace_bytes", n, d)
+            ws = C.workspace("barlow", ws_bytes, dev)
             C.check(L.ssvb_barlow_bwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), normalize, lmbda, C.ptr(go),
                                       C.ptr(saved), C.ptr(dzi), C.ptr(dzj), _ld(dzi), _ld(dzj), C.ptr(ws), ws_bytes,
                                       C.stream_ptr(dev)), "ssvb_barlow_bwd")
@@ -330,10 +330,10 @@ class _SwavFn(torch.autograd.Function):
         k = pc.shape[0]
         L = C.lib()
         dev = x1.device
-        with torch.cuda.device(dev):
-            saved = C.byte_buffer(L.ssvb_swav_saved_bytes(nb, nbank, k, d), dev)
-            ws_bytes = L.ssvb_swav_workspace_bytes(nb, nbank, k, d)
-            ws = C.byte_buffer(ws_bytes, dev)
+        with C.on_device(dev):
+            saved = C.byte_buffer(C.cached_size("ssvb_swav_saved_bytes", nb, nbank, k, d), dev)
+            ws_bytes = C.cached_size("ssvb_swav_workspace_bytes", nb, nbank, k, d)
+            ws = C.workspace("swav", ws_bytes, dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             C.check(L.ssvb_swav_fwd(C.ptr(x1), C.ptr(x2), C.ptr(bk), C.ptr(pc), nb, nbank, k, d, _ld(x1), _ld(x2),
                                     _ld(bk) if bk is not None else 0, _ld(pc), float(temperature), float(eps),
@@ -353,11 +353,11 @@ class _SwavFn(torch.autograd.Function):
         k = pc.shape[0]
         L = C.lib()
         dev = x1.device
-        with torch.cuda.device(dev):
-            go = grad_out.to(torch.float32).contiguous()
+        with C.on_device(dev):
+            go = C.f32_scalar(grad_out)
             dz1, dz2, dpc = torch.empty_like(x1), torch.empty_like(x2), torch.empty_like(pc)
-            ws_bytes = L.ssvb_swav_workspace_bytes(nb, nbank, k, d)
-            ws = C.byte_buffer(ws_bytes, dev)
+            ws_bytes = C.cached_size("ssvb_swav_workspace_bytes", nb, nbank, k, d)
+            ws = C.workspace("swav", ws_bytes, dev)
             C.check(L.ssvb_swav_bwd(C.ptr(x1), C.ptr(x2), C.ptr(bk), C.ptr(pc), nb, nbank, k, d, _ld(x1), _ld(x2),
                                     _ld(bk) if bk is not None else 0, _ld(pc), temperature, C.ptr(go), C.ptr(saved),
                                     C.ptr(dz1), C.ptr(dz2), C.ptr(dpc), _ld(dz1), _ld(dz2), _ld(dpc), C.ptr(ws),
@@ -387,10 +387,10 @@ class SwavLoss(nn.Module):
         b, k = s.shape
         L = C.lib()
         dev = s.device
-        with torch.cuda.device(dev):
+        with C.on_device(dev):
             codes = torch.empty(b, k, dtype=torch.float32, device=dev)
-            ws_bytes = L.ssvb_sinkhorn_workspace_bytes(b, k)
-            ws = C.byte_buffer(ws_bytes, dev)
+            ws_bytes = C.cached_size("ssvb_sinkhorn_workspace_bytes", b, k)
+            ws = C.workspace("sinkhorn", ws_bytes, dev)
             C.check(L.ssvb_sinkhorn(C.ptr(s), b, k, s.stride(0), float(self.eps), int(self.n_iters), C.ptr(codes),
                                     codes.stride(0), C.ptr(ws), ws_bytes, C.stream_ptr(dev)), "ssvb_sinkhorn")
         return codes
