@@ -19,6 +19,7 @@ struct SkWs {
   float* smax;       // [1]
   float* upart;      // [grid x kpad]
   float* alpha;      // [kpad]
+  unsigned int* counter;
   size_t bytes;
   int grid;
   int kpad;
@@ -33,11 +34,13 @@ SkWs sk_ws(void* base, int64_t k) {
   w.smax = c.take<float>(4);
   w.upart = c.take<float>(static_cast<size_t>(w.grid) * w.kpad);
   w.alpha = c.take<float>(w.kpad);
+  w.counter = c.take<unsigned int>(4);
   w.bytes = c.used();
   return w;
 }
 
-__global__ void sk_max_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, float* part) {
+__global__ void sk_max_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, float* part,
+                              unsigned int* counter, float* __restrict__ out) {
   float m = -INFINITY;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -50,30 +53,74 @@ __global__ void sk_max_kernel(const float* __restrict__ s, int64_t b, int k, int
   if (threadIdx.x < 32) {
     float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
     t = warp_max(t);
-    if (threadIdx.x == 0) part[blockIdx.x] = t;
+    // last block to finish reduces the per-block maxima (max is order-independent -> deterministic)
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+      part[blockIdx.x] = t;
+      __threadfence();
+      is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncwarp();
+    is_last = __shfl_sync(0xffffffffu, is_last ? 1 : 0, 0) != 0;
+    if (is_last) {
+      __threadfence();
+      float m = -INFINITY;
+      for (unsigned int i = threadIdx.x; i < gridDim.x; i += 32) m = fmaxf(m, __ldcg(part + i));
+      m = warp_max(m);
+      if (threadIdx.x == 0) {
+        out[0] = m;
+        *counter = 0;
+      }
+    }
   }
 }
-__global__ void sk_max_final_kernel(const float* part, int n, float* out) {
-  float m = -INFINITY;
-  for (int i = threadIdx.x; i < n; i += 32) m = fmaxf(m, part[i]);
-  m = warp_max(m);
-  if (threadIdx.x == 0) out[0] = m;
+// alpha_k = (1/K) / sum_g upart[g][k].  block (32 columns, 8 row-slices): each thread sums every 8th partial row of
+// its column (coalesced 128-byte row segments), fixed-order combine through shared memory -> ~94 CTAs instead of 12.
+__global__ void sk_alpha_kernel(const float* __restrict__ upart, int grid, int kpad, int k, float* __restrict__ alpha) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float u = 0.f;
+  if (c < k)
+    for (int g = threadIdx.y; g < grid; g += 8) u += upart[static_cast<size_t>(g) * kpad + c];
+  sh[threadIdx.y][threadIdx.x] = u;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < k) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    alpha[c] = (1.f / static_cast<float>(k)) / t;
+  }
 }
 
-// alpha_k = (1/K) / sum_g upart[g][k]
-__global__ void sk_alpha_kernel(const float* __restrict__ upart, int grid, int kpad, int k, float* __restrict__ alpha) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= k) return;
-  float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;  // fixed summation order, 4 loads in flight
-  int g = 0;
-  for (; g + 4 <= grid; g += 4) {
-    u0 += upart[static_cast<size_t>(g) * kpad + c];
-    u1 += upart[static_cast<size_t>(g + 1) * kpad + c];
-    u2 += upart[static_cast<size_t>(g + 2) * kpad + c];
-    u3 += upart[static_cast<size_t>(g + 3) * kpad + c];
+// first alpha after the online-max PHASE 0 of the fast path: block partials carry their own reference maximum
+__global__ void sk_alpha0_kernel(const float* __restrict__ upart, const float* __restrict__ mpart, int grid, int kpad,
+                                 int k, float inv_eps_log2e, float* __restrict__ alpha, float* __restrict__ smax) {
+  __shared__ float sh[8][33];
+  __shared__ float msh[8][33];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  float m = -INFINITY;
+  for (int g = tid; g < grid; g += 256) m = fmaxf(m, mpart[g]);
+  msh[threadIdx.y][threadIdx.x] = m;
+  __syncthreads();
+  float M = -INFINITY;
+  for (int i = 0; i < 8; ++i)
+    for (int j = 0; j < 32; ++j) M = fmaxf(M, msh[i][j]);
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float u = 0.f;
+  if (c < k)
+    for (int g = threadIdx.y; g < grid; g += 8) {
+      const float mg = mpart[g];
+      if (mg != -INFINITY) u = fmaf(upart[static_cast<size_t>(g) * kpad + c], ex2f((mg - M) * inv_eps_log2e), u);
+    }
+  sh[threadIdx.y][threadIdx.x] = u;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < k) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    alpha[c] = (1.f / static_cast<float>(k)) / t;
   }
-  for (; g < grid; ++g) u0 += upart[static_cast<size_t>(g) * kpad + c];
-  alpha[c] = (1.f / static_cast<float>(k)) / ((u0 + u1) + (u2 + u3));
+  if (blockIdx.x == 0 && tid == 0) smax[0] = M;
 }
 
 // PHASE 0: u_k = sum_b E_bk                     (beta uniform: the reference's Q / sum(Q) scalar cancels)
@@ -167,7 +214,7 @@ template <int PHASE>
 __global__ void __launch_bounds__(256, 1)
 sk_rowreg_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, float inv_eps_log2e,
                  const float* __restrict__ smax, const float* __restrict__ alpha, float* __restrict__ upart, int kpad,
-                 float* __restrict__ codes, int64_t ldc) {
+                 float* __restrict__ codes, int64_t ldc, float* __restrict__ mpart) {
   extern __shared__ float sk_smem[];  // [kpad] alpha, then (PHASE != 2) [8][kpad] per-warp column sums
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int k4 = k >> 2;
@@ -176,7 +223,11 @@ sk_rowreg_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, floa
     for (int c = threadIdx.x; c < k; c += blockDim.x) alpha_s[c] = alpha[c];
     __syncthreads();
   }
-  const float shift = smax[0] * inv_eps_log2e;
+  // PHASE 0 needs no prior max pass: every warp keeps a running max Mw of the scores it has seen and rescales its
+  // column sums when Mw grows (online, like a streaming softmax); blocks are combined with exp((M_blk - M)/eps) in
+  // sk_alpha0_kernel, which also publishes the global max for the later passes.
+  float shift = (PHASE == 0) ? 0.f : smax[0] * inv_eps_log2e;
+  float Mw = -INFINITY;
   const float inv_b = 1.f / static_cast<float>(b);
   float4 acc[kSkNV];
 #pragma unroll
@@ -188,6 +239,19 @@ sk_rowreg_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, floa
     for (int j = 0; j < kSkNV; ++j) {
       const int c4 = lane + 32 * j;
       e[j] = (c4 < k4) ? __ldg(row + c4) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    if (PHASE == 0) {
+      float rm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kSkNV; ++j) rm = fmaxf(rm, fmaxf(fmaxf(e[j].x, e[j].y), fmaxf(e[j].z, e[j].w)));
+      rm = warp_max(rm);
+      if (rm > Mw) {  // warp-uniform
+        const float sc = ex2f((Mw - rm) * inv_eps_log2e);  // 0 on the first row (Mw = -inf)
+#pragma unroll
+        for (int j = 0; j < kSkNV; ++j) { acc[j].x *= sc; acc[j].y *= sc; acc[j].z *= sc; acc[j].w *= sc; }
+        Mw = rm;
+      }
+      shift = Mw * inv_eps_log2e;
     }
     float v = 0.f;
 #pragma unroll
@@ -231,16 +295,25 @@ sk_rowreg_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, floa
     }
   }
   if (PHASE != 2) {
+    __shared__ float mw_s[8];
     float* mine = sk_smem + kpad + w * kpad;
 #pragma unroll
     for (int j = 0; j < kSkNV; ++j) {
       const int c4 = lane + 32 * j;
       if (c4 < k4) reinterpret_cast<float4*>(mine)[c4] = acc[j];
     }
+    if (PHASE == 0 && lane == 0) mw_s[w] = Mw;
     __syncthreads();
+    float wsc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    if (PHASE == 0) {
+      float mb = -INFINITY;
+      for (int ww = 0; ww < nwarp; ++ww) mb = fmaxf(mb, mw_s[ww]);
+      for (int ww = 0; ww < nwarp; ++ww) wsc[ww] = (mw_s[ww] == -INFINITY) ? 0.f : ex2f((mw_s[ww] - mb) * inv_eps_log2e);
+      if (threadIdx.x == 0) mpart[blockIdx.x] = mb;
+    }
     for (int c = threadIdx.x; c < k; c += blockDim.x) {
       float t = 0.f;
-      for (int ww = 0; ww < nwarp; ++ww) t += sk_smem[kpad + ww * kpad + c];
+      for (int ww = 0; ww < nwarp; ++ww) t = fmaf(sk_smem[kpad + ww * kpad + c], wsc[ww], t);
       upart[static_cast<size_t>(blockIdx.x) * kpad + c] = t;
     }
   }
@@ -250,7 +323,8 @@ template <int PHASE>
 int sk_launch_fast(int grid, size_t smem, cudaStream_t s, const float* scores, int64_t b, int k, int64_t ld, float iel,
                    const SkWs& ws, float* codes, int64_t ldc) {
   SSVB_CUDA(cudaFuncSetAttribute(sk_rowreg_kernel<PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  sk_rowreg_kernel<PHASE><<<grid, 256, smem, s>>>(scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart, ws.kpad, codes, ldc);
+  sk_rowreg_kernel<PHASE><<<grid, 256, smem, s>>>(scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart, ws.kpad, codes, ldc,
+                                                  ws.smax_part);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
@@ -292,24 +366,30 @@ int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, f
                     !(reinterpret_cast<uintptr_t>(scores) & 15) && !(reinterpret_cast<uintptr_t>(codes) & 15);
   const size_t smem_fast = static_cast<size_t>(9) * ws.kpad * 4;
   const int fgrid = num_sms();  // one 8-warp CTA per SM; partial rows [fgrid x kpad]
-  sk_max_kernel<<<ws.grid, 256, 0, s>>>(scores, b, kk, ld_scores, ws.smax_part);
-  SSVB_LAUNCH_CHECK();
-  sk_max_final_kernel<<<1, 32, 0, s>>>(ws.smax_part, ws.grid, ws.smax);
-  SSVB_LAUNCH_CHECK();
+  if (!(fast && n_iters > 0)) {  // the fast path finds the max online inside its first pass
+    SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
+    sk_max_kernel<<<ws.grid, 256, 0, s>>>(scores, b, kk, ld_scores, ws.smax_part, ws.counter, ws.smax);
+    SSVB_LAUNCH_CHECK();
+  }
   const unsigned agrid = static_cast<unsigned>(ceil_div(k, 256));  // (alpha / fill kernels: 256 columns per CTA)
   if (n_iters <= 0) {
     // no iterations: codes = E / rowsum(E)  (alpha = 1)
     fill_kernel<<<agrid, 256, 0, s>>>(ws.alpha, k, 1.f);
     SSVB_LAUNCH_CHECK();
   } else {
-    if (fast) SSVB_TRY(sk_launch_fast<0>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
-    else SSVB_TRY(sk_launch<0>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
-    sk_alpha_kernel<<<agrid, 256, 0, s>>>(ws.upart, fast ? fgrid : ws.grid, ws.kpad, kk, ws.alpha);
+    if (fast) {
+      SSVB_TRY(sk_launch_fast<0>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+      sk_alpha0_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, 8), 0, s>>>(ws.upart, ws.smax_part, fgrid, ws.kpad,
+                                                                                      kk, iel, ws.alpha, ws.smax);
+    } else {
+      SSVB_TRY(sk_launch<0>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+      sk_alpha_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, 8), 0, s>>>(ws.upart, ws.grid, ws.kpad, kk, ws.alpha);
+    }
     SSVB_LAUNCH_CHECK();
     for (int it = 1; it < n_iters; ++it) {
       if (fast) SSVB_TRY(sk_launch_fast<1>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
       else SSVB_TRY(sk_launch<1>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
-      sk_alpha_kernel<<<agrid, 256, 0, s>>>(ws.upart, fast ? fgrid : ws.grid, ws.kpad, kk, ws.alpha);
+      sk_alpha_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, 8), 0, s>>>(ws.upart, fast ? fgrid : ws.grid, ws.kpad, kk, ws.alpha);
       SSVB_LAUNCH_CHECK();
     }
   }
