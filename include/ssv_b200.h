@@ -160,12 +160,67 @@ int ssvb_barlow_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
                     void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * a4/e  Distributed Barlow Twins (the reference has no multi-GPU path: semantics =
+ *     BarlowLoss on the rank-order concatenation of all ranks' rows, n_global = world * n_local, every
+ *     rank receiving the gradient rows of its own inputs).  Batch rows are sharded; the exchange steps are
+ *     the caller's collectives (NCCL through torch.distributed), the stages below are everything between:
+ *     1 stats:     local column (mean, M2) of both views -> stats_local [2 views][2][d]
+ *                  -> caller ALL-GATHERS into stats_all [world][2][2][d]
+ *     2 xcorr:     Chan-combine in rank order -> global mean / unbiased std; standardise the local rows (bf16);
+ *                  c_partial [d x d] fp32 = Xi~_r^T Xj~_r / n_global
+ *                  -> caller REDUCE-SCATTERS (or all-reduces) c_partial: the cross-correlation all-reduce
+ *     3 epilogue:  loss terms + dC (bf16) of a row slab [row0, row0+rows) of the summed matrix
+ *                  -> caller ALL-GATHERS the dC slabs (the second half of the all-reduce, in bf16) and
+ *                  all-reduces the scalar loss partials
+ *     4 bwd_gemm:  dT_i = Xj~ dC^T / n_global, dT_j = Xi~ dC / n_global for the local rows (kept in `workspace`)
+ *                  and their local column sums colsum_local [2 views][2][d] (sum dT, sum dT*x~)
+ *                  -> caller ALL-REDUCES colsum (sum)
+ *     5 bwd_finish: standardise (+ row-normalise) backward with the global reductions -> dzi, dzj.
+ *     The same `workspace` buffer must be passed to bwd_gemm and bwd_finish without other use in between.
+ * ------------------------------------------------------------------------------------- */
+size_t ssvb_barlow_dist_saved_bytes(int64_t n_local, int64_t d);
+size_t ssvb_barlow_dist_workspace_bytes(int64_t n_local, int64_t d);
+int ssvb_barlow_dist_stats(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                           int64_t ld_zj, int normalize, float* stats_local, void* saved, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int ssvb_barlow_dist_xcorr(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                           int64_t ld_zj, int normalize, const float* stats_all, int64_t world, float* c_partial,
+                           void* saved, void* stream);
+int ssvb_barlow_dist_epilogue(const float* c_rows, int64_t row0, int64_t rows, int64_t d, float lambda,
+                              void* dC_rows /* bf16 [rows x d] */, float* loss_partial, void* workspace,
+                              size_t workspace_bytes, void* stream);
+int ssvb_barlow_dist_bwd_gemm(const float* zi, const float* zj, int64_t n_local, int64_t n_global, int64_t d,
+                              int64_t ld_zi, int64_t ld_zj, int normalize, const void* dC /* bf16 [d x d] */,
+                              const void* saved, float* colsum_local, void* workspace, size_t workspace_bytes,
+                              void* stream);
+int ssvb_barlow_dist_bwd_finish(const float* zi, const float* zj, int64_t n_local, int64_t n_global, int64_t d,
+                                int64_t ld_zi, int64_t ld_zj, int normalize, const float* colsum_global,
+                                const float* grad_out, const void* saved, float* dzi, float* dzj, int64_t ld_dzi,
+                                int64_t ld_dzj, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * a5  Sinkhorn-Knopp codes — replaces SwavLoss.compute_codes_sinkhorn (utils/losses.py:213-224).
  *     scores: [b x k] -> codes [b x k] (rows sum to 1).  ld % 4 == 0 not required.
  * ------------------------------------------------------------------------------------- */
 size_t ssvb_sinkhorn_workspace_bytes(int64_t b, int64_t k);
 int ssvb_sinkhorn(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters,
                   float* codes, int64_t ld_codes, void* workspace, size_t workspace_bytes, void* stream);
+
+/* a5/e  Distributed Sinkhorn: the B sample rows are sharded (b_local per rank, b_global in total),
+ *     prototypes / columns replicated.  The only cross-rank quantity is the K-vector of prototype marginals:
+ *       pass(phase 0): u_local[0..k) = sum_b E_bk relative to this rank's maximum, u_local[k] = that maximum;
+ *       pass(phase 1): u_local[0..k) = sum_b E_bk / (b_global v_b)  (needs the global alpha [k] and smax [1]);
+ *       pass(phase 2): codes of the local rows.
+ *     Between passes the caller ALL-GATHERS u_local (k+1 floats per rank) and calls ssvb_sinkhorn_dist_alpha, which
+ *     combines the blocks in rank order (identical on every rank: the all-reduce of the marginals) into
+ *     alpha_k = (1/K)/u_k and, after phase 0, the global maximum.  n_iters iterations = phase 0, (n_iters-1) x
+ *     phase 1, phase 2 — the same schedule as ssvb_sinkhorn. */
+int ssvb_sinkhorn_dist_pass(int phase, const float* scores, int64_t b_local, int64_t b_global, int64_t k,
+                            int64_t ld_scores, float eps, const float* alpha, const float* smax, float* u_local,
+                            float* codes, int64_t ld_codes, void* workspace, size_t workspace_bytes, void* stream);
+int ssvb_sinkhorn_dist_alpha(const float* u_all /* world blocks of k+1 floats, rank_stride floats apart */,
+                             int64_t world, int64_t rank_stride, int64_t k, int phase0, float eps, float* alpha,
+                             float* smax, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * a6  SwAV loss — replaces SwavLoss.forward (utils/losses.py:226-235; call models/swav.py:140).
@@ -183,6 +238,19 @@ int ssvb_swav_bwd(const float* z1, const float* z2, const float* bank, const flo
                   int64_t ld_proto, float temperature, const float* grad_out, const void* saved, float* dz1,
                   float* dz2, float* dproto, int64_t ld_dz1, int64_t ld_dz2, int64_t ld_dproto, void* workspace,
                   size_t workspace_bytes, void* stream);
+
+/* a6/e  Distributed SwAV loss: every rank holds nb live rows (+ nbank bank rows) per view; B' is summed over ranks
+ *     (bp_global).  scores (caller buffer, fp32 [2*(nb+nbank) x ssvb_swav_kpad(k)], view 1 rows then view 2 rows) ->
+ *     caller runs the distributed Sinkhorn passes on each view's half -> codes (same layout) -> dist_ce writes this
+ *     rank's share of the loss (sum of local row terms / bp_global; the caller all-reduces it) and the dscores used by
+ *     ssvb_swav_bwd (unchanged; its dproto is this rank's partial: the caller all-reduces it). */
+int64_t ssvb_swav_kpad(int64_t k);
+int ssvb_swav_dist_scores(const float* z1, const float* z2, const float* bank, const float* prototypes, int64_t nb,
+                          int64_t nbank, int64_t k, int64_t d, int64_t ld_z1, int64_t ld_z2, int64_t ld_bank,
+                          int64_t ld_proto, float* scores, void* saved, void* stream);
+int ssvb_swav_dist_ce(const float* scores, const float* codes, int64_t nb, int64_t nbank, int64_t bp_global,
+                      int64_t k, int64_t d, float temperature, float* loss_local, void* saved, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * a8/a9  Row-dot regression losses.

@@ -61,6 +61,46 @@ BarlowWs barlow_ws(void* base, int64_t n, int64_t d) {
   return w;
 }
 
+
+// distributed: the saved blob holds only LOCAL rows; dC is a caller-visible tensor (it is all-gathered)
+struct BarlowDistSaved {
+  __nv_bfloat16 *xi, *xj;                    // standardised local rows [n_local x d]
+  float *mean_i, *rstd_i, *mean_j, *rstd_j;  // [d] GLOBAL statistics
+  float *inv_i, *inv_j;                      // [n_local]
+  size_t bytes;
+};
+BarlowDistSaved barlow_dist_saved(void* base, int64_t n, int64_t d) {
+  Carver c(base);
+  BarlowDistSaved s;
+  s.xi = c.take<__nv_bfloat16>(n * d);
+  s.xj = c.take<__nv_bfloat16>(n * d);
+  s.mean_i = c.take<float>(d);
+  s.rstd_i = c.take<float>(d);
+  s.mean_j = c.take<float>(d);
+  s.rstd_j = c.take<float>(d);
+  s.inv_i = c.take<float>(n);
+  s.inv_j = c.take<float>(n);
+  s.bytes = c.used();
+  return s;
+}
+struct BarlowDistWs {
+  float* colpart;   // [2 views][kRowSplit][2][d]
+  float *dti, *dtj; // backward: [n_local x d] fp32 each (live between bwd_gemm and bwd_finish)
+  float* colred;    // [2][2][d]
+  size_t bytes;
+};
+constexpr int kEpiGridMax = 148 * 8;
+BarlowDistWs barlow_dist_ws(void* base, int64_t n, int64_t d) {
+  Carver c(base);
+  BarlowDistWs w;
+  w.colpart = c.take<float>(2 * kRowSplit * 2 * d);
+  w.dti = c.take<float>(n * d);
+  w.dtj = c.take<float>(n * d);
+  w.colred = c.take<float>(4 * d);
+  w.bytes = c.used();
+  return w;
+}
+
 // row 1/max(||x||, eps): one warp per row
 __global__ void row_invnorm_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld, float* __restrict__ inv) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -197,6 +237,105 @@ __global__ void barlow_finish_kernel(const float* __restrict__ x, int64_t ldx, c
   }
 }
 
+
+// ---- distributed (batch rows sharded over ranks) -------------------------------------------------------------
+// local column statistics of one rank: out0 = local mean, out1 = local M2 = sum_r (x - mean_local)^2
+__global__ void col_local_moments_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ x,
+                                         const float* __restrict__ inv_row, int64_t n, int d, float* __restrict__ out0,
+                                         float* __restrict__ out1) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= d) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < nsplit; ++i) {
+    s1 += part[(static_cast<int64_t>(i) * 2 + 0) * d + col];
+    s2 += part[(static_cast<int64_t>(i) * 2 + 1) * d + col];
+  }
+  const float fn = static_cast<float>(n);
+  const float v0 = x[col] * (inv_row ? inv_row[0] : 1.f);
+  out0[col] = v0 + s1 / fn;
+  out1[col] = fmaxf(s2 - s1 * s1 / fn, 0.f);
+}
+
+// Chan's pairwise combination of the per-rank (count, mean, M2) in RANK ORDER (identical on every rank) ->
+// global mean and 1/std (unbiased over n_global = world * n_local rows).  stats_all: [world][2 views][2][d].
+__global__ void col_combine_moments_kernel(const float* __restrict__ stats_all, int world, int64_t n_local, int d,
+                                           int view, float* __restrict__ mean, float* __restrict__ rstd) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= d) return;
+  const float nb = static_cast<float>(n_local);
+  float na = 0.f, mu = 0.f, m2 = 0.f;
+  for (int r = 0; r < world; ++r) {
+    const float* blk = stats_all + (static_cast<int64_t>(r) * 2 + view) * 2 * d;
+    const float mb = blk[col], m2b = blk[d + col];
+    const float nt = na + nb, delta = mb - mu;
+    mu += delta * (nb / nt);
+    m2 += m2b + delta * delta * (na * nb / nt);
+    na = nt;
+  }
+  mean[col] = mu;
+  rstd[col] = rsqrtf(m2 / (na - 1.f));
+}
+
+// loss terms + dC (bf16) for `rows` rows (global rows row0 ..) of the SUMMED cross-correlation matrix
+__global__ void xcorr_epilogue_kernel(const float* __restrict__ c, int64_t ldc, int64_t row0, int64_t rows, int d4,
+                                      float lambda, __nv_bfloat16* __restrict__ dC, int64_t ld_dc,
+                                      float* __restrict__ part) {
+  float acc = 0.f;
+  const int64_t total = rows * d4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / d4;
+    const int c4 = static_cast<int>(i - r * d4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(c + r * ldc) + c4);
+    const float e[4] = {v.x, v.y, v.z, v.w};
+    float g[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool diag = (row0 + r) == static_cast<int64_t>(4 * c4 + j);
+      const float t = diag ? e[j] - 1.f : e[j];
+      const float w = diag ? 1.f : lambda;
+      acc = fmaf(w * t, t, acc);
+      g[j] = 2.f * w * t;
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(g[0], g[1]), hi = __floats2bfloat162_rn(g[2], g[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dC + r * ld_dc + 4 * c4) = pk;
+  }
+  __shared__ float red[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+  }
+}
+
+// raw column sums of the backward reductions: out0 = sum_0 dT, out1 = sum_0 dT x~  (local rows; all-reduced by the caller)
+__global__ void col_sum_partials_kernel(const float* __restrict__ part, int nsplit, int d, float* __restrict__ out0,
+                                        float* __restrict__ out1) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= d) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < nsplit; ++i) {
+    s1 += part[(static_cast<int64_t>(i) * 2 + 0) * d + col];
+    s2 += part[(static_cast<int64_t>(i) * 2 + 1) * d + col];
+  }
+  out0[col] = s1;
+  out1[col] = s2;
+}
+// m1 = sum / n_global, m2 = sum / (n_global - 1) for the 2 views x 2 reductions: colsum [2][2][d] -> colred [2][2][d]
+__global__ void col_scale_sums_kernel(const float* __restrict__ colsum, int d, float inv_n, float inv_nm1,
+                                      float* __restrict__ colred) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4 * d) return;
+  colred[i] = colsum[i] * (((i / d) & 1) ? inv_nm1 : inv_n);
+}
+
+
 int check_rows(const void* p, int64_t ld) {
   if (!p) return SSVB_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(p) & 15) || (ld & 3)) return SSVB_ERR_ALIGNMENT;
@@ -326,6 +465,185 @@ int ssvb_barlow_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   barlow_finish_kernel<<<static_cast<unsigned>(n), 256, 0, s>>>(zj, ld_zj, inv_j, sv.mean_j, sv.rstd_j, ws.dtj, d,
                                                               ws.colred + 2 * d, ws.colred + 3 * d, static_cast<int>(d),
                                                               grad_out, dzj, ld_dzj);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Distributed Barlow Twins: batch rows sharded over `world` ranks, n_local rows each; semantics =
+// BarlowLoss on the rank-order concatenation (n_global = world * n_local rows).  See include/ssv_b200.h.
+// ------------------------------------------------------------------------------------------------------------
+size_t ssvb_barlow_dist_saved_bytes(int64_t n_local, int64_t d) {
+  if (n_local <= 0 || d <= 0) return 0;
+  return barlow_dist_saved(nullptr, n_local, d).bytes;
+}
+size_t ssvb_barlow_dist_workspace_bytes(int64_t n_local, int64_t d) {
+  if (n_local <= 0 || d <= 0) return 0;
+  return barlow_dist_ws(nullptr, n_local, d).bytes;
+}
+
+int ssvb_barlow_dist_stats(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                           int normalize, float* stats_local, void* saved, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (n_local < 1 || d <= 0) return SSVB_ERR_INVALID;
+  if (d % 8) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  if (!stats_local || !saved || !workspace) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_barlow_dist_workspace_bytes(n_local, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BarlowDistSaved sv = barlow_dist_saved(saved, n_local, d);
+  BarlowDistWs ws = barlow_dist_ws(workspace, n_local, d);
+  const int di = static_cast<int>(d);
+  dim3 grid(static_cast<unsigned>(ceil_div(d, kColsPerBlock)), kRowSplit), block(32, 8);
+  for (int v = 0; v < 2; ++v) {
+    const float* x = v ? zj : zi;
+    const int64_t ld = v ? ld_zj : ld_zi;
+    float* inv_row = v ? sv.inv_j : sv.inv_i;
+    const float* inv = nullptr;
+    if (normalize) {
+      row_invnorm_kernel<<<static_cast<unsigned>(ceil_div(n_local, 8)), 256, 0, s>>>(x, n_local, di, ld, inv_row);
+      SSVB_LAUNCH_CHECK();
+      inv = inv_row;
+    }
+    float* part = ws.colpart + v * kRowSplit * 2 * d;
+    col_partials_kernel<0><<<grid, block, 0, s>>>(x, ld, inv, nullptr, 0, nullptr, nullptr, n_local, di, part);
+    SSVB_LAUNCH_CHECK();
+    col_local_moments_kernel<<<static_cast<unsigned>(ceil_div(d, 256)), 256, 0, s>>>(
+        part, kRowSplit, x, inv, n_local, di, stats_local + (v * 2 + 0) * d, stats_local + (v * 2 + 1) * d);
+    SSVB_LAUNCH_CHECK();
+  }
+  return SSVB_OK;
+}
+
+int ssvb_barlow_dist_xcorr(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                           int normalize, const float* stats_all, int64_t world, float* c_partial, void* saved,
+                           void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (n_local < 1 || d <= 0 || world < 1 || n_local * world < 2) return SSVB_ERR_INVALID;
+  if (d % 8) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  SSVB_TRY(check_rows(c_partial, d));
+  if (!stats_all || !saved) return SSVB_ERR_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BarlowDistSaved sv = barlow_dist_saved(saved, n_local, d);
+  const int di = static_cast<int>(d);
+  const unsigned cgrid = static_cast<unsigned>(ceil_div(d, 256));
+  col_combine_moments_kernel<<<cgrid, 256, 0, s>>>(stats_all, static_cast<int>(world), n_local, di, 0, sv.mean_i, sv.rstd_i);
+  SSVB_LAUNCH_CHECK();
+  col_combine_moments_kernel<<<cgrid, 256, 0, s>>>(stats_all, static_cast<int>(world), n_local, di, 1, sv.mean_j, sv.rstd_j);
+  SSVB_LAUNCH_CHECK();
+  const int64_t total = n_local * (d / 4);
+  int64_t g = ceil_div(total, 256 * 4);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  standardize_kernel<<<static_cast<unsigned>(g), 256, 0, s>>>(zi, ld_zi, normalize ? sv.inv_i : nullptr, sv.mean_i,
+                                                              sv.rstd_i, n_local, static_cast<int>(d / 4), sv.xi, d);
+  SSVB_LAUNCH_CHECK();
+  standardize_kernel<<<static_cast<unsigned>(g), 256, 0, s>>>(zj, ld_zj, normalize ? sv.inv_j : nullptr, sv.mean_j,
+                                                              sv.rstd_j, n_local, static_cast<int>(d / 4), sv.xj, d);
+  SSVB_LAUNCH_CHECK();
+  // partial C_r = Xi~_r^T Xj~_r / n_global (fp32, summed over ranks by the caller's collective)
+  GemmParams p{};
+  p.M = di;
+  p.N = di;
+  p.K = static_cast<int>(n_local);
+  p.alpha = 1.f / static_cast<float>(n_local * world);
+  p.out = c_partial;
+  p.ldc = d;
+  SSVB_TRY(launch_gemm({sv.xi, d, true}, {sv.xj, d, true}, p, 256, EPI_STORE_F32, 0, s));
+  return SSVB_OK;
+}
+
+int ssvb_barlow_dist_epilogue(const float* c_rows, int64_t row0, int64_t rows, int64_t d, float lambda, void* dC_rows,
+                              float* loss_partial, void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (rows <= 0 || d <= 0 || row0 < 0 || row0 + rows > d) return SSVB_ERR_INVALID;
+  if (d % 8) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(c_rows, d));
+  if (!dC_rows || !loss_partial || !workspace) return SSVB_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(dC_rows) & 15) return SSVB_ERR_ALIGNMENT;
+  if (workspace_bytes < static_cast<size_t>(kEpiGridMax) * sizeof(float)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* part = static_cast<float*>(workspace);
+  int64_t g = ceil_div(rows * (d / 4), 256 * 4);
+  if (g > kEpiGridMax) g = kEpiGridMax;
+  xcorr_epilogue_kernel<<<static_cast<unsigned>(g), 256, 0, s>>>(c_rows, d, row0, rows, static_cast<int>(d / 4), lambda,
+                                                                 static_cast<__nv_bfloat16*>(dC_rows), d, part);
+  SSVB_LAUNCH_CHECK();
+  sum_partials_kernel<<<1, 256, 0, s>>>(part, static_cast<int>(g), 1.f, loss_partial);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_barlow_dist_bwd_gemm(const float* zi, const float* zj, int64_t n_local, int64_t n_global, int64_t d,
+                              int64_t ld_zi, int64_t ld_zj, int normalize, const void* dC, const void* saved,
+                              float* colsum_local, void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (n_local < 1 || n_global < 2 || n_global < n_local || d <= 0) return SSVB_ERR_INVALID;
+  if (d % 8) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  if (!dC || !saved || !colsum_local || !workspace) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_barlow_dist_workspace_bytes(n_local, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BarlowDistSaved sv = barlow_dist_saved(const_cast<void*>(saved), n_local, d);
+  BarlowDistWs ws = barlow_dist_ws(workspace, n_local, d);
+  const int di = static_cast<int>(d);
+  GemmParams p{};
+  p.M = static_cast<int>(n_local);
+  p.N = di;
+  p.K = di;
+  p.alpha = 1.f / static_cast<float>(n_global);
+  p.ldc = d;
+  p.out = ws.dti;  // dTi[n, a] = sum_b Xj~[n, b] dC[a, b]
+  SSVB_TRY(launch_gemm({sv.xj, d, false}, {dC, d, false}, p, 256, EPI_STORE_F32, 0, s));
+  p.out = ws.dtj;  // dTj[n, b] = sum_a Xi~[n, a] dC[a, b]
+  SSVB_TRY(launch_gemm({sv.xi, d, false}, {dC, d, true}, p, 256, EPI_STORE_F32, 0, s));
+  dim3 grid(static_cast<unsigned>(ceil_div(d, kColsPerBlock)), kRowSplit), block(32, 8);
+  const unsigned fgrid = static_cast<unsigned>(ceil_div(d, 256));
+  for (int v = 0; v < 2; ++v) {
+    float* part = ws.colpart + v * kRowSplit * 2 * d;
+    col_partials_kernel<1><<<grid, block, 0, s>>>(v ? zj : zi, v ? ld_zj : ld_zi,
+                                                  normalize ? (v ? sv.inv_j : sv.inv_i) : nullptr, v ? ws.dtj : ws.dti, d,
+                                                  v ? sv.mean_j : sv.mean_i, v ? sv.rstd_j : sv.rstd_i, n_local, di, part);
+    SSVB_LAUNCH_CHECK();
+    col_sum_partials_kernel<<<fgrid, 256, 0, s>>>(part, kRowSplit, di, colsum_local + (v * 2 + 0) * d,
+                                                  colsum_local + (v * 2 + 1) * d);
+    SSVB_LAUNCH_CHECK();
+  }
+  return SSVB_OK;
+}
+
+int ssvb_barlow_dist_bwd_finish(const float* zi, const float* zj, int64_t n_local, int64_t n_global, int64_t d,
+                                int64_t ld_zi, int64_t ld_zj, int normalize, const float* colsum_global,
+                                const float* grad_out, const void* saved, float* dzi, float* dzj, int64_t ld_dzi,
+                                int64_t ld_dzj, void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (n_local < 1 || n_global < 2 || n_global < n_local || d <= 0) return SSVB_ERR_INVALID;
+  if (d % 8) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  SSVB_TRY(check_rows(dzi, ld_dzi));
+  SSVB_TRY(check_rows(dzj, ld_dzj));
+  if (!colsum_global || !grad_out || !saved || !workspace) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_barlow_dist_workspace_bytes(n_local, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BarlowDistSaved sv = barlow_dist_saved(const_cast<void*>(saved), n_local, d);
+  BarlowDistWs ws = barlow_dist_ws(workspace, n_local, d);
+  const int di = static_cast<int>(d);
+  col_scale_sums_kernel<<<static_cast<unsigned>(ceil_div(4 * d, 256)), 256, 0, s>>>(
+      colsum_global, di, 1.f / static_cast<float>(n_global), 1.f / static_cast<float>(n_global - 1), ws.colred);
+  SSVB_LAUNCH_CHECK();
+  barlow_finish_kernel<<<static_cast<unsigned>(n_local), 256, 0, s>>>(
+      zi, ld_zi, normalize ? sv.inv_i : nullptr, sv.mean_i, sv.rstd_i, ws.dti, d, ws.colred, ws.colred + d, di, grad_out,
+      dzi, ld_dzi);
+  SSVB_LAUNCH_CHECK();
+  barlow_finish_kernel<<<static_cast<unsigned>(n_local), 256, 0, s>>>(
+      zj, ld_zj, normalize ? sv.inv_j : nullptr, sv.mean_j, sv.rstd_j, ws.dtj, d, ws.colred + 2 * d, ws.colred + 3 * d, di,
+      grad_out, dzj, ld_dzj);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }

@@ -76,7 +76,8 @@ __global__ void sk_max_kernel(const float* __restrict__ s, int64_t b, int k, int
 }
 // alpha_k = (1/K) / sum_g upart[g][k].  block (32 columns, 8 row-slices): each thread sums every 8th partial row of
 // its column (coalesced 128-byte row segments), fixed-order combine through shared memory -> ~94 CTAs instead of 12.
-__global__ void sk_alpha_kernel(const float* __restrict__ upart, int grid, int kpad, int k, float* __restrict__ alpha) {
+__global__ void sk_alpha_kernel(const float* __restrict__ upart, int grid, int kpad, int k, float* __restrict__ alpha,
+                                int raw = 0) {
   __shared__ float sh[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float u = 0.f;
@@ -94,7 +95,8 @@ __global__ void sk_alpha_kernel(const float* __restrict__ upart, int grid, int k
 
 // first alpha after the online-max PHASE 0 of the fast path: block partials carry their own reference maximum
 __global__ void sk_alpha0_kernel(const float* __restrict__ upart, const float* __restrict__ mpart, int grid, int kpad,
-                                 int k, float inv_eps_log2e, float* __restrict__ alpha, float* __restrict__ smax) {
+                                 int k, float inv_eps_log2e, float* __restrict__ alpha, float* __restrict__ smax,
+                                 int raw = 0) {
   __shared__ float sh[8][33];
   __shared__ float msh[8][33];
   const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -118,9 +120,34 @@ __global__ void sk_alpha0_kernel(const float* __restrict__ upart, const float* _
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
-    alpha[c] = (1.f / static_cast<float>(k)) / t;
+    alpha[c] = raw ? t : (1.f / static_cast<float>(k)) / t;
   }
   if (blockIdx.x == 0 && tid == 0) smax[0] = M;
+}
+
+// distributed: combine the gathered per-rank column sums u_all [world][k+1] (entry k of a PHASE-0 block = that rank's
+// reference maximum) in RANK ORDER -> alpha_k = (1/K) / u_k and (PHASE 0) the global maximum.
+__global__ void sk_dist_alpha_kernel(const float* __restrict__ u_all, int world, int64_t rank_stride, int k, int phase0,
+                                     float inv_eps_log2e,
+                                     float* __restrict__ alpha, float* __restrict__ smax) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  float M = -INFINITY;
+  if (phase0)
+    for (int r = 0; r < world; ++r) M = fmaxf(M, u_all[r * rank_stride + k]);
+  if (c < k) {
+    float u = 0.f;
+    for (int r = 0; r < world; ++r) {
+      const float* blk = u_all + r * rank_stride;
+      if (phase0) {
+        const float mr = blk[k];
+        if (mr != -INFINITY) u = fmaf(blk[c], ex2f((mr - M) * inv_eps_log2e), u);
+      } else {
+        u += blk[c];
+      }
+    }
+    alpha[c] = (1.f / static_cast<float>(k)) / u;
+  }
+  if (phase0 && blockIdx.x == 0 && threadIdx.x == 0) smax[0] = M;
 }
 
 // PHASE 0: u_k = sum_b E_bk                     (beta uniform: the reference's Q / sum(Q) scalar cancels)
@@ -133,7 +160,8 @@ constexpr int kSkJ = 16;
 template <int PHASE, bool REGACC>
 __global__ void sk_pass_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, float inv_eps_log2e,
                                const float* __restrict__ smax, const float* __restrict__ alpha,
-                               float* __restrict__ upart, int kpad, float* __restrict__ codes, int64_t ldc) {
+                               float* __restrict__ upart, int kpad, float* __restrict__ codes, int64_t ldc,
+                               float inv_b) {
   extern __shared__ float sk_smem[];
   __shared__ float beta_s[32];
   const int nwarp = blockDim.x >> 5;
@@ -148,7 +176,6 @@ __global__ void sk_pass_kernel(const float* __restrict__ s, int64_t b, int k, in
     for (int c = threadIdx.x; c < kpad; c += blockDim.x) uloc[c] = 0.f;
     __syncthreads();
   }
-  const float inv_b = 1.f / static_cast<float>(b);
   for (int64_t base = static_cast<int64_t>(blockIdx.x) * nwarp; base < b; base += static_cast<int64_t>(gridDim.x) * nwarp) {
     const int64_t r = base + w;
     if (r < b) {
@@ -214,7 +241,7 @@ template <int PHASE>
 __global__ void __launch_bounds__(256, 1)
 sk_rowreg_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, float inv_eps_log2e,
                  const float* __restrict__ smax, const float* __restrict__ alpha, float* __restrict__ upart, int kpad,
-                 float* __restrict__ codes, int64_t ldc, float* __restrict__ mpart) {
+                 float* __restrict__ codes, int64_t ldc, float* __restrict__ mpart, float inv_b) {
   extern __shared__ float sk_smem[];  // [kpad] alpha, then (PHASE != 2) [8][kpad] per-warp column sums
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int k4 = k >> 2;
@@ -228,7 +255,6 @@ sk_rowreg_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, floa
   // sk_alpha0_kernel, which also publishes the global max for the later passes.
   float shift = (PHASE == 0) ? 0.f : smax[0] * inv_eps_log2e;
   float Mw = -INFINITY;
-  const float inv_b = 1.f / static_cast<float>(b);
   float4 acc[kSkNV];
 #pragma unroll
   for (int j = 0; j < kSkNV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -321,27 +347,27 @@ sk_rowreg_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, floa
 
 template <int PHASE>
 int sk_launch_fast(int grid, size_t smem, cudaStream_t s, const float* scores, int64_t b, int k, int64_t ld, float iel,
-                   const SkWs& ws, float* codes, int64_t ldc) {
+                   const SkWs& ws, float* codes, int64_t ldc, float inv_b) {
   SSVB_CUDA(cudaFuncSetAttribute(sk_rowreg_kernel<PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   sk_rowreg_kernel<PHASE><<<grid, 256, smem, s>>>(scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart, ws.kpad, codes, ldc,
-                                                  ws.smax_part);
+                                                  ws.smax_part, inv_b);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
 
 template <int PHASE>
 int sk_launch(bool regacc, int grid, int threads, size_t smem, cudaStream_t s, const float* scores, int64_t b, int k,
-              int64_t ld, float iel, const SkWs& ws, float* codes, int64_t ldc) {
+              int64_t ld, float iel, const SkWs& ws, float* codes, int64_t ldc, float inv_b) {
   if (regacc) {
     SSVB_CUDA(cudaFuncSetAttribute(sk_pass_kernel<PHASE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
     sk_pass_kernel<PHASE, true><<<grid, threads, smem, s>>>(scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart,
-                                                            ws.kpad, codes, ldc);
+                                                            ws.kpad, codes, ldc, inv_b);
   } else {
     SSVB_CUDA(cudaFuncSetAttribute(sk_pass_kernel<PHASE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
     sk_pass_kernel<PHASE, false><<<grid, threads, smem, s>>>(scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart,
-                                                             ws.kpad, codes, ldc);
+                                                             ws.kpad, codes, ldc, inv_b);
   }
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
@@ -356,6 +382,7 @@ int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, f
   SkWs ws = sk_ws(workspace, k);
   const int kk = static_cast<int>(k);
   const float iel = SSVB_LOG2E / eps;
+  const float inv_b = 1.f / static_cast<float>(b);
   int nwarp = 8;
   while (nwarp > 1 && static_cast<size_t>(nwarp + 1) * ws.kpad * 4 > 200 * 1024) nwarp >>= 1;
   const size_t smem = static_cast<size_t>(nwarp + 1) * ws.kpad * 4;
@@ -378,23 +405,83 @@ int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, f
     SSVB_LAUNCH_CHECK();
   } else {
     if (fast) {
-      SSVB_TRY(sk_launch_fast<0>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+      SSVB_TRY(sk_launch_fast<0>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
       sk_alpha0_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, 8), 0, s>>>(ws.upart, ws.smax_part, fgrid, ws.kpad,
                                                                                       kk, iel, ws.alpha, ws.smax);
     } else {
-      SSVB_TRY(sk_launch<0>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+      SSVB_TRY(sk_launch<0>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
       sk_alpha_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, 8), 0, s>>>(ws.upart, ws.grid, ws.kpad, kk, ws.alpha);
     }
     SSVB_LAUNCH_CHECK();
     for (int it = 1; it < n_iters; ++it) {
-      if (fast) SSVB_TRY(sk_launch_fast<1>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
-      else SSVB_TRY(sk_launch<1>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+      if (fast) SSVB_TRY(sk_launch_fast<1>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
+      else SSVB_TRY(sk_launch<1>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
       sk_alpha_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, 8), 0, s>>>(ws.upart, fast ? fgrid : ws.grid, ws.kpad, kk, ws.alpha);
       SSVB_LAUNCH_CHECK();
     }
   }
-  if (fast) SSVB_TRY(sk_launch_fast<2>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
-  else SSVB_TRY(sk_launch<2>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes));
+  if (fast) SSVB_TRY(sk_launch_fast<2>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
+  else SSVB_TRY(sk_launch<2>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
+  return SSVB_OK;
+}
+// One pass of the row-sharded (distributed) iteration over this rank's b_local rows.  phase 0: u_local[0..k) = column
+// sums of E relative to the LOCAL maximum, u_local[k] = that maximum; phase 1: column sums of E / (b_global v_b) with the
+// global alpha / smax; phase 2: codes.  The caller all-gathers u_local and calls sinkhorn_dist_alpha between passes.
+int sinkhorn_dist_pass(int phase, const float* scores, int64_t b, int64_t b_global, int64_t k, int64_t ld_scores,
+                       float eps, const float* alpha, const float* smax, float* u_local, float* codes, int64_t ld_codes,
+                       void* workspace, cudaStream_t s) {
+  SkWs ws = sk_ws(workspace, k);
+  const int kk = static_cast<int>(k);
+  const float iel = SSVB_LOG2E / eps;
+  const float inv_b = 1.f / static_cast<float>(b_global);
+  int nwarp = 8;
+  while (nwarp > 1 && static_cast<size_t>(nwarp + 1) * ws.kpad * 4 > 200 * 1024) nwarp >>= 1;
+  const size_t smem = static_cast<size_t>(nwarp + 1) * ws.kpad * 4;
+  if (smem > 200 * 1024) return SSVB_ERR_UNSUPPORTED;
+  const int threads = nwarp * 32;
+  const bool regacc = (nwarp == 8) && (k <= static_cast<int64_t>(kSkJ) * threads);
+  const bool fast = (k % 4 == 0) && (k <= 128 * kSkNV) && (ld_scores % 4 == 0) && !(reinterpret_cast<uintptr_t>(scores) & 15) &&
+                    (phase != 2 || ((ld_codes % 4 == 0) && !(reinterpret_cast<uintptr_t>(codes) & 15)));
+  const size_t smem_fast = static_cast<size_t>(9) * ws.kpad * 4;
+  const int fgrid = num_sms();
+  const dim3 ablock(32, 8);
+  const unsigned agrid = static_cast<unsigned>(ceil_div(k, 32));
+  if (phase != 0) {  // global scaling vector / maximum from the caller
+    ws.alpha = const_cast<float*>(alpha);
+    ws.smax = const_cast<float*>(smax);
+  }
+  if (phase == 0) {
+    if (fast) {
+      SSVB_TRY(sk_launch_fast<0>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, nullptr, 0, inv_b));
+      sk_alpha0_kernel<<<agrid, ablock, 0, s>>>(ws.upart, ws.smax_part, fgrid, ws.kpad, kk, iel, u_local, u_local + k, 1);
+    } else {
+      SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
+      sk_max_kernel<<<ws.grid, 256, 0, s>>>(scores, b, kk, ld_scores, ws.smax_part, ws.counter, ws.smax);
+      SSVB_LAUNCH_CHECK();
+      SSVB_TRY(sk_launch<0>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, nullptr, 0, inv_b));
+      sk_alpha_kernel<<<agrid, ablock, 0, s>>>(ws.upart, ws.grid, ws.kpad, kk, u_local, 1);
+      SSVB_LAUNCH_CHECK();
+      SSVB_CUDA(cudaMemcpyAsync(u_local + k, ws.smax, sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    SSVB_LAUNCH_CHECK();
+  } else if (phase == 1) {
+    if (fast) SSVB_TRY(sk_launch_fast<1>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, nullptr, 0, inv_b));
+    else SSVB_TRY(sk_launch<1>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, nullptr, 0, inv_b));
+    sk_alpha_kernel<<<agrid, ablock, 0, s>>>(ws.upart, fast ? fgrid : ws.grid, ws.kpad, kk, u_local, 1);
+    SSVB_LAUNCH_CHECK();
+    fill_kernel<<<1, 32, 0, s>>>(u_local + k, 1, 0.f);
+    SSVB_LAUNCH_CHECK();
+  } else {
+    if (fast) SSVB_TRY(sk_launch_fast<2>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
+    else SSVB_TRY(sk_launch<2>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
+  }
+  return SSVB_OK;
+}
+int sinkhorn_dist_alpha(const float* u_all, int64_t world, int64_t rank_stride, int64_t k, int phase0, float eps,
+                        float* alpha, float* smax, cudaStream_t s) {
+  sk_dist_alpha_kernel<<<static_cast<unsigned>(ceil_div(k, 256)), 256, 0, s>>>(
+      u_all, static_cast<int>(world), rank_stride, static_cast<int>(k), phase0, SSVB_LOG2E / eps, alpha, smax);
+  SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
 size_t sinkhorn_ws_bytes(int64_t k) { return sk_ws(nullptr, k).bytes; }
@@ -416,6 +503,29 @@ int ssvb_sinkhorn(const float* scores, int64_t b, int64_t k, int64_t ld_scores, 
   if (workspace_bytes < sk_ws(nullptr, k).bytes) return SSVB_ERR_WORKSPACE;
   return sinkhorn_run(scores, b, k, ld_scores, eps, n_iters, codes, ld_codes, workspace,
                       static_cast<cudaStream_t>(stream));
+}
+
+// ---- distributed (sample rows sharded over ranks): see include/ssv_b200.h
+int ssvb_sinkhorn_dist_pass(int phase, const float* scores, int64_t b_local, int64_t b_global, int64_t k,
+                            int64_t ld_scores, float eps, const float* alpha, const float* smax, float* u_local,
+                            float* codes, int64_t ld_codes, void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (!scores || !workspace || b_local <= 0 || b_global < b_local || k <= 0 || !(eps > 0.f) || ld_scores < k ||
+      phase < 0 || phase > 2)
+    return SSVB_ERR_INVALID;
+  if (phase != 0 && (!alpha || !smax)) return SSVB_ERR_INVALID;
+  if (phase != 2 && !u_local) return SSVB_ERR_INVALID;
+  if (phase == 2 && (!codes || ld_codes < k)) return SSVB_ERR_INVALID;
+  if (workspace_bytes < sk_ws(nullptr, k).bytes) return SSVB_ERR_WORKSPACE;
+  return sinkhorn_dist_pass(phase, scores, b_local, b_global, k, ld_scores, eps, alpha, smax, u_local, codes, ld_codes,
+                            workspace, static_cast<cudaStream_t>(stream));
+}
+int ssvb_sinkhorn_dist_alpha(const float* u_all, int64_t world, int64_t rank_stride, int64_t k, int phase0, float eps,
+                             float* alpha, float* smax, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (!u_all || !alpha || world <= 0 || k <= 0 || rank_stride < k + 1 || !(eps > 0.f) || (phase0 && !smax))
+    return SSVB_ERR_INVALID;
+  return sinkhorn_dist_alpha(u_all, world, rank_stride, k, phase0, eps, alpha, smax, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

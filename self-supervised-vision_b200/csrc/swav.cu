@@ -162,6 +162,51 @@ unsigned grid_for(int64_t total, int per_block) {
   return static_cast<unsigned>(g);
 }
 
+
+// stage [Z1; Z2] (each = live rows then bank rows) and the prototypes as bf16, then scores[2B' x K] = [Z1; Z2] C^T
+int stage_scores(const float* z1, const float* z2, const float* bank, const float* prototypes, const SwavDims& m,
+                 int64_t ld_z1, int64_t ld_z2, int64_t ld_bank, int64_t ld_proto, const SwavSaved& sv, float* scores,
+                 cudaStream_t s) {
+  const int di = static_cast<int>(m.d), dp = static_cast<int>(m.dpad);
+  const int64_t nb = m.nb, nbank = m.nbank, k = m.k;
+  rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(nb, 8)), 256, 0, s>>>(z1, nb, di, ld_z1, dp, nullptr, sv.z);
+  SSVB_LAUNCH_CHECK();
+  rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(nb, 8)), 256, 0, s>>>(z2, nb, di, ld_z2, dp, nullptr,
+                                                                             sv.z + m.bp * m.dpad);
+  SSVB_LAUNCH_CHECK();
+  if (nbank > 0) {
+    rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(nbank, 8)), 256, 0, s>>>(bank, nbank, di, ld_bank, dp, nullptr,
+                                                                                  sv.z + nb * m.dpad);
+    SSVB_LAUNCH_CHECK();
+    SSVB_CUDA(cudaMemcpyAsync(sv.z + (m.bp + nb) * m.dpad, sv.z + nb * m.dpad, nbank * m.dpad * sizeof(__nv_bfloat16),
+                              cudaMemcpyDeviceToDevice, s));
+  }
+  rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(k, 8)), 256, 0, s>>>(prototypes, k, di, ld_proto, dp, nullptr, sv.c);
+  SSVB_LAUNCH_CHECK();
+  GemmParams p{};
+  p.M = static_cast<int>(2 * m.bp);
+  p.N = static_cast<int>(k);
+  p.K = static_cast<int>(m.dpad);
+  p.alpha = 1.f;
+  p.out = scores;
+  p.ldc = m.kp4;
+  return launch_gemm({sv.z, m.dpad, false}, {sv.c, m.dpad, false}, p, 256, EPI_STORE_F32, 0, s);
+}
+
+// row-wise cross-entropy of both views: loss = sum of the local row terms / bp_total; dscores (bf16) carry the
+// 1/(2 bp_total T) coefficient (bp_total = rows per view over ALL ranks; = m.bp on one GPU)
+int stage_ce(const float* scores, const float* codes, const SwavDims& m, int64_t bp_total, float temperature,
+             const SwavSaved& sv, float* loss_part, float* loss, cudaStream_t s) {
+  swav_ce_kernel<<<static_cast<unsigned>(m.bp), 256, 0, s>>>(scores, codes, m.bp, static_cast<int>(m.k), m.kp4,
+                                                           1.f / temperature,
+                                                           0.5f / (static_cast<float>(bp_total) * temperature),
+                                                           loss_part, sv.ds, m.kp8);
+  SSVB_LAUNCH_CHECK();
+  sum_partials_kernel<<<1, 1024, 0, s>>>(loss_part, static_cast<int>(m.bp), 1.f / static_cast<float>(bp_total), loss);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -191,44 +236,45 @@ int ssvb_swav_fwd(const float* z1, const float* z2, const float* bank, const flo
   const SwavDims m = dims(nb, nbank, k, d);
   SwavSaved sv = swav_saved(saved, m);
   SwavWs ws = swav_ws(workspace, m);
-  const int di = static_cast<int>(d), dp = static_cast<int>(m.dpad);
-
-  // stage [Z1; Z2] (each = live rows then bank rows) and the prototypes as bf16
-  rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(nb, 8)), 256, 0, s>>>(z1, nb, di, ld_z1, dp, nullptr, sv.z);
-  SSVB_LAUNCH_CHECK();
-  rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(nb, 8)), 256, 0, s>>>(z2, nb, di, ld_z2, dp, nullptr,
-                                                                             sv.z + m.bp * m.dpad);
-  SSVB_LAUNCH_CHECK();
-  if (nbank > 0) {
-    rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(nbank, 8)), 256, 0, s>>>(bank, nbank, di, ld_bank, dp, nullptr,
-                                                                                  sv.z + nb * m.dpad);
-    SSVB_LAUNCH_CHECK();
-    SSVB_CUDA(cudaMemcpyAsync(sv.z + (m.bp + nb) * m.dpad, sv.z + nb * m.dpad, nbank * m.dpad * sizeof(__nv_bfloat16),
-                              cudaMemcpyDeviceToDevice, s));
-  }
-  rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(k, 8)), 256, 0, s>>>(prototypes, k, di, ld_proto, dp, nullptr, sv.c);
-  SSVB_LAUNCH_CHECK();
-
-  // scores[2B' x K] = [Z1; Z2] C^T
-  GemmParams p{};
-  p.M = static_cast<int>(2 * m.bp);
-  p.N = static_cast<int>(k);
-  p.K = static_cast<int>(m.dpad);
-  p.alpha = 1.f;
-  p.out = ws.scores;
-  p.ldc = m.kp4;
-  SSVB_TRY(launch_gemm({sv.z, m.dpad, false}, {sv.c, m.dpad, false}, p, 256, EPI_STORE_F32, 0, s));
+  SSVB_TRY(stage_scores(z1, z2, bank, prototypes, m, ld_z1, ld_z2, ld_bank, ld_proto, sv, ws.scores, s));
   // codes per view (Sinkhorn normalises over the B' rows of ONE view)
   SSVB_TRY(sinkhorn_run(ws.scores, m.bp, k, m.kp4, eps, n_iters, ws.codes, m.kp4, ws.sk, s));
   SSVB_TRY(sinkhorn_run(ws.scores + m.bp * m.kp4, m.bp, k, m.kp4, eps, n_iters, ws.codes + m.bp * m.kp4, m.kp4, ws.sk, s));
-  swav_ce_kernel<<<static_cast<unsigned>(m.bp), 256, 0, s>>>(ws.scores, ws.codes, m.bp, static_cast<int>(k), m.kp4,
-                                                           1.f / temperature,
-                                                           0.5f / (static_cast<float>(m.bp) * temperature),
-                                                           ws.loss_part, sv.ds, m.kp8);
-  SSVB_LAUNCH_CHECK();
-  sum_partials_kernel<<<1, 1024, 0, s>>>(ws.loss_part, static_cast<int>(m.bp), 1.f / static_cast<float>(m.bp), loss);
-  SSVB_LAUNCH_CHECK();
-  return SSVB_OK;
+  return stage_ce(ws.scores, ws.codes, m, m.bp, temperature, sv, ws.loss_part, loss, s);
+}
+
+// ---- distributed (sample rows sharded over ranks; prototypes replicated): see include/ssv_b200.h ----------------
+int64_t ssvb_swav_kpad(int64_t k) { return k > 0 ? round_up(k, 4) : 0; }
+
+int ssvb_swav_dist_scores(const float* z1, const float* z2, const float* bank, const float* prototypes, int64_t nb,
+                          int64_t nbank, int64_t k, int64_t d, int64_t ld_z1, int64_t ld_z2, int64_t ld_bank,
+                          int64_t ld_proto, float* scores, void* saved, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(check_shape(nb, nbank, k, d, 1.f));
+  SSVB_TRY(check_rows(z1, ld_z1));
+  SSVB_TRY(check_rows(z2, ld_z2));
+  SSVB_TRY(check_rows(prototypes, ld_proto));
+  if (nbank > 0) SSVB_TRY(check_rows(bank, ld_bank));
+  if (!scores || !saved) return SSVB_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(scores) & 15) return SSVB_ERR_ALIGNMENT;
+  const SwavDims m = dims(nb, nbank, k, d);
+  SwavSaved sv = swav_saved(saved, m);
+  return stage_scores(z1, z2, bank, prototypes, m, ld_z1, ld_z2, ld_bank, ld_proto, sv, scores,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int ssvb_swav_dist_ce(const float* scores, const float* codes, int64_t nb, int64_t nbank, int64_t bp_global, int64_t k,
+                      int64_t d, float temperature, float* loss_local, void* saved, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(check_shape(nb, nbank, k, d, temperature));
+  if (!scores || !codes || !loss_local || !saved || !workspace || bp_global < nb + nbank) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_swav_workspace_bytes(nb, nbank, k, d)) return SSVB_ERR_WORKSPACE;
+  const SwavDims m = dims(nb, nbank, k, d);
+  SwavSaved sv = swav_saved(saved, m);
+  SwavWs ws = swav_ws(workspace, m);
+  return stage_ce(scores, codes, m, bp_global, temperature, sv, ws.loss_part, loss_local,
+                  static_cast<cudaStream_t>(stream));
 }
 
 int ssvb_swav_bwd(const float* z1, const float* z2, const float* bank, const float* prototypes, int64_t nb,

@@ -220,3 +220,316 @@ class DistributedSimclrLoss(nn.Module):
 
     def forward(self, zi, zj):
         return _NtxentDistFn.apply(zi, zj, self.normalize, self.temperature, self.group, self.stages, self.transport)
+
+
+# ======================================================================================================= helpers
+def _world_rank(group):
+    if dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def _is_nccl(group):
+    return dist.is_initialized() and dist.get_backend(group) == "nccl"
+
+
+def _all_reduce_sum(t, group):
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+def _reduce_scatter_rows(full, rows, rank, group):
+    """Sum `full` [world*rows x cols] over the ranks; return this rank's row slab [rows x cols]."""
+    if _is_nccl(group):
+        out = torch.empty(rows, full.shape[1], dtype=full.dtype, device=full.device)
+        dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=group)
+        return out
+    dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)  # gloo (tests): no reduce-scatter
+    return full[rank * rows:(rank + 1) * rows]
+
+
+# ======================================================================================================= Barlow Twins
+class BarlowCudaStages:
+    """The product path of the distributed Barlow loss: the `ssvb_barlow_dist_*` stages of the C ABI."""
+
+    def alloc_saved(self, n, d, dev):
+        return C.byte_buffer(C.cached_size("ssvb_barlow_dist_saved_bytes", n, d), dev)
+
+    def _ws(self, n, d, dev):
+        nbytes = C.cached_size("ssvb_barlow_dist_workspace_bytes", n, d)
+        return C.workspace("barlow_dist", nbytes, dev), nbytes
+
+    def stats(self, zi, zj, normalize, stats_local, saved):
+        n, d = zi.shape
+        ws, nb = self._ws(n, d, zi.device)
+        C.check(C.lib().ssvb_barlow_dist_stats(C.ptr(zi), C.ptr(zj), n, d, zi.stride(0), zj.stride(0), normalize,
+                                               C.ptr(stats_local), C.ptr(saved), C.ptr(ws), nb,
+                                               C.stream_ptr(zi.device)), "ssvb_barlow_dist_stats")
+
+    def xcorr(self, zi, zj, normalize, stats_all, world, c_partial, saved):
+        n, d = zi.shape
+        C.check(C.lib().ssvb_barlow_dist_xcorr(C.ptr(zi), C.ptr(zj), n, d, zi.stride(0), zj.stride(0), normalize,
+                                               C.ptr(stats_all), world, C.ptr(c_partial), C.ptr(saved),
+                                               C.stream_ptr(zi.device)), "ssvb_barlow_dist_xcorr")
+
+    def epilogue(self, c_rows, row0, lmbda, dc_rows, loss_partial, n):
+        rows, d = c_rows.shape
+        ws, nb = self._ws(n, d, c_rows.device)
+        C.check(C.lib().ssvb_barlow_dist_epilogue(C.ptr(c_rows), row0, rows, d, lmbda, C.ptr(dc_rows),
+                                                  C.ptr(loss_partial), C.ptr(ws), nb, C.stream_ptr(c_rows.device)),
+                "ssvb_barlow_dist_epilogue")
+
+    def bwd_gemm(self, zi, zj, n_global, normalize, dc, saved, colsum):
+        n, d = zi.shape
+        ws, nb = self._ws(n, d, zi.device)
+        C.check(C.lib().ssvb_barlow_dist_bwd_gemm(C.ptr(zi), C.ptr(zj), n, n_global, d, zi.stride(0), zj.stride(0),
+                                                  normalize, C.ptr(dc), C.ptr(saved), C.ptr(colsum), C.ptr(ws), nb,
+                                                  C.stream_ptr(zi.device)), "ssvb_barlow_dist_bwd_gemm")
+
+    def bwd_finish(self, zi, zj, n_global, normalize, colsum, grad_out, saved, dzi, dzj):
+        n, d = zi.shape
+        ws, nb = self._ws(n, d, zi.device)
+        C.check(C.lib().ssvb_barlow_dist_bwd_finish(C.ptr(zi), C.ptr(zj), n, n_global, d, zi.stride(0), zj.stride(0),
+                                                    normalize, C.ptr(colsum), C.ptr(grad_out), C.ptr(saved), C.ptr(dzi),
+                                                    C.ptr(dzj), dzi.stride(0), dzj.stride(0), C.ptr(ws), nb,
+                                                    C.stream_ptr(zi.device)), "ssvb_barlow_dist_bwd_finish")
+
+
+class _BarlowDistFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, zi, zj, normalize, lmbda, group, stages):
+        world, rank = _world_rank(group)
+        cuda = isinstance(stages, BarlowCudaStages)
+        if cuda:
+            C.require_cuda(zi, zj)
+            xi, xj = C.as_f32_rows(zi), C.as_f32_rows(zj)
+        else:
+            xi, xj = zi.detach().float().contiguous(), zj.detach().float().contiguous()
+        if xi.shape != xj.shape or xi.dim() != 2:
+            raise ValueError("BarlowLoss expects two [N, D] tensors of the same shape")
+        n, d = xi.shape
+        dev = xi.device
+        norm = int(bool(normalize))
+        saved = stages.alloc_saved(n, d, dev)
+        # 1. local column moments -> all-gather (tiny) -> every rank combines them in rank order
+        stats_all = torch.empty(world, 2, 2, d, dtype=torch.float32, device=dev)
+        stages.stats(xi, xj, norm, stats_all[rank], saved)
+        if world > 1:
+            _gather_slots(stats_all.view(world, 4 * d), stats_all[rank].view(1, 4 * d), group, inplace=cuda)
+        # 2. partial cross-correlation of the local rows, summed over ranks: reduce-scatter -> this rank's row slab
+        c_partial = torch.empty(d, d, dtype=torch.float32, device=dev)
+        stages.xcorr(xi, xj, norm, stats_all, world, c_partial, saved)
+        sharded = world > 1 and d % world == 0
+        dc = torch.empty(d, d, dtype=torch.bfloat16, device=dev)
+        parts = torch.zeros(world if sharded else 1, dtype=torch.float32, device=dev)
+        if sharded:
+            rows = d // world
+            c_rows = _reduce_scatter_rows(c_partial, rows, rank, group)
+            # 3. loss terms + dC of the slab, then all-gather dC in bf16 (second half of the all-reduce at half width)
+            stages.epilogue(c_rows, rank * rows, float(lmbda), dc[rank * rows:(rank + 1) * rows], parts[rank:rank + 1], n)
+            _gather_slots(dc, dc[rank * rows:(rank + 1) * rows], group, inplace=cuda)
+            _gather_slots(parts.view(world, 1), parts[rank:rank + 1].view(1, 1), group, inplace=cuda)
+            loss = parts.sum()  # same values, same order on every rank -> identical global loss, no all-reduce
+        else:
+            if world > 1:
+                _all_reduce_sum(c_partial, group)
+            stages.epilogue(c_partial, 0, float(lmbda), dc, parts, n)
+            loss = parts[0].clone()
+        del c_partial
+        ctx.save_for_backward(xi, xj, saved, dc)
+        ctx.cfg = (norm, world, group, stages, zi.dtype, zj.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xi, xj, saved, dc = ctx.saved_tensors
+        norm, world, group, stages, dti, dtj = ctx.cfg
+        n, d = xi.shape
+        go = C.f32_scalar(grad_out)
+        colsum = torch.empty(2, 2, d, dtype=torch.float32, device=xi.device)
+        stages.bwd_gemm(xi, xj, n * world, norm, dc, saved, colsum)
+        _all_reduce_sum(colsum, group)
+        dzi, dzj = torch.empty_like(xi), torch.empty_like(xj)
+        stages.bwd_finish(xi, xj, n * world, norm, colsum, go, saved, dzi, dzj)
+        return dzi.to(dti), dzj.to(dtj), None, None, None, None
+
+
+class DistributedBarlowLoss(nn.Module):
+    """BarlowLoss (reference utils/losses.py:120-142, same ctor kwargs) over the global batch of a process group:
+    batch rows sharded, column statistics all-gathered, the D x D cross-correlation all-reduced as
+    reduce-scatter(fp32) -> fused loss/dC epilogue on the slab -> all-gather(bf16), the two column reductions of the
+    standardisation backward all-reduced.  Every rank gets the gradient rows of its own inputs (no 1/world rescale)."""
+
+    def __init__(self, normalize=True, off_diagonal_weight=0.005, group=None, stages=None):
+        super().__init__()
+        self.normalize = normalize
+        self.lmbda = off_diagonal_weight
+        self.group = group
+        self.stages = stages if stages is not None else BarlowCudaStages()
+
+    def forward(self, z_i, z_j):
+        return _BarlowDistFn.apply(z_i, z_j, self.normalize, self.lmbda, self.group, self.stages)
+
+
+# ======================================================================================================= SwAV / Sinkhorn
+class SwavCudaStages:
+    """The product path of the distributed SwAV loss / Sinkhorn: C-ABI stages."""
+
+    def kpad(self, k):
+        return C.cached_size("ssvb_swav_kpad", k)
+
+    def alloc_saved(self, nb, nbank, k, d, dev):
+        return C.byte_buffer(C.cached_size("ssvb_swav_saved_bytes", nb, nbank, k, d), dev)
+
+    def sk_pass(self, phase, scores, b_global, k, eps, alpha, smax, u_local, codes):
+        dev = scores.device
+        nbytes = C.cached_size("ssvb_sinkhorn_workspace_bytes", scores.shape[0], k)
+        ws = C.workspace("sinkhorn_dist", nbytes, dev)
+        C.check(C.lib().ssvb_sinkhorn_dist_pass(phase, C.ptr(scores), scores.shape[0], b_global, k, scores.stride(0),
+                                                eps, C.ptr(alpha), C.ptr(smax), C.ptr(u_local), C.ptr(codes),
+                                                codes.stride(0) if codes is not None else 0, C.ptr(ws), nbytes,
+                                                C.stream_ptr(dev)), "ssvb_sinkhorn_dist_pass")
+
+    def sk_alpha(self, u_all_view, world, rank_stride, k, phase0, eps, alpha, smax):
+        C.check(C.lib().ssvb_sinkhorn_dist_alpha(C.ptr(u_all_view), world, rank_stride, k, int(phase0), eps,
+                                                 C.ptr(alpha), C.ptr(smax), C.stream_ptr(alpha.device)),
+                "ssvb_sinkhorn_dist_alpha")
+
+    def scores(self, z1, z2, bank, protos, scores, saved):
+        nb, d = z1.shape
+        nbank = bank.shape[0] if bank is not None else 0
+        C.check(C.lib().ssvb_swav_dist_scores(C.ptr(z1), C.ptr(z2), C.ptr(bank), C.ptr(protos), nb, nbank,
+                                              protos.shape[0], d, z1.stride(0), z2.stride(0),
+                                              bank.stride(0) if bank is not None else 0, protos.stride(0),
+                                              C.ptr(scores), C.ptr(saved), C.stream_ptr(z1.device)),
+                "ssvb_swav_dist_scores")
+
+    def ce(self, scores, codes, nb, nbank, bp_global, k, d, temperature, loss_local, saved):
+        dev = scores.device
+        nbytes = C.cached_size("ssvb_swav_workspace_bytes", nb, nbank, k, d)
+        ws = C.workspace("swav", nbytes, dev)
+        C.check(C.lib().ssvb_swav_dist_ce(C.ptr(scores), C.ptr(codes), nb, nbank, bp_global, k, d, temperature,
+                                          C.ptr(loss_local), C.ptr(saved), C.ptr(ws), nbytes, C.stream_ptr(dev)),
+                "ssvb_swav_dist_ce")
+
+    def bwd(self, z1, z2, bank, protos, temperature, grad_out, saved, dz1, dz2, dproto):
+        nb, d = z1.shape
+        nbank = bank.shape[0] if bank is not None else 0
+        k = protos.shape[0]
+        dev = z1.device
+        nbytes = C.cached_size("ssvb_swav_workspace_bytes", nb, nbank, k, d)
+        ws = C.workspace("swav", nbytes, dev)
+        C.check(C.lib().ssvb_swav_bwd(C.ptr(z1), C.ptr(z2), C.ptr(bank), C.ptr(protos), nb, nbank, k, d, z1.stride(0),
+                                      z2.stride(0), bank.stride(0) if bank is not None else 0, protos.stride(0),
+                                      temperature, C.ptr(grad_out), C.ptr(saved), C.ptr(dz1), C.ptr(dz2), C.ptr(dproto),
+                                      dz1.stride(0), dz2.stride(0), dproto.stride(0), C.ptr(ws), nbytes,
+                                      C.stream_ptr(dev)), "ssvb_swav_bwd")
+
+
+def _dist_sinkhorn(stages, scores_views, codes_views, k, eps, n_iters, group, inplace):
+    """Row-sharded Sinkhorn-Knopp on one or more views at once (their marginals travel in ONE all-gather per pass).
+    scores_views / codes_views: lists of [b_local, >=k] fp32 tensors (same b_local on every rank)."""
+    world, rank = _world_rank(group)
+    nv = len(scores_views)
+    b_local = scores_views[0].shape[0]
+    b_global = b_local * world
+    dev = scores_views[0].device
+    u_all = torch.empty(world, nv, k + 1, dtype=torch.float32, device=dev)
+    alpha = torch.empty(nv, k, dtype=torch.float32, device=dev)
+    smax = torch.empty(nv, 1, dtype=torch.float32, device=dev)
+    eps = float(eps)
+
+    def exchange(phase0):
+        if world > 1:
+            _gather_slots(u_all.view(world, nv * (k + 1)), u_all[rank].view(1, nv * (k + 1)), group, inplace=inplace)
+        for v in range(nv):
+            stages.sk_alpha(u_all[0, v], world, nv * (k + 1), k, phase0, eps, alpha[v], smax[v])
+
+    for v in range(nv):
+        stages.sk_pass(0, scores_views[v], b_global, k, eps, None, None, u_all[rank, v], None)
+    exchange(True)
+    if n_iters <= 0:
+        alpha.fill_(1.0)  # no iterations: codes = E / rowsum(E)
+    for _ in range(1, int(n_iters)):
+        for v in range(nv):
+            stages.sk_pass(1, scores_views[v], b_global, k, eps, alpha[v], smax[v], u_all[rank, v], None)
+        exchange(False)
+    for v in range(nv):
+        stages.sk_pass(2, scores_views[v], b_global, k, eps, alpha[v], smax[v], None, codes_views[v])
+
+
+class _SwavDistFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z1, z2, prototypes, bank, temperature, eps, n_iters, group, stages):
+        world, rank = _world_rank(group)
+        cuda = isinstance(stages, SwavCudaStages)
+        if cuda:
+            C.require_cuda(z1, z2, prototypes, bank)
+            x1, x2, pc = C.as_f32_rows(z1), C.as_f32_rows(z2), C.as_f32_rows(prototypes)
+            bk = C.as_f32_rows(bank.detach()) if bank is not None and bank.shape[0] > 0 else None
+        else:
+            x1, x2, pc = (t.detach().float().contiguous() for t in (z1, z2, prototypes))
+            bk = bank.detach().float().contiguous() if bank is not None and bank.shape[0] > 0 else None
+        if x1.shape != x2.shape or x1.dim() != 2 or pc.dim() != 2 or pc.shape[1] != x1.shape[1]:
+            raise ValueError("SwavLoss expects z_1/z_2 [B, d] and prototypes [K, d]")
+        nb, d = x1.shape
+        nbank = bk.shape[0] if bk is not None else 0
+        k = pc.shape[0]
+        bp = nb + nbank
+        dev = x1.device
+        kp = stages.kpad(k)
+        saved = stages.alloc_saved(nb, nbank, k, d, dev)
+        scores = torch.empty(2 * bp, kp, dtype=torch.float32, device=dev)
+        codes = torch.empty(2 * bp, kp, dtype=torch.float32, device=dev)
+        stages.scores(x1, x2, bk, pc, scores, saved)
+        _dist_sinkhorn(stages, [scores[:bp], scores[bp:]], [codes[:bp], codes[bp:]], k, eps, n_iters, group, cuda)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        stages.ce(scores, codes, nb, nbank, bp * world, k, d, float(temperature), loss, saved)
+        _all_reduce_sum(loss, group)
+        ctx.save_for_backward(x1, x2, pc, saved, *([bk] if bk is not None else []))
+        ctx.cfg = (float(temperature), group, stages, z1.dtype, z2.dtype, prototypes.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x1, x2, pc, saved, *rest = ctx.saved_tensors
+        bk = rest[0] if rest else None
+        temperature, group, stages, dt1, dt2, dtp = ctx.cfg
+        go = C.f32_scalar(grad_out)
+        dz1, dz2, dpc = torch.empty_like(x1), torch.empty_like(x2), torch.empty_like(pc)
+        stages.bwd(x1, x2, bk, pc, temperature, go, saved, dz1, dz2, dpc)
+        _all_reduce_sum(dpc, group)  # prototypes are replicated: their gradient sums over every rank's rows
+        return dz1.to(dt1), dz2.to(dt2), dpc.to(dtp), None, None, None, None, None, None
+
+
+class DistributedSwavLoss(nn.Module):
+    """SwavLoss (reference utils/losses.py:204-235, same ctor kwargs) over the global batch of a process group: sample
+    rows (and each rank's bank rows) sharded, prototypes replicated.  Per Sinkhorn pass ONE all-gather of the K-vector
+    prototype marginals of both views (combined in rank order = their all-reduce); all-reduce of the scalar loss and of
+    the prototype gradient.  Every rank gets the gradient rows of its own inputs."""
+
+    def __init__(self, temperature=0.1, sinkhorn_eps=0.05, sinkhorn_iters=3, group=None, stages=None):
+        super().__init__()
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.temperature = temperature
+        self.n_iters = sinkhorn_iters
+        self.eps = sinkhorn_eps
+        self.group = group
+        self.stages = stages if stages is not None else SwavCudaStages()
+
+    @torch.no_grad()
+    def compute_codes_sinkhorn(self, scores):
+        """Codes of this rank's rows of the row-sharded global score matrix (utils/losses.py:213-224 on the concatenation)."""
+        cuda = isinstance(self.stages, SwavCudaStages)
+        if cuda:
+            C.require_cuda(scores)
+        s = scores.detach()
+        if s.dtype != torch.float32 or s.stride(1) != 1:
+            s = s.float().contiguous()
+        codes = torch.empty(s.shape[0], s.shape[1], dtype=torch.float32, device=s.device)
+        _dist_sinkhorn(self.stages, [s], [codes], s.shape[1], self.eps, self.n_iters, self.group, cuda)
+        return codes
+
+    def forward(self, z_1, z_2, prototypes, bank_features=None):
+        return _SwavDistFn.apply(z_1, z_2, prototypes, bank_features, self.temperature, self.eps, self.n_iters,
+                                 self.group, self.stages)

@@ -102,3 +102,235 @@ def test_distributed_ntxent_matches_global_oracle(normalize, tau):
         assert np.linalg.norm(gi - 2 * ref_dzi[sl]) / np.linalg.norm(2 * ref_dzi[sl]) < 2e-2
         assert np.linalg.norm(gj - 2 * ref_dzj[sl]) / np.linalg.norm(2 * ref_dzj[sl]) < 2e-2
     assert out[0][0] == out[1][0], "every rank must report the same global loss"
+
+
+# ======================================================================================================= Barlow Twins
+class EmulatedBarlowStages:
+    """torch-fp64 stand-in for the ssvb_barlow_dist_* stages (test-only): same contracts, same buffers."""
+
+    def alloc_saved(self, n, d, dev):
+        return torch.zeros(2 * n * d + 4 * d + 2 * n, dtype=torch.float64)
+
+    @staticmethod
+    def _views(saved, n, d):
+        o = 0
+        out = []
+        for cnt, shape in ((n * d, (n, d)), (n * d, (n, d)), (d, (d,)), (d, (d,)), (d, (d,)), (d, (d,)), (n, (n,)), (n, (n,))):
+            out.append(saved[o:o + cnt].view(*shape))
+            o += cnt
+        return out  # xi~, xj~, mean_i, rstd_i, mean_j, rstd_j, inv_i, inv_j
+
+    def stats(self, zi, zj, normalize, stats_local, saved):
+        n, d = zi.shape
+        v = self._views(saved, n, d)
+        for k, z in enumerate((zi, zj)):
+            x = z.double()
+            inv = 1.0 / x.norm(dim=1).clamp_min(1e-12) if normalize else torch.ones(n, dtype=torch.float64)
+            v[6 + k].copy_(inv)
+            x = x * inv[:, None]
+            mu = x.mean(0)
+            stats_local[k, 0].copy_(mu.float())
+            stats_local[k, 1].copy_(((x - mu) ** 2).sum(0).float())
+
+    def xcorr(self, zi, zj, normalize, stats_all, world, c_partial, saved):
+        n, d = zi.shape
+        v = self._views(saved, n, d)
+        ng = n * world
+        xt = []
+        for k, z in enumerate((zi, zj)):
+            mu_r = stats_all[:, k, 0].double()
+            m2_r = stats_all[:, k, 1].double()
+            mu = mu_r.mean(0)
+            m2 = m2_r.sum(0) + n * ((mu_r - mu) ** 2).sum(0)
+            rstd = 1.0 / torch.sqrt(m2 / (ng - 1))
+            v[2 + 2 * k].copy_(mu)
+            v[3 + 2 * k].copy_(rstd)
+            x = z.double() * v[6 + k][:, None]
+            v[k].copy_((x - mu) * rstd)
+            xt.append(v[k])
+        c_partial.copy_((xt[0].t() @ xt[1] / ng).float())
+
+    def epilogue(self, c_rows, row0, lmbda, dc_rows, loss_partial, n):
+        rows, d = c_rows.shape
+        c = c_rows.double()
+        eye = torch.zeros(rows, d, dtype=torch.bool)
+        eye[torch.arange(rows), row0 + torch.arange(rows)] = True
+        t = torch.where(eye, c - 1.0, c)
+        w = torch.where(eye, torch.ones_like(c), torch.full_like(c, lmbda))
+        loss_partial.copy_((w * t * t).sum().float().view(1))
+        dc_rows.copy_((2.0 * w * t).to(dc_rows.dtype))
+
+    def bwd_gemm(self, zi, zj, n_global, normalize, dc, saved, colsum):
+        n, d = zi.shape
+        v = self._views(saved, n, d)
+        g = dc.double()
+        self.dti = v[1] @ g.t() / n_global
+        self.dtj = v[0] @ g / n_global
+        colsum[0, 0].copy_(self.dti.sum(0).float())
+        colsum[0, 1].copy_((self.dti * v[0]).sum(0).float())
+        colsum[1, 0].copy_(self.dtj.sum(0).float())
+        colsum[1, 1].copy_((self.dtj * v[1]).sum(0).float())
+
+    def bwd_finish(self, zi, zj, n_global, normalize, colsum, grad_out, saved, dzi, dzj):
+        n, d = zi.shape
+        v = self._views(saved, n, d)
+        for k, (z, dt, out) in enumerate(((zi, self.dti, dzi), (zj, self.dtj, dzj))):
+            m1 = colsum[k, 0].double() / n_global
+            m2 = colsum[k, 1].double() / (n_global - 1)
+            g = (dt - m1 - v[k] * m2) * v[3 + 2 * k] * grad_out.double()
+            if normalize:
+                xh = z.double() * v[6 + k][:, None]
+                g = (g - (g * xh).sum(1, keepdim=True) * xh) * v[6 + k][:, None]
+            out.copy_(g.float())
+
+
+def _barlow_worker(rank, world, port, n_local, d, normalize, lmbda, out):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "self-supervised-vision_b200")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ssv_b200.dist import DistributedBarlowLoss
+    g = torch.Generator().manual_seed(200 + rank)
+    zi = (torch.randn(n_local, d, generator=g) * 1.5 + 0.3).requires_grad_(True)
+    zj = (zi.detach() * 0.7 + 0.5 * torch.randn(n_local, d, generator=g)).requires_grad_(True)
+    loss = DistributedBarlowLoss(normalize, lmbda, stages=EmulatedBarlowStages())(zi, zj)
+    (3.0 * loss).backward()
+    out[rank] = (loss.item(), zi.grad.numpy().copy(), zj.grad.numpy().copy(), zi.detach().numpy().copy(),
+                 zj.detach().numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("normalize,d", [(False, 32), (True, 32), (False, 33)])  # d=33: not divisible -> all-reduce path
+def test_distributed_barlow_matches_global_oracle(normalize, d):
+    from oracle import ssl_oracle as O
+    world, n_local, lmbda = 2, 20, 0.005
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_barlow_worker, args=(world, port, n_local, d, normalize, lmbda, out), nprocs=world, join=True)
+    zi = np.concatenate([out[r][3] for r in range(world)])
+    zj = np.concatenate([out[r][4] for r in range(world)])
+    ref_loss, ref_dzi, ref_dzj = O.barlow(zi, zj, normalize, lmbda)
+    for r in range(world):
+        loss, gi, gj, _, _ = out[r]
+        assert abs(loss - ref_loss) / abs(ref_loss) < 1e-3
+        sl = slice(r * n_local, (r + 1) * n_local)
+        assert np.linalg.norm(gi - 3 * ref_dzi[sl]) / np.linalg.norm(3 * ref_dzi[sl]) < 2e-2  # dC staged in bf16
+        assert np.linalg.norm(gj - 3 * ref_dzj[sl]) / np.linalg.norm(3 * ref_dzj[sl]) < 2e-2
+    assert out[0][0] == out[1][0], "every rank must report the same global loss"
+
+
+# ======================================================================================================= SwAV / Sinkhorn
+class EmulatedSwavStages:
+    """torch-fp64 stand-in for the distributed SwAV / Sinkhorn C-ABI stages (test-only)."""
+
+    def kpad(self, k):
+        return (k + 3) // 4 * 4
+
+    def alloc_saved(self, nb, nbank, k, d, dev):
+        return torch.zeros(1)
+
+    def sk_pass(self, phase, scores, b_global, k, eps, alpha, smax, u_local, codes):
+        s = scores[:, :k].double()
+        if phase == 0:
+            m = s.max()
+            u_local[:k].copy_(torch.exp((s - m) / eps).sum(0).float())
+            u_local[k] = m.float()
+            return
+        e = torch.exp((s - smax.double()) / eps)
+        v = e @ alpha.double()
+        if phase == 1:
+            u_local[:k].copy_((e / (b_global * v[:, None])).sum(0).float())
+            u_local[k] = 0.0
+        else:
+            codes[:, :k].copy_((e * alpha.double() / v[:, None]).float())
+
+    def sk_alpha(self, u_all_view, world, rank_stride, k, phase0, eps, alpha, smax):
+        blocks = u_all_view.as_strided((world, k + 1), (rank_stride, 1)).double()
+        if phase0:
+            m = blocks[:, k].max()
+            u = (blocks[:, :k] * torch.exp((blocks[:, k] - m) / eps)[:, None]).sum(0)
+            smax.copy_(m.float().view(1))
+        else:
+            u = blocks[:, :k].sum(0)
+        alpha.copy_(((1.0 / k) / u).float())
+
+    def scores(self, z1, z2, bank, protos, scores, saved):
+        rows = [torch.cat([z, bank]) if bank is not None else z for z in (z1, z2)]
+        self.z = torch.cat(rows).double()
+        self.c = protos.double()
+        scores[:, :protos.shape[0]].copy_((self.z @ self.c.t()).float())
+
+    def ce(self, scores, codes, nb, nbank, bp_global, k, d, temperature, loss_local, saved):
+        bp = nb + nbank
+        s = scores[:, :k].double() / temperature
+        q = codes[:, :k].double()
+        p = torch.log_softmax(s, 1)
+        q1, q2, p1, p2 = q[:bp], q[bp:], p[:bp], p[bp:]
+        loss_local.copy_((-0.5 * ((q1 * p2).sum() + (q2 * p1).sum()) / bp_global).float())
+        coef = 0.5 / (bp_global * temperature)
+        ds1 = -(q2 - torch.exp(p1) * q2.sum(1, keepdim=True)) * coef
+        ds2 = -(q1 - torch.exp(p2) * q1.sum(1, keepdim=True)) * coef
+        self.ds = torch.cat([ds1, ds2])
+        self.bp, self.nb = bp, nb
+
+    def bwd(self, z1, z2, bank, protos, temperature, grad_out, saved, dz1, dz2, dproto):
+        go = grad_out.double()
+        dz = self.ds @ self.c * go
+        dz1.copy_(dz[:self.nb].float())
+        dz2.copy_(dz[self.bp:self.bp + self.nb].float())
+        dproto.copy_((self.ds.t() @ self.z * go).float())
+
+
+def _swav_worker(rank, world, port, nb, nbank, k, d, out):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "self-supervised-vision_b200")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ssv_b200.dist import DistributedSwavLoss
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(300 + rank)
+    z1 = F.normalize(torch.randn(nb, d, generator=g)).requires_grad_(True)
+    z2 = F.normalize(torch.randn(nb, d, generator=g)).requires_grad_(True)
+    bank = F.normalize(torch.randn(nbank, d, generator=g)) if nbank else None
+    gp = torch.Generator().manual_seed(7)  # prototypes are replicated: same on every rank
+    pc = F.normalize(torch.randn(k, d, generator=gp)).requires_grad_(True)
+    fn = DistributedSwavLoss(0.1, 0.05, 3, stages=EmulatedSwavStages())
+    loss = fn(z1, z2, pc, bank)
+    (2.0 * loss).backward()
+    sc = (z1.detach() @ pc.detach().t())
+    codes = fn.compute_codes_sinkhorn(sc)
+    out[rank] = dict(loss=loss.item(), dz1=z1.grad.numpy().copy(), dz2=z2.grad.numpy().copy(), dpc=pc.grad.numpy().copy(),
+                     z1=z1.detach().numpy().copy(), z2=z2.detach().numpy().copy(),
+                     bank=None if bank is None else bank.numpy().copy(), pc=pc.detach().numpy().copy(),
+                     sc=sc.numpy().copy(), codes=codes.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nbank", [0, 12])
+def test_distributed_swav_matches_global_oracle(nbank):
+    from oracle import ssl_oracle as O
+    world, nb, k, d = 2, 16, 10, 8
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_swav_worker, args=(world, port, nb, nbank, k, d, out), nprocs=world, join=True)
+    # the single-process reference sees: live rows of all ranks, then bank rows of all ranks (row order within a view is
+    # irrelevant to the loss as long as both views use the same order)
+    z1 = np.concatenate([out[r]["z1"] for r in range(world)])
+    z2 = np.concatenate([out[r]["z2"] for r in range(world)])
+    bank = np.concatenate([out[r]["bank"] for r in range(world)]) if nbank else None
+    ref_loss, ref_dz1, ref_dz2, ref_dc = O.swav(z1, z2, out[0]["pc"], bank, 0.1, 0.05, 3)
+    for r in range(world):
+        o = out[r]
+        assert abs(o["loss"] - ref_loss) / abs(ref_loss) < 1e-4
+        sl = slice(r * nb, (r + 1) * nb)
+        assert np.linalg.norm(o["dz1"] - 2 * ref_dz1[sl]) / np.linalg.norm(2 * ref_dz1[sl]) < 1e-3
+        assert np.linalg.norm(o["dz2"] - 2 * ref_dz2[sl]) / np.linalg.norm(2 * ref_dz2[sl]) < 1e-3
+        assert np.linalg.norm(o["dpc"] - 2 * ref_dc) / np.linalg.norm(2 * ref_dc) < 1e-3
+    assert out[0]["loss"] == out[1]["loss"]
+    assert np.array_equal(out[0]["dpc"], out[1]["dpc"])
+    # stand-alone distributed Sinkhorn: codes of the row-sharded score matrix == rows of the global codes
+    ref_codes = O.sinkhorn(np.concatenate([out[r]["sc"] for r in range(world)]), 0.05, 3)
+    for r in range(world):
+        assert np.allclose(out[r]["codes"], ref_codes[r * nb:(r + 1) * nb], rtol=1e-4, atol=1e-7)
