@@ -133,6 +133,42 @@ int ssvb_moco_bwd(const float* query, const float* keys, const float* queue, con
                   int64_t ld_dq, int64_t ld_dk, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * a2/e  MoCo with the queue SHARDED over `world` ranks (semantics = MocoLoss on the rank-order
+ *     concatenation of all ranks' queries / keys against the whole queue; every rank gets the gradients of its own
+ *     rows).  Rank s owns k_local consecutive queue rows; every rank has n_local queries (n_global = world*n_local).
+ *     1 prep:       normalise the local rows; bf16 queries into slot `rank` of qhat_all
+ *                   [ssvb_moco_dist_npad(n_global) x ssvb_ntxent_dpad(d)]; rowstat_local [3][n_local] = 1/|q|, 1/|k|,
+ *                   positive logit (unscaled).            -> caller ALL-GATHERS the qhat slots
+ *     2 shard_fwd:  all n_global queries against this rank's shard -> part_local
+ *                   [m (n_global) | l (n_global) | pos (n_local)] (log2-domain max / sum of exponentials over the shard)
+ *                                                          -> caller ALL-GATHERS part_local into part_all [world][..]
+ *     3 finalize:   combine the shards in rank order + the positive -> lse2_all [npad] and the global loss
+ *                   (identical on every rank: no all-reduce)
+ *     4 shard_bwd:  dacc_partial [npad x dpad] fp32 = sum_{j in shard} p_aj m_j for every global query
+ *                                                          -> caller REDUCE-SCATTERS (sum) the first n_global rows
+ *     5 finish:     gradients of the local query / key rows from the reduced dacc_local [n_local x dpad].
+ * ------------------------------------------------------------------------------------- */
+int64_t ssvb_moco_dist_npad(int64_t n_global);
+size_t ssvb_moco_dist_workspace_bytes(int64_t n_global, int64_t k_local, int64_t d);
+int ssvb_moco_dist_prep(const float* query, const float* keys, int64_t n_local, int64_t d, int64_t ld_q,
+                        int64_t ld_k, int normalize, int64_t world, int64_t rank, void* qhat_all,
+                        float* rowstat_local, void* stream);
+int ssvb_moco_dist_shard_fwd(const void* qhat_all, int64_t n_global, const float* queue_shard,
+                             const void* queue_shard_bf16, int64_t k_local, int64_t d, int64_t ld_queue,
+                             float temperature, const float* rowstat_local, int64_t n_local, float* part_local,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int ssvb_moco_dist_finalize(const float* part_all, int64_t world, int64_t n_local, float temperature,
+                            float* lse2_all, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+int ssvb_moco_dist_shard_bwd(const void* qhat_all, int64_t n_global, const float* queue_shard,
+                             const void* queue_shard_bf16, int64_t k_local, int64_t d, int64_t ld_queue,
+                             float temperature, const float* lse2_all, float* dacc_partial, void* workspace,
+                             size_t workspace_bytes, void* stream);
+int ssvb_moco_dist_finish(const float* query, const float* keys, int64_t n_local, int64_t n_global, int64_t d,
+                          int64_t ld_q, int64_t ld_k, int normalize, float temperature, const float* rowstat_local,
+                          const float* lse2_local, const float* dacc_local, const float* grad_out, float* dquery,
+                          float* dkeys, int64_t ld_dq, int64_t ld_dk, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * a3/a7  Ring-buffer enqueue — replaces MemoryBank.add_batch (models/moco.py:31-36,
  *     normalize=1) and FeatureBank.add_vectors (models/swav.py:70-75, normalize=0).
  *     Row i of `batch` is written to bank row (ptr + i) mod size; when n > size only the
@@ -143,6 +179,14 @@ int ssvb_moco_bwd(const float* query, const float* keys, const float* queue, con
 int ssvb_ring_enqueue(float* bank, void* bank_bf16, int64_t size, int64_t d, int64_t ld_bank,
                       const float* batch, int64_t n, int64_t ld_batch, int64_t ptr, int normalize,
                       int64_t* new_ptr, void* stream);
+
+/* Sharded ring (MoCo queue range-partitioned over ranks): `bank_shard` holds global rows
+ * [shard_lo, shard_lo + shard_rows) of a ring of `size` rows; `batch` is the GLOBAL batch (every rank's keys in rank
+ * order, all-gathered by the caller); only rows whose slot falls into this shard are written.  The pointer arithmetic
+ * is the single-process ring's and identical on every rank (bit-exact bookkeeping). */
+int ssvb_ring_enqueue_shard(float* bank_shard, void* bank_shard_bf16, int64_t size, int64_t shard_lo,
+                            int64_t shard_rows, int64_t d, int64_t ld_bank, const float* batch, int64_t n,
+                            int64_t ld_batch, int64_t ptr, int normalize, int64_t* new_ptr, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * a4  Barlow Twins — replaces BarlowLoss.forward (utils/losses.py:127-142; call models/barlow.py:90).

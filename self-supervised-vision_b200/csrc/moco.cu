@@ -125,6 +125,47 @@ __global__ void moco_grad_finish_kernel(const float* __restrict__ q, const float
   }
 }
 
+// ---- sharded queue (distributed) -----------------------------------------------------------------------------
+// combine the per-chunk partials of the local shard into ONE (m, l) pair per global query row (one warp per row)
+__global__ void shard_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l, int nparts,
+                                     int stride, int nrows, float* __restrict__ out_m, float* __restrict__ out_l) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= nrows) return;
+  float M = -1e30f;
+  for (int i = lane; i < nparts; i += 32) M = fmaxf(M, part_m[static_cast<size_t>(i) * stride + r]);
+  M = warp_max(M);
+  float L = 0.f;
+  for (int i = lane; i < nparts; i += 32)
+    L += part_l[static_cast<size_t>(i) * stride + r] * exp2f(part_m[static_cast<size_t>(i) * stride + r] - M);
+  L = warp_sum(L);
+  if (lane == 0) {
+    out_m[r] = M;
+    out_l[r] = L;
+  }
+}
+// part_all: [world] blocks of [m (n_global) | l (n_global) | pos of the block's own n_local rows]; combine in rank
+// order with the positive logit (label-0 column) -> lse2_all and the global loss (identical on every rank).
+__global__ void shard_finalize_kernel(const float* __restrict__ part_all, int world, int n_local, float c,
+                                      float* __restrict__ lse2_all, float* block_sums, unsigned int* counter,
+                                      float loss_scale, float* loss) {
+  const int n_global = world * n_local;
+  const int64_t blk = 2 * static_cast<int64_t>(n_global) + n_local;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  float term = 0.f;
+  if (r < n_global) {
+    const float p2 = part_all[(r / n_local) * blk + 2 * n_global + (r % n_local)] * c;
+    float M = p2;
+    for (int w = 0; w < world; ++w) M = fmaxf(M, part_all[w * blk + r]);
+    float L = exp2f(p2 - M);
+    for (int w = 0; w < world; ++w) L += part_all[w * blk + n_global + r] * exp2f(part_all[w * blk + r] - M);
+    const float lse2 = M + log2f(L);
+    lse2_all[r] = lse2;
+    term = (lse2 - p2) * SSVB_LN2;
+  }
+  const float bt = block_sum_256(term);
+  grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false);
+}
+
 int check_rows(const void* p, int64_t ld) {
   if (!p) return SSVB_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(p) & 15) || (ld & 3)) return SSVB_ERR_ALIGNMENT;
@@ -236,6 +277,141 @@ int ssvb_moco_bwd(const float* query, const float* keys, const float* queue, con
   moco_grad_finish_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(
       query, keys, ld_q, ld_k, static_cast<int>(n), static_cast<int>(d), ws.dacc, static_cast<int>(dpad), sv,
       normalize, c, 1.f / (static_cast<float>(n) * temperature), grad_out, dquery, dkeys, ld_dq, ld_dk);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// MoCo with the queue sharded over ranks.  See include/ssv_b200.h for the stage contract.
+// ------------------------------------------------------------------------------------------------------------
+int64_t ssvb_moco_dist_npad(int64_t n_global) { return n_global > 0 ? round_up(n_global, 128) : 0; }
+size_t ssvb_moco_dist_workspace_bytes(int64_t n_global, int64_t k_local, int64_t d) {
+  if (n_global <= 0 || k_local <= 0 || d <= 0) return 0;
+  return moco_ws(nullptr, n_global, k_local, sim_dpad(d)).bytes;
+}
+
+int ssvb_moco_dist_prep(const float* query, const float* keys, int64_t n_local, int64_t d, int64_t ld_q, int64_t ld_k,
+                        int normalize, int64_t world, int64_t rank, void* qhat_all, float* rowstat_local, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(check_shape(n_local, 1, d, 1.f));
+  SSVB_TRY(check_rows(query, ld_q));
+  SSVB_TRY(check_rows(keys, ld_k));
+  if (!qhat_all || !rowstat_local || world < 1 || rank < 0 || rank >= world) return SSVB_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(qhat_all) & 15) return SSVB_ERR_ALIGNMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t dpad = sim_dpad(d), ng = n_local * world, npad = round_up(ng, 128);
+  __nv_bfloat16* qh = static_cast<__nv_bfloat16*>(qhat_all);
+  if (npad > ng) SSVB_CUDA(cudaMemsetAsync(qh + ng * dpad, 0, (npad - ng) * dpad * sizeof(__nv_bfloat16), s));
+  pair_prep_kernel<<<static_cast<unsigned>(ceil_div(n_local, 8)), 256, 0, s>>>(
+      query, keys, static_cast<int>(n_local), static_cast<int>(d), ld_q, ld_k, normalize, 0, qh + rank * n_local * dpad,
+      nullptr, static_cast<int>(dpad), rowstat_local, rowstat_local + n_local, rowstat_local + 2 * n_local, nullptr);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_moco_dist_shard_fwd(const void* qhat_all, int64_t n_global, const float* queue_shard,
+                             const void* queue_shard_bf16, int64_t k_local, int64_t d, int64_t ld_queue,
+                             float temperature, const float* rowstat_local, int64_t n_local, float* part_local,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(check_shape(n_global, k_local, d, temperature));
+  if (!qhat_all || !rowstat_local || !part_local || !workspace || (!queue_shard && !queue_shard_bf16) ||
+      n_local <= 0 || n_local > n_global)
+    return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_moco_dist_workspace_bytes(n_global, k_local, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t dpad = sim_dpad(d), npad = round_up(n_global, 128);
+  MocoWs ws = moco_ws(workspace, n_global, k_local, dpad);
+  const float c = SSVB_LOG2E / temperature;
+  const __nv_bfloat16* qb = nullptr;
+  SSVB_TRY(get_queue_bf16(queue_shard, queue_shard_bf16, k_local, d, ld_queue, dpad, ws, s, &qb));
+  SimParams p;
+  moco_plan(p, n_global, k_local, c, 256, 2);
+  p.part_m = ws.part_m;
+  p.part_l = ws.part_l;
+  p.part_stride = static_cast<int>(npad);
+  SSVB_TRY(launch_sim_fwd(SIM_MOCO, qhat_all, npad, qb, k_local, dpad, p, s));
+  shard_combine_kernel<<<static_cast<unsigned>(ceil_div(n_global, 8)), 256, 0, s>>>(
+      ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride, static_cast<int>(n_global), part_local, part_local + n_global);
+  SSVB_LAUNCH_CHECK();
+  SSVB_CUDA(cudaMemcpyAsync(part_local + 2 * n_global, rowstat_local + 2 * n_local, n_local * sizeof(float),
+                            cudaMemcpyDeviceToDevice, s));
+  return SSVB_OK;
+}
+
+int ssvb_moco_dist_finalize(const float* part_all, int64_t world, int64_t n_local, float temperature, float* lse2_all,
+                            float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (!part_all || !lse2_all || !loss || !workspace || world < 1 || n_local < 1 || !(temperature > 0.f))
+    return SSVB_ERR_INVALID;
+  const int64_t ng = world * n_local;
+  const int64_t nblk = ceil_div(ng, 256);
+  if (workspace_bytes < static_cast<size_t>(nblk + 8) * sizeof(float) + 256) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Carver cv(workspace);
+  unsigned int* counter = cv.take<unsigned int>(4);
+  float* block_sums = cv.take<float>(nblk + 8);
+  SSVB_CUDA(cudaMemsetAsync(counter, 0, 16, s));
+  shard_finalize_kernel<<<static_cast<unsigned>(nblk), 256, 0, s>>>(part_all, static_cast<int>(world),
+                                                                    static_cast<int>(n_local), SSVB_LOG2E / temperature,
+                                                                    lse2_all, block_sums, counter,
+                                                                    1.f / static_cast<float>(ng), loss);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_moco_dist_shard_bwd(const void* qhat_all, int64_t n_global, const float* queue_shard,
+                             const void* queue_shard_bf16, int64_t k_local, int64_t d, int64_t ld_queue,
+                             float temperature, const float* lse2_all, float* dacc_partial, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(check_shape(n_global, k_local, d, temperature));
+  if (!qhat_all || !lse2_all || !dacc_partial || !workspace || (!queue_shard && !queue_shard_bf16))
+    return SSVB_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(dacc_partial) & 15) return SSVB_ERR_ALIGNMENT;
+  if (workspace_bytes < ssvb_moco_dist_workspace_bytes(n_global, k_local, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t dpad = sim_dpad(d), npad = round_up(n_global, 128);
+  MocoWs ws = moco_ws(workspace, n_global, k_local, dpad);
+  const float c = SSVB_LOG2E / temperature;
+  const __nv_bfloat16* qb = nullptr;
+  SSVB_TRY(get_queue_bf16(queue_shard, queue_shard_bf16, k_local, d, ld_queue, dpad, ws, s, &qb));
+  SimParams p;
+  moco_plan(p, n_global, k_local, c, 128, 4);
+  p.rowstat = const_cast<float*>(lse2_all);
+  p.colstat = nullptr;
+  p.dacc = dacc_partial;
+  p.ld_dacc = static_cast<int>(dpad);
+  p.use_atomic = p.nchunks > 1;
+  if (p.use_atomic) SSVB_CUDA(cudaMemsetAsync(dacc_partial, 0, npad * dpad * sizeof(float), s));
+  SSVB_TRY(launch_sim_bwd(SIM_MOCO, qhat_all, npad, qb, k_local, dpad, p, s));
+  return SSVB_OK;
+}
+
+int ssvb_moco_dist_finish(const float* query, const float* keys, int64_t n_local, int64_t n_global, int64_t d,
+                          int64_t ld_q, int64_t ld_k, int normalize, float temperature, const float* rowstat_local,
+                          const float* lse2_local, const float* dacc_local, const float* grad_out, float* dquery,
+                          float* dkeys, int64_t ld_dq, int64_t ld_dk, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(check_shape(n_local, 1, d, temperature));
+  SSVB_TRY(check_rows(query, ld_q));
+  SSVB_TRY(check_rows(keys, ld_k));
+  if (dquery) SSVB_TRY(check_rows(dquery, ld_dq));
+  if (dkeys) SSVB_TRY(check_rows(dkeys, ld_dk));
+  if (!rowstat_local || !lse2_local || !dacc_local || !grad_out || (!dquery && !dkeys) || n_global < n_local)
+    return SSVB_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(dacc_local) & 15) return SSVB_ERR_ALIGNMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t dpad = sim_dpad(d);
+  MocoSaved sv{};
+  sv.inv_q = const_cast<float*>(rowstat_local);
+  sv.inv_k = const_cast<float*>(rowstat_local) + n_local;
+  sv.pos = const_cast<float*>(rowstat_local) + 2 * n_local;
+  sv.lse2 = const_cast<float*>(lse2_local);
+  moco_grad_finish_kernel<<<static_cast<unsigned>(ceil_div(n_local, 8)), 256, 0, s>>>(
+      query, keys, ld_q, ld_k, static_cast<int>(n_local), static_cast<int>(d), dacc_local, static_cast<int>(dpad), sv,
+      normalize, SSVB_LOG2E / temperature, 1.f / (static_cast<float>(n_global) * temperature), grad_out, dquery, dkeys,
+      ld_dq, ld_dk);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }

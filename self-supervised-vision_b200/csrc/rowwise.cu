@@ -120,11 +120,15 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __r
 // which is exactly "last writer wins" of the reference's sequential loop.
 __global__ void ring_enqueue_kernel(float* __restrict__ bank, __nv_bfloat16* __restrict__ bank_bf16, int64_t size,
                                     int d, int dpad, int64_t ld_bank, const float* __restrict__ batch, int64_t n,
-                                    int64_t ld_batch, int64_t ptr, int normalize) {
+                                    int64_t ld_batch, int64_t ptr, int normalize, int64_t shard_lo,
+                                    int64_t shard_rows) {
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n || i < n - size) return;
-  const int64_t slot = (ptr + i) % size;
+  int64_t slot = (ptr + i) % size;
+  // sharded ring: `bank` holds global rows [shard_lo, shard_lo + shard_rows); other slots belong to other ranks
+  if (slot < shard_lo || slot >= shard_lo + shard_rows) return;
+  slot -= shard_lo;
   const float4* src = reinterpret_cast<const float4*>(batch + i * ld_batch);
   float inv = 1.f;
   if (normalize) {
@@ -427,7 +431,35 @@ int ssvb_ring_enqueue(float* bank, void* bank_bf16, int64_t size, int64_t d, int
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   ring_enqueue_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(
       bank, static_cast<__nv_bfloat16*>(bank_bf16), size, static_cast<int>(d), static_cast<int>(sim_dpad(d)), ld_bank,
-      batch, n, ld_batch, ptr, normalize);
+      batch, n, ld_batch, ptr, normalize, 0, size);
+  SSVB_LAUNCH_CHECK();
+  *new_ptr = (ptr + n) % size;
+  return SSVB_OK;
+}
+
+// sharded ring (MoCo queue range-partitioned over ranks): `bank_shard` holds global rows
+// [shard_lo, shard_lo + shard_rows) of a ring of `size` rows; `batch` is the GLOBAL batch (all ranks' keys in rank
+// order, all-gathered by the caller); only the rows whose slot falls into this shard are written.  ptr arithmetic is
+// the single-process ring's, identical on every rank.
+int ssvb_ring_enqueue_shard(float* bank_shard, void* bank_shard_bf16, int64_t size, int64_t shard_lo, int64_t shard_rows,
+                            int64_t d, int64_t ld_bank, const float* batch, int64_t n, int64_t ld_batch, int64_t ptr,
+                            int normalize, int64_t* new_ptr, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (size <= 0 || d <= 0 || n < 0 || ptr < 0 || ptr >= size || !new_ptr || shard_lo < 0 || shard_rows <= 0 ||
+      shard_lo + shard_rows > size)
+    return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(bank_shard, ld_bank));
+  if (n == 0) {
+    *new_ptr = ptr;
+    return SSVB_OK;
+  }
+  SSVB_TRY(check_rows(batch, ld_batch));
+  if (bank_shard_bf16 && (reinterpret_cast<uintptr_t>(bank_shard_bf16) & 15)) return SSVB_ERR_ALIGNMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ring_enqueue_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(
+      bank_shard, static_cast<__nv_bfloat16*>(bank_shard_bf16), size, static_cast<int>(d), static_cast<int>(sim_dpad(d)),
+      ld_bank, batch, n, ld_batch, ptr, normalize, shard_lo, shard_rows);
   SSVB_LAUNCH_CHECK();
   *new_ptr = (ptr + n) % size;
   return SSVB_OK;

@@ -89,7 +89,7 @@ __global__ void sk_alpha_kernel(const float* __restrict__ upart, int grid, int k
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
-    alpha[c] = (1.f / static_cast<float>(k)) / t;
+    alpha[c] = raw ? t : (1.f / static_cast<float>(k)) / t;  // raw: the column sums themselves (distributed path)
   }
 }
 

@@ -533,3 +533,172 @@ class DistributedSwavLoss(nn.Module):
     def forward(self, z_1, z_2, prototypes, bank_features=None):
         return _SwavDistFn.apply(z_1, z_2, prototypes, bank_features, self.temperature, self.eps, self.n_iters,
                                  self.group, self.stages)
+
+
+# ======================================================================================================= MoCo (sharded queue)
+class MocoCudaStages:
+    """The product path of the sharded-queue MoCo loss: the `ssvb_moco_dist_*` stages of the C ABI."""
+
+    def dpad(self, d):
+        return C.cached_size("ssvb_ntxent_dpad", d)
+
+    def npad(self, n_global):
+        return C.cached_size("ssvb_moco_dist_npad", n_global)
+
+    def _ws(self, n_global, k_local, d, dev):
+        nbytes = C.cached_size("ssvb_moco_dist_workspace_bytes", n_global, k_local, d)
+        return C.workspace("moco_dist", nbytes, dev), nbytes
+
+    def prep(self, q, k, normalize, world, rank, qhat_all, rowstat):
+        n, d = q.shape
+        C.check(C.lib().ssvb_moco_dist_prep(C.ptr(q), C.ptr(k), n, d, q.stride(0), k.stride(0), normalize, world, rank,
+                                            C.ptr(qhat_all), C.ptr(rowstat), C.stream_ptr(q.device)),
+                "ssvb_moco_dist_prep")
+
+    def shard_fwd(self, qhat_all, n_global, shard, shadow, d, temperature, rowstat, n_local, part_local):
+        ws, nb = self._ws(n_global, shard.shape[0], d, shard.device)
+        C.check(C.lib().ssvb_moco_dist_shard_fwd(C.ptr(qhat_all), n_global, C.ptr(shard), C.ptr(shadow), shard.shape[0],
+                                                 d, shard.stride(0), temperature, C.ptr(rowstat), n_local,
+                                                 C.ptr(part_local), C.ptr(ws), nb, C.stream_ptr(shard.device)),
+                "ssvb_moco_dist_shard_fwd")
+
+    def finalize(self, part_all, world, n_local, temperature, lse2_all, loss, k_local, d):
+        ws, nb = self._ws(world * n_local, k_local, d, part_all.device)
+        C.check(C.lib().ssvb_moco_dist_finalize(C.ptr(part_all), world, n_local, temperature, C.ptr(lse2_all),
+                                                C.ptr(loss), C.ptr(ws), nb, C.stream_ptr(part_all.device)),
+                "ssvb_moco_dist_finalize")
+
+    def shard_bwd(self, qhat_all, n_global, shard, shadow, d, temperature, lse2_all, dacc_partial):
+        ws, nb = self._ws(n_global, shard.shape[0], d, shard.device)
+        C.check(C.lib().ssvb_moco_dist_shard_bwd(C.ptr(qhat_all), n_global, C.ptr(shard), C.ptr(shadow), shard.shape[0],
+                                                 d, shard.stride(0), temperature, C.ptr(lse2_all), C.ptr(dacc_partial),
+                                                 C.ptr(ws), nb, C.stream_ptr(shard.device)), "ssvb_moco_dist_shard_bwd")
+
+    def finish(self, q, k, n_global, normalize, temperature, rowstat, lse2_local, dacc_local, grad_out, dq, dk):
+        n, d = q.shape
+        C.check(C.lib().ssvb_moco_dist_finish(C.ptr(q), C.ptr(k), n, n_global, d, q.stride(0), k.stride(0), normalize,
+                                              temperature, C.ptr(rowstat), C.ptr(lse2_local), C.ptr(dacc_local),
+                                              C.ptr(grad_out), C.ptr(dq), C.ptr(dk), dq.stride(0), dk.stride(0),
+                                              C.stream_ptr(q.device)), "ssvb_moco_dist_finish")
+
+
+class _MocoDistFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, query, keys, shard, normalize, temperature, group, stages):
+        world, rank = _world_rank(group)
+        cuda = isinstance(stages, MocoCudaStages)
+        if cuda:
+            C.require_cuda(query, keys, shard)
+            q, k = C.as_f32_rows(query), C.as_f32_rows(keys)
+            mem = C.as_f32_rows(shard.detach())
+            from .banks import lookup_shadow
+            shadow = lookup_shadow(shard) if mem.data_ptr() == shard.data_ptr() else None
+        else:
+            q, k, mem = (t.detach().float().contiguous() for t in (query, keys, shard))
+            shadow = None
+        if q.shape != k.shape or q.dim() != 2 or mem.dim() != 2 or mem.shape[1] != q.shape[1]:
+            raise ValueError("MocoLoss expects query/keys [N, d] and a queue shard [K_local, d]")
+        n, d = q.shape
+        ng = n * world
+        dev = q.device
+        norm = int(bool(normalize))
+        tau = float(temperature)
+        npad, dpad = stages.npad(ng), stages.dpad(d)
+        qhat_all = torch.empty(npad, dpad, dtype=torch.bfloat16, device=dev)
+        rowstat = torch.empty(3, n, dtype=torch.float32, device=dev)
+        stages.prep(q, k, norm, world, rank, qhat_all, rowstat)
+        if world > 1:
+            _gather_slots(qhat_all[:ng], qhat_all[rank * n:(rank + 1) * n], group, inplace=cuda)
+        blk = 2 * ng + n
+        part_all = torch.empty(world, blk, dtype=torch.float32, device=dev)
+        stages.shard_fwd(qhat_all, ng, mem, shadow, d, tau, rowstat, n, part_all[rank])
+        if world > 1:
+            _gather_slots(part_all, part_all[rank:rank + 1], group, inplace=cuda)
+        lse2_all = torch.zeros(npad, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        stages.finalize(part_all, world, n, tau, lse2_all, loss, mem.shape[0], d)
+        ctx.save_for_backward(q, k, mem, qhat_all, rowstat, lse2_all)
+        ctx.shadow = shadow
+        ctx.cfg = (norm, tau, world, rank, group, stages, query.dtype, keys.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        q, k, mem, qhat_all, rowstat, lse2_all = ctx.saved_tensors
+        norm, tau, world, rank, group, stages, dtq, dtk = ctx.cfg
+        n, d = q.shape
+        ng = n * world
+        dev = q.device
+        go = C.f32_scalar(grad_out)
+        dacc = torch.empty(qhat_all.shape[0], qhat_all.shape[1], dtype=torch.float32, device=dev)
+        stages.shard_bwd(qhat_all, ng, mem, ctx.shadow, d, tau, lse2_all, dacc)
+        # sum_j p_aj m_j over ALL shards, for this rank's own query rows only: reduce-scatter
+        dacc_local = _reduce_scatter_rows(dacc[:ng], n, rank, group) if world > 1 else dacc[:n]
+        dq, dk = torch.empty_like(q), torch.empty_like(k)
+        stages.finish(q, k, ng, norm, tau, rowstat, lse2_all[rank * n:(rank + 1) * n], dacc_local, go, dq, dk)
+        return dq.to(dtq), dk.to(dtk), None, None, None, None, None
+
+
+class DistributedMocoLoss(nn.Module):
+    """MocoLoss (reference utils/losses.py:49-72, same ctor kwargs) with the queue SHARDED over the ranks of a process
+    group: forward(query, keys, queue_shard) where queue_shard is this rank's K/world rows (ShardedMemoryBank).
+    all-gather of the bf16 queries, all-gather of the per-shard (max, sum-exp) partials (combined in rank order: the
+    global loss is identical on every rank), reduce-scatter of the query-gradient partials."""
+
+    def __init__(self, normalize=True, temperature=1.0, group=None, stages=None):
+        super().__init__()
+        self.normalize = normalize
+        self.temperature = temperature
+        self.group = group
+        self.stages = stages if stages is not None else MocoCudaStages()
+
+    def forward(self, query, keys, memory_vectors):
+        return _MocoDistFn.apply(query, keys, memory_vectors, self.normalize, self.temperature, self.group, self.stages)
+
+
+class ShardedMemoryBank:
+    """MemoryBank (reference models/moco.py:23-39) range-partitioned over the ranks of a process group: rank s holds
+    global rows [s*K/world, (s+1)*K/world).  `add_batch(keys)` all-gathers the local keys (rank order = the
+    concatenated global batch) and every rank writes the rows of [ptr, ptr + N_global) mod K that fall into its shard;
+    `ptr` is the single-process ring's pointer, identical on every rank (bit-exact bookkeeping)."""
+
+    def __init__(self, queue_size, feature_size, group=None, device=None):
+        from .banks import _Ring
+        world, rank = _world_rank(group)
+        if queue_size % world:
+            raise ValueError("queue_size must be divisible by the world size")
+        self.size = queue_size
+        self.group = group
+        self.world, self.rank = world, rank
+        self.shard_rows = queue_size // world
+        self.shard_lo = rank * self.shard_rows
+        self._ring = _Ring()
+        self._ring._init_ring(self.shard_rows, feature_size, device, normalize=True, with_shadow=True)
+        self.ptr = 0
+
+    @property
+    def bank(self):
+        return self._ring._data
+
+    def get_vectors(self):
+        return self._ring._data
+
+    def add_batch(self, batch):
+        import ctypes
+        r = self._ring
+        b = C.as_f32_rows(batch.detach().to(r._device, non_blocking=True))
+        if self.world > 1:
+            allb = torch.empty(self.world * b.shape[0], b.shape[1], dtype=torch.float32, device=r._device)
+            dist.all_gather_into_tensor(allb, b, group=self.group)
+        else:
+            allb = b
+        rows, dim = r._data.shape
+        new_ptr = ctypes.c_int64(-1)
+        shadow_ok = r._shadow is not None and r._shadow_version == r._data._version
+        with torch.cuda.device(r._device):
+            C.check(C.lib().ssvb_ring_enqueue_shard(C.ptr(r._data), C.ptr(r._shadow) if shadow_ok else None, self.size,
+                                                    self.shard_lo, rows, dim, r._data.stride(0), C.ptr(allb),
+                                                    allb.shape[0], allb.stride(0), int(self.ptr), 1,
+                                                    ctypes.cast(ctypes.pointer(new_ptr), ctypes.c_void_p),
+                                                    C.stream_ptr(r._device)), "ssvb_ring_enqueue_shard")
+        self.ptr = int(new_ptr.value)

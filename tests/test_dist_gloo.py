@@ -334,3 +334,107 @@ def test_distributed_swav_matches_global_oracle(nbank):
     ref_codes = O.sinkhorn(np.concatenate([out[r]["sc"] for r in range(world)]), 0.05, 3)
     for r in range(world):
         assert np.allclose(out[r]["codes"], ref_codes[r * nb:(r + 1) * nb], rtol=1e-4, atol=1e-7)
+
+
+# ======================================================================================================= MoCo (sharded queue)
+class EmulatedMocoStages:
+    """torch-fp64 stand-in for the ssvb_moco_dist_* stages (test-only): log2-domain (max, sum) shard partials."""
+    LOG2E = 1.4426950408889634
+
+    def dpad(self, d):
+        return d
+
+    def npad(self, n_global):
+        return n_global
+
+    def prep(self, q, k, normalize, world, rank, qhat_all, rowstat):
+        n = q.shape[0]
+        qd, kd = q.double(), k.double()
+        iq = 1.0 / qd.norm(dim=1).clamp_min(1e-12) if normalize else torch.ones(n, dtype=torch.float64)
+        ik = 1.0 / kd.norm(dim=1).clamp_min(1e-12) if normalize else torch.ones(n, dtype=torch.float64)
+        qh, kh = qd * iq[:, None], kd * ik[:, None]
+        qhat_all[rank * n:(rank + 1) * n] = qh.to(qhat_all.dtype)
+        rowstat[0].copy_(iq.float())
+        rowstat[1].copy_(ik.float())
+        rowstat[2].copy_((qh * kh).sum(1).float())
+
+    def shard_fwd(self, qhat_all, n_global, shard, shadow, d, temperature, rowstat, n_local, part_local):
+        c = self.LOG2E / temperature
+        t = (qhat_all[:n_global].double() @ shard.double().t()) * c
+        m = t.max(1).values
+        part_local[:n_global].copy_(m.float())
+        part_local[n_global:2 * n_global].copy_(torch.exp2(t - m[:, None]).sum(1).float())
+        part_local[2 * n_global:].copy_(rowstat[2])
+
+    def finalize(self, part_all, world, n_local, temperature, lse2_all, loss, k_local, d):
+        ng = world * n_local
+        c = self.LOG2E / temperature
+        pa = part_all.double()
+        p2 = torch.cat([pa[w, 2 * ng:] for w in range(world)]) * c
+        m = torch.maximum(pa[:, :ng].max(0).values, p2)
+        l = torch.exp2(p2 - m) + (pa[:, ng:2 * ng] * torch.exp2(pa[:, :ng] - m)).sum(0)
+        lse2 = m + torch.log2(l)
+        lse2_all[:ng].copy_(lse2.float())
+        loss.copy_((((lse2 - p2) / self.LOG2E).sum() / ng).float())
+
+    def shard_bwd(self, qhat_all, n_global, shard, shadow, d, temperature, lse2_all, dacc_partial):
+        c = self.LOG2E / temperature
+        t = (qhat_all[:n_global].double() @ shard.double().t()) * c
+        p = torch.exp2(t - lse2_all[:n_global].double()[:, None])
+        dacc_partial[:n_global].copy_((p @ shard.double()).float())
+
+    def finish(self, q, k, n_global, normalize, temperature, rowstat, lse2_local, dacc_local, grad_out, dq, dk):
+        c = self.LOG2E / temperature
+        iq, ik, pos = rowstat[0].double(), rowstat[1].double(), rowstat[2].double()
+        qh, kh = q.double() * iq[:, None], k.double() * ik[:, None]
+        p0m1 = (torch.exp2(pos * c - lse2_local.double()) - 1.0)[:, None]
+        scale = grad_out.double() / (n_global * temperature)
+        gq = (p0m1 * kh + dacc_local.double()) * scale
+        gk = p0m1 * qh * scale
+        if normalize:
+            gq = (gq - (gq * qh).sum(1, keepdim=True) * qh) * iq[:, None]
+            gk = (gk - (gk * kh).sum(1, keepdim=True) * kh) * ik[:, None]
+        dq.copy_(gq.float())
+        dk.copy_(gk.float())
+
+
+def _moco_worker(rank, world, port, n_local, k_total, d, tau, out):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "self-supervised-vision_b200")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ssv_b200.dist import DistributedMocoLoss
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(400 + rank)
+    q = torch.randn(n_local, d, generator=g, requires_grad=True)
+    k = torch.randn(n_local, d, generator=g, requires_grad=True)
+    gq = torch.Generator().manual_seed(9)
+    queue = F.normalize(torch.randn(k_total, d, generator=gq))
+    queue[3] = 0.0  # a never-written (zero) row, as in a fresh MemoryBank
+    kl = k_total // world
+    shard = queue[rank * kl:(rank + 1) * kl].contiguous()
+    loss = DistributedMocoLoss(True, tau, stages=EmulatedMocoStages())(q, k, shard)
+    (0.5 * loss).backward()
+    out[rank] = dict(loss=loss.item(), dq=q.grad.numpy().copy(), dk=k.grad.numpy().copy(), q=q.detach().numpy().copy(),
+                     k=k.detach().numpy().copy(), queue=queue.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tau", [0.07, 1.0])
+def test_distributed_moco_sharded_queue_matches_global_oracle(tau):
+    from oracle import ssl_oracle as O
+    world, n_local, k_total, d = 2, 12, 40, 16
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 35500 + (os.getpid() % 2000)
+    mp.spawn(_moco_worker, args=(world, port, n_local, k_total, d, tau, out), nprocs=world, join=True)
+    q = np.concatenate([out[r]["q"] for r in range(world)])
+    k = np.concatenate([out[r]["k"] for r in range(world)])
+    ref_loss, ref_dq, ref_dk = O.moco(q, k, out[0]["queue"], True, tau)
+    for r in range(world):
+        o = out[r]
+        assert abs(o["loss"] - ref_loss) / abs(ref_loss) < 1e-3  # queries travel in bf16
+        sl = slice(r * n_local, (r + 1) * n_local)
+        assert np.linalg.norm(o["dq"] - 0.5 * ref_dq[sl]) / np.linalg.norm(0.5 * ref_dq[sl]) < 2e-2  # bf16 query gather
+        assert np.linalg.norm(o["dk"] - 0.5 * ref_dk[sl]) / np.linalg.norm(0.5 * ref_dk[sl]) < 2e-2
+    assert out[0]["loss"] == out[1]["loss"]

@@ -55,3 +55,159 @@ def test_dist_ntxent_vs_oracle(n_local, d, normalize, tau, transport):
         sl = slice(r * n_local, (r + 1) * n_local)
         assert np.linalg.norm(gi - ref_dzi[sl]) / np.linalg.norm(ref_dzi[sl]) <= 1e-2
         assert np.linalg.norm(gj - ref_dzj[sl]) / np.linalg.norm(ref_dzj[sl]) <= 1e-2
+
+
+# ======================================================================================================= other losses
+def _init(rank, world, port):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "self-supervised-vision_b200")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+
+
+def _unit(x):
+    return torch.nn.functional.normalize(x, dim=1)
+
+
+def _barlow_worker(rank, world, port, n_local, d, normalize, out):
+    _init(rank, world, port)
+    from ssv_b200.dist import DistributedBarlowLoss
+    g = torch.Generator().manual_seed(200 + rank)
+    zi = torch.randn(n_local, d, generator=g) * 1.5 + 0.3
+    zj = zi * 0.7 + 0.5 * torch.randn(n_local, d, generator=g)
+    a, b = zi.cuda().requires_grad_(True), zj.cuda().requires_grad_(True)
+    fn = DistributedBarlowLoss(normalize, 0.005)
+    for _ in range(2):
+        a.grad = None; b.grad = None
+        loss = fn(a, b)
+        loss.backward()
+    torch.cuda.synchronize()
+    out[rank] = (loss.item(), a.grad.cpu().numpy(), b.grad.cpu().numpy(), zi.numpy(), zj.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_local,d,normalize", [(128, 1024, False), (100, 264, True), (64, 1000, False)])
+def test_dist_barlow_vs_oracle(n_local, d, normalize):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from oracle import ssl_oracle as O
+    world = min(torch.cuda.device_count(), 4)
+    if d == 1000:
+        world = min(world, 3) if torch.cuda.device_count() >= 3 else 2  # 1000 % 3 != 0 -> all-reduce path at world 3
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29900 + (os.getpid() % 2000)
+    mp.spawn(_barlow_worker, args=(world, port, n_local, d, normalize, out), nprocs=world, join=True)
+    zi = np.concatenate([out[r][3] for r in range(world)])
+    zj = np.concatenate([out[r][4] for r in range(world)])
+    ref_loss, ref_di, ref_dj = O.barlow(zi, zj, normalize, 0.005)
+    for r in range(world):
+        loss, gi, gj, _, _ = out[r]
+        assert abs(loss - ref_loss) / abs(ref_loss) <= 1e-3
+        sl = slice(r * n_local, (r + 1) * n_local)
+        assert np.linalg.norm(gi - ref_di[sl]) / np.linalg.norm(ref_di[sl]) <= 1e-2
+        assert np.linalg.norm(gj - ref_dj[sl]) / np.linalg.norm(ref_dj[sl]) <= 1e-2
+    assert len({out[r][0] for r in range(world)}) == 1, "every rank must report the same global loss"
+
+
+def _swav_worker(rank, world, port, nb, nbank, k, d, out):
+    _init(rank, world, port)
+    from ssv_b200.dist import DistributedSwavLoss
+    g = torch.Generator().manual_seed(300 + rank)
+    z1 = _unit(torch.randn(nb, d, generator=g))
+    z2 = _unit(0.6 * z1 + 0.4 * torch.randn(nb, d, generator=g))
+    bank = _unit(torch.randn(nbank, d, generator=g)) if nbank else None
+    pc = _unit(torch.randn(k, d, generator=torch.Generator().manual_seed(7)))
+    a, b, p = z1.cuda().requires_grad_(True), z2.cuda().requires_grad_(True), pc.cuda().requires_grad_(True)
+    fn = DistributedSwavLoss(0.1, 0.05, 3)
+    loss = fn(a, b, p, bank.cuda() if nbank else None)
+    loss.backward()
+    sc = (z1 @ pc.t()).contiguous()
+    codes = fn.compute_codes_sinkhorn(sc.cuda())
+    torch.cuda.synchronize()
+    out[rank] = dict(loss=loss.item(), dz1=a.grad.cpu().numpy(), dz2=b.grad.cpu().numpy(), dpc=p.grad.cpu().numpy(),
+                     z1=z1.numpy(), z2=z2.numpy(), bank=bank.numpy() if nbank else None, pc=pc.numpy(), sc=sc.numpy(),
+                     codes=codes.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nb,nbank,k,d", [(256, 0, 3000, 128), (128, 200, 1000, 64)])
+def test_dist_swav_vs_oracle(nb, nbank, k, d):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from oracle import ssl_oracle as O
+    world = min(torch.cuda.device_count(), 4)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 30100 + (os.getpid() % 2000)
+    mp.spawn(_swav_worker, args=(world, port, nb, nbank, k, d, out), nprocs=world, join=True)
+    z1 = np.concatenate([out[r]["z1"] for r in range(world)])
+    z2 = np.concatenate([out[r]["z2"] for r in range(world)])
+    bank = np.concatenate([out[r]["bank"] for r in range(world)]) if nbank else None
+    ref_loss, ref_dz1, ref_dz2, ref_dc = O.swav(z1, z2, out[0]["pc"], bank, 0.1, 0.05, 3)
+    rl2 = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)  # noqa: E731
+    for r in range(world):
+        o = out[r]
+        assert abs(o["loss"] - ref_loss) / abs(ref_loss) <= 1e-3
+        sl = slice(r * nb, (r + 1) * nb)
+        assert rl2(o["dz1"], ref_dz1[sl]) <= 1e-2 and rl2(o["dz2"], ref_dz2[sl]) <= 1e-2 and rl2(o["dpc"], ref_dc) <= 1e-2
+    ref_codes = O.sinkhorn(np.concatenate([out[r]["sc"] for r in range(world)]), 0.05, 3)
+    for r in range(world):
+        assert rl2(out[r]["codes"], ref_codes[r * nb:(r + 1) * nb]) < 1e-4
+
+
+def _moco_worker(rank, world, port, n_local, k_total, d, tau, out):
+    _init(rank, world, port)
+    from ssv_b200.dist import DistributedMocoLoss, ShardedMemoryBank
+    g = torch.Generator().manual_seed(400 + rank)
+    q = torch.randn(n_local, d, generator=g)
+    k = torch.randn(n_local, d, generator=g)
+    fill = torch.randn(k_total - 40, d, generator=torch.Generator().manual_seed(9))  # same on every rank
+    bank = ShardedMemoryBank(k_total, d)
+    per = fill.shape[0] // world  # each rank contributes its slice; the all-gather restores rank order
+    bank.add_batch(fill[rank * per:(rank + 1) * per].cuda())
+    a, b = q.cuda().requires_grad_(True), k.cuda().requires_grad_(True)
+    before = bank.get_vectors().cpu().numpy().copy()
+    loss = DistributedMocoLoss(True, tau)(a, b, bank.get_vectors())
+    loss.backward()
+    ptr_before = bank.ptr
+    bank.add_batch(b.detach())   # wraps around the end of the ring
+    torch.cuda.synchronize()
+    out[rank] = dict(loss=loss.item(), dq=a.grad.cpu().numpy(), dk=b.grad.cpu().numpy(), q=q.numpy(), k=k.numpy(),
+                     before=before, after=bank.get_vectors().cpu().numpy(), ptr_before=ptr_before, ptr=bank.ptr,
+                     fill=fill[:per * world].numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_local,k_total,d,tau", [(64, 8192, 128, 0.07), (48, 1024, 64, 0.2)])
+def test_dist_moco_sharded_queue_vs_oracle(n_local, k_total, d, tau):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from oracle import ssl_oracle as O
+    world = 4 if torch.cuda.device_count() >= 4 else 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 30300 + (os.getpid() % 2000)
+    mp.spawn(_moco_worker, args=(world, port, n_local, k_total, d, tau, out), nprocs=world, join=True)
+    q = np.concatenate([out[r]["q"] for r in range(world)])
+    k = np.concatenate([out[r]["k"] for r in range(world)])
+    queue = np.concatenate([out[r]["before"] for r in range(world)])
+    # the sharded ring after the fill == single-process ring fed the same global batch
+    ref_bank, ref_ptr = O.ring_enqueue(np.zeros((k_total, d), np.float32), 0, out[0]["fill"], True)
+    np.testing.assert_allclose(queue, ref_bank, rtol=5e-7, atol=0)
+    assert all(out[r]["ptr_before"] == ref_ptr for r in range(world))
+    ref_loss, ref_dq, ref_dk = O.moco(q, k, queue, True, tau)
+    rl2 = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)  # noqa: E731
+    for r in range(world):
+        o = out[r]
+        assert abs(o["loss"] - ref_loss) / abs(ref_loss) <= 1e-3
+        sl = slice(r * n_local, (r + 1) * n_local)
+        assert rl2(o["dq"], ref_dq[sl]) <= 1e-2 and rl2(o["dk"], ref_dk[sl]) <= 1e-2
+    assert len({out[r]["loss"] for r in range(world)}) == 1
+    ref_bank2, ref_ptr2 = O.ring_enqueue(queue.copy(), ref_ptr, k, True)
+    after = np.concatenate([out[r]["after"] for r in range(world)])
+    np.testing.assert_allclose(after, ref_bank2, rtol=5e-7, atol=0)
+    assert all(out[r]["ptr"] == ref_ptr2 for r in range(world))
