@@ -255,6 +255,8 @@ int ssvb_sinkhorn(const float* scores, int64_t b, int64_t k, int64_t ld_scores, 
  *       pass(phase 0): u_local[0..k) = sum_b E_bk relative to this rank's maximum, u_local[k] = that maximum;
  *       pass(phase 1): u_local[0..k) = sum_b E_bk / (b_global v_b)  (needs the global alpha [k] and smax [1]);
  *       pass(phase 2): codes of the local rows.
+ *     `codes` must be the SAME buffer in all three phases (its alignment selects the kernel family); it is written
+ *     in phase 2 only.
  *     Between passes the caller ALL-GATHERS u_local (k+1 floats per rank) and calls ssvb_sinkhorn_dist_alpha, which
  *     combines the blocks in rank order (identical on every rank: the all-reduce of the marginals) into
  *     alpha_k = (1/K)/u_k and, after phase 0, the global maximum.  n_iters iterations = phase 0, (n_iters-1) x

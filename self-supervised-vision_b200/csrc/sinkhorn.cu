@@ -74,21 +74,24 @@ __global__ void sk_max_kernel(const float* __restrict__ s, int64_t b, int k, int
     }
   }
 }
-// alpha_k = (1/K) / sum_g upart[g][k].  block (32 columns, 8 row-slices): each thread sums every 8th partial row of
+constexpr int kSkSlices = 32;  // row slices per column group in the alpha kernels (block = 32 x 32 threads)
+// alpha_k = (1/K) / sum_g upart[g][k].  block (32 columns, kSkSlices row-slices): each thread sums every 8th partial row of
 // its column (coalesced 128-byte row segments), fixed-order combine through shared memory -> ~94 CTAs instead of 12.
 __global__ void sk_alpha_kernel(const float* __restrict__ upart, int grid, int kpad, int k, float* __restrict__ alpha,
                                 int raw = 0) {
-  __shared__ float sh[8][33];
+  __shared__ float sh[kSkSlices][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float u = 0.f;
-  if (c < k)
-    for (int g = threadIdx.y; g < grid; g += 8) u += upart[static_cast<size_t>(g) * kpad + c];
+  if (c < k) {
+#pragma unroll 6
+    for (int g = threadIdx.y; g < grid; g += kSkSlices) u += upart[static_cast<size_t>(g) * kpad + c];
+  }
   sh[threadIdx.y][threadIdx.x] = u;
   __syncthreads();
   if (threadIdx.y == 0 && c < k) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    for (int i = 0; i < kSkSlices; ++i) t += sh[i][threadIdx.x];
     alpha[c] = raw ? t : (1.f / static_cast<float>(k)) / t;  // raw: the column sums themselves (distributed path)
   }
 }
@@ -97,29 +100,33 @@ __global__ void sk_alpha_kernel(const float* __restrict__ upart, int grid, int k
 __global__ void sk_alpha0_kernel(const float* __restrict__ upart, const float* __restrict__ mpart, int grid, int kpad,
                                  int k, float inv_eps_log2e, float* __restrict__ alpha, float* __restrict__ smax,
                                  int raw = 0) {
-  __shared__ float sh[8][33];
-  __shared__ float msh[8][33];
+  __shared__ float sh[kSkSlices][33];
+  __shared__ float msh[32];
   const int tid = threadIdx.y * 32 + threadIdx.x;
   float m = -INFINITY;
-  for (int g = tid; g < grid; g += 256) m = fmaxf(m, mpart[g]);
-  msh[threadIdx.y][threadIdx.x] = m;
+  for (int g = tid; g < grid; g += 32 * kSkSlices) m = fmaxf(m, mpart[g]);
+  m = warp_max(m);
+  if (threadIdx.x == 0) msh[threadIdx.y] = m;
   __syncthreads();
   float M = -INFINITY;
-  for (int i = 0; i < 8; ++i)
-    for (int j = 0; j < 32; ++j) M = fmaxf(M, msh[i][j]);
+#pragma unroll
+  for (int i = 0; i < kSkSlices; ++i) M = fmaxf(M, msh[i]);
   const int c = blockIdx.x * 32 + threadIdx.x;
   float u = 0.f;
-  if (c < k)
-    for (int g = threadIdx.y; g < grid; g += 8) {
+  if (c < k) {
+#pragma unroll 6
+    for (int g = threadIdx.y; g < grid; g += kSkSlices) {
       const float mg = mpart[g];
-      if (mg != -INFINITY) u = fmaf(upart[static_cast<size_t>(g) * kpad + c], ex2f((mg - M) * inv_eps_log2e), u);
+      const float x = upart[static_cast<size_t>(g) * kpad + c];
+      if (mg != -INFINITY) u = fmaf(x, ex2f((mg - M) * inv_eps_log2e), u);
     }
+  }
   sh[threadIdx.y][threadIdx.x] = u;
   __syncthreads();
   if (threadIdx.y == 0 && c < k) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    for (int i = 0; i < kSkSlices; ++i) t += sh[i][threadIdx.x];
     alpha[c] = raw ? t : (1.f / static_cast<float>(k)) / t;
   }
   if (blockIdx.x == 0 && tid == 0) smax[0] = M;
@@ -345,12 +352,206 @@ sk_rowreg_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, floa
   }
 }
 
+// Fast path v2 (K <= 3072, K % 4 == 0, 16-byte aligned rows): the row stream is decoupled from the math by a TMA ring.
+// One producer warp issues 1-D bulk copies (cp.async.bulk, one whole score row = K*4 bytes per copy, completion on an
+// mbarrier) into a ring of `nst` row slots (up to 16 rows = 192 KB in flight per SM); 8 consumer warps take rows round
+// robin, pull the row from shared memory into registers (24 float4 per lane), hand the slot straight back to the
+// producer, and run the same per-row math as sk_rowreg_kernel (online max in PHASE 0, column sums in registers).
+// The ring is reused for the fixed-order cross-warp combine at the end.
+constexpr int kSkConsumers = 7;  // + 1 producer warp = 8 warps: 2 per SM sub-partition, so 255 registers stay available
+
+// Fast path v2 (K <= 3072, K % 4 == 0, 16-byte aligned rows): the row stream is decoupled from the math by a TMA ring.
+// One producer warp issues 1-D bulk copies (cp.async.bulk, one whole score row = K*4 bytes per copy, completion on an
+// mbarrier) into a ring of `nst` row slots (up to 16 rows = 192 KB in flight per SM); the scaling vector alpha arrives
+// by one more bulk copy (a serial LDG -> STS prologue cost 27 % of the kernel).  7 consumer warps take rows round
+// robin, pull the row from shared memory into registers (24 float4 per lane), hand the slot straight back to the
+// producer, and run the per-row math (online max in PHASE 0, column sums in registers).  The ring is reused for the
+// fixed-order cross-warp combine at the end.
+// Measured (profiles/r1_sinkhorn_tuning.md): a pass is bound by the ~6.5 TB/s the L2 -> SM fabric delivers (one row
+// per warp every ~1.9 us while its math takes ~1 us), so caching exp() between passes or fusing the passes into one
+// cooperative kernel (both tried) buys nothing; the remaining cost is the fixed ~3-4 us per launch.
 template <int PHASE>
-int sk_launch_fast(int grid, size_t smem, cudaStream_t s, const float* scores, int64_t b, int k, int64_t ld, float iel,
+__global__ void __launch_bounds__((kSkConsumers + 1) * 32, 1)
+sk_tma_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, float inv_eps_log2e,
+              const float* __restrict__ smax, const float* __restrict__ alpha, float* __restrict__ upart, int kpad,
+              float* __restrict__ codes, int64_t ldc, float* __restrict__ mpart, float inv_b, int nst, int rowf) {
+  extern __shared__ __align__(128) float sk_smem[];  // [nst][rowf] ring | [kpad] alpha | 2*nst + 1 mbarriers
+  float* ring = sk_smem;
+  float* alpha_s = sk_smem + static_cast<size_t>(nst) * rowf;
+  uint64_t* full = reinterpret_cast<uint64_t*>(alpha_s + kpad);
+  uint64_t* empty = full + nst;
+  uint64_t* abar = empty + nst;
+  __shared__ float mw_s[kSkConsumers];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k4 = k >> 2;
+  const int n_my = blockIdx.x < b ? static_cast<int>((b - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nst; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(abar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  float4 acc[kSkNV];
+#pragma unroll
+  for (int j = 0; j < kSkNV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float Mw = -INFINITY;
+
+  if (w == kSkConsumers) {
+    // ---- producer: one elected lane streams this CTA's rows through the ring
+    if (lane == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(k) * 4u;
+      if (PHASE != 0) {
+        mbar_expect_tx(abar, bytes);
+        bulk_load_1d(alpha_s, alpha, bytes, abar);
+      }
+      for (int i = 0; i < n_my; ++i) {
+        const int slot = i % nst;
+        if (i >= nst) mbar_wait(&empty[slot], ((i / nst) - 1) & 1);
+        const int64_t r = blockIdx.x + static_cast<int64_t>(i) * gridDim.x;
+        mbar_expect_tx(&full[slot], bytes);
+        bulk_load_1d(ring + static_cast<size_t>(slot) * rowf, s + r * ld, bytes, &full[slot]);
+      }
+    }
+  } else {
+    float shift = 0.f;
+    if (PHASE != 0) {
+      shift = smax[0] * inv_eps_log2e;
+      mbar_wait(abar, 0);
+    }
+    for (int i = w; i < n_my; i += kSkConsumers) {
+      const int slot = i % nst;
+      const int64_t r = blockIdx.x + static_cast<int64_t>(i) * gridDim.x;
+      mbar_wait(&full[slot], (i / nst) & 1);
+      const float4* row = reinterpret_cast<const float4*>(ring + static_cast<size_t>(slot) * rowf);
+      float4 e[kSkNV];
+#pragma unroll
+      for (int j = 0; j < kSkNV; ++j) {
+        const int c4 = lane + 32 * j;
+        e[j] = (c4 < k4) ? row[c4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);  // the row now lives in registers: give the slot back
+      if (PHASE == 0) {
+        float rm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kSkNV; ++j) rm = fmaxf(rm, fmaxf(fmaxf(e[j].x, e[j].y), fmaxf(e[j].z, e[j].w)));
+        rm = warp_max(rm);
+        if (rm > Mw) {  // warp-uniform
+          const float sc = ex2f((Mw - rm) * inv_eps_log2e);  // 0 on the first row (Mw = -inf)
+#pragma unroll
+          for (int j = 0; j < kSkNV; ++j) { acc[j].x *= sc; acc[j].y *= sc; acc[j].z *= sc; acc[j].w *= sc; }
+          Mw = rm;
+        }
+        shift = Mw * inv_eps_log2e;
+      }
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < kSkNV; ++j) {
+        e[j].x = ex2f(fmaf(e[j].x, inv_eps_log2e, -shift));
+        e[j].y = ex2f(fmaf(e[j].y, inv_eps_log2e, -shift));
+        e[j].z = ex2f(fmaf(e[j].z, inv_eps_log2e, -shift));
+        e[j].w = ex2f(fmaf(e[j].w, inv_eps_log2e, -shift));
+        if (PHASE != 0) {
+          const int c4 = lane + 32 * j;
+          if (c4 < k4) {
+            const float4 a = reinterpret_cast<const float4*>(alpha_s)[c4];
+            v += (e[j].x * a.x + e[j].y * a.y) + (e[j].z * a.z + e[j].w * a.w);
+          }
+        }
+      }
+      if (PHASE == 0) {
+#pragma unroll
+        for (int j = 0; j < kSkNV; ++j) { acc[j].x += e[j].x; acc[j].y += e[j].y; acc[j].z += e[j].z; acc[j].w += e[j].w; }
+      } else {
+        v = warp_sum(v);
+        if (PHASE == 1) {
+          const float beta = inv_b / v;
+#pragma unroll
+          for (int j = 0; j < kSkNV; ++j) {
+            acc[j].x = fmaf(e[j].x, beta, acc[j].x); acc[j].y = fmaf(e[j].y, beta, acc[j].y);
+            acc[j].z = fmaf(e[j].z, beta, acc[j].z); acc[j].w = fmaf(e[j].w, beta, acc[j].w);
+          }
+        } else {
+          const float iv = 1.f / v;
+          float4* out = reinterpret_cast<float4*>(codes + r * ldc);
+#pragma unroll
+          for (int j = 0; j < kSkNV; ++j) {
+            const int c4 = lane + 32 * j;
+            if (c4 < k4) {
+              const float4 a = reinterpret_cast<const float4*>(alpha_s)[c4];
+              out[c4] = make_float4(e[j].x * a.x * iv, e[j].y * a.y * iv, e[j].z * a.z * iv, e[j].w * a.w * iv);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (PHASE != 2) {
+    // every bulk copy has been consumed (each consumer waited on all of its rows): the ring is free for the combine
+    __syncthreads();
+    if (w < kSkConsumers) {
+      float* mine = ring + static_cast<size_t>(w) * kpad;
+#pragma unroll
+      for (int j = 0; j < kSkNV; ++j) {
+        const int c4 = lane + 32 * j;
+        if (c4 < k4) reinterpret_cast<float4*>(mine)[c4] = acc[j];
+      }
+      if (PHASE == 0 && lane == 0) mw_s[w] = Mw;
+    }
+    __syncthreads();
+    float wsc[kSkConsumers];
+#pragma unroll
+    for (int ww = 0; ww < kSkConsumers; ++ww) wsc[ww] = 1.f;
+    if (PHASE == 0) {
+      float mb = -INFINITY;
+      for (int ww = 0; ww < kSkConsumers; ++ww) mb = fmaxf(mb, mw_s[ww]);
+      for (int ww = 0; ww < kSkConsumers; ++ww)
+        wsc[ww] = (mw_s[ww] == -INFINITY) ? 0.f : ex2f((mw_s[ww] - mb) * inv_eps_log2e);
+      if (threadIdx.x == 0) mpart[blockIdx.x] = mb;
+    }
+    for (int c = threadIdx.x; c < k; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < kSkConsumers; ++ww) t = fmaf(ring[static_cast<size_t>(ww) * kpad + c], wsc[ww], t);
+      upart[static_cast<size_t>(blockIdx.x) * kpad + c] = t;
+    }
+  }
+}
+
+// ring geometry of sk_tma_kernel for a K-column problem
+struct SkRing {
+  int nst, rowf;
+  size_t smem;
+};
+inline SkRing sk_ring(int kpad) {
+  SkRing g;
+  g.rowf = static_cast<int>(round_up(kpad, 32));
+  const size_t rowbytes = static_cast<size_t>(g.rowf) * 4, fixed = static_cast<size_t>(kpad) * 4 + 2 * 16 * 8 + 8 + 128;
+  int nst = static_cast<int>((212 * 1024 - fixed) / rowbytes);
+  if (nst > 16) nst = 16;
+  g.nst = nst;  // >= 7 whenever kpad <= 3072 (the combine area needs kSkConsumers * kpad floats inside the ring)
+  g.smem = static_cast<size_t>(nst) * rowbytes + static_cast<size_t>(kpad) * 4 + (2 * nst + 1) * 8 + 128;
+  return g;
+}
+template <int PHASE>
+int sk_launch_fast(int grid, size_t smem_unused, cudaStream_t s, const float* scores, int64_t b, int k, int64_t ld, float iel,
                    const SkWs& ws, float* codes, int64_t ldc, float inv_b) {
+  (void)smem_unused;
+#ifdef SSVB_SK_ROWREG  // previous fast path (global loads straight into registers), kept for A/B timing
+  const size_t smem = static_cast<size_t>(9) * ws.kpad * 4;
   SSVB_CUDA(cudaFuncSetAttribute(sk_rowreg_kernel<PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   sk_rowreg_kernel<PHASE><<<grid, 256, smem, s>>>(scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart, ws.kpad, codes, ldc,
                                                   ws.smax_part, inv_b);
+#else
+  const SkRing g = sk_ring(ws.kpad);
+  SSVB_CUDA(cudaFuncSetAttribute(sk_tma_kernel<PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem)));
+  sk_tma_kernel<PHASE><<<grid, (kSkConsumers + 1) * 32, g.smem, s>>>(scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart,
+                                                                     ws.kpad, codes, ldc, ws.smax_part, inv_b, g.nst, g.rowf);
+#endif
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
@@ -406,17 +607,17 @@ int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, f
   } else {
     if (fast) {
       SSVB_TRY(sk_launch_fast<0>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
-      sk_alpha0_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, 8), 0, s>>>(ws.upart, ws.smax_part, fgrid, ws.kpad,
+      sk_alpha0_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, kSkSlices), 0, s>>>(ws.upart, ws.smax_part, fgrid, ws.kpad,
                                                                                       kk, iel, ws.alpha, ws.smax);
     } else {
       SSVB_TRY(sk_launch<0>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
-      sk_alpha_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, 8), 0, s>>>(ws.upart, ws.grid, ws.kpad, kk, ws.alpha);
+      sk_alpha_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, kSkSlices), 0, s>>>(ws.upart, ws.grid, ws.kpad, kk, ws.alpha);
     }
     SSVB_LAUNCH_CHECK();
     for (int it = 1; it < n_iters; ++it) {
       if (fast) SSVB_TRY(sk_launch_fast<1>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
       else SSVB_TRY(sk_launch<1>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
-      sk_alpha_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, 8), 0, s>>>(ws.upart, fast ? fgrid : ws.grid, ws.kpad, kk, ws.alpha);
+      sk_alpha_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, kSkSlices), 0, s>>>(ws.upart, fast ? fgrid : ws.grid, ws.kpad, kk, ws.alpha);
       SSVB_LAUNCH_CHECK();
     }
   }
@@ -440,11 +641,12 @@ int sinkhorn_dist_pass(int phase, const float* scores, int64_t b, int64_t b_glob
   if (smem > 200 * 1024) return SSVB_ERR_UNSUPPORTED;
   const int threads = nwarp * 32;
   const bool regacc = (nwarp == 8) && (k <= static_cast<int64_t>(kSkJ) * threads);
+  // (`fast` must come out the same in all three phases: the caller passes the codes buffer every time)
   const bool fast = (k % 4 == 0) && (k <= 128 * kSkNV) && (ld_scores % 4 == 0) && !(reinterpret_cast<uintptr_t>(scores) & 15) &&
-                    (phase != 2 || ((ld_codes % 4 == 0) && !(reinterpret_cast<uintptr_t>(codes) & 15)));
+                    (ld_codes % 4 == 0) && !(reinterpret_cast<uintptr_t>(codes) & 15);
   const size_t smem_fast = static_cast<size_t>(9) * ws.kpad * 4;
   const int fgrid = num_sms();
-  const dim3 ablock(32, 8);
+  const dim3 ablock(32, kSkSlices);
   const unsigned agrid = static_cast<unsigned>(ceil_div(k, 32));
   if (phase != 0) {  // global scaling vector / maximum from the caller
     ws.alpha = const_cast<float*>(alpha);
@@ -452,7 +654,7 @@ int sinkhorn_dist_pass(int phase, const float* scores, int64_t b, int64_t b_glob
   }
   if (phase == 0) {
     if (fast) {
-      SSVB_TRY(sk_launch_fast<0>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, nullptr, 0, inv_b));
+      SSVB_TRY(sk_launch_fast<0>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
       sk_alpha0_kernel<<<agrid, ablock, 0, s>>>(ws.upart, ws.smax_part, fgrid, ws.kpad, kk, iel, u_local, u_local + k, 1);
     } else {
       SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
@@ -465,7 +667,7 @@ int sinkhorn_dist_pass(int phase, const float* scores, int64_t b, int64_t b_glob
     }
     SSVB_LAUNCH_CHECK();
   } else if (phase == 1) {
-    if (fast) SSVB_TRY(sk_launch_fast<1>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, nullptr, 0, inv_b));
+    if (fast) SSVB_TRY(sk_launch_fast<1>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
     else SSVB_TRY(sk_launch<1>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, nullptr, 0, inv_b));
     sk_alpha_kernel<<<agrid, ablock, 0, s>>>(ws.upart, fast ? fgrid : ws.grid, ws.kpad, kk, u_local, 1);
     SSVB_LAUNCH_CHECK();
@@ -488,6 +690,7 @@ size_t sinkhorn_ws_bytes(int64_t k) { return sk_ws(nullptr, k).bytes; }
 }  // namespace ssvb
 
 extern "C" {
+
 
 size_t ssvb_sinkhorn_workspace_bytes(int64_t b, int64_t k) {
   (void)b;
@@ -515,7 +718,7 @@ int ssvb_sinkhorn_dist_pass(int phase, const float* scores, int64_t b_local, int
     return SSVB_ERR_INVALID;
   if (phase != 0 && (!alpha || !smax)) return SSVB_ERR_INVALID;
   if (phase != 2 && !u_local) return SSVB_ERR_INVALID;
-  if (phase == 2 && (!codes || ld_codes < k)) return SSVB_ERR_INVALID;
+  if (!codes || ld_codes < k) return SSVB_ERR_INVALID;  // same buffer in every phase (it selects the kernel family)
   if (workspace_bytes < sk_ws(nullptr, k).bytes) return SSVB_ERR_WORKSPACE;
   return sinkhorn_dist_pass(phase, scores, b_local, b_global, k, ld_scores, eps, alpha, smax, u_local, codes, ld_codes,
                             workspace, static_cast<cudaStream_t>(stream));

@@ -446,13 +446,13 @@ def _dist_sinkhorn(stages, scores_views, codes_views, k, eps, n_iters, group, in
             stages.sk_alpha(u_all[0, v], world, nv * (k + 1), k, phase0, eps, alpha[v], smax[v])
 
     for v in range(nv):
-        stages.sk_pass(0, scores_views[v], b_global, k, eps, None, None, u_all[rank, v], None)
+        stages.sk_pass(0, scores_views[v], b_global, k, eps, None, None, u_all[rank, v], codes_views[v])
     exchange(True)
     if n_iters <= 0:
         alpha.fill_(1.0)  # no iterations: codes = E / rowsum(E)
     for _ in range(1, int(n_iters)):
         for v in range(nv):
-            stages.sk_pass(1, scores_views[v], b_global, k, eps, alpha[v], smax[v], u_all[rank, v], None)
+            stages.sk_pass(1, scores_views[v], b_global, k, eps, alpha[v], smax[v], u_all[rank, v], codes_views[v])
         exchange(False)
     for v in range(nv):
         stages.sk_pass(2, scores_views[v], b_global, k, eps, alpha[v], smax[v], None, codes_views[v])

@@ -85,7 +85,7 @@ def test_dist_sinkhorn_emulated_ranks(S, b, k, iters, world):
             C.check(L.ssvb_sinkhorn_dist_pass(phase, C.ptr(sl), bl, b, k, s.stride(0), 0.05,
                                               C.ptr(alpha) if phase else None, C.ptr(smax) if phase else None,
                                               C.ptr(u_all[r]) if phase < 2 else None,
-                                              C.ptr(codes[r * bl:(r + 1) * bl]) if phase == 2 else None, codes.stride(0),
+                                              C.ptr(codes[r * bl:(r + 1) * bl]), codes.stride(0),
                                               C.ptr(ws), nbytes, st), "pass")
 
     run_pass(0)
