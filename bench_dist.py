@@ -105,9 +105,18 @@ def main():
     a, b = zi.to(dev).requires_grad_(True), zj.to(dev).requires_grad_(True)
     fn_b = DistributedBarlowLoss(False, 0.005)
     ms = timed(fwd_bwd(lambda: fn_b(a, b), a, b), max(5, args.reps // 2))
-    emit("DistributedBarlowLoss", f"cfg3 global 2048x8192 ({nl} rows/rank), C all-reduced", ms, n, flops=6 * n * d * d,
-         note="reduce-scatter fp32 C (256 MiB) + all-gather bf16 dC (128 MiB) per step")
-    del a, b, fn_b
+    emit("DistributedBarlowLoss[allreduce]", f"cfg3 global 2048x8192 ({nl} rows/rank), C all-reduced", ms, n,
+         flops=6 * n * d * d, note="reduce-scatter fp32 C (256 MiB) + all-gather bf16 dC (128 MiB) per step")
+    del fn_b
+    torch.cuda.empty_cache()
+    if d % (8 * world) == 0:
+        fn_c = DistributedBarlowLoss(False, 0.005, mode="colshard")
+        ms = timed(fwd_bwd(lambda: fn_c(a, b), a, b), max(5, args.reps // 2))
+        emit("DistributedBarlowLoss[colshard]", f"cfg3 global 2048x8192 ({nl} rows/rank), column slab of C and C^T per rank",
+             ms, n, flops=6 * n * d * d,
+             note="all-gather bf16 standardised rows (64 MiB), all-to-all of the gradient slabs; C never crosses NVLink")
+        del fn_c
+    del a, b
     torch.cuda.empty_cache()
 
     # ---- Sinkhorn cfg4: global 4096 x 3000

@@ -250,6 +250,32 @@ size_t ssvb_sinkhorn_workspace_bytes(int64_t b, int64_t k);
 int ssvb_sinkhorn(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters,
                   float* codes, int64_t ld_codes, void* workspace, size_t workspace_bytes, void* stream);
 
+/* a4/e (alternative)  Column-sharded distributed Barlow — what SURVEY.md §8e asks to measure next to the all-reduce:
+ *     the D x D matrix never crosses NVLink.  After the same stats exchange, every rank standardises its rows into its
+ *     slot of two gathered bf16 matrices Xi~, Xj~ [n_global x d] (caller ALL-GATHERS them: 2 * n_global * d * 2 bytes),
+ *     then owns the column slab [col0, col0+ncols) of BOTH C = Xi~^T Xj~ / n and C^T:
+ *       cs_fwd(xa, xb):  slab of xa^T xb / n with the fused loss / dC epilogue -> dc_slab bf16 [d x ncols] and (optional)
+ *                        the slab's loss terms; called as (Xi~, Xj~) [loss counted here] and (Xj~, Xi~) [C^T, no loss];
+ *       cs_bwd(xa, xb, dc_slab): dT = xa dc_slab / n for ALL n_global rows, then the standardisation backward of the
+ *                        slab's columns (their reductions over the batch are local now) -> dxb_slab fp32
+ *                        [n_global x ncols], complete; called as (Xi~, Xj~, dC slab, view 1) and (Xj~, Xi~, dC^T slab, 0);
+ *       caller ALL-TO-ALLs the row blocks of the slabs to their owners (n_local x ncols floats per pair);
+ *       cs_finish: reassemble [world][n_local x ncols] into the local gradient rows (+ row-normalise backward).
+ *     `saved` is the ssvb_barlow_dist_* blob of this rank (global mean / rstd, local row norms). */
+int ssvb_barlow_dist_standardize(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                                 int64_t ld_zj, int normalize, const float* stats_all, int64_t world,
+                                 void* xt_i_slot /* bf16 [n_local x d] */, void* xt_j_slot, void* saved, void* stream);
+size_t ssvb_barlow_cs_workspace_bytes(int64_t n_global, int64_t d, int64_t ncols);
+int ssvb_barlow_cs_fwd(const void* xa_all, const void* xb_all, int64_t n_global, int64_t d, int64_t col0,
+                       int64_t ncols, float lambda, void* dc_slab, float* loss_partial, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int ssvb_barlow_cs_bwd(const void* xa_all, const void* xb_all, const void* dc_slab, int64_t n_global, int64_t d,
+                       int64_t col0, int64_t ncols, const void* saved, int64_t n_local, int view_b,
+                       const float* grad_out, float* dxb_slab, void* workspace, size_t workspace_bytes, void* stream);
+int ssvb_barlow_cs_finish(const float* recv /* [world][n_local x ncols] */, int64_t world, int64_t n_local,
+                          int64_t ncols, const float* x, int64_t ld_x, int normalize, const void* saved, int view,
+                          float* dx, int64_t ld_dx, void* stream);
+
 /* a5/e  Distributed Sinkhorn: the B sample rows are sharded (b_local per rank, b_global in total),
  *     prototypes / columns replicated.  The only cross-rank quantity is the K-vector of prototype marginals:
  *       pass(phase 0): u_local[0..k) = sum_b E_bk relative to this rank's maximum, u_local[k] = that maximum;

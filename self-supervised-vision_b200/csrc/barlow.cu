@@ -336,6 +336,83 @@ __global__ void col_scale_sums_kernel(const float* __restrict__ colsum, int d, f
 }
 
 
+// ---- column-sharded variant (all-gather of the standardised rows instead of an all-reduce of C) -------------------
+// column sums over ALL n rows of a [n x ncols] fp32 slab dT and of dT * x~ (x~ = bf16 gathered rows, columns
+// col0.. of a [n x ldx] matrix); same (32 columns, 8 row phases) x row-stripe layout as col_partials_kernel.
+__global__ void slab_col_partials_kernel(const float* __restrict__ dt, int64_t lddt, const __nv_bfloat16* __restrict__ xt,
+                                         int64_t ldx, int64_t n, int ncols, float* __restrict__ part) {
+  const int col = blockIdx.x * kColsPerBlock + threadIdx.x;
+  const int stripe = blockIdx.y;
+  const int64_t rows_per = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = stripe * rows_per, r1 = min(n, r0 + rows_per);
+  float s1 = 0.f, s2 = 0.f;
+  if (col < ncols) {
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      const float g = dt[r * lddt + col];
+      s1 += g;
+      s2 = fmaf(g, __bfloat162float(xt[r * ldx + col]), s2);
+    }
+  }
+  __shared__ float sh1[8][kColsPerBlock + 1], sh2[8][kColsPerBlock + 1];
+  sh1[threadIdx.y][threadIdx.x] = s1;
+  sh2[threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < ncols) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += sh1[i][threadIdx.x]; b += sh2[i][threadIdx.x]; }
+    part[(static_cast<int64_t>(stripe) * 2 + 0) * ncols + col] = a;
+    part[(static_cast<int64_t>(stripe) * 2 + 1) * ncols + col] = b;
+  }
+}
+// in place: dt[r, c] = (dt - m1_c - x~ m2_c) * rstd_c * grad_out, m1 = sum1 / n, m2 = sum2 / (n - 1)
+__global__ void slab_finish_kernel(float* __restrict__ dt, int64_t lddt, const __nv_bfloat16* __restrict__ xt, int64_t ldx,
+                                   const float* __restrict__ rstd, const float* __restrict__ part, int nsplit, int64_t n,
+                                   int ncols, const float* __restrict__ grad_out) {
+  const int col = blockIdx.x * kColsPerBlock + threadIdx.x;
+  if (col >= ncols) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < nsplit; ++i) {
+    s1 += part[(static_cast<int64_t>(i) * 2 + 0) * ncols + col];
+    s2 += part[(static_cast<int64_t>(i) * 2 + 1) * ncols + col];
+  }
+  const float m1 = s1 / static_cast<float>(n), m2 = s2 / static_cast<float>(n - 1);
+  const float sc = rstd[col] * __ldg(grad_out);
+  const int64_t rows_per = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
+  for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    const float g = dt[r * lddt + col];
+    dt[r * lddt + col] = (g - m1 - __bfloat162float(xt[r * ldx + col]) * m2) * sc;
+  }
+}
+// dx[n, q * ncols + c] = recv[q][n][c]  (+ row-normalise backward with x, inv_row); one block per local row
+__global__ void slab_gather_rows_kernel(const float* __restrict__ recv, int world, int64_t n_local, int ncols,
+                                        const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row,
+                                        float* __restrict__ dx, int64_t lddx) {
+  const int64_t r = blockIdx.x;
+  const int d = world * ncols;
+  __shared__ float red[32];
+  float dot = 0.f;
+  const float sc = inv_row ? inv_row[r] : 1.f;
+  if (inv_row) {
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      const int q = c / ncols, cc = c - q * ncols;
+      dot = fmaf(recv[(static_cast<int64_t>(q) * n_local + r) * ncols + cc], x[r * ldx + c] * sc, dot);
+    }
+    dot = warp_sum(dot);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    float t = (threadIdx.x & 31) < (blockDim.x >> 5) ? red[threadIdx.x & 31] : 0.f;
+    dot = warp_sum(t);
+  }
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const int q = c / ncols, cc = c - q * ncols;
+    float g = recv[(static_cast<int64_t>(q) * n_local + r) * ncols + cc];
+    if (inv_row) g = (g - dot * x[r * ldx + c] * sc) * sc;
+    dx[r * lddx + c] = g;
+  }
+}
+
 int check_rows(const void* p, int64_t ld) {
   if (!p) return SSVB_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(p) & 15) || (ld & 3)) return SSVB_ERR_ALIGNMENT;
@@ -644,6 +721,135 @@ int ssvb_barlow_dist_bwd_finish(const float* zi, const float* zj, int64_t n_loca
   barlow_finish_kernel<<<static_cast<unsigned>(n_local), 256, 0, s>>>(
       zj, ld_zj, normalize ? sv.inv_j : nullptr, sv.mean_j, sv.rstd_j, ws.dtj, d, ws.colred + 2 * d, ws.colred + 3 * d, di,
       grad_out, dzj, ld_dzj);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Column-sharded distributed Barlow (the low-traffic alternative SURVEY.md §8e asks to measure): all-gather the
+// standardised bf16 rows (N x D per view) instead of all-reducing the D x D fp32 matrix; rank r owns the column slab
+// [col0, col0 + ncols) of C AND of C^T, so both gradient slabs come out complete and only an all-to-all of N*D/G
+// floats per view remains.  See include/ssv_b200.h.
+// ------------------------------------------------------------------------------------------------------------
+int ssvb_barlow_dist_standardize(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                                 int64_t ld_zj, int normalize, const float* stats_all, int64_t world, void* xt_i_slot,
+                                 void* xt_j_slot, void* saved, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (n_local < 1 || d <= 0 || world < 1 || n_local * world < 2) return SSVB_ERR_INVALID;
+  if (d % 8) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  if (!stats_all || !saved || !xt_i_slot || !xt_j_slot) return SSVB_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(xt_i_slot) | reinterpret_cast<uintptr_t>(xt_j_slot)) & 15) return SSVB_ERR_ALIGNMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BarlowDistSaved sv = barlow_dist_saved(saved, n_local, d);
+  const int di = static_cast<int>(d);
+  const unsigned cgrid = static_cast<unsigned>(ceil_div(d, 256));
+  col_combine_moments_kernel<<<cgrid, 256, 0, s>>>(stats_all, static_cast<int>(world), n_local, di, 0, sv.mean_i, sv.rstd_i);
+  SSVB_LAUNCH_CHECK();
+  col_combine_moments_kernel<<<cgrid, 256, 0, s>>>(stats_all, static_cast<int>(world), n_local, di, 1, sv.mean_j, sv.rstd_j);
+  SSVB_LAUNCH_CHECK();
+  const int64_t total = n_local * (d / 4);
+  int64_t g = ceil_div(total, 256 * 4);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  standardize_kernel<<<static_cast<unsigned>(g), 256, 0, s>>>(zi, ld_zi, normalize ? sv.inv_i : nullptr, sv.mean_i, sv.rstd_i,
+                                                              n_local, static_cast<int>(d / 4),
+                                                              static_cast<__nv_bfloat16*>(xt_i_slot), d);
+  SSVB_LAUNCH_CHECK();
+  standardize_kernel<<<static_cast<unsigned>(g), 256, 0, s>>>(zj, ld_zj, normalize ? sv.inv_j : nullptr, sv.mean_j, sv.rstd_j,
+                                                              n_local, static_cast<int>(d / 4),
+                                                              static_cast<__nv_bfloat16*>(xt_j_slot), d);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+size_t ssvb_barlow_cs_workspace_bytes(int64_t n_global, int64_t d, int64_t ncols) {
+  (void)n_global; (void)d;
+  if (ncols <= 0) return 0;
+  Carver c(nullptr);
+  c.take<float>(kMaxGemmCtas);
+  c.take<float>(kRowSplit * 2 * ncols);
+  return c.used();
+}
+
+int ssvb_barlow_cs_fwd(const void* xa_all, const void* xb_all, int64_t n_global, int64_t d, int64_t col0, int64_t ncols,
+                       float lambda, void* dc_slab, float* loss_partial, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (!xa_all || !xb_all || !dc_slab || !workspace || n_global < 2 || d <= 0 || col0 < 0 || ncols <= 0 || col0 + ncols > d)
+    return SSVB_ERR_INVALID;
+  if ((d % 8) || (ncols % 8) || (col0 % 8)) return SSVB_ERR_ALIGNMENT;
+  if (workspace_bytes < ssvb_barlow_cs_workspace_bytes(n_global, d, ncols)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Carver cv(workspace);
+  float* lp = cv.take<float>(kMaxGemmCtas);
+  // C[:, col0 .. col0+ncols) = Xa~^T Xb~[:, slab] / n : both operands MN-major in place, contraction over ALL n rows
+  GemmParams p{};
+  p.M = static_cast<int>(d);
+  p.N = static_cast<int>(ncols);
+  p.K = static_cast<int>(n_global);
+  p.alpha = 1.f / static_cast<float>(n_global);
+  p.lambda = lambda;
+  p.dC = static_cast<__nv_bfloat16*>(dc_slab);
+  p.ld_dc = ncols;
+  p.loss_partials = lp;
+  p.diag_off = static_cast<int>(col0);
+  SSVB_CUDA(cudaMemsetAsync(lp, 0, kMaxGemmCtas * sizeof(float), s));
+  SSVB_TRY(launch_gemm({xa_all, d, true}, {static_cast<const __nv_bfloat16*>(xb_all) + col0, d, true}, p, 256, EPI_BARLOW,
+                       kMaxGemmCtas, s));
+  if (loss_partial) {
+    sum_partials_kernel<<<1, 256, 0, s>>>(lp, kMaxGemmCtas, 1.f, loss_partial);
+    SSVB_LAUNCH_CHECK();
+  }
+  return SSVB_OK;
+}
+
+int ssvb_barlow_cs_bwd(const void* xa_all, const void* xb_all, const void* dc_slab, int64_t n_global, int64_t d,
+                       int64_t col0, int64_t ncols, const void* saved, int64_t n_local, int view_b, const float* grad_out,
+                       float* dxb_slab, void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (!xa_all || !xb_all || !dc_slab || !saved || !grad_out || !dxb_slab || !workspace || n_global < 2 || d <= 0 ||
+      col0 < 0 || ncols <= 0 || col0 + ncols > d || n_local < 1 || (view_b != 0 && view_b != 1))
+    return SSVB_ERR_INVALID;
+  if ((d % 8) || (ncols % 8) || (col0 % 8)) return SSVB_ERR_ALIGNMENT;
+  if (workspace_bytes < ssvb_barlow_cs_workspace_bytes(n_global, d, ncols)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BarlowDistSaved sv = barlow_dist_saved(const_cast<void*>(saved), n_local, d);
+  Carver cv(workspace);
+  cv.take<float>(kMaxGemmCtas);
+  float* part = cv.take<float>(kRowSplit * 2 * ncols);
+  // dT[n, c] = sum_k Xa~[n, k] dC[k, c] / n   (A K-major; B = the slab [d x ncols] consumed MN-major)
+  GemmParams p{};
+  p.M = static_cast<int>(n_global);
+  p.N = static_cast<int>(ncols);
+  p.K = static_cast<int>(d);
+  p.alpha = 1.f / static_cast<float>(n_global);
+  p.out = dxb_slab;
+  p.ldc = ncols;
+  SSVB_TRY(launch_gemm({xa_all, d, false}, {dc_slab, ncols, true}, p, 256, EPI_STORE_F32, 0, s));
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(xb_all) + col0;
+  dim3 grid(static_cast<unsigned>(ceil_div(ncols, kColsPerBlock)), kRowSplit), block(32, 8);
+  slab_col_partials_kernel<<<grid, block, 0, s>>>(dxb_slab, ncols, xb, d, n_global, static_cast<int>(ncols), part);
+  SSVB_LAUNCH_CHECK();
+  slab_finish_kernel<<<grid, block, 0, s>>>(dxb_slab, ncols, xb, d, (view_b ? sv.rstd_j : sv.rstd_i) + col0, part, kRowSplit,
+                                            n_global, static_cast<int>(ncols), grad_out);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_barlow_cs_finish(const float* recv, int64_t world, int64_t n_local, int64_t ncols, const float* x, int64_t ld_x,
+                          int normalize, const void* saved, int view, float* dx, int64_t ld_dx, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (!recv || !x || !saved || !dx || world < 1 || n_local < 1 || ncols <= 0 || (view != 0 && view != 1))
+    return SSVB_ERR_INVALID;
+  SSVB_TRY(check_rows(x, ld_x));
+  SSVB_TRY(check_rows(dx, ld_dx));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BarlowDistSaved sv = barlow_dist_saved(const_cast<void*>(saved), n_local, world * ncols);
+  slab_gather_rows_kernel<<<static_cast<unsigned>(n_local), 256, 0, s>>>(
+      recv, static_cast<int>(world), n_local, static_cast<int>(ncols), x, ld_x,
+      normalize ? (view ? sv.inv_j : sv.inv_i) : nullptr, dx, ld_dx);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }

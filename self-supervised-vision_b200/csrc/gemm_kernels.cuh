@@ -28,6 +28,7 @@ struct GemmParams {
   __nv_bfloat16* dC;
   int64_t ld_dc;
   float* loss_partials;  // [gridDim.x]
+  int diag_off;          // the output is a column slab of the full matrix: global column = n + diag_off
 };
 
 template <int BN>
@@ -190,7 +191,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int e = 0; e < 2; ++e) {
               const int col = col0 + 2 * i + e;
               const float c = __uint_as_float(v[2 * i + e]) * p.alpha;
-              const bool diag = (col == row);
+              const bool diag = (col + p.diag_off == row);
               const float r = diag ? (c - 1.f) : c;
               const float w = diag ? 1.f : p.lambda;
               if (row_ok && col < p.N) loss_acc = fmaf(w * r, r, loss_acc);

@@ -105,6 +105,7 @@ class _PeerTransport:
             hz.barrier()
             self.bufs.append((z, hz, st, hs))
         self.parity = 0
+        self.gen = [0, 0]  # pushes seen by each buffer pair (backward checks its pair has not been re-used)
 
     @classmethod
     def get(cls, group, world, mpad, dpad, n_local, dev):
@@ -116,6 +117,7 @@ class _PeerTransport:
 
     def next(self):
         self.parity ^= 1
+        self.gen[self.parity] += 1
         return self.bufs[self.parity]
 
 
@@ -134,7 +136,7 @@ def _gather_slots(full, slot, group, inplace):
 
 class _NtxentDistFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, zi, zj, normalize, temperature, group, stages, transport):
+    def forward(ctx, zi, zj, normalize, temperature, group, stages, transport, retain=True):
         global _P2P_BROKEN
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -164,13 +166,20 @@ class _NtxentDistFn(torch.autograd.Function):
             loss = torch.empty((), dtype=torch.float32, device=dev)
             stages.prep_push(xi, xj, norm, world, rank, hz.buffer_ptrs_dev, inv_local, pos_local)
             hz.barrier()
-            zhat_all = zbuf.view(mpad, dpad).clone()
+            zhat_all = zbuf.view(mpad, dpad)
+            stat_all = sbuf.view(world, 2, 2 * n)
+            if retain:  # private copies: backward stays valid however many forwards follow
+                zhat_all = zhat_all.clone()
             stages.rows_fwd_push(zhat_all, world, rank, n, d, norm, float(temperature), pos_local, hs.buffer_ptrs_dev, loss)
             hs.barrier()
-            stat_all = sbuf.view(world, 2, 2 * n).clone()
+            if retain:
+                stat_all = stat_all.clone()
             stages.dist_loss(stat_all, world, n, loss)
             ctx.save_for_backward(xi, xj, zhat_all, stat_all, inv_local)
             ctx.cfg = (norm, float(temperature), world, rank, stages, zi.dtype, zj.dtype)
+            # without copies backward reads the transport buffers in place; they are double-buffered, so they stay
+            # intact until the SECOND forward after this one (checked in backward: fails loudly, never silently)
+            ctx.peer_ticket = None if retain else (peer, peer.parity, peer.gen[peer.parity])
             return loss
         zhat_all = torch.empty(mpad, dpad, dtype=torch.bfloat16, device=dev)
         # per rank: [lse2 (2L) | per-row loss term (2L)] -> one all-gather serves the backward AND the global loss
@@ -192,26 +201,38 @@ class _NtxentDistFn(torch.autograd.Function):
             loss = loss_sum / m
         ctx.save_for_backward(xi, xj, zhat_all, stat_all, inv_local)
         ctx.cfg = (norm, float(temperature), world, rank, stages, zi.dtype, zj.dtype)
+        ctx.peer_ticket = None
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
         xi, xj, zhat_all, stat_all, inv_local = ctx.saved_tensors
         norm, temperature, world, rank, stages, dti, dtj = ctx.cfg
+        if ctx.peer_ticket is not None:
+            peer, parity, gen = ctx.peer_ticket
+            if peer.gen[parity] != gen:
+                raise RuntimeError("DistributedSimclrLoss(retain_gathered=False): two more forwards ran before this "
+                                   "backward and re-used its gather buffers; construct the loss with "
+                                   "retain_gathered=True for this call pattern")
         go = C.f32_scalar(grad_out)
         dzi, dzj = torch.empty_like(xi), torch.empty_like(xj)
         stages.rows_bwd(xi, xj, norm, temperature, world, rank, zhat_all, stat_all, inv_local, go, dzi, dzj)
-        return dzi.to(dti), dzj.to(dtj), None, None, None, None, None
+        return dzi.to(dti), dzj.to(dtj), None, None, None, None, None, None
 
 
 class DistributedSimclrLoss(nn.Module):
     """SimclrLoss over the global batch of a process group: same ctor kwargs as the reference's
     SimclrLoss (utils/losses.py:10-13) plus an optional process group."""
 
-    def __init__(self, normalize=False, temperature=1.0, group=None, stages=None, transport="auto"):
+    def __init__(self, normalize=False, temperature=1.0, group=None, stages=None, transport="auto",
+                 retain_gathered=False):
         """transport: "p2p" = kernels store into all peers' buffers over NVLink (torch symmetric memory) + barriers;
-        "nccl" = two all-gathers; "auto" = p2p when symmetric memory is available, else nccl."""
+        "nccl" = two all-gathers; "auto" = p2p when symmetric memory is available, else nccl.
+        retain_gathered (p2p only): False = backward reads the double-buffered transport buffers in place (valid for the
+        usual forward -> backward -> forward loop and for one extra forward in between; anything else raises in
+        backward); True = forward copies the gathered rows / statistics into private tensors (16 MiB + 256 KiB at cfg5)."""
         super().__init__()
+        self.retain_gathered = retain_gathered
         self.normalize = normalize
         self.temperature = temperature
         self.group = group
@@ -219,7 +240,8 @@ class DistributedSimclrLoss(nn.Module):
         self.transport = transport
 
     def forward(self, zi, zj):
-        return _NtxentDistFn.apply(zi, zj, self.normalize, self.temperature, self.group, self.stages, self.transport)
+        return _NtxentDistFn.apply(zi, zj, self.normalize, self.temperature, self.group, self.stages, self.transport,
+                                   self.retain_gathered)
 
 
 # ======================================================================================================= helpers
@@ -295,6 +317,116 @@ class BarlowCudaStages:
                                                     C.stream_ptr(zi.device)), "ssvb_barlow_dist_bwd_finish")
 
 
+    # ---- column-sharded variant (all-gather of the standardised rows; the D x D matrix never crosses NVLink)
+    def standardize(self, zi, zj, normalize, stats_all, world, xi_slot, xj_slot, saved):
+        n, d = zi.shape
+        C.check(C.lib().ssvb_barlow_dist_standardize(C.ptr(zi), C.ptr(zj), n, d, zi.stride(0), zj.stride(0), normalize,
+                                                     C.ptr(stats_all), world, C.ptr(xi_slot), C.ptr(xj_slot),
+                                                     C.ptr(saved), C.stream_ptr(zi.device)), "ssvb_barlow_dist_standardize")
+
+    def _cs_ws(self, ng, d, ncols, dev):
+        nbytes = C.cached_size("ssvb_barlow_cs_workspace_bytes", ng, d, ncols)
+        return C.workspace("barlow_cs", nbytes, dev), nbytes
+
+    def cs_fwd(self, xa_all, xb_all, col0, ncols, lmbda, dc_slab, loss_partial):
+        ng, d = xa_all.shape
+        ws, nb = self._cs_ws(ng, d, ncols, xa_all.device)
+        C.check(C.lib().ssvb_barlow_cs_fwd(C.ptr(xa_all), C.ptr(xb_all), ng, d, col0, ncols, lmbda, C.ptr(dc_slab),
+                                           C.ptr(loss_partial), C.ptr(ws), nb, C.stream_ptr(xa_all.device)),
+                "ssvb_barlow_cs_fwd")
+
+    def cs_bwd(self, xa_all, xb_all, dc_slab, col0, ncols, saved, n_local, view_b, grad_out, dxb_slab):
+        ng, d = xa_all.shape
+        ws, nb = self._cs_ws(ng, d, ncols, xa_all.device)
+        C.check(C.lib().ssvb_barlow_cs_bwd(C.ptr(xa_all), C.ptr(xb_all), C.ptr(dc_slab), ng, d, col0, ncols, C.ptr(saved),
+                                           n_local, view_b, C.ptr(grad_out), C.ptr(dxb_slab), C.ptr(ws), nb,
+                                           C.stream_ptr(xa_all.device)), "ssvb_barlow_cs_bwd")
+
+    def cs_finish(self, recv, world, n_local, ncols, x, normalize, saved, view, dx):
+        C.check(C.lib().ssvb_barlow_cs_finish(C.ptr(recv), world, n_local, ncols, C.ptr(x), x.stride(0), normalize,
+                                              C.ptr(saved), view, C.ptr(dx), dx.stride(0), C.stream_ptr(x.device)),
+                "ssvb_barlow_cs_finish")
+
+
+def _all_to_all_blocks(send, group, nccl):
+    """send: [world][block...] -> recv[q] = the block rank q addressed to this rank."""
+    recv = torch.empty_like(send)
+    if nccl:
+        dist.all_to_all_single(recv, send, group=group)
+    else:  # gloo (tests): emulate with an all-gather
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        parts = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(parts, send.contiguous(), group=group)
+        for q in range(world):
+            recv[q].copy_(parts[q][rank])
+    return recv
+
+
+class _BarlowColShardFn(torch.autograd.Function):
+    """Column-sharded global-batch Barlow Twins (see DistributedBarlowLoss, mode="colshard")."""
+
+    @staticmethod
+    def forward(ctx, zi, zj, normalize, lmbda, group, stages):
+        world, rank = _world_rank(group)
+        cuda = isinstance(stages, BarlowCudaStages)
+        if cuda:
+            C.require_cuda(zi, zj)
+            xi, xj = C.as_f32_rows(zi), C.as_f32_rows(zj)
+        else:
+            xi, xj = zi.detach().float().contiguous(), zj.detach().float().contiguous()
+        if xi.shape != xj.shape or xi.dim() != 2:
+            raise ValueError("BarlowLoss expects two [N, D] tensors of the same shape")
+        n, d = xi.shape
+        if d % world:
+            raise ValueError("colshard mode needs D divisible by the world size")
+        ng, ncols = n * world, d // world
+        col0 = rank * ncols
+        dev = xi.device
+        norm = int(bool(normalize))
+        saved = stages.alloc_saved(n, d, dev)
+        stats_all = torch.empty(world, 2, 2, d, dtype=torch.float32, device=dev)
+        stages.stats(xi, xj, norm, stats_all[rank], saved)
+        if world > 1:
+            _gather_slots(stats_all.view(world, 4 * d), stats_all[rank].view(1, 4 * d), group, inplace=cuda)
+        # standardised rows straight into this rank's slot of the gathered matrices, then ONE all-gather per view
+        xt = torch.empty(2, ng, d, dtype=torch.bfloat16, device=dev)
+        my = slice(rank * n, (rank + 1) * n)
+        stages.standardize(xi, xj, norm, stats_all, world, xt[0, my], xt[1, my], saved)
+        if world > 1:
+            _gather_slots(xt[0], xt[0, my], group, inplace=cuda)
+            _gather_slots(xt[1], xt[1, my], group, inplace=cuda)
+        # column slab of C (loss + dC) and of C^T (dC^T): both gradient slabs will be complete, no reduction of C at all
+        dc = torch.empty(2, d, ncols, dtype=torch.bfloat16, device=dev)
+        parts = torch.zeros(world, dtype=torch.float32, device=dev)
+        stages.cs_fwd(xt[0], xt[1], col0, ncols, float(lmbda), dc[0], parts[rank:rank + 1])
+        stages.cs_fwd(xt[1], xt[0], col0, ncols, float(lmbda), dc[1], None)
+        if world > 1:
+            _gather_slots(parts.view(world, 1), parts[rank:rank + 1].view(1, 1), group, inplace=cuda)
+        loss = parts.sum()  # same values, same order on every rank
+        ctx.save_for_backward(xi, xj, saved, xt, dc)
+        ctx.cfg = (norm, world, rank, group, stages, cuda, zi.dtype, zj.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xi, xj, saved, xt, dc = ctx.saved_tensors
+        norm, world, rank, group, stages, cuda, dti, dtj = ctx.cfg
+        n, d = xi.shape
+        ng, ncols = n * world, d // world
+        col0 = rank * ncols
+        go = C.f32_scalar(grad_out)
+        slabs = torch.empty(2, ng, ncols, dtype=torch.float32, device=xi.device)
+        # d Xj~[:, slab] = Xi~ dC[:, slab];  d Xi~[:, slab] = Xj~ dC^T[:, slab]; standardisation backward is column-local
+        stages.cs_bwd(xt[0], xt[1], dc[0], col0, ncols, saved, n, 1, go, slabs[1])
+        stages.cs_bwd(xt[1], xt[0], dc[1], col0, ncols, saved, n, 0, go, slabs[0])
+        dzi, dzj = torch.empty_like(xi), torch.empty_like(xj)
+        for view, (x, out) in enumerate(((xi, dzi), (xj, dzj))):
+            send = slabs[view].view(world, n, ncols)  # row block q of the slab belongs to rank q
+            recv = _all_to_all_blocks(send, group, cuda) if world > 1 else send
+            stages.cs_finish(recv, world, n, ncols, x, norm, saved, view, out)
+        return dzi.to(dti), dzj.to(dtj), None, None, None, None
+
+
 class _BarlowDistFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, zi, zj, normalize, lmbda, group, stages):
@@ -360,15 +492,23 @@ class DistributedBarlowLoss(nn.Module):
     reduce-scatter(fp32) -> fused loss/dC epilogue on the slab -> all-gather(bf16), the two column reductions of the
     standardisation backward all-reduced.  Every rank gets the gradient rows of its own inputs (no 1/world rescale)."""
 
-    def __init__(self, normalize=True, off_diagonal_weight=0.005, group=None, stages=None):
+    def __init__(self, normalize=True, off_diagonal_weight=0.005, group=None, stages=None, mode="allreduce"):
+        """mode "allreduce": the all-reduce of the cross-correlation described above (BASELINE.json's wording);
+        mode "colshard": all-gather the standardised bf16 rows instead and give every rank a column slab of C and C^T
+        (~4x less NVLink traffic at D = 8192, no all-reduce of C, gradients re-sharded by one small all-to-all);
+        needs D % (8 * world) == 0."""
         super().__init__()
+        if mode not in ("allreduce", "colshard"):
+            raise ValueError("mode must be 'allreduce' or 'colshard'")
         self.normalize = normalize
         self.lmbda = off_diagonal_weight
         self.group = group
         self.stages = stages if stages is not None else BarlowCudaStages()
+        self.mode = mode
 
     def forward(self, z_i, z_j):
-        return _BarlowDistFn.apply(z_i, z_j, self.normalize, self.lmbda, self.group, self.stages)
+        fn = _BarlowColShardFn if self.mode == "colshard" else _BarlowDistFn
+        return fn.apply(z_i, z_j, self.normalize, self.lmbda, self.group, self.stages)
 
 
 # ======================================================================================================= SwAV / Sinkhorn

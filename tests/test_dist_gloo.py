@@ -184,7 +184,51 @@ class EmulatedBarlowStages:
             out.copy_(g.float())
 
 
-def _barlow_worker(rank, world, port, n_local, d, normalize, lmbda, out):
+    # ---- column-sharded variant
+    def standardize(self, zi, zj, normalize, stats_all, world, xi_slot, xj_slot, saved):
+        n, d = zi.shape
+        v = self._views(saved, n, d)
+        ng = n * world
+        for k, (z, slot) in enumerate(((zi, xi_slot), (zj, xj_slot))):
+            mu_r, m2_r = stats_all[:, k, 0].double(), stats_all[:, k, 1].double()
+            mu = mu_r.mean(0)
+            m2 = m2_r.sum(0) + n * ((mu_r - mu) ** 2).sum(0)
+            rstd = 1.0 / torch.sqrt(m2 / (ng - 1))
+            v[2 + 2 * k].copy_(mu)
+            v[3 + 2 * k].copy_(rstd)
+            slot.copy_((((z.double() * v[6 + k][:, None]) - mu) * rstd).to(slot.dtype))
+
+    def cs_fwd(self, xa_all, xb_all, col0, ncols, lmbda, dc_slab, loss_partial):
+        ng, d = xa_all.shape
+        c = xa_all.double().t() @ xb_all.double()[:, col0:col0 + ncols] / ng
+        eye = torch.zeros(d, ncols, dtype=torch.bool)
+        eye[col0 + torch.arange(ncols), torch.arange(ncols)] = True
+        t = torch.where(eye, c - 1.0, c)
+        w = torch.where(eye, torch.ones_like(c), torch.full_like(c, lmbda))
+        dc_slab.copy_((2.0 * w * t).to(dc_slab.dtype))
+        if loss_partial is not None:
+            loss_partial.copy_((w * t * t).sum().float().view(1))
+
+    def cs_bwd(self, xa_all, xb_all, dc_slab, col0, ncols, saved, n_local, view_b, grad_out, dxb_slab):
+        ng, d = xa_all.shape
+        v = self._views(saved, n_local, d)
+        dt = xa_all.double() @ dc_slab.double() / ng
+        xb = xb_all.double()[:, col0:col0 + ncols]
+        m1 = dt.mean(0)
+        m2 = (dt * xb).sum(0) / (ng - 1)
+        dxb_slab.copy_(((dt - m1 - xb * m2) * v[3 + 2 * view_b][col0:col0 + ncols] * grad_out.double()).float())
+
+    def cs_finish(self, recv, world, n_local, ncols, x, normalize, saved, view, dx):
+        d = world * ncols
+        v = self._views(saved, n_local, d)
+        g = recv.double().permute(1, 0, 2).reshape(n_local, d)
+        if normalize:
+            xh = x.double() * v[6 + view][:, None]
+            g = (g - (g * xh).sum(1, keepdim=True) * xh) * v[6 + view][:, None]
+        dx.copy_(g.float())
+
+
+def _barlow_worker(rank, world, port, n_local, d, normalize, lmbda, out, mode="allreduce"):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "self-supervised-vision_b200")]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -192,7 +236,7 @@ def _barlow_worker(rank, world, port, n_local, d, normalize, lmbda, out):
     g = torch.Generator().manual_seed(200 + rank)
     zi = (torch.randn(n_local, d, generator=g) * 1.5 + 0.3).requires_grad_(True)
     zj = (zi.detach() * 0.7 + 0.5 * torch.randn(n_local, d, generator=g)).requires_grad_(True)
-    loss = DistributedBarlowLoss(normalize, lmbda, stages=EmulatedBarlowStages())(zi, zj)
+    loss = DistributedBarlowLoss(normalize, lmbda, stages=EmulatedBarlowStages(), mode=mode)(zi, zj)
     (3.0 * loss).backward()
     out[rank] = (loss.item(), zi.grad.numpy().copy(), zj.grad.numpy().copy(), zi.detach().numpy().copy(),
                  zj.detach().numpy().copy())
@@ -200,14 +244,16 @@ def _barlow_worker(rank, world, port, n_local, d, normalize, lmbda, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("normalize,d", [(False, 32), (True, 32), (False, 33)])  # d=33: not divisible -> all-reduce path
-def test_distributed_barlow_matches_global_oracle(normalize, d):
+# d=33: not divisible by the world size -> plain all-reduce of C instead of reduce-scatter + all-gather
+@pytest.mark.parametrize("normalize,d,mode", [(False, 32, "allreduce"), (True, 32, "allreduce"), (False, 33, "allreduce"),
+                                              (False, 32, "colshard"), (True, 32, "colshard")])
+def test_distributed_barlow_matches_global_oracle(normalize, d, mode):
     from oracle import ssl_oracle as O
     world, n_local, lmbda = 2, 20, 0.005
     mgr = mp.Manager()
     out = mgr.dict()
     port = 31500 + (os.getpid() % 2000)
-    mp.spawn(_barlow_worker, args=(world, port, n_local, d, normalize, lmbda, out), nprocs=world, join=True)
+    mp.spawn(_barlow_worker, args=(world, port, n_local, d, normalize, lmbda, out, mode), nprocs=world, join=True)
     zi = np.concatenate([out[r][3] for r in range(world)])
     zj = np.concatenate([out[r][4] for r in range(world)])
     ref_loss, ref_dzi, ref_dzj = O.barlow(zi, zj, normalize, lmbda)

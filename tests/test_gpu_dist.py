@@ -31,6 +31,30 @@ def _worker(rank, world, port, n_local, d, normalize, tau, out, transport="auto"
         loss.backward()
     torch.cuda.synchronize()
     out[rank] = (loss.item(), a.grad.cpu().numpy(), b.grad.cpu().numpy(), zi.numpy(), zj.numpy())
+    if transport == "p2p":
+        # in-place use of the double-buffered transport buffers: one extra forward in between is fine, a second one
+        # must make the stale backward fail loudly; retain_gathered=True lifts the restriction
+        l1 = fn(a, b); l2 = fn(a, b)
+        a.grad = None; b.grad = None
+        l1.backward()
+        torch.cuda.synchronize()
+        g_ = a.grad.cpu().numpy()  # (column-chunked accumulation uses red.add: equal up to fp32 summation order)
+        assert np.linalg.norm(g_ - out[rank][1]) <= 1e-5 * np.linalg.norm(out[rank][1])
+        l1 = fn(a, b); l2 = fn(a, b); l3 = fn(a, b)
+        try:
+            l1.backward()
+            raised = False
+        except RuntimeError:
+            raised = True
+        assert raised, "stale backward must raise"
+        fr = DistributedSimclrLoss(normalize, tau, transport=transport, retain_gathered=True)
+        l1 = fr(a, b); l2 = fr(a, b); l3 = fr(a, b)
+        a.grad = None; b.grad = None
+        l1.backward()
+        torch.cuda.synchronize()
+        g_ = a.grad.cpu().numpy()  # (column-chunked accumulation uses red.add: equal up to fp32 summation order)
+        assert np.linalg.norm(g_ - out[rank][1]) <= 1e-5 * np.linalg.norm(out[rank][1])
+        del l2, l3
     dist.barrier()
     dist.destroy_process_group()
 
@@ -69,14 +93,14 @@ def _unit(x):
     return torch.nn.functional.normalize(x, dim=1)
 
 
-def _barlow_worker(rank, world, port, n_local, d, normalize, out):
+def _barlow_worker(rank, world, port, n_local, d, normalize, out, mode="allreduce"):
     _init(rank, world, port)
     from ssv_b200.dist import DistributedBarlowLoss
     g = torch.Generator().manual_seed(200 + rank)
     zi = torch.randn(n_local, d, generator=g) * 1.5 + 0.3
     zj = zi * 0.7 + 0.5 * torch.randn(n_local, d, generator=g)
     a, b = zi.cuda().requires_grad_(True), zj.cuda().requires_grad_(True)
-    fn = DistributedBarlowLoss(normalize, 0.005)
+    fn = DistributedBarlowLoss(normalize, 0.005, mode=mode)
     for _ in range(2):
         a.grad = None; b.grad = None
         loss = fn(a, b)
@@ -87,8 +111,10 @@ def _barlow_worker(rank, world, port, n_local, d, normalize, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_local,d,normalize", [(128, 1024, False), (100, 264, True), (64, 1000, False)])
-def test_dist_barlow_vs_oracle(n_local, d, normalize):
+@pytest.mark.parametrize("n_local,d,normalize,mode", [(128, 1024, False, "allreduce"), (100, 264, True, "allreduce"),
+                                                      (64, 1000, False, "allreduce"), (128, 1024, False, "colshard"),
+                                                      (100, 256, True, "colshard")])
+def test_dist_barlow_vs_oracle(n_local, d, normalize, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     from oracle import ssl_oracle as O
@@ -98,7 +124,7 @@ def test_dist_barlow_vs_oracle(n_local, d, normalize):
     mgr = mp.Manager()
     out = mgr.dict()
     port = 29900 + (os.getpid() % 2000)
-    mp.spawn(_barlow_worker, args=(world, port, n_local, d, normalize, out), nprocs=world, join=True)
+    mp.spawn(_barlow_worker, args=(world, port, n_local, d, normalize, out, mode), nprocs=world, join=True)
     zi = np.concatenate([out[r][3] for r in range(world)])
     zj = np.concatenate([out[r][4] for r in range(world)])
     ref_loss, ref_di, ref_dj = O.barlow(zi, zj, normalize, 0.005)

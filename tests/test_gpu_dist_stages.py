@@ -22,13 +22,15 @@ def unit(x):
 
 
 # ------------------------------------------------------------------------------------------------ world = 1
-@pytest.mark.parametrize("n,d,norm", [(256, 1000, False), (200, 264, True), (512, 4096, False)])
-def test_dist_barlow_world1(S, n, d, norm):
+@pytest.mark.parametrize("n,d,norm,mode", [(256, 1000, False, "allreduce"), (200, 264, True, "allreduce"),
+                                           (512, 4096, False, "allreduce"), (256, 1000, False, "colshard"),
+                                           (200, 264, True, "colshard"), (512, 4096, False, "colshard")])
+def test_dist_barlow_world1(S, n, d, norm, mode):
     from ssv_b200.dist import DistributedBarlowLoss
     zi, zj = barlow_inputs(n, d)
     ref = O.barlow(zi, zj, norm, 0.005)
     a, b = dev(zi), dev(zj)
-    loss = DistributedBarlowLoss(norm, 0.005)(a, b)
+    loss = DistributedBarlowLoss(norm, 0.005, mode=mode)(a, b)
     loss.backward()
     check(loss.item(), [a.grad, b.grad], ref[0], ref[1:], f"dist barlow world=1 n={n} d={d}")
 
@@ -228,5 +230,56 @@ def test_dist_barlow_emulated_ranks(S, n, d, world, norm):
         C.check(L.ssvb_barlow_dist_bwd_finish(C.ptr(Zi[sl[r]]), C.ptr(Zj[sl[r]]), n, ng, d, d, d, int(norm), C.ptr(colsum),
                                               C.ptr(go), C.ptr(saved[r]), C.ptr(di[sl[r]]), C.ptr(dj[sl[r]]), d, d,
                                               C.ptr(wss[r]), wb, st), "bwd_finish")
+    assert rel_l2(di.cpu().numpy(), ref_di) <= 1e-2
+    assert rel_l2(dj.cpu().numpy(), ref_dj) <= 1e-2
+
+
+@pytest.mark.parametrize("n,d,world,norm", [(256, 512, 4, False), (96, 256, 2, True)])
+def test_dist_barlow_colshard_emulated_ranks(S, n, d, world, norm):
+    """Column-sharded variant with the ranks emulated in one process: the all-gather of the standardised rows is a
+    shared [N x D] buffer, the all-to-all of the gradient slabs is a block transpose."""
+    from ssv_b200 import _cabi as C
+    L = C.lib()
+    ng, ncols = n * world, d // world
+    zi, zj = barlow_inputs(ng, d)
+    ref_loss, ref_di, ref_dj = O.barlow(zi, zj, norm, 0.005)
+    Zi, Zj = dev(zi, False), dev(zj, False)
+    st = C.stream_ptr(Zi.device)
+    sb, wb = L.ssvb_barlow_dist_saved_bytes(n, d), L.ssvb_barlow_dist_workspace_bytes(n, d)
+    saved = [torch.empty(sb, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    ws = torch.empty(wb, dtype=torch.uint8, device="cuda")
+    stats_all = torch.empty(world, 2, 2, d, device="cuda")
+    sl = [slice(r * n, (r + 1) * n) for r in range(world)]
+    for r in range(world):
+        C.check(L.ssvb_barlow_dist_stats(C.ptr(Zi[sl[r]]), C.ptr(Zj[sl[r]]), n, d, d, d, int(norm), C.ptr(stats_all[r]),
+                                         C.ptr(saved[r]), C.ptr(ws), wb, st), "stats")
+    xt = torch.empty(2, ng, d, dtype=torch.bfloat16, device="cuda")
+    for r in range(world):
+        C.check(L.ssvb_barlow_dist_standardize(C.ptr(Zi[sl[r]]), C.ptr(Zj[sl[r]]), n, d, d, d, int(norm), C.ptr(stats_all),
+                                               world, C.ptr(xt[0, sl[r]]), C.ptr(xt[1, sl[r]]), C.ptr(saved[r]), st),
+                "standardize")
+    cb = L.ssvb_barlow_cs_workspace_bytes(ng, d, ncols)
+    cws = torch.empty(cb, dtype=torch.uint8, device="cuda")
+    dc = torch.empty(world, 2, d, ncols, dtype=torch.bfloat16, device="cuda")
+    parts = torch.zeros(world, device="cuda")
+    for r in range(world):
+        C.check(L.ssvb_barlow_cs_fwd(C.ptr(xt[0]), C.ptr(xt[1]), ng, d, r * ncols, ncols, 0.005, C.ptr(dc[r, 0]),
+                                     C.ptr(parts[r:]), C.ptr(cws), cb, st), "cs_fwd")
+        C.check(L.ssvb_barlow_cs_fwd(C.ptr(xt[1]), C.ptr(xt[0]), ng, d, r * ncols, ncols, 0.005, C.ptr(dc[r, 1]), None,
+                                     C.ptr(cws), cb, st), "cs_fwd T")
+    assert rel_scalar(parts.sum().item(), ref_loss) <= 1e-3
+    go = torch.ones((), device="cuda")
+    slabs = torch.empty(world, 2, ng, ncols, device="cuda")  # [owner of the columns][view]
+    for r in range(world):
+        C.check(L.ssvb_barlow_cs_bwd(C.ptr(xt[0]), C.ptr(xt[1]), C.ptr(dc[r, 0]), ng, d, r * ncols, ncols, C.ptr(saved[r]), n,
+                                     1, C.ptr(go), C.ptr(slabs[r, 1]), C.ptr(cws), cb, st), "cs_bwd j")
+        C.check(L.ssvb_barlow_cs_bwd(C.ptr(xt[1]), C.ptr(xt[0]), C.ptr(dc[r, 1]), ng, d, r * ncols, ncols, C.ptr(saved[r]), n,
+                                     0, C.ptr(go), C.ptr(slabs[r, 0]), C.ptr(cws), cb, st), "cs_bwd i")
+    di, dj = torch.empty(ng, d, device="cuda"), torch.empty(ng, d, device="cuda")
+    for q in range(world):      # receiver q gets row block q of every owner's slab
+        for view, (Z, out) in enumerate(((Zi, di), (Zj, dj))):
+            recv = torch.stack([slabs[r, view, sl[q]] for r in range(world)]).contiguous()
+            C.check(L.ssvb_barlow_cs_finish(C.ptr(recv), world, n, ncols, C.ptr(Z[sl[q]]), d, int(norm), C.ptr(saved[q]), view,
+                                            C.ptr(out[sl[q]]), d, st), "cs_finish")
     assert rel_l2(di.cpu().numpy(), ref_di) <= 1e-2
     assert rel_l2(dj.cpu().numpy(), ref_dj) <= 1e-2
