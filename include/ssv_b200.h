@@ -363,6 +363,34 @@ int ssvb_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int6
                     int64_t ld_y, float* dx, int64_t ld_dx, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (f) "next" rows of SURVEY.md §8, built to the same parity + measurement bar.
+ *
+ * EMA of the momentum (key / target / teacher) network — models/moco.py:108-111, byol.py:120-123,
+ *     relic.py:119-122, dino.py:129-134:  t = m*t + (1-m)*s for every parameter, ONE launch for the whole network.
+ *     chunk_table: DEVICE array of n_chunks entries {float* t; const float* s; int64 n} (24 bytes each), every tensor
+ *     split by the caller into chunks of <= ssvb_ema_chunk_elems() elements (one CTA per chunk).  `m` and
+ *     `one_minus_m` are passed separately so the caller's double-precision (1.0 - m) is rounded exactly as the
+ *     reference's scalar is; products and sum are rounded separately (no FMA): bit-exact with the eager ops.
+ * ------------------------------------------------------------------------------------- */
+int64_t ssvb_ema_chunk_elems(void);
+int ssvb_ema_update(const void* chunk_table, int64_t n_chunks, float m, float one_minus_m, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * DinoLoss — replaces DinoLoss.forward (utils/losses.py:80-89; call site models/dino.py:161-162).
+ *     teacher: [bs x 2 x k] contiguous, student: [bs x nv x k] contiguous, center: [k].
+ *     loss = -(1/(bs nv)) sum_{b,v,k} (T_0 + T_1) log_softmax(student/temp_s),  T_g = softmax((teacher_g - center)/temp_t);
+ *     gradient to the student only (the teacher runs under no_grad, models/dino.py:151-152).
+ *     ssvb_dino_center_update: models/dino.py:136-141 (first != 0: center = mean of the rows).
+ * ------------------------------------------------------------------------------------- */
+size_t ssvb_dino_workspace_bytes(int64_t bs);
+int ssvb_dino_fwd(const float* teacher, const float* student, const float* center, int64_t bs, int64_t nv, int64_t k,
+                  float temp_s, float temp_t, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+int ssvb_dino_bwd(const float* teacher, const float* student, const float* center, int64_t bs, int64_t nv, int64_t k,
+                  float temp_s, float temp_t, const float* grad_out, float* dstudent, void* stream);
+int ssvb_dino_center_update(const float* teacher_rows, int64_t rows, int64_t k, int64_t ld, float momentum,
+                            float one_minus_m, int first, float* center, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Measurement hooks (bench.py only; OFF by default, not on the loss path).
  *   ssvb_launch_count: number of kernels this library has launched (reset != 0 zeroes it).
  *   ssvb_profile_enable(1): record a CUDA-event pair around every tensor-core kernel launch, on

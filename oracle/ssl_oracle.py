@@ -296,3 +296,40 @@ def swav(z1, z2, prototypes, bank=None, temperature=0.1, eps=0.05, n_iters=3):
 def prototypes_forward(embedding):
     """models/swav.py:51-54: rows of the embedding table L2-normalised each call."""
     return l2_normalize(embedding)[0]
+
+
+# --------------------------------------------------------------------------
+# (f) next rows: DinoLoss (utils/losses.py:75-89) + centre EMA (models/dino.py:136-141) + parameter EMA
+# --------------------------------------------------------------------------
+def _log_softmax(x):
+    return x - _lse(x, -1)[..., None]
+
+
+def dino(teacher, student, temp_s, temp_t, center):
+    """utils/losses.py:80-89.  teacher [bs,2,K], student [bs,nv,K], center [K] -> (loss, dstudent).
+    targets_g = softmax((teacher[:, g] - center)/temp_t) broadcast over the nv student views (:83-86);
+    loss = sum_g -mean_{b,v} sum_k targets_g * log_softmax(student/temp_s) (:87-89).  No gradient reaches the teacher
+    (models/dino.py:151-152 runs it under no_grad)."""
+    t, s, c = _f64(teacher), _f64(student), _f64(center)
+    bs, nv, _ = s.shape
+    tg = np.exp(_log_softmax((t - c) / temp_t))          # [bs, 2, K]
+    tsum = tg.sum(1)[:, None, :]                          # [bs, 1, K]
+    logp = _log_softmax(s / temp_s)
+    loss = -(tsum * logp).sum() / (bs * nv)
+    dstudent = (2.0 * np.exp(logp) - tsum) / (temp_s * bs * nv)
+    return loss, dstudent
+
+
+def dino_center_update(center, teacher_rows, m):
+    """models/dino.py:136-141 in fp32 (bit-level restatement: separate roundings of the two products and the sum)."""
+    mean = np.asarray(teacher_rows, dtype=np.float32).mean(0, dtype=np.float32)
+    if center is None:
+        return mean
+    return np.float32(m) * np.asarray(center, np.float32) + np.float32(1.0 - m) * mean
+
+
+def ema_update(target, source, m):
+    """models/moco.py:108-111 (byol.py:120-123, relic.py:119-122, dino.py:129-134): t = m*t + (1-m)*s in fp32 with the
+    reference's roundings (scalar (1-m) formed in double, then each product and the sum rounded to fp32)."""
+    t, s = np.asarray(target, np.float32), np.asarray(source, np.float32)
+    return np.float32(m) * t + np.float32(1.0 - m) * s

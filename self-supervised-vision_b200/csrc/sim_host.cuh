@@ -204,7 +204,10 @@ static __global__ void pair_prep_push_kernel(const float* __restrict__ xi, const
   const float2 fj01 = unpack_h2(vj.x, f16), fj23 = unpack_h2(vj.y, f16);
   float dot = warp_sum(fi01.x * fj01.x + fi01.y * fj01.y + fi23.x * fj23.x + fi23.y * fj23.y);
   if (k < dpad) {
-    for (int pr = 0; pr < world; ++pr) {
+    // start at a different peer per CTA so the ranks do not all hit the same NVLink port at the same time
+    const int p0 = static_cast<int>(blockIdx.x % static_cast<unsigned>(world));
+    for (int q = 0; q < world; ++q) {
+      const int pr = (p0 + q) % world;
       __nv_bfloat16* base = static_cast<__nv_bfloat16*>(peers[pr]);
       *reinterpret_cast<uint2*>(base + (row_i + warp) * dpad + k) = vi;
       *reinterpret_cast<uint2*>(base + (row_j + warp) * dpad + k) = vj;

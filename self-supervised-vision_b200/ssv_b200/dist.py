@@ -166,10 +166,10 @@ class _NtxentDistFn(torch.autograd.Function):
             loss = torch.empty((), dtype=torch.float32, device=dev)
             stages.prep_push(xi, xj, norm, world, rank, hz.buffer_ptrs_dev, inv_local, pos_local)
             hz.barrier()
-            zhat_all = zbuf.view(mpad, dpad)
+            # the gathered rows are always copied out (16 MiB, ~10 us): the tensor-core kernels stream them many times and
+            # read a peer-mapped (symmetric-memory) buffer 12-15 % slower than ordinary device memory (measured at 2 GPUs)
+            zhat_all = zbuf.view(mpad, dpad).clone()
             stat_all = sbuf.view(world, 2, 2 * n)
-            if retain:  # private copies: backward stays valid however many forwards follow
-                zhat_all = zhat_all.clone()
             stages.rows_fwd_push(zhat_all, world, rank, n, d, norm, float(temperature), pos_local, hs.buffer_ptrs_dev, loss)
             hs.barrier()
             if retain:
@@ -228,9 +228,9 @@ class DistributedSimclrLoss(nn.Module):
                  retain_gathered=False):
         """transport: "p2p" = kernels store into all peers' buffers over NVLink (torch symmetric memory) + barriers;
         "nccl" = two all-gathers; "auto" = p2p when symmetric memory is available, else nccl.
-        retain_gathered (p2p only): False = backward reads the double-buffered transport buffers in place (valid for the
+        retain_gathered (p2p only): False = backward reads the double-buffered statistics buffer in place (valid for the
         usual forward -> backward -> forward loop and for one extra forward in between; anything else raises in
-        backward); True = forward copies the gathered rows / statistics into private tensors (16 MiB + 256 KiB at cfg5)."""
+        backward); True = forward copies it into a private tensor as well (the gathered rows are always copied)."""
         super().__init__()
         self.retain_gathered = retain_gathered
         self.normalize = normalize

@@ -397,3 +397,67 @@ class SwavLoss(nn.Module):
 
     def forward(self, z_1, z_2, prototypes, bank_features=None):
         return _SwavFn.apply(z_1, z_2, prototypes, bank_features, self.temperature, self.eps, self.n_iters)
+
+
+# --------------------------------------------------------------------------------------------- DINO
+class _DinoFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, teacher, student, temp_s, temp_t, center):
+        C.require_cuda(teacher, student, center)
+        if teacher.dim() != 3 or student.dim() != 3 or teacher.shape[1] != 2 or teacher.shape[0] != student.shape[0] \
+                or teacher.shape[2] != student.shape[2] or center.numel() != student.shape[2]:
+            raise ValueError("DinoLoss expects teacher [bs, 2, K], student [bs, 2+V, K] and center [K]")
+        t = teacher.detach().float().contiguous()
+        s = student.detach().float().contiguous()
+        c = center.detach().float().contiguous().view(-1)
+        bs, nv, k = s.shape
+        L = C.lib()
+        dev = s.device
+        with C.on_device(dev):
+            ws_bytes = C.cached_size("ssvb_dino_workspace_bytes", bs)
+            ws = C.workspace("dino", ws_bytes, dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            C.check(L.ssvb_dino_fwd(C.ptr(t), C.ptr(s), C.ptr(c), bs, nv, k, float(temp_s), float(temp_t), C.ptr(loss),
+                                    C.ptr(ws), ws_bytes, C.stream_ptr(dev)), "ssvb_dino_fwd")
+        ctx.save_for_backward(t, s, c)
+        ctx.cfg = (float(temp_s), float(temp_t), student.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        t, s, c = ctx.saved_tensors
+        temp_s, temp_t, dts = ctx.cfg
+        bs, nv, k = s.shape
+        dev = s.device
+        with C.on_device(dev):
+            go = C.f32_scalar(grad_out)
+            ds = torch.empty_like(s)
+            C.check(C.lib().ssvb_dino_bwd(C.ptr(t), C.ptr(s), C.ptr(c), bs, nv, k, temp_s, temp_t, C.ptr(go), C.ptr(ds),
+                                          C.stream_ptr(dev)), "ssvb_dino_bwd")
+        return None, ds.to(dts), None, None, None
+
+
+class DinoLoss(nn.Module):
+    """Reference: utils/losses.py:75-89 (call site models/dino.py:161-162).  Gradient flows to the student only (the
+    reference evaluates the teacher under no_grad, models/dino.py:151-152)."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, teacher_fvecs, student_fvecs, temp_s, temp_t, center):
+        return _DinoFn.apply(teacher_fvecs, student_fvecs, temp_s, temp_t, center)
+
+
+@torch.no_grad()
+def update_teacher_center(center, teacher_fvecs, momentum):
+    """models/dino.py:136-141: returns the new centre (`center` may be None on the first call, as in the reference)."""
+    C.require_cuda(teacher_fvecs, center)
+    t = C.as_f32_rows(teacher_fvecs.detach().reshape(-1, teacher_fvecs.shape[-1]))
+    rows, k = t.shape
+    first = center is None
+    out = torch.empty(k, dtype=torch.float32, device=t.device) if first else center.detach().float().contiguous().clone()
+    with C.on_device(t.device):
+        C.check(C.lib().ssvb_dino_center_update(C.ptr(t), rows, k, t.stride(0), float(momentum), float(1.0 - momentum),
+                                                int(first), C.ptr(out), C.stream_ptr(t.device)),
+                "ssvb_dino_center_update")
+    return out

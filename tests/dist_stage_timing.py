@@ -56,15 +56,15 @@ def p2p_body(ev):
     zbuf, hz, sbuf, hs = peer.next()
     st.prep_push(zi, zj, 1, world, rank, hz.buffer_ptrs_dev, inv, pos); ev[1].record()
     hz.barrier(); ev[2].record()
-    z = zbuf.view(mpad, dpad).clone(); ev[3].record()
-    st.rows_fwd_push(z, world, rank, n, d, 1, tau, pos, hs.buffer_ptrs_dev, ls); ev[4].record()
-    hs.barrier(); ev[5].record()
-    s_all = sbuf.view(world, 2, 2 * n).clone(); st.dist_loss(s_all, world, n, ls); ev[6].record()
-    st.rows_bwd(zi, zj, 1, tau, world, rank, z, s_all, inv, go, dzi, dzj); ev[7].record()
+    z = zbuf.view(mpad, dpad)
+    st.rows_fwd_push(z, world, rank, n, d, 1, tau, pos, hs.buffer_ptrs_dev, ls); ev[3].record()
+    hs.barrier(); ev[4].record()
+    s_all = sbuf.view(world, 2, 2 * n); st.dist_loss(s_all, world, n, ls); ev[5].record()
+    st.rows_bwd(zi, zj, 1, tau, world, rank, z, s_all, inv, go, dzi, dzj); ev[6].record()
 
 
 if rank == 0: print("--- NCCL transport")
 run(["prep", "allgather zhat", "rows_fwd", "allgather stat", "loss", "rows_bwd"], nccl_body)
 if rank == 0: print("--- peer-memory transport")
-run(["prep+push", "barrier", "clone zhat", "rows_fwd+push", "barrier", "clone stat+loss", "rows_bwd"], p2p_body)
+run(["prep+push", "barrier", "rows_fwd+push", "barrier", "loss", "rows_bwd"], p2p_body)
 dist.destroy_process_group()

@@ -194,6 +194,30 @@ def main():
             cases[f"sw_{tag}_bank"] = npy(bank)
     save("swav", **cases)
 
+    # ---- (f) next rows: DinoLoss, centre EMA, parameter EMA ------------------------------------------
+    cases = {}
+    dl = ref_losses.DinoLoss()
+    for tag, bs, nv, k, ts, tt in [("a", 6, 4, 16, 0.1, 0.04), ("b", 12, 6, 40, 0.1, 0.07)]:
+        teacher, student, center = q32(randn(0, bs, 2, k), randn(1, bs, nv, k), 0.1 * randn(2, k))
+        st = student.clone().requires_grad_(True)
+        loss = dl(teacher, st, ts, tt, center)
+        loss.backward()
+        cases.update({f"{tag}_teacher": npy(teacher), f"{tag}_student": npy(student), f"{tag}_center": npy(center),
+                      f"{tag}_cfg": np.array([ts, tt]), f"{tag}_loss": npy(loss), f"{tag}_dstudent": npy(st.grad)})
+    # the reference's own update expressions (models/dino.py:138-141, models/moco.py:110-111), fp32 on CPU
+    tf = randn(3, 24, 16, dtype=torch.float32)
+    c0 = tf.mean(0)
+    tf2 = randn(4, 24, 16, dtype=torch.float32)
+    m = 0.9
+    c1 = m * c0 + (1 - m) * tf2.mean(0)
+    cases.update(center_rows0=npy(tf), center_rows1=npy(tf2), center0=npy(c0), center1=npy(c1), center_m=np.array(m))
+    for tag, m in [("p", 0.99), ("q", 0.996)]:
+        k_param, q_param = randn(5, 1000, dtype=torch.float32), randn(6, 1000, dtype=torch.float32)
+        out = m * k_param + (1.0 - m) * q_param
+        cases.update({f"ema_{tag}_t": npy(k_param), f"ema_{tag}_s": npy(q_param), f"ema_{tag}_m": np.array(m),
+                      f"ema_{tag}_out": npy(out)})
+    save("next_rows", **cases)
+
 
 if __name__ == "__main__":
     main()

@@ -99,3 +99,24 @@ def test_swav(tag):
     assert rel_l2(dz1, g[f"sw_{tag}_dz1"]) < 5 * TOL32
     assert rel_l2(dz2, g[f"sw_{tag}_dz2"]) < 5 * TOL32
     assert rel_l2(dc, g[f"sw_{tag}_dc"]) < 5 * TOL32
+
+
+# --------------------------------------------------------------------------- (f) next rows
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_dino_oracle_vs_reference(tag):
+    g = load_golden("next_rows")
+    ts, tt = (float(x) for x in g[f"{tag}_cfg"])
+    loss, ds = O.dino(g[f"{tag}_teacher"], g[f"{tag}_student"], ts, tt, g[f"{tag}_center"])
+    assert rel_scalar(loss, float(g[f"{tag}_loss"])) < 1e-9
+    assert rel_l2(ds, g[f"{tag}_dstudent"]) < 1e-9
+
+
+def test_ema_and_center_oracle_bit_exact_vs_reference():
+    g = load_golden("next_rows")
+    for tag in ("p", "q"):
+        out = O.ema_update(g[f"ema_{tag}_t"], g[f"ema_{tag}_s"], float(g[f"ema_{tag}_m"]))
+        assert out.dtype == np.float32 and np.array_equal(out, g[f"ema_{tag}_out"])
+    c0 = O.dino_center_update(None, g["center_rows0"], float(g["center_m"]))
+    np.testing.assert_allclose(c0, g["center0"], rtol=2e-6, atol=1e-7)  # torch / numpy sum the 24 rows in different orders
+    c1 = O.dino_center_update(g["center0"], g["center_rows1"], float(g["center_m"]))
+    np.testing.assert_allclose(c1, g["center1"], rtol=2e-6, atol=1e-7)
