@@ -56,7 +56,7 @@ def p2p_body(ev):
     zbuf, hz, sbuf, hs = peer.next()
     st.prep_push(zi, zj, 1, world, rank, hz.buffer_ptrs_dev, inv, pos); ev[1].record()
     hz.barrier(); ev[2].record()
-    z = zbuf.view(mpad, dpad)
+    z = zbuf.view(mpad, dpad).clone()
     st.rows_fwd_push(z, world, rank, n, d, 1, tau, pos, hs.buffer_ptrs_dev, ls); ev[3].record()
     hs.barrier(); ev[4].record()
     s_all = sbuf.view(world, 2, 2 * n); st.dist_loss(s_all, world, n, ls); ev[5].record()
