@@ -248,6 +248,45 @@ def main():
                cpu_s=cpu_time(lambda: O.relic(zi.numpy(), zj.numpy(), zo.numpy(), True, 1.0, 0.5)),
                note="FLOPs of the contrastive part only; the KL term adds 9*N*d*4 bytes")
 
+    # ---- DinoLoss (reference shape bs 64, 2+6 views, K 1024; and a large one) and the parameter EMA
+    for (bs, nv, k) in ((64, 8, 1024), (1024, 8, 4096)):
+        teacher, student, center = randn(0, bs, 2, k), randn(1, bs, nv, k), 0.1 * randn(2, k)
+        t, st, c = teacher.to(dev), student.to(dev).requires_grad_(True), center.to(dev)
+        fn_d = S.DinoLoss()
+        _f = fwd_bwd(lambda: fn_d(t, st, 0.1, 0.04, c), st)
+        ms = time_gpu(_f, args.reps, flush)
+        gms = time_graph(_f, args.reps, flush)
+        record("DinoLoss", f"bs {bs} x (2 teacher, {nv} student views) x K {k}", ms, bs,
+               bytes_=(2 * (2 + nv) + nv) * bs * k * 4, graph_ms=gms,
+               cpu_s=cpu_time(lambda: O.dino(teacher.numpy(), student.numpy(), 0.1, 0.04, center.numpy())),
+               note="bytes: fwd reads teacher + student, bwd reads them again and writes dstudent")
+    # PirlLoss at the reference's shape (bs 256, 1000 negatives, d 128, tau 0.07) and with a 65536-row negative set
+    for (n, k) in ((256, 1000), (256, 65536)):
+        img, patch = randn(0, n, 128), randn(1, n, 128)
+        mp, mn = unit(0.6 * unit(img) + 0.4 * unit(randn(2, n, 128))), unit(randn(3, k, 128))
+        a, b, mpd, mnd = img.to(dev).requires_grad_(True), patch.to(dev).requires_grad_(True), mp.to(dev), mn.to(dev)
+        fn_p = S.PirlLoss(True, 0.07, 0.5)
+        _f = fwd_bwd(lambda: fn_p(a, b, mpd, mnd), a, b)
+        ms = time_gpu(_f, args.reps, flush)
+        gms = time_graph(_f, args.reps, flush)
+        record("PirlLoss", f"{n} x {k} negatives x 128 tau=0.07", ms, n, bytes_=k * 128 * 4 + 5 * n * 128 * 4, graph_ms=gms,
+               cpu_s=cpu_time(lambda: O.pirl(img.numpy(), patch.numpy(), mp.numpy(), mn.numpy(), True, 0.07, 0.5)),
+               note="bytes: negatives read once (shared by both heads) + the row-wise inputs / gradients")
+    torch.manual_seed(0)
+    n_params = 11_200_000   # ~ResNet-18 sized network split into 62 tensors of mixed sizes
+    sizes = [64 * 3 * 9, 64, 64] + [n_params // 60] * 58 + [512 * 1000]
+    ema_tgt = [torch.randn(n, device=dev) for n in sizes]
+    ema_src = [torch.randn(n, device=dev) for n in sizes]
+    up = S.EmaUpdater(ema_tgt, ema_src)
+    tot = sum(sizes)
+    _f = lambda: up.step(0.99)
+    ms = time_gpu(_f, args.reps, flush)
+    gms = time_graph(_f, args.reps, flush)
+    record("EmaUpdater.step (momentum_update)", f"{len(sizes)} tensors, {tot / 1e6:.1f} M parameters", ms, tot,
+           bytes_=3 * tot * 4, graph_ms=gms,
+           cpu_s=cpu_time(lambda: [O.ema_update(a.cpu().numpy(), b.cpu().numpy(), 0.99) for a, b in zip(ema_tgt[:3], ema_src[:3])]),
+           note="bytes: read target + source, write target; one launch for the whole network (samples = parameters)")
+
     hdr = (f"| loss | config | fwd+bwd ms (eager) | ms (CUDA-graph replay) | samples/s | bound | achieved | "
            f"frac of {src} peak | CPU port s |")
     print(hdr, file=sys.stderr)

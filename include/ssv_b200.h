@@ -391,6 +391,32 @@ int ssvb_dino_center_update(const float* teacher_rows, int64_t rows, int64_t k, 
                             float one_minus_m, int first, float* center, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * PirlLoss — replaces PirlLoss.forward (utils/losses.py:100-117; call site models/pirl.py:134).
+ *     img, patch, mem_pos: [n x d]; mem_neg: [k x d].  Two InfoNCE heads over the SAME negatives:
+ *     logits_h = [mem_pos . v_h / tau | mem_pos mem_neg^T / tau], v_0 = patch, v_1 = img (L2-normalised when
+ *     `normalize`; the memory rows are used as stored), loss = w CE_0 + (1 - w) CE_1 (label 0).
+ *     loss2[0] / loss2[1] receive the two weighted head losses (the caller adds them).  The memory rows carry no
+ *     gradient (models/pirl.py:131-133 reads them from the bank), so backward is one row-wise kernel.  d <= 128.
+ *     ssvb_bank_scatter / ssvb_bank_gather: the per-sample momentum bank of models/pirl.py:22-46
+ *     (mode 0 initialize_vectors, mode 1 update_vectors; indices: DEVICE int64).
+ * ------------------------------------------------------------------------------------- */
+size_t ssvb_pirl_saved_bytes(int64_t n, int64_t d);
+size_t ssvb_pirl_workspace_bytes(int64_t n, int64_t k, int64_t d);
+int ssvb_pirl_fwd(const float* img, const float* patch, const float* mem_pos, const float* mem_neg, int64_t n,
+                  int64_t k, int64_t d, int64_t ld_img, int64_t ld_patch, int64_t ld_pos, int64_t ld_neg,
+                  int normalize, float temperature, float loss_weight, float* loss2, void* saved, void* workspace,
+                  size_t workspace_bytes, void* stream);
+int ssvb_pirl_bwd(const float* img, const float* patch, const float* mem_pos, int64_t n, int64_t d, int64_t ld_img,
+                  int64_t ld_patch, int64_t ld_pos, int normalize, float temperature, float loss_weight,
+                  const float* grad_out, const void* saved, float* d_img, float* d_patch, int64_t ld_dimg,
+                  int64_t ld_dpatch, void* stream);
+int ssvb_bank_scatter(float* bank, int64_t size, int64_t d, int64_t ld_bank, const int64_t* indices, int64_t n,
+                      const float* vectors, int64_t ld_vectors, float momentum, float one_minus_m, int mode,
+                      void* stream);
+int ssvb_bank_gather(const float* bank, int64_t size, int64_t d, int64_t ld_bank, const int64_t* indices, int64_t n,
+                     float* out, int64_t ld_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Measurement hooks (bench.py only; OFF by default, not on the loss path).
  *   ssvb_launch_count: number of kernels this library has launched (reset != 0 zeroes it).
  *   ssvb_profile_enable(1): record a CUDA-event pair around every tensor-core kernel launch, on

@@ -333,3 +333,42 @@ def ema_update(target, source, m):
     reference's roundings (scalar (1-m) formed in double, then each product and the sum rounded to fp32)."""
     t, s = np.asarray(target, np.float32), np.asarray(source, np.float32)
     return np.float32(m) * t + np.float32(1.0 - m) * s
+
+
+def pirl(img, patch, mem_pos, mem_neg, normalize=True, temperature=1.0, loss_weight=0.5):
+    """utils/losses.py:100-117.  Two cross-entropies (label 0) over [positive | negatives] logits that share the negatives
+    mem_pos @ mem_neg^T (:109); head 1 positive = mem_pos . v_patch (:107), head 2 = mem_pos . v_img (:108); the memory
+    rows are used as stored.  Returns (loss, d_img, d_patch) (the memory features carry no gradient)."""
+    vi, vp, mp, mn = _f64(img), _f64(patch), _f64(mem_pos), _f64(mem_neg)
+    n = vi.shape[0]
+    if normalize:
+        vih, di_ = l2_normalize(vi)
+        vph, dp_ = l2_normalize(vp)
+    else:
+        vih, vph = vi, vp
+    neg = mp @ mn.T / temperature
+    out = []
+    for vh, w in ((vph, loss_weight), (vih, 1.0 - loss_weight)):
+        pos = (mp * vh).sum(1) / temperature
+        logits = np.concatenate([pos[:, None], neg], 1)
+        lse = _lse(logits, -1)
+        p0 = np.exp(pos - lse)
+        out.append((w * (lse - pos).mean(), w * (p0 - 1.0)[:, None] * mp / (n * temperature)))
+    (l1, dph), (l2, dih) = out
+    if normalize:
+        d_img, d_patch = l2_normalize_bwd(dih, vih, di_), l2_normalize_bwd(dph, vph, dp_)
+    else:
+        d_img, d_patch = dih, dph
+    return l1 + l2, d_img, d_patch
+
+
+def pirl_bank_update(bank, indices, vectors, m=None):
+    """models/pirl.py:32-38 in fp32: m is None -> initialize_vectors (bank[idx] = normalize(v)); else update_vectors
+    (bank[idx] = m * bank[idx] + (1 - m) * normalize(v), separate roundings)."""
+    bank = np.array(bank, dtype=np.float32, copy=True)
+    v = np.asarray(vectors, dtype=np.float32)
+    den = np.maximum(np.sqrt((v.astype(np.float32) ** 2).sum(1, dtype=np.float32)), np.float32(1e-12))[:, None]
+    vh = (v / den).astype(np.float32)
+    idx = np.asarray(indices, dtype=np.int64)
+    bank[idx] = vh if m is None else np.float32(m) * bank[idx] + np.float32(1.0 - m) * vh
+    return bank

@@ -166,6 +166,69 @@ __global__ void shard_finalize_kernel(const float* __restrict__ part_all, int wo
   grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false);
 }
 
+// ---- PIRL: two InfoNCE heads sharing the negatives; gradient only to the (normalised) key side ----------
+struct PirlSaved {
+  __nv_bfloat16* qhat;  // memory_pos rows as stored, bf16 [npad x dpad]
+  float *inv_patch, *inv_img, *pos_patch, *pos_img, *lse_patch, *lse_img, *unused;
+  size_t bytes;
+};
+PirlSaved pirl_saved(void* base, int64_t n, int64_t dpad) {
+  Carver c(base);
+  PirlSaved s;
+  const int64_t npad = round_up(n, 128);
+  s.qhat = c.take<__nv_bfloat16>(npad * dpad);
+  s.inv_patch = c.take<float>(npad);
+  s.inv_img = c.take<float>(npad);
+  s.pos_patch = c.take<float>(npad);
+  s.pos_img = c.take<float>(npad);
+  s.lse_patch = c.take<float>(npad);
+  s.lse_img = c.take<float>(npad);
+  s.unused = c.take<float>(npad);
+  s.bytes = c.used();
+  return s;
+}
+// d v^_h = w_h (p0_h - 1) mem_pos / (N tau), chained through the row normalisation of v_h; one warp per row, both heads
+__global__ void pirl_grad_kernel(const float* __restrict__ img, const float* __restrict__ patch,
+                                 const float* __restrict__ mem_pos, int64_t ld_img, int64_t ld_patch, int64_t ld_pos, int n,
+                                 int d, const PirlSaved sv, int normalize, float c, float inv_n_tau, float w,
+                                 const float* __restrict__ grad_out, float* __restrict__ d_img, float* __restrict__ d_patch,
+                                 int64_t ld_dimg, int64_t ld_dpatch) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float scale = inv_n_tau * __ldg(grad_out);
+  const int k4 = lane * 4;
+  float q[4] = {0.f, 0.f, 0.f, 0.f};
+  if (k4 < d) {
+    const float4 v = *reinterpret_cast<const float4*>(mem_pos + static_cast<int64_t>(row) * ld_pos + k4);
+    q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {  // head 0: patch (weight w), head 1: img (weight 1 - w)
+    float* dst = h ? d_img : d_patch;
+    if (!dst) continue;
+    const float* src = h ? img : patch;
+    const int64_t lds = h ? ld_img : ld_patch, ldd = h ? ld_dimg : ld_dpatch;
+    const float pos = h ? sv.pos_img[row] : sv.pos_patch[row];
+    const float lse2 = h ? sv.lse_img[row] : sv.lse_patch[row];
+    const float iv = normalize ? (h ? sv.inv_img[row] : sv.inv_patch[row]) : 1.f;
+    const float coef = (exp2f(pos * c - lse2) - 1.f) * scale * (h ? 1.f - w : w);
+    float g[4], xh[4] = {0.f, 0.f, 0.f, 0.f};
+    if (k4 < d) {
+      const float4 v = *reinterpret_cast<const float4*>(src + static_cast<int64_t>(row) * lds + k4);
+      xh[0] = v.x * iv; xh[1] = v.y * iv; xh[2] = v.z * iv; xh[3] = v.w * iv;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) g[e] = coef * q[e];
+    if (normalize) {
+      float dot = g[0] * xh[0] + g[1] * xh[1] + g[2] * xh[2] + g[3] * xh[3];
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) g[e] = (g[e] - dot * xh[e]) * iv;
+    }
+    if (k4 < d) *reinterpret_cast<float4*>(dst + static_cast<int64_t>(row) * ldd + k4) = make_float4(g[0], g[1], g[2], g[3]);
+  }
+}
+
 int check_rows(const void* p, int64_t ld) {
   if (!p) return SSVB_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(p) & 15) || (ld & 3)) return SSVB_ERR_ALIGNMENT;
@@ -412,6 +475,85 @@ int ssvb_moco_dist_finish(const float* query, const float* keys, int64_t n_local
       query, keys, ld_q, ld_k, static_cast<int>(n_local), static_cast<int>(d), dacc_local, static_cast<int>(dpad), sv,
       normalize, SSVB_LOG2E / temperature, 1.f / (static_cast<float>(n_global) * temperature), grad_out, dquery, dkeys,
       ld_dq, ld_dk);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PirlLoss — utils/losses.py:92-117, call site models/pirl.py:134.  See include/ssv_b200.h.
+// ------------------------------------------------------------------------------------------------------------
+size_t ssvb_pirl_saved_bytes(int64_t n, int64_t d) {
+  if (n <= 0 || d <= 0) return 0;
+  return pirl_saved(nullptr, n, sim_dpad(d)).bytes;
+}
+size_t ssvb_pirl_workspace_bytes(int64_t n, int64_t k, int64_t d) { return ssvb_moco_workspace_bytes(n, k, d); }
+
+int ssvb_pirl_fwd(const float* img, const float* patch, const float* mem_pos, const float* mem_neg, int64_t n, int64_t k,
+                  int64_t d, int64_t ld_img, int64_t ld_patch, int64_t ld_pos, int64_t ld_neg, int normalize,
+                  float temperature, float loss_weight, float* loss2, void* saved, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(check_shape(n, k, d, temperature));
+  SSVB_TRY(check_rows(img, ld_img));
+  SSVB_TRY(check_rows(patch, ld_patch));
+  SSVB_TRY(check_rows(mem_pos, ld_pos));
+  SSVB_TRY(check_rows(mem_neg, ld_neg));
+  if (!loss2 || !saved || !workspace) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_pirl_workspace_bytes(n, k, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t dpad = sim_dpad(d), npad = round_up(n, 128);
+  PirlSaved sv = pirl_saved(saved, n, dpad);
+  MocoWs ws = moco_ws(workspace, n, k, dpad);
+  const float c = SSVB_LOG2E / temperature;
+  const int ni = static_cast<int>(n), di = static_cast<int>(d), dp = static_cast<int>(dpad);
+  const unsigned pgrid = static_cast<unsigned>(ceil_div(n, 8));
+  if (npad > n) SSVB_CUDA(cudaMemsetAsync(sv.qhat + n * dpad, 0, (npad - n) * dpad * sizeof(__nv_bfloat16), s));
+  // "query" = memory_pos rows AS STORED (never normalised, :107-109); "keys" = patch / img rows (normalised if asked)
+  const int mask = normalize ? 2 : 0;
+  pair_prep_kernel<<<pgrid, 256, 0, s>>>(mem_pos, patch, ni, di, ld_pos, ld_patch, 0, 0, sv.qhat, nullptr, dp, sv.unused,
+                                         sv.inv_patch, sv.pos_patch, nullptr, mask);
+  SSVB_LAUNCH_CHECK();
+  pair_prep_kernel<<<pgrid, 256, 0, s>>>(mem_pos, img, ni, di, ld_pos, ld_img, 0, 0, nullptr, nullptr, dp, sv.unused,
+                                         sv.inv_img, sv.pos_img, nullptr, mask);
+  SSVB_LAUNCH_CHECK();
+  const __nv_bfloat16* qb = nullptr;
+  SSVB_TRY(get_queue_bf16(mem_neg, nullptr, k, d, ld_neg, dpad, ws, s, &qb));
+  // the negatives' logits are shared by both heads (:109): one pass of the tensor-core kernel, two LSE finalizes
+  SimParams p;
+  moco_plan(p, n, k, c, 256, 2);
+  p.part_m = ws.part_m;
+  p.part_l = ws.part_l;
+  p.part_stride = static_cast<int>(npad);
+  SSVB_TRY(launch_sim_fwd(SIM_MOCO, sv.qhat, npad, qb, k, dpad, p, s));
+  for (int h = 0; h < 2; ++h) {
+    SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
+    lse_finalize_wide_kernel<SIM_MOCO><<<pgrid, 256, 0, s>>>(
+        ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride, ni, h ? sv.pos_img : sv.pos_patch, c,
+        h ? sv.lse_img : sv.lse_patch, ws.block_sums, ws.counter,
+        (h ? 1.f - loss_weight : loss_weight) / static_cast<float>(n), loss2 + h);
+    SSVB_LAUNCH_CHECK();
+  }
+  return SSVB_OK;
+}
+
+int ssvb_pirl_bwd(const float* img, const float* patch, const float* mem_pos, int64_t n, int64_t d, int64_t ld_img,
+                  int64_t ld_patch, int64_t ld_pos, int normalize, float temperature, float loss_weight,
+                  const float* grad_out, const void* saved, float* d_img, float* d_patch, int64_t ld_dimg,
+                  int64_t ld_dpatch, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(check_shape(n, 1, d, temperature));
+  SSVB_TRY(check_rows(img, ld_img));
+  SSVB_TRY(check_rows(patch, ld_patch));
+  SSVB_TRY(check_rows(mem_pos, ld_pos));
+  if (d_img) SSVB_TRY(check_rows(d_img, ld_dimg));
+  if (d_patch) SSVB_TRY(check_rows(d_patch, ld_dpatch));
+  if (!grad_out || !saved || (!d_img && !d_patch)) return SSVB_ERR_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PirlSaved sv = pirl_saved(const_cast<void*>(saved), n, sim_dpad(d));
+  pirl_grad_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(
+      img, patch, mem_pos, ld_img, ld_patch, ld_pos, static_cast<int>(n), static_cast<int>(d), sv, normalize,
+      SSVB_LOG2E / temperature, 1.f / (static_cast<float>(n) * temperature), loss_weight, grad_out, d_img, d_patch, ld_dimg,
+      ld_dpatch);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }

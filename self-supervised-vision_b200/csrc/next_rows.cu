@@ -51,7 +51,7 @@ __global__ void ema_kernel(const EmaChunk* __restrict__ table, float m, float om
 //   logp_v = log_softmax(student[b, v] / temp_s)
 //   loss = -(1 / (bs nv)) sum_b sum_v sum_k (T_0 + T_1) logp_v                   (utils/losses.py:86-89)
 //   d student[b, v] = (2 softmax(student/temp_s) - (T_0 + T_1)) * grad_out / (temp_s bs nv)   (sum_k T_g = 1)
-// The block first builds Tsum = T_0 + T_1 in shared memory (K floats), then walks the nv student rows.
+// The block first builds Tsum = T_0 + T_1 (in registers), then walks the nv student rows.
 __device__ __forceinline__ float block_reduce_f(float v, bool is_max, float* red) {
   v = is_max ? warp_max(v) : warp_sum(v);
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -62,57 +62,96 @@ __device__ __forceinline__ float block_reduce_f(float v, bool is_max, float* red
   return is_max ? warp_max(t) : warp_sum(t);
 }
 
-template <bool BWD>
-__global__ void dino_kernel(const float* __restrict__ teacher, int64_t ld_tb, int64_t ld_tv,
-                            const float* __restrict__ student, int64_t ld_sb, int64_t ld_sv, int nv, int k,
-                            const float* __restrict__ center, float inv_ts, float inv_tt,
-                            float* __restrict__ loss_part /* [bs] */, const float* __restrict__ grad_out, float coef,
-                            float* __restrict__ dstudent, int64_t ld_db, int64_t ld_dv) {
-  extern __shared__ float dino_smem[];  // [k] Tsum
+// Every row (K floats) is loaded ONCE into registers (EPT values per thread, coalesced: column = tid + e * 256) and the
+// max / sum / dot / gradient passes run on the registers; one block reduction per statistic.
+template <bool BWD, int EPT>
+__global__ void __launch_bounds__(256)
+dino_kernel(const float* __restrict__ teacher, int64_t ld_tb, int64_t ld_tv, const float* __restrict__ student,
+            int64_t ld_sb, int64_t ld_sv, int nv, int k, const float* __restrict__ center, float inv_ts, float inv_tt,
+            float* __restrict__ loss_part /* [bs] */, const float* __restrict__ grad_out, float coef,
+            float* __restrict__ dstudent, int64_t ld_db, int64_t ld_dv) {
   __shared__ float red[32];
   const int64_t b = blockIdx.x;
-  float* tsum = dino_smem;
+  float tsum[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) tsum[e] = 0.f;
   for (int g = 0; g < 2; ++g) {
     const float* t = teacher + b * ld_tb + g * ld_tv;
+    float x[EPT];
     float m = -INFINITY;
-    for (int c = threadIdx.x; c < k; c += blockDim.x) m = fmaxf(m, (t[c] - center[c]) * inv_tt);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int c = threadIdx.x + e * 256;
+      x[e] = c < k ? (t[c] - __ldg(center + c)) * inv_tt : -INFINITY;
+      m = fmaxf(m, x[e]);
+    }
     m = block_reduce_f(m, true, red);
     float z = 0.f;
-    for (int c = threadIdx.x; c < k; c += blockDim.x) z += __expf((t[c] - center[c]) * inv_tt - m);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      x[e] = __expf(x[e] - m);  // exp(-inf) = 0 for the padding
+      z += x[e];
+    }
     z = block_reduce_f(z, false, red);
     const float iz = 1.f / z;
-    for (int c = threadIdx.x; c < k; c += blockDim.x) {
-      const float p = __expf((t[c] - center[c]) * inv_tt - m) * iz;
-      tsum[c] = g == 0 ? p : tsum[c] + p;
-    }
-    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) tsum[e] = fmaf(x[e], iz, tsum[e]);
   }
   float acc = 0.f;
   const float go = BWD ? __ldg(grad_out) * coef : 0.f;
   for (int v = 0; v < nv; ++v) {
     const float* s = student + b * ld_sb + v * ld_sv;
+    float x[EPT];
     float m = -INFINITY;
-    for (int c = threadIdx.x; c < k; c += blockDim.x) m = fmaxf(m, s[c] * inv_ts);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int c = threadIdx.x + e * 256;
+      x[e] = c < k ? s[c] * inv_ts : -INFINITY;
+      m = fmaxf(m, x[e]);
+    }
     m = block_reduce_f(m, true, red);
     float z = 0.f, dot = 0.f;
-    for (int c = threadIdx.x; c < k; c += blockDim.x) {
-      const float x = s[c] * inv_ts;
-      z += __expf(x - m);
-      dot = fmaf(tsum[c], x, dot);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      if (!BWD && threadIdx.x + e * 256 < k) dot = fmaf(tsum[e], x[e], dot);
+      x[e] = __expf(x[e] - m);
+      z += x[e];
     }
     z = block_reduce_f(z, false, red);
     if (!BWD) {
       dot = block_reduce_f(dot, false, red);
-      // sum_k Tsum (x - lse) with sum_k Tsum = 2
-      acc += dot - 2.f * (m + __logf(z));
+      acc += dot - 2.f * (m + __logf(z));  // sum_k Tsum (x - lse) with sum_k Tsum = 2
     } else {
-      const float iz = 1.f / z;
+      const float iz = 2.f / z;
       float* d = dstudent + b * ld_db + v * ld_dv;
-      for (int c = threadIdx.x; c < k; c += blockDim.x)
-        d[c] = (2.f * __expf(s[c] * inv_ts - m) * iz - tsum[c]) * go;
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int c = threadIdx.x + e * 256;
+        if (c < k) d[c] = (x[e] * iz - tsum[e]) * go;
+      }
     }
   }
   if (!BWD && threadIdx.x == 0) loss_part[b] = -acc;
+}
+
+template <bool BWD>
+int dino_launch(const float* teacher, const float* student, const float* center, int64_t bs, int64_t nv, int64_t k,
+                float temp_s, float temp_t, float* part, const float* grad_out, float coef, float* dstudent,
+                cudaStream_t s) {
+  const unsigned grid = static_cast<unsigned>(bs);
+  const int ki = static_cast<int>(k), nvi = static_cast<int>(nv);
+  const float its = 1.f / temp_s, itt = 1.f / temp_t;
+#define SSVB_DINO(E)                                                                                                   \
+  dino_kernel<BWD, E><<<grid, 256, 0, s>>>(teacher, 2 * k, k, student, nv * k, k, nvi, ki, center, its, itt, part, grad_out, \
+                                           coef, dstudent, nv * k, k)
+  if (k <= 4 * 256) SSVB_DINO(4);
+  else if (k <= 8 * 256) SSVB_DINO(8);
+  else if (k <= 16 * 256) SSVB_DINO(16);
+  else if (k <= 32 * 256) SSVB_DINO(32);
+  else return SSVB_ERR_UNSUPPORTED;
+#undef SSVB_DINO
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
 }
 
 // centre EMA (models/dino.py:136-141): center = m * center + (1 - m) * mean_rows(teacher_fvecs); first call: plain mean.
@@ -161,16 +200,11 @@ int ssvb_dino_fwd(const float* teacher, const float* student, const float* cente
   if (!teacher || !student || !center || !loss || !workspace || bs <= 0 || nv <= 0 || k <= 0 || !(temp_s > 0.f) ||
       !(temp_t > 0.f))
     return SSVB_ERR_INVALID;
-  if (k > 12 * 1024 || bs > 0x7fffffffLL) return SSVB_ERR_UNSUPPORTED;
+  if (k > 8192 || bs > 0x7fffffffLL) return SSVB_ERR_UNSUPPORTED;
   if (workspace_bytes < ssvb_dino_workspace_bytes(bs)) return SSVB_ERR_WORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* part = static_cast<float*>(workspace);
-  const size_t smem = static_cast<size_t>(k) * sizeof(float);
-  dino_kernel<false><<<static_cast<unsigned>(bs), 256, smem, s>>>(teacher, 2 * k, k, student, nv * k, k,
-                                                                  static_cast<int>(nv), static_cast<int>(k), center,
-                                                                  1.f / temp_s, 1.f / temp_t, part, nullptr, 0.f, nullptr,
-                                                                  0, 0);
-  SSVB_LAUNCH_CHECK();
+  SSVB_TRY(dino_launch<false>(teacher, student, center, bs, nv, k, temp_s, temp_t, part, nullptr, 0.f, nullptr, s));
   sum_partials_kernel<<<1, 1024, 0, s>>>(part, static_cast<int>(bs), 1.f / static_cast<float>(bs * nv), loss);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
@@ -182,14 +216,10 @@ int ssvb_dino_bwd(const float* teacher, const float* student, const float* cente
   if (!teacher || !student || !center || !grad_out || !dstudent || bs <= 0 || nv <= 0 || k <= 0 || !(temp_s > 0.f) ||
       !(temp_t > 0.f))
     return SSVB_ERR_INVALID;
-  if (k > 12 * 1024 || bs > 0x7fffffffLL) return SSVB_ERR_UNSUPPORTED;
+  if (k > 8192 || bs > 0x7fffffffLL) return SSVB_ERR_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t smem = static_cast<size_t>(k) * sizeof(float);
-  dino_kernel<true><<<static_cast<unsigned>(bs), 256, smem, s>>>(
-      teacher, 2 * k, k, student, nv * k, k, static_cast<int>(nv), static_cast<int>(k), center, 1.f / temp_s, 1.f / temp_t,
-      nullptr, grad_out, 1.f / (temp_s * static_cast<float>(bs * nv)), dstudent, nv * k, k);
-  SSVB_LAUNCH_CHECK();
-  return SSVB_OK;
+  return dino_launch<true>(teacher, student, center, bs, nv, k, temp_s, temp_t, nullptr, grad_out,
+                           1.f / (temp_s * static_cast<float>(bs * nv)), dstudent, s);
 }
 
 int ssvb_dino_center_update(const float* teacher_rows, int64_t rows, int64_t k, int64_t ld, float momentum,

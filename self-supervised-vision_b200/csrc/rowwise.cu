@@ -160,6 +160,54 @@ __global__ void ring_enqueue_kernel(float* __restrict__ bank, __nv_bfloat16* __r
   }
 }
 
+// =========================================================================================== PIRL indexed bank
+// models/pirl.py:22-46: per-sample momentum bank.  mode 0 (initialize_vectors :32-34): bank[idx] = normalize(v);
+// mode 1 (update_vectors :36-38): bank[idx] = m * bank[idx] + (1 - m) * normalize(v) (products and sum rounded
+// separately, like the eager expression).  One warp per row; duplicate indices are not supported (as undefined in the
+// reference's index_put).
+__global__ void bank_scatter_kernel(float* __restrict__ bank, int64_t size, int d, int64_t ld_bank,
+                                    const long long* __restrict__ idx, int64_t n, const float* __restrict__ v,
+                                    int64_t ld_v, float m, float om, int mode) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const long long slot = idx[i];
+  if (slot < 0 || slot >= size) return;
+  const float4* src = reinterpret_cast<const float4*>(v + i * ld_v);
+  float s = 0.f;
+  for (int c = lane; c < d / 4; c += 32) {
+    const float4 x = __ldg(src + c);
+    s += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+  }
+  s = warp_sum(s);
+  const float den = fmaxf(sqrtf(s), 1e-12f);
+  float4* dst = reinterpret_cast<float4*>(bank + slot * ld_bank);
+  for (int c = lane; c < d / 4; c += 32) {
+    float4 x = __ldg(src + c);
+    x.x = x.x / den; x.y = x.y / den; x.z = x.z / den; x.w = x.w / den;
+    if (mode == 1) {
+      const float4 b = dst[c];
+      x.x = __fadd_rn(__fmul_rn(m, b.x), __fmul_rn(om, x.x));
+      x.y = __fadd_rn(__fmul_rn(m, b.y), __fmul_rn(om, x.y));
+      x.z = __fadd_rn(__fmul_rn(m, b.z), __fmul_rn(om, x.z));
+      x.w = __fadd_rn(__fmul_rn(m, b.w), __fmul_rn(om, x.w));
+    }
+    dst[c] = x;
+  }
+}
+// out[i] = bank[idx[i]]  (get_positives :40-41, get_negatives :43-45)
+__global__ void bank_gather_kernel(const float* __restrict__ bank, int64_t size, int d, int64_t ld_bank,
+                                   const long long* __restrict__ idx, int64_t n, float* __restrict__ out, int64_t ld_out) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const long long slot = idx[i];
+  float4* dst = reinterpret_cast<float4*>(out + i * ld_out);
+  for (int c = lane; c < d / 4; c += 32)
+    dst[c] = (slot >= 0 && slot < size) ? __ldg(reinterpret_cast<const float4*>(bank + slot * ld_bank) + c)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // =========================================================================================== ReLIC KL
 struct RelicSaved {
   float *a, *b, *inv_i, *inv_j, *inv_o, *scal;  // scal: [lse_a, lse_b, sum(p*q), kl]
@@ -510,6 +558,38 @@ int ssvb_relic_kl_bwd(const float* zi, const float* zj, const float* zo, int64_t
   relic_bwd_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(
       zi, zj, zo, n, static_cast<int>(d), ld_zi, ld_zj, ld_zo, normalize, 1.f / temperature, alpha, grad_out, sv, dzi,
       dzj, dzo, ld_dzi, ld_dzj, ld_dzo);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_bank_scatter(float* bank, int64_t size, int64_t d, int64_t ld_bank, const int64_t* indices, int64_t n,
+                      const float* vectors, int64_t ld_vectors, float momentum, float one_minus_m, int mode,
+                      void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (size <= 0 || d <= 0 || n < 0 || (mode != 0 && mode != 1)) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(bank, ld_bank));
+  if (n == 0) return SSVB_OK;
+  if (!indices) return SSVB_ERR_INVALID;
+  SSVB_TRY(check_rows(vectors, ld_vectors));
+  bank_scatter_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      bank, size, static_cast<int>(d), ld_bank, reinterpret_cast<const long long*>(indices), n, vectors, ld_vectors,
+      momentum, one_minus_m, mode);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_bank_gather(const float* bank, int64_t size, int64_t d, int64_t ld_bank, const int64_t* indices, int64_t n,
+                     float* out, int64_t ld_out, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (size <= 0 || d <= 0 || n < 0) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(bank, ld_bank));
+  if (n == 0) return SSVB_OK;
+  if (!indices) return SSVB_ERR_INVALID;
+  SSVB_TRY(check_rows(out, ld_out));
+  bank_gather_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      bank, size, static_cast<int>(d), ld_bank, reinterpret_cast<const long long*>(indices), n, out, ld_out);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }

@@ -117,11 +117,13 @@ inline int launch_sim_bwd(int mode, const void* A, int64_t a_rows, const void* B
 static __global__ void pair_prep_kernel(const float* __restrict__ xi, const float* __restrict__ xj, int n, int d,
                                  int64_t ldi, int64_t ldj, int normalize, int f16, __nv_bfloat16* __restrict__ out_i,
                                  __nv_bfloat16* __restrict__ out_j, int dpad, float* __restrict__ inv_i,
-                                 float* __restrict__ inv_j, float* __restrict__ pos_i, float* __restrict__ pos_j) {
+                                 float* __restrict__ inv_j, float* __restrict__ pos_i, float* __restrict__ pos_j,
+                                 int norm_mask = -1 /* >= 0: bit 0 normalises xi, bit 1 xj (overrides `normalize`) */) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n) return;
   const float* ri = xi + static_cast<int64_t>(warp) * ldi;
   const float* rj = xj + static_cast<int64_t>(warp) * ldj;
+  const int nmask = norm_mask >= 0 ? norm_mask : (normalize ? 3 : 0);
   // dpad <= 256: up to two float4 per lane
   float4 a[2], b[2];
   float si = 0.f, sj = 0.f;
@@ -140,10 +142,8 @@ static __global__ void pair_prep_kernel(const float* __restrict__ xi, const floa
   si = warp_sum(si);
   sj = warp_sum(sj);
   float ivi = 1.f, ivj = 1.f;
-  if (normalize) {
-    ivi = 1.f / fmaxf(sqrtf(si), 1e-12f);
-    ivj = 1.f / fmaxf(sqrtf(sj), 1e-12f);
-  }
+  if (nmask & 1) ivi = 1.f / fmaxf(sqrtf(si), 1e-12f);
+  if (nmask & 2) ivj = 1.f / fmaxf(sqrtf(sj), 1e-12f);
   float dot = 0.f;
 #pragma unroll
   for (int it = 0; it < 2; ++it) {

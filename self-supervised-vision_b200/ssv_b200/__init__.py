@@ -5,10 +5,10 @@ and the ring buffers of `models/moco.py` / `models/swav.py`; the arithmetic runs
 CUDA kernels behind the C ABI of include/ssv_b200.h.  No CPU fallback.
 """
 from . import _cabi  # noqa: F401
-from .losses import (BarlowLoss, DinoLoss, MocoLoss, MSELoss, RelicLoss, SimclrLoss, SimSiamLoss, SwavLoss,  # noqa: F401
+from .losses import (BarlowLoss, DinoLoss, MocoLoss, MSELoss, PirlLoss, RelicLoss, SimclrLoss, SimSiamLoss, SwavLoss,  # noqa: F401
                      update_teacher_center)
 from .ema import EmaUpdater, momentum_update  # noqa: F401
-from .banks import FeatureBank, MemoryBank, Prototypes  # noqa: F401
+from .banks import FeatureBank, MemoryBank, PirlMemoryBank, Prototypes  # noqa: F401
 
 __all__ = ["SimclrLoss", "MocoLoss", "BarlowLoss", "SimSiamLoss", "RelicLoss", "SwavLoss", "MSELoss",
-           "MemoryBank", "FeatureBank", "Prototypes", "DinoLoss", "update_teacher_center", "EmaUpdater", "momentum_update"]
+           "MemoryBank", "FeatureBank", "Prototypes", "DinoLoss", "PirlLoss", "PirlMemoryBank", "update_teacher_center", "EmaUpdater", "momentum_update"]

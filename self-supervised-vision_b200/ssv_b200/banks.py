@@ -157,3 +157,54 @@ class Prototypes(nn.Module):
         if w.device != torch.device(device):
             w = w.to(device)
         return l2_normalize(w)
+
+
+class PirlMemoryBank:
+    """Per-sample momentum bank of PIRL (reference models/pirl.py:22-46), device-resident: same attributes (`bank`,
+    `num_negatives`, `data_size`, `size`, `m`, `ptr`) and methods.  initialize / update are one scatter kernel each
+    (the reference round-trips through the CPU); the choice of negatives stays the reference's host-side randperm."""
+
+    def __init__(self, data_size, feature_size, momentum=0.5, num_negatives=1000, device=None):
+        self._device = _default_device(device)
+        self.bank = torch.zeros(data_size, feature_size, dtype=torch.float32, device=self._device)
+        self.num_negatives = num_negatives
+        self.data_size = data_size
+        self.size = data_size
+        self.m = momentum
+        self.ptr = 0
+
+    def _idx(self, indices):
+        return torch.as_tensor(indices).to(self._device, dtype=torch.int64).contiguous().view(-1)
+
+    def _scatter(self, indices, vectors, mode):
+        idx = self._idx(indices)
+        v = C.as_f32_rows(vectors.detach().to(self._device))
+        with torch.cuda.device(self._device):
+            C.check(C.lib().ssvb_bank_scatter(C.ptr(self.bank), self.data_size, self.bank.shape[1], self.bank.stride(0),
+                                              C.ptr(idx), idx.numel(), C.ptr(v), v.stride(0), float(self.m),
+                                              float(1 - self.m), mode, C.stream_ptr(self._device)), "ssvb_bank_scatter")
+
+    def initialize_vectors(self, indices, vectors):
+        self._scatter(indices, vectors, 0)
+
+    def update_vectors(self, indices, new_vectors):
+        self._scatter(indices, new_vectors, 1)
+
+    def _gather(self, indices):
+        idx = self._idx(indices)
+        out = torch.empty(idx.numel(), self.bank.shape[1], dtype=torch.float32, device=self._device)
+        with torch.cuda.device(self._device):
+            C.check(C.lib().ssvb_bank_gather(C.ptr(self.bank), self.data_size, self.bank.shape[1], self.bank.stride(0),
+                                             C.ptr(idx), idx.numel(), C.ptr(out), out.stride(0),
+                                             C.stream_ptr(self._device)), "ssvb_bank_gather")
+        return out
+
+    def get_positives(self, indices):
+        return self._gather(indices)
+
+    def get_negatives(self, exclude_idx):
+        # models/pirl.py:43-45: host-side random permutation minus the batch's own indices (bookkeeping, bit-exact
+        # with the reference under the same torch RNG state)
+        ex = set(int(i) for i in torch.as_tensor(exclude_idx).view(-1).tolist())
+        indices = torch.tensor([i for i in torch.randperm(self.data_size).tolist() if i not in ex]).long()
+        return self._gather(indices[:self.num_negatives])

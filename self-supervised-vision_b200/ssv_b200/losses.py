@@ -461,3 +461,59 @@ def update_teacher_center(center, teacher_fvecs, momentum):
                                                 int(first), C.ptr(out), C.stream_ptr(t.device)),
                 "ssvb_dino_center_update")
     return out
+
+
+# --------------------------------------------------------------------------------------------- PIRL
+class _PirlFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, patch, mem_pos, mem_neg, normalize, temperature, loss_weight):
+        C.require_cuda(img, patch, mem_pos, mem_neg)
+        if img.shape != patch.shape or img.shape != mem_pos.shape or img.dim() != 2 or mem_neg.dim() != 2 \
+                or mem_neg.shape[1] != img.shape[1]:
+            raise ValueError("PirlLoss expects img/patch/memory_pos [N, d] and memory_neg [K, d]")
+        xi, xp = C.as_f32_rows(img), C.as_f32_rows(patch)
+        mp, mn = C.as_f32_rows(mem_pos.detach()), C.as_f32_rows(mem_neg.detach())
+        n, d = xi.shape
+        k = mn.shape[0]
+        L = C.lib()
+        dev = xi.device
+        norm = int(bool(normalize))
+        with C.on_device(dev):
+            saved = C.byte_buffer(C.cached_size("ssvb_pirl_saved_bytes", n, d), dev)
+            ws_bytes = C.cached_size("ssvb_pirl_workspace_bytes", n, k, d)
+            ws = C.workspace("moco", ws_bytes, dev)
+            out = torch.empty(2, dtype=torch.float32, device=dev)
+            C.check(L.ssvb_pirl_fwd(C.ptr(xi), C.ptr(xp), C.ptr(mp), C.ptr(mn), n, k, d, _ld(xi), _ld(xp), _ld(mp), _ld(mn),
+                                    norm, float(temperature), float(loss_weight), C.ptr(out), C.ptr(saved), C.ptr(ws),
+                                    ws_bytes, C.stream_ptr(dev)), "ssvb_pirl_fwd")
+        ctx.save_for_backward(xi, xp, mp, saved)
+        ctx.cfg = (norm, float(temperature), float(loss_weight), img.dtype, patch.dtype)
+        return out.sum()  # loss_weight * loss_1 + (1 - loss_weight) * loss_2  (utils/losses.py:117)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xi, xp, mp, saved = ctx.saved_tensors
+        norm, temperature, w, dti, dtp = ctx.cfg
+        n, d = xi.shape
+        dev = xi.device
+        with C.on_device(dev):
+            go = C.f32_scalar(grad_out)
+            di, dp = torch.empty_like(xi), torch.empty_like(xp)
+            C.check(C.lib().ssvb_pirl_bwd(C.ptr(xi), C.ptr(xp), C.ptr(mp), n, d, _ld(xi), _ld(xp), _ld(mp), norm,
+                                          temperature, w, C.ptr(go), C.ptr(saved), C.ptr(di), C.ptr(dp), _ld(di), _ld(dp),
+                                          C.stream_ptr(dev)), "ssvb_pirl_bwd")
+        return di.to(dti), dp.to(dtp), None, None, None, None, None
+
+
+class PirlLoss(nn.Module):
+    """Reference: utils/losses.py:92-117 (ctor defaults normalize=True, temperature=1.0, loss_weight=0.5)."""
+
+    def __init__(self, normalize=True, temperature=1.0, loss_weight=0.5):
+        super().__init__()
+        self.loss_weight = loss_weight
+        self.normalize = normalize
+        self.temp = temperature
+
+    def forward(self, img_features, patch_features, memory_pos_features, memory_neg_features):
+        return _PirlFn.apply(img_features, patch_features, memory_pos_features, memory_neg_features, self.normalize,
+                             self.temp, self.loss_weight)

@@ -216,6 +216,27 @@ def main():
         out = m * k_param + (1.0 - m) * q_param
         cases.update({f"ema_{tag}_t": npy(k_param), f"ema_{tag}_s": npy(q_param), f"ema_{tag}_m": np.array(m),
                       f"ema_{tag}_out": npy(out)})
+    # PirlLoss (utils/losses.py:92-117) in fp64 + the per-sample momentum bank of models/pirl.py:22-46 (fp32)
+    from models.pirl import MemoryBank as RefPirlBank
+    for tag, n, k, d, norm, tau, w in [("pa", 12, 20, 8, True, 0.07, 0.5), ("pb", 24, 50, 16, True, 0.2, 0.3),
+                                       ("pc", 10, 16, 8, False, 1.0, 0.5)]:
+        img, patch = q32(randn(10, n, d), randn(11, n, d))
+        mp = q32(0.7 * torch.nn.functional.normalize(img, dim=-1) + 0.3 * torch.nn.functional.normalize(randn(12, n, d), dim=-1))
+        mn = q32(torch.nn.functional.normalize(randn(13, k, d), dim=-1))
+        fn = ref_losses.PirlLoss(norm, tau, w)
+        li, lp = img.clone().requires_grad_(True), patch.clone().requires_grad_(True)
+        loss = fn(li, lp, mp, mn)
+        loss.backward()
+        cases.update({f"{tag}_img": npy(img), f"{tag}_patch": npy(patch), f"{tag}_mp": npy(mp), f"{tag}_mn": npy(mn),
+                      f"{tag}_cfg": np.array([float(norm), tau, w]), f"{tag}_loss": npy(loss), f"{tag}_dimg": npy(li.grad),
+                      f"{tag}_dpatch": npy(lp.grad)})
+    pb = RefPirlBank(20, 8, momentum=0.5, num_negatives=5)
+    idx0 = torch.tensor([3, 7, 0, 19, 11])
+    v0, v1 = randn(14, 5, 8, dtype=torch.float32), randn(15, 5, 8, dtype=torch.float32)
+    pb.initialize_vectors(idx0, v0)
+    cases.update(pbank_idx=idx0.numpy(), pbank_v0=npy(v0), pbank_v1=npy(v1), pbank_after_init=npy(pb.bank.clone()))
+    pb.update_vectors(idx0, v1)
+    cases.update(pbank_after_update=npy(pb.bank.clone()), pbank_pos=npy(pb.get_positives(torch.tensor([7, 11]))))
     save("next_rows", **cases)
 
 

@@ -109,6 +109,25 @@ def test_dropin_signatures_match_reference():
     assert [n for n, _ in sig(S.FeatureBank.__init__)][:2] == ["bank_size", "feature_dim"]
     assert sig(S.FeatureBank.add_vectors) == [("fvecs", E)] and sig(S.FeatureBank.return_vectors) == [("device", E)]
     assert sig(S.Prototypes.__init__) == [("hidden_dim", E), ("prototype_size", E)]
+    # utils/losses.py:77,80,94,100; models/pirl.py:24,32,36,40,43
+    assert sig(S.DinoLoss.__init__) == []
+    assert sig(S.DinoLoss.forward) == [("teacher_fvecs", E), ("student_fvecs", E), ("temp_s", E), ("temp_t", E), ("center", E)]
+    assert sig(S.PirlLoss.__init__) == [("normalize", True), ("temperature", 1.0), ("loss_weight", 0.5)]
+    assert sig(S.PirlLoss.forward) == [("img_features", E), ("patch_features", E), ("memory_pos_features", E),
+                                       ("memory_neg_features", E)]
+    assert sig(S.PirlMemoryBank.__init__)[:4] == [("data_size", E), ("feature_size", E), ("momentum", 0.5),
+                                                  ("num_negatives", 1000)]
+    assert sig(S.PirlMemoryBank.initialize_vectors) == [("indices", E), ("vectors", E)]
+    assert sig(S.PirlMemoryBank.update_vectors) == [("indices", E), ("new_vectors", E)]
+    assert sig(S.PirlMemoryBank.get_positives) == [("indices", E)] and sig(S.PirlMemoryBank.get_negatives) == [("exclude_idx", E)]
+    # multi-GPU variants keep the single-GPU ctor kwargs in front
+    from ssv_b200 import dist as D
+    assert sig(D.DistributedSimclrLoss.__init__)[:2] == [("normalize", False), ("temperature", 1.0)]
+    assert sig(D.DistributedBarlowLoss.__init__)[:2] == [("normalize", True), ("off_diagonal_weight", 0.005)]
+    assert sig(D.DistributedSwavLoss.__init__)[:3] == [("temperature", 0.1), ("sinkhorn_eps", 0.05), ("sinkhorn_iters", 3)]
+    assert sig(D.DistributedMocoLoss.__init__)[:2] == [("normalize", True), ("temperature", 1.0)]
+    assert sig(D.DistributedMocoLoss.forward) == [("query", E), ("keys", E), ("memory_vectors", E)]
+    assert sig(D.ShardedMemoryBank.add_batch) == [("batch", E)] and sig(D.ShardedMemoryBank.get_vectors) == []
     # config-splat construction as in models/simclr.py:58 etc.
     S.SimclrLoss(**{"normalize": True, "temperature": 0.5})
     S.SwavLoss(**{"temperature": 0.1, "sinkhorn_eps": 0.05, "sinkhorn_iters": 3})

@@ -86,3 +86,58 @@ def test_momentum_update_modules(S):
     S.momentum_update(a, b, 0.9)
     for p, r, q in zip(a.parameters(), ref, b.parameters()):
         assert torch.equal(p.data, 0.9 * r + (1.0 - 0.9) * q.data)
+
+
+# ------------------------------------------------------------------------------------------------ PIRL
+@pytest.mark.parametrize("tag", ["pa", "pb", "pc"])
+def test_pirl_golden(S, tag):
+    g = load_golden("next_rows")
+    norm, tau, w = bool(g[f"{tag}_cfg"][0]), float(g[f"{tag}_cfg"][1]), float(g[f"{tag}_cfg"][2])
+    img, patch = dev(g[f"{tag}_img"]), dev(g[f"{tag}_patch"])
+    loss = S.PirlLoss(norm, tau, w)(img, patch, dev(g[f"{tag}_mp"], False), dev(g[f"{tag}_mn"], False))
+    loss.backward()
+    # "pa" is d = 8 at tau = 0.07: 8-term dot products of bf16-rounded rows do not average the rounding error (measured
+    # 1.3e-2); north_star's tolerance is stated for its shapes (d = 128: 2e-3 in test_pirl_oracle), so this tiny fixture
+    # gets 2e-2 explicitly instead of a quiet change of the fixture
+    check(loss.item(), [img.grad, patch.grad], float(g[f"{tag}_loss"]), [g[f"{tag}_dimg"], g[f"{tag}_dpatch"]], f"pirl[{tag}]",
+          grad_tol=2e-2 if tag == "pa" else 1e-2)
+
+
+@pytest.mark.parametrize("n,k,d,tau,w", [(256, 1000, 128, 0.07, 0.5), (100, 4100, 64, 0.2, 0.3), (300, 65536, 128, 0.07, 0.5)])
+def test_pirl_oracle(S, n, k, d, tau, w):
+    def unit(x):
+        return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+    img, patch = randn(0, n, d), randn(1, n, d)
+    mp = (0.6 * unit(img) + 0.4 * unit(randn(2, n, d))).astype(np.float32)   # EMA-like rows: near unit norm, not exactly
+    mn = unit(randn(3, k, d))
+    ref = O.pirl(img, patch, mp, mn, True, tau, w)
+    a, b = dev(img), dev(patch)
+    loss = S.PirlLoss(True, tau, w)(a, b, dev(mp, False), dev(mn, False))
+    loss.backward()
+    check(loss.item(), [a.grad, b.grad], ref[0], ref[1:], f"pirl n={n} k={k}")
+
+
+def test_pirl_memory_bank(S):
+    g = load_golden("next_rows")
+    pb = S.PirlMemoryBank(20, 8, momentum=0.5, num_negatives=5)
+    pb.initialize_vectors(torch.from_numpy(g["pbank_idx"]), torch.from_numpy(g["pbank_v0"]))
+    np.testing.assert_allclose(pb.bank.cpu().numpy(), g["pbank_after_init"], rtol=3e-7, atol=0)
+    assert ((pb.bank.cpu().numpy() == 0) == (g["pbank_after_init"] == 0)).all()      # untouched rows stay zero
+    pb.update_vectors(torch.from_numpy(g["pbank_idx"]), torch.from_numpy(g["pbank_v1"]).cuda())
+    np.testing.assert_allclose(pb.bank.cpu().numpy(), g["pbank_after_update"], rtol=3e-7, atol=0)
+    pos = pb.get_positives(torch.tensor([7, 11]))
+    assert torch.equal(pos, pb.bank[[7, 11]])
+    torch.manual_seed(5)
+    neg = pb.get_negatives(torch.tensor([3, 7]))
+    torch.manual_seed(5)
+    ref_idx = torch.tensor([i for i in torch.randperm(20) if i not in torch.tensor([3, 7])]).long()[:5]
+    assert torch.equal(neg, pb.bank[ref_idx.cuda()]), "negative selection must follow the reference's host RNG bookkeeping"
+    # larger bank vs the fp32 oracle
+    big = S.PirlMemoryBank(5000, 128, momentum=0.5)
+    idx = torch.randperm(5000)[:512]
+    v0, v1 = randn(7, 512, 128), randn(8, 512, 128)
+    big.initialize_vectors(idx, torch.from_numpy(v0))
+    big.update_vectors(idx, torch.from_numpy(v1))
+    ref = O.pirl_bank_update(O.pirl_bank_update(np.zeros((5000, 128), np.float32), idx.numpy(), v0), idx.numpy(), v1, 0.5)
+    # (m*a + (1-m)*b cancels for opposite-sign entries: the 1-ulp difference of the two normalisations is absolute)
+    np.testing.assert_allclose(big.bank.cpu().numpy(), ref, rtol=1e-6, atol=2e-7)

@@ -120,3 +120,22 @@ def test_ema_and_center_oracle_bit_exact_vs_reference():
     np.testing.assert_allclose(c0, g["center0"], rtol=2e-6, atol=1e-7)  # torch / numpy sum the 24 rows in different orders
     c1 = O.dino_center_update(g["center0"], g["center_rows1"], float(g["center_m"]))
     np.testing.assert_allclose(c1, g["center1"], rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag", ["pa", "pb", "pc"])
+def test_pirl_oracle_vs_reference(tag):
+    g = load_golden("next_rows")
+    norm, tau, w = bool(g[f"{tag}_cfg"][0]), float(g[f"{tag}_cfg"][1]), float(g[f"{tag}_cfg"][2])
+    loss, dimg, dpatch = O.pirl(g[f"{tag}_img"], g[f"{tag}_patch"], g[f"{tag}_mp"], g[f"{tag}_mn"], norm, tau, w)
+    assert rel_scalar(loss, float(g[f"{tag}_loss"])) < TOL64
+    assert rel_l2(dimg, g[f"{tag}_dimg"]) < TOL64
+    assert rel_l2(dpatch, g[f"{tag}_dpatch"]) < TOL64
+
+
+def test_pirl_bank_oracle_vs_reference():
+    g = load_golden("next_rows")
+    bank = O.pirl_bank_update(np.zeros((20, 8), np.float32), g["pbank_idx"], g["pbank_v0"])
+    np.testing.assert_allclose(bank, g["pbank_after_init"], rtol=3e-7, atol=0)
+    bank2 = O.pirl_bank_update(g["pbank_after_init"], g["pbank_idx"], g["pbank_v1"], 0.5)
+    np.testing.assert_allclose(bank2, g["pbank_after_update"], rtol=3e-7, atol=0)
+    assert np.array_equal(g["pbank_pos"], g["pbank_after_update"][[7, 11]])
