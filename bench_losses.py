@@ -99,7 +99,9 @@ def main():
     ap.add_argument("--cpu", action="store_true")
     args = ap.parse_args()
     import ssv_b200 as S
-    from oracle import ssl_oracle as O
+    O = None
+    if args.cpu:  # the oracle is test / baseline infrastructure: only the --cpu leg may load it
+        from oracle import ssl_oracle as O
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
