@@ -58,6 +58,13 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return SSVB_ERR_DRIVER;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return SSVB_ERR_ALIGNMENT;
+  // the driver call needs a context bound to THIS thread; autograd's backward thread may not have touched the runtime
+  // yet.  cudaFree(0) binds the primary context of the current device (once per thread; the retry below stays as a net).
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
