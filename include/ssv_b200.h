@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SSVB_VERSION 100
+#define SSVB_VERSION 110 /* 110: multi-GPU stage entry points, next rows (EMA, DINO, PIRL) */
 
 enum {
   SSVB_OK = 0,

@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported(cabi):
 
 def test_version_and_error_strings(cabi):
     L = cabi.lib()
-    assert L.ssvb_version() == 100
+    assert L.ssvb_version() == 110
     assert cabi.strerror(0) == "ok"
     for rc in (-1, -2, -3, -4, -5, -6):
         assert "ssv_b200" in cabi.strerror(rc)
