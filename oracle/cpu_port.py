@@ -51,11 +51,12 @@ def time_ntxent_sample(n: int, d: int, temperature: float, rows: int, reps: int 
     for it in range(reps + 1):  # first pass is the warm-up
         t0 = time.perf_counter()
         zhat = torch.nn.functional.normalize(torch.cat([zi, zj]), dim=-1)   # (:20-25)
-        loss_sum, d_rows, d_cols = ntxent_row_slab(zhat, n, 0, rows, temperature)
-        d_cols[:rows] += d_rows
+        r0 = ((max(it - 1, 0)) * rows) % (m - rows + 1) if m > rows else 0   # a different slab of rows every repetition
+        loss_sum, d_rows, d_cols = ntxent_row_slab(zhat, n, r0, rows, temperature)
+        d_cols[r0:r0 + rows] += d_rows
         float(loss_sum)
         if it > 0 or reps == 0:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
     return {"seconds": sec, "samples_per_s": (n * rows / m) / sec, "threads": torch.get_num_threads(),
-            "rows": rows, "m": m}
+            "rows": rows, "m": m, "reps": len(times), "total_seconds": sum(times)}
