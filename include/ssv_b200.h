@@ -88,7 +88,7 @@ int64_t ssvb_ntxent_dpad(int64_t d);                 /* padded feature dim of zh
 int64_t ssvb_ntxent_mpad(int64_t n_global);          /* padded row count of zhat_all (n_global = world*L) */
 size_t ssvb_ntxent_dist_workspace_bytes(int64_t world, int64_t n_local, int64_t d);
 int ssvb_ntxent_dist_prep(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
-                          int64_t ld_zj, int normalize, int64_t world, int64_t rank,
+                          int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
                           void* zhat_all /* bf16 [mpad x dpad] */, float* inv_norm_local /* [2L] */,
                           float* pos_local /* [2L] */, void* stream);
 int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
@@ -100,7 +100,8 @@ int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t world, int64_t rank,
  * this rank's [lse | term] block into slot `rank` of every rank's [world][2][2L] buffer.  The caller separates the
  * stages with a barrier on the same peer group.  dist_loss sums the gathered per-row terms into the global loss. */
 int ssvb_ntxent_dist_prep_push(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
-                               int64_t ld_zj, int normalize, int64_t world, int64_t rank, void* const* peer_zhat,
+                               int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
+                               void* const* peer_zhat,
                                float* inv_norm_local, float* pos_local, void* stream);
 int ssvb_ntxent_dist_rows_fwd_push(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
                                    int normalize, float temperature, const float* pos_local,

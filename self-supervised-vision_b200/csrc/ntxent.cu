@@ -17,7 +17,10 @@ struct NtxPlan {
   int64_t n_glob, m, mpad, d, dpad;
   int mode;
   int normalize;
-  float c, shift;
+  float c, shift;   // what the kernels apply to the accumulator: x = s * c - shift
+  float prescale;   // what pair_prep multiplies the staged rows with
+  float wscale;     // FIXED mode: backward weights carry this power of two (fp16 normal range), undone in grad_finish
+  float pos_c;      // log2-domain positive logit = pos * pos_c
 };
 
 int make_plan(NtxPlan& pl, int64_t n_glob, int64_t d, int normalize, float temperature) {
@@ -31,11 +34,32 @@ int make_plan(NtxPlan& pl, int64_t n_glob, int64_t d, int normalize, float tempe
   pl.d = d;
   pl.dpad = sim_dpad(d);
   pl.normalize = normalize ? 1 : 0;
-  pl.c = SSVB_LOG2E / temperature;
-  pl.shift = pl.c;
-  // unit-norm rows bound |s| <= 1/tau: a constant shift replaces the running max as long as
-  // exp2(-2c) stays far from fp32 underflow (tau >= ~0.045); otherwise (or for raw inputs) online max.
-  pl.mode = (normalize && 2.f * pl.c <= 64.f) ? SIM_NTX_FIXED : SIM_NTX_ONLINE;
+  const float c = SSVB_LOG2E / temperature;
+  // unit-norm rows bound |s| <= 1/tau, i.e. the log2-domain logits lie in [-c, c]: for c <= 32 (tau >= ~0.045)
+  // exp2 needs neither a running max nor a shift (sums stay below 2^(32+30)); otherwise (or for raw inputs) online max.
+  pl.mode = (normalize && 2.f * c <= 64.f) ? SIM_NTX_FIXED : SIM_NTX_ONLINE;
+  if (pl.mode == SIM_NTX_FIXED) {
+    // the staged fp16 rows are pre-scaled by sqrt(c): the tensor-core accumulator IS the log2-domain logit and the
+    // exp loops carry no scale/shift instruction.
+    pl.prescale = sqrtf(c);
+    pl.c = 1.f;
+    pl.shift = 0.f;
+    pl.pos_c = 1.f;
+    // W_ab = P_ab + P_ba is ~2/M: below fp16's normal range for M > 2^15.  Carry 2^k with k = floor(log2 M) - 4
+    // (typical W -> 2^-3, largest possible W = 2 -> 2^(k+1) <= 32768 < 65504).
+    int k = 0;
+    while ((int64_t{2} << k) <= pl.m) ++k;  // k = floor(log2 M)
+    k -= 4;
+    if (k < 0) k = 0;
+    if (k > 14) k = 14;
+    pl.wscale = static_cast<float>(1 << k);
+  } else {
+    pl.prescale = 1.f;
+    pl.c = c;
+    pl.shift = c;
+    pl.pos_c = c;
+    pl.wscale = 1.f;
+  }
   return SSVB_OK;
 }
 
@@ -93,7 +117,9 @@ __global__ void ntx_grad_finish_kernel(const float* __restrict__ zi, const float
                                        const __nv_bfloat16* __restrict__ zhat, int dpad,
                                        const float* __restrict__ inv_norm, int normalize, float inv_m_tau,
                                        const float* __restrict__ grad_out, float* __restrict__ dzi,
-                                       float* __restrict__ dzj, int64_t ld_dzi, int64_t ld_dzj) {
+                                       float* __restrict__ dzj, int64_t ld_dzi, int64_t ld_dzj,
+                                       float acc_scale, float zp_scale) {
+  // acc_scale / zp_scale undo the staging scales: dacc = wscale * prescale * sum_b W_ab zh_b, staged rows = prescale * zh
   const int lrow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (lrow >= 2 * n_view) return;
   const int view = lrow >= n_view;
@@ -111,10 +137,11 @@ __global__ void ntx_grad_finish_kernel(const float* __restrict__ zi, const float
     const uint2 pz = *reinterpret_cast<const uint2*>(zhat + static_cast<int64_t>(partner) * dpad + k);
     const float2 p01 = unpack_h2(pz.x, normalize != 0), p23 = unpack_h2(pz.y, normalize != 0);  // fp16 iff normalised
     const float4 zz = *reinterpret_cast<const float4*>(z + k);
-    g[0] = (acc.x - 2.f * p01.x) * scale;
-    g[1] = (acc.y - 2.f * p01.y) * scale;
-    g[2] = (acc.z - 2.f * p23.x) * scale;
-    g[3] = (acc.w - 2.f * p23.y) * scale;
+    const float za = -2.f * zp_scale;
+    g[0] = fmaf(acc.x, acc_scale, za * p01.x) * scale;
+    g[1] = fmaf(acc.y, acc_scale, za * p01.y) * scale;
+    g[2] = fmaf(acc.z, acc_scale, za * p23.x) * scale;
+    g[3] = fmaf(acc.w, acc_scale, za * p23.y) * scale;
     zh[0] = zz.x * inv; zh[1] = zz.y * inv; zh[2] = zz.z * inv; zh[3] = zz.w * inv;
   }
   if (normalize) {
@@ -185,7 +212,7 @@ int ssvb_ntxent_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
     pair_prep_kernel<<<static_cast<unsigned>(ceil_div(n, wpb)), wpb * 32, 0, s>>>(
         zi, zj, static_cast<int>(n), static_cast<int>(d), ld_zi, ld_zj, normalize, normalize ? 1 : 0, sv.zhat,
         sv.zhat + n * pl.dpad,
-        static_cast<int>(pl.dpad), sv.inv_norm, sv.inv_norm + n, ws.pos, ws.pos + n);
+        static_cast<int>(pl.dpad), sv.inv_norm, sv.inv_norm + n, ws.pos, ws.pos + n, -1, pl.prescale);
     SSVB_LAUNCH_CHECK();
   }
   SimParams p;
@@ -204,7 +231,8 @@ int ssvb_ntxent_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
     if (pl.mode == SIM_NTX_FIXED)
       lse_finalize_kernel<SIM_NTX_FIXED><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride,
                                                             static_cast<int>(pl.m), ws.pos, pl.c, pl.shift,
-                                                            sv.stat, nullptr, ws.block_sums, ws.counter, scale, loss);
+                                                            sv.stat, nullptr, ws.block_sums, ws.counter, scale, loss,
+                                                            nullptr, nullptr, 0, 0, pl.wscale);
     else
       lse_finalize_kernel<SIM_NTX_ONLINE><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride,
                                                              static_cast<int>(pl.m), ws.pos, pl.c, pl.shift,
@@ -255,7 +283,8 @@ int ssvb_ntxent_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
     ntx_grad_finish_kernel<<<static_cast<unsigned>(ceil_div(pl.m, wpb)), wpb * 32, 0, s>>>(
         zi, zj, ld_zi, ld_zj, static_cast<int>(n), static_cast<int>(d), 0, ws.dacc,
         static_cast<int>(pl.dpad), sv.zhat, static_cast<int>(pl.dpad), sv.inv_norm, normalize,
-        1.f / (static_cast<float>(pl.m) * temperature), grad_out, dzi, dzj, ld_dzi, ld_dzj);
+        1.f / (static_cast<float>(pl.m) * temperature), grad_out, dzi, dzj, ld_dzi, ld_dzj,
+        1.f / (pl.wscale * pl.prescale), 1.f / pl.prescale);
     SSVB_LAUNCH_CHECK();
   }
   return SSVB_OK;
@@ -278,12 +307,12 @@ int dist_check(int64_t world, int64_t rank, int64_t n_local) {
 }  // namespace
 
 int ssvb_ntxent_dist_prep(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
-                          int64_t ld_zj, int normalize, int64_t world, int64_t rank, void* zhat_all,
-                          float* inv_norm_local, float* pos_local, void* stream) {
+                          int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
+                          void* zhat_all, float* inv_norm_local, float* pos_local, void* stream) {
   SSVB_TRY(check_device_sm100());
   SSVB_TRY(dist_check(world, rank, n_local));
   NtxPlan pl;
-  SSVB_TRY(make_plan(pl, n_local * world, d, normalize, 1.f));
+  SSVB_TRY(make_plan(pl, n_local * world, d, normalize, temperature));
   SSVB_TRY(check_rows(zi, ld_zi));
   SSVB_TRY(check_rows(zj, ld_zj));
   if (!zhat_all || !inv_norm_local || !pos_local) return SSVB_ERR_INVALID;
@@ -297,7 +326,7 @@ int ssvb_ntxent_dist_prep(const float* zi, const float* zj, int64_t n_local, int
       zi, zj, static_cast<int>(n_local), static_cast<int>(d), ld_zi, ld_zj, normalize, normalize ? 1 : 0,
       zh + row0 * pl.dpad,
       zh + (row0 + n_local) * pl.dpad, static_cast<int>(pl.dpad), inv_norm_local, inv_norm_local + n_local,
-      pos_local, pos_local + n_local);
+      pos_local, pos_local + n_local, -1, pl.prescale);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
@@ -370,12 +399,12 @@ int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_l
 // Fused normalise + all-gather: like dist_prep, but every bf16 row goes to the same slot of EVERY rank's gathered
 // matrix through `peer_zhat` (a DEVICE array of `world` peer-mapped base pointers, e.g. torch symmetric memory).
 int ssvb_ntxent_dist_prep_push(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
-                               int64_t ld_zj, int normalize, int64_t world, int64_t rank, void* const* peer_zhat,
-                               float* inv_norm_local, float* pos_local, void* stream) {
+                               int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
+                               void* const* peer_zhat, float* inv_norm_local, float* pos_local, void* stream) {
   SSVB_TRY(check_device_sm100());
   SSVB_TRY(dist_check(world, rank, n_local));
   NtxPlan pl;
-  SSVB_TRY(make_plan(pl, n_local * world, d, normalize, 1.f));
+  SSVB_TRY(make_plan(pl, n_local * world, d, normalize, temperature));
   SSVB_TRY(check_rows(zi, ld_zi));
   SSVB_TRY(check_rows(zj, ld_zj));
   if (!peer_zhat || !inv_norm_local || !pos_local) return SSVB_ERR_INVALID;
@@ -384,7 +413,7 @@ int ssvb_ntxent_dist_prep_push(const float* zi, const float* zj, int64_t n_local
   pair_prep_push_kernel<<<static_cast<unsigned>(ceil_div(n_local, 8)), 256, 0, s>>>(
       zi, zj, static_cast<int>(n_local), static_cast<int>(d), ld_zi, ld_zj, normalize, normalize ? 1 : 0, peer_zhat,
       static_cast<int>(world), row0, row0 + n_local, static_cast<int>(pl.dpad), inv_norm_local,
-      inv_norm_local + n_local, pos_local, pos_local + n_local);
+      inv_norm_local + n_local, pos_local, pos_local + n_local, pl.prescale);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
@@ -433,13 +462,13 @@ namespace {
 // lse2 (all rows) -> the column statistic the backward kernel consumes, with finite padding
 // gathered layout: [world][2][2L] (per rank: 2L lse2 values, then 2L per-row loss terms)
 __global__ void dist_stat_kernel(const float* __restrict__ gathered, float* __restrict__ stat, int m, int mpad, int lr,
-                                 int fixed, float shift) {
+                                 int fixed, float shift, float wscale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= mpad) return;
   if (i < m) {
     const int r = i / lr;
     const float l2 = gathered[static_cast<size_t>(r) * 2 * lr + (i - r * lr)];
-    stat[i] = fixed ? exp2f(shift - l2) : l2;
+    stat[i] = fixed ? wscale * exp2f(shift - l2) : l2;
   } else {
     stat[i] = fixed ? 0.f : 1e30f;
   }
@@ -467,7 +496,7 @@ int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local,
   // column statistics for all M rows live in the (otherwise unused here) partial buffer
   float* stat = ws.part_m;
   dist_stat_kernel<<<static_cast<unsigned>(ceil_div(pl.mpad, 256)), 256, 0, s>>>(
-      stat_all, stat, static_cast<int>(pl.m), static_cast<int>(pl.mpad), static_cast<int>(lr), pl.mode == SIM_NTX_FIXED, pl.shift);
+      stat_all, stat, static_cast<int>(pl.m), static_cast<int>(pl.mpad), static_cast<int>(lr), pl.mode == SIM_NTX_FIXED, pl.shift, pl.wscale);
   SSVB_LAUNCH_CHECK();
 
   SimParams p;
@@ -484,7 +513,8 @@ int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local,
   ntx_grad_finish_kernel<<<static_cast<unsigned>(ceil_div(lr, wpb)), wpb * 32, 0, s>>>(
       zi, zj, ld_zi, ld_zj, static_cast<int>(n_local), static_cast<int>(d), static_cast<int>(rank * lr), ws.dacc,
       static_cast<int>(pl.dpad), static_cast<const __nv_bfloat16*>(zhat_all), static_cast<int>(pl.dpad),
-      inv_norm_local, normalize, 1.f / (static_cast<float>(pl.m) * temperature), grad_out, dzi, dzj, ld_dzi, ld_dzj);
+      inv_norm_local, normalize, 1.f / (static_cast<float>(pl.m) * temperature), grad_out, dzi, dzj, ld_dzi, ld_dzj,
+        1.f / (pl.wscale * pl.prescale), 1.f / pl.prescale);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }

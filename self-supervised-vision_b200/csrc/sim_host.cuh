@@ -118,7 +118,9 @@ static __global__ void pair_prep_kernel(const float* __restrict__ xi, const floa
                                  int64_t ldi, int64_t ldj, int normalize, int f16, __nv_bfloat16* __restrict__ out_i,
                                  __nv_bfloat16* __restrict__ out_j, int dpad, float* __restrict__ inv_i,
                                  float* __restrict__ inv_j, float* __restrict__ pos_i, float* __restrict__ pos_j,
-                                 int norm_mask = -1 /* >= 0: bit 0 normalises xi, bit 1 xj (overrides `normalize`) */) {
+                                 int norm_mask = -1 /* >= 0: bit 0 normalises xi, bit 1 xj (overrides `normalize`) */,
+                                 float prescale = 1.f /* staged rows = x_hat * prescale (NT-Xent FIXED mode:
+                                 sqrt(log2(e)/tau), so the tensor-core accumulator is the log2-domain logit) */) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n) return;
   const float* ri = xi + static_cast<int64_t>(warp) * ldi;
@@ -145,15 +147,16 @@ static __global__ void pair_prep_kernel(const float* __restrict__ xi, const floa
   if (nmask & 1) ivi = 1.f / fmaxf(sqrtf(si), 1e-12f);
   if (nmask & 2) ivj = 1.f / fmaxf(sqrtf(sj), 1e-12f);
   float dot = 0.f;
+  const float si_ = ivi * prescale, sj_ = ivj * prescale;  // inv_norm outputs stay the plain 1/||x||
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
     const int k = it * 128 + lane * 4;
     if (k < dpad) {
       uint2 vi, vj;
-      vi.x = f16 ? pack_f16x2(a[it].x * ivi, a[it].y * ivi) : pack_bf16x2(a[it].x * ivi, a[it].y * ivi);
-      vi.y = f16 ? pack_f16x2(a[it].z * ivi, a[it].w * ivi) : pack_bf16x2(a[it].z * ivi, a[it].w * ivi);
-      vj.x = f16 ? pack_f16x2(b[it].x * ivj, b[it].y * ivj) : pack_bf16x2(b[it].x * ivj, b[it].y * ivj);
-      vj.y = f16 ? pack_f16x2(b[it].z * ivj, b[it].w * ivj) : pack_bf16x2(b[it].z * ivj, b[it].w * ivj);
+      vi.x = f16 ? pack_f16x2(a[it].x * si_, a[it].y * si_) : pack_bf16x2(a[it].x * si_, a[it].y * si_);
+      vi.y = f16 ? pack_f16x2(a[it].z * si_, a[it].w * si_) : pack_bf16x2(a[it].z * si_, a[it].w * si_);
+      vj.x = f16 ? pack_f16x2(b[it].x * sj_, b[it].y * sj_) : pack_bf16x2(b[it].x * sj_, b[it].y * sj_);
+      vj.y = f16 ? pack_f16x2(b[it].z * sj_, b[it].w * sj_) : pack_bf16x2(b[it].z * sj_, b[it].w * sj_);
       const float2 fi01 = unpack_h2(vi.x, f16), fi23 = unpack_h2(vi.y, f16);
       const float2 fj01 = unpack_h2(vj.x, f16), fj23 = unpack_h2(vj.y, f16);
       dot += fi01.x * fj01.x + fi01.y * fj01.y + fi23.x * fj23.x + fi23.y * fj23.y;
@@ -177,7 +180,8 @@ static __global__ void pair_prep_push_kernel(const float* __restrict__ xi, const
                                              void* const* __restrict__ peers,
                                              int world, int64_t row_i, int64_t row_j, int dpad,
                                              float* __restrict__ inv_i, float* __restrict__ inv_j,
-                                             float* __restrict__ pos_i, float* __restrict__ pos_j) {
+                                             float* __restrict__ pos_i, float* __restrict__ pos_j,
+                                             float prescale = 1.f) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n) return;
   const float* ri = xi + static_cast<int64_t>(warp) * ldi;
@@ -196,10 +200,11 @@ static __global__ void pair_prep_push_kernel(const float* __restrict__ xi, const
     ivj = 1.f / fmaxf(sqrtf(sj), 1e-12f);
   }
   uint2 vi, vj;
-  vi.x = f16 ? pack_f16x2(a.x * ivi, a.y * ivi) : pack_bf16x2(a.x * ivi, a.y * ivi);
-  vi.y = f16 ? pack_f16x2(a.z * ivi, a.w * ivi) : pack_bf16x2(a.z * ivi, a.w * ivi);
-  vj.x = f16 ? pack_f16x2(b.x * ivj, b.y * ivj) : pack_bf16x2(b.x * ivj, b.y * ivj);
-  vj.y = f16 ? pack_f16x2(b.z * ivj, b.w * ivj) : pack_bf16x2(b.z * ivj, b.w * ivj);
+  const float si_ = ivi * prescale, sj_ = ivj * prescale;
+  vi.x = f16 ? pack_f16x2(a.x * si_, a.y * si_) : pack_bf16x2(a.x * si_, a.y * si_);
+  vi.y = f16 ? pack_f16x2(a.z * si_, a.w * si_) : pack_bf16x2(a.z * si_, a.w * si_);
+  vj.x = f16 ? pack_f16x2(b.x * sj_, b.y * sj_) : pack_bf16x2(b.x * sj_, b.y * sj_);
+  vj.y = f16 ? pack_f16x2(b.z * sj_, b.w * sj_) : pack_bf16x2(b.z * sj_, b.w * sj_);
   const float2 fi01 = unpack_h2(vi.x, f16), fi23 = unpack_h2(vi.y, f16);
   const float2 fj01 = unpack_h2(vj.x, f16), fj23 = unpack_h2(vj.y, f16);
   float dot = warp_sum(fi01.x * fj01.x + fi01.y * fj01.y + fi23.x * fj23.x + fi23.y * fj23.y);
@@ -272,7 +277,7 @@ __global__ void lse_finalize_kernel(const float* __restrict__ part_m, const floa
                                     float* __restrict__ stat, float* __restrict__ lse2_out,
                                     float* block_sums, unsigned int* counter, float loss_scale, float* loss,
                                     float* __restrict__ term_out = nullptr, float* const* __restrict__ peer_stat = nullptr,
-                                    int world = 0, size_t peer_off = 0) {
+                                    int world = 0, size_t peer_off = 0, float wscale = 1.f) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   float term = 0.f;
   if (r < nrows) {
@@ -282,7 +287,7 @@ __global__ void lse_finalize_kernel(const float* __restrict__ part_m, const floa
       float L = 0.f;
       for (int i = 0; i < nparts; ++i) L += part_l[static_cast<size_t>(i) * stride + r];
       lse2 = shift + log2f(L);
-      st = 1.f / L;
+      st = wscale / L;  // backward weight W = e^s (st_a + st_b): wscale = 2^k keeps W in fp16's normal range
     } else {
       float M = (MODE == SIM_MOCO) ? p2 : -1e30f;
       for (int i = 0; i < nparts; ++i) M = fmaxf(M, part_m[static_cast<size_t>(i) * stride + r]);

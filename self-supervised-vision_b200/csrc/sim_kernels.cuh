@@ -87,15 +87,47 @@ __device__ __forceinline__ UnitInfo decode_unit(const SimParams& p, int u) {
 #endif
 
 __device__ __forceinline__ float ex2_poly3(float x);
-// ---- timing-experiment knobs (tests/ab_bench.sh): each one REMOVES a piece of work, results become wrong ----
+// ---- timing-experiment knobs (tools/ab_bench.sh): each one REMOVES a piece of work, results become wrong ----
 #ifdef SSVB_DBG_NOEXP
 #define SSVB_EX2(x) (x)
 #else
 #define SSVB_EX2(x) ex2f(x)
 #endif
 #ifndef SSVB_POLY_MOD_FWD
-#define SSVB_POLY_MOD_FWD 3
+#define SSVB_POLY_MOD_FWD 3   // masked (rare) tiles only: every 3rd element on the scalar polynomial
 #endif
+// FIXED mode hot loops: one PAIR of every SSVB_POLY_PAIR_* pairs takes the packed polynomial exp2 (0 = none)
+#ifndef SSVB_POLY_PAIR_FWD
+#define SSVB_POLY_PAIR_FWD 2
+#endif
+#ifndef SSVB_POLY_PAIR_BWD
+#define SSVB_POLY_PAIR_BWD 0
+#endif
+
+// exp2 of two values on the FMA pipe with packed instructions (Cody-Waite split + degree-3 minimax, max rel. error
+// 7.5e-5): 6 FADD2/FFMA2 + 2 IMAD per pair = 4 issue slots per element and no MUFU slot.  Valid for x > -126.
+__device__ __forceinline__ unsigned long long ex2_poly3_x2(unsigned long long x2) {
+  const unsigned long long magic2 = pack_f32x2(12582912.f, 12582912.f);
+  const unsigned long long nmagic2 = pack_f32x2(-12582912.f, -12582912.f);
+  const unsigned long long r2 = add_f32x2(x2, magic2);      // low mantissa bits = round(x)
+  const unsigned long long t2 = add_f32x2(r2, nmagic2);     // round(x) as a float (exact)
+  const unsigned long long f2 = fma_f32x2(t2, pack_f32x2(-1.f, -1.f), x2);  // f in [-0.5, 0.5]
+  unsigned long long q2 = fma_f32x2(f2, pack_f32x2(5.517166745e-2f, 5.517166745e-2f),
+                                    pack_f32x2(2.426111221e-1f, 2.426111221e-1f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(6.932609858e-1f, 6.932609858e-1f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(9.999280736e-1f, 9.999280736e-1f));
+  float q0, q1, r0, r1;
+  unpack_f32x2(q2, q0, q1);
+  unpack_f32x2(r2, r0, r1);
+  const float e0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+  const float e1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
+  return pack_f32x2(e0, e1);
+}
+// 16-byte shared-memory load from a 32-bit shared address (the generic-pointer form costs two address instructions
+// per load plus a generic->shared window computation per call site)
+__device__ __forceinline__ void lds_v4(uint32_t saddr, unsigned long long& lo, unsigned long long& hi) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(saddr));
+}
 
 // =====================================================================================================
 // forward
@@ -145,19 +177,18 @@ __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int
     }
     const int colbase = j0 + cc * 32;
     if (MODE == SIM_NTX_FIXED && !MASKED) {
-      // packed scale/shift FFMA and packed row-sum FADD: 2 issue slots per element instead of 3
-      const unsigned long long c2 = pack_f32x2(p.c, p.c), ns2 = pack_f32x2(-p.shift, -p.shift);
+      // FIXED mode operands are pre-scaled by sqrt(log2(e)/tau) (pair_prep), so the accumulator IS the log2-domain
+      // logit: no scale/shift FFMA.  Per pair: two MUFU.EX2 or one packed polynomial, one packed row-sum FADD2.
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const unsigned long long x2 =
-            fma_f32x2(pack_f32x2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), c2, ns2);
-        float x0, x1;
-        unpack_f32x2(x2, x0, x1);
-        const bool p0 = SSVB_POLY_MOD_FWD > 0 && ((2 * i) % (SSVB_POLY_MOD_FWD > 0 ? SSVB_POLY_MOD_FWD : 1)) == 1;
-        const bool p1 = SSVB_POLY_MOD_FWD > 0 && ((2 * i + 1) % (SSVB_POLY_MOD_FWD > 0 ? SSVB_POLY_MOD_FWD : 1)) == 1;
-        const float e0 = p0 ? ex2_poly3(x0) : SSVB_EX2(x0);
-        const float e1 = p1 ? ex2_poly3(x1) : SSVB_EX2(x1);
-        l2[i & 1] = add_f32x2(l2[i & 1], pack_f32x2(e0, e1));
+        const bool poly = SSVB_POLY_PAIR_FWD > 0 && (i % (SSVB_POLY_PAIR_FWD > 0 ? SSVB_POLY_PAIR_FWD : 1)) == 1;
+        unsigned long long e2;
+        if (poly) {
+          e2 = ex2_poly3_x2(pack_f32x2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])));
+        } else {
+          e2 = pack_f32x2(SSVB_EX2(__uint_as_float(cur[2 * i])), SSVB_EX2(__uint_as_float(cur[2 * i + 1])));
+        }
+        l2[i & 1] = add_f32x2(l2[i & 1], e2);
       }
     } else if (MODE == SIM_NTX_FIXED) {
 #pragma unroll
@@ -405,29 +436,28 @@ __device__ __forceinline__ float ex2_poly3(float x) {
 // weights of 32 consecutive columns [cb, cb+32) of one row: sv = S values, pk = packed bf16 pairs out
 template <int MODE, bool MASKED, bool OPF16>
 __device__ __forceinline__ void bwd_weights32(const uint32_t (&sv)[32], uint32_t (&pk)[16], const SimParams& p,
-                                              int a_glob, int colbase, float rs, const void* cs32) {
+                                              int a_glob, int colbase, float rs, uint32_t cs32) {
 #ifndef SSVB_BWD_SCALAR_MATH
   if (MODE == SIM_NTX_FIXED && !MASKED) {
-    // issue-bound loop: packed fp32 arithmetic (two elements per FFMA2 / FADD2 / FMUL2), one MUFU per element, one
-    // pack per pair -> 3 issue slots per element instead of 5.  Column factors arrive as fp32 pairs (LDS.128 = 2 pairs).
-    const unsigned long long c2 = pack_f32x2(p.c, p.c), ns2 = pack_f32x2(-p.shift, -p.shift), rs2 = pack_f32x2(rs, rs);
-    const ulonglong2* cw = reinterpret_cast<const ulonglong2*>(cs32);
+    // issue-bound loop.  Operands are pre-scaled (the S accumulator is the log2-domain logit): per pair two MUFU.EX2
+    // (or one packed polynomial), FADD2 (row + column factor), FMUL2, one pack -> 2.5 issue slots per element.
+    // Column factors: fp32 pairs straight from shared memory (LDS.128 = 2 pairs, 32-bit shared address).
+    const unsigned long long rs2 = pack_f32x2(rs, rs);
 #pragma unroll
     for (int i2 = 0; i2 < 8; ++i2) {
-      const ulonglong2 cu = cw[i2];  // column factors of 4 consecutive columns
+      unsigned long long cu[2];  // column factors of 4 consecutive columns
+      lds_v4(cs32 + i2 * 16, cu[0], cu[1]);
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int i = i2 * 2 + e;  // pair index: columns 2i, 2i+1
-        const unsigned long long x2 =
-            fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, ns2);
-        float x0, x1;
-        unpack_f32x2(x2, x0, x1);
-        // a share of the exponentials runs as a polynomial on the FMA pipe (MUFU is the binding pipe of this loop)
-        const bool q0 = SSVB_POLY_MOD_BWD > 0 && ((2 * i) % (SSVB_POLY_MOD_BWD > 0 ? SSVB_POLY_MOD_BWD : 1)) == 1;
-        const bool q1 = SSVB_POLY_MOD_BWD > 0 && ((2 * i + 1) % (SSVB_POLY_MOD_BWD > 0 ? SSVB_POLY_MOD_BWD : 1)) == 1;
-        const float e0 = q0 ? ex2_poly3(x0) : SSVB_EX2(x0);
-        const float e1 = q1 ? ex2_poly3(x1) : SSVB_EX2(x1);
-        const unsigned long long w2 = mul_f32x2(pack_f32x2(e0, e1), add_f32x2(rs2, e ? cu.y : cu.x));
+        const bool poly = SSVB_POLY_PAIR_BWD > 0 && (i % (SSVB_POLY_PAIR_BWD > 0 ? SSVB_POLY_PAIR_BWD : 1)) == 1;
+        unsigned long long e2;
+        if (poly) {
+          e2 = ex2_poly3_x2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])));
+        } else {
+          e2 = pack_f32x2(SSVB_EX2(__uint_as_float(sv[2 * i])), SSVB_EX2(__uint_as_float(sv[2 * i + 1])));
+        }
+        const unsigned long long w2 = mul_f32x2(e2, add_f32x2(rs2, cu[e]));
         float w0, w1;
         unpack_f32x2(w2, w0, w1);
         pk[i] = pack_h2<OPF16>(w0, w1);
@@ -440,8 +470,10 @@ __device__ __forceinline__ void bwd_weights32(const uint32_t (&sv)[32], uint32_t
   for (int i4 = 0; i4 < 8; ++i4) {
     float csv[4] = {0.f, 0.f, 0.f, 0.f};
     if (MODE != SIM_MOCO) {
-      const float4 c4 = reinterpret_cast<const float4*>(cs32)[i4];
-      csv[0] = c4.x; csv[1] = c4.y; csv[2] = c4.z; csv[3] = c4.w;
+      unsigned long long c01, c23;
+      lds_v4(cs32 + i4 * 16, c01, c23);
+      unpack_f32x2(c01, csv[0], csv[1]);
+      unpack_f32x2(c23, csv[2], csv[3]);
     }
     float w[4];
 #pragma unroll
@@ -658,7 +690,7 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int j0 = t * BN + half * 64;
         const bool special = (MODE != SIM_MOCO) && (j0 < ui.g0 + 128) && (j0 + 64 > ui.g0);
         const uint32_t t_w = tmem + tlane + C::T_W + pair * 64 + half * 32;
-        const uint8_t* cs = sC + st * C::CS_BYTES + half * 64 * 4;
+        const uint32_t cs = smem_u32(sC) + st * C::CS_BYTES + half * 64 * 4;
         constexpr int CSTEP = 32 * 4;
         // all 64 weights are computed and packed before waiting for the W buffer (the dZ GEMM of tile t-2 may still
         // be reading it): that wait is off the critical path unless the tensor pipe is the bottleneck

@@ -36,9 +36,10 @@ class CudaStages:
     def mpad(self, n_global):
         return C.cached_size("ssvb_ntxent_mpad", n_global)
 
-    def prep(self, zi, zj, normalize, world, rank, zhat_all, inv_local, pos_local):
+    def prep(self, zi, zj, normalize, temperature, world, rank, zhat_all, inv_local, pos_local):
         n, d = zi.shape
-        C.check(C.lib().ssvb_ntxent_dist_prep(C.ptr(zi), C.ptr(zj), n, d, zi.stride(0), zj.stride(0), normalize, world,
+        C.check(C.lib().ssvb_ntxent_dist_prep(C.ptr(zi), C.ptr(zj), n, d, zi.stride(0), zj.stride(0), normalize,
+                                              temperature, world,
                                               rank, C.ptr(zhat_all), C.ptr(inv_local), C.ptr(pos_local),
                                               C.stream_ptr(zi.device)), "ssvb_ntxent_dist_prep")
 
@@ -64,10 +65,10 @@ class CudaStages:
 
 
     # ---- fused compute + all-gather over NVLink peer memory (no NCCL on the data path)
-    def prep_push(self, zi, zj, normalize, world, rank, peer_zhat_dev, inv_local, pos_local):
+    def prep_push(self, zi, zj, normalize, temperature, world, rank, peer_zhat_dev, inv_local, pos_local):
         n, d = zi.shape
         C.check(C.lib().ssvb_ntxent_dist_prep_push(C.ptr(zi), C.ptr(zj), n, d, zi.stride(0), zj.stride(0), normalize,
-                                                   world, rank, C.c_void_p(peer_zhat_dev), C.ptr(inv_local),
+                                                   temperature, world, rank, C.c_void_p(peer_zhat_dev), C.ptr(inv_local),
                                                    C.ptr(pos_local), C.stream_ptr(zi.device)), "ssvb_ntxent_dist_prep_push")
 
     def rows_fwd_push(self, zhat_all, world, rank, n_local, d, normalize, temperature, pos_local, peer_stat_dev, loss_sum):
@@ -164,7 +165,7 @@ class _NtxentDistFn(torch.autograd.Function):
         if peer is not None:
             zbuf, hz, sbuf, hs = peer.next()
             loss = torch.empty((), dtype=torch.float32, device=dev)
-            stages.prep_push(xi, xj, norm, world, rank, hz.buffer_ptrs_dev, inv_local, pos_local)
+            stages.prep_push(xi, xj, norm, float(temperature), world, rank, hz.buffer_ptrs_dev, inv_local, pos_local)
             hz.barrier()
             # the gathered rows are always copied out (16 MiB, ~10 us): the tensor-core kernels stream them many times and
             # read a peer-mapped (symmetric-memory) buffer 12-15 % slower than ordinary device memory (measured at 2 GPUs)
@@ -185,7 +186,7 @@ class _NtxentDistFn(torch.autograd.Function):
         # per rank: [lse2 (2L) | per-row loss term (2L)] -> one all-gather serves the backward AND the global loss
         stat_all = torch.empty(world, 2, 2 * n, dtype=torch.float32, device=dev)
         loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
-        stages.prep(xi, xj, norm, world, rank, zhat_all, inv_local, pos_local)
+        stages.prep(xi, xj, norm, float(temperature), world, rank, zhat_all, inv_local, pos_local)
         my = slice(rank * 2 * n, (rank + 1) * 2 * n)
         if world > 1:
             _gather_slots(zhat_all[:m], zhat_all[my], group, inplace=cuda)

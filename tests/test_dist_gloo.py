@@ -25,7 +25,7 @@ class EmulatedStages:
     def mpad(self, n_global):
         return 2 * n_global
 
-    def prep(self, zi, zj, normalize, world, rank, zhat_all, inv_local, pos_local):
+    def prep(self, zi, zj, normalize, temperature, world, rank, zhat_all, inv_local, pos_local):
         n = zi.shape[0]
         z = torch.cat([zi, zj]).double()
         den = z.norm(dim=1, keepdim=True).clamp_min(1e-12) if normalize else torch.ones(2 * n, 1, dtype=torch.float64)

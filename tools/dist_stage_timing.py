@@ -44,7 +44,7 @@ def run(names, body):
 
 
 def nccl_body(ev):
-    st.prep(zi, zj, 1, world, rank, zhat, inv, pos); ev[1].record()
+    st.prep(zi, zj, 1, 0.5, world, rank, zhat, inv, pos); ev[1].record()
     _gather_slots(zhat[:m], zhat[my], None, True); ev[2].record()
     st.rows_fwd(zhat, world, rank, n, d, 1, tau, pos, stat[rank], ls); ev[3].record()
     _gather_slots(stat.view(world * 2, 2 * n), stat[rank], None, True); ev[4].record()
@@ -54,7 +54,7 @@ def nccl_body(ev):
 
 def p2p_body(ev):
     zbuf, hz, sbuf, hs = peer.next()
-    st.prep_push(zi, zj, 1, world, rank, hz.buffer_ptrs_dev, inv, pos); ev[1].record()
+    st.prep_push(zi, zj, 1, 0.5, world, rank, hz.buffer_ptrs_dev, inv, pos); ev[1].record()
     hz.barrier(); ev[2].record()
     z = zbuf.view(mpad, dpad).clone()
     st.rows_fwd_push(z, world, rank, n, d, 1, tau, pos, hs.buffer_ptrs_dev, ls); ev[3].record()

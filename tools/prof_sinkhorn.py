@@ -1,4 +1,4 @@
-"""Profiling / timing driver (not a test): Sinkhorn at cfg4.  `python tests/prof_sinkhorn.py time` prints the
+"""Profiling / timing driver (not a test): Sinkhorn at cfg4.  `python tools/prof_sinkhorn.py time` prints the
 CUDA-graph replay time (L2 flushed between replays) of compute_codes_sinkhorn and of the full SwAV loss."""
 import os, sys, statistics
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,5 +1,5 @@
 """compute-sanitizer driver (not a test): every kernel family once on small shapes.
-    compute-sanitizer --tool memcheck python tests/sanitize_small.py"""
+    compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "self-supervised-vision_b200")]
