@@ -104,6 +104,72 @@ def cpu_sample(rows=4096, reps=1):
     return r
 
 
+REF_SAMPLE_N = 4096   # the reference's classes materialise ~14 N^2 floats: N = 32768 needs > 150 GB
+
+
+def reference_step_fn(n):
+    """One fwd+bwd of the UNMODIFIED reference SimclrLoss (utils/losses.py:8-46) at per-view batch n on the host
+    cores, or None when no staged copy of the reference exists (oracle/make_ref.py -> baseline/_ref)."""
+    import torch
+    from oracle import ref_loader
+    R = ref_loader.load()
+    if R is None:
+        return None
+    torch.set_num_threads(os.cpu_count())
+    g = torch.Generator().manual_seed(0)
+    zi = torch.randn(n, DIM, generator=g).requires_grad_(True)
+    zj = torch.randn(n, DIM, generator=g).requires_grad_(True)
+    fn = R.losses.SimclrLoss(True, TAU)
+
+    def step():
+        zi.grad = None
+        zj.grad = None
+        loss = fn(zi, zj)
+        loss.backward()
+        return float(loss)
+    return step
+
+
+def extrapolate(n_sample, sec):
+    """fwd+bwd time grows with N^2 beyond cache (365 ms / 1.365 s at N = 2048 / 4096), so
+    samples/s at N_GLOBAL = (n_sample / sec) * n_sample / N_GLOBAL."""
+    return (n_sample / sec) * n_sample / N_GLOBAL
+
+
+def cpu_baseline_leg():
+    """cpu_baseline of our arm (rank 0, N = 1): the reference's own classes when staged, beside the slab port."""
+    import torch
+    out = {}
+    port = cpu_sample(rows=4096, reps=2)
+    port_d = {"value": port["samples_per_s"], "unit": "samples/s", "cores": port["threads"], "kind": "port",
+              "sample": (f"{port['reps']} row slabs of {port['rows']} of the {port['m']} similarity rows x all columns "
+                         f"(each {port['rows']}/{port['m']} of the full job), torch CPU fp32 closed form fwd+bwd, "
+                         f"{port['seconds']:.2f} s per slab")}
+    series = []
+    for n, reps in ((1024, 3), (4096, 3), (8192, 1)):
+        step = reference_step_fn(n)
+        if step is None:
+            break
+        step()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            step()
+        sec = (time.perf_counter() - t0) / reps
+        series.append({"n": n, "seconds": sec, "samples_per_s": n / sec, "extrapolated_to_32768": extrapolate(n, sec)})
+    if series:
+        last = series[-1]
+        out = {"value": last["extrapolated_to_32768"], "unit": "samples/s", "cores": torch.get_num_threads(),
+               "kind": "reference", "extrapolated": True,
+               "sample": (f"the reference's own SimclrLoss(True, {TAU}) fwd+bwd (utils/losses.py:8-46, unmodified, "
+                          f"baseline/_ref) at N = {last['n']} ({last['seconds']:.2f} s), extrapolated ~N^2 to N = {N_GLOBAL} "
+                          f"because the reference needs > 150 GB of N x N intermediates there"),
+               "series": series, "port": port_d}
+    else:
+        out = dict(port_d)
+        out["note"] = "no staged reference (baseline/_ref): oracle port only"
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -111,17 +177,29 @@ def run_reference(args):
     import torch
     from oracle import cpu_port
     torch.set_num_threads(os.cpu_count())
-    rows = 4096
-    g = torch.Generator().manual_seed(0)
-    zi = torch.randn(N_GLOBAL, DIM, generator=g)
-    zj = torch.randn(N_GLOBAL, DIM, generator=g)
     m = 2 * N_GLOBAL
+    step = reference_step_fn(REF_SAMPLE_N)
+    if step is not None:
+        kind = "reference"
+        sample = (f"each step = one fwd+bwd of the reference's own SimclrLoss(True, {TAU}) (utils/losses.py:8-46, "
+                  f"unmodified copy in baseline/_ref) at N = {REF_SAMPLE_N} on the host cores; value extrapolated ~N^2 to "
+                  f"N = {N_GLOBAL} (the reference cannot run that size: > 150 GB of N x N intermediates)")
+        to_value = lambda dt: extrapolate(REF_SAMPLE_N, dt)  # noqa: E731
+    else:
+        kind = "port"
+        rows = 4096
+        g = torch.Generator().manual_seed(0)
+        zi = torch.randn(N_GLOBAL, DIM, generator=g)
+        zj = torch.randn(N_GLOBAL, DIM, generator=g)
 
-    def step():
-        zhat = torch.nn.functional.normalize(torch.cat([zi, zj]), dim=-1)
-        loss_sum, d_rows, d_cols = cpu_port.ntxent_row_slab(zhat, N_GLOBAL, 0, rows, TAU)
-        d_cols[:rows] += d_rows
-        return float(loss_sum)
+        def step():
+            zhat = torch.nn.functional.normalize(torch.cat([zi, zj]), dim=-1)
+            loss_sum, d_rows, d_cols = cpu_port.ntxent_row_slab(zhat, N_GLOBAL, 0, rows, TAU)
+            d_cols[:rows] += d_rows
+            return float(loss_sum)
+        sample = (f"row slab: {rows} of the {m} similarity rows x all {m} columns per step (= {rows}/{m} of the full "
+                  f"6*M^2*d job), torch CPU fp32, fwd + both gradient GEMMs (no staged reference found)")
+        to_value = lambda dt: (N_GLOBAL * rows / m) / dt  # noqa: E731
 
     for _ in range(args.warmup):
         step()
@@ -129,17 +207,73 @@ def run_reference(args):
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    value = (N_GLOBAL * rows / m) / dt
-    sample = (f"row slab: {rows} of the {m} similarity rows x all {m} columns per step (= {rows}/{m} of the full "
-              f"6*M^2*d job), torch CPU fp32, fwd + both gradient GEMMs")
+    value = to_value(dt)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": N_GLOBAL, "dim": DIM},
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+                             "extrapolated": kind == "reference", "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- parity witness
+def parity_witness(zi, zj, dzi, loss_value, world, rank, dist_mod, rows=4096, tau=TAU, dzj=None):
+    """Loss and gradient of the global batch from a chunked fp32 closed form on the GPU (plain torch.matmul, TF32
+    off; reference math utils/losses.py:15-46 restated as in SURVEY.md §8 a1), compared with what the kernels
+    produced: the global loss, and the gradient of this rank's first `rows` rows of view i.  Runs once, outside the
+    timed region; max over ranks."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = zi.device
+    n_local = zi.shape[0]
+    with torch.no_grad():
+        if world > 1:
+            gi = [torch.empty_like(zi) for _ in range(world)]
+            gj = [torch.empty_like(zj) for _ in range(world)]
+            dist_mod.all_gather(gi, zi.detach().contiguous())
+            dist_mod.all_gather(gj, zj.detach().contiguous())
+            zgi, zgj = torch.cat(gi), torch.cat(gj)
+        else:
+            zgi, zgj = zi.detach(), zj.detach()
+        n = zgi.shape[0]
+        m = 2 * n
+        z = torch.cat([zgi, zgj])
+        nrm = z.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        zh = z / nrm
+        lse = torch.empty(m, device=dev)
+        for c0 in range(0, m, rows):
+            s = zh[c0:c0 + rows] @ zh.t() / tau
+            idx = torch.arange(c0, min(c0 + rows, m), device=dev)
+            s[idx - c0, idx] = float("-inf")
+            lse[c0:c0 + rows] = torch.logsumexp(s, dim=1)
+        pos = (zh[:n] * zh[n:]).sum(1) / tau
+        loss_w = (lse.double().sum() - 2.0 * pos.double().sum()) / m
+        r0 = rank * n_local
+        rr = min(rows, n_local)
+        idx = torch.arange(r0, r0 + rr, device=dev)
+        s = zh[idx] @ zh.t() / tau
+        w = torch.exp(s - lse[idx, None]) + torch.exp(s - lse[None, :])
+        w[torch.arange(rr, device=dev), idx] = 0.0
+        g = (w @ zh - 2.0 * zh[idx + n]) / (m * tau)
+        g = (g - (g * zh[idx]).sum(1, keepdim=True) * zh[idx]) / nrm[idx]
+        loss_rel = abs(float(loss_value) - float(loss_w)) / abs(float(loss_w))
+        grad_rel = float((dzi[:rr].double() - g.double()).norm() / g.double().norm())
+        if dzj is not None:   # the same rows of view j (global rows n + idx)
+            s = zh[idx + n] @ zh.t() / tau
+            w = torch.exp(s - lse[idx + n, None]) + torch.exp(s - lse[None, :])
+            w[torch.arange(rr, device=dev), idx + n] = 0.0
+            g = (w @ zh - 2.0 * zh[idx]) / (m * tau)
+            g = (g - (g * zh[idx + n]).sum(1, keepdim=True) * zh[idx + n]) / nrm[idx + n]
+            grad_rel = max(grad_rel, float((dzj[:rr].double() - g.double()).norm() / g.double().norm()))
+        t = torch.tensor([loss_rel, grad_rel], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+    return {"loss_rel": t[0].item(), "grad_rel_l2": t[1].item(), "loss": float(loss_value), "witness_loss": float(loss_w),
+            "grad_rows_checked_per_rank": rr, "tolerance": {"loss_rel": 1e-3, "grad_rel_l2": 1e-2},
+            "witness": "chunked fp32 closed form on the GPU (torch.matmul, TF32 off) over the gathered global batch; "
+                       "max over ranks"}
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -260,6 +394,15 @@ def run_ours(args):
     clocks = sampler.stop()
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
 
+    # correctness evidence carried by the bench line itself (every N): one more step, outside the timed regions
+    zi.grad = None
+    zj.grad = None
+    loss_chk = loss_fn(zi, zj)
+    loss_chk.backward()
+    torch.cuda.synchronize()
+    parity = parity_witness(zi, zj, zi.grad, loss_chk.item(), world, rank, dist)
+    parity_ok = parity["loss_rel"] <= 1e-3 and parity["grad_rel_l2"] <= 1e-2
+
     peaks = load_peaks()
     value = N_GLOBAL / (ms_step * 1e-3)
     e2e_value = N_GLOBAL / (ms_e2e * 1e-3)
@@ -278,13 +421,15 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if world == 1 and os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("sim_bwd_kernel")  # bytes per launch from the committed ncu capture
-    roofline = {"bound": "tensor", "kernel": "sim_bwd_kernel<2,0>", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "tensor", "kernel": "sim_bwd_kernel<KB=2, SIM_NTX_FIXED, OPF16=1>", "achieved": achieved, "peak": peak,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this "
+                                  "kernel at this shape (profiles/traffic.json), not measured in this run",
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": f"{peaks['source']} {'sustained (sw_power_cap active)' if capped else 'burst'} bf16 "
                                f"(MEASURED_PEAKS.json)",
                 "frac_of_burst": achieved / peaks["bf16_tflops"],
                 "kernel_ms": bwd_ms, "flops_per_launch": bwd_flops,
-                "fwd_kernel": {"name": "sim_fwd_kernel<2,0>", "ms": fwd_ms,
+                "fwd_kernel": {"name": "sim_fwd_kernel<KB=2, SIM_NTX_FIXED, OPF16=1>", "ms": fwd_ms,
                                "achieved": fwd_flops / (fwd_ms * 1e-3) / 1e12,
                                "frac": fwd_flops / (fwd_ms * 1e-3) / 1e12 / peak},
                 "step": {"flops": 6.0 * m * m * DIM, "achieved": 6.0 * m * m * DIM / (ms_step * 1e-3) / 1e12 / world,
@@ -294,15 +439,22 @@ def run_ours(args):
     line = None
     if rank == 0:
         cpu = None
+        per_config = None
         if world == 1 and not args.no_cpu:
-            r = cpu_sample(rows=4096, reps=8)
-            cpu = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["threads"], "kind": "port",
-                   "sample": (f"{r['reps']} row slabs of {r['rows']} of the {r['m']} similarity rows x all columns "
-                              f"(each {r['rows']}/{r['m']} of the full job; {r['reps'] * r['rows']}/{r['m']} in total), "
-                              f"torch CPU fp32 fwd+bwd, {r['seconds']:.2f} s per slab, {r['total_seconds']:.1f} s timed")}
+            cpu = cpu_baseline_leg()
+        if world == 1 and not args.no_per_config:
+            # every BASELINE config (and the other §8 rows) beside its CPU arm and the reference run eagerly on this B200
+            import bench_losses
+            del flush
+            torch.cuda.empty_cache()
+            per_config = bench_losses.run_all(dev, reps=10, cpu=not args.no_cpu, ref_gpu=True,
+                                              only=("cfg1", "cfg2", "cfg3", "cfg4", "swav", "rowdot128", "rowdot1024",
+                                                    "relic512", "relic4096", "ntx8192"))
         line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "dtype_detail": "fp16 tensor-core operands (unit-norm rows scaled by sqrt(log2(e)/tau); bf16 for raw "
+                                "inputs), fp32 accumulation / statistics / loss / gradients",
                 "config": {"workload": WORKLOAD, "global_batch": N_GLOBAL, "dim": DIM, "rows_per_rank": 2 * n_local,
                            "parallelism": f"row-sharded x{world}, all-gather zhat + lse", "l2": "flushed (256 MiB write) between timed iterations"},
                 "roofline": roofline, "cpu_baseline": cpu,
@@ -310,11 +462,14 @@ def run_ours(args):
                         "h2d_bytes_per_step": 2 * n_local * DIM * 4 * world, "d2h_bytes_per_step": 4 * world,
                         "pipeline": "H2D of step t+1 (pinned, side stream, double-buffered) overlaps the kernels of step t; "
                                     "every copy is issued inside a timed step; each step ends with the loss D2H + sync"},
-                "gpu_launches": int(launches), "clocks": clocks}
+                "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "parity_ok": parity_ok,
+                "per_config": per_config}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not parity_ok:
+        raise SystemExit(f"parity check failed: {parity}")
 
 
 def main():
@@ -323,7 +478,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-per-config", action="store_true", help="skip the per_config array (the other BASELINE configs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

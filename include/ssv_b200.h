@@ -108,6 +108,38 @@ int ssvb_ntxent_dist_rows_fwd_push(const void* zhat_all, int64_t world, int64_t 
                                    void* const* peer_stat, float* loss_sum, void* workspace,
                                    size_t workspace_bytes, void* stream);
 int ssvb_ntxent_dist_loss(const float* stat_all, int64_t world, int64_t n_local, float* loss, void* stream);
+
+/* ---- NVLink peer-memory transport with generation flags (no NCCL, no host-issued barrier on the data path).
+ * Multi-GPU form of SimclrLoss.forward (reference utils/losses.py:15-46 on the rank-order concatenation, SURVEY.md
+ * §8e).  Every rank owns one SYMMETRIC arena of ssvb_ntxent_p2p_arena_bytes() bytes (zero-initialised once, then a
+ * group barrier); `peer_arenas` is a DEVICE array of the `world` peer-mapped arena base pointers (index = rank,
+ * including this rank's own), `arena_local` this rank's base, `multicast_arena` the NVSwitch multicast mapping of the
+ * same allocation or NULL (then unicast peer stores are used).  `gen` = 1, 2, 3, ... is the forward's generation,
+ * identical on every rank; buffers inside the arena are double-buffered by its parity.
+ *   prep_push : normalise + stage this rank's rows into EVERY arena, then publish flag[rows][rank] = gen everywhere
+ *   wait_copy : wait for every rank's rows of `gen`, copy the gathered matrix into private memory `zhat_all`
+ *   rows_fwd  : similarity rows of this rank -> [lse | term] stored into every arena, flag[stat][rank] = gen
+ *   stat_loss : wait for every rank's statistics, write the backward's column statistics `colstat` [mpad] and the
+ *               global loss (fixed summation order: bit-identical on every rank)
+ *   rows_bwd  : complete gradient of this rank's rows from zhat_all + colstat (no exchange) */
+size_t ssvb_ntxent_p2p_arena_bytes(int64_t world, int64_t n_local, int64_t d);
+int ssvb_ntxent_p2p_prep_push(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                              int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
+                              void* arena_local, void* const* peer_arenas, void* multicast_arena, int64_t gen,
+                              float* inv_norm_local, float* pos_local, void* stream);
+int ssvb_ntxent_p2p_wait_copy(const void* arena_local, int64_t world, int64_t rank, int64_t n_local, int64_t d,
+                              int64_t gen, void* zhat_all, void* stream);
+int ssvb_ntxent_p2p_rows_fwd(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
+                             int normalize, float temperature, const float* pos_local, void* const* peer_arenas,
+                             int64_t gen, float* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
+int ssvb_ntxent_p2p_stat_loss(const void* arena_local, int64_t world, int64_t rank, int64_t n_local, int64_t d,
+                              int normalize, float temperature, int64_t gen, float* colstat, float* loss,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int ssvb_ntxent_p2p_rows_bwd(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                             int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
+                             const void* zhat_all, const float* colstat, const float* inv_norm_local,
+                             const float* grad_out, float* dzi, float* dzj, int64_t ld_dzi, int64_t ld_dzj,
+                             void* workspace, size_t workspace_bytes, void* stream);
 int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
                               int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
                               const void* zhat_all, const float* stat_all /* [world][2][2L] */,
@@ -353,6 +385,17 @@ int ssvb_relic_kl_bwd(const float* zi, const float* zj, const float* zo, int64_t
                       int64_t ld_zj, int64_t ld_zo, int normalize, float temperature, float alpha,
                       const float* grad_out, const void* saved, float* dzi, float* dzj, float* dzo,
                       int64_t ld_dzi, int64_t ld_dzj, int64_t ld_dzo, void* stream);
+
+/* Multi-GPU ReLIC-KL (SURVEY.md §8e last row): the KL's softmaxes run over the batch axis (utils/losses.py:196-200),
+ * so the per-row logits of all ranks are all-gathered between two stages.  dist_dots writes this rank's a_n, b_n into
+ * `saved` and into ab_local [2][n_local]; the caller all-gathers ab_local into ab_all [world][2][n_local]; dist_reduce
+ * derives the global softmax statistics (into `saved`) and alpha*KL (identical on every rank); ssvb_relic_kl_bwd then
+ * yields the gradient rows of this rank's inputs.  The contrastive term is ssvb_ntxent_dist_* / ssvb_ntxent_p2p_*. */
+int ssvb_relic_kl_dist_dots(const float* zi, const float* zj, const float* zo, int64_t n_local, int64_t d,
+                            int64_t ld_zi, int64_t ld_zj, int64_t ld_zo, int normalize, float temperature,
+                            void* saved, float* ab_local, void* stream);
+int ssvb_relic_kl_dist_reduce(const float* ab_all, int64_t world, int64_t n_local, float alpha, void* saved, float* kl,
+                              void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Row L2-normalise (F.normalize(x, p=2, dim=-1), eps 1e-12) forward / backward —

@@ -334,7 +334,8 @@ int ssvb_ntxent_dist_prep(const float* zi, const float* zj, int64_t n_local, int
 namespace {
 int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d, int normalize,
                   float temperature, const float* pos_local, float* stat_local, float* const* peer_stat,
-                  float* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
+                  float* loss_sum, void* workspace, size_t workspace_bytes, void* stream, size_t peer_stat_off = 0,
+                  size_t peer_flag_off = 0, uint32_t gen = 0);
 }
 int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
                               int normalize, float temperature, const float* pos_local, float* stat_local,
@@ -354,7 +355,8 @@ int ssvb_ntxent_dist_rows_fwd_push(const void* zhat_all, int64_t world, int64_t 
 namespace {
 int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d, int normalize,
                   float temperature, const float* pos_local, float* stat_local, float* const* peer_stat,
-                  float* loss_sum, void* workspace, size_t workspace_bytes, void* stream) {
+                  float* loss_sum, void* workspace, size_t workspace_bytes, void* stream, size_t peer_stat_off,
+                  size_t peer_flag_off, uint32_t gen) {
   SSVB_TRY(check_device_sm100());
   SSVB_TRY(dist_check(world, rank, n_local));
   NtxPlan pl;
@@ -368,7 +370,7 @@ int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_l
   // local outputs either go to the caller's [2][2L] block or (push mode) into slot `rank` of every peer's buffer
   float* lse_out = stat_local;
   float* term_out = stat_local ? stat_local + lr : nullptr;
-  const size_t peer_off = static_cast<size_t>(rank) * 2 * lr;
+  const size_t peer_off = peer_stat_off / sizeof(float) + static_cast<size_t>(rank) * 2 * lr;
   SimParams p;
   fill_sim_params_rows(p, pl, 1, lr, rank * lr, 0);
   plan_chunks(p, 256, 4);
@@ -384,13 +386,14 @@ int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_l
                                                           static_cast<int>(lr), pos_local, pl.c, pl.shift,
                                                           ws.dacc /*scratch*/, lse_out, ws.block_sums, ws.counter,
                                                           1.f, loss_sum, term_out, peer_stat, static_cast<int>(world),
-                                                          peer_off);
+                                                          peer_off, 1.f, peer_flag_off, static_cast<int>(rank), gen);
   else
     lse_finalize_kernel<SIM_NTX_ONLINE><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride,
                                                            static_cast<int>(lr), pos_local, pl.c, pl.shift,
                                                            ws.dacc /*scratch*/, lse_out, ws.block_sums,
                                                            ws.counter, 1.f, loss_sum, term_out, peer_stat,
-                                                           static_cast<int>(world), peer_off);
+                                                           static_cast<int>(world), peer_off, 1.f, peer_flag_off,
+                                                           static_cast<int>(rank), gen);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
@@ -475,11 +478,28 @@ __global__ void dist_stat_kernel(const float* __restrict__ gathered, float* __re
 }
 }  // namespace
 
+namespace {
+int rows_bwd_impl(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                  int normalize, float temperature, int64_t world, int64_t rank, const void* zhat_all,
+                  const float* stat_all, const float* colstat, const float* inv_norm_local, const float* grad_out,
+                  float* dzi, float* dzj, int64_t ld_dzi, int64_t ld_dzj, void* workspace, size_t workspace_bytes,
+                  void* stream);
+}
 int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
                               int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
                               const void* zhat_all, const float* stat_all, const float* inv_norm_local,
                               const float* grad_out, float* dzi, float* dzj, int64_t ld_dzi, int64_t ld_dzj,
                               void* workspace, size_t workspace_bytes, void* stream) {
+  if (!stat_all) return SSVB_ERR_INVALID;
+  return rows_bwd_impl(zi, zj, n_local, d, ld_zi, ld_zj, normalize, temperature, world, rank, zhat_all, stat_all,
+                       nullptr, inv_norm_local, grad_out, dzi, dzj, ld_dzi, ld_dzj, workspace, workspace_bytes, stream);
+}
+namespace {
+int rows_bwd_impl(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                  int normalize, float temperature, int64_t world, int64_t rank, const void* zhat_all,
+                  const float* stat_all, const float* colstat, const float* inv_norm_local, const float* grad_out,
+                  float* dzi, float* dzj, int64_t ld_dzi, int64_t ld_dzj, void* workspace, size_t workspace_bytes,
+                  void* stream) {
   SSVB_TRY(check_device_sm100());
   SSVB_TRY(dist_check(world, rank, n_local));
   NtxPlan pl;
@@ -488,16 +508,20 @@ int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local,
   SSVB_TRY(check_rows(zj, ld_zj));
   SSVB_TRY(check_rows(dzi, ld_dzi));
   SSVB_TRY(check_rows(dzj, ld_dzj));
-  if (!zhat_all || !stat_all || !inv_norm_local || !grad_out || !workspace) return SSVB_ERR_INVALID;
+  if (!zhat_all || (!stat_all && !colstat) || !inv_norm_local || !grad_out || !workspace) return SSVB_ERR_INVALID;
   if (workspace_bytes < ssvb_ntxent_dist_workspace_bytes(world, n_local, d)) return SSVB_ERR_WORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t lr = 2 * n_local;
   WsLayout ws = ws_layout(workspace, lr, ceil_div(lr, 128), pl.m, pl.dpad);
-  // column statistics for all M rows live in the (otherwise unused here) partial buffer
-  float* stat = ws.part_m;
-  dist_stat_kernel<<<static_cast<unsigned>(ceil_div(pl.mpad, 256)), 256, 0, s>>>(
-      stat_all, stat, static_cast<int>(pl.m), static_cast<int>(pl.mpad), static_cast<int>(lr), pl.mode == SIM_NTX_FIXED, pl.shift, pl.wscale);
-  SSVB_LAUNCH_CHECK();
+  const float* stat = colstat;  // peer-memory transport: already derived (and padded) by the statistics kernel
+  if (!stat) {
+    // column statistics for all M rows live in the (otherwise unused here) partial buffer
+    dist_stat_kernel<<<static_cast<unsigned>(ceil_div(pl.mpad, 256)), 256, 0, s>>>(
+        stat_all, ws.part_m, static_cast<int>(pl.m), static_cast<int>(pl.mpad), static_cast<int>(lr),
+        pl.mode == SIM_NTX_FIXED, pl.shift, pl.wscale);
+    SSVB_LAUNCH_CHECK();
+    stat = ws.part_m;
+  }
 
   SimParams p;
   fill_sim_params_rows(p, pl, 1, lr, rank * lr, 0);
@@ -517,6 +541,266 @@ int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local,
         1.f / (pl.wscale * pl.prescale), 1.f / pl.prescale);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
+}
+}  // namespace
+
+}  // extern "C"
+
+// =====================================================================================================
+// NVLink peer-memory transport (fused compute + all-gather, no NCCL and no host-issued barrier on the data path).
+// Every rank owns one SYMMETRIC arena (same layout everywhere, peer-mapped, e.g. torch symmetric memory):
+//     zhat[2]  : 2 x (2L*world) x dpad 16-bit rows   - the gathered normalised rows, double-buffered by generation parity
+//     stat[2]  : 2 x [world][2][2L] fp32              - the gathered [lse2 | per-row loss term] blocks, double-buffered
+//     flags    : [2][world] uint32                    - flags[k][r] = last generation rank r has completely published
+//                                                       (k = 0 rows, k = 1 statistics) into THIS arena
+//     counter  : 1 uint32 (+ padding)                 - last-block counter of the push kernel (self-resetting)
+// A forward of generation g:  p2p_prep_push (normalise, store own slot into every arena - unicast peer stores or one
+// multicast store through the switch -, last block publishes flags[0][rank] = g everywhere)  ->  p2p_wait_copy (waits
+// for flags[0][*] >= g, copies the gathered rows into a private matrix: the tensor-core kernels read ordinary device
+// memory faster than a peer-mapped mapping)  ->  sim_fwd + finalize (stores [lse2 | term] into every arena,
+// publishes flags[1][rank] = g)  ->  p2p_stat_loss (waits for flags[1][*] >= g, derives the backward's column
+// statistics and the global loss in a fixed order: bit-identical on every rank).  Backward needs no exchange.
+// Double buffering makes the protocol barrier-free: a rank can only push generation g+2 (same parity as g) after it
+// has seen every peer's generation g+1 statistics, which a peer publishes after it has finished reading generation g.
+// =====================================================================================================
+struct ArenaLayout {
+  size_t zhat[2], stat[2], flags, counter, bytes;
+};
+ArenaLayout arena_layout(int64_t world, int64_t n_local, int64_t dpad) {
+  ArenaLayout a;
+  size_t off = 0;
+  auto take = [&](size_t nbytes) {
+    off = (off + 1023) & ~static_cast<size_t>(1023);
+    const size_t r = off;
+    off += nbytes;
+    return r;
+  };
+  const size_t m = static_cast<size_t>(2 * n_local * world);
+  for (int i = 0; i < 2; ++i) a.zhat[i] = take(m * dpad * sizeof(__nv_bfloat16));
+  for (int i = 0; i < 2; ++i) a.stat[i] = take(m * 2 * sizeof(float));
+  a.flags = take(2 * static_cast<size_t>(world) * sizeof(uint32_t));
+  a.counter = take(64);
+  a.bytes = (off + 1023) & ~static_cast<size_t>(1023);
+  return a;
+}
+
+namespace {
+__global__ void p2p_prep_push_kernel(const float* __restrict__ xi, const float* __restrict__ xj, int n, int d,
+                                     int64_t ldi, int64_t ldj, int normalize, int f16, float prescale,
+                                     uint8_t* const* __restrict__ peers, uint8_t* mc_base, size_t zoff, size_t flag_off,
+                                     unsigned int* counter, int world, int rank, int64_t row_i, int64_t row_j, int dpad,
+                                     float* __restrict__ inv_i, float* __restrict__ inv_j, float* __restrict__ pos_i,
+                                     float* __restrict__ pos_j, uint32_t gen) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp < n) {
+    const float* ri = xi + static_cast<int64_t>(warp) * ldi;
+    const float* rj = xj + static_cast<int64_t>(warp) * ldj;
+    const int k = lane * 4;  // dpad <= 128: one float4 per lane
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (k < d) {
+      a = *reinterpret_cast<const float4*>(ri + k);
+      b = *reinterpret_cast<const float4*>(rj + k);
+    }
+    const float si = warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w);
+    const float sj = warp_sum(b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w);
+    float ivi = 1.f, ivj = 1.f;
+    if (normalize) {
+      ivi = 1.f / fmaxf(sqrtf(si), 1e-12f);
+      ivj = 1.f / fmaxf(sqrtf(sj), 1e-12f);
+    }
+    const float si_ = ivi * prescale, sj_ = ivj * prescale;
+    uint2 vi, vj;
+    vi.x = f16 ? pack_f16x2(a.x * si_, a.y * si_) : pack_bf16x2(a.x * si_, a.y * si_);
+    vi.y = f16 ? pack_f16x2(a.z * si_, a.w * si_) : pack_bf16x2(a.z * si_, a.w * si_);
+    vj.x = f16 ? pack_f16x2(b.x * sj_, b.y * sj_) : pack_bf16x2(b.x * sj_, b.y * sj_);
+    vj.y = f16 ? pack_f16x2(b.z * sj_, b.w * sj_) : pack_bf16x2(b.z * sj_, b.w * sj_);
+    const float2 fi01 = unpack_h2(vi.x, f16), fi23 = unpack_h2(vi.y, f16);
+    const float2 fj01 = unpack_h2(vj.x, f16), fj23 = unpack_h2(vj.y, f16);
+    const float dot = warp_sum(fi01.x * fj01.x + fi01.y * fj01.y + fi23.x * fj23.x + fi23.y * fj23.y);
+    if (k < dpad) {
+      const size_t oi = zoff + (static_cast<size_t>(row_i + warp) * dpad + k) * 2;
+      const size_t oj = zoff + (static_cast<size_t>(row_j + warp) * dpad + k) * 2;
+      if (mc_base) {  // one store each through the NVSwitch multicast mapping reaches every rank's arena
+        multimem_st_v2(mc_base + oi, vi);
+        multimem_st_v2(mc_base + oj, vj);
+      } else {
+        // start at a different peer per CTA so the ranks do not all hit the same NVLink port at the same time
+        const int p0 = static_cast<int>(blockIdx.x % static_cast<unsigned>(world));
+        for (int q = 0; q < world; ++q) {
+          uint8_t* base = peers[(p0 + q) % world];
+          *reinterpret_cast<uint2*>(base + oi) = vi;
+          *reinterpret_cast<uint2*>(base + oj) = vj;
+        }
+      }
+    }
+    if (lane == 0) {
+      inv_i[warp] = ivi; inv_j[warp] = ivj; pos_i[warp] = dot; pos_j[warp] = dot;
+    }
+  }
+  // publish: every thread's peer stores are performed system-wide, then the last block to finish raises this rank's
+  // flag in every arena
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence_system();
+    if (threadIdx.x < world) {
+      uint32_t* f = reinterpret_cast<uint32_t*>(peers[threadIdx.x] + flag_off);
+      st_release_sys_u32(f + rank, gen);
+    }
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+// waits (per slot) until the owning rank has published generation `gen`, then copies that slot of the local arena
+// into the private gathered matrix.  CTA b serves slot (b + rank) % world, so the local slot is handled first.
+__global__ void p2p_wait_copy_kernel(const uint8_t* __restrict__ arena, size_t zoff, size_t flag_off, int world, int rank,
+                                     uint32_t gen, uint4* __restrict__ dst, size_t slot_vecs) {
+  const int slot = (static_cast<int>(blockIdx.x) + rank) % world;
+  const int part = blockIdx.x / world, nparts = gridDim.x / world;
+  if (part >= nparts) return;
+  if (threadIdx.x == 0) spin_wait_gen(reinterpret_cast<const uint32_t*>(arena + flag_off) + slot, gen);
+  __syncthreads();
+  const uint4* src = reinterpret_cast<const uint4*>(arena + zoff) + static_cast<size_t>(slot) * slot_vecs;
+  uint4* out = dst + static_cast<size_t>(slot) * slot_vecs;
+  for (size_t i = static_cast<size_t>(part) * blockDim.x + threadIdx.x; i < slot_vecs;
+       i += static_cast<size_t>(nparts) * blockDim.x)
+    out[i] = __ldcg(src + i);
+}
+
+// waits for every rank's statistics of generation `gen`, then (a) column statistics of all M rows for the backward
+// kernel (FIXED: wscale / L', else lse2; finite padding), (b) the global loss = fixed-order sum of the per-row terms.
+__global__ void p2p_stat_loss_kernel(const uint8_t* __restrict__ arena, size_t soff, size_t flag_off, int world,
+                                     uint32_t gen, int lr, int m, int mpad, int fixed, float shift, float wscale,
+                                     float* __restrict__ colstat, float* block_sums, unsigned int* counter, float scale,
+                                     float* loss) {
+  if (threadIdx.x < world)
+    spin_wait_gen(reinterpret_cast<const uint32_t*>(arena + flag_off) + world + threadIdx.x, gen);
+  __syncthreads();
+  const float* g = reinterpret_cast<const float*>(arena + soff);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float term = 0.f;
+  if (i < mpad) {
+    if (i < m) {
+      const int r = i / lr;
+      const size_t base = static_cast<size_t>(r) * 2 * lr + (i - r * lr);
+      const float l2 = __ldcg(g + base);
+      term = __ldcg(g + base + lr);
+      colstat[i] = fixed ? wscale * exp2f(shift - l2) : l2;
+    } else {
+      colstat[i] = fixed ? 0.f : 1e30f;
+    }
+  }
+  const float bt = block_sum_256(term);
+  grid_sum_finish(bt, block_sums, counter, scale, loss, false);
+}
+}  // namespace
+
+extern "C" {
+
+size_t ssvb_ntxent_p2p_arena_bytes(int64_t world, int64_t n_local, int64_t d) {
+  if (world <= 0 || n_local <= 0 || d <= 0) return 0;
+  return arena_layout(world, n_local, sim_dpad(d)).bytes;
+}
+
+int ssvb_ntxent_p2p_prep_push(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                              int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
+                              void* arena_local, void* const* peer_arenas, void* multicast_arena, int64_t gen,
+                              float* inv_norm_local, float* pos_local, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(dist_check(world, rank, n_local));
+  if (world > 256) return SSVB_ERR_UNSUPPORTED;
+  NtxPlan pl;
+  SSVB_TRY(make_plan(pl, n_local * world, d, normalize, temperature));
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  if (!arena_local || !peer_arenas || !inv_norm_local || !pos_local || gen <= 0) return SSVB_ERR_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const ArenaLayout al = arena_layout(world, n_local, pl.dpad);
+  const int64_t row0 = rank * 2 * n_local;
+  const uint32_t g = static_cast<uint32_t>(gen);
+  p2p_prep_push_kernel<<<static_cast<unsigned>(ceil_div(n_local, 8)), 256, 0, s>>>(
+      zi, zj, static_cast<int>(n_local), static_cast<int>(d), ld_zi, ld_zj, normalize, normalize ? 1 : 0, pl.prescale,
+      reinterpret_cast<uint8_t* const*>(peer_arenas), static_cast<uint8_t*>(multicast_arena), al.zhat[g & 1], al.flags,
+      reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(arena_local) + al.counter), static_cast<int>(world),
+      static_cast<int>(rank), row0, row0 + n_local, static_cast<int>(pl.dpad), inv_norm_local,
+      inv_norm_local + n_local, pos_local, pos_local + n_local, g);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_ntxent_p2p_wait_copy(const void* arena_local, int64_t world, int64_t rank, int64_t n_local, int64_t d,
+                              int64_t gen, void* zhat_all, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(dist_check(world, rank, n_local));
+  if (!arena_local || !zhat_all || gen <= 0 || d <= 0) return SSVB_ERR_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t dpad = sim_dpad(d), m = 2 * n_local * world, mpad = sim_mpad(m);
+  const ArenaLayout al = arena_layout(world, n_local, dpad);
+  __nv_bfloat16* zh = static_cast<__nv_bfloat16*>(zhat_all);
+  if (mpad > m) SSVB_CUDA(cudaMemsetAsync(zh + m * dpad, 0, (mpad - m) * dpad * sizeof(__nv_bfloat16), s));
+  const size_t slot_vecs = static_cast<size_t>(2 * n_local) * dpad * 2 / 16;  // dpad % 64 == 0: whole 16-byte vectors
+  // enough CTAs to run at copy bandwidth, a whole number of them per slot, all co-resident (they spin on flags)
+  int parts = static_cast<int>(ceil_div(2 * num_sms(), world));
+  const int64_t max_parts = ceil_div(static_cast<int64_t>(slot_vecs), 256);
+  if (parts > max_parts) parts = static_cast<int>(max_parts);
+  if (parts < 1) parts = 1;
+  p2p_wait_copy_kernel<<<static_cast<unsigned>(parts * world), 256, 0, s>>>(
+      static_cast<const uint8_t*>(arena_local), al.zhat[static_cast<uint32_t>(gen) & 1], al.flags,
+      static_cast<int>(world), static_cast<int>(rank), static_cast<uint32_t>(gen), reinterpret_cast<uint4*>(zhat_all),
+      slot_vecs);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_ntxent_p2p_rows_fwd(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
+                             int normalize, float temperature, const float* pos_local, void* const* peer_arenas,
+                             int64_t gen, float* loss_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!peer_arenas || gen <= 0 || d <= 0) return SSVB_ERR_INVALID;
+  const ArenaLayout al = arena_layout(world, n_local, sim_dpad(d));
+  return rows_fwd_impl(zhat_all, world, rank, n_local, d, normalize, temperature, pos_local, nullptr,
+                       reinterpret_cast<float* const*>(peer_arenas), loss_sum, workspace, workspace_bytes, stream,
+                       al.stat[static_cast<uint32_t>(gen) & 1], al.flags + world * sizeof(uint32_t),
+                       static_cast<uint32_t>(gen));
+}
+
+int ssvb_ntxent_p2p_stat_loss(const void* arena_local, int64_t world, int64_t rank, int64_t n_local, int64_t d,
+                              int normalize, float temperature, int64_t gen, float* colstat, float* loss,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  SSVB_TRY(dist_check(world, rank, n_local));
+  NtxPlan pl;
+  SSVB_TRY(make_plan(pl, n_local * world, d, normalize, temperature));
+  if (!arena_local || !colstat || !loss || !workspace || gen <= 0 || world > 256) return SSVB_ERR_INVALID;
+  if (workspace_bytes < ssvb_ntxent_dist_workspace_bytes(world, n_local, d)) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t lr = 2 * n_local;
+  WsLayout ws = ws_layout(workspace, lr, ceil_div(lr, 128), pl.m, pl.dpad);
+  const ArenaLayout al = arena_layout(world, n_local, pl.dpad);
+  // block partials: part_l is free again once the finalize kernel of this forward has run (same stream)
+  float* block_sums = ws.part_l;
+  p2p_stat_loss_kernel<<<static_cast<unsigned>(ceil_div(pl.mpad, 256)), 256, 0, s>>>(
+      static_cast<const uint8_t*>(arena_local), al.stat[static_cast<uint32_t>(gen) & 1], al.flags,
+      static_cast<int>(world), static_cast<uint32_t>(gen), static_cast<int>(lr), static_cast<int>(pl.m),
+      static_cast<int>(pl.mpad), pl.mode == SIM_NTX_FIXED, pl.shift, pl.wscale, colstat, block_sums, ws.counter,
+      1.f / static_cast<float>(pl.m), loss);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_ntxent_p2p_rows_bwd(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
+                             int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
+                             const void* zhat_all, const float* colstat, const float* inv_norm_local,
+                             const float* grad_out, float* dzi, float* dzj, int64_t ld_dzi, int64_t ld_dzj,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  if (!colstat) return SSVB_ERR_INVALID;
+  return rows_bwd_impl(zi, zj, n_local, d, ld_zi, ld_zj, normalize, temperature, world, rank, zhat_all, nullptr,
+                       colstat, inv_norm_local, grad_out, dzi, dzj, ld_dzi, ld_dzj, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -271,26 +271,43 @@ __device__ float block_reduce_1024(float v, bool is_max) {
 }
 
 // single block: softmax over the batch axis of a, log-softmax of b, quirk-KL (utils/losses.py:198-200)
-__global__ void relic_softmax_kernel(int64_t n, RelicSaved sv, float alpha, float* __restrict__ kl_out) {
+// `gathered` (multi-GPU): the N-vectors are read from the all-gathered buffer [world][2][n_local] (n = world * n_local,
+// rank-order concatenation = the single-process batch axis); otherwise from the saved blob.
+struct RelicVec {
+  const float* a;
+  const float* b;
+  int64_t n_local;  // 0: plain vectors
+  __device__ __forceinline__ float A(int64_t i) const {
+    if (!n_local) return a[i];
+    const int64_t r = i / n_local;
+    return a[r * 2 * n_local + (i - r * n_local)];
+  }
+  __device__ __forceinline__ float B(int64_t i) const {
+    if (!n_local) return b[i];
+    const int64_t r = i / n_local;
+    return a[r * 2 * n_local + n_local + (i - r * n_local)];
+  }
+};
+__global__ void relic_softmax_kernel(int64_t n, RelicVec v, RelicSaved sv, float alpha, float* __restrict__ kl_out) {
   float ma = -INFINITY, mb = -INFINITY;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    ma = fmaxf(ma, sv.a[i]);
-    mb = fmaxf(mb, sv.b[i]);
+    ma = fmaxf(ma, v.A(i));
+    mb = fmaxf(mb, v.B(i));
   }
   ma = block_reduce_1024(ma, true);
   mb = block_reduce_1024(mb, true);
   float sa = 0.f, sb = 0.f;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    sa += expf(sv.a[i] - ma);
-    sb += expf(sv.b[i] - mb);
+    sa += expf(v.A(i) - ma);
+    sb += expf(v.B(i) - mb);
   }
   sa = block_reduce_1024(sa, false);
   sb = block_reduce_1024(sb, false);
   const float lse_a = ma + logf(sa), lse_b = mb + logf(sb);
   float kl = 0.f, spq = 0.f;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const float p = expf(sv.a[i] - lse_a);
-    const float lq = sv.b[i] - lse_b;
+    const float p = expf(v.A(i) - lse_a);
+    const float lq = v.B(i) - lse_b;
     const float q = expf(lq);
     kl += q * (lq - p);
     spq += p * q;
@@ -535,7 +552,42 @@ int ssvb_relic_kl_fwd(const float* zi, const float* zj, const float* zo, int64_t
                                                                           ld_zj, ld_zo, normalize, 1.f / temperature,
                                                                           sv);
   SSVB_LAUNCH_CHECK();
-  relic_softmax_kernel<<<1, 1024, 0, s>>>(n, sv, alpha, kl);
+  relic_softmax_kernel<<<1, 1024, 0, s>>>(n, RelicVec{sv.a, sv.b, 0}, sv, alpha, kl);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+// ---- multi-GPU ReLIC-KL: the KL's two softmaxes run over the BATCH axis (utils/losses.py:196-200), so the
+// per-row logits a_n, b_n of all ranks are all-gathered (2 * n_local floats per rank) between two stages:
+//   dist_dots   : this rank's a, b (+ inverse norms) into `saved`, and into ab_local [2][n_local] for the all-gather
+//   dist_reduce : global softmax statistics + alpha * KL from the gathered [world][2][n_local] buffer (fixed order,
+//                 identical on every rank); the statistics land in this rank's `saved`, so the unchanged
+//                 ssvb_relic_kl_bwd produces the gradient rows of this rank's inputs.
+int ssvb_relic_kl_dist_dots(const float* zi, const float* zj, const float* zo, int64_t n_local, int64_t d,
+                            int64_t ld_zi, int64_t ld_zj, int64_t ld_zo, int normalize, float temperature,
+                            void* saved, float* ab_local, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (n_local <= 0 || d <= 0 || !saved || !ab_local || !(temperature > 0.f)) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(zi, ld_zi));
+  SSVB_TRY(check_rows(zj, ld_zj));
+  SSVB_TRY(check_rows(zo, ld_zo));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  RelicSaved sv = relic_saved(saved, n_local);
+  relic_dots_kernel<<<static_cast<unsigned>(ceil_div(n_local, 8)), 256, 0, s>>>(
+      zi, zj, zo, n_local, static_cast<int>(d), ld_zi, ld_zj, ld_zo, normalize, 1.f / temperature, sv);
+  SSVB_LAUNCH_CHECK();
+  SSVB_CUDA(cudaMemcpyAsync(ab_local, sv.a, n_local * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  SSVB_CUDA(cudaMemcpyAsync(ab_local + n_local, sv.b, n_local * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return SSVB_OK;
+}
+int ssvb_relic_kl_dist_reduce(const float* ab_all, int64_t world, int64_t n_local, float alpha, void* saved, float* kl,
+                              void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (!ab_all || world <= 0 || n_local <= 0 || !saved || !kl) return SSVB_ERR_INVALID;
+  RelicSaved sv = relic_saved(saved, n_local);
+  relic_softmax_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(world * n_local, RelicVec{ab_all, ab_all, n_local},
+                                                                          sv, alpha, kl);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }

@@ -241,7 +241,7 @@ __device__ __forceinline__ float block_sum_256(float v) {
   }
   return t;  // valid in warp 0
 }
-__device__ __forceinline__ void grid_sum_finish(float block_total, float* block_sums, unsigned int* counter,
+__device__ __forceinline__ bool grid_sum_finish(float block_total, float* block_sums, unsigned int* counter,
                                                 float scale, float* out, bool accumulate) {
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
@@ -264,6 +264,33 @@ __device__ __forceinline__ void grid_sum_finish(float block_total, float* block_
       *counter = 0;
     }
   }
+  return is_last;  // block-uniform: true in the block that arrived last (all other blocks' writes are visible to it)
+}
+
+// ---- NVLink peer-memory transport helpers (symmetric arenas, generation flags; see ntxent.cu) ----
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// wait until a peer has published generation `gen` (monotonic counters, wrap-safe compare).  Bounded: a rank that
+// never arrives turns into a CUDA error after ~30 s instead of a hung GPU.
+__device__ __forceinline__ void spin_wait_gen(const uint32_t* flag, uint32_t gen) {
+  const long long t0 = clock64();
+  while (static_cast<int32_t>(ld_acquire_sys_u32(flag) - gen) < 0) {
+    __nanosleep(64);
+    if (clock64() - t0 > 60000000000LL) __trap();
+  }
+}
+// 8-byte store to the same offset of EVERY rank's arena through the NVSwitch multicast mapping (one store on the
+// wire instead of `world`)
+__device__ __forceinline__ void multimem_st_v2(void* mc_addr, uint2 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y))
+               : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -277,7 +304,9 @@ __global__ void lse_finalize_kernel(const float* __restrict__ part_m, const floa
                                     float* __restrict__ stat, float* __restrict__ lse2_out,
                                     float* block_sums, unsigned int* counter, float loss_scale, float* loss,
                                     float* __restrict__ term_out = nullptr, float* const* __restrict__ peer_stat = nullptr,
-                                    int world = 0, size_t peer_off = 0, float wscale = 1.f) {
+                                    int world = 0, size_t peer_off = 0, float wscale = 1.f,
+                                    size_t peer_flag_off = 0 /* bytes; 0 = no flags */, int rank = 0,
+                                    uint32_t gen = 0) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   float term = 0.f;
   if (r < nrows) {
@@ -309,8 +338,16 @@ __global__ void lse_finalize_kernel(const float* __restrict__ part_m, const floa
       }
     }
   }
+  if (peer_stat && peer_flag_off) __threadfence_system();  // this thread's peer stores are performed system-wide
   const float bt = block_sum_256(term);
-  grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false);
+  const bool last = grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false);
+  if (peer_stat && peer_flag_off && last && threadIdx.x < world) {
+    // every block fenced its peer stores before its counter increment: publish "statistics of generation `gen`
+    // from rank `rank` are complete" in every peer's flag array
+    __threadfence_system();
+    uint32_t* f = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(peer_stat[threadIdx.x]) + peer_flag_off);
+    st_release_sys_u32(f + rank, gen);
+  }
 }
 
 // Same combine for MANY partials per row (MoCo: the queue axis is split into up to 128 chunks x 4 warpgroups):

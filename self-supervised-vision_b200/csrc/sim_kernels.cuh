@@ -96,12 +96,21 @@ __device__ __forceinline__ float ex2_poly3(float x);
 #ifndef SSVB_POLY_MOD_FWD
 #define SSVB_POLY_MOD_FWD 3   // masked (rare) tiles only: every 3rd element on the scalar polynomial
 #endif
-// FIXED mode hot loops: one PAIR of every SSVB_POLY_PAIR_* pairs takes the packed polynomial exp2 (0 = none)
-#ifndef SSVB_POLY_PAIR_FWD
-#define SSVB_POLY_PAIR_FWD 2
+// FIXED mode hot loops: of every SSVB_POLY_*_MOD consecutive PAIRS, the first SSVB_POLY_*_CNT take the packed
+// polynomial exp2 and the rest two MUFU.EX2 (CNT = 0: MUFU only).  MUFU issues through the MIO queue at 16 / clk / SM
+// and is co-critical with the tensor pipe in both kernels (ncu: mio_throttle on MUFU.EX2), so a share of the
+// exponentials moves to the FMA pipe; tuned by A/B builds (profiles/r2_tuning_log.md).
+#ifndef SSVB_POLY_FWD_MOD
+#define SSVB_POLY_FWD_MOD 2
 #endif
-#ifndef SSVB_POLY_PAIR_BWD
-#define SSVB_POLY_PAIR_BWD 0
+#ifndef SSVB_POLY_FWD_CNT
+#define SSVB_POLY_FWD_CNT 1
+#endif
+#ifndef SSVB_POLY_BWD_MOD
+#define SSVB_POLY_BWD_MOD 3
+#endif
+#ifndef SSVB_POLY_BWD_CNT
+#define SSVB_POLY_BWD_CNT 1
 #endif
 
 // exp2 of two values on the FMA pipe with packed instructions (Cody-Waite split + degree-3 minimax, max rel. error
@@ -181,7 +190,7 @@ __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int
       // logit: no scale/shift FFMA.  Per pair: two MUFU.EX2 or one packed polynomial, one packed row-sum FADD2.
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const bool poly = SSVB_POLY_PAIR_FWD > 0 && (i % (SSVB_POLY_PAIR_FWD > 0 ? SSVB_POLY_PAIR_FWD : 1)) == 1;
+        const bool poly = (i % SSVB_POLY_FWD_MOD) < SSVB_POLY_FWD_CNT;
         unsigned long long e2;
         if (poly) {
           e2 = ex2_poly3_x2(pack_f32x2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])));
@@ -450,7 +459,7 @@ __device__ __forceinline__ void bwd_weights32(const uint32_t (&sv)[32], uint32_t
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int i = i2 * 2 + e;  // pair index: columns 2i, 2i+1
-        const bool poly = SSVB_POLY_PAIR_BWD > 0 && (i % (SSVB_POLY_PAIR_BWD > 0 ? SSVB_POLY_PAIR_BWD : 1)) == 1;
+        const bool poly = (i % SSVB_POLY_BWD_MOD) < SSVB_POLY_BWD_CNT;
         unsigned long long e2;
         if (poly) {
           e2 = ex2_poly3_x2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])));

@@ -5,9 +5,12 @@ of all ranks' (zi, zj); every rank gets the gradient rows of its own inputs, no 
 
 Row sharding: rank r owns the 2L rows of its local batch (L = per-rank batch) and computes their
 similarity rows against ALL columns.  One exchange each way:
-  transport "p2p" (default when torch symmetric memory works): the normalise kernel and the LSE-finalize kernel
-            store their rank's slot directly into EVERY peer's gather buffer over NVLink (fused compute +
-            all-gather), a symmetric-memory barrier publishes it - no NCCL on the data path;
+  transport "p2p" (default when torch symmetric memory works): fused compute + all-gather over NVLink peer memory.
+            Every rank owns one symmetric arena; the normalise kernel stores its rows into EVERY arena (unicast peer
+            stores, or ONE multicast store through the NVSwitch when the allocation has a multicast mapping) and the
+            LSE-finalize kernel does the same with its [lse | term] block; completion is published with per-rank
+            generation flags that the consuming kernels poll on the device - no NCCL call and no host-issued barrier
+            on the data path, and the buffers are double-buffered by generation parity so no pre-push barrier exists;
   transport "nccl":
   forward : all-gather of the bf16 normalised rows (2L x dpad per rank), then ONE all-gather of
             [per-row LSE | per-row loss term] (4L floats per rank) that serves both the backward's column
@@ -64,65 +67,109 @@ class CudaStages:
                                             C.ptr(ws), ws_bytes, C.stream_ptr(dev)), "ssvb_ntxent_dist_rows_bwd")
 
 
-    # ---- fused compute + all-gather over NVLink peer memory (no NCCL on the data path)
-    def prep_push(self, zi, zj, normalize, temperature, world, rank, peer_zhat_dev, inv_local, pos_local):
+    # ---- fused compute + all-gather over NVLink peer memory (generation flags, no NCCL / barrier on the data path)
+    def p2p_prep_push(self, zi, zj, normalize, temperature, world, rank, arena, gen, inv_local, pos_local):
         n, d = zi.shape
-        C.check(C.lib().ssvb_ntxent_dist_prep_push(C.ptr(zi), C.ptr(zj), n, d, zi.stride(0), zj.stride(0), normalize,
-                                                   temperature, world, rank, C.c_void_p(peer_zhat_dev), C.ptr(inv_local),
-                                                   C.ptr(pos_local), C.stream_ptr(zi.device)), "ssvb_ntxent_dist_prep_push")
+        C.check(C.lib().ssvb_ntxent_p2p_prep_push(C.ptr(zi), C.ptr(zj), n, d, zi.stride(0), zj.stride(0), normalize,
+                                                  temperature, world, rank, C.c_void_p(arena.local_ptr),
+                                                  C.c_void_p(arena.peers_dev), C.c_void_p(arena.multicast_ptr or None),
+                                                  gen, C.ptr(inv_local), C.ptr(pos_local), C.stream_ptr(zi.device)),
+                "ssvb_ntxent_p2p_prep_push")
 
-    def rows_fwd_push(self, zhat_all, world, rank, n_local, d, normalize, temperature, pos_local, peer_stat_dev, loss_sum):
-        L = C.lib()
-        dev = zhat_all.device
+    def p2p_wait_copy(self, arena, world, rank, n_local, d, gen, zhat_all):
+        C.check(C.lib().ssvb_ntxent_p2p_wait_copy(C.c_void_p(arena.local_ptr), world, rank, n_local, d, gen,
+                                                  C.ptr(zhat_all), C.stream_ptr(zhat_all.device)),
+                "ssvb_ntxent_p2p_wait_copy")
+
+    def _dist_ws(self, world, n_local, d, dev):
         ws_bytes = C.cached_size("ssvb_ntxent_dist_workspace_bytes", world, n_local, d)
-        ws = C.workspace("ntxent_dist", ws_bytes, dev)
-        C.check(L.ssvb_ntxent_dist_rows_fwd_push(C.ptr(zhat_all), world, rank, n_local, d, normalize, temperature,
-                                                 C.ptr(pos_local), C.c_void_p(peer_stat_dev), C.ptr(loss_sum), C.ptr(ws),
-                                                 ws_bytes, C.stream_ptr(dev)), "ssvb_ntxent_dist_rows_fwd_push")
+        return C.workspace("ntxent_dist", ws_bytes, dev), ws_bytes
+
+    def p2p_rows_fwd(self, zhat_all, world, rank, n_local, d, normalize, temperature, pos_local, arena, gen, loss_sum):
+        dev = zhat_all.device
+        ws, ws_bytes = self._dist_ws(world, n_local, d, dev)
+        C.check(C.lib().ssvb_ntxent_p2p_rows_fwd(C.ptr(zhat_all), world, rank, n_local, d, normalize, temperature,
+                                                 C.ptr(pos_local), C.c_void_p(arena.peers_dev), gen, C.ptr(loss_sum),
+                                                 C.ptr(ws), ws_bytes, C.stream_ptr(dev)), "ssvb_ntxent_p2p_rows_fwd")
+
+    def p2p_stat_loss(self, arena, world, rank, n_local, d, normalize, temperature, gen, colstat, loss):
+        dev = colstat.device
+        ws, ws_bytes = self._dist_ws(world, n_local, d, dev)
+        C.check(C.lib().ssvb_ntxent_p2p_stat_loss(C.c_void_p(arena.local_ptr), world, rank, n_local, d, normalize,
+                                                  temperature, gen, C.ptr(colstat), C.ptr(loss), C.ptr(ws), ws_bytes,
+                                                  C.stream_ptr(dev)), "ssvb_ntxent_p2p_stat_loss")
+
+    def p2p_rows_bwd(self, zi, zj, normalize, temperature, world, rank, zhat_all, colstat, inv_local, grad_out, dzi, dzj):
+        n, d = zi.shape
+        dev = zi.device
+        ws, ws_bytes = self._dist_ws(world, n, d, dev)
+        C.check(C.lib().ssvb_ntxent_p2p_rows_bwd(C.ptr(zi), C.ptr(zj), n, d, zi.stride(0), zj.stride(0), normalize,
+                                                 temperature, world, rank, C.ptr(zhat_all), C.ptr(colstat),
+                                                 C.ptr(inv_local), C.ptr(grad_out), C.ptr(dzi), C.ptr(dzj),
+                                                 dzi.stride(0), dzj.stride(0), C.ptr(ws), ws_bytes, C.stream_ptr(dev)),
+                "ssvb_ntxent_p2p_rows_bwd")
 
     def dist_loss(self, stat_all, world, n_local, loss):
         C.check(C.lib().ssvb_ntxent_dist_loss(C.ptr(stat_all), world, n_local, C.ptr(loss),
                                               C.stream_ptr(stat_all.device)), "ssvb_ntxent_dist_loss")
 
 
-class _PeerTransport:
-    """Double-buffered symmetric (peer-mapped) gather buffers for one (group, shape): every rank's kernels store
-    their slot straight into all peers' buffers over NVLink; a symmetric-memory barrier publishes the data.
-    Double buffering makes a pre-push barrier unnecessary (a rank can never be two pushes ahead of a peer: it must
-    pass the peer's previous post-push barrier first), and the gathered data is copied into a private tensor before
-    use, so the autograd graph never references a buffer a later forward may overwrite."""
+class _PeerArena:
+    """One symmetric (peer-mapped) arena per (group, shape) holding the double-buffered gather buffers and the
+    generation flags of the NVLink transport (layout: csrc/ntxent.cu `ArenaLayout`).  Created collectively: zeroed,
+    then ONE group barrier so that no peer can push before the flags are cleared; after that the protocol needs no
+    barrier (see include/ssv_b200.h).  `gen` counts the forwards of this arena and is identical on every rank."""
 
     _cache = {}
 
-    def __init__(self, group, world, mpad, dpad, n_local, dev):
+    def __init__(self, group, world, n_local, d, dev, multicast):
         import torch.distributed._symmetric_memory as symm_mem
-        self.bufs = []
-        for _ in range(2):
-            z = symm_mem.empty(mpad * dpad, dtype=torch.bfloat16, device=dev)
-            z.zero_()  # padding rows stay zero for ever (nobody writes them)
-            hz = symm_mem.rendezvous(z, group)
-            st = symm_mem.empty(world * 4 * n_local, dtype=torch.float32, device=dev)
-            hs = symm_mem.rendezvous(st, group)
-            hz.barrier()
-            self.bufs.append((z, hz, st, hs))
-        self.parity = 0
-        self.gen = [0, 0]  # pushes seen by each buffer pair (backward checks its pair has not been re-used)
+        nbytes = C.cached_size("ssvb_ntxent_p2p_arena_bytes", world, n_local, d)
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.hdl.barrier()
+        self.local_ptr = self.buf.data_ptr()
+        self.peers_dev = self.hdl.buffer_ptrs_dev
+        mc = getattr(self.hdl, "multicast_ptr", 0) or 0
+        self.multicast_ptr = mc if multicast else 0
+        self.gen = 0
 
     @classmethod
-    def get(cls, group, world, mpad, dpad, n_local, dev):
+    def get(cls, group, world, n_local, d, dev, multicast=True):
         g = group if group is not None else dist.group.WORLD
-        key = (id(g), world, mpad, dpad, n_local, dev.index)
+        key = (id(g), world, n_local, d, dev.index, bool(multicast))
         if key not in cls._cache:
-            cls._cache[key] = cls(g, world, mpad, dpad, n_local, dev)
+            cls._cache[key] = cls(g, world, n_local, d, dev, multicast)
         return cls._cache[key]
 
-    def next(self):
-        self.parity ^= 1
-        self.gen[self.parity] += 1
-        return self.bufs[self.parity]
+    def next_gen(self):
+        self.gen += 1
+        return self.gen
 
 
-_P2P_BROKEN = False
+_P2P_STATE = {}   # id(group) -> True (peer arenas work on EVERY rank) / False (some rank failed: NCCL everywhere)
+
+
+def _p2p_available(group, world, n_local, d, dev, multicast, required):
+    """The transport must be the same on every rank (mixing peer flags with NCCL collectives would deadlock), so the
+    outcome of the arena set-up is agreed on collectively: MIN over the ranks of a success flag."""
+    g = group if group is not None else dist.group.WORLD
+    key = (id(g), world, n_local, d, dev.index, bool(multicast))
+    if key in _P2P_STATE:
+        return _P2P_STATE[key]
+    ok, err = 1, None
+    try:
+        _PeerArena.get(group, world, n_local, d, dev, multicast)
+    except Exception as e:  # noqa: BLE001  (symmetric memory unavailable on this system)
+        ok, err = 0, e
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    good = bool(flag.item())
+    _P2P_STATE[key] = good
+    if not good and required:
+        raise RuntimeError(f"transport='p2p' requested but peer-memory arenas are unavailable on some rank: {err!r}")
+    return good
 
 
 def _gather_slots(full, slot, group, inplace):
@@ -137,8 +184,7 @@ def _gather_slots(full, slot, group, inplace):
 
 class _NtxentDistFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, zi, zj, normalize, temperature, group, stages, transport, retain=True):
-        global _P2P_BROKEN
+    def forward(ctx, zi, zj, normalize, temperature, group, stages, transport):
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         cuda = isinstance(stages, CudaStages)
@@ -154,33 +200,26 @@ class _NtxentDistFn(torch.autograd.Function):
         norm = int(bool(normalize))
         inv_local = torch.empty(2 * n, dtype=torch.float32, device=dev)
         pos_local = torch.empty(2 * n, dtype=torch.float32, device=dev)
-        peer = None
-        if cuda and world > 1 and transport in ("auto", "p2p") and not _P2P_BROKEN:
-            try:
-                peer = _PeerTransport.get(group, world, mpad, dpad, n, dev)
-            except Exception:  # symmetric memory unavailable on this system: NCCL collectives instead
-                if transport == "p2p":
-                    raise
-                _P2P_BROKEN = True
-        if peer is not None:
-            zbuf, hz, sbuf, hs = peer.next()
+        use_p2p = False
+        multicast = transport != "p2p-unicast"
+        if cuda and world > 1 and transport in ("auto", "p2p", "p2p-unicast"):
+            use_p2p = _p2p_available(group, world, n, d, dev, multicast, required=transport != "auto")
+        if use_p2p:
+            arena = _PeerArena.get(group, world, n, d, dev, multicast)
+            gen = arena.next_gen()
             loss = torch.empty((), dtype=torch.float32, device=dev)
-            stages.prep_push(xi, xj, norm, float(temperature), world, rank, hz.buffer_ptrs_dev, inv_local, pos_local)
-            hz.barrier()
-            # the gathered rows are always copied out (16 MiB, ~10 us): the tensor-core kernels stream them many times and
-            # read a peer-mapped (symmetric-memory) buffer 12-15 % slower than ordinary device memory (measured at 2 GPUs)
-            zhat_all = zbuf.view(mpad, dpad).clone()
-            stat_all = sbuf.view(world, 2, 2 * n)
-            stages.rows_fwd_push(zhat_all, world, rank, n, d, norm, float(temperature), pos_local, hs.buffer_ptrs_dev, loss)
-            hs.barrier()
-            if retain:
-                stat_all = stat_all.clone()
-            stages.dist_loss(stat_all, world, n, loss)
-            ctx.save_for_backward(xi, xj, zhat_all, stat_all, inv_local)
-            ctx.cfg = (norm, float(temperature), world, rank, stages, zi.dtype, zj.dtype)
-            # without copies backward reads the transport buffers in place; they are double-buffered, so they stay
-            # intact until the SECOND forward after this one (checked in backward: fails loudly, never silently)
-            ctx.peer_ticket = None if retain else (peer, peer.parity, peer.gen[peer.parity])
+            loss_sum = torch.empty((), dtype=torch.float32, device=dev)
+            zhat_all = torch.empty(mpad, dpad, dtype=torch.bfloat16, device=dev)
+            colstat = torch.empty(mpad, dtype=torch.float32, device=dev)
+            tau = float(temperature)
+            stages.p2p_prep_push(xi, xj, norm, tau, world, rank, arena, gen, inv_local, pos_local)
+            stages.p2p_wait_copy(arena, world, rank, n, d, gen, zhat_all)
+            stages.p2p_rows_fwd(zhat_all, world, rank, n, d, norm, tau, pos_local, arena, gen, loss_sum)
+            stages.p2p_stat_loss(arena, world, rank, n, d, norm, tau, gen, colstat, loss)
+            # everything the backward needs is private memory: the arena is never read again after this forward
+            ctx.save_for_backward(xi, xj, zhat_all, colstat, inv_local)
+            ctx.cfg = (norm, tau, world, rank, stages, zi.dtype, zj.dtype)
+            ctx.p2p = True
             return loss
         zhat_all = torch.empty(mpad, dpad, dtype=torch.bfloat16, device=dev)
         # per rank: [lse2 (2L) | per-row loss term (2L)] -> one all-gather serves the backward AND the global loss
@@ -202,23 +241,20 @@ class _NtxentDistFn(torch.autograd.Function):
             loss = loss_sum / m
         ctx.save_for_backward(xi, xj, zhat_all, stat_all, inv_local)
         ctx.cfg = (norm, float(temperature), world, rank, stages, zi.dtype, zj.dtype)
-        ctx.peer_ticket = None
+        ctx.p2p = False
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
         xi, xj, zhat_all, stat_all, inv_local = ctx.saved_tensors
         norm, temperature, world, rank, stages, dti, dtj = ctx.cfg
-        if ctx.peer_ticket is not None:
-            peer, parity, gen = ctx.peer_ticket
-            if peer.gen[parity] != gen:
-                raise RuntimeError("DistributedSimclrLoss(retain_gathered=False): two more forwards ran before this "
-                                   "backward and re-used its gather buffers; construct the loss with "
-                                   "retain_gathered=True for this call pattern")
         go = C.f32_scalar(grad_out)
         dzi, dzj = torch.empty_like(xi), torch.empty_like(xj)
-        stages.rows_bwd(xi, xj, norm, temperature, world, rank, zhat_all, stat_all, inv_local, go, dzi, dzj)
-        return dzi.to(dti), dzj.to(dtj), None, None, None, None, None, None
+        if ctx.p2p:   # stat_all is the derived column-statistics vector here
+            stages.p2p_rows_bwd(xi, xj, norm, temperature, world, rank, zhat_all, stat_all, inv_local, go, dzi, dzj)
+        else:
+            stages.rows_bwd(xi, xj, norm, temperature, world, rank, zhat_all, stat_all, inv_local, go, dzi, dzj)
+        return dzi.to(dti), dzj.to(dtj), None, None, None, None, None
 
 
 class DistributedSimclrLoss(nn.Module):
@@ -226,12 +262,13 @@ class DistributedSimclrLoss(nn.Module):
     SimclrLoss (utils/losses.py:10-13) plus an optional process group."""
 
     def __init__(self, normalize=False, temperature=1.0, group=None, stages=None, transport="auto",
-                 retain_gathered=False):
-        """transport: "p2p" = kernels store into all peers' buffers over NVLink (torch symmetric memory) + barriers;
-        "nccl" = two all-gathers; "auto" = p2p when symmetric memory is available, else nccl.
-        retain_gathered (p2p only): False = backward reads the double-buffered statistics buffer in place (valid for the
-        usual forward -> backward -> forward loop and for one extra forward in between; anything else raises in
-        backward); True = forward copies it into a private tensor as well (the gathered rows are always copied)."""
+                 retain_gathered=True):
+        """transport: "p2p" = kernels store into all peers' arenas over NVLink (torch symmetric memory; one multicast
+        store through the NVSwitch when available) and poll generation flags on the device; "p2p-unicast" = the same
+        with per-peer stores only; "nccl" = two all-gathers; "auto" = p2p when the arenas can be set up on EVERY rank
+        (agreed collectively), else nccl.
+        retain_gathered: kept for API compatibility; the backward only ever reads private copies, so any
+        forward / backward interleaving is valid."""
         super().__init__()
         self.retain_gathered = retain_gathered
         self.normalize = normalize
@@ -241,8 +278,120 @@ class DistributedSimclrLoss(nn.Module):
         self.transport = transport
 
     def forward(self, zi, zj):
-        return _NtxentDistFn.apply(zi, zj, self.normalize, self.temperature, self.group, self.stages, self.transport,
-                                   self.retain_gathered)
+        return _NtxentDistFn.apply(zi, zj, self.normalize, self.temperature, self.group, self.stages, self.transport)
+
+
+# ======================================================================================================= ReLIC
+class RelicKlCudaStages:
+    """The KL term of the distributed ReLIC loss: `ssvb_relic_kl_dist_dots / _dist_reduce` + `ssvb_relic_kl_bwd`."""
+
+    def alloc_saved(self, n, dev):
+        return C.byte_buffer(C.cached_size("ssvb_relic_kl_saved_bytes", n), dev)
+
+    def dots(self, zi, zj, zo, normalize, temperature, saved, ab_local):
+        n, d = zi.shape
+        C.check(C.lib().ssvb_relic_kl_dist_dots(C.ptr(zi), C.ptr(zj), C.ptr(zo), n, d, zi.stride(0), zj.stride(0),
+                                                zo.stride(0), normalize, temperature, C.ptr(saved), C.ptr(ab_local),
+                                                C.stream_ptr(zi.device)), "ssvb_relic_kl_dist_dots")
+
+    def reduce(self, ab_all, world, n_local, alpha, saved, kl):
+        C.check(C.lib().ssvb_relic_kl_dist_reduce(C.ptr(ab_all), world, n_local, alpha, C.ptr(saved), C.ptr(kl),
+                                                  C.stream_ptr(ab_all.device)), "ssvb_relic_kl_dist_reduce")
+
+    def bwd(self, zi, zj, zo, normalize, temperature, alpha, grad_out, saved, dzi, dzj, dzo):
+        n, d = zi.shape
+        C.check(C.lib().ssvb_relic_kl_bwd(C.ptr(zi), C.ptr(zj), C.ptr(zo), n, d, zi.stride(0), zj.stride(0),
+                                          zo.stride(0), normalize, temperature, alpha, C.ptr(grad_out), C.ptr(saved),
+                                          C.ptr(dzi), C.ptr(dzj), C.ptr(dzo), dzi.stride(0), dzj.stride(0),
+                                          dzo.stride(0), C.stream_ptr(zi.device)), "ssvb_relic_kl_bwd")
+
+
+class _RelicKlDistFn(torch.autograd.Function):
+    """alpha * KL_quirk of RelicLoss (utils/losses.py:196-200) with the two softmaxes taken over the GLOBAL batch axis:
+    one all-gather of this rank's two N_local-vectors of logits; no exchange in backward (the global softmax
+    statistics are identical on every rank and each rank differentiates its own rows)."""
+
+    @staticmethod
+    def forward(ctx, zi, zj, zo, normalize, temperature, alpha, group, stages):
+        world, rank = _world_rank(group)
+        cuda = isinstance(stages, RelicKlCudaStages)
+        if cuda:
+            C.require_cuda(zi, zj, zo)
+            xi, xj, xo = C.as_f32_rows(zi), C.as_f32_rows(zj), C.as_f32_rows(zo)
+        else:
+            xi, xj, xo = (t.detach().float().contiguous() for t in (zi, zj, zo))
+        n = xi.shape[0]
+        dev = xi.device
+        norm = int(bool(normalize))
+        saved = stages.alloc_saved(n, dev)
+        ab_all = torch.empty(world, 2, n, dtype=torch.float32, device=dev)
+        stages.dots(xi, xj, xo, norm, float(temperature), saved, ab_all[rank])
+        if world > 1:
+            _gather_slots(ab_all.view(world * 2, n), ab_all[rank], group, inplace=cuda and _is_nccl(group))
+        kl = torch.empty((), dtype=torch.float32, device=dev)
+        stages.reduce(ab_all, world, n, float(alpha), saved, kl)
+        if torch.is_tensor(saved):
+            ctx.save_for_backward(xi, xj, xo, saved)
+        else:   # emulated stages (tests) keep a host-side object
+            ctx.save_for_backward(xi, xj, xo)
+            ctx.saved_obj = saved
+        ctx.cfg = (norm, float(temperature), float(alpha), stages, zi.dtype, zj.dtype, zo.dtype)
+        return kl
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if len(ctx.saved_tensors) == 4:
+            xi, xj, xo, saved = ctx.saved_tensors
+        else:
+            (xi, xj, xo), saved = ctx.saved_tensors, ctx.saved_obj
+        norm, temperature, alpha, stages, dti, dtj, dto = ctx.cfg
+        go = C.f32_scalar(grad_out)
+        # ssvb_relic_kl_bwd ACCUMULATES into dzi / dzj (it composes with the contrastive backward) and overwrites dzo
+        dzi, dzj, dzo = torch.zeros_like(xi), torch.zeros_like(xj), torch.empty_like(xo)
+        stages.bwd(xi, xj, xo, norm, temperature, alpha, go, saved, dzi, dzj, dzo)
+        return dzi.to(dti), dzj.to(dtj), dzo.to(dto), None, None, None, None, None
+
+
+class DistributedRelicLoss(nn.Module):
+    """RelicLoss (reference utils/losses.py:154-201, same ctor kwargs) over the global batch of a process group:
+    contrastive term = DistributedSimclrLoss (rows all-gathered over NVLink, no gradient exchange), KL term = the
+    batch-axis softmaxes over the all-gathered per-row logits (SURVEY.md §8e last row).  Every rank gets the gradient
+    rows of its own inputs; the value equals the single-process RelicLoss on the rank-order concatenation."""
+
+    def __init__(self, normalize=True, temperature=1.0, alpha=0.5, group=None, stages=None, kl_stages=None,
+                 transport="auto"):
+        super().__init__()
+        self.normalize = normalize
+        self.temperature = temperature
+        self.alpha = alpha
+        self.group = group
+        self.contrastive = DistributedSimclrLoss(normalize, temperature, group=group, stages=stages, transport=transport)
+        self.kl_stages = kl_stages if kl_stages is not None else RelicKlCudaStages()
+
+    def forward(self, zi, zj, z_orig):
+        kl = _RelicKlDistFn.apply(zi, zj, z_orig, self.normalize, self.temperature, self.alpha, self.group,
+                                  self.kl_stages)
+        return self.contrastive(zi, zj) + kl   # contrastive + alpha * KL (utils/losses.py:201)
+
+
+# ======================================================================================================= DINO centre
+@torch.no_grad()
+def distributed_update_teacher_center(center, teacher_fvecs, momentum, group=None):
+    """models/dino.py:136-141 over the global batch of a process group: the batch mean of the teacher outputs is taken
+    over ALL ranks' rows (all-reduce of the K-vector of row sums + the row count, so unequal per-rank batches are
+    weighted correctly), then the same EMA kernel as the single-GPU `update_teacher_center`.  `center` may be None on
+    the first call, as in the reference.  Every rank ends up with the identical centre."""
+    from .losses import update_teacher_center
+    world, _ = _world_rank(group)
+    local_mean = update_teacher_center(None, teacher_fvecs, 0.0)   # first call == plain batch mean (one kernel)
+    if world > 1:
+        rows = teacher_fvecs.numel() // teacher_fvecs.shape[-1]
+        packed = torch.cat([local_mean * float(rows), local_mean.new_full((1,), float(rows))])
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        local_mean = packed[:-1] / packed[-1]
+    if center is None:
+        return local_mean
+    return update_teacher_center(center, local_mean.view(1, -1), momentum)
 
 
 # ======================================================================================================= helpers

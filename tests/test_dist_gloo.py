@@ -484,3 +484,85 @@ def test_distributed_moco_sharded_queue_matches_global_oracle(tau):
         assert np.linalg.norm(o["dq"] - 0.5 * ref_dq[sl]) / np.linalg.norm(0.5 * ref_dq[sl]) < 2e-2  # bf16 query gather
         assert np.linalg.norm(o["dk"] - 0.5 * ref_dk[sl]) / np.linalg.norm(0.5 * ref_dk[sl]) < 2e-2
     assert out[0]["loss"] == out[1]["loss"]
+
+
+# ======================================================================================================= ReLIC (KL over the global batch axis)
+class EmulatedRelicKlStages:
+    """torch-fp64 stand-in for ssvb_relic_kl_dist_dots / _dist_reduce / ssvb_relic_kl_bwd (test-only)."""
+
+    def alloc_saved(self, n, dev):
+        return {}
+
+    def dots(self, zi, zj, zo, normalize, temperature, saved, ab_local):
+        def nrm(z):
+            z = z.double()
+            den = z.norm(dim=1, keepdim=True).clamp_min(1e-12) if normalize else torch.ones(z.shape[0], 1, dtype=torch.float64)
+            return z / den, den
+        (ih, idn), (jh, jdn), (oh, odn) = nrm(zi), nrm(zj), nrm(zo)
+        a, b = (ih * oh).sum(1) / temperature, (jh * oh).sum(1) / temperature
+        saved.update(ih=ih, jh=jh, oh=oh, idn=idn, jdn=jdn, odn=odn, a=a, b=b)
+        ab_local[0].copy_(a.float())
+        ab_local[1].copy_(b.float())
+
+    def reduce(self, ab_all, world, n_local, alpha, saved, kl):
+        a = ab_all[:, 0, :].reshape(-1).double()      # rank-order concatenation = the global batch axis
+        b = ab_all[:, 1, :].reshape(-1).double()
+        lse_a, lse_b = torch.logsumexp(a, 0), torch.logsumexp(b, 0)
+        p, lq = torch.exp(a - lse_a), b - lse_b
+        q = torch.exp(lq)
+        klv = (q * (lq - p)).sum()
+        saved.update(lse_a=lse_a, lse_b=lse_b, spq=(p * q).sum(), kl=klv)
+        kl.copy_((alpha * klv).float())
+
+    def bwd(self, zi, zj, zo, normalize, temperature, alpha, grad_out, saved, dzi, dzj, dzo):
+        s = saved
+        p, lq = torch.exp(s["a"] - s["lse_a"]), s["b"] - s["lse_b"]
+        q = torch.exp(lq)
+        g = grad_out.double() * alpha / temperature
+        da = -(p * q - p * s["spq"]) * g
+        db = (q * (lq - p) + q - q * (s["kl"] + 1.0)) * g
+        dih, djh = da[:, None] * s["oh"], db[:, None] * s["oh"]
+        doh = da[:, None] * s["ih"] + db[:, None] * s["jh"]
+
+        def back(dh, h, den):
+            return (dh - (dh * h).sum(1, keepdim=True) * h) / den if normalize else dh
+        dzi.add_(back(dih, s["ih"], s["idn"]).float())
+        dzj.add_(back(djh, s["jh"], s["jdn"]).float())
+        dzo.copy_(back(doh, s["oh"], s["odn"]).float())
+
+
+def _relic_worker(rank, world, port, n_local, d, normalize, tau, alpha, out):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "self-supervised-vision_b200")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ssv_b200.dist import DistributedRelicLoss
+    g = torch.Generator().manual_seed(300 + rank)
+    zi, zj, zo = (torch.randn(n_local, d, generator=g, requires_grad=True) for _ in range(3))
+    fn = DistributedRelicLoss(normalize, tau, alpha, stages=EmulatedStages(), kl_stages=EmulatedRelicKlStages())
+    loss = fn(zi, zj, zo)
+    loss.backward()
+    out[rank] = (loss.item(),) + tuple(t.grad.numpy().copy() for t in (zi, zj, zo)) + \
+        tuple(t.detach().numpy().copy() for t in (zi, zj, zo))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("normalize,tau,alpha", [(True, 1.0, 0.5), (True, 0.5, 2.0)])
+def test_distributed_relic_matches_global_oracle(normalize, tau, alpha):
+    """DistributedRelicLoss under gloo (world 2): the KL's batch-axis softmaxes must span BOTH ranks' rows
+    (reference utils/losses.py:196-200 on the concatenation), each rank gets its own gradient rows."""
+    from oracle import ssl_oracle as O
+    world, n_local, d = 2, 20, 16
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 2000) + 7
+    mp.spawn(_relic_worker, args=(world, port, n_local, d, normalize, tau, alpha, out), nprocs=world, join=True)
+    zi, zj, zo = (np.concatenate([out[r][4 + k] for r in range(world)]) for k in range(3))
+    ref = O.relic(zi, zj, zo, normalize, tau, alpha)
+    for r in range(world):
+        sl = slice(r * n_local, (r + 1) * n_local)
+        assert abs(out[r][0] - ref[0]) / abs(ref[0]) < 1e-4
+        for k in range(3):
+            g, rg = out[r][1 + k], ref[1 + k][sl]
+            assert np.linalg.norm(g - rg) / np.linalg.norm(rg) < 2e-2, f"rank {r} grad {k}"
+    assert out[0][0] == out[1][0]

@@ -283,3 +283,154 @@ def test_dist_barlow_colshard_emulated_ranks(S, n, d, world, norm):
                                             C.ptr(out[sl[q]]), d, st), "cs_finish")
     assert rel_l2(di.cpu().numpy(), ref_di) <= 1e-2
     assert rel_l2(dj.cpu().numpy(), ref_dj) <= 1e-2
+
+
+# ------------------------------------------------------------------------------------------------ NT-Xent (headline multi-GPU path)
+@pytest.mark.parametrize("world,n,d,norm,tau", [(4, 96, 128, True, 0.5), (2, 256, 64, True, 0.07), (3, 100, 96, False, 1.0),
+                                                (8, 64, 128, True, 0.5), (4, 512, 128, True, 0.02)])
+def test_dist_ntxent_emulated_ranks(S, world, n, d, norm, tau):
+    """The row-sharded NT-Xent stages (ssvb_ntxent_dist_prep / rows_fwd / dist_loss / rows_bwd) with `world` ranks
+    emulated in ONE process: every rank's slot is written into one shared gathered matrix (= the all-gather of the
+    normalised rows), every rank's [lse | term] block into one statistics buffer (= the second all-gather), and every
+    rank's backward reads only those two buffers.  Checked against the fp64 oracle on the rank-order concatenation of
+    the inputs (SURVEY.md §8e semantics; reference math utils/losses.py:15-46): loss, and each rank's gradient rows."""
+    from ssv_b200 import _cabi as C
+    from ssv_b200.dist import CudaStages
+    stg = CudaStages()
+    zi, zj = randn(0, world * n, d), randn(1, world * n, d)
+    if 0.05 < tau < 0.1:  # peaky softmax: correlated positives (at tau = 0.02 that would make the loss ~1e-9)
+        zj = (0.8 * zi + 0.6 * zj).astype(np.float32)
+    ref_loss, ref_di, ref_dj = O.ntxent(zi, zj, norm, tau)
+    Zi, Zj = dev(zi, False), dev(zj, False)
+    mpad, dpad = stg.mpad(n * world), stg.dpad(d)
+    zhat_all = torch.zeros(mpad, dpad, dtype=torch.bfloat16, device="cuda")
+    stat_all = torch.empty(world, 2, 2 * n, dtype=torch.float32, device="cuda")
+    inv = [torch.empty(2 * n, device="cuda") for _ in range(world)]
+    pos = [torch.empty(2 * n, device="cuda") for _ in range(world)]
+    sums = [torch.zeros((), device="cuda") for _ in range(world)]
+    sl = [slice(r * n, (r + 1) * n) for r in range(world)]
+    for r in range(world):
+        stg.prep(Zi[sl[r]], Zj[sl[r]], int(norm), tau, world, r, zhat_all, inv[r], pos[r])
+    for r in range(world):
+        stg.rows_fwd(zhat_all, world, r, n, d, int(norm), tau, pos[r], stat_all[r], sums[r])
+    loss = torch.empty((), device="cuda")
+    stg.dist_loss(stat_all, world, n, loss)
+    m = 2 * n * world
+    assert rel_scalar(loss.item(), ref_loss) <= 1e-3
+    assert rel_scalar(sum(s.item() for s in sums) / m, ref_loss) <= 1e-3   # the NCCL transport's world = 1 reduction
+    go = torch.full((), 1.5, device="cuda")
+    for r in range(world):
+        dzi, dzj = torch.empty(n, d, device="cuda"), torch.empty(n, d, device="cuda")
+        stg.rows_bwd(Zi[sl[r]], Zj[sl[r]], int(norm), tau, world, r, zhat_all, stat_all, inv[r], go, dzi, dzj)
+        assert rel_l2(dzi.cpu().numpy(), 1.5 * ref_di[sl[r]]) <= 1e-2, f"rank {r} dzi"
+        assert rel_l2(dzj.cpu().numpy(), 1.5 * ref_dj[sl[r]]) <= 1e-2, f"rank {r} dzj"
+
+
+@pytest.mark.parametrize("world,n,d,norm,tau", [(4, 96, 128, True, 0.5), (8, 64, 128, True, 0.5), (2, 300, 64, True, 0.07),
+                                                (3, 100, 96, False, 1.0)])
+def test_dist_ntxent_p2p_emulated_ranks(S, world, n, d, norm, tau):
+    """The NVLink peer-memory transport (ssvb_ntxent_p2p_*: pushes into every rank's arena + generation flags) with
+    the ranks emulated on ONE GPU: `world` arenas in the same device memory stand in for the peer-mapped arenas, the
+    kernels are the ones the multi-GPU path launches (unicast stores).  Three generations with different inputs
+    exercise both buffer parities and the monotonic flags; the loss must be bit-identical on every rank."""
+    from ssv_b200 import _cabi as C
+    from ssv_b200.dist import CudaStages
+    stg = CudaStages()
+    nbytes = C.lib().ssvb_ntxent_p2p_arena_bytes(world, n, d)
+    arenas = [torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    peers = torch.tensor([a.data_ptr() for a in arenas], dtype=torch.int64, device="cuda")
+
+    class Arena:
+        def __init__(self, r):
+            self.local_ptr, self.peers_dev, self.multicast_ptr = arenas[r].data_ptr(), peers.data_ptr(), 0
+    ar = [Arena(r) for r in range(world)]
+    mpad, dpad = stg.mpad(n * world), stg.dpad(d)
+    sl = [slice(r * n, (r + 1) * n) for r in range(world)]
+    for gen in (1, 2, 3):
+        zi, zj = randn(10 * gen, world * n, d), randn(10 * gen + 1, world * n, d)
+        if tau < 0.1:
+            zj = (0.8 * zi + 0.6 * zj).astype(np.float32)
+        ref_loss, ref_di, ref_dj = O.ntxent(zi, zj, norm, tau)
+        Zi, Zj = dev(zi, False), dev(zj, False)
+        inv = [torch.empty(2 * n, device="cuda") for _ in range(world)]
+        pos = [torch.empty(2 * n, device="cuda") for _ in range(world)]
+        zh = [torch.empty(mpad, dpad, dtype=torch.bfloat16, device="cuda") for _ in range(world)]
+        cs = [torch.empty(mpad, device="cuda") for _ in range(world)]
+        losses = [torch.empty((), device="cuda") for _ in range(world)]
+        tmp = torch.empty((), device="cuda")
+        for r in range(world):
+            stg.p2p_prep_push(Zi[sl[r]], Zj[sl[r]], int(norm), tau, world, r, ar[r], gen, inv[r], pos[r])
+        for r in range(world):
+            stg.p2p_wait_copy(ar[r], world, r, n, d, gen, zh[r])
+        for r in range(1, world):
+            assert torch.equal(zh[0][:2 * n * world], zh[r][:2 * n * world]), "every rank must gather the same rows"
+        for r in range(world):
+            stg.p2p_rows_fwd(zh[r], world, r, n, d, int(norm), tau, pos[r], ar[r], gen, tmp)
+        for r in range(world):
+            stg.p2p_stat_loss(ar[r], world, r, n, d, int(norm), tau, gen, cs[r], losses[r])
+        torch.cuda.synchronize()
+        assert all(torch.equal(losses[0], l) for l in losses), "the global loss must be bit-identical on every rank"
+        assert rel_scalar(losses[0].item(), ref_loss) <= 1e-3, f"gen {gen}"
+        go = torch.full((), 0.5, device="cuda")
+        for r in range(world):
+            dzi, dzj = torch.empty(n, d, device="cuda"), torch.empty(n, d, device="cuda")
+            stg.p2p_rows_bwd(Zi[sl[r]], Zj[sl[r]], int(norm), tau, world, r, zh[r], cs[r], inv[r], go, dzi, dzj)
+            assert rel_l2(dzi.cpu().numpy(), 0.5 * ref_di[sl[r]]) <= 1e-2, f"gen {gen} rank {r} dzi"
+            assert rel_l2(dzj.cpu().numpy(), 0.5 * ref_dj[sl[r]]) <= 1e-2, f"gen {gen} rank {r} dzj"
+
+
+# ------------------------------------------------------------------------------------------------ ReLIC (KL over the global batch)
+@pytest.mark.parametrize("n,d,tau,alpha", [(512, 128, 1.0, 0.5), (300, 64, 0.5, 2.0)])
+def test_dist_relic_world1(S, n, d, tau, alpha):
+    from ssv_b200.dist import DistributedRelicLoss
+    zi, zj, zo = randn(0, n, d), randn(1, n, d), randn(2, n, d)
+    ref = O.relic(zi, zj, zo, True, tau, alpha)
+    a, b, c = dev(zi), dev(zj), dev(zo)
+    loss = DistributedRelicLoss(True, tau, alpha)(a, b, c)
+    loss.backward()
+    check(loss.item(), [a.grad, b.grad, c.grad], ref[0], ref[1:], f"dist relic world=1 n={n}")
+
+
+@pytest.mark.parametrize("world,n,d,tau,alpha", [(4, 96, 128, 1.0, 0.5), (3, 100, 64, 0.5, 1.5)])
+def test_dist_relic_kl_emulated_ranks(S, world, n, d, tau, alpha):
+    """The KL stages of the distributed ReLIC loss with the ranks emulated in one process: per-rank dots, the all-gather
+    = one shared [world][2][n] buffer, per-rank reduce + backward.  KL value and gradients = oracle RelicLoss minus
+    oracle NT-Xent (the contrastive part) on the concatenation (reference utils/losses.py:196-200)."""
+    from ssv_b200.dist import RelicKlCudaStages
+    stg = RelicKlCudaStages()
+    zi, zj, zo = randn(0, world * n, d), randn(1, world * n, d), randn(2, world * n, d)
+    full = O.relic(zi, zj, zo, True, tau, alpha)
+    con = O.ntxent(zi, zj, True, tau)
+    ref_kl, ref_di, ref_dj, ref_do = full[0] - con[0], full[1] - con[1], full[2] - con[2], full[3]
+    Zi, Zj, Zo = dev(zi, False), dev(zj, False), dev(zo, False)
+    sl = [slice(r * n, (r + 1) * n) for r in range(world)]
+    ab_all = torch.empty(world, 2, n, device="cuda")
+    saved = [stg.alloc_saved(n, Zi.device) for _ in range(world)]
+    for r in range(world):
+        stg.dots(Zi[sl[r]], Zj[sl[r]], Zo[sl[r]], 1, tau, saved[r], ab_all[r])
+    kls = [torch.empty((), device="cuda") for _ in range(world)]
+    for r in range(world):
+        stg.reduce(ab_all, world, n, alpha, saved[r], kls[r])
+    assert all(torch.equal(kls[0], k) for k in kls)
+    assert rel_scalar(kls[0].item(), ref_kl) <= 1e-3
+    go = torch.ones((), device="cuda")
+    for r in range(world):
+        dzi, dzj, dzo = torch.zeros(n, d, device="cuda"), torch.zeros(n, d, device="cuda"), torch.empty(n, d, device="cuda")
+        stg.bwd(Zi[sl[r]], Zj[sl[r]], Zo[sl[r]], 1, tau, alpha, go, saved[r], dzi, dzj, dzo)
+        assert rel_l2(dzi.cpu().numpy(), ref_di[sl[r]]) <= 1e-2
+        assert rel_l2(dzj.cpu().numpy(), ref_dj[sl[r]]) <= 1e-2
+        assert rel_l2(dzo.cpu().numpy(), ref_do[sl[r]]) <= 1e-2
+
+
+def test_dist_dino_center_world1(S):
+    """distributed_update_teacher_center without a process group == the single-GPU kernel == the oracle
+    (reference models/dino.py:136-141)."""
+    from ssv_b200.dist import distributed_update_teacher_center
+    t = randn(0, 64, 2, 1024)
+    c0 = 0.1 * randn(1, 1024)
+    ref_first = O.dino_center_update(None, t.reshape(-1, 1024), 0.9)
+    ref = O.dino_center_update(c0, t.reshape(-1, 1024), 0.9)
+    got_first = distributed_update_teacher_center(None, dev(t.reshape(-1, 1024), False), 0.9)
+    got = distributed_update_teacher_center(dev(c0, False), dev(t.reshape(-1, 1024), False), 0.9)
+    np.testing.assert_allclose(got_first.cpu().numpy(), ref_first, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=2e-5, atol=1e-6)

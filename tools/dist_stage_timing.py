@@ -4,7 +4,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "self-supervised-vision_b200")]
 import torch, torch.distributed as dist
-from ssv_b200.dist import CudaStages, _gather_slots, _PeerTransport
+from ssv_b200.dist import CudaStages, _gather_slots, _PeerArena
 
 rank, world, lr_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr_)
@@ -22,7 +22,7 @@ inv = torch.empty(2 * n, device=dev); pos = torch.empty(2 * n, device=dev)
 stat = torch.empty(world, 2, 2 * n, device=dev); ls = torch.zeros((), device=dev)
 go = torch.ones((), device=dev); dzi = torch.empty_like(zi); dzj = torch.empty_like(zj)
 my = slice(rank * 2 * n, (rank + 1) * 2 * n)
-peer = _PeerTransport.get(None, world, mpad, dpad, n, dev)
+colstat = torch.empty(mpad, device=dev); loss = torch.empty((), device=dev)
 reps = 30
 
 
@@ -52,19 +52,23 @@ def nccl_body(ev):
     st.rows_bwd(zi, zj, 1, tau, world, rank, zhat, stat, inv, go, dzi, dzj); ev[6].record()
 
 
-def p2p_body(ev):
-    zbuf, hz, sbuf, hs = peer.next()
-    st.prep_push(zi, zj, 1, 0.5, world, rank, hz.buffer_ptrs_dev, inv, pos); ev[1].record()
-    hz.barrier(); ev[2].record()
-    z = zbuf.view(mpad, dpad).clone()
-    st.rows_fwd_push(z, world, rank, n, d, 1, tau, pos, hs.buffer_ptrs_dev, ls); ev[3].record()
-    hs.barrier(); ev[4].record()
-    s_all = sbuf.view(world, 2, 2 * n); st.dist_loss(s_all, world, n, ls); ev[5].record()
-    st.rows_bwd(zi, zj, 1, tau, world, rank, z, s_all, inv, go, dzi, dzj); ev[6].record()
+def make_p2p_body(arena):
+    def p2p_body(ev):
+        gen = arena.next_gen()
+        st.p2p_prep_push(zi, zj, 1, tau, world, rank, arena, gen, inv, pos); ev[1].record()
+        st.p2p_wait_copy(arena, world, rank, n, d, gen, zhat); ev[2].record()
+        st.p2p_rows_fwd(zhat, world, rank, n, d, 1, tau, pos, arena, gen, ls); ev[3].record()
+        st.p2p_stat_loss(arena, world, rank, n, d, 1, tau, gen, colstat, loss); ev[4].record()
+        st.p2p_rows_bwd(zi, zj, 1, tau, world, rank, zhat, colstat, inv, go, dzi, dzj); ev[5].record()
+    return p2p_body
 
 
 if rank == 0: print("--- NCCL transport")
 run(["prep", "allgather zhat", "rows_fwd", "allgather stat", "loss", "rows_bwd"], nccl_body)
-if rank == 0: print("--- peer-memory transport")
-run(["prep+push", "barrier", "rows_fwd+push", "barrier", "loss", "rows_bwd"], p2p_body)
+P2P = ["prep+push+flags", "wait+copy", "rows_fwd+push+flags", "wait+stat+loss", "rows_bwd"]
+if world > 1:
+    for mc in (True, False):
+        arena = _PeerArena.get(None, world, n, d, dev, multicast=mc)
+        if rank == 0: print(f"--- peer-memory transport, multicast={'on' if (mc and arena.multicast_ptr) else 'off'}")
+        run(P2P, make_p2p_body(arena))
 dist.destroy_process_group()
