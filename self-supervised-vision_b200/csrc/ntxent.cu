@@ -585,24 +585,37 @@ ArenaLayout arena_layout(int64_t world, int64_t n_local, int64_t dpad) {
 }
 
 namespace {
-__global__ void p2p_prep_push_kernel(const float* __restrict__ xi, const float* __restrict__ xj, int n, int d,
+// ROWS_PER_WARP row pairs per warp with all their loads issued up front (the one-row-per-warp form is latency-bound:
+// one 16-byte load per lane in flight), 8 warps per CTA.
+constexpr int P2P_RPW = 4;
+__global__ void __launch_bounds__(256)
+p2p_prep_push_kernel(const float* __restrict__ xi, const float* __restrict__ xj, int n, int d,
                                      int64_t ldi, int64_t ldj, int normalize, int f16, float prescale,
                                      uint8_t* const* __restrict__ peers, uint8_t* mc_base, size_t zoff, size_t flag_off,
                                      unsigned int* counter, int world, int rank, int64_t row_i, int64_t row_j, int dpad,
                                      float* __restrict__ inv_i, float* __restrict__ inv_j, float* __restrict__ pos_i,
                                      float* __restrict__ pos_j, uint32_t gen) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp < n) {
-    const float* ri = xi + static_cast<int64_t>(warp) * ldi;
-    const float* rj = xj + static_cast<int64_t>(warp) * ldj;
-    const int k = lane * 4;  // dpad <= 128: one float4 per lane
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (k < d) {
-      a = *reinterpret_cast<const float4*>(ri + k);
-      b = *reinterpret_cast<const float4*>(rj + k);
+  const int r0 = warp * P2P_RPW;
+  const int k = lane * 4;  // dpad <= 128: one float4 per lane and row
+  float4 a[P2P_RPW], b[P2P_RPW];
+#pragma unroll
+  for (int j = 0; j < P2P_RPW; ++j) {
+    a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    b[j] = a[j];
+    if (r0 + j < n && k < d) {
+      a[j] = __ldg(reinterpret_cast<const float4*>(xi + static_cast<int64_t>(r0 + j) * ldi + k));
+      b[j] = __ldg(reinterpret_cast<const float4*>(xj + static_cast<int64_t>(r0 + j) * ldj + k));
     }
-    const float si = warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w);
-    const float sj = warp_sum(b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w);
+  }
+  // start at a different peer per CTA so the ranks do not all hit the same NVLink port at the same time
+  const int p0 = static_cast<int>(blockIdx.x % static_cast<unsigned>(world));
+#pragma unroll
+  for (int j = 0; j < P2P_RPW; ++j) {
+    const int row = r0 + j;
+    if (row >= n) break;  // warp-uniform
+    const float si = warp_sum(a[j].x * a[j].x + a[j].y * a[j].y + a[j].z * a[j].z + a[j].w * a[j].w);
+    const float sj = warp_sum(b[j].x * b[j].x + b[j].y * b[j].y + b[j].z * b[j].z + b[j].w * b[j].w);
     float ivi = 1.f, ivj = 1.f;
     if (normalize) {
       ivi = 1.f / fmaxf(sqrtf(si), 1e-12f);
@@ -610,22 +623,20 @@ __global__ void p2p_prep_push_kernel(const float* __restrict__ xi, const float* 
     }
     const float si_ = ivi * prescale, sj_ = ivj * prescale;
     uint2 vi, vj;
-    vi.x = f16 ? pack_f16x2(a.x * si_, a.y * si_) : pack_bf16x2(a.x * si_, a.y * si_);
-    vi.y = f16 ? pack_f16x2(a.z * si_, a.w * si_) : pack_bf16x2(a.z * si_, a.w * si_);
-    vj.x = f16 ? pack_f16x2(b.x * sj_, b.y * sj_) : pack_bf16x2(b.x * sj_, b.y * sj_);
-    vj.y = f16 ? pack_f16x2(b.z * sj_, b.w * sj_) : pack_bf16x2(b.z * sj_, b.w * sj_);
+    vi.x = f16 ? pack_f16x2(a[j].x * si_, a[j].y * si_) : pack_bf16x2(a[j].x * si_, a[j].y * si_);
+    vi.y = f16 ? pack_f16x2(a[j].z * si_, a[j].w * si_) : pack_bf16x2(a[j].z * si_, a[j].w * si_);
+    vj.x = f16 ? pack_f16x2(b[j].x * sj_, b[j].y * sj_) : pack_bf16x2(b[j].x * sj_, b[j].y * sj_);
+    vj.y = f16 ? pack_f16x2(b[j].z * sj_, b[j].w * sj_) : pack_bf16x2(b[j].z * sj_, b[j].w * sj_);
     const float2 fi01 = unpack_h2(vi.x, f16), fi23 = unpack_h2(vi.y, f16);
     const float2 fj01 = unpack_h2(vj.x, f16), fj23 = unpack_h2(vj.y, f16);
     const float dot = warp_sum(fi01.x * fj01.x + fi01.y * fj01.y + fi23.x * fj23.x + fi23.y * fj23.y);
     if (k < dpad) {
-      const size_t oi = zoff + (static_cast<size_t>(row_i + warp) * dpad + k) * 2;
-      const size_t oj = zoff + (static_cast<size_t>(row_j + warp) * dpad + k) * 2;
+      const size_t oi = zoff + (static_cast<size_t>(row_i + row) * dpad + k) * 2;
+      const size_t oj = zoff + (static_cast<size_t>(row_j + row) * dpad + k) * 2;
       if (mc_base) {  // one store each through the NVSwitch multicast mapping reaches every rank's arena
         multimem_st_v2(mc_base + oi, vi);
         multimem_st_v2(mc_base + oj, vj);
       } else {
-        // start at a different peer per CTA so the ranks do not all hit the same NVLink port at the same time
-        const int p0 = static_cast<int>(blockIdx.x % static_cast<unsigned>(world));
         for (int q = 0; q < world; ++q) {
           uint8_t* base = peers[(p0 + q) % world];
           *reinterpret_cast<uint2*>(base + oi) = vi;
@@ -634,22 +645,23 @@ __global__ void p2p_prep_push_kernel(const float* __restrict__ xi, const float* 
       }
     }
     if (lane == 0) {
-      inv_i[warp] = ivi; inv_j[warp] = ivj; pos_i[warp] = dot; pos_j[warp] = dot;
+      inv_i[row] = ivi; inv_j[row] = ivj; pos_i[row] = dot; pos_j[row] = dot;
     }
   }
-  // publish: every thread's peer stores are performed system-wide, then the last block to finish raises this rank's
-  // flag in every arena
-  __threadfence_system();
+  // publish: CTA barrier, then ONE thread fences at system scope (cumulative over the stores it has observed through
+  // the barrier - the cooperative-groups grid-sync idiom) and counts the CTA in; the last CTA raises this rank's flag
+  // in every arena.
   __syncthreads();
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned int done = atomicAdd(counter, 1u);
     is_last = (done == gridDim.x - 1);
   }
   __syncthreads();
   if (is_last) {
-    __threadfence_system();
     if (threadIdx.x < world) {
+      __threadfence_system();
       uint32_t* f = reinterpret_cast<uint32_t*>(peers[threadIdx.x] + flag_off);
       st_release_sys_u32(f + rank, gen);
     }
@@ -724,7 +736,7 @@ int ssvb_ntxent_p2p_prep_push(const float* zi, const float* zj, int64_t n_local,
   const ArenaLayout al = arena_layout(world, n_local, pl.dpad);
   const int64_t row0 = rank * 2 * n_local;
   const uint32_t g = static_cast<uint32_t>(gen);
-  p2p_prep_push_kernel<<<static_cast<unsigned>(ceil_div(n_local, 8)), 256, 0, s>>>(
+  p2p_prep_push_kernel<<<static_cast<unsigned>(ceil_div(n_local, 8 * P2P_RPW)), 256, 0, s>>>(
       zi, zj, static_cast<int>(n_local), static_cast<int>(d), ld_zi, ld_zj, normalize, normalize ? 1 : 0, pl.prescale,
       reinterpret_cast<uint8_t* const*>(peer_arenas), static_cast<uint8_t*>(multicast_arena), al.zhat[g & 1], al.flags,
       reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(arena_local) + al.counter), static_cast<int>(world),

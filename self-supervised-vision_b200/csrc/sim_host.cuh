@@ -242,11 +242,12 @@ __device__ __forceinline__ float block_sum_256(float v) {
   return t;  // valid in warp 0
 }
 __device__ __forceinline__ bool grid_sum_finish(float block_total, float* block_sums, unsigned int* counter,
-                                                float scale, float* out, bool accumulate) {
+                                                float scale, float* out, bool accumulate, bool sys_fence = false) {
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
     block_sums[blockIdx.x] = block_total;
-    __threadfence();
+    if (sys_fence) __threadfence_system();  // the CTA also stored into peer memory: order those stores too
+    else __threadfence();
     const unsigned int done = atomicAdd(counter, 1u);
     is_last = (done == gridDim.x - 1);
   }
@@ -338,9 +339,9 @@ __global__ void lse_finalize_kernel(const float* __restrict__ part_m, const floa
       }
     }
   }
-  if (peer_stat && peer_flag_off) __threadfence_system();  // this thread's peer stores are performed system-wide
-  const float bt = block_sum_256(term);
-  const bool last = grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false);
+  const float bt = block_sum_256(term);  // (contains CTA barriers: thread 0 has observed every thread's peer stores)
+  __syncthreads();
+  const bool last = grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false, peer_stat && peer_flag_off);
   if (peer_stat && peer_flag_off && last && threadIdx.x < world) {
     // every block fenced its peer stores before its counter increment: publish "statistics of generation `gen`
     // from rank `rank` are complete" in every peer's flag array

@@ -15,7 +15,10 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # SSVB_LIB selects an A/B tuning build (e.g. libssv_b200_x.so) for experiments; default is the product build
 LIB_PATH = os.path.join(_HERE, os.environ.get("SSVB_LIB", "libssv_b200.so"))
-HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "ssv_b200.h"))
+# the header the prototypes are bound from: the repository's include/ when the package runs in-tree (always current),
+# else the copy `make` places next to the library (installed / relocated package)
+_REPO_HEADER = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "ssv_b200.h"))
+HEADER_PATH = _REPO_HEADER if os.path.exists(_REPO_HEADER) else os.path.join(_HERE, "ssv_b200.h")
 
 _CTYPE = {
     "int": c_int, "float": c_float, "int64_t": c_int64, "size_t": c_size_t,
@@ -77,9 +80,17 @@ def strerror(rc: int) -> str:
     return lib().ssvb_strerror(rc).decode()
 
 
+_LIMITS = ("supported envelope (INTEGRATION.md §4): fp32 rows, row stride and feature dim multiples of 4, 16-byte aligned "
+           "base pointers; d <= 128 for the similarity losses (SimclrLoss / MocoLoss / RelicLoss / PirlLoss); "
+           "K <= 8192 for DinoLoss")
+
+
 def check(rc: int, what: str):
     if rc != 0:
-        raise RuntimeError(f"{what} failed (rc={rc}): {strerror(rc)}")
+        msg = f"{what} failed (rc={rc}): {strerror(rc)}"
+        if rc < 0:   # argument / shape / alignment / unsupported: name the envelope instead of a bare code
+            msg += f" -- {_LIMITS}"
+        raise RuntimeError(msg)
 
 
 def ptr(t):
@@ -131,7 +142,8 @@ _SIZES = {}
 
 def cached_size(fn_name: str, *args) -> int:
     """Memoised `*_saved_bytes` / `*_workspace_bytes` queries (pure functions of the shape)."""
-    key = (fn_name,) + args
+    # keyed by the current device too: workspace sizes follow the chunk plan, which depends on that device's SM count
+    key = (fn_name, torch.cuda.current_device() if torch.cuda.is_available() else -1) + args
     v = _SIZES.get(key)
     if v is None:
         v = int(getattr(lib(), fn_name)(*args))

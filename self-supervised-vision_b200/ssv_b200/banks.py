@@ -15,6 +15,7 @@ import weakref
 
 import torch
 import torch.nn as nn
+from torch.autograd.function import once_differentiable
 
 from . import _cabi as C
 
@@ -72,6 +73,12 @@ class _Ring:
                                               int(self._normalize), ctypes.cast(ctypes.pointer(new_ptr), ctypes.c_void_p),
                                               C.stream_ptr(self._device)), "ssvb_ring_enqueue")
         self.ptr = int(new_ptr.value)
+        # the kernel wrote the storage behind torch's back: bump the version counter so autograd's saved-tensor check
+        # fires if a pending backward still needs the OLD contents (MocoLoss re-reads the queue in backward; the
+        # reference is immune because `get_vectors().to(device)` hands it a copy), then re-sync the shadow's version
+        torch.autograd.graph.increment_version(self._data)
+        if shadow_ok:
+            self._shadow_version = self._data._version
 
 
 class MemoryBank(_Ring):
@@ -107,7 +114,9 @@ class FeatureBank(_Ring):
         self._enqueue(fvecs)
 
     def return_vectors(self, device):
-        return self._data.to(device)
+        # a SNAPSHOT, like the reference's host->device copy (models/swav.py:77-79): its own training loop enqueues the
+        # new features BEFORE loss.backward() (swav.py:140-144), so the loss must not alias the live ring
+        return self._data.to(device, copy=True)
 
 
 class _L2NormFn(torch.autograd.Function):
@@ -127,6 +136,7 @@ class _L2NormFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy):
         y, inv = ctx.saved_tensors
         n, d = y.shape
@@ -183,6 +193,7 @@ class PirlMemoryBank:
             C.check(C.lib().ssvb_bank_scatter(C.ptr(self.bank), self.data_size, self.bank.shape[1], self.bank.stride(0),
                                               C.ptr(idx), idx.numel(), C.ptr(v), v.stride(0), float(self.m),
                                               float(1 - self.m), mode, C.stream_ptr(self._device)), "ssvb_bank_scatter")
+        torch.autograd.graph.increment_version(self.bank)   # raw kernel write (get_positives / get_negatives return copies)
 
     def initialize_vectors(self, indices, vectors):
         self._scatter(indices, vectors, 0)

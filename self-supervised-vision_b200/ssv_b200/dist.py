@@ -26,6 +26,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 import torch.nn as nn
+from torch.autograd.function import once_differentiable
 
 from . import _cabi as C
 
@@ -245,6 +246,7 @@ class _NtxentDistFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         xi, xj, zhat_all, stat_all, inv_local = ctx.saved_tensors
         norm, temperature, world, rank, stages, dti, dtj = ctx.cfg
@@ -339,6 +341,7 @@ class _RelicKlDistFn(torch.autograd.Function):
         return kl
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         if len(ctx.saved_tensors) == 4:
             xi, xj, xo, saved = ctx.saved_tensors
@@ -558,6 +561,7 @@ class _BarlowColShardFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         xi, xj, saved, xt, dc = ctx.saved_tensors
         norm, world, rank, group, stages, cuda, dti, dtj = ctx.cfg
@@ -623,6 +627,7 @@ class _BarlowDistFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         xi, xj, saved, dc = ctx.saved_tensors
         norm, world, group, stages, dti, dtj = ctx.cfg
@@ -750,7 +755,8 @@ def _dist_sinkhorn(stages, scores_views, codes_views, k, eps, n_iters, group, in
 
 class _SwavDistFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z1, z2, prototypes, bank, temperature, eps, n_iters, group, stages):
+    def forward(ctx, z1, z2, prototypes, bank, temperature, eps, n_iters, group, stages, reduce_dproto=False):
+        ctx.reduce_dproto = bool(reduce_dproto)
         world, rank = _world_rank(group)
         cuda = isinstance(stages, SwavCudaStages)
         if cuda:
@@ -781,6 +787,7 @@ class _SwavDistFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         x1, x2, pc, saved, *rest = ctx.saved_tensors
         bk = rest[0] if rest else None
@@ -788,18 +795,31 @@ class _SwavDistFn(torch.autograd.Function):
         go = C.f32_scalar(grad_out)
         dz1, dz2, dpc = torch.empty_like(x1), torch.empty_like(x2), torch.empty_like(pc)
         stages.bwd(x1, x2, bk, pc, temperature, go, saved, dz1, dz2, dpc)
-        _all_reduce_sum(dpc, group)  # prototypes are replicated: their gradient sums over every rank's rows
-        return dz1.to(dt1), dz2.to(dt2), dpc.to(dtp), None, None, None, None, None, None
+        # Prototypes are replicated.  By default this rank returns its LOCAL contribution (the rows it owns), exactly like
+        # dz1 / dz2 feed only local contributions into the encoder's parameter gradients: whatever uniform cross-rank
+        # reduction the training loop applies to its replicated parameters (DDP mean, a SUM all-reduce) then treats
+        # encoder and prototypes alike.  reduce_prototype_grad=True instead returns the complete global gradient on
+        # every rank - for loops that EXCLUDE the prototypes from gradient synchronisation.
+        if ctx.reduce_dproto:
+            _all_reduce_sum(dpc, group)
+        return dz1.to(dt1), dz2.to(dt2), dpc.to(dtp), None, None, None, None, None, None, None
 
 
 class DistributedSwavLoss(nn.Module):
     """SwavLoss (reference utils/losses.py:204-235, same ctor kwargs) over the global batch of a process group: sample
     rows (and each rank's bank rows) sharded, prototypes replicated.  Per Sinkhorn pass ONE all-gather of the K-vector
-    prototype marginals of both views (combined in rank order = their all-reduce); all-reduce of the scalar loss and of
-    the prototype gradient.  Every rank gets the gradient rows of its own inputs."""
+    prototype marginals of both views (combined in rank order = their all-reduce); all-reduce of the scalar loss.
+    Every rank gets the gradient rows of its own inputs and its local contribution to the prototype gradient (see
+    `reduce_prototype_grad`)."""
 
-    def __init__(self, temperature=0.1, sinkhorn_eps=0.05, sinkhorn_iters=3, group=None, stages=None):
+    def __init__(self, temperature=0.1, sinkhorn_eps=0.05, sinkhorn_iters=3, group=None, stages=None,
+                 reduce_prototype_grad=False):
+        """reduce_prototype_grad=False (default): the prototype gradient returned on each rank is that rank's LOCAL
+        contribution, like the row gradients - reduce it together with the encoder's parameter gradients (DDP or an
+        all-reduce).  True: every rank gets the complete global prototype gradient (then keep the prototypes OUT of the
+        gradient synchronisation, or they end up `world` times too large relative to the encoder)."""
         super().__init__()
+        self.reduce_prototype_grad = reduce_prototype_grad
         self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
         self.temperature = temperature
         self.n_iters = sinkhorn_iters
@@ -822,7 +842,7 @@ class DistributedSwavLoss(nn.Module):
 
     def forward(self, z_1, z_2, prototypes, bank_features=None):
         return _SwavDistFn.apply(z_1, z_2, prototypes, bank_features, self.temperature, self.eps, self.n_iters,
-                                 self.group, self.stages)
+                                 self.group, self.stages, self.reduce_prototype_grad)
 
 
 # ======================================================================================================= MoCo (sharded queue)
@@ -913,6 +933,7 @@ class _MocoDistFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         q, k, mem, qhat_all, rowstat, lse2_all = ctx.saved_tensors
         norm, tau, world, rank, group, stages, dtq, dtk = ctx.cfg

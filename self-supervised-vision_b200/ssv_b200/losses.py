@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
+from torch.autograd.function import once_differentiable
 
 from . import _cabi as C
 
@@ -41,6 +42,7 @@ class _NtxentFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         xi, xj, saved = ctx.saved_tensors
         normalize, temperature, dti, dtj = ctx.cfg
@@ -106,6 +108,7 @@ class _MocoFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         q, k, mem, saved = ctx.saved_tensors
         normalize, temperature, dtq, dtk = ctx.cfg
@@ -143,6 +146,10 @@ class _RowdotFn(torch.autograd.Function):
         C.require_cuda(o, t)
         if o.shape != t.shape:
             raise ValueError("row-dot losses expect two tensors of the same shape")
+        if kind == 1 and o.dim() != 2:
+            # -(o * t).sum(1).mean() (utils/losses.py:150-151) sums over dim 1: for > 2-D inputs that is not the last
+            # axis and the divisor differs from a flattened [N, d] view; the reference only ever passes [N, d]
+            raise ValueError("SimSiamLoss expects [N, d] inputs (the reference's shape); reshape before the call")
         oo = C.as_f32_rows(o.reshape(-1, o.shape[-1]) if o.dim() != 2 else o)
         tt = C.as_f32_rows(t.reshape(-1, t.shape[-1]) if t.dim() != 2 else t)
         n, d = oo.shape
@@ -159,6 +166,7 @@ class _RowdotFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         oo, tt = ctx.saved_tensors
         kind, shape, dto, dtt = ctx.cfg
@@ -229,6 +237,7 @@ class _RelicFn(torch.autograd.Function):
         return out.sum()  # contrastive + alpha * KL  (utils/losses.py:201)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         xi, xj, xo, saved_c, saved_k = ctx.saved_tensors
         norm, temperature, alpha, dti, dtj, dto = ctx.cfg
@@ -287,6 +296,7 @@ class _BarlowFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         xi, xj, saved = ctx.saved_tensors
         normalize, lmbda, dti, dtj = ctx.cfg
@@ -344,6 +354,7 @@ class _SwavFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         x1, x2, pc, saved, *rest = ctx.saved_tensors
         bk = rest[0] if rest else None
@@ -424,6 +435,7 @@ class _DinoFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         t, s, c = ctx.saved_tensors
         temp_s, temp_t, dts = ctx.cfg
@@ -491,6 +503,7 @@ class _PirlFn(torch.autograd.Function):
         return out.sum()  # loss_weight * loss_1 + (1 - loss_weight) * loss_2  (utils/losses.py:117)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out):
         xi, xp, mp, saved = ctx.saved_tensors
         norm, temperature, w, dti, dtp = ctx.cfg

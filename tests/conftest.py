@@ -35,3 +35,14 @@ def rel_scalar(a, b):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+def ulp_diff(a, b):
+    """Largest distance in units-in-the-last-place between two fp32 arrays (same-sign finite values; 0 == -0)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    ia = a.view(np.int32).astype(np.int64)
+    ib = b.view(np.int32).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & 0x7FFFFFFF), ia)   # map the sign-magnitude encoding onto a monotonic integer line
+    ib = np.where(ib < 0, -(ib & 0x7FFFFFFF), ib)
+    return int(np.abs(ia - ib).max()) if a.size else 0

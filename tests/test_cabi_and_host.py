@@ -5,6 +5,7 @@ import ctypes
 import inspect
 import os
 import subprocess
+import sys
 
 import pytest
 import torch
@@ -140,3 +141,20 @@ def test_product_path_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in src.replace("# oracle", ""), f"{f} references the oracle"
+
+
+def test_relocated_package_binds_from_its_own_header(tmp_path):
+    """the package must not depend on the repository layout - `make` ships the public header next to
+    the library, and a copy of ssv_b200/ placed anywhere binds every prototype from it."""
+    import shutil
+    import subprocess
+    src = os.path.join(ROOT, "self-supervised-vision_b200", "ssv_b200")
+    dst = tmp_path / "site" / "ssv_b200"
+    shutil.copytree(src, dst, ignore=shutil.ignore_patterns("__pycache__"))
+    assert (dst / "ssv_b200.h").exists(), "make must place the header next to the library"
+    code = ("import sys; sys.path.insert(0, sys.argv[1]); import ssv_b200; from ssv_b200 import _cabi;"
+            "assert _cabi.HEADER_PATH.startswith(sys.argv[1]), _cabi.HEADER_PATH;"
+            "L = _cabi.lib(); assert L.ssvb_version() >= 100; print(len(_cabi.parse_header()))")
+    out = subprocess.run([sys.executable, "-c", code, str(tmp_path / "site")], capture_output=True, text=True, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr[-1500:]
+    assert int(out.stdout.strip()) >= 80

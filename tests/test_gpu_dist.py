@@ -170,7 +170,9 @@ def test_dist_swav_vs_oracle(nb, nbank, k, d):
         o = out[r]
         assert abs(o["loss"] - ref_loss) / abs(ref_loss) <= 1e-3
         sl = slice(r * nb, (r + 1) * nb)
-        assert rl2(o["dz1"], ref_dz1[sl]) <= 1e-2 and rl2(o["dz2"], ref_dz2[sl]) <= 1e-2 and rl2(o["dpc"], ref_dc) <= 1e-2
+        assert rl2(o["dz1"], ref_dz1[sl]) <= 1e-2 and rl2(o["dz2"], ref_dz2[sl]) <= 1e-2
+    # prototype gradient: every rank returns its local contribution; their sum is the single-process gradient
+    assert rl2(sum(out[r]["dpc"].astype(np.float64) for r in range(world)), ref_dc) <= 1e-2
     ref_codes = O.sinkhorn(np.concatenate([out[r]["sc"] for r in range(world)]), 0.05, 3)
     for r in range(world):
         assert rl2(out[r]["codes"], ref_codes[r * nb:(r + 1) * nb]) < 1e-4
@@ -215,7 +217,7 @@ def test_dist_moco_sharded_queue_vs_oracle(n_local, k_total, d, tau):
     queue = np.concatenate([out[r]["before"] for r in range(world)])
     # the sharded ring after the fill == single-process ring fed the same global batch
     ref_bank, ref_ptr = O.ring_enqueue(np.zeros((k_total, d), np.float32), 0, out[0]["fill"], True)
-    np.testing.assert_allclose(queue, ref_bank, rtol=5e-7, atol=0)
+    np.testing.assert_allclose(queue, ref_bank, rtol=1.2e-7, atol=0)  # <= 1 ulp
     assert all(out[r]["ptr_before"] == ref_ptr for r in range(world))
     ref_loss, ref_dq, ref_dk = O.moco(q, k, queue, True, tau)
     rl2 = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)  # noqa: E731
@@ -227,7 +229,7 @@ def test_dist_moco_sharded_queue_vs_oracle(n_local, k_total, d, tau):
     assert len({out[r]["loss"] for r in range(world)}) == 1
     ref_bank2, ref_ptr2 = O.ring_enqueue(queue.copy(), ref_ptr, k, True)
     after = np.concatenate([out[r]["after"] for r in range(world)])
-    np.testing.assert_allclose(after, ref_bank2, rtol=5e-7, atol=0)
+    np.testing.assert_allclose(after, ref_bank2, rtol=1.2e-7, atol=0)  # <= 1 ulp
     assert all(out[r]["ptr"] == ref_ptr2 for r in range(world))
 
 

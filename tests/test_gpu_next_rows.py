@@ -88,6 +88,32 @@ def test_momentum_update_modules(S):
         assert torch.equal(p.data, 0.9 * r + (1.0 - 0.9) * q.data)
 
 
+def test_ema_follows_repointed_parameters_and_odd_layouts(S):
+    """the updater must follow parameters whose storage was re-pointed after construction (the reference's
+    own loop does `t_param.data = ...`, models/moco.py:110-111; `module.to()` / `half()` do the same), must not pin or
+    confuse modules through id() reuse, and must not raise on channels_last / non-fp32 parameters."""
+    import gc
+    import torch.nn as nn
+    tgt = nn.Sequential(nn.Conv2d(3, 8, 3), nn.Linear(8, 4)).cuda()
+    src = nn.Sequential(nn.Conv2d(3, 8, 3), nn.Linear(8, 4)).cuda()
+    S.momentum_update(tgt, src, 0.5)
+    for p in tgt.parameters():                       # re-point every target parameter (new storage, same values)
+        p.data = p.data.clone()
+    tgt[0].weight.data = tgt[0].weight.data.contiguous(memory_format=torch.channels_last)   # non-contiguous layout
+    tgt[1].bias.data = tgt[1].bias.data.double()                                             # non-fp32
+    src[1].bias.data = src[1].bias.data.double()
+    before = [p.detach().clone() for p in tgt.parameters()]
+    S.momentum_update(tgt, src, 0.9)
+    for p, r, q in zip(tgt.parameters(), before, src.parameters()):
+        exp = 0.9 * r + (1.0 - 0.9) * q.data.to(r.dtype)
+        assert torch.equal(p.data, exp), "live (re-pointed) parameters must receive the update"
+    from ssv_b200 import ema
+    n0 = len(ema._UPDATERS)
+    del tgt
+    gc.collect()
+    assert len(ema._UPDATERS) == n0 - 1, "the updater cache must not keep a dead target module alive"
+
+
 # ------------------------------------------------------------------------------------------------ PIRL
 @pytest.mark.parametrize("tag", ["pa", "pb", "pc"])
 def test_pirl_golden(S, tag):
