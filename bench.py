@@ -45,7 +45,10 @@ def load_peaks():
 
 # ----------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """`nvidia-smi -lms 20` in the background, started early (it needs a few hundred ms before its first sample);
+    `mark()` stamps the start of the region of interest and `stop()` keeps the samples taken from then on (warm-up +
+    timed region), so idle samples from set-up do not dilute the clocks-under-load figure."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -53,6 +56,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t_mark = None
 
     def start(self):
         try:
@@ -61,7 +65,12 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def mark(self):
+        import datetime
+        self.t_mark = datetime.datetime.now()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
@@ -72,28 +81,30 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        clocks, reasons, mx = [], set(), None
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 8:
+            if len(parts) < 9:
                 continue
             try:
-                clocks.append(float(parts[1]))
-                mx = float(parts[2])
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(parts[2]), float(parts[3]), [nm for nm, v in zip(names, parts[5:9]) if v.lower() == "active"]))
             except ValueError:
                 continue
-            for nm, val in zip(names, parts[4:8]):
-                if val.lower() == "active":
-                    reasons.add(nm)
         try:
             os.unlink(self.f.name)
         except OSError:
             pass
-        if clocks:
+        if self.t_mark is not None:
+            inside = [r for r in rows if r[0] >= self.t_mark - datetime.timedelta(milliseconds=20)]
+            rows = inside if len(inside) >= 3 else rows[-10:]   # a very short region: the last samples before the stop
+        if rows:
+            clocks = [r[1] for r in rows]
+            reasons = sorted({nm for r in rows for nm in r[3]})
             # median over the upper half of the samples == "under load" (idle gaps between steps drop out)
             top = sorted(clocks)[len(clocks) // 2:]
-            out.update(sm_mhz=statistics.median(top), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(clocks))
+            out.update(sm_mhz=statistics.median(top), sm_max_mhz=rows[-1][2], reasons=reasons, samples=len(clocks))
         return out
 
 
@@ -292,6 +303,10 @@ def run_ours(args):
             raise SystemExit("bench.py --gpus N>1 must be launched with torchrun (one rank per GPU)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # nvidia-smi needs a few hundred ms before its first sample: start it now so that it is sampling every 20 ms by the
+    # time the warm-up and the timed region run (the timed region of the default run lasts only ~60 ms)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _cabi.lib()
@@ -388,8 +403,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item() / steps, launches, prof
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     ms_step, launches, prof = timed(step_resident, args.steps, args.warmup, profile=True)
     clocks = sampler.stop()
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))

@@ -156,14 +156,18 @@ int ssvb_ntxent_dist_rows_bwd(const float* zi, const float* zj, int64_t n_local,
  * ------------------------------------------------------------------------------------- */
 size_t ssvb_moco_saved_bytes(int64_t n, int64_t k, int64_t d);
 size_t ssvb_moco_workspace_bytes(int64_t n, int64_t k, int64_t d);
-int ssvb_moco_fwd(const float* query, const float* keys, const float* queue, const void* queue_bf16, int64_t n,
-                  int64_t k, int64_t d, int64_t ld_q, int64_t ld_k, int64_t ld_queue, int normalize,
-                  float temperature, float* loss, void* saved, void* workspace, size_t workspace_bytes,
+/* queue_unit_norm != 0 asserts that every queue row is unit-norm or zero (a MemoryBank: rows are normalised on enqueue,
+ * models/moco.py:31-36).  With normalize != 0 that bounds every logit by 1/tau and selects the fused single-pass form:
+ * the forward reads the queue ONCE and also produces sum_j p_aj m_j (kept in `saved`), the backward is one row-wise
+ * kernel that never touches the queue.  Pass 0 for arbitrary `memory_vectors` (two-pass online-max form). */
+int ssvb_moco_fwd(const float* query, const float* keys, const float* queue, const void* queue_bf16,
+                  int queue_unit_norm, int64_t n, int64_t k, int64_t d, int64_t ld_q, int64_t ld_k, int64_t ld_queue,
+                  int normalize, float temperature, float* loss, void* saved, void* workspace, size_t workspace_bytes,
                   void* stream);
-int ssvb_moco_bwd(const float* query, const float* keys, const float* queue, const void* queue_bf16, int64_t n,
-                  int64_t k, int64_t d, int64_t ld_q, int64_t ld_k, int64_t ld_queue, int normalize,
-                  float temperature, const float* grad_out, const void* saved, float* dquery, float* dkeys,
-                  int64_t ld_dq, int64_t ld_dk, void* workspace, size_t workspace_bytes, void* stream);
+int ssvb_moco_bwd(const float* query, const float* keys, const float* queue, const void* queue_bf16,
+                  int queue_unit_norm, int64_t n, int64_t k, int64_t d, int64_t ld_q, int64_t ld_k, int64_t ld_queue,
+                  int normalize, float temperature, const float* grad_out, const void* saved, float* dquery,
+                  float* dkeys, int64_t ld_dq, int64_t ld_dk, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * a2/e  MoCo with the queue SHARDED over `world` ranks (semantics = MocoLoss on the rank-order
@@ -369,6 +373,19 @@ int ssvb_rowdot_fwd(int kind, const float* o, const float* t, int64_t n, int64_t
 int ssvb_rowdot_bwd(int kind, const float* o, const float* t, int64_t n, int64_t d, int64_t ld_o, int64_t ld_t,
                     const float* grad_out, float* d_o, float* d_t, int64_t ld_do, int64_t ld_dt, void* stream);
 
+/* f1: the same two losses taken on the RAW projection-head outputs, with the head's final
+ * F.normalize (models/byol.py:47,59; models/simsiam.py:48,69) fused into the loss: one pass forward (row norms + row
+ * dot), one pass backward (normalise-backward projection from three saved scalars per row) instead of the reference's
+ * normalise fwd / loss fwd / loss bwd / normalise bwd passes.  normalize_o / normalize_t select which operand is
+ * normalised inside (the other is taken as given).  Value and gradients equal loss(F.normalize(o), F.normalize(t)). */
+size_t ssvb_rowdot_norm_saved_bytes(int64_t n);
+int ssvb_rowdot_norm_fwd(int kind, const float* o, const float* t, int64_t n, int64_t d, int64_t ld_o, int64_t ld_t,
+                         int normalize_o, int normalize_t, float* loss, void* saved, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int ssvb_rowdot_norm_bwd(int kind, const float* o, const float* t, int64_t n, int64_t d, int64_t ld_o, int64_t ld_t,
+                         int normalize_o, int normalize_t, const float* grad_out, const void* saved, float* d_o,
+                         float* d_t, int64_t ld_do, int64_t ld_dt, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * a10  ReLIC KL term — the `alpha * kl_div_loss` part of RelicLoss.forward
  *     (utils/losses.py:196-201; call models/relic.py:129), reproducing the reference quirk:
@@ -418,6 +435,18 @@ int ssvb_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int6
  * ------------------------------------------------------------------------------------- */
 int64_t ssvb_ema_chunk_elems(void);
 int ssvb_ema_update(const void* chunk_table, int64_t n_chunks, float m, float one_minus_m, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * SeLA self-labelling - the per-batch body of SeLA.self_label_step
+ * (reference models/sela.py:146-166): P = pow(log_softmax(logits, -1), lambda)^T [K x B];
+ * num_iters x { alpha = 1 / (P beta); beta = 1 / (alpha^T P)^T }; labels_b = argmax_k alpha_k P_kb beta_b.
+ * alpha [k] and beta [b] are the state carried from batch to batch (sela.py:72-73), updated in place.
+ * logits: [b x k] fp32 row-major (leading dimension ld); labels: int64 [b]; one launch for the whole step.
+ * ------------------------------------------------------------------------------------- */
+size_t ssvb_sela_workspace_bytes(int64_t b, int64_t k);
+int ssvb_sela_self_label(const float* logits, int64_t b, int64_t k, int64_t ld, float lambda, int64_t num_iters,
+                         float* alpha, float* beta, int64_t* labels, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * DinoLoss — replaces DinoLoss.forward (utils/losses.py:80-89; call site models/dino.py:161-162).

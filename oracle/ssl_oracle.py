@@ -372,3 +372,23 @@ def pirl_bank_update(bank, indices, vectors, m=None):
     idx = np.asarray(indices, dtype=np.int64)
     bank[idx] = vh if m is None else np.float32(m) * bank[idx] + np.float32(1.0 - m) * vh
     return bank
+
+
+# --------------------------------------------------------------------------
+# f4: SeLA self-labelling   (models/sela.py:146-166, per-batch body)
+# --------------------------------------------------------------------------
+def sela_self_label(logits, alpha, beta, lmbd, num_iters):
+    """P = pow(log_softmax(logits, -1), lmbd)^T (:152); num_iters x {alpha = 1/(P beta); beta = 1/(alpha^T P)^T}
+    (:154-156); labels = argmax_k alpha_k P_kb beta_b (:158-160).  alpha [K], beta [B] are carried state.
+    Returns (alpha, beta, labels, score) with score [B x K] = (diag(alpha) P diag(beta))^T, the matrix the argmax is
+    taken over (so a test can tell real disagreements from near-ties)."""
+    x = _f64(logits)
+    logp = x - _lse(x, -1)[..., None] if _lse(x, -1).ndim == x.ndim - 1 else x - _lse(x, -1)
+    p = np.power(logp, lmbd).T                      # [K, B]
+    a = _f64(alpha).reshape(-1, 1).copy()
+    b = _f64(beta).reshape(-1, 1).copy()
+    for _ in range(int(num_iters)):
+        a = 1.0 / (p @ b)
+        b = 1.0 / (a.T @ p).T
+    score = (a * p * b.T).T                         # [B, K]
+    return a[:, 0], b[:, 0], score.argmax(-1), score

@@ -15,7 +15,7 @@ template <int BN, bool A_MN, bool B_MN, int EPI>
 int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, int max_ctas, cudaStream_t s) {
   auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
   constexpr int smem = GemmCfg<BN>::SMEM;
-  SSVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  SSVB_TRY((set_smem_once<gemm_kernel<BN, A_MN, B_MN, EPI>>(smem)));
   const int ntiles = p.tiles_m * p.tiles_n;
   int grid = ntiles < num_sms() ? ntiles : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;

@@ -124,4 +124,19 @@ inline int num_sms() {
     SSVB_CUDA(cudaGetLastError());   \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device) instead of on every launch:
+// the attribute is per device and sticky, and the call costs ~1 us of the launch-bound small-shape path.
+template <auto Kern>   // the kernel itself is the template argument: one static per kernel instantiation
+int set_smem_once(int smem) {
+  static unsigned long long done_mask = 0;  // bit = device ordinal
+  int dev = 0;
+  SSVB_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(__atomic_load_n(&done_mask, __ATOMIC_ACQUIRE) & bit)) {
+    SSVB_CUDA(cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    __atomic_fetch_or(&done_mask, bit, __ATOMIC_RELEASE);
+  }
+  return SSVB_OK;
+}
+
 }  // namespace ssvb

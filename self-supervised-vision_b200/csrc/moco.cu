@@ -16,6 +16,7 @@ namespace {
 struct MocoSaved {
   __nv_bfloat16* qhat;  // [npad x dpad]
   float *inv_q, *inv_k, *pos, *lse2;
+  float* pm;  // [npad x dpad] fused path: sum_j p_aj m_j, produced by the FORWARD pass (backward never reads the queue)
   size_t bytes;
 };
 MocoSaved moco_saved(void* base, int64_t n, int64_t dpad) {
@@ -27,8 +28,18 @@ MocoSaved moco_saved(void* base, int64_t n, int64_t dpad) {
   s.inv_k = c.take<float>(npad);
   s.pos = c.take<float>(npad);
   s.lse2 = c.take<float>(npad);
+  s.pm = c.take<float>(npad * dpad);
   s.bytes = c.used();
   return s;
+}
+
+// Fused single-pass form (flash-attention shaped): when the queries are L2-normalised and the queue rows are unit-norm
+// or zero (a MemoryBank: rows are normalised on enqueue, models/moco.py:31-36), every logit is bounded by 1/tau, a
+// constant shift replaces the running max, and ONE pass over the queue yields both the row sums of exp (-> LSE, loss)
+// and sum_j exp(l_aj) m_j (-> the gradient) as plain sums over column chunks.  The queue is read once per step
+// instead of twice and the backward is a single row-wise kernel.
+inline bool moco_fused(int normalize, int queue_unit_norm, float temperature) {
+  return normalize && queue_unit_norm && (2.f * SSVB_LOG2E / temperature <= 120.f);
 }
 
 struct MocoWs {
@@ -53,11 +64,13 @@ MocoWs moco_ws(void* base, int64_t n, int64_t k, int64_t dpad) {
   Carver c(base);
   MocoWs w;
   const int64_t npad = round_up(n, 128);
-  SimParams p;
-  moco_plan(p, n, k, 1.f, 256, 2);
+  SimParams p, pb;
+  moco_plan(p, n, k, 1.f, kFwdBN, 512 / kFwdBN);
+  moco_plan(pb, n, k, 1.f, 128, 4);  // the fused single-pass form runs the backward-shaped kernel with its own chunk plan
+  const int nch = p.nchunks > pb.nchunks ? p.nchunks : pb.nchunks;
   w.queue_bf16 = c.take<__nv_bfloat16>(k * dpad);
-  w.part_m = c.take<float>(static_cast<size_t>(4 * p.nchunks) * npad);
-  w.part_l = c.take<float>(static_cast<size_t>(4 * p.nchunks) * npad);
+  w.part_m = c.take<float>(static_cast<size_t>(4 * nch) * npad);
+  w.part_l = c.take<float>(static_cast<size_t>(4 * nch) * npad);
   w.block_sums = c.take<float>(ceil_div(npad, 8) + 8);
   w.counter = c.take<unsigned int>(4);
   w.dacc = c.take<float>(npad * dpad);
@@ -80,6 +93,37 @@ __global__ void queue_to_bf16_kernel(const float* __restrict__ q, int64_t k, int
     pk.y = *reinterpret_cast<uint32_t*>(&hi);
     *reinterpret_cast<uint2*>(out + row * dpad + c) = pk;
   }
+}
+
+// fused path: combine the per-chunk row sums (fixed order), add the positive logit's term, emit lse2 / the loss term and
+// turn the accumulated sum_j exp2(l_aj - shift) m_j into sum_j p_aj m_j.  One warp per query row.
+__global__ void moco_fused_finalize_kernel(const float* __restrict__ part_l, int nparts, int stride, int nrows, int dpad,
+                                           const float* __restrict__ pos, float c, float shift,
+                                           const float* __restrict__ dacc, float* __restrict__ pm,
+                                           float* __restrict__ lse2_out, float* block_sums, unsigned int* counter,
+                                           float loss_scale, float* loss) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  float term = 0.f;
+  if (r < nrows) {
+    float L = 0.f;
+    for (int i = lane; i < nparts; i += 32) L += part_l[static_cast<size_t>(i) * stride + r];
+    L = warp_sum(L);
+    const float p2 = pos[r] * c;
+    L += exp2f(p2 - shift);  // label-0 column of the reference's cat (utils/losses.py:70)
+    const float lse2 = shift + log2f(L);
+    const float inv = 1.f / L;
+    for (int k = lane * 4; k < dpad; k += 128) {
+      float4 v = *reinterpret_cast<const float4*>(dacc + static_cast<size_t>(r) * dpad + k);
+      v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+      *reinterpret_cast<float4*>(pm + static_cast<size_t>(r) * dpad + k) = v;
+    }
+    if (lane == 0) {
+      lse2_out[r] = lse2;
+      term = (lse2 - p2) * SSVB_LN2;
+    }
+  }
+  const float bt = block_sum_256(term);
+  grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false);
 }
 
 __global__ void moco_grad_finish_kernel(const float* __restrict__ q, const float* __restrict__ kk, int64_t ldq,
@@ -270,9 +314,9 @@ size_t ssvb_moco_workspace_bytes(int64_t n, int64_t k, int64_t d) {
   return moco_ws(nullptr, n, k, sim_dpad(d)).bytes;
 }
 
-int ssvb_moco_fwd(const float* query, const float* keys, const float* queue, const void* queue_bf16, int64_t n,
-                  int64_t k, int64_t d, int64_t ld_q, int64_t ld_k, int64_t ld_queue, int normalize,
-                  float temperature, float* loss, void* saved, void* workspace, size_t workspace_bytes,
+int ssvb_moco_fwd(const float* query, const float* keys, const float* queue, const void* queue_bf16,
+                  int queue_unit_norm, int64_t n, int64_t k, int64_t d, int64_t ld_q, int64_t ld_k, int64_t ld_queue,
+                  int normalize, float temperature, float* loss, void* saved, void* workspace, size_t workspace_bytes,
                   void* stream) {
   SSVB_TRY(check_device_sm100());
   SSVB_TRY(check_shape(n, k, d, temperature));
@@ -296,7 +340,27 @@ int ssvb_moco_fwd(const float* query, const float* keys, const float* queue, con
   SSVB_TRY(get_queue_bf16(queue, queue_bf16, k, d, ld_queue, dpad, ws, s, &qb));
 
   SimParams p;
-  moco_plan(p, n, k, c, 256, 2);
+  if (moco_fused(normalize, queue_unit_norm, temperature)) {
+    // one pass over the queue: S tile -> exp2(l - c) -> (row sums, W * M accumulated in TMEM) with the backward-shaped
+    // kernel; the column chunks add into a zeroed accumulator
+    moco_plan(p, n, k, c, 128, 4);
+    p.shift = c;
+    p.rowstat = nullptr;  // -> constant shift
+    p.colstat = nullptr;
+    p.part_l = ws.part_l;
+    p.part_stride = static_cast<int>(npad);
+    p.dacc = ws.dacc;
+    p.ld_dacc = static_cast<int>(dpad);
+    p.use_atomic = p.nchunks > 1;
+    if (p.use_atomic) SSVB_CUDA(cudaMemsetAsync(ws.dacc, 0, npad * dpad * sizeof(float), s));
+    SSVB_TRY(launch_sim_bwd(SIM_MOCO, sv.qhat, npad, qb, k, dpad, p, s));
+    moco_fused_finalize_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(
+        ws.part_l, 4 * p.nchunks, p.part_stride, static_cast<int>(n), static_cast<int>(dpad), sv.pos, c, c, ws.dacc,
+        sv.pm, sv.lse2, ws.block_sums, ws.counter, 1.f / static_cast<float>(n), loss);
+    SSVB_LAUNCH_CHECK();
+    return SSVB_OK;
+  }
+  moco_plan(p, n, k, c, kFwdBN, 512 / kFwdBN);
   p.part_m = ws.part_m;
   p.part_l = ws.part_l;
   p.part_stride = static_cast<int>(npad);
@@ -308,10 +372,10 @@ int ssvb_moco_fwd(const float* query, const float* keys, const float* queue, con
   return SSVB_OK;
 }
 
-int ssvb_moco_bwd(const float* query, const float* keys, const float* queue, const void* queue_bf16, int64_t n,
-                  int64_t k, int64_t d, int64_t ld_q, int64_t ld_k, int64_t ld_queue, int normalize,
-                  float temperature, const float* grad_out, const void* saved, float* dquery, float* dkeys,
-                  int64_t ld_dq, int64_t ld_dk, void* workspace, size_t workspace_bytes, void* stream) {
+int ssvb_moco_bwd(const float* query, const float* keys, const float* queue, const void* queue_bf16,
+                  int queue_unit_norm, int64_t n, int64_t k, int64_t d, int64_t ld_q, int64_t ld_k, int64_t ld_queue,
+                  int normalize, float temperature, const float* grad_out, const void* saved, float* dquery,
+                  float* dkeys, int64_t ld_dq, int64_t ld_dk, void* workspace, size_t workspace_bytes, void* stream) {
   SSVB_TRY(check_device_sm100());
   SSVB_TRY(check_shape(n, k, d, temperature));
   SSVB_TRY(check_rows(query, ld_q));
@@ -325,6 +389,14 @@ int ssvb_moco_bwd(const float* query, const float* keys, const float* queue, con
   MocoSaved sv = moco_saved(const_cast<void*>(saved), n, dpad);
   MocoWs ws = moco_ws(workspace, n, k, dpad);
   const float c = SSVB_LOG2E / temperature;
+  if (moco_fused(normalize, queue_unit_norm, temperature)) {
+    // sum_j p_aj m_j was produced by the forward pass: the backward is the row-wise finish only (no queue access)
+    moco_grad_finish_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(
+        query, keys, ld_q, ld_k, static_cast<int>(n), static_cast<int>(d), sv.pm, static_cast<int>(dpad), sv,
+        normalize, c, 1.f / (static_cast<float>(n) * temperature), grad_out, dquery, dkeys, ld_dq, ld_dk);
+    SSVB_LAUNCH_CHECK();
+    return SSVB_OK;
+  }
   const __nv_bfloat16* qb = nullptr;
   SSVB_TRY(get_queue_bf16(queue, queue_bf16, k, d, ld_queue, dpad, ws, s, &qb));
 
@@ -389,7 +461,7 @@ int ssvb_moco_dist_shard_fwd(const void* qhat_all, int64_t n_global, const float
   const __nv_bfloat16* qb = nullptr;
   SSVB_TRY(get_queue_bf16(queue_shard, queue_shard_bf16, k_local, d, ld_queue, dpad, ws, s, &qb));
   SimParams p;
-  moco_plan(p, n_global, k_local, c, 256, 2);
+  moco_plan(p, n_global, k_local, c, kFwdBN, 512 / kFwdBN);
   p.part_m = ws.part_m;
   p.part_l = ws.part_l;
   p.part_stride = static_cast<int>(npad);
@@ -520,7 +592,7 @@ int ssvb_pirl_fwd(const float* img, const float* patch, const float* mem_pos, co
   SSVB_TRY(get_queue_bf16(mem_neg, nullptr, k, d, ld_neg, dpad, ws, s, &qb));
   // the negatives' logits are shared by both heads (:109): one pass of the tensor-core kernel, two LSE finalizes
   SimParams p;
-  moco_plan(p, n, k, c, 256, 2);
+  moco_plan(p, n, k, c, kFwdBN, 512 / kFwdBN);
   p.part_m = ws.part_m;
   p.part_l = ws.part_l;
   p.part_stride = static_cast<int>(npad);

@@ -97,7 +97,7 @@ WsLayout ws_layout(void* base, int64_t local_rows, int64_t row_blocks, int64_t c
   SimParams p{};
   p.row_blocks = static_cast<int>(row_blocks);
   p.cols = static_cast<int>(cols);
-  plan_chunks(p, 256, 4);
+  plan_chunks(p, kFwdBN, kFwdMinTiles);
   size_t part_elems = static_cast<size_t>(4 * p.nchunks + 2) * lr;
   if (part_elems < static_cast<size_t>(sim_mpad(cols))) part_elems = sim_mpad(cols);
   w.pos = c.take<float>(lr);
@@ -217,7 +217,7 @@ int ssvb_ntxent_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   }
   SimParams p;
   fill_sim_params_rows(p, pl, 1, pl.m, 0, 0);
-  plan_chunks(p, 256, 4);
+  plan_chunks(p, kFwdBN, kFwdMinTiles);
   p.part_m = ws.part_m;
   p.part_l = ws.part_l;
   p.part_stride = static_cast<int>(round_up(pl.m, 256));
@@ -373,7 +373,7 @@ int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_l
   const size_t peer_off = peer_stat_off / sizeof(float) + static_cast<size_t>(rank) * 2 * lr;
   SimParams p;
   fill_sim_params_rows(p, pl, 1, lr, rank * lr, 0);
-  plan_chunks(p, 256, 4);
+  plan_chunks(p, kFwdBN, kFwdMinTiles);
   p.part_m = ws.part_m;
   p.part_l = ws.part_l;
   p.part_stride = static_cast<int>(round_up(lr, 256));

@@ -15,18 +15,48 @@ int check_rows(const void* p, int64_t ld) {
 
 // =========================================================================================== rowdot
 // kind 0: sum (o-t)^2 ; kind 1: sum o*t          (models/byol.py:89 nn.MSELoss, utils/losses.py:150-151)
-template <int KIND>
-__global__ void rowdot_fwd_kernel(const float* __restrict__ o, const float* __restrict__ t, int64_t n, int d4,
-                                  int64_t ldo, int64_t ldt, float* block_sums, unsigned int* counter, float scale,
-                                  float* loss) {
+// FLAT: all rows contiguous (ld == d, the usual case): one flat float4 index, no 64-bit division per element.
+// Every thread keeps U float4 of each operand in flight (2U independent 16-byte loads before the first use).
+template <bool FLAT>
+__device__ __forceinline__ int64_t rowdot_off(int64_t j, int d4, int64_t ld4) {
+  if (FLAT) return j;
+  const int64_t r = j / d4;
+  return r * ld4 + (j - r * d4);
+}
+template <int KIND, bool FLAT>
+__global__ void __launch_bounds__(256)
+rowdot_fwd_kernel(const float* __restrict__ o, const float* __restrict__ t, int64_t n, int d4, int64_t ldo,
+                  int64_t ldt, float* block_sums, unsigned int* counter, float scale, float* loss) {
   const int64_t total = n * d4;
+  const float4* o4 = reinterpret_cast<const float4*>(o);
+  const float4* t4 = reinterpret_cast<const float4*>(t);
+  const int64_t lo4 = ldo >> 2, lt4 = ldt >> 2;
   float acc0 = 0.f, acc1 = 0.f;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / d4;
-    const int c = static_cast<int>(i - r * d4);
-    const float4 a = __ldg(reinterpret_cast<const float4*>(o + r * ldo) + c);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(t + r * ldt) + c);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  constexpr int U = 4;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < total; i += U * stride) {
+    float4 a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      a[u] = __ldg(o4 + rowdot_off<FLAT>(i + u * stride, d4, lo4));
+      b[u] = __ldg(t4 + rowdot_off<FLAT>(i + u * stride, d4, lt4));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (KIND == 0) {
+        const float dx = a[u].x - b[u].x, dy = a[u].y - b[u].y, dz = a[u].z - b[u].z, dw = a[u].w - b[u].w;
+        acc0 += dx * dx + dy * dy;
+        acc1 += dz * dz + dw * dw;
+      } else {
+        acc0 += a[u].x * b[u].x + a[u].y * b[u].y;
+        acc1 += a[u].z * b[u].z + a[u].w * b[u].w;
+      }
+    }
+  }
+  for (; i < total; i += stride) {
+    const float4 a = __ldg(o4 + rowdot_off<FLAT>(i, d4, lo4));
+    const float4 b = __ldg(t4 + rowdot_off<FLAT>(i, d4, lt4));
     if (KIND == 0) {
       const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
       acc0 += dx * dx + dy * dy;
@@ -40,34 +70,154 @@ __global__ void rowdot_fwd_kernel(const float* __restrict__ o, const float* __re
   grid_sum_finish(bt, block_sums, counter, scale, loss, false);
 }
 
-template <int KIND>
-__global__ void rowdot_bwd_kernel(const float* __restrict__ o, const float* __restrict__ t, int64_t n, int d4,
-                                  int64_t ldo, int64_t ldt, const float* __restrict__ grad_out, float coef,
-                                  float* __restrict__ d_o, float* __restrict__ d_t, int64_t lddo, int64_t lddt) {
+template <int KIND, bool FLAT>
+__global__ void __launch_bounds__(256)
+rowdot_bwd_kernel(const float* __restrict__ o, const float* __restrict__ t, int64_t n, int d4, int64_t ldo,
+                  int64_t ldt, const float* __restrict__ grad_out, float coef, float* __restrict__ d_o,
+                  float* __restrict__ d_t, int64_t lddo, int64_t lddt) {
   const int64_t total = n * d4;
   const float g = __ldg(grad_out) * coef;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / d4;
-    const int c = static_cast<int>(i - r * d4);
-    float4 go, gt;
-    if (KIND == 0) {  // d/do mean((o-t)^2) = 2 (o-t) / (N D)
-      const float4 a = __ldg(reinterpret_cast<const float4*>(o + r * ldo) + c);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(t + r * ldt) + c);
-      go = make_float4((a.x - b.x) * g, (a.y - b.y) * g, (a.z - b.z) * g, (a.w - b.w) * g);
-      gt = make_float4(-go.x, -go.y, -go.z, -go.w);
-    } else {  // d/do -(1/N) sum o t = -t / N
-      if (d_o) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(t + r * ldt) + c);
-        go = make_float4(b.x * g, b.y * g, b.z * g, b.w * g);
-      }
-      if (d_t) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(o + r * ldo) + c);
-        gt = make_float4(a.x * g, a.y * g, a.z * g, a.w * g);
+  const float4* o4 = reinterpret_cast<const float4*>(o);
+  const float4* t4 = reinterpret_cast<const float4*>(t);
+  float4* do4 = reinterpret_cast<float4*>(d_o);
+  float4* dt4 = reinterpret_cast<float4*>(d_t);
+  const int64_t lo4 = ldo >> 2, lt4 = ldt >> 2, ldo4 = lddo >> 2, ldt4 = lddt >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  constexpr int U = 4;
+  const bool need_o = (KIND == 0) || d_t != nullptr;   // kind 1: d_t = -o/N needs o, d_o = -t/N needs t
+  const bool need_t = (KIND == 0) || d_o != nullptr;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += U * stride) {
+    float4 a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t j = i + u * stride;
+      a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      b[u] = a[u];
+      if (j < total) {
+        if (need_o) a[u] = __ldg(o4 + rowdot_off<FLAT>(j, d4, lo4));
+        if (need_t) b[u] = __ldg(t4 + rowdot_off<FLAT>(j, d4, lt4));
       }
     }
-    if (d_o) reinterpret_cast<float4*>(d_o + r * lddo)[c] = go;
-    if (d_t) reinterpret_cast<float4*>(d_t + r * lddt)[c] = gt;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t j = i + u * stride;
+      if (j >= total) break;
+      float4 go, gt;
+      if (KIND == 0) {  // d/do mean((o-t)^2) = 2 (o-t) / (N D)
+        go = make_float4((a[u].x - b[u].x) * g, (a[u].y - b[u].y) * g, (a[u].z - b[u].z) * g, (a[u].w - b[u].w) * g);
+        gt = make_float4(-go.x, -go.y, -go.z, -go.w);
+      } else {  // d/do -(1/N) sum o t = -t / N
+        go = make_float4(b[u].x * g, b[u].y * g, b[u].z * g, b[u].w * g);
+        gt = make_float4(a[u].x * g, a[u].y * g, a[u].z * g, a[u].w * g);
+      }
+      if (d_o) do4[rowdot_off<FLAT>(j, d4, ldo4)] = go;
+      if (d_t) dt4[rowdot_off<FLAT>(j, d4, ldt4)] = gt;
+    }
+  }
+}
+
+// =========================================================================================== rowdot on RAW rows (f1)
+// The reference's BYOL / SimSiam heads end in F.normalize (models/byol.py:47,59; simsiam.py:48,69) and the loss then
+// reads the unit rows again: normalise fwd (r + w per operand), loss fwd (2 r), loss bwd (2 r + w), normalise bwd
+// (2 r + w per operand).  Fused: the loss takes the RAW head outputs, one pass computes |o|^2, |t|^2, o.t per row (warp
+// per row) -> loss; the backward is one pass as well (normalise-backward projection from the saved row scalars).
+struct RowdotNormSaved {
+  float *inv_o, *inv_t, *cosv;
+  size_t bytes;
+};
+RowdotNormSaved rowdot_norm_saved(void* base, int64_t n) {
+  Carver c(base);
+  RowdotNormSaved s;
+  s.inv_o = c.take<float>(n);
+  s.inv_t = c.take<float>(n);
+  s.cosv = c.take<float>(n);
+  s.bytes = c.used();
+  return s;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+rowdot_norm_fwd_kernel(const float* __restrict__ o, const float* __restrict__ t, int64_t n, int d4, int64_t ldo,
+                       int64_t ldt, int norm_o, int norm_t, RowdotNormSaved sv, float* block_sums,
+                       unsigned int* counter, float scale, float* loss) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  float acc = 0.f;
+  for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n; row += wstride) {
+    const float4* po = reinterpret_cast<const float4*>(o + row * ldo);
+    const float4* pt = reinterpret_cast<const float4*>(t + row * ldt);
+    float so = 0.f, st = 0.f, sot = 0.f;
+    for (int c = lane; c < d4; c += 32) {
+      const float4 a = __ldg(po + c), b = __ldg(pt + c);
+      so += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+      st += b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+      sot += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    }
+    so = warp_sum(so); st = warp_sum(st); sot = warp_sum(sot);
+    const float io = norm_o ? 1.f / fmaxf(sqrtf(so), 1e-12f) : 1.f;
+    const float it = norm_t ? 1.f / fmaxf(sqrtf(st), 1e-12f) : 1.f;
+    const float cs = sot * io * it;                 // o^ . t^
+    if (lane == 0) {
+      sv.inv_o[row] = io; sv.inv_t[row] = it; sv.cosv[row] = cs;
+      acc += (KIND == 0) ? (so * io * io + st * it * it - 2.f * cs) : cs;
+    }
+  }
+  const float bt = block_sum_256(acc);
+  grid_sum_finish(bt, block_sums, counter, scale, loss, false);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+rowdot_norm_bwd_kernel(const float* __restrict__ o, const float* __restrict__ t, int64_t n, int d4, int64_t ldo,
+                       int64_t ldt, int norm_o, int norm_t, const RowdotNormSaved sv,
+                       const float* __restrict__ grad_out, float coef, float* __restrict__ d_o,
+                       float* __restrict__ d_t, int64_t lddo, int64_t lddt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const float g = __ldg(grad_out) * coef;
+  for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n; row += wstride) {
+    const float io = sv.inv_o[row], it = sv.inv_t[row], cs = sv.cosv[row];
+    const float4* po = reinterpret_cast<const float4*>(o + row * ldo);
+    const float4* pt = reinterpret_cast<const float4*>(t + row * ldt);
+    float4* qo = d_o ? reinterpret_cast<float4*>(d_o + row * lddo) : nullptr;
+    float4* qt = d_t ? reinterpret_cast<float4*>(d_t + row * lddt) : nullptr;
+    // squared norms of the normalised rows (1 for ordinary rows, 0 for zero rows, |x|^2 when not normalised): needed for
+    // the exact projection; recomputed from the row below
+    float so = 0.f, st = 0.f;
+    if (KIND == 0) {
+      for (int c = lane; c < d4; c += 32) {
+        const float4 a = __ldg(po + c), b = __ldg(pt + c);
+        so += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+        st += b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+      }
+      so = warp_sum(so) * io * io;
+      st = warp_sum(st) * it * it;
+    }
+    for (int c = lane; c < d4; c += 32) {
+      const float4 a = __ldg(po + c), b = __ldg(pt + c);
+      const float oh[4] = {a.x * io, a.y * io, a.z * io, a.w * io};
+      const float th[4] = {b.x * it, b.y * it, b.z * it, b.w * it};
+      float go[4], gt[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float dgo, dgt, po_dot, pt_dot;  // gradient w.r.t. the normalised rows and its dot with them
+        if (KIND == 0) {  // d/do^ mean((o^-t^)^2) = 2 (o^-t^) g
+          dgo = 2.f * (oh[e] - th[e]) * g;
+          dgt = -dgo;
+          po_dot = 2.f * (so - cs) * g;
+          pt_dot = 2.f * (st - cs) * g;
+        } else {          // d/do^ -(1/N) sum o^.t^ = -t^ g ... (g carries the sign and 1/N)
+          dgo = th[e] * g;
+          dgt = oh[e] * g;
+          po_dot = cs * g;
+          pt_dot = cs * g;
+        }
+        go[e] = norm_o ? (dgo - po_dot * oh[e]) * io : dgo;
+        gt[e] = norm_t ? (dgt - pt_dot * th[e]) * it : dgt;
+      }
+      if (qo) qo[c] = make_float4(go[0], go[1], go[2], go[3]);
+      if (qt) qt[c] = make_float4(gt[0], gt[1], gt[2], gt[3]);
+    }
   }
 }
 
@@ -413,14 +563,73 @@ int ssvb_rowdot_fwd(int kind, const float* o, const float* t, int64_t n, int64_t
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
+  const bool flat = (ld_o == d) && (ld_t == d);
+  const int d4 = static_cast<int>(d / 4);
+  const float sc = kind == 0 ? 1.f / (static_cast<float>(n) * d) : -1.f / static_cast<float>(n);
+  const unsigned g = static_cast<unsigned>(grid);
+#define SSVB_RD(K, F) rowdot_fwd_kernel<K, F><<<g, 256, 0, s>>>(o, t, n, d4, ld_o, ld_t, ws.block_sums, ws.counter, sc, loss)
+  if (kind == 0) { if (flat) SSVB_RD(0, true); else SSVB_RD(0, false); }
+  else           { if (flat) SSVB_RD(1, true); else SSVB_RD(1, false); }
+#undef SSVB_RD
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+size_t ssvb_rowdot_norm_saved_bytes(int64_t n) { return n > 0 ? rowdot_norm_saved(nullptr, n).bytes : 0; }
+
+int ssvb_rowdot_norm_fwd(int kind, const float* o, const float* t, int64_t n, int64_t d, int64_t ld_o, int64_t ld_t,
+                         int normalize_o, int normalize_t, float* loss, void* saved, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (n <= 0 || d <= 0 || !loss || !saved || !workspace || (kind != 0 && kind != 1)) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(o, ld_o));
+  SSVB_TRY(check_rows(t, ld_t));
+  if (workspace_bytes < rowdot_ws(nullptr).bytes) return SSVB_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  RowdotWs ws = rowdot_ws(workspace);
+  RowdotNormSaved sv = rowdot_norm_saved(saved, n);
+  SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
+  int64_t grid = ceil_div(n, 8);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (grid > cap) grid = cap;
+  const int d4 = static_cast<int>(d / 4);
   if (kind == 0)
-    rowdot_fwd_kernel<0><<<static_cast<unsigned>(grid), 256, 0, s>>>(o, t, n, static_cast<int>(d / 4), ld_o, ld_t,
-                                                                     ws.block_sums, ws.counter,
-                                                                     1.f / (static_cast<float>(n) * d), loss);
+    rowdot_norm_fwd_kernel<0><<<static_cast<unsigned>(grid), 256, 0, s>>>(
+        o, t, n, d4, ld_o, ld_t, normalize_o, normalize_t, sv, ws.block_sums, ws.counter,
+        1.f / (static_cast<float>(n) * d), loss);
   else
-    rowdot_fwd_kernel<1><<<static_cast<unsigned>(grid), 256, 0, s>>>(o, t, n, static_cast<int>(d / 4), ld_o, ld_t,
-                                                                     ws.block_sums, ws.counter,
-                                                                     -1.f / static_cast<float>(n), loss);
+    rowdot_norm_fwd_kernel<1><<<static_cast<unsigned>(grid), 256, 0, s>>>(
+        o, t, n, d4, ld_o, ld_t, normalize_o, normalize_t, sv, ws.block_sums, ws.counter, -1.f / static_cast<float>(n),
+        loss);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
+int ssvb_rowdot_norm_bwd(int kind, const float* o, const float* t, int64_t n, int64_t d, int64_t ld_o, int64_t ld_t,
+                         int normalize_o, int normalize_t, const float* grad_out, const void* saved, float* d_o,
+                         float* d_t, int64_t ld_do, int64_t ld_dt, void* stream) {
+  SSVB_TRY(check_device_sm100());
+  if (n <= 0 || d <= 0 || !grad_out || !saved || (kind != 0 && kind != 1) || (!d_o && !d_t)) return SSVB_ERR_INVALID;
+  if (d % 4) return SSVB_ERR_ALIGNMENT;
+  SSVB_TRY(check_rows(o, ld_o));
+  SSVB_TRY(check_rows(t, ld_t));
+  if (d_o) SSVB_TRY(check_rows(d_o, ld_do));
+  if (d_t) SSVB_TRY(check_rows(d_t, ld_dt));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  RowdotNormSaved sv = rowdot_norm_saved(const_cast<void*>(saved), n);
+  int64_t grid = ceil_div(n, 8);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (grid > cap) grid = cap;
+  const int d4 = static_cast<int>(d / 4);
+  if (kind == 0)
+    rowdot_norm_bwd_kernel<0><<<static_cast<unsigned>(grid), 256, 0, s>>>(
+        o, t, n, d4, ld_o, ld_t, normalize_o, normalize_t, sv, grad_out, 1.f / (static_cast<float>(n) * d), d_o, d_t,
+        ld_do, ld_dt);
+  else
+    rowdot_norm_bwd_kernel<1><<<static_cast<unsigned>(grid), 256, 0, s>>>(
+        o, t, n, d4, ld_o, ld_t, normalize_o, normalize_t, sv, grad_out, -1.f / static_cast<float>(n), d_o, d_t, ld_do,
+        ld_dt);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
@@ -436,18 +645,19 @@ int ssvb_rowdot_bwd(int kind, const float* o, const float* t, int64_t n, int64_t
   if (d_t) SSVB_TRY(check_rows(d_t, ld_dt));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t total = n * (d / 4);
-  int64_t grid = ceil_div(total, 256 * 2);
-  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  int64_t grid = ceil_div(total, 256 * 4);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  if (kind == 0)
-    rowdot_bwd_kernel<0><<<static_cast<unsigned>(grid), 256, 0, s>>>(o, t, n, static_cast<int>(d / 4), ld_o, ld_t,
-                                                                     grad_out, 2.f / (static_cast<float>(n) * d),
-                                                                     d_o, d_t, ld_do, ld_dt);
-  else
-    rowdot_bwd_kernel<1><<<static_cast<unsigned>(grid), 256, 0, s>>>(o, t, n, static_cast<int>(d / 4), ld_o, ld_t,
-                                                                     grad_out, -1.f / static_cast<float>(n), d_o,
-                                                                     d_t, ld_do, ld_dt);
+  const bool flat = (ld_o == d) && (ld_t == d) && (!d_o || ld_do == d) && (!d_t || ld_dt == d);
+  const int d4 = static_cast<int>(d / 4);
+  const float cf = kind == 0 ? 2.f / (static_cast<float>(n) * d) : -1.f / static_cast<float>(n);
+  const unsigned g = static_cast<unsigned>(grid);
+#define SSVB_RD(K, F) \
+  rowdot_bwd_kernel<K, F><<<g, 256, 0, s>>>(o, t, n, d4, ld_o, ld_t, grad_out, cf, d_o, d_t, ld_do, ld_dt)
+  if (kind == 0) { if (flat) SSVB_RD(0, true); else SSVB_RD(0, false); }
+  else           { if (flat) SSVB_RD(1, true); else SSVB_RD(1, false); }
+#undef SSVB_RD
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }

@@ -8,6 +8,8 @@ namespace ssvb {
 
 inline int64_t sim_dpad(int64_t d) { return round_up(d, 64); }
 inline int64_t sim_mpad(int64_t m) { return round_up(m, 256); }
+// forward chunk plan: tile width and the smallest number of tiles a column chunk may have (1024 columns)
+constexpr int kFwdMinTiles = 1024 / kFwdBN;
 
 // Choose the column chunking: (row block, chunk) units are statically strided over one CTA per SM, so the number
 // of units should fill whole waves of `num_sms()` CTAs (tail effect) while every chunk keeps >= min_tiles tiles
@@ -40,7 +42,7 @@ template <int KB, int MODE, bool OPF16 = false>
 int launch_sim_fwd_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const SimParams& p, cudaStream_t s) {
   auto kern = sim_fwd_kernel<KB, MODE, OPF16>;
   constexpr int smem = FwdCfg<KB>::SMEM;
-  SSVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  SSVB_TRY((set_smem_once<sim_fwd_kernel<KB, MODE, OPF16>>(smem)));
   const int nunits = p.row_blocks * p.nchunks;
   const int grid = nunits < num_sms() ? nunits : num_sms();
   const int slot = prof_begin(PROF_SIM_FWD, s);
@@ -53,7 +55,7 @@ template <int KB, int MODE, bool OPF16 = false>
 int launch_sim_bwd_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const SimParams& p, cudaStream_t s) {
   auto kern = sim_bwd_kernel<KB, MODE, OPF16>;
   constexpr int smem = BwdCfg<KB>::SMEM;
-  SSVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  SSVB_TRY((set_smem_once<sim_bwd_kernel<KB, MODE, OPF16>>(smem)));
   const int nunits = p.row_blocks * p.nchunks;
   const int grid = nunits < num_sms() ? nunits : num_sms();
   const int slot = prof_begin(PROF_SIM_BWD, s);
@@ -68,7 +70,7 @@ inline int launch_sim_fwd(int mode, const void* A, int64_t a_rows, const void* B
                           const SimParams& p, cudaStream_t s) {
   CUtensorMap tmA, tmB;
   SSVB_TRY(make_tmap_bf16(&tmA, A, a_rows, dpad, dpad, 128, p.opf16 != 0));
-  SSVB_TRY(make_tmap_bf16(&tmB, B, b_rows, dpad, dpad, 256, p.opf16 != 0));
+  SSVB_TRY(make_tmap_bf16(&tmB, B, b_rows, dpad, dpad, kFwdBN, p.opf16 != 0));
   const int KB = static_cast<int>(dpad / 64);
 #define SSVB_DISPATCH(KBV)                                                      \
   switch (mode) {                                                               \

@@ -141,19 +141,27 @@ __device__ __forceinline__ void lds_v4(uint32_t saddr, unsigned long long& lo, u
 // =====================================================================================================
 // forward
 // =====================================================================================================
+// Forward tile width.  256: two 256-column S buffers, a warpgroup PAIR shares a tile (one 128-column half each) and the
+// buffer is handed back after 3/4 of the pair's math (default).  128: FOUR 128-column S buffers, each softmax warpgroup
+// owns a whole tile in its own buffer (more independent MMA -> softmax streams); kept as a build option, measured slower.
+#ifndef SSVB_FWD_BN
+#define SSVB_FWD_BN 256   // measured (profiles/r2_tuning_log.md): 128 is 4 % slower (16 instead of 8 MMAs + commits per 256 columns on the one issuing thread)
+#endif
+constexpr int kFwdBN = SSVB_FWD_BN;
 template <int KB>
 struct FwdCfg {
-  static constexpr int BN = 256;
+  static constexpr int BN = kFwdBN;
+  static constexpr int NBUF = 512 / BN;  // S buffers in TMEM
   static constexpr int A_BYTES = 128 * 128 * KB;
   static constexpr int B_BYTES = BN * 128 * KB;
-  static constexpr int NSTAGE = (KB == 1) ? 6 : 3;  // deep enough to cover the TMA latency of a 64 KB tile
-  static constexpr int NBARS = 4 + 2 * NSTAGE + 4;
+  static constexpr int NSTAGE = ((KB == 1) ? 6 : 3) * (256 / BN);  // deep enough to cover the TMA latency (192 KB ring)
+  static constexpr int NBARS = 4 + 2 * NSTAGE + 2 * NBUF;
   static constexpr int SMEM = 1024 + A_BYTES + NSTAGE * B_BYTES + NBARS * 8 + 16;
 };
 
 template <int MODE, bool MASKED>
 __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int a_glob, int j0, float& m,
-                                         float (&l)[4], uint64_t* s_empty_bar, int lane
+                                         float (&l)[4], uint32_t s_empty_bar, int lane
 #ifdef SSVB_DBG_TIMING
                                          , long long (&_t_acc)[8], long long& _t_prev
 #endif
@@ -182,7 +190,7 @@ __device__ __forceinline__ void fwd_tile(uint32_t taddr, const SimParams& p, int
       // the S buffer is fully in registers: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty_bar);
+      if (lane == 0) mbar_arrive_a(s_empty_bar);
     }
     const int colbase = j0 + cc * 32;
     if (MODE == SIM_NTX_FIXED && !MASKED) {
@@ -249,7 +257,7 @@ template <int KB, int MODE, bool OPF16 = false>
 __global__ void __launch_bounds__(640, 1)
 sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SimParams p) {
   using C = FwdCfg<KB>;
-  constexpr int BN = C::BN, NSTAGE = C::NSTAGE;
+  constexpr int BN = C::BN, NSTAGE = C::NSTAGE, NBUF = C::NBUF;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sA = smem;
@@ -260,8 +268,8 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* b_full = bars + 4;
   uint64_t* b_empty = b_full + NSTAGE;
   uint64_t* s_full = b_empty + NSTAGE;
-  uint64_t* s_empty = s_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
+  uint64_t* s_empty = s_full + NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -272,8 +280,10 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < NBUF; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 8);
+      mbar_init(&s_empty[i], 16 / NBUF);  // the warps that drain one S buffer: a warpgroup pair (8) or one warpgroup (4)
     }
     for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(&b_full[i], 1);
@@ -325,9 +335,9 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const UnitInfo ui = decode_unit(p, u);
       mbar_wait(&a_full[0], ucount & 1);
       for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
-        const int st = gt % NSTAGE, buf = gt & 1;
+        const int st = gt % NSTAGE, buf = gt % NBUF;
         mbar_wait(&b_full[st], (gt / NSTAGE) & 1);
-        mbar_wait(&s_empty[buf], ((gt >> 1) & 1) ^ 1);
+        mbar_wait(&s_empty[buf], ((gt / NBUF) & 1) ^ 1);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t bbase = smem_u32(sB + st * C::B_BYTES);
@@ -356,6 +366,8 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row_l = q * 32 + lane;
     const uint32_t tlane = static_cast<uint32_t>(q * 32) << 16;
     int gt = 0;
+    const int my_buf = NBUF == 2 ? pair : wgi;
+    const uint32_t a_s_full = smem_u32(&s_full[my_buf]), a_s_empty = smem_u32(&s_empty[my_buf]);  // hoisted (see bwd)
 #ifdef SSVB_DBG_TIMING
     long long _t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
@@ -366,25 +378,27 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float m = -1e30f;
       float l[4] = {0.f, 0.f, 0.f, 0.f};
       for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
-        if ((gt & 1) != pair) continue;
-        const int buf = pair;
+        // BN = 256: tile t belongs to the warpgroup pair (t & 1), each warpgroup of the pair streams one 128-column half;
+        // BN = 128: tile t belongs to warpgroup (t & 3) alone (its own S buffer)
+        if (NBUF == 2 ? ((gt & 1) != pair) : ((gt & 3) != wgi)) continue;
+        const int buf = NBUF == 2 ? pair : wgi;
         SSVB_TP(0);  // loop / other
-        mbar_wait(&s_full[buf], (gt >> 1) & 1);
+        mbar_wait_a(a_s_full, (gt / NBUF) & 1);
         tc_fence_after();
         SSVB_TP(1);  // wait s_full
-        const int j0 = t * BN + half * 128;
+        const int j0 = t * BN + (NBUF == 2 ? half * 128 : 0);
         const bool special = (MODE != SIM_MOCO && j0 < ui.g0 + 128 && j0 + 128 > ui.g0) || (j0 + 128 > p.cols);
-        const uint32_t taddr = tmem + tlane + buf * BN + half * 128;
+        const uint32_t taddr = tmem + tlane + buf * BN + (NBUF == 2 ? half * 128 : 0);
 #ifdef SSVB_DBG_TIMING
         if (special)
-          fwd_tile<MODE, true>(taddr, p, a_glob, j0, m, l, &s_empty[buf], lane, _t_acc, _t_prev);
+          fwd_tile<MODE, true>(taddr, p, a_glob, j0, m, l, a_s_empty, lane, _t_acc, _t_prev);
         else
-          fwd_tile<MODE, false>(taddr, p, a_glob, j0, m, l, &s_empty[buf], lane, _t_acc, _t_prev);
+          fwd_tile<MODE, false>(taddr, p, a_glob, j0, m, l, a_s_empty, lane, _t_acc, _t_prev);
 #else
         if (special)
-          fwd_tile<MODE, true>(taddr, p, a_glob, j0, m, l, &s_empty[buf], lane);
+          fwd_tile<MODE, true>(taddr, p, a_glob, j0, m, l, a_s_empty, lane);
         else
-          fwd_tile<MODE, false>(taddr, p, a_glob, j0, m, l, &s_empty[buf], lane);
+          fwd_tile<MODE, false>(taddr, p, a_glob, j0, m, l, a_s_empty, lane);
 #endif
       }
       if (row_l < ui.nvalid) {
@@ -445,7 +459,7 @@ __device__ __forceinline__ float ex2_poly3(float x) {
 // weights of 32 consecutive columns [cb, cb+32) of one row: sv = S values, pk = packed bf16 pairs out
 template <int MODE, bool MASKED, bool OPF16>
 __device__ __forceinline__ void bwd_weights32(const uint32_t (&sv)[32], uint32_t (&pk)[16], const SimParams& p,
-                                              int a_glob, int colbase, float rs, uint32_t cs32) {
+                                              int a_glob, int colbase, float rs, uint32_t cs32, float& wsum) {
 #ifndef SSVB_BWD_SCALAR_MATH
   if (MODE == SIM_NTX_FIXED && !MASKED) {
     // issue-bound loop.  Operands are pre-scaled (the S accumulator is the log2-domain logit): per pair two MUFU.EX2
@@ -500,7 +514,9 @@ __device__ __forceinline__ void bwd_weights32(const uint32_t (&sv)[32], uint32_t
       } else {
         wv = ex2f(fmaf(s, p.c, -rs));
       }
-      if (MASKED && (colbase + i == a_glob)) wv = 0.f;
+      if (MASKED && MODE != SIM_MOCO && (colbase + i == a_glob)) wv = 0.f;
+      if (MASKED && MODE == SIM_MOCO && (colbase + i >= p.cols)) wv = 0.f;  // queue tail (zero-filled B rows)
+      if (MODE == SIM_MOCO) wsum += wv;  // fused MoCo forward: row sums of the un-normalised weights
       w[e] = wv;
     }
     pk[i4 * 2] = pack_h2<OPF16>(w[0], w[1]);
@@ -660,6 +676,11 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row_l = q * 32 + lane;
     const uint32_t tlane = static_cast<uint32_t>(q * 32) << 16;
     int gt = 0, ucount = 0;
+    // barrier addresses in the shared window, computed once (a generic pointer costs a cvta sequence per use)
+    const uint32_t a_s_full = smem_u32(&s_full[pair]), a_s_empty = smem_u32(&s_empty[pair]);
+    const uint32_t a_w_full = smem_u32(&w_full[pair]), a_w_empty = smem_u32(&w_empty[pair]);
+    const uint32_t a_dz_full = smem_u32(dz_full), a_dz_empty = smem_u32(dz_empty);
+    const uint32_t a_sC = smem_u32(sC) + half * 64 * 4;
 #ifdef SSVB_DBG_TIMING
     long long _t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
@@ -669,7 +690,8 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int a_glob = ui.g0 + row_l;
       const bool valid = row_l < ui.nvalid;
       float rs = 0.f;
-      if (valid) rs = (MODE == SIM_MOCO) ? p.rowstat[ui.lrow0 + row_l] : p.rowstat[a_glob];
+      if (valid) rs = (MODE == SIM_MOCO) ? (p.rowstat ? p.rowstat[ui.lrow0 + row_l] : p.shift) : p.rowstat[a_glob];
+      float lsum = 0.f;  // SIM_MOCO with p.part_l: sum over this unit's columns of exp2(l - shift) (fused forward)
       for (int t = ui.t0; t < ui.t1; ++t, ++gt) {
         if ((gt & 1) != pair) continue;
         const int st = gt % NSTAGE;
@@ -677,7 +699,7 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // no separate wait on b_full: S(t) was issued only after the MMA warp observed b_full[st], so observing
         // s_full(t) also orders this warp after the TMA / bulk-copy writes of the B tile and its column statistics
         SSVB_TP(1);
-        mbar_wait(&s_full[pair], (gt >> 1) & 1);
+        mbar_wait_a(a_s_full, (gt >> 1) & 1);
         tc_fence_after();
         SSVB_TP(2);  // wait s_full
         const uint32_t t_s = tmem + tlane + C::T_S + pair * BN + half * 64;
@@ -694,25 +716,25 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // this half of the S tile is in registers: give the buffer back so S(t+2) can be issued right away
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[pair]);
+        if (lane == 0) mbar_arrive_a(a_s_empty);
         SSVB_TP(3);  // tmem loads + release
         const int j0 = t * BN + half * 64;
-        const bool special = (MODE != SIM_MOCO) && (j0 < ui.g0 + 128) && (j0 + 64 > ui.g0);
+        const bool special = (MODE != SIM_MOCO) ? ((j0 < ui.g0 + 128) && (j0 + 64 > ui.g0)) : (j0 + 64 > p.cols);
         const uint32_t t_w = tmem + tlane + C::T_W + pair * 64 + half * 32;
-        const uint32_t cs = smem_u32(sC) + st * C::CS_BYTES + half * 64 * 4;
+        const uint32_t cs = a_sC + st * C::CS_BYTES;
         constexpr int CSTEP = 32 * 4;
         // all 64 weights are computed and packed before waiting for the W buffer (the dZ GEMM of tile t-2 may still
         // be reading it): that wait is off the critical path unless the tensor pipe is the bottleneck
         uint32_t pk[2][16];
         if (special) {
-          bwd_weights32<MODE, true, OPF16>(sv[0], pk[0], p, a_glob, j0, rs, cs);
-          bwd_weights32<MODE, true, OPF16>(sv[1], pk[1], p, a_glob, j0 + 32, rs, cs + CSTEP);
+          bwd_weights32<MODE, true, OPF16>(sv[0], pk[0], p, a_glob, j0, rs, cs, lsum);
+          bwd_weights32<MODE, true, OPF16>(sv[1], pk[1], p, a_glob, j0 + 32, rs, cs + CSTEP, lsum);
         } else {
-          bwd_weights32<MODE, false, OPF16>(sv[0], pk[0], p, a_glob, j0, rs, cs);
-          bwd_weights32<MODE, false, OPF16>(sv[1], pk[1], p, a_glob, j0 + 32, rs, cs + CSTEP);
+          bwd_weights32<MODE, false, OPF16>(sv[0], pk[0], p, a_glob, j0, rs, cs, lsum);
+          bwd_weights32<MODE, false, OPF16>(sv[1], pk[1], p, a_glob, j0 + 32, rs, cs + CSTEP, lsum);
         }
         SSVB_TP(4);  // 64 weights
-        mbar_wait(&w_empty[pair], ((gt >> 1) & 1) ^ 1);
+        mbar_wait_a(a_w_empty, ((gt >> 1) & 1) ^ 1);
         tc_fence_after();
         SSVB_TP(5);  // wait w_empty
         tmem_st_x16(t_w, pk[0]);
@@ -721,11 +743,13 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&w_full[pair]);
+        if (lane == 0) mbar_arrive_a(a_w_full);
         SSVB_TP(7);  // st drain + arrive
       }
+      if (MODE == SIM_MOCO && p.part_l != nullptr && valid)
+        p.part_l[static_cast<size_t>(ui.ch * 4 + wgi) * p.part_stride + ui.lrow0 + row_l] = lsum;
       // ---- epilogue: the four warpgroups drain DP/4 accumulator columns each (DP = 64: only two of them have work)
-      mbar_wait(dz_full, ucount & 1);
+      mbar_wait_a(a_dz_full, ucount & 1);
       tc_fence_after();
       if (DP == 128 || wgi < 2) {
         const int col0 = wgi * 32;
@@ -750,7 +774,7 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(dz_empty);
+      if (lane == 0) mbar_arrive_a(a_dz_empty);
     }
 #ifdef SSVB_DBG_TIMING
     if (p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0)

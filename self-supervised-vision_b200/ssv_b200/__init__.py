@@ -9,6 +9,8 @@ from .losses import (BarlowLoss, DinoLoss, MocoLoss, MSELoss, PirlLoss, RelicLos
                      update_teacher_center)
 from .ema import EmaUpdater, momentum_update  # noqa: F401
 from .banks import FeatureBank, MemoryBank, PirlMemoryBank, Prototypes  # noqa: F401
+from .fused import NormalizedMSELoss, NormalizedSimSiamLoss, SelaLabeler, graphed  # noqa: F401
 
 __all__ = ["SimclrLoss", "MocoLoss", "BarlowLoss", "SimSiamLoss", "RelicLoss", "SwavLoss", "MSELoss",
-           "MemoryBank", "FeatureBank", "Prototypes", "DinoLoss", "PirlLoss", "PirlMemoryBank", "update_teacher_center", "EmaUpdater", "momentum_update"]
+           "MemoryBank", "FeatureBank", "Prototypes", "DinoLoss", "PirlLoss", "PirlMemoryBank", "update_teacher_center", "EmaUpdater", "momentum_update",
+           "NormalizedMSELoss", "NormalizedSimSiamLoss", "SelaLabeler", "graphed"]

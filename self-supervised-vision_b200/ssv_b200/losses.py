@@ -99,10 +99,22 @@ class _MocoFn(torch.autograd.Function):
             ws_bytes = C.cached_size("ssvb_moco_workspace_bytes", n, kq, d)
             ws = C.workspace("moco", ws_bytes, dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
-            C.check(L.ssvb_moco_fwd(C.ptr(q), C.ptr(k), C.ptr(mem), C.ptr(shadow), n, kq, d, _ld(q), _ld(k), _ld(mem),
+            # a MemoryBank's rows are unit-norm or zero by construction (normalised on enqueue): with its shadow in hand the
+            # fused single-pass kernel applies (queue read once, backward without queue access)
+            unit = int(shadow is not None)
+            C.check(L.ssvb_moco_fwd(C.ptr(q), C.ptr(k), C.ptr(mem), C.ptr(shadow), unit, n, kq, d, _ld(q), _ld(k), _ld(mem),
                                     int(bool(normalize)), float(temperature), C.ptr(loss), C.ptr(saved), C.ptr(ws),
                                     ws_bytes, C.stream_ptr(dev)), "ssvb_moco_fwd")
-        ctx.save_for_backward(q, k, mem, saved)
+        # fused single-pass form (csrc/moco.cu `moco_fused`): everything the backward needs was produced by the forward
+        # and lives in `saved`, so the queue is NOT a saved tensor - the bank may be enqueued before backward (any loop
+        # order works, like the reference whose loss sees a per-step copy of the queue, models/moco.py:117).  Otherwise
+        # the backward re-reads the queue and `mem` is saved, so autograd's version check guards it.
+        fused = bool(unit and normalize and 2.0 * 1.4426950408889634 / float(temperature) <= 120.0)
+        if fused:
+            ctx.save_for_backward(q, k, saved)
+            ctx.mem = mem
+        else:
+            ctx.save_for_backward(q, k, mem, saved)
         ctx.shadow = shadow
         ctx.cfg = (int(bool(normalize)), float(temperature), query.dtype, keys.dtype)
         return loss
@@ -110,7 +122,10 @@ class _MocoFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_out):
-        q, k, mem, saved = ctx.saved_tensors
+        if len(ctx.saved_tensors) == 3:
+            (q, k, saved), mem = ctx.saved_tensors, ctx.mem
+        else:
+            q, k, mem, saved = ctx.saved_tensors
         normalize, temperature, dtq, dtk = ctx.cfg
         n, d = q.shape
         kq = mem.shape[0]
@@ -121,7 +136,8 @@ class _MocoFn(torch.autograd.Function):
             dq, dk = torch.empty_like(q), torch.empty_like(k)
             ws_bytes = C.cached_size("ssvb_moco_workspace_bytes", n, kq, d)
             ws = C.workspace("moco", ws_bytes, dev)
-            C.check(L.ssvb_moco_bwd(C.ptr(q), C.ptr(k), C.ptr(mem), C.ptr(ctx.shadow), n, kq, d, _ld(q), _ld(k),
+            C.check(L.ssvb_moco_bwd(C.ptr(q), C.ptr(k), C.ptr(mem), C.ptr(ctx.shadow), int(ctx.shadow is not None), n, kq, d,
+                                    _ld(q), _ld(k),
                                     _ld(mem), normalize, temperature, C.ptr(go), C.ptr(saved), C.ptr(dq), C.ptr(dk),
                                     _ld(dq), _ld(dk), C.ptr(ws), ws_bytes, C.stream_ptr(dev)), "ssvb_moco_bwd")
         return dq.to(dtq), dk.to(dtk), None, None, None

@@ -239,6 +239,32 @@ def main():
     cases.update(pbank_after_update=npy(pb.bank.clone()), pbank_pos=npy(pb.get_positives(torch.tensor([7, 11]))))
     save("next_rows", **cases)
 
+    # ---- SeLA self-labelling: the per-batch body of SeLA.self_label_step (models/sela.py:152-160), the reference's own
+    # statements on CPU fp32 tensors (the method itself needs the model and the data loaders).  Case "ref" is the
+    # reference's own configuration (lambda = 25, 80 iterations, 128 clusters, batch 500: configs/sela.yaml) - in fp32 it
+    # drives alpha to 0 and beta to inf, which is what a drop-in has to reproduce; "s1"/"s2" stay finite.
+    import torch.nn.functional as F
+    cases = {}
+    for tag, b, k, lmbd, iters in [("s1", 50, 16, 3, 20), ("s2", 96, 40, 5, 12), ("ref", 500, 128, 25, 80)]:
+        logits = randn(20, b, k, dtype=torch.float32)
+        alpha = torch.FloatTensor(k, 1).normal_(0, 1, generator=torch.Generator().manual_seed(21))
+        beta = torch.FloatTensor(b, 1).normal_(0, 1, generator=torch.Generator().manual_seed(22))
+        a, bb = alpha.clone(), beta.clone()
+        log_probs = torch.pow(F.log_softmax(logits, -1), lmbd).t()                         # sela.py:152
+        for _ in range(iters):
+            a = 1.0 / torch.mm(log_probs, bb)                                               # sela.py:155
+            bb = 1.0 / torch.mm(a.t(), log_probs).t()                                       # sela.py:156
+        alpha_diag = torch.eye(a.size(0)) * a                                               # sela.py:158
+        beta_diag = torch.eye(bb.size(0)) * bb                                              # sela.py:159
+        score = (alpha_diag @ log_probs @ beta_diag).t()
+        labels = score.argmax(-1)                                                           # sela.py:160
+        cases.update({f"{tag}_logits": npy(logits), f"{tag}_alpha0": npy(alpha), f"{tag}_beta0": npy(beta),
+                      f"{tag}_cfg": np.array([lmbd, iters]), f"{tag}_alpha": npy(a), f"{tag}_beta": npy(bb),
+                      f"{tag}_labels": labels.numpy()})
+        if tag != "ref":   # (all NaN there)
+            cases[f"{tag}_score"] = npy(score)
+    save("sela", **cases)
+
 
 if __name__ == "__main__":
     main()

@@ -217,7 +217,7 @@ def test_dist_moco_sharded_queue_vs_oracle(n_local, k_total, d, tau):
     queue = np.concatenate([out[r]["before"] for r in range(world)])
     # the sharded ring after the fill == single-process ring fed the same global batch
     ref_bank, ref_ptr = O.ring_enqueue(np.zeros((k_total, d), np.float32), 0, out[0]["fill"], True)
-    np.testing.assert_allclose(queue, ref_bank, rtol=1.2e-7, atol=0)  # <= 1 ulp
+    np.testing.assert_allclose(queue, ref_bank, rtol=2.4e-7, atol=0)  # <= 2 ulp of the fp64-rounded oracle (fp32 norm: 1 ulp + 1 ulp for the quotient)
     assert all(out[r]["ptr_before"] == ref_ptr for r in range(world))
     ref_loss, ref_dq, ref_dk = O.moco(q, k, queue, True, tau)
     rl2 = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)  # noqa: E731
@@ -229,7 +229,7 @@ def test_dist_moco_sharded_queue_vs_oracle(n_local, k_total, d, tau):
     assert len({out[r]["loss"] for r in range(world)}) == 1
     ref_bank2, ref_ptr2 = O.ring_enqueue(queue.copy(), ref_ptr, k, True)
     after = np.concatenate([out[r]["after"] for r in range(world)])
-    np.testing.assert_allclose(after, ref_bank2, rtol=1.2e-7, atol=0)  # <= 1 ulp
+    np.testing.assert_allclose(after, ref_bank2, rtol=2.4e-7, atol=0)  # <= 2 ulp of the fp64-rounded oracle (fp32 norm: 1 ulp + 1 ulp for the quotient)
     assert all(out[r]["ptr"] == ref_ptr2 for r in range(world))
 
 

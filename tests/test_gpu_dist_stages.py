@@ -182,7 +182,7 @@ def test_sharded_ring_enqueue_bit_exact(S):
         ptr = new_ptrs[0]
         got = torch.cat(shards).cpu().numpy()
         assert np.array_equal(got, whole.bank.cpu().numpy()), f"step {step}: shards differ from the unsharded kernel"
-        np.testing.assert_allclose(got, ref_bank, rtol=1.2e-7, atol=0)  # <= 1 ulp
+        np.testing.assert_allclose(got, ref_bank, rtol=2.4e-7, atol=0)  # <= 2 ulp of the fp64-rounded oracle (fp32 norm: 1 ulp + 1 ulp for the quotient)
         assert ((got == 0) == (ref_bank == 0)).all()
 
 

@@ -167,3 +167,97 @@ def test_pirl_memory_bank(S):
     ref = O.pirl_bank_update(O.pirl_bank_update(np.zeros((5000, 128), np.float32), idx.numpy(), v0), idx.numpy(), v1, 0.5)
     # (m*a + (1-m)*b cancels for opposite-sign entries: the 1-ulp difference of the two normalisations is absolute)
     np.testing.assert_allclose(big.bank.cpu().numpy(), ref, rtol=1e-6, atol=2e-7)
+
+
+# ------------------------------------------------------------------------------------------------ f1: fused head normalise + loss
+@pytest.mark.parametrize("n,d", [(512, 128), (333, 1024), (64, 20)])
+@pytest.mark.parametrize("kind", ["mse", "simsiam"])
+def test_fused_normalised_rowdot_losses(S, n, d, kind):
+    """NormalizedMSELoss / NormalizedSimSiamLoss on RAW rows == the reference's F.normalize (models/byol.py:47,59;
+    simsiam.py:48,69) followed by its loss (byol.py:89 nn.MSELoss; utils/losses.py:150-151), value and gradients:
+    oracle = l2_normalize -> loss -> l2_normalize_bwd composed in fp64.  Includes a zero row (F.normalize eps clamp)."""
+    o, t = (3.0 * randn(0, n, d)).astype(np.float32), (0.2 * randn(1, n, d) + 0.5 * randn(0, n, d)).astype(np.float32)
+    o[5] = 0.0
+    oh, oden = O.l2_normalize(o)
+    th, tden = O.l2_normalize(t)
+    if kind == "mse":
+        ref_loss, dho, dht = O.mse(oh, th)
+        dht = -dho if dht is None else dht
+        fn = S.NormalizedMSELoss()
+    else:
+        ref_loss, dho, dht = O.simsiam(oh, th)
+        fn = S.NormalizedSimSiamLoss()
+    ref_do, ref_dt = O.l2_normalize_bwd(dho, oh, oden), O.l2_normalize_bwd(dht, th, tden)
+    a, b = dev(o), dev(t)
+    loss = fn(a, b)
+    (1.5 * loss).backward()
+    assert rel_scalar(loss.item(), ref_loss) <= 1e-5
+    assert rel_l2(a.grad.cpu().numpy(), 1.5 * ref_do) <= 1e-5
+    assert rel_l2(b.grad.cpu().numpy(), 1.5 * ref_dt) <= 1e-5
+    # and against the unfused drop-in modules on the same GPU
+    a2, b2 = dev(o), dev(t)
+    unf = (S.MSELoss() if kind == "mse" else S.SimSiamLoss())(torch.nn.functional.normalize(a2), torch.nn.functional.normalize(b2))
+    unf.backward()
+    assert rel_scalar(loss.item(), unf.item()) <= 1e-5
+    assert rel_l2(a.grad.cpu().numpy(), 1.5 * a2.grad.cpu().numpy()) <= 1e-5
+
+
+def test_graphed_loss_modules_match_eager(S):
+    """ssv_b200.graphed: forward + backward of a loss module captured in CUDA graphs and replayed on NEW data of the same
+    shape must reproduce the eager kernels bit for bit (cfg1 shape: the reference's own batch size)."""
+    zi, zj = randn(0, 256, 128), randn(1, 256, 128)
+    a, b = dev(zi), dev(zj)
+    g = S.graphed(S.SimclrLoss(True, 0.5), a, b)
+    for seed in (5, 6):
+        xi, xj = dev(randn(seed, 256, 128)), dev(randn(seed + 10, 256, 128))
+        l_g = g(xi, xj)
+        l_g.backward()
+        yi, yj = dev(randn(seed, 256, 128)), dev(randn(seed + 10, 256, 128))
+        l_e = S.SimclrLoss(True, 0.5)(yi, yj)
+        l_e.backward()
+        assert torch.equal(l_g.detach(), l_e.detach())
+        assert torch.equal(xi.grad, yi.grad) and torch.equal(xj.grad, yj.grad)
+    ref = O.ntxent(randn(6, 256, 128), randn(16, 256, 128), True, 0.5)
+    check(l_g.item(), [xi.grad, xj.grad], ref[0], ref[1:], "graphed SimclrLoss")
+
+
+# ------------------------------------------------------------------------------------------------ f4: SeLA self-labelling
+@pytest.mark.parametrize("tag", ["s1", "s2", "ref"])
+def test_sela_self_label_golden(S, tag):
+    """ssvb_sela_self_label against the reference's own statements (models/sela.py:152-160, fixture generated by
+    tests/golden/make_golden.py).  Finite cases: the gauge-free score matrix alpha_k P_kb beta_b and the labels (outside
+    near-ties); the reference's own configuration ("ref": lambda 25, 80 iterations) degenerates in fp32 to alpha = 0,
+    beta = inf, all labels 0 - reproduced exactly."""
+    g = load_golden("sela")
+    lmbd, iters = (int(v) for v in g[f"{tag}_cfg"])
+    logits = g[f"{tag}_logits"]
+    b, k = logits.shape
+    lab = S.SelaLabeler(k, b, lmbd, device="cuda")
+    lab.alpha.copy_(torch.from_numpy(g[f"{tag}_alpha0"]))
+    lab.beta.copy_(torch.from_numpy(g[f"{tag}_beta0"]))
+    labels = lab.step(torch.from_numpy(logits).cuda(), num_iters=iters).cpu().numpy()
+    a, bt = lab.alpha.cpu().numpy()[:, 0], lab.beta.cpu().numpy()[:, 0]
+    if tag == "ref":
+        # degenerate regime: once products overflow, WHICH non-finite pattern appears (alpha = -0 / beta = +inf in the
+        # reference's summation order, NaN as soon as infinities of both signs meet in another order) depends on fp32
+        # rounding history; what is reproducible - and what the training loop consumes - are the labels: every score is
+        # NaN, torch.argmax returns index 0, and so does the kernel's NaN-aware argmax
+        assert np.array_equal(labels, g["ref_labels"]) and not labels.any()
+        assert np.all((a == 0) | np.isnan(a)) and np.all(np.isinf(bt) | np.isnan(bt))
+        return
+    logp = torch.log_softmax(torch.from_numpy(logits).double(), -1).numpy()
+    score = (a[:, None].astype(np.float64) * np.power(logp, lmbd).T * bt[None, :].astype(np.float64)).T
+    ref_score = g[f"{tag}_score"].astype(np.float64)
+    np.testing.assert_allclose(score, ref_score, rtol=5e-3, atol=1e-6 * np.abs(ref_score).max())
+    top2 = np.sort(ref_score, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-3 * np.abs(top2[:, 1])
+    assert np.array_equal(labels[clear], g[f"{tag}_labels"][clear])
+    # the oracle (fp64) agrees as well, and the state carries over to a second batch
+    oa, ob, ol, _ = O.sela_self_label(logits, g[f"{tag}_alpha0"][:, 0], g[f"{tag}_beta0"][:, 0], lmbd, iters)
+    assert np.array_equal(labels[clear], ol[clear])
+    logits2 = randn(77, b, k)
+    labels2 = lab.step(torch.from_numpy(logits2).cuda(), num_iters=iters).cpu().numpy()
+    _, _, ol2, sc2 = O.sela_self_label(logits2, a, bt, lmbd, iters)
+    t2 = np.sort(sc2, axis=1)[:, -2:]
+    clear2 = (t2[:, 1] - t2[:, 0]) > 1e-3 * np.abs(t2[:, 1])
+    assert np.array_equal(labels2[clear2], ol2[clear2])

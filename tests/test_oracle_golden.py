@@ -139,3 +139,26 @@ def test_pirl_bank_oracle_vs_reference():
     bank2 = O.pirl_bank_update(g["pbank_after_init"], g["pbank_idx"], g["pbank_v1"], 0.5)
     np.testing.assert_allclose(bank2, g["pbank_after_update"], rtol=3e-7, atol=0)
     assert np.array_equal(g["pbank_pos"], g["pbank_after_update"][[7, 11]])
+
+
+@pytest.mark.parametrize("tag", ["s1", "s2"])
+def test_sela_self_label_oracle_vs_reference(tag):
+    """SeLA self-labelling (models/sela.py:152-160): the fp64 oracle against the reference's own fp32 statements.
+    alpha / beta individually carry a gauge (alpha * c, beta / c) that the fp32 iteration fixes by its rounding history,
+    so the comparison is on the gauge-free score matrix and on the labels (wherever the top-2 margin is not a near-tie)."""
+    g = load_golden("sela")
+    lmbd, iters = (int(v) for v in g[f"{tag}_cfg"])
+    a, b, labels, score = O.sela_self_label(g[f"{tag}_logits"], g[f"{tag}_alpha0"][:, 0], g[f"{tag}_beta0"][:, 0], lmbd, iters)
+    ref_score = g[f"{tag}_score"].astype(np.float64)
+    np.testing.assert_allclose(score, ref_score, rtol=5e-3, atol=1e-6 * np.abs(ref_score).max())
+    top2 = np.sort(ref_score, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-3 * np.abs(top2[:, 1])
+    assert clear.mean() > 0.9
+    assert np.array_equal(labels[clear], g[f"{tag}_labels"][clear])
+
+
+def test_sela_reference_configuration_degenerates_in_fp32():
+    """The reference's own configuration (lambda 25, 80 iterations, 128 clusters: configs/sela.yaml) underflows in fp32:
+    alpha -> 0, beta -> inf, every label 0.  The fixture pins that behaviour (a drop-in has to reproduce it)."""
+    g = load_golden("sela")
+    assert not np.any(g["ref_alpha"]) and np.all(np.isinf(g["ref_beta"])) and not np.any(g["ref_labels"])

@@ -35,3 +35,39 @@ f4b = ssv_b200.SwavLoss(); bench("SwavLoss", step(lambda: f4b(a, b, pc), a, b, p
 q = torch.nn.functional.normalize(torch.randn(1024, 128, device=dev))
 f5 = DistributedMocoLoss(True, 0.07); bench("DistributedMocoLoss (world 1)", step(lambda: f5(a, b, q), a, b))
 f5b = ssv_b200.MocoLoss(True, 0.07); bench("MocoLoss", step(lambda: f5b(a, b, q), a, b))
+
+# ---- where the host time goes (cProfile of 2000 SimclrLoss fwd+bwd steps; cumulative, top 35)
+import cProfile, pstats, io
+run = step(lambda: f1(a, b), a, b)
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(2000):
+    run()
+pr.disable()
+torch.cuda.synchronize()
+sio = io.StringIO()
+pstats.Stats(pr, stream=sio).sort_stats("cumulative").print_stats(35)
+print(sio.getvalue()[:6000])
+# forward only / backward only split
+import time
+def fwd_only():
+    return f1(a, b)
+for _ in range(50): fwd_only()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(1000): l = fwd_only()
+t1 = time.perf_counter(); torch.cuda.synchronize()
+print(f"SimclrLoss forward only: host {1e6 * (t1 - t0) / 1000:.1f} us")
+from ssv_b200 import _cabi as C
+L = C.lib()
+t0 = time.perf_counter()
+for _ in range(20000): L.ssvb_version()
+print(f"bare ctypes call: {1e6 * (time.perf_counter() - t0) / 20000:.2f} us")
+t0 = time.perf_counter()
+for _ in range(20000): C.stream_ptr(dev)
+print(f"stream_ptr: {1e6 * (time.perf_counter() - t0) / 20000:.2f} us")
+t0 = time.perf_counter()
+for _ in range(20000): torch.empty((), dtype=torch.float32, device=dev)
+print(f"torch.empty scalar: {1e6 * (time.perf_counter() - t0) / 20000:.2f} us")
+t0 = time.perf_counter()
+for _ in range(20000): C.ptr(a)
+print(f"C.ptr: {1e6 * (time.perf_counter() - t0) / 20000:.2f} us")
