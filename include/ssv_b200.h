@@ -94,19 +94,6 @@ int ssvb_ntxent_dist_prep(const float* zi, const float* zj, int64_t n_local, int
 int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
                               int normalize, float temperature, const float* pos_local, float* stat_local,
                               float* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
-/* Fused compute + all-gather over NVLink peer memory (no NCCL on the data path): `peer_zhat` / `peer_stat` are
- * DEVICE arrays of `world` peer-mapped base pointers (every rank's gathered buffer, e.g. torch symmetric memory).
- * prep_push stores each normalised bf16 row into this rank's slot of EVERY rank's zhat buffer; rows_fwd_push stores
- * this rank's [lse | term] block into slot `rank` of every rank's [world][2][2L] buffer.  The caller separates the
- * stages with a barrier on the same peer group.  dist_loss sums the gathered per-row terms into the global loss. */
-int ssvb_ntxent_dist_prep_push(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
-                               int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
-                               void* const* peer_zhat,
-                               float* inv_norm_local, float* pos_local, void* stream);
-int ssvb_ntxent_dist_rows_fwd_push(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
-                                   int normalize, float temperature, const float* pos_local,
-                                   void* const* peer_stat, float* loss_sum, void* workspace,
-                                   size_t workspace_bytes, void* stream);
 int ssvb_ntxent_dist_loss(const float* stat_all, int64_t world, int64_t n_local, float* loss, void* stream);
 
 /* ---- NVLink peer-memory transport with generation flags (no NCCL, no host-issued barrier on the data path).
@@ -116,10 +103,10 @@ int ssvb_ntxent_dist_loss(const float* stat_all, int64_t world, int64_t n_local,
  * including this rank's own), `arena_local` this rank's base, `multicast_arena` the NVSwitch multicast mapping of the
  * same allocation or NULL (then unicast peer stores are used).  `gen` = 1, 2, 3, ... is the forward's generation,
  * identical on every rank; buffers inside the arena are double-buffered by its parity.
- *   prep_push : normalise + stage this rank's rows into EVERY arena, then publish flag[rows][rank] = gen everywhere
+ *   prep_push : normalise + stage this rank's rows into EVERY arena, then publish flag[rank] = gen everywhere
  *   wait_copy : wait for every rank's rows of `gen`, copy the gathered matrix into private memory `zhat_all`
- *   rows_fwd  : similarity rows of this rank -> [lse | term] stored into every arena, flag[stat][rank] = gen
- *   stat_loss : wait for every rank's statistics, write the backward's column statistics `colstat` [mpad] and the
+ *   rows_fwd  : similarity rows of this rank -> [lse | term] stored into every arena as 8-byte {value, gen} pairs
+ *   stat_loss : wait for every pair of generation `gen`, write the backward's column statistics `colstat` [mpad] and the
  *               global loss (fixed summation order: bit-identical on every rank)
  *   rows_bwd  : complete gradient of this rank's rows from zhat_all + colstat (no exchange) */
 size_t ssvb_ntxent_p2p_arena_bytes(int64_t world, int64_t n_local, int64_t d);
@@ -130,11 +117,18 @@ int ssvb_ntxent_p2p_prep_push(const float* zi, const float* zj, int64_t n_local,
 int ssvb_ntxent_p2p_wait_copy(const void* arena_local, int64_t world, int64_t rank, int64_t n_local, int64_t d,
                               int64_t gen, void* zhat_all, void* stream);
 int ssvb_ntxent_p2p_rows_fwd(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
-                             int normalize, float temperature, const float* pos_local, void* const* peer_arenas,
-                             int64_t gen, float* loss_sum, void* workspace, size_t workspace_bytes, void* stream);
-int ssvb_ntxent_p2p_stat_loss(const void* arena_local, int64_t world, int64_t rank, int64_t n_local, int64_t d,
+                             int normalize, float temperature, const float* pos_local, void* arena_local,
+                             void* const* peer_arenas, int64_t gen, float* loss_sum, void* workspace,
+                             size_t workspace_bytes, void* stream);
+int ssvb_ntxent_p2p_stat_loss(void* arena_local, int64_t world, int64_t rank, int64_t n_local, int64_t d,
                               int normalize, float temperature, int64_t gen, float* colstat, float* loss,
                               void* workspace, size_t workspace_bytes, void* stream);
+/* prep_push + wait_copy + rows_fwd + stat_loss in one call (same arguments, same order of launches). */
+int ssvb_ntxent_p2p_forward(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                            int normalize, float temperature, int64_t world, int64_t rank, void* arena_local,
+                            void* const* peer_arenas, void* multicast_arena, int64_t gen, void* zhat_all,
+                            float* inv_norm_local, float* pos_local, float* colstat, float* loss_sum, float* loss,
+                            void* workspace, size_t workspace_bytes, void* stream);
 int ssvb_ntxent_p2p_rows_bwd(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
                              int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
                              const void* zhat_all, const float* colstat, const float* inv_norm_local,

@@ -335,7 +335,7 @@ namespace {
 int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d, int normalize,
                   float temperature, const float* pos_local, float* stat_local, float* const* peer_stat,
                   float* loss_sum, void* workspace, size_t workspace_bytes, void* stream, size_t peer_stat_off = 0,
-                  size_t peer_flag_off = 0, uint32_t gen = 0);
+                  uint32_t gen = 0, unsigned int* counter = nullptr);
 }
 int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
                               int normalize, float temperature, const float* pos_local, float* stat_local,
@@ -344,19 +344,11 @@ int ssvb_ntxent_dist_rows_fwd(const void* zhat_all, int64_t world, int64_t rank,
   return rows_fwd_impl(zhat_all, world, rank, n_local, d, normalize, temperature, pos_local, stat_local, nullptr,
                        loss_sum, workspace, workspace_bytes, stream);
 }
-int ssvb_ntxent_dist_rows_fwd_push(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
-                                   int normalize, float temperature, const float* pos_local,
-                                   void* const* peer_stat, float* loss_sum, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
-  if (!peer_stat) return SSVB_ERR_INVALID;
-  return rows_fwd_impl(zhat_all, world, rank, n_local, d, normalize, temperature, pos_local, nullptr,
-                       reinterpret_cast<float* const*>(peer_stat), loss_sum, workspace, workspace_bytes, stream);
-}
 namespace {
 int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d, int normalize,
                   float temperature, const float* pos_local, float* stat_local, float* const* peer_stat,
                   float* loss_sum, void* workspace, size_t workspace_bytes, void* stream, size_t peer_stat_off,
-                  size_t peer_flag_off, uint32_t gen) {
+                  uint32_t gen, unsigned int* counter) {
   SSVB_TRY(check_device_sm100());
   SSVB_TRY(dist_check(world, rank, n_local));
   NtxPlan pl;
@@ -366,11 +358,17 @@ int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_l
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t lr = 2 * n_local;
   WsLayout ws = ws_layout(workspace, lr, ceil_div(lr, 128), pl.m, pl.dpad);
-  SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
+  // last-block counter of the finalize kernel: the workspace one needs zeroing (arbitrary contents); the peer-memory
+  // transport passes one that lives in the zero-initialised arena and resets itself after every use (one launch less)
+  if (!counter) {
+    counter = ws.counter;
+    SSVB_CUDA(cudaMemsetAsync(counter, 0, 16, s));
+  }
   // local outputs either go to the caller's [2][2L] block or (push mode) into slot `rank` of every peer's buffer
   float* lse_out = stat_local;
   float* term_out = stat_local ? stat_local + lr : nullptr;
-  const size_t peer_off = peer_stat_off / sizeof(float) + static_cast<size_t>(rank) * 2 * lr;
+  // element offset of this rank's block inside every peer's buffer: plain floats, or 8-byte {value, generation} pairs
+  const size_t peer_off = peer_stat_off / (gen ? sizeof(uint2) : sizeof(float)) + static_cast<size_t>(rank) * 2 * lr;
   SimParams p;
   fill_sim_params_rows(p, pl, 1, lr, rank * lr, 0);
   plan_chunks(p, kFwdBN, kFwdMinTiles);
@@ -384,42 +382,19 @@ int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_l
   if (pl.mode == SIM_NTX_FIXED)
     lse_finalize_kernel<SIM_NTX_FIXED><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride,
                                                           static_cast<int>(lr), pos_local, pl.c, pl.shift,
-                                                          ws.dacc /*scratch*/, lse_out, ws.block_sums, ws.counter,
+                                                          ws.dacc /*scratch*/, lse_out, ws.block_sums, counter,
                                                           1.f, loss_sum, term_out, peer_stat, static_cast<int>(world),
-                                                          peer_off, 1.f, peer_flag_off, static_cast<int>(rank), gen);
+                                                          peer_off, 1.f, gen);
   else
     lse_finalize_kernel<SIM_NTX_ONLINE><<<grid, 256, 0, s>>>(ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride,
                                                            static_cast<int>(lr), pos_local, pl.c, pl.shift,
                                                            ws.dacc /*scratch*/, lse_out, ws.block_sums,
-                                                           ws.counter, 1.f, loss_sum, term_out, peer_stat,
-                                                           static_cast<int>(world), peer_off, 1.f, peer_flag_off,
-                                                           static_cast<int>(rank), gen);
+                                                           counter, 1.f, loss_sum, term_out, peer_stat,
+                                                           static_cast<int>(world), peer_off, 1.f, gen);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
 }  // namespace
-
-// Fused normalise + all-gather: like dist_prep, but every bf16 row goes to the same slot of EVERY rank's gathered
-// matrix through `peer_zhat` (a DEVICE array of `world` peer-mapped base pointers, e.g. torch symmetric memory).
-int ssvb_ntxent_dist_prep_push(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,
-                               int64_t ld_zj, int normalize, float temperature, int64_t world, int64_t rank,
-                               void* const* peer_zhat, float* inv_norm_local, float* pos_local, void* stream) {
-  SSVB_TRY(check_device_sm100());
-  SSVB_TRY(dist_check(world, rank, n_local));
-  NtxPlan pl;
-  SSVB_TRY(make_plan(pl, n_local * world, d, normalize, temperature));
-  SSVB_TRY(check_rows(zi, ld_zi));
-  SSVB_TRY(check_rows(zj, ld_zj));
-  if (!peer_zhat || !inv_norm_local || !pos_local) return SSVB_ERR_INVALID;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int64_t row0 = rank * 2 * n_local;
-  pair_prep_push_kernel<<<static_cast<unsigned>(ceil_div(n_local, 8)), 256, 0, s>>>(
-      zi, zj, static_cast<int>(n_local), static_cast<int>(d), ld_zi, ld_zj, normalize, normalize ? 1 : 0, peer_zhat,
-      static_cast<int>(world), row0, row0 + n_local, static_cast<int>(pl.dpad), inv_norm_local,
-      inv_norm_local + n_local, pos_local, pos_local + n_local, pl.prescale);
-  SSVB_LAUNCH_CHECK();
-  return SSVB_OK;
-}
 
 // global loss from the gathered per-row terms: loss = sum(stat_all[:, 1, :]) / (2 * world * L); fixed order
 namespace {
@@ -550,15 +525,17 @@ int rows_bwd_impl(const float* zi, const float* zj, int64_t n_local, int64_t d, 
 // NVLink peer-memory transport (fused compute + all-gather, no NCCL and no host-issued barrier on the data path).
 // Every rank owns one SYMMETRIC arena (same layout everywhere, peer-mapped, e.g. torch symmetric memory):
 //     zhat[2]  : 2 x (2L*world) x dpad 16-bit rows   - the gathered normalised rows, double-buffered by generation parity
-//     stat[2]  : 2 x [world][2][2L] fp32              - the gathered [lse2 | per-row loss term] blocks, double-buffered
-//     flags    : [2][world] uint32                    - flags[k][r] = last generation rank r has completely published
-//                                                       (k = 0 rows, k = 1 statistics) into THIS arena
-//     counter  : 1 uint32 (+ padding)                 - last-block counter of the push kernel (self-resetting)
+//     stat[2]  : 2 x [world][2][2L] x 8 bytes         - the gathered [lse2 | per-row loss term] blocks, double-buffered
+//     stat[2]  : (see above) every element is an 8-byte {value, generation} pair ("LL" form: an 8-byte store is one
+//                transaction, the consumer validates each element by its tag - no fence, no completion flag)
+//     flags    : [world] uint32                       - flags[r] = last generation whose ROWS rank r has completely
+//                                                       published into THIS arena
+//     counter  : 3 x uint32 (+ padding)               - self-resetting last-block counters (push / finalize / stat_loss)
 // A forward of generation g:  p2p_prep_push (normalise, store own slot into every arena - unicast peer stores or one
-// multicast store through the switch -, last block publishes flags[0][rank] = g everywhere)  ->  p2p_wait_copy (waits
-// for flags[0][*] >= g, copies the gathered rows into a private matrix: the tensor-core kernels read ordinary device
-// memory faster than a peer-mapped mapping)  ->  sim_fwd + finalize (stores [lse2 | term] into every arena,
-// publishes flags[1][rank] = g)  ->  p2p_stat_loss (waits for flags[1][*] >= g, derives the backward's column
+// multicast store through the switch -, last block publishes flags[rank] = g everywhere)  ->  p2p_wait_copy (waits
+// for flags[*] >= g, copies the gathered rows into a private matrix: the tensor-core kernels read ordinary device
+// memory faster than a peer-mapped mapping)  ->  sim_fwd + finalize (stores tagged [lse2 | term] pairs into every
+// arena)  ->  p2p_stat_loss (waits for every pair of generation g, derives the backward's column
 // statistics and the global loss in a fixed order: bit-identical on every rank).  Backward needs no exchange.
 // Double buffering makes the protocol barrier-free: a rank can only push generation g+2 (same parity as g) after it
 // has seen every peer's generation g+1 statistics, which a peer publishes after it has finished reading generation g.
@@ -577,8 +554,8 @@ ArenaLayout arena_layout(int64_t world, int64_t n_local, int64_t dpad) {
   };
   const size_t m = static_cast<size_t>(2 * n_local * world);
   for (int i = 0; i < 2; ++i) a.zhat[i] = take(m * dpad * sizeof(__nv_bfloat16));
-  for (int i = 0; i < 2; ++i) a.stat[i] = take(m * 2 * sizeof(float));
-  a.flags = take(2 * static_cast<size_t>(world) * sizeof(uint32_t));
+  for (int i = 0; i < 2; ++i) a.stat[i] = take(m * 2 * sizeof(uint2));  // {value, generation} pairs
+  a.flags = take(static_cast<size_t>(world) * sizeof(uint32_t));
   a.counter = take(64);
   a.bytes = (off + 1023) & ~static_cast<size_t>(1023);
   return a;
@@ -687,22 +664,19 @@ __global__ void p2p_wait_copy_kernel(const uint8_t* __restrict__ arena, size_t z
 
 // waits for every rank's statistics of generation `gen`, then (a) column statistics of all M rows for the backward
 // kernel (FIXED: wscale / L', else lse2; finite padding), (b) the global loss = fixed-order sum of the per-row terms.
-__global__ void p2p_stat_loss_kernel(const uint8_t* __restrict__ arena, size_t soff, size_t flag_off, int world,
-                                     uint32_t gen, int lr, int m, int mpad, int fixed, float shift, float wscale,
+__global__ void p2p_stat_loss_kernel(const uint8_t* arena, size_t soff, uint32_t gen, int lr, int m, int mpad, int fixed, float shift, float wscale,
                                      float* __restrict__ colstat, float* block_sums, unsigned int* counter, float scale,
                                      float* loss) {
-  if (threadIdx.x < world)
-    spin_wait_gen(reinterpret_cast<const uint32_t*>(arena + flag_off) + world + threadIdx.x, gen);
-  __syncthreads();
-  const float* g = reinterpret_cast<const float*>(arena + soff);
+  // every element arrives as an 8-byte {value, generation} pair: wait for the tag of THIS generation, element by element
+  const uint2* g = reinterpret_cast<const uint2*>(arena + soff);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float term = 0.f;
   if (i < mpad) {
     if (i < m) {
       const int r = i / lr;
       const size_t base = static_cast<size_t>(r) * 2 * lr + (i - r * lr);
-      const float l2 = __ldcg(g + base);
-      term = __ldcg(g + base + lr);
+      const float l2 = ll_wait_value(g + base, gen);
+      term = ll_wait_value(g + base + lr, gen);
       colstat[i] = fixed ? wscale * exp2f(shift - l2) : l2;
     } else {
       colstat[i] = fixed ? 0.f : 1e30f;
@@ -771,17 +745,18 @@ int ssvb_ntxent_p2p_wait_copy(const void* arena_local, int64_t world, int64_t ra
 }
 
 int ssvb_ntxent_p2p_rows_fwd(const void* zhat_all, int64_t world, int64_t rank, int64_t n_local, int64_t d,
-                             int normalize, float temperature, const float* pos_local, void* const* peer_arenas,
-                             int64_t gen, float* loss_sum, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!peer_arenas || gen <= 0 || d <= 0) return SSVB_ERR_INVALID;
+                             int normalize, float temperature, const float* pos_local, void* arena_local,
+                             void* const* peer_arenas, int64_t gen, float* loss_sum, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (!arena_local || !peer_arenas || gen <= 0 || d <= 0) return SSVB_ERR_INVALID;
   const ArenaLayout al = arena_layout(world, n_local, sim_dpad(d));
   return rows_fwd_impl(zhat_all, world, rank, n_local, d, normalize, temperature, pos_local, nullptr,
                        reinterpret_cast<float* const*>(peer_arenas), loss_sum, workspace, workspace_bytes, stream,
-                       al.stat[static_cast<uint32_t>(gen) & 1], al.flags + world * sizeof(uint32_t),
-                       static_cast<uint32_t>(gen));
+                       al.stat[static_cast<uint32_t>(gen) & 1], static_cast<uint32_t>(gen),
+                       reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(arena_local) + al.counter) + 1);
 }
 
-int ssvb_ntxent_p2p_stat_loss(const void* arena_local, int64_t world, int64_t rank, int64_t n_local, int64_t d,
+int ssvb_ntxent_p2p_stat_loss(void* arena_local, int64_t world, int64_t rank, int64_t n_local, int64_t d,
                               int normalize, float temperature, int64_t gen, float* colstat, float* loss,
                               void* workspace, size_t workspace_bytes, void* stream) {
   SSVB_TRY(check_device_sm100());
@@ -797,12 +772,29 @@ int ssvb_ntxent_p2p_stat_loss(const void* arena_local, int64_t world, int64_t ra
   // block partials: part_l is free again once the finalize kernel of this forward has run (same stream)
   float* block_sums = ws.part_l;
   p2p_stat_loss_kernel<<<static_cast<unsigned>(ceil_div(pl.mpad, 256)), 256, 0, s>>>(
-      static_cast<const uint8_t*>(arena_local), al.stat[static_cast<uint32_t>(gen) & 1], al.flags,
-      static_cast<int>(world), static_cast<uint32_t>(gen), static_cast<int>(lr), static_cast<int>(pl.m),
-      static_cast<int>(pl.mpad), pl.mode == SIM_NTX_FIXED, pl.shift, pl.wscale, colstat, block_sums, ws.counter,
+      static_cast<const uint8_t*>(arena_local), al.stat[static_cast<uint32_t>(gen) & 1],
+      static_cast<uint32_t>(gen), static_cast<int>(lr), static_cast<int>(pl.m),
+      static_cast<int>(pl.mpad), pl.mode == SIM_NTX_FIXED, pl.shift, pl.wscale, colstat, block_sums,
+      reinterpret_cast<unsigned int*>(const_cast<uint8_t*>(static_cast<const uint8_t*>(arena_local)) + al.counter) + 2,
       1.f / static_cast<float>(pl.m), loss);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
+}
+
+// The four forward stages in ONE call (the product path of DistributedSimclrLoss): at 8 GPUs the whole step is ~0.4 ms,
+// so every host microsecond between the launches shows; one ctypes crossing instead of four.
+int ssvb_ntxent_p2p_forward(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                            int normalize, float temperature, int64_t world, int64_t rank, void* arena_local,
+                            void* const* peer_arenas, void* multicast_arena, int64_t gen, void* zhat_all,
+                            float* inv_norm_local, float* pos_local, float* colstat, float* loss_sum, float* loss,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(ssvb_ntxent_p2p_prep_push(zi, zj, n_local, d, ld_zi, ld_zj, normalize, temperature, world, rank, arena_local,
+                                     peer_arenas, multicast_arena, gen, inv_norm_local, pos_local, stream));
+  SSVB_TRY(ssvb_ntxent_p2p_wait_copy(arena_local, world, rank, n_local, d, gen, zhat_all, stream));
+  SSVB_TRY(ssvb_ntxent_p2p_rows_fwd(zhat_all, world, rank, n_local, d, normalize, temperature, pos_local, arena_local,
+                                    peer_arenas, gen, loss_sum, workspace, workspace_bytes, stream));
+  return ssvb_ntxent_p2p_stat_loss(arena_local, world, rank, n_local, d, normalize, temperature, gen, colstat, loss,
+                                   workspace, workspace_bytes, stream);
 }
 
 int ssvb_ntxent_p2p_rows_bwd(const float* zi, const float* zj, int64_t n_local, int64_t d, int64_t ld_zi,

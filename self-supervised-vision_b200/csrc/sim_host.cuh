@@ -175,56 +175,6 @@ static __global__ void pair_prep_kernel(const float* __restrict__ xi, const floa
   }
 }
 
-// pair_prep + fused all-gather: every bf16 row is stored into the same slot of EVERY rank's gathered matrix through
-// peer-mapped pointers (NVLink stores), so no separate collective is needed (a barrier publishes the data).
-static __global__ void pair_prep_push_kernel(const float* __restrict__ xi, const float* __restrict__ xj, int n, int d,
-                                             int64_t ldi, int64_t ldj, int normalize, int f16,
-                                             void* const* __restrict__ peers,
-                                             int world, int64_t row_i, int64_t row_j, int dpad,
-                                             float* __restrict__ inv_i, float* __restrict__ inv_j,
-                                             float* __restrict__ pos_i, float* __restrict__ pos_j,
-                                             float prescale = 1.f) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n) return;
-  const float* ri = xi + static_cast<int64_t>(warp) * ldi;
-  const float* rj = xj + static_cast<int64_t>(warp) * ldj;
-  const int k = lane * 4;  // dpad <= 128: one float4 per lane
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-  if (k < d) {
-    a = *reinterpret_cast<const float4*>(ri + k);
-    b = *reinterpret_cast<const float4*>(rj + k);
-  }
-  float si = warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w);
-  float sj = warp_sum(b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w);
-  float ivi = 1.f, ivj = 1.f;
-  if (normalize) {
-    ivi = 1.f / fmaxf(sqrtf(si), 1e-12f);
-    ivj = 1.f / fmaxf(sqrtf(sj), 1e-12f);
-  }
-  uint2 vi, vj;
-  const float si_ = ivi * prescale, sj_ = ivj * prescale;
-  vi.x = f16 ? pack_f16x2(a.x * si_, a.y * si_) : pack_bf16x2(a.x * si_, a.y * si_);
-  vi.y = f16 ? pack_f16x2(a.z * si_, a.w * si_) : pack_bf16x2(a.z * si_, a.w * si_);
-  vj.x = f16 ? pack_f16x2(b.x * sj_, b.y * sj_) : pack_bf16x2(b.x * sj_, b.y * sj_);
-  vj.y = f16 ? pack_f16x2(b.z * sj_, b.w * sj_) : pack_bf16x2(b.z * sj_, b.w * sj_);
-  const float2 fi01 = unpack_h2(vi.x, f16), fi23 = unpack_h2(vi.y, f16);
-  const float2 fj01 = unpack_h2(vj.x, f16), fj23 = unpack_h2(vj.y, f16);
-  float dot = warp_sum(fi01.x * fj01.x + fi01.y * fj01.y + fi23.x * fj23.x + fi23.y * fj23.y);
-  if (k < dpad) {
-    // start at a different peer per CTA so the ranks do not all hit the same NVLink port at the same time
-    const int p0 = static_cast<int>(blockIdx.x % static_cast<unsigned>(world));
-    for (int q = 0; q < world; ++q) {
-      const int pr = (p0 + q) % world;
-      __nv_bfloat16* base = static_cast<__nv_bfloat16*>(peers[pr]);
-      *reinterpret_cast<uint2*>(base + (row_i + warp) * dpad + k) = vi;
-      *reinterpret_cast<uint2*>(base + (row_j + warp) * dpad + k) = vj;
-    }
-  }
-  if (lane == 0) {
-    inv_i[warp] = ivi; inv_j[warp] = ivj; pos_i[warp] = dot; pos_j[warp] = dot;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // deterministic block-sum -> scalar: every block writes its partial, the last block to finish adds
 // them in index order (no float atomics -> run-to-run bit-stable loss).
@@ -244,12 +194,11 @@ __device__ __forceinline__ float block_sum_256(float v) {
   return t;  // valid in warp 0
 }
 __device__ __forceinline__ bool grid_sum_finish(float block_total, float* block_sums, unsigned int* counter,
-                                                float scale, float* out, bool accumulate, bool sys_fence = false) {
+                                                float scale, float* out, bool accumulate) {
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
     block_sums[blockIdx.x] = block_total;
-    if (sys_fence) __threadfence_system();  // the CTA also stored into peer memory: order those stores too
-    else __threadfence();
+    __threadfence();
     const unsigned int done = atomicAdd(counter, 1u);
     is_last = (done == gridDim.x - 1);
   }
@@ -279,6 +228,27 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_volatile_u2(uint2* p, uint2 v) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint2 ld_volatile_u2(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+// LL consumer: spin until the 8-byte {value, tag} pair carries generation `gen`; bounded like spin_wait_gen
+__device__ __forceinline__ float ll_wait_value(const uint2* p, uint32_t gen) {
+  uint2 v = ld_volatile_u2(p);
+  if (v.y != gen) {
+    const long long t0 = clock64();
+    do {
+      __nanosleep(32);
+      v = ld_volatile_u2(p);
+      if (clock64() - t0 > 60000000000LL) __trap();
+    } while (v.y != gen);
+  }
+  return __uint_as_float(v.x);
+}
 // wait until a peer has published generation `gen` (monotonic counters, wrap-safe compare).  Bounded: a rank that
 // never arrives turns into a CUDA error after ~30 s instead of a hung GPU.
 __device__ __forceinline__ void spin_wait_gen(const uint32_t* flag, uint32_t gen) {
@@ -307,17 +277,26 @@ __global__ void lse_finalize_kernel(const float* __restrict__ part_m, const floa
                                     float* __restrict__ stat, float* __restrict__ lse2_out,
                                     float* block_sums, unsigned int* counter, float loss_scale, float* loss,
                                     float* __restrict__ term_out = nullptr, float* const* __restrict__ peer_stat = nullptr,
-                                    int world = 0, size_t peer_off = 0, float wscale = 1.f,
-                                    size_t peer_flag_off = 0 /* bytes; 0 = no flags */, int rank = 0,
-                                    uint32_t gen = 0) {
+                                    int world = 0, size_t peer_off = 0 /* elements (floats, or 8-byte pairs if gen) */,
+                                    float wscale = 1.f, uint32_t gen = 0) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   float term = 0.f;
   if (r < nrows) {
     float lse2, st;
     const float p2 = pos[r] * c;
     if (MODE == SIM_NTX_FIXED) {
+      // 8 partials in flight per trip (the plain loop issued one dependent-latency load at a time: 9-11 us for 36-64
+      // partials per row on the multi-GPU path); the summation ORDER is unchanged (index order), so the result is too
       float L = 0.f;
-      for (int i = 0; i < nparts; ++i) L += part_l[static_cast<size_t>(i) * stride + r];
+      int i = 0;
+      for (; i + 8 <= nparts; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(part_l + static_cast<size_t>(i + u) * stride + r);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) L += v[u];
+      }
+      for (; i < nparts; ++i) L += __ldcg(part_l + static_cast<size_t>(i) * stride + r);
       lse2 = shift + log2f(L);
       st = wscale / L;  // backward weight W = e^s (st_a + st_b): wscale = 2^k keeps W in fp16's normal range
     } else {
@@ -333,24 +312,27 @@ __global__ void lse_finalize_kernel(const float* __restrict__ part_m, const floa
     if (lse2_out) lse2_out[r] = lse2;
     term = (lse2 - p2) * SSVB_LN2;
     if (term_out) term_out[r] = term;
-    if (peer_stat) {  // fused all-gather: store this rank's [lse2 | term] block straight into every peer's buffer
+    if (peer_stat) {
+      // fused all-gather of this rank's [lse2 | term] block into every peer's buffer.  `gen` != 0: "LL" form - every
+      // value travels as ONE 8-byte store {value, generation}; 8-byte stores are single transactions, so the consumer
+      // validates each element by its tag and neither a system fence nor a completion flag is needed (a fence after
+      // remote stores costs ~8 us on NVLink: profiles/r2_stage_timing.md).  gen == 0: plain floats (the caller
+      // separates the stages with a barrier).
       for (int pr = 0; pr < world; ++pr) {
-        float* dst = peer_stat[pr] + peer_off;
-        dst[r] = lse2;
-        dst[nrows + r] = term;
+        if (gen) {
+          uint2* dst = reinterpret_cast<uint2*>(peer_stat[pr]) + peer_off;
+          st_volatile_u2(dst + r, make_uint2(__float_as_uint(lse2), gen));
+          st_volatile_u2(dst + nrows + r, make_uint2(__float_as_uint(term), gen));
+        } else {
+          float* dst = peer_stat[pr] + peer_off;
+          dst[r] = lse2;
+          dst[nrows + r] = term;
+        }
       }
     }
   }
-  const float bt = block_sum_256(term);  // (contains CTA barriers: thread 0 has observed every thread's peer stores)
-  __syncthreads();
-  const bool last = grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false, peer_stat && peer_flag_off);
-  if (peer_stat && peer_flag_off && last && threadIdx.x < world) {
-    // every block fenced its peer stores before its counter increment: publish "statistics of generation `gen`
-    // from rank `rank` are complete" in every peer's flag array
-    __threadfence_system();
-    uint32_t* f = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(peer_stat[threadIdx.x]) + peer_flag_off);
-    st_release_sys_u32(f + rank, gen);
-  }
+  const float bt = block_sum_256(term);
+  grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false);
 }
 
 // Same combine for MANY partials per row (MoCo: the queue axis is split into up to 128 chunks x 4 warpgroups):

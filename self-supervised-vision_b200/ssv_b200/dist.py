@@ -90,7 +90,8 @@ class CudaStages:
         dev = zhat_all.device
         ws, ws_bytes = self._dist_ws(world, n_local, d, dev)
         C.check(C.lib().ssvb_ntxent_p2p_rows_fwd(C.ptr(zhat_all), world, rank, n_local, d, normalize, temperature,
-                                                 C.ptr(pos_local), C.c_void_p(arena.peers_dev), gen, C.ptr(loss_sum),
+                                                 C.ptr(pos_local), C.c_void_p(arena.local_ptr), C.c_void_p(arena.peers_dev),
+                                                 gen, C.ptr(loss_sum),
                                                  C.ptr(ws), ws_bytes, C.stream_ptr(dev)), "ssvb_ntxent_p2p_rows_fwd")
 
     def p2p_stat_loss(self, arena, world, rank, n_local, d, normalize, temperature, gen, colstat, loss):
@@ -100,13 +101,31 @@ class CudaStages:
                                                   temperature, gen, C.ptr(colstat), C.ptr(loss), C.ptr(ws), ws_bytes,
                                                   C.stream_ptr(dev)), "ssvb_ntxent_p2p_stat_loss")
 
+    def p2p_forward(self, zi, zj, normalize, temperature, world, rank, arena, gen, zhat_all, aux_ptr, n_aux, loss):
+        """All four forward stages in one C call.  `aux_ptr` = base address of one fp32 scratch tensor laid out as
+        [inv_norm (2L) | pos (2L) | colstat (mpad) | loss_sum | pad] (`n_aux` = (2L, mpad))."""
+        n, d = zi.shape
+        dev = zi.device
+        ws, ws_bytes = self._dist_ws(world, n, d, dev)
+        two_l, mpad = n_aux
+        p_inv, p_pos = aux_ptr, aux_ptr + 4 * two_l
+        p_col = aux_ptr + 8 * two_l
+        p_sum = p_col + 4 * mpad
+        C.check(C.lib().ssvb_ntxent_p2p_forward(C.ptr(zi), C.ptr(zj), n, d, zi.stride(0), zj.stride(0), normalize,
+                                                temperature, world, rank, C.c_void_p(arena.local_ptr),
+                                                C.c_void_p(arena.peers_dev), C.c_void_p(arena.multicast_ptr or None), gen,
+                                                C.ptr(zhat_all), C.c_void_p(p_inv), C.c_void_p(p_pos), C.c_void_p(p_col),
+                                                C.c_void_p(p_sum), C.ptr(loss), C.ptr(ws), ws_bytes,
+                                                C.stream_ptr(dev)), "ssvb_ntxent_p2p_forward")
+
     def p2p_rows_bwd(self, zi, zj, normalize, temperature, world, rank, zhat_all, colstat, inv_local, grad_out, dzi, dzj):
         n, d = zi.shape
         dev = zi.device
         ws, ws_bytes = self._dist_ws(world, n, d, dev)
+        as_ptr = lambda x: C.c_void_p(x) if isinstance(x, int) else C.ptr(x)  # noqa: E731  (tensor or raw device address)
         C.check(C.lib().ssvb_ntxent_p2p_rows_bwd(C.ptr(zi), C.ptr(zj), n, d, zi.stride(0), zj.stride(0), normalize,
-                                                 temperature, world, rank, C.ptr(zhat_all), C.ptr(colstat),
-                                                 C.ptr(inv_local), C.ptr(grad_out), C.ptr(dzi), C.ptr(dzj),
+                                                 temperature, world, rank, C.ptr(zhat_all), as_ptr(colstat),
+                                                 as_ptr(inv_local), C.ptr(grad_out), C.ptr(dzi), C.ptr(dzj),
                                                  dzi.stride(0), dzj.stride(0), C.ptr(ws), ws_bytes, C.stream_ptr(dev)),
                 "ssvb_ntxent_p2p_rows_bwd")
 
@@ -199,8 +218,6 @@ class _NtxentDistFn(torch.autograd.Function):
         m = 2 * n * world
         mpad, dpad = stages.mpad(n * world), stages.dpad(d)  # (memoised for the CUDA stages)
         norm = int(bool(normalize))
-        inv_local = torch.empty(2 * n, dtype=torch.float32, device=dev)
-        pos_local = torch.empty(2 * n, dtype=torch.float32, device=dev)
         use_p2p = False
         multicast = transport != "p2p-unicast"
         if cuda and world > 1 and transport in ("auto", "p2p", "p2p-unicast"):
@@ -208,20 +225,21 @@ class _NtxentDistFn(torch.autograd.Function):
         if use_p2p:
             arena = _PeerArena.get(group, world, n, d, dev, multicast)
             gen = arena.next_gen()
-            loss = torch.empty((), dtype=torch.float32, device=dev)
-            loss_sum = torch.empty((), dtype=torch.float32, device=dev)
-            zhat_all = torch.empty(mpad, dpad, dtype=torch.bfloat16, device=dev)
-            colstat = torch.empty(mpad, dtype=torch.float32, device=dev)
             tau = float(temperature)
-            stages.p2p_prep_push(xi, xj, norm, tau, world, rank, arena, gen, inv_local, pos_local)
-            stages.p2p_wait_copy(arena, world, rank, n, d, gen, zhat_all)
-            stages.p2p_rows_fwd(zhat_all, world, rank, n, d, norm, tau, pos_local, arena, gen, loss_sum)
-            stages.p2p_stat_loss(arena, world, rank, n, d, norm, tau, gen, colstat, loss)
+            zhat_all = torch.empty(mpad, dpad, dtype=torch.bfloat16, device=dev)
+            # one fp32 scratch tensor for everything small: [inv_norm 2L | pos 2L | colstat mpad | loss_sum | loss]
+            # (each torch.empty costs ~2 us of host time and the whole 8-GPU step is ~0.4 ms)
+            two_l = 2 * n
+            aux = torch.empty(2 * two_l + mpad + 2, dtype=torch.float32, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)   # (an output must not be a view of a saved tensor)
+            stages.p2p_forward(xi, xj, norm, tau, world, rank, arena, gen, zhat_all, aux.data_ptr(), (two_l, mpad), loss)
             # everything the backward needs is private memory: the arena is never read again after this forward
-            ctx.save_for_backward(xi, xj, zhat_all, colstat, inv_local)
+            ctx.save_for_backward(xi, xj, zhat_all, aux)
             ctx.cfg = (norm, tau, world, rank, stages, zi.dtype, zj.dtype)
-            ctx.p2p = True
+            ctx.p2p = (two_l, mpad)
             return loss
+        inv_local = torch.empty(2 * n, dtype=torch.float32, device=dev)
+        pos_local = torch.empty(2 * n, dtype=torch.float32, device=dev)
         zhat_all = torch.empty(mpad, dpad, dtype=torch.bfloat16, device=dev)
         # per rank: [lse2 (2L) | per-row loss term (2L)] -> one all-gather serves the backward AND the global loss
         stat_all = torch.empty(world, 2, 2 * n, dtype=torch.float32, device=dev)
@@ -242,19 +260,23 @@ class _NtxentDistFn(torch.autograd.Function):
             loss = loss_sum / m
         ctx.save_for_backward(xi, xj, zhat_all, stat_all, inv_local)
         ctx.cfg = (norm, float(temperature), world, rank, stages, zi.dtype, zj.dtype)
-        ctx.p2p = False
+        ctx.p2p = None
         return loss
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_out):
-        xi, xj, zhat_all, stat_all, inv_local = ctx.saved_tensors
         norm, temperature, world, rank, stages, dti, dtj = ctx.cfg
         go = C.f32_scalar(grad_out)
-        dzi, dzj = torch.empty_like(xi), torch.empty_like(xj)
-        if ctx.p2p:   # stat_all is the derived column-statistics vector here
-            stages.p2p_rows_bwd(xi, xj, norm, temperature, world, rank, zhat_all, stat_all, inv_local, go, dzi, dzj)
+        if ctx.p2p is not None:
+            xi, xj, zhat_all, aux = ctx.saved_tensors
+            two_l, mpad = ctx.p2p
+            dzi, dzj = torch.empty_like(xi), torch.empty_like(xj)
+            base = aux.data_ptr()   # raw addresses instead of two view objects: [inv_norm | pos | colstat | ...]
+            stages.p2p_rows_bwd(xi, xj, norm, temperature, world, rank, zhat_all, base + 8 * two_l, base, go, dzi, dzj)
         else:
+            xi, xj, zhat_all, stat_all, inv_local = ctx.saved_tensors
+            dzi, dzj = torch.empty_like(xi), torch.empty_like(xj)
             stages.rows_bwd(xi, xj, norm, temperature, world, rank, zhat_all, stat_all, inv_local, go, dzi, dzj)
         return dzi.to(dti), dzj.to(dtj), None, None, None, None, None
 
