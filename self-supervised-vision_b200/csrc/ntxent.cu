@@ -564,7 +564,7 @@ ArenaLayout arena_layout(int64_t world, int64_t n_local, int64_t dpad) {
 namespace {
 // ROWS_PER_WARP row pairs per warp with all their loads issued up front (the one-row-per-warp form is latency-bound:
 // one 16-byte load per lane in flight), 8 warps per CTA.
-constexpr int P2P_RPW = 4;
+constexpr int P2P_RPW = 2;
 __global__ void __launch_bounds__(256)
 p2p_prep_push_kernel(const float* __restrict__ xi, const float* __restrict__ xj, int n, int d,
                                      int64_t ldi, int64_t ldj, int normalize, int f16, float prescale,
@@ -634,11 +634,14 @@ p2p_prep_push_kernel(const float* __restrict__ xi, const float* __restrict__ xj,
     __threadfence_system();
     const unsigned int done = atomicAdd(counter, 1u);
     is_last = (done == gridDim.x - 1);
+    if (is_last) __threadfence();  // acquire side of the counter hand-off (device scope: the counter is local)
   }
   __syncthreads();
   if (is_last) {
+    // every CTA fenced its stores at SYSTEM scope before counting in and this CTA has acquired all of those increments:
+    // the system-scope release store below is ordered after all of them - no second system fence (each costs a
+    // round trip over NVLink once remote stores are outstanding)
     if (threadIdx.x < world) {
-      __threadfence_system();
       uint32_t* f = reinterpret_cast<uint32_t*>(peers[threadIdx.x] + flag_off);
       st_release_sys_u32(f + rank, gen);
     }
