@@ -100,6 +100,52 @@ def time_graph(fn, reps, flush):
         return None
 
 
+TIMELINE = None   # file object: when set, legs() also prints the kernel timeline of one graph replay of each row
+
+
+def graph_timeline(fn, flush, title, out):
+    """Per-kernel start / gap / duration of ONE CUDA-graph replay of `fn` (torch.profiler = CUPTI; L2 flushed before)."""
+    from torch.profiler import ProfilerActivity, profile
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                flush.zero_()
+                g.replay()
+                torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        evs.sort(key=lambda e: e.time_range.start)
+        # the last replay = everything after the last flush fill (a 256 MiB FillFunctor<unsigned char> launch)
+        cut = max(i for i, e in enumerate(evs) if "FillFunctor<unsigned char>" in e.name)
+        step = evs[cut + 1:]
+        if not step:
+            return
+        t0 = step[0].time_range.start
+        print(f"## {title}: {len(step)} device activities, {step[-1].time_range.end - t0:.1f} us first start -> last end",
+              file=out)
+        prev = t0
+        for e in step:
+            s_, dur = e.time_range.start - t0, e.time_range.end - e.time_range.start
+            print(f"  +{s_:8.1f} us  gap {e.time_range.start - prev:6.1f}  dur {dur:8.1f}  {e.name[:110]}", file=out)
+            prev = e.time_range.end
+        out.flush()
+    except Exception as e:  # noqa: BLE001
+        print(f"## {title}: timeline failed: {type(e).__name__}: {str(e)[:160]}", file=out)
+        torch.cuda.synchronize()
+
+
 def time_cpu(fn, budget_s=4.0, max_reps=5):
     """1 warm-up + up to max_reps timed repetitions within ~budget_s; mean seconds."""
     fn()
@@ -168,6 +214,10 @@ def run_all(dev=None, reps=20, cpu=True, ref_gpu=True, only=None, emit=None):
         rp = reps_ or reps
         ms = time_gpu(ours, rp, flush)
         gms = time_graph(ours, rp, flush)
+        if TIMELINE is not None:
+            legs.count = getattr(legs, "count", 0) + 1
+            graph_timeline(ours, flush, f"row {legs.count} (eager {ms * 1e3:.1f} us, graph "
+                           f"{(gms or 0) * 1e3:.1f} us)", TIMELINE)
         ref_ms = None
         if ref_gpu and R is not None and ref_cuda is not None:
             try:
@@ -454,8 +504,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--only", default=None, help="comma-separated row tags (cfg1,cfg2,cfg3,cfg4,swav,rowdot128,...)")
+    ap.add_argument("--timeline", default=None, help="also write the per-kernel timeline of one graph replay per row here")
     args = ap.parse_args()
     torch.cuda.set_device(0)
+    if args.timeline:
+        global TIMELINE
+        TIMELINE = open(args.timeline, "w")
     rows = run_all(torch.device("cuda", 0), reps=args.reps, cpu=not args.no_cpu, ref_gpu=not args.no_ref_gpu,
                    only=args.only.split(",") if args.only else None,
                    emit=lambda r: print(json.dumps(r), flush=True))

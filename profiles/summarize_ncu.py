@@ -66,5 +66,40 @@ def report(path):
             print(f"    {h:30s} {v:8.2f}")
 
 
+def metrics(path):
+    """Per-kernel means of every metric in a `ncu --metrics a,b,c --csv` log (one line per launch and metric)."""
+    rows = list(csv.reader(open(path, errors="ignore")))
+    hdr = None
+    per = collections.OrderedDict()   # kernel -> metric -> [values]
+    for r in rows:
+        if "Kernel Name" in r:
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr):
+            d = dict(zip(hdr, r))
+            try:
+                v = float(d["Metric Value"].replace(",", ""))
+            except ValueError:
+                continue
+            u = d["Metric Unit"]
+            scale = {"ns": 1e-3, "nsecond": 1e-3, "ms": 1e3, "msecond": 1e3, "Kbyte": 1e-3, "Gbyte": 1e3, "byte": 1e-6}.get(u, 1.0)
+            per.setdefault(d["Kernel Name"].split("(")[0][:60], collections.OrderedDict()).setdefault(
+                d["Metric Name"], []).append(v * scale)
+    names = []
+    for m in per.values():
+        for k in m:
+            if k not in names:
+                names.append(k)
+    short = {"gpu__time_duration.sum": "us", "dram__bytes_read.sum": "rd_MB", "dram__bytes_write.sum": "wr_MB",
+             "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_%", "lts__t_sector_hit_rate.pct": "l2hit_%",
+             "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_%", "launch__grid_size": "grid",
+             "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_%"}
+    print(f"# ncu --metrics ... --clock-control none : {path}   (means over the launches of each kernel; time in us, bytes in MB)")
+    print(f"{'kernel':62s} {'n':>4s} " + " ".join(f"{short.get(k, k[:10]):>9s}" for k in names))
+    for kname, m in sorted(per.items(), key=lambda kv: -sum(kv[1].get("gpu__time_duration.sum", [0]))):
+        n = len(next(iter(m.values())))
+        print(f"{kname:62s} {n:4d} " + " ".join(f"{(sum(m[k]) / len(m[k]) if k in m else float('nan')):9.2f}" for k in names))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "report": report, "metrics": metrics}[sys.argv[1]](sys.argv[2])
