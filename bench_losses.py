@@ -382,8 +382,12 @@ def run_all(dev=None, reps=20, cpu=True, ref_gpu=True, only=None, emit=None):
                       port_cpu=lambda: O.swav(z1.numpy(), z2.numpy(), c.numpy(), bk.numpy())))
 
     # ---- BYOL MSE / SimSiam
-    for (n, d) in ((32768, 128), (4096, 1024)):
-        if not on(f"rowdot{d}"):
+    for (n, d) in ((32768, 128), (4096, 1024), (524288, 128)):
+        # the last shape is 268 MB per operand (> the 126 MB L2): the streaming rate of the kernels without the
+        # launch / ramp share that dominates the 17 MB reference-sized rows
+        big = n * d * 4 > 128 * 1024 * 1024
+        rtag = "rowdot_big" if big else f"rowdot{d}"
+        if not on(rtag):
             continue
         o, t = unit(randn(0, n, d)), unit(randn(1, n, d))
         a, b = o.to(dev).requires_grad_(True), t.to(dev)
@@ -391,9 +395,9 @@ def run_all(dev=None, reps=20, cpu=True, ref_gpu=True, only=None, emit=None):
         rmse = torch.nn.MSELoss()                 # BYOL's loss IS torch.nn.MSELoss (models/byol.py:89)
         co, = req(o)
         go, = req(o.to(dev))
-        record(f"rowdot{d}", "MSELoss (BYOL)", f"{n}x{d}", bytes_=(2 + 3) * n * d * 4,
+        record(rtag, "MSELoss (BYOL)", f"{n}x{d}", bytes_=(2 + 3) * n * d * 4,
                **legs(fwd_bwd(lambda: fn_e(a, b), a), n,
-                      ref_cpu=fwd_bwd(lambda: rmse(co, t), co) if R else None,
+                      ref_cpu=fwd_bwd(lambda: rmse(co, t), co) if (R and not big) else None,
                       port_cpu=lambda: O.mse(o.numpy(), t.numpy()),
                       ref_cuda=fwd_bwd(lambda: rmse(go, b), go) if R else None))
         b2 = t.to(dev).requires_grad_(True)
@@ -401,9 +405,9 @@ def run_all(dev=None, reps=20, cpu=True, ref_gpu=True, only=None, emit=None):
         rss = R.losses.SimSiamLoss() if R else None
         co2, ct2 = req(o, t)
         go2, gt2 = req(o.to(dev), t.to(dev))
-        record(f"rowdot{d}", "SimSiamLoss", f"{n}x{d}", bytes_=(2 + 4) * n * d * 4,
+        record(rtag, "SimSiamLoss", f"{n}x{d}", bytes_=(2 + 4) * n * d * 4,
                **legs(fwd_bwd(lambda: fn_ss(a, b2), a, b2), n,
-                      ref_cpu=fwd_bwd(lambda: rss(co2, ct2), co2, ct2) if R else None,
+                      ref_cpu=fwd_bwd(lambda: rss(co2, ct2), co2, ct2) if (R and not big) else None,
                       port_cpu=lambda: O.simsiam(o.numpy(), t.numpy()),
                       ref_cuda=fwd_bwd(lambda: rss(go2, gt2), go2, gt2) if R else None))
 
@@ -457,10 +461,12 @@ def run_all(dev=None, reps=20, cpu=True, ref_gpu=True, only=None, emit=None):
                       ref_cpu=fwd_bwd(lambda: rp_(ci, cp, mp, mn), ci, cp) if R else None,
                       port_cpu=lambda: O.pirl(img.numpy(), patch.numpy(), mp.numpy(), mn.numpy(), True, 0.07, 0.5),
                       ref_cuda=fwd_bwd(lambda: rp_(gi, gp, mpd, mnd), gi, gp) if R else None))
-    if on("ema"):
+    for ema_tag, n_params, n_mid in (("ema", 11_200_000, 58), ("ema_big", 25_600_000, 158)):
+        if not on(ema_tag):
+            continue
         torch.manual_seed(0)
-        n_params = 11_200_000   # ~ResNet-18 sized network split into 62 tensors of mixed sizes
-        sizes = [64 * 3 * 9, 64, 64] + [n_params // 60] * 58 + [512 * 1000]
+        # ~ResNet-18 (62 tensors) / ~ResNet-50 (162 tensors, 307 MB of traffic > L2) sized networks, mixed tensor sizes
+        sizes = [64 * 3 * 9, 64, 64] + [n_params // (n_mid + 2)] * n_mid + [512 * 1000]
         ema_tgt = [torch.randn(n, device=dev) for n in sizes]
         ema_src = [torch.randn(n, device=dev) for n in sizes]
         up = S.EmaUpdater(ema_tgt, ema_src)
@@ -475,7 +481,7 @@ def run_all(dev=None, reps=20, cpu=True, ref_gpu=True, only=None, emit=None):
         def ref_ema_cpu():
             for tp, sp in zip(c_tgt, c_src):
                 tp.data = 0.99 * tp.data + (1.0 - 0.99) * sp.data
-        record("ema", "EmaUpdater.step (momentum_update)", f"{len(sizes)} tensors, {tot / 1e6:.1f} M parameters",
+        record(ema_tag, "EmaUpdater.step (momentum_update)", f"{len(sizes)} tensors, {tot / 1e6:.1f} M parameters",
                bytes_=3 * tot * 4,
                note="bytes: read target + source, write target; one launch for the whole network (samples = parameters)",
                **legs(lambda: up.step(0.99), tot, ref_cpu=ref_ema_cpu if R else None, ref_cuda=ref_ema if R else None))

@@ -396,6 +396,16 @@ int ssvb_relic_kl_bwd(const float* zi, const float* zj, const float* zo, int64_t
                       int64_t ld_zj, int64_t ld_zo, int normalize, float temperature, float alpha,
                       const float* grad_out, const void* saved, float* dzi, float* dzj, float* dzo,
                       int64_t ld_dzi, int64_t ld_dzj, int64_t ld_dzo, void* stream);
+/* The whole RelicLoss.forward / backward (utils/losses.py:162-201) in one call each: ssvb_ntxent_fwd on (zi, zj) followed by
+ * the KL term; `loss` = contrastive + alpha*KL.  saved_ntxent: ssvb_ntxent_saved_bytes(n, d); saved_kl:
+ * ssvb_relic_kl_saved_bytes(n); workspace: ssvb_ntxent_workspace_bytes(n, d). */
+int ssvb_relic_fwd(const float* zi, const float* zj, const float* zo, int64_t n, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                   int64_t ld_zo, int normalize, float temperature, float alpha, float* loss, void* saved_ntxent,
+                   void* saved_kl, void* workspace, size_t workspace_bytes, void* stream);
+int ssvb_relic_bwd(const float* zi, const float* zj, const float* zo, int64_t n, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                   int64_t ld_zo, int normalize, float temperature, float alpha, const float* grad_out,
+                   const void* saved_ntxent, const void* saved_kl, float* dzi, float* dzj, float* dzo, int64_t ld_dzi,
+                   int64_t ld_dzj, int64_t ld_dzo, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Multi-GPU ReLIC-KL (SURVEY.md §8e last row): the KL's softmaxes run over the batch axis (utils/losses.py:196-200),
  * so the per-row logits of all ranks are all-gathered between two stages.  dist_dots writes this rank's a_n, b_n into
@@ -462,7 +472,7 @@ int ssvb_dino_center_update(const float* teacher_rows, int64_t rows, int64_t k, 
  *     img, patch, mem_pos: [n x d]; mem_neg: [k x d].  Two InfoNCE heads over the SAME negatives:
  *     logits_h = [mem_pos . v_h / tau | mem_pos mem_neg^T / tau], v_0 = patch, v_1 = img (L2-normalised when
  *     `normalize`; the memory rows are used as stored), loss = w CE_0 + (1 - w) CE_1 (label 0).
- *     loss2[0] / loss2[1] receive the two weighted head losses (the caller adds them).  The memory rows carry no
+ *     `loss` receives w CE_0 + (1 - w) CE_1 (one deterministic reduction over both heads).  The memory rows carry no
  *     gradient (models/pirl.py:131-133 reads them from the bank), so backward is one row-wise kernel.  d <= 128.
  *     ssvb_bank_scatter / ssvb_bank_gather: the per-sample momentum bank of models/pirl.py:22-46
  *     (mode 0 initialize_vectors, mode 1 update_vectors; indices: DEVICE int64).
@@ -471,7 +481,7 @@ size_t ssvb_pirl_saved_bytes(int64_t n, int64_t d);
 size_t ssvb_pirl_workspace_bytes(int64_t n, int64_t k, int64_t d);
 int ssvb_pirl_fwd(const float* img, const float* patch, const float* mem_pos, const float* mem_neg, int64_t n,
                   int64_t k, int64_t d, int64_t ld_img, int64_t ld_patch, int64_t ld_pos, int64_t ld_neg,
-                  int normalize, float temperature, float loss_weight, float* loss2, void* saved, void* workspace,
+                  int normalize, float temperature, float loss_weight, float* loss, void* saved, void* workspace,
                   size_t workspace_bytes, void* stream);
 int ssvb_pirl_bwd(const float* img, const float* patch, const float* mem_pos, int64_t n, int64_t d, int64_t ld_img,
                   int64_t ld_patch, int64_t ld_pos, int normalize, float temperature, float loss_weight,

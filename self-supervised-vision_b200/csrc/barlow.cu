@@ -18,7 +18,14 @@ namespace {
 
 constexpr int kColsPerBlock = 32;
 constexpr int kRowSplit = 8;  // row stripes per column group (fills the SMs at D = 4096..8192)
+constexpr int kStatSplit = 32;       // row stripes of the float4 statistics kernel (128 columns per block)
+constexpr int kMaxFusedStripes = 256;  // fused backward column partials: one stripe per (128-row tile, epilogue warp)
 constexpr int kMaxGemmCtas = 160;
+// stripes of the backward column partials written by the GEMM epilogue (0: too many rows, separate reduction pass)
+inline int fused_stripes(int64_t n) {
+  const int64_t t = ceil_div(n, 128) * 4;
+  return t <= kMaxFusedStripes ? static_cast<int>(t) : 0;
+}
 
 struct BarlowSaved {
   __nv_bfloat16 *xi, *xj;  // standardised operands [n x d]
@@ -43,7 +50,8 @@ BarlowSaved barlow_saved(void* base, int64_t n, int64_t d) {
   return s;
 }
 struct BarlowWs {
-  float* colpart;        // [2 views][kRowSplit][2][d]
+  float* colpart;        // [2 views][stripes][2][d], stripes = max(kStatSplit, fused_stripes(n), kRowSplit)
+  int64_t view_stride;   // floats between the two views' partials
   float* loss_partials;  // [kMaxGemmCtas]
   float *dti, *dtj;      // backward: [n x d] fp32 each
   float* colred;         // [2 views][2][d]  (mean of dT, sum(dT x~)/(n-1))
@@ -52,7 +60,10 @@ struct BarlowWs {
 BarlowWs barlow_ws(void* base, int64_t n, int64_t d) {
   Carver c(base);
   BarlowWs w;
-  w.colpart = c.take<float>(2 * kRowSplit * 2 * d);
+  int64_t stripes = kStatSplit > kRowSplit ? kStatSplit : kRowSplit;
+  if (fused_stripes(n) > stripes) stripes = fused_stripes(n);
+  w.view_stride = stripes * 2 * d;
+  w.colpart = c.take<float>(2 * w.view_stride);
   w.loss_partials = c.take<float>(kMaxGemmCtas);
   w.dti = c.take<float>(n * d);
   w.dtj = c.take<float>(n * d);
@@ -155,6 +166,57 @@ __global__ void col_partials_kernel(const float* __restrict__ x, int64_t ldx, co
     for (int i = 0; i < 8; ++i) { a += sh1[i][threadIdx.x]; b += sh2[i][threadIdx.x]; }
     part[(static_cast<int64_t>(stripe) * 2 + 0) * d + col] = a;
     part[(static_cast<int64_t>(stripe) * 2 + 1) * d + col] = b;
+  }
+}
+
+// Forward statistics, float4 version of MODE 0: block (32, 8) covers 128 columns (one float4 per thread and row), four
+// rows in flight per thread; same shifted sums and the same partial layout [stripe][2][d].
+__global__ void __launch_bounds__(256)
+col_stats4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row, int64_t n, int d,
+                  float* __restrict__ part) {
+  const int c4 = blockIdx.x * 32 + threadIdx.x;
+  const int stripe = blockIdx.y;
+  const int64_t rows_per = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = stripe * rows_per, r1 = min(n, r0 + rows_per);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  const bool ok = c4 * 4 < d;
+  if (ok) {
+    const float sc0 = inv_row ? inv_row[0] : 1.f;
+    float4 v0 = __ldg(reinterpret_cast<const float4*>(x) + c4);
+    v0 = make_float4(v0.x * sc0, v0.y * sc0, v0.z * sc0, v0.w * sc0);
+    auto acc = [&](const float4 v, const float sc) {
+      const float tx = v.x * sc - v0.x, ty = v.y * sc - v0.y, tz = v.z * sc - v0.z, tw = v.w * sc - v0.w;
+      s1.x += tx; s1.y += ty; s1.z += tz; s1.w += tw;
+      s2.x = fmaf(tx, tx, s2.x); s2.y = fmaf(ty, ty, s2.y); s2.z = fmaf(tz, tz, s2.z); s2.w = fmaf(tw, tw, s2.w);
+    };
+    int64_t r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {
+      float4 v[4];
+      float sc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = __ldg(reinterpret_cast<const float4*>(x + (r + 8 * u) * ldx) + c4);
+        sc[u] = inv_row ? inv_row[r + 8 * u] : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc(v[u], sc[u]);
+    }
+    for (; r < r1; r += 8) acc(__ldg(reinterpret_cast<const float4*>(x + r * ldx) + c4), inv_row ? inv_row[r] : 1.f);
+  }
+  __shared__ float4 sh1[8][32], sh2[8][32];
+  sh1[threadIdx.y][threadIdx.x] = s1;
+  sh2[threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && ok) {
+    float4 a = sh1[0][threadIdx.x], b = sh2[0][threadIdx.x];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      const float4 u = sh1[i][threadIdx.x], w = sh2[i][threadIdx.x];
+      a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+      b.x += w.x; b.y += w.y; b.z += w.z; b.w += w.w;
+    }
+    *reinterpret_cast<float4*>(part + (static_cast<int64_t>(stripe) * 2 + 0) * d + c4 * 4) = a;
+    *reinterpret_cast<float4*>(part + (static_cast<int64_t>(stripe) * 2 + 1) * d + c4 * 4) = b;
   }
 }
 
@@ -455,10 +517,10 @@ int stats_and_standardize(const float* x, int64_t ld, int normalize, int64_t n, 
     SSVB_LAUNCH_CHECK();
     inv = inv_row;
   }
-  dim3 grid(static_cast<unsigned>(ceil_div(d, kColsPerBlock)), kRowSplit), block(32, 8);
-  col_partials_kernel<0><<<grid, block, 0, s>>>(x, ld, inv, nullptr, 0, nullptr, nullptr, n, static_cast<int>(d), colpart);
+  dim3 grid(static_cast<unsigned>(ceil_div(d, 128)), kStatSplit), block(32, 8);
+  col_stats4_kernel<<<grid, block, 0, s>>>(x, ld, inv, n, static_cast<int>(d), colpart);
   SSVB_LAUNCH_CHECK();
-  col_finalize_kernel<0><<<static_cast<unsigned>(ceil_div(d, 256)), 256, 0, s>>>(colpart, kRowSplit, x, inv, n,
+  col_finalize_kernel<0><<<static_cast<unsigned>(ceil_div(d, 256)), 256, 0, s>>>(colpart, kStatSplit, x, inv, n,
                                                                                  static_cast<int>(d), mean, rstd);
   SSVB_LAUNCH_CHECK();
   const int64_t total = n * (d / 4);
@@ -497,7 +559,7 @@ int ssvb_barlow_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   BarlowWs ws = barlow_ws(workspace, n, d);
   SSVB_TRY(stats_and_standardize(zi, ld_zi, normalize, n, d, sv.inv_i, sv.mean_i, sv.rstd_i, sv.xi, ws.colpart, s));
   SSVB_TRY(stats_and_standardize(zj, ld_zj, normalize, n, d, sv.inv_j, sv.mean_j, sv.rstd_j, sv.xj,
-                                 ws.colpart + kRowSplit * 2 * d, s));
+                                 ws.colpart + ws.view_stride, s));
   // C = Xi~^T Xj~ / n : contraction over the batch axis, both operands MN-major in place
   GemmParams p{};
   p.M = static_cast<int>(d);
@@ -508,9 +570,10 @@ int ssvb_barlow_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   p.dC = sv.dC;
   p.ld_dc = d;
   p.loss_partials = ws.loss_partials;
-  SSVB_CUDA(cudaMemsetAsync(ws.loss_partials, 0, kMaxGemmCtas * sizeof(float), s));
   SSVB_TRY(launch_gemm({sv.xi, d, true}, {sv.xj, d, true}, p, 256, EPI_BARLOW, kMaxGemmCtas, s));
-  sum_partials_kernel<<<1, 256, 0, s>>>(ws.loss_partials, kMaxGemmCtas, 1.f, loss);
+  // every launched CTA wrote its partial (persistent kernel, grid = min(tiles, SMs)): sum exactly those, no memset
+  sum_partials_kernel<<<1, 256, 0, s>>>(ws.loss_partials, gemm_grid(ceil_div(d, 128) * ceil_div(d, 256), kMaxGemmCtas),
+                                        1.f, loss);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
@@ -538,25 +601,39 @@ int ssvb_barlow_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   p.alpha = 1.f / static_cast<float>(n);
   p.ldc = d;
   // dTi[n, a] = sum_b Xj~[n, b] dC[a, b]          (A K-major, B = dC rows K-major)
-  p.out = ws.dti;
-  SSVB_TRY(launch_gemm({sv.xj, d, false}, {sv.dC, d, false}, p, 256, EPI_STORE_F32, 0, s));
   // dTj[n, b] = sum_a Xi~[n, a] dC[a, b]          (A K-major, B = dC consumed MN-major)
-  p.out = ws.dtj;
-  SSVB_TRY(launch_gemm({sv.xi, d, false}, {sv.dC, d, true}, p, 256, EPI_STORE_F32, 0, s));
-
-  dim3 grid(static_cast<unsigned>(ceil_div(d, kColsPerBlock)), kRowSplit), block(32, 8);
+  // ONE launch for both (a shared persistent tile queue: 2 x 512 tiles = 6.9 waves of 148 CTAs instead of 2 x 3.46),
+  // and the epilogue leaves the column partials sum_n dT, sum_n dT x~ per (row tile, warp) beside the output
   const float* inv_i = normalize ? sv.inv_i : nullptr;
   const float* inv_j = normalize ? sv.inv_j : nullptr;
   float* part_i = ws.colpart;
-  float* part_j = ws.colpart + kRowSplit * 2 * d;
-  col_partials_kernel<1><<<grid, block, 0, s>>>(zi, ld_zi, inv_i, ws.dti, d, sv.mean_i, sv.rstd_i, n, static_cast<int>(d), part_i);
-  SSVB_LAUNCH_CHECK();
-  col_partials_kernel<1><<<grid, block, 0, s>>>(zj, ld_zj, inv_j, ws.dtj, d, sv.mean_j, sv.rstd_j, n, static_cast<int>(d), part_j);
-  SSVB_LAUNCH_CHECK();
+  float* part_j = ws.colpart + ws.view_stride;
+  int nsplit = fused_stripes(n);
+  p.out = ws.dti;
+  p.out2 = ws.dtj;
+  if (nsplit && gemm_tma_store_allowed()) {
+    p.colpart = part_i;
+    p.colpart2 = part_j;
+    p.xt = sv.xi;
+    p.xt2 = sv.xj;
+    p.ldx = d;
+  } else {
+    nsplit = 0;
+  }
+  const GemmOperand a2{sv.xi, d, false}, b2{sv.dC, d, true};
+  SSVB_TRY(launch_gemm({sv.xj, d, false}, {sv.dC, d, false}, p, 256, EPI_STORE_F32, 0, s, false, &a2, &b2));
+  if (!nsplit) {
+    nsplit = kRowSplit;
+    dim3 grid(static_cast<unsigned>(ceil_div(d, kColsPerBlock)), kRowSplit), block(32, 8);
+    col_partials_kernel<1><<<grid, block, 0, s>>>(zi, ld_zi, inv_i, ws.dti, d, sv.mean_i, sv.rstd_i, n, static_cast<int>(d), part_i);
+    SSVB_LAUNCH_CHECK();
+    col_partials_kernel<1><<<grid, block, 0, s>>>(zj, ld_zj, inv_j, ws.dtj, d, sv.mean_j, sv.rstd_j, n, static_cast<int>(d), part_j);
+    SSVB_LAUNCH_CHECK();
+  }
   const unsigned fgrid = static_cast<unsigned>(ceil_div(d, 256));
-  col_finalize_kernel<1><<<fgrid, 256, 0, s>>>(part_i, kRowSplit, nullptr, nullptr, n, static_cast<int>(d), ws.colred, ws.colred + d);
+  col_finalize_kernel<1><<<fgrid, 256, 0, s>>>(part_i, nsplit, nullptr, nullptr, n, static_cast<int>(d), ws.colred, ws.colred + d);
   SSVB_LAUNCH_CHECK();
-  col_finalize_kernel<1><<<fgrid, 256, 0, s>>>(part_j, kRowSplit, nullptr, nullptr, n, static_cast<int>(d), ws.colred + 2 * d, ws.colred + 3 * d);
+  col_finalize_kernel<1><<<fgrid, 256, 0, s>>>(part_j, nsplit, nullptr, nullptr, n, static_cast<int>(d), ws.colred + 2 * d, ws.colred + 3 * d);
   SSVB_LAUNCH_CHECK();
   barlow_finish_kernel<<<static_cast<unsigned>(n), 256, 0, s>>>(zi, ld_zi, inv_i, sv.mean_i, sv.rstd_i, ws.dti, d, ws.colred,
                                                               ws.colred + d, static_cast<int>(d), grad_out, dzi, ld_dzi);

@@ -11,53 +11,119 @@ struct GemmOperand {
   bool mn_major;     // false: global [rows x K]; true: global [K x rows]
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, int max_ctas, cudaStream_t s) {
-  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
-  constexpr int smem = GemmCfg<BN>::SMEM;
-  SSVB_TRY((set_smem_once<gemm_kernel<BN, A_MN, B_MN, EPI>>(smem)));
-  const int ntiles = p.tiles_m * p.tiles_n;
-  int grid = ntiles < num_sms() ? ntiles : num_sms();
+// grid of a persistent GEMM launch (also the number of EPI_BARLOW loss partials written)
+inline int gemm_grid(int64_t nunits, int max_ctas) {
+  int grid = nunits < num_sms() ? static_cast<int>(nunits) : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  return grid;
+}
+
+// split-K factor for a GEMM with `tiles` output tiles and `nkb` 64-wide K blocks: only when the tiles fill less than
+// half of the SMs, every slice keeps >= 4 K blocks, and no slice is empty
+inline void gemm_plan_splits(GemmParams& p, int64_t tiles, bool allow) {
+  const int nkb = static_cast<int>(ceil_div(p.K, 64));
+  int splits = 1;
+  if (allow && tiles * 2 <= num_sms()) {
+    splits = static_cast<int>(num_sms() / tiles);
+    if (splits > nkb / 4) splits = nkb / 4;
+    if (splits < 1) splits = 1;
+  }
+  p.kb_per_split = static_cast<int>(ceil_div(nkb, splits));
+  p.splits = static_cast<int>(ceil_div(nkb, p.kb_per_split));
+}
+
+inline bool gemm_tma_store_allowed() {
+  static int v = -1;
+  if (v < 0) v = getenv("SSVB_GEMM_NO_TMA_STORE") ? 0 : 1;  // A/B switch: per-thread row stores instead
+  return v != 0;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, bool DUAL>
+int launch_gemm_t(const CUtensorMap* tm, GemmParams p, int max_ctas, cudaStream_t s) {
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, DUAL>;
+  constexpr int smem = GemmCfg<BN>::SMEM;
+  SSVB_TRY((set_smem_once<gemm_kernel<BN, A_MN, B_MN, EPI, DUAL>>(smem)));
+  const int64_t nunits = static_cast<int64_t>(p.tiles_m) * p.tiles_n * (DUAL ? 2 : 1) * p.splits;
+  const int grid = gemm_grid(nunits, max_ctas);
   const int slot = prof_begin(PROF_GEMM, s);
-  kern<<<grid, 192, smem, s>>>(tmA, tmB, p);
+  kern<<<grid, 192, smem, s>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
   prof_end(slot, s);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
 
 // C[M x N] = alpha * A * B^T-style contraction over K (see gemm_kernels.cuh).  bn = 128 or 256.
-// For EPI_BARLOW the grid is capped at `max_ctas` (= size of p.loss_partials).
+// For EPI_BARLOW the grid is capped at `max_ctas` (>= the number of p.loss_partials written = gemm_grid(tiles, max_ctas)).
+// split_k: allow the split-K (add) epilogue - the caller has ZEROED p.out on the stream.
+// A2 / B2 (with p.out2): a second problem of the same shape in the same launch (B2 MN-major, B K-major).
 inline int launch_gemm(const GemmOperand& A, const GemmOperand& B, GemmParams p, int bn, int epi, int max_ctas,
-                       cudaStream_t s) {
+                       cudaStream_t s, bool split_k = false, const GemmOperand* A2 = nullptr,
+                       const GemmOperand* B2 = nullptr) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return SSVB_ERR_INVALID;
-  CUtensorMap tmA, tmB;
-  if (A.mn_major)
-    SSVB_TRY(make_tmap_bf16(&tmA, A.ptr, p.K, p.M, A.ld, 64));
-  else
-    SSVB_TRY(make_tmap_bf16(&tmA, A.ptr, p.M, p.K, A.ld, 128));
-  if (B.mn_major)
-    SSVB_TRY(make_tmap_bf16(&tmB, B.ptr, p.K, p.N, B.ld, 64));
-  else
-    SSVB_TRY(make_tmap_bf16(&tmB, B.ptr, p.N, p.K, B.ld, bn));
+  const bool dual = A2 != nullptr;
+  if (dual && (!B2 || A.mn_major || A2->mn_major || B.mn_major || !B2->mn_major || bn != 256 || epi != EPI_STORE_F32 || !p.out2))
+    return SSVB_ERR_UNSUPPORTED;
+  CUtensorMap tm[6];
+  auto operand_maps = [&](const GemmOperand& a, const GemmOperand& b, CUtensorMap* ta, CUtensorMap* tb) -> int {
+    if (a.mn_major)
+      SSVB_TRY(make_tmap_bf16(ta, a.ptr, p.K, p.M, a.ld, 64));
+    else
+      SSVB_TRY(make_tmap_bf16(ta, a.ptr, p.M, p.K, a.ld, 128));
+    if (b.mn_major)
+      SSVB_TRY(make_tmap_bf16(tb, b.ptr, p.K, p.N, b.ld, 64));
+    else
+      SSVB_TRY(make_tmap_bf16(tb, b.ptr, p.N, p.K, b.ld, bn));
+    return SSVB_OK;
+  };
+  SSVB_TRY(operand_maps(A, B, &tm[0], &tm[1]));
+  tm[3] = tm[0];
+  tm[4] = tm[1];
+  if (dual) SSVB_TRY(operand_maps(*A2, *B2, &tm[3], &tm[4]));
   p.tiles_m = static_cast<int>(ceil_div(p.M, 128));
   p.tiles_n = static_cast<int>(ceil_div(p.N, bn));
-#define SSVB_G(BNV, AM, BM_, E) return launch_gemm_t<BNV, AM, BM_, E>(tmA, tmB, p, max_ctas, s)
+  // staged TMA-store epilogue whenever the output rows are 16-byte aligned; otherwise per-thread row stores
   if (epi == EPI_BARLOW) {
-    if (bn == 256 && A.mn_major && B.mn_major) SSVB_G(256, true, true, EPI_BARLOW);
+    p.tma_store = gemm_tma_store_allowed() && !(reinterpret_cast<uintptr_t>(p.dC) & 15) && (p.ld_dc % 8 == 0);
+    if (p.tma_store) SSVB_TRY(make_tmap_out(&tm[2], p.dC, p.M, p.N, p.ld_dc, 2));
+  } else {
+    p.tma_store = gemm_tma_store_allowed() && !(reinterpret_cast<uintptr_t>(p.out) & 15) && (p.ldc % 4 == 0) &&
+                  (!dual || !(reinterpret_cast<uintptr_t>(p.out2) & 15));
+    if (p.tma_store) SSVB_TRY(make_tmap_out(&tm[2], p.out, p.M, p.N, p.ldc, 4));
+  }
+  if (!p.tma_store) {
+    tm[2] = tm[0];  // never dereferenced
+    if (p.colpart) return SSVB_ERR_ALIGNMENT;  // the fused column partials live in the staged epilogue
+  }
+  tm[5] = tm[2];
+  if (dual && p.tma_store) SSVB_TRY(make_tmap_out(&tm[5], p.out2, p.M, p.N, p.ldc, 4));
+  gemm_plan_splits(p, static_cast<int64_t>(p.tiles_m) * p.tiles_n,
+                   split_k && p.tma_store && epi == EPI_STORE_F32 && !dual && !p.colpart);
+#define SSVB_G(BNV, AM, BM_, E, D) return launch_gemm_t<BNV, AM, BM_, E, D>(tm, p, max_ctas, s)
+  if (epi == EPI_BARLOW) {
+    if (bn == 256 && A.mn_major && B.mn_major) SSVB_G(256, true, true, EPI_BARLOW, false);
     return SSVB_ERR_UNSUPPORTED;
   }
+  if (dual) SSVB_G(256, false, false, EPI_STORE_F32, true);
   if (bn == 256) {
-    if (!A.mn_major && !B.mn_major) SSVB_G(256, false, false, EPI_STORE_F32);
-    if (!A.mn_major && B.mn_major) SSVB_G(256, false, true, EPI_STORE_F32);
-    if (A.mn_major && B.mn_major) SSVB_G(256, true, true, EPI_STORE_F32);
+    if (!A.mn_major && !B.mn_major) SSVB_G(256, false, false, EPI_STORE_F32, false);
+    if (!A.mn_major && B.mn_major) SSVB_G(256, false, true, EPI_STORE_F32, false);
+    if (A.mn_major && B.mn_major) SSVB_G(256, true, true, EPI_STORE_F32, false);
   } else if (bn == 128) {
-    if (!A.mn_major && !B.mn_major) SSVB_G(128, false, false, EPI_STORE_F32);
-    if (!A.mn_major && B.mn_major) SSVB_G(128, false, true, EPI_STORE_F32);
-    if (A.mn_major && B.mn_major) SSVB_G(128, true, true, EPI_STORE_F32);
+    if (!A.mn_major && !B.mn_major) SSVB_G(128, false, false, EPI_STORE_F32, false);
+    if (!A.mn_major && B.mn_major) SSVB_G(128, false, true, EPI_STORE_F32, false);
+    if (A.mn_major && B.mn_major) SSVB_G(128, true, true, EPI_STORE_F32, false);
   }
 #undef SSVB_G
   return SSVB_ERR_UNSUPPORTED;
+}
+
+// whether launch_gemm(..., split_k = true) will use the add epilogue for this problem (the caller then zeroes the output)
+inline bool gemm_will_split(int64_t M, int64_t N, int64_t K, int bn, const float* out, int64_t ldc) {
+  if (!gemm_tma_store_allowed() || (reinterpret_cast<uintptr_t>(out) & 15) || (ldc % 4)) return false;
+  GemmParams p{};
+  p.K = static_cast<int>(K);
+  gemm_plan_splits(p, ceil_div(M, 128) * ceil_div(N, bn), true);
+  return p.splits > 1;
 }
 
 // fp32 [rows x d] (ld) -> bf16 [rows x dpad] zero padded; optional per-row scale.  One warp per row.

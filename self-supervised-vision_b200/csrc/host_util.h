@@ -88,6 +88,32 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64
   return r == CUDA_SUCCESS ? SSVB_OK : SSVB_ERR_DRIVER;
 }
 
+// OUTPUT map of the GEMM epilogue's TMA stores: row-major [rows x cols] of 4-byte (fp32) or 2-byte (bf16) elements,
+// box = 128 bytes of one row x 32 rows, SWIZZLE_128B (the staging layout of gemm_kernels.cuh); stores beyond
+// rows / cols are clipped by the TMA unit.
+inline int make_tmap_out(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int elem_bytes) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return SSVB_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * elem_bytes) & 15)) return SSVB_ERR_ALIGNMENT;
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS && getenv("SSVB_DEBUG"))
+    fprintf(stderr, "[ssv_b200] cuTensorMapEncodeTiled(out) -> %d (ptr=%p rows=%lld cols=%lld ld=%lld eb=%d)\n",
+            static_cast<int>(r), ptr, static_cast<long long>(rows), static_cast<long long>(cols),
+            static_cast<long long>(ld), elem_bytes);
+  return r == CUDA_SUCCESS ? SSVB_OK : SSVB_ERR_DRIVER;
+}
+
 inline int check_device_sm100() {
   static int cached = -1;  // per-process; all devices of one box are identical
   if (cached >= 0) return cached;

@@ -95,6 +95,56 @@ __global__ void queue_to_bf16_kernel(const float* __restrict__ q, int64_t k, int
   }
 }
 
+// the first kPartBatch lane-strided partials of row r (partial i lives at part[i * stride + r]) in registers: all loads
+// in flight at once.  nparts <= 32 * kPartBatch covers every plan (<= 4 x 74 chunks); callers loop over the rest.
+constexpr int kPartBatch = 12;
+__device__ __forceinline__ void load_row_partials(const float* __restrict__ part, int nparts, int stride, int r, int lane,
+                                                  float fill, float (&v)[kPartBatch]) {
+#pragma unroll
+  for (int u = 0; u < kPartBatch; ++u) {
+    const int i = lane + 32 * u;
+    v[u] = i < nparts ? part[static_cast<size_t>(i) * stride + r] : fill;
+  }
+}
+
+// PIRL: BOTH InfoNCE heads from one read of the shared negatives' (max, sum) partials - head 0 = patch, head 1 = image
+// (utils/losses.py:109-117) - and the combined loss w CE_0 + (1 - w) CE_1 in one deterministic reduction.
+__global__ void pirl_finalize_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l, int nparts,
+                                     int stride, int nrows, const float* __restrict__ pos0,
+                                     const float* __restrict__ pos1, float c, float* __restrict__ lse0,
+                                     float* __restrict__ lse1, float w0, float w1, float* block_sums,
+                                     unsigned int* counter, float loss_scale, float* loss) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  float term = 0.f;
+  if (r < nrows) {
+    float mv[kPartBatch], lv[kPartBatch];
+    load_row_partials(part_m, nparts, stride, r, lane, -1e30f, mv);
+    load_row_partials(part_l, nparts, stride, r, lane, 0.f, lv);
+    const float p0 = pos0[r] * c, p1 = pos1[r] * c;
+    float Mn = -1e30f;  // max over the negatives' partials
+#pragma unroll
+    for (int u = 0; u < kPartBatch; ++u) Mn = fmaxf(Mn, mv[u]);
+    for (int i = lane + 32 * kPartBatch; i < nparts; i += 32) Mn = fmaxf(Mn, part_m[static_cast<size_t>(i) * stride + r]);
+    Mn = warp_max(Mn);
+    float Ln = 0.f;     // sum over the negatives relative to Mn
+#pragma unroll
+    for (int u = 0; u < kPartBatch; ++u) Ln += lv[u] * exp2f(mv[u] - Mn);
+    for (int i = lane + 32 * kPartBatch; i < nparts; i += 32)
+      Ln += part_l[static_cast<size_t>(i) * stride + r] * exp2f(part_m[static_cast<size_t>(i) * stride + r] - Mn);
+    Ln = warp_sum(Ln);
+    if (lane == 0) {
+      const float M0 = fmaxf(Mn, p0), M1 = fmaxf(Mn, p1);
+      const float l0 = M0 + log2f(Ln * exp2f(Mn - M0) + exp2f(p0 - M0));
+      const float l1 = M1 + log2f(Ln * exp2f(Mn - M1) + exp2f(p1 - M1));
+      lse0[r] = l0;
+      lse1[r] = l1;
+      term = (w0 * (l0 - p0) + w1 * (l1 - p1)) * SSVB_LN2;
+    }
+  }
+  const float bt = block_sum_256(term);
+  grid_sum_finish(bt, block_sums, counter, loss_scale, loss, false);
+}
+
 // fused path: combine the per-chunk row sums (fixed order), add the positive logit's term, emit lse2 / the loss term and
 // turn the accumulated sum_j exp2(l_aj - shift) m_j into sum_j p_aj m_j.  One warp per query row.
 __global__ void moco_fused_finalize_kernel(const float* __restrict__ part_l, int nparts, int stride, int nrows, int dpad,
@@ -105,15 +155,24 @@ __global__ void moco_fused_finalize_kernel(const float* __restrict__ part_l, int
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   float term = 0.f;
   if (r < nrows) {
+    // every load of this row is issued before the first use (one memory round trip instead of ~10 dependent ones: the
+    // partials of a row are `stride` floats apart); summation order unchanged (lane-strided, then the shuffle tree)
+    float pv[kPartBatch];
+    load_row_partials(part_l, nparts, stride, r, lane, 0.f, pv);
+    const float4 acc0 = lane * 4 < dpad ? *reinterpret_cast<const float4*>(dacc + static_cast<size_t>(r) * dpad + lane * 4)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float pos_r = pos[r];
     float L = 0.f;
-    for (int i = lane; i < nparts; i += 32) L += part_l[static_cast<size_t>(i) * stride + r];
+#pragma unroll
+    for (int u = 0; u < kPartBatch; ++u) L += pv[u];
+    for (int i = lane + 32 * kPartBatch; i < nparts; i += 32) L += part_l[static_cast<size_t>(i) * stride + r];
     L = warp_sum(L);
-    const float p2 = pos[r] * c;
+    const float p2 = pos_r * c;
     L += exp2f(p2 - shift);  // label-0 column of the reference's cat (utils/losses.py:70)
     const float lse2 = shift + log2f(L);
     const float inv = 1.f / L;
     for (int k = lane * 4; k < dpad; k += 128) {
-      float4 v = *reinterpret_cast<const float4*>(dacc + static_cast<size_t>(r) * dpad + k);
+      float4 v = k < 128 ? acc0 : *reinterpret_cast<const float4*>(dacc + static_cast<size_t>(r) * dpad + k);
       v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
       *reinterpret_cast<float4*>(pm + static_cast<size_t>(r) * dpad + k) = v;
     }
@@ -331,10 +390,13 @@ int ssvb_moco_fwd(const float* query, const float* keys, const float* queue, con
   const float c = SSVB_LOG2E / temperature;
 
   if (npad > n) SSVB_CUDA(cudaMemsetAsync(sv.qhat + n * dpad, 0, (npad - n) * dpad * sizeof(__nv_bfloat16), s));
-  SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
-  pair_prep_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(
+  // the prep kernel also zeroes the last-block counter and (fused path) the P*M accumulator the column chunks add
+  // into: no memset nodes in front of / between the kernels
+  const bool fused_path = moco_fused(normalize, queue_unit_norm, temperature);
+  pair_prep_kernel<<<static_cast<unsigned>(ceil_div(fused_path ? npad : n, 8)), 256, 0, s>>>(
       query, keys, static_cast<int>(n), static_cast<int>(d), ld_q, ld_k, normalize, 0, sv.qhat, nullptr,
-      static_cast<int>(dpad), sv.inv_q, sv.inv_k, sv.pos, nullptr);
+      static_cast<int>(dpad), sv.inv_q, sv.inv_k, sv.pos, nullptr, -1, 1.f, ws.counter,
+      fused_path ? ws.dacc : nullptr, static_cast<int>(dpad), static_cast<int>(npad));
   SSVB_LAUNCH_CHECK();
   const __nv_bfloat16* qb = nullptr;
   SSVB_TRY(get_queue_bf16(queue, queue_bf16, k, d, ld_queue, dpad, ws, s, &qb));
@@ -351,8 +413,7 @@ int ssvb_moco_fwd(const float* query, const float* keys, const float* queue, con
     p.part_stride = static_cast<int>(npad);
     p.dacc = ws.dacc;
     p.ld_dacc = static_cast<int>(dpad);
-    p.use_atomic = p.nchunks > 1;
-    if (p.use_atomic) SSVB_CUDA(cudaMemsetAsync(ws.dacc, 0, npad * dpad * sizeof(float), s));
+    p.use_atomic = p.nchunks > 1;  // (ws.dacc was zeroed by the prep kernel)
     SSVB_TRY(launch_sim_bwd(SIM_MOCO, sv.qhat, npad, qb, k, dpad, p, s));
     moco_fused_finalize_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(
         ws.part_l, 4 * p.nchunks, p.part_stride, static_cast<int>(n), static_cast<int>(dpad), sv.pos, c, c, ws.dacc,
@@ -562,7 +623,7 @@ size_t ssvb_pirl_workspace_bytes(int64_t n, int64_t k, int64_t d) { return ssvb_
 
 int ssvb_pirl_fwd(const float* img, const float* patch, const float* mem_pos, const float* mem_neg, int64_t n, int64_t k,
                   int64_t d, int64_t ld_img, int64_t ld_patch, int64_t ld_pos, int64_t ld_neg, int normalize,
-                  float temperature, float loss_weight, float* loss2, void* saved, void* workspace,
+                  float temperature, float loss_weight, float* loss, void* saved, void* workspace,
                   size_t workspace_bytes, void* stream) {
   SSVB_TRY(check_device_sm100());
   SSVB_TRY(check_shape(n, k, d, temperature));
@@ -570,7 +631,7 @@ int ssvb_pirl_fwd(const float* img, const float* patch, const float* mem_pos, co
   SSVB_TRY(check_rows(patch, ld_patch));
   SSVB_TRY(check_rows(mem_pos, ld_pos));
   SSVB_TRY(check_rows(mem_neg, ld_neg));
-  if (!loss2 || !saved || !workspace) return SSVB_ERR_INVALID;
+  if (!loss || !saved || !workspace) return SSVB_ERR_INVALID;
   if (workspace_bytes < ssvb_pirl_workspace_bytes(n, k, d)) return SSVB_ERR_WORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t dpad = sim_dpad(d), npad = round_up(n, 128);
@@ -583,28 +644,24 @@ int ssvb_pirl_fwd(const float* img, const float* patch, const float* mem_pos, co
   // "query" = memory_pos rows AS STORED (never normalised, :107-109); "keys" = patch / img rows (normalised if asked)
   const int mask = normalize ? 2 : 0;
   pair_prep_kernel<<<pgrid, 256, 0, s>>>(mem_pos, patch, ni, di, ld_pos, ld_patch, 0, 0, sv.qhat, nullptr, dp, sv.unused,
-                                         sv.inv_patch, sv.pos_patch, nullptr, mask);
+                                         sv.inv_patch, sv.pos_patch, nullptr, mask, 1.f, ws.counter);
   SSVB_LAUNCH_CHECK();
   pair_prep_kernel<<<pgrid, 256, 0, s>>>(mem_pos, img, ni, di, ld_pos, ld_img, 0, 0, nullptr, nullptr, dp, sv.unused,
                                          sv.inv_img, sv.pos_img, nullptr, mask);
   SSVB_LAUNCH_CHECK();
   const __nv_bfloat16* qb = nullptr;
   SSVB_TRY(get_queue_bf16(mem_neg, nullptr, k, d, ld_neg, dpad, ws, s, &qb));
-  // the negatives' logits are shared by both heads (:109): one pass of the tensor-core kernel, two LSE finalizes
+  // the negatives' logits are shared by both heads (:109): one pass of the tensor-core kernel, one finalize for both
   SimParams p;
   moco_plan(p, n, k, c, kFwdBN, 512 / kFwdBN);
   p.part_m = ws.part_m;
   p.part_l = ws.part_l;
   p.part_stride = static_cast<int>(npad);
   SSVB_TRY(launch_sim_fwd(SIM_MOCO, sv.qhat, npad, qb, k, dpad, p, s));
-  for (int h = 0; h < 2; ++h) {
-    SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
-    lse_finalize_wide_kernel<SIM_MOCO><<<pgrid, 256, 0, s>>>(
-        ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride, ni, h ? sv.pos_img : sv.pos_patch, c,
-        h ? sv.lse_img : sv.lse_patch, ws.block_sums, ws.counter,
-        (h ? 1.f - loss_weight : loss_weight) / static_cast<float>(n), loss2 + h);
-    SSVB_LAUNCH_CHECK();
-  }
+  pirl_finalize_kernel<<<pgrid, 256, 0, s>>>(ws.part_m, ws.part_l, 4 * p.nchunks, p.part_stride, ni, sv.pos_patch,
+                                             sv.pos_img, c, sv.lse_patch, sv.lse_img, loss_weight, 1.f - loss_weight,
+                                             ws.block_sums, ws.counter, 1.f / static_cast<float>(n), loss);
+  SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
 

@@ -84,67 +84,68 @@ __device__ __forceinline__ float block_reduce_f(float v, bool is_max, float* red
 }
 
 // Every row (K floats) is loaded ONCE into registers (EPT values per thread, coalesced: column = tid + e * 256) and the
-// max / sum / dot / gradient passes run on the registers; one block reduction per statistic.
+// max / sum / dot / gradient passes run on the registers; one block reduction per statistic.  The 2 + nv rows of a
+// sample form one sequence and the loads of row r + 1 are issued BEFORE the reductions of row r (register double
+// buffer), so every CTA keeps a row of HBM traffic in flight through its barrier / exp phases.
 template <bool BWD, int EPT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (EPT <= 16 ? 3 : 1))
 dino_kernel(const float* __restrict__ teacher, int64_t ld_tb, int64_t ld_tv, const float* __restrict__ student,
             int64_t ld_sb, int64_t ld_sv, int nv, int k, const float* __restrict__ center, float inv_ts, float inv_tt,
             float* __restrict__ loss_part /* [bs] */, const float* __restrict__ grad_out, float coef,
             float* __restrict__ dstudent, int64_t ld_db, int64_t ld_dv) {
   __shared__ float red[32];
   const int64_t b = blockIdx.x;
-  float tsum[EPT];
+  const int nrows = 2 + nv;
+  auto row_ptr = [&](int r) -> const float* {
+    return r < 2 ? teacher + b * ld_tb + r * ld_tv : student + b * ld_sb + static_cast<int64_t>(r - 2) * ld_sv;
+  };
+  float tsum[EPT], nxt[EPT];
 #pragma unroll
-  for (int e = 0; e < EPT; ++e) tsum[e] = 0.f;
-  for (int g = 0; g < 2; ++g) {
-    const float* t = teacher + b * ld_tb + g * ld_tv;
-    float x[EPT];
-    float m = -INFINITY;
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      const int c = threadIdx.x + e * 256;
-      x[e] = c < k ? (t[c] - __ldg(center + c)) * inv_tt : -INFINITY;
-      m = fmaxf(m, x[e]);
-    }
-    m = block_reduce_f(m, true, red);
-    float z = 0.f;
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      x[e] = __expf(x[e] - m);  // exp(-inf) = 0 for the padding
-      z += x[e];
-    }
-    z = block_reduce_f(z, false, red);
-    const float iz = 1.f / z;
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) tsum[e] = fmaf(x[e], iz, tsum[e]);
+  for (int e = 0; e < EPT; ++e) {
+    const int c = threadIdx.x + e * 256;
+    tsum[e] = 0.f;
+    nxt[e] = c < k ? row_ptr(0)[c] : 0.f;
   }
   float acc = 0.f;
   const float go = BWD ? __ldg(grad_out) * coef : 0.f;
-  for (int v = 0; v < nv; ++v) {
-    const float* s = student + b * ld_sb + v * ld_sv;
+  for (int r = 0; r < nrows; ++r) {
     float x[EPT];
+    const bool is_teacher = r < 2;
     float m = -INFINITY;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       const int c = threadIdx.x + e * 256;
-      x[e] = c < k ? s[c] * inv_ts : -INFINITY;
+      const float raw = nxt[e];
+      x[e] = c < k ? (is_teacher ? (raw - __ldg(center + c)) * inv_tt : raw * inv_ts) : -INFINITY;
       m = fmaxf(m, x[e]);
+    }
+    if (r + 1 < nrows) {  // block-uniform: next row's loads go out before this row's reductions
+      const float* np = row_ptr(r + 1);
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int c = threadIdx.x + e * 256;
+        nxt[e] = c < k ? np[c] : 0.f;
+      }
     }
     m = block_reduce_f(m, true, red);
     float z = 0.f, dot = 0.f;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-      if (!BWD && threadIdx.x + e * 256 < k) dot = fmaf(tsum[e], x[e], dot);
-      x[e] = __expf(x[e] - m);
+      if (!BWD && !is_teacher && threadIdx.x + e * 256 < k) dot = fmaf(tsum[e], x[e], dot);
+      x[e] = __expf(x[e] - m);  // exp(-inf) = 0 for the padding
       z += x[e];
     }
     z = block_reduce_f(z, false, red);
-    if (!BWD) {
+    if (is_teacher) {
+      const float iz = 1.f / z;
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) tsum[e] = fmaf(x[e], iz, tsum[e]);
+    } else if (!BWD) {
       dot = block_reduce_f(dot, false, red);
       acc += dot - 2.f * (m + __logf(z));  // sum_k Tsum (x - lse) with sum_k Tsum = 2
     } else {
       const float iz = 2.f / z;
-      float* d = dstudent + b * ld_db + v * ld_dv;
+      float* d = dstudent + b * ld_db + static_cast<int64_t>(r - 2) * ld_dv;
 #pragma unroll
       for (int e = 0; e < EPT; ++e) {
         const int c = threadIdx.x + e * 256;

@@ -206,13 +206,12 @@ int ssvb_ntxent_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   // zero the padding rows of the bf16 staging matrix and the reduction counter
   if (pl.mpad > pl.m)
     SSVB_CUDA(cudaMemsetAsync(sv.zhat + pl.m * pl.dpad, 0, (pl.mpad - pl.m) * pl.dpad * sizeof(__nv_bfloat16), s));
-  SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
   {
-    const int wpb = 8;
+    const int wpb = 8;  // (the prep kernel also zeroes the finalize kernel's last-block counter: no memset node)
     pair_prep_kernel<<<static_cast<unsigned>(ceil_div(n, wpb)), wpb * 32, 0, s>>>(
         zi, zj, static_cast<int>(n), static_cast<int>(d), ld_zi, ld_zj, normalize, normalize ? 1 : 0, sv.zhat,
         sv.zhat + n * pl.dpad,
-        static_cast<int>(pl.dpad), sv.inv_norm, sv.inv_norm + n, ws.pos, ws.pos + n, -1, pl.prescale);
+        static_cast<int>(pl.dpad), sv.inv_norm, sv.inv_norm + n, ws.pos, ws.pos + n, -1, pl.prescale, ws.counter);
     SSVB_LAUNCH_CHECK();
   }
   SimParams p;

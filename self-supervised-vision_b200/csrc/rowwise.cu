@@ -7,6 +7,23 @@ using namespace ssvb;
 
 namespace {
 
+// fixed-order sum of the per-block partials by one block -> out = scale * sum.  The single-kernel losses use this
+// second tiny launch instead of a last-block counter: a counter needs a memset node in front of the kernel, and a
+// memset -> kernel edge costs 2-4 us in a CUDA graph where a kernel -> kernel edge costs ~0.3 us.
+__global__ void block_sums_finish_kernel(const float* __restrict__ part, int n, float scale, float* __restrict__ out) {
+  __shared__ float red[8];
+  float v = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) v += part[i];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) out[0] = t * scale;
+  }
+}
+
 int check_rows(const void* p, int64_t ld) {
   if (!p) return SSVB_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(p) & 15) || (ld & 3)) return SSVB_ERR_ALIGNMENT;
@@ -438,7 +455,8 @@ struct RelicVec {
     return a[r * 2 * n_local + n_local + (i - r * n_local)];
   }
 };
-__global__ void relic_softmax_kernel(int64_t n, RelicVec v, RelicSaved sv, float alpha, float* __restrict__ kl_out) {
+__global__ void relic_softmax_kernel(int64_t n, RelicVec v, RelicSaved sv, float alpha, float* kl_out,
+                                     const float* add_in = nullptr /* may alias kl_out: *kl_out = *add_in + alpha KL */) {
   float ma = -INFINITY, mb = -INFINITY;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
     ma = fmaxf(ma, v.A(i));
@@ -466,7 +484,7 @@ __global__ void relic_softmax_kernel(int64_t n, RelicVec v, RelicSaved sv, float
   spq = block_reduce_1024(spq, false);
   if (threadIdx.x == 0) {
     sv.scal[0] = lse_a; sv.scal[1] = lse_b; sv.scal[2] = spq; sv.scal[3] = kl;
-    *kl_out = alpha * kl;
+    *kl_out = (add_in ? *add_in : 0.f) + alpha * kl;
   }
 }
 
@@ -557,7 +575,6 @@ int ssvb_rowdot_fwd(int kind, const float* o, const float* t, int64_t n, int64_t
   if (workspace_bytes < rowdot_ws(nullptr).bytes) return SSVB_ERR_WORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   RowdotWs ws = rowdot_ws(workspace);
-  SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
   const int64_t total = n * (d / 4);
   int64_t grid = ceil_div(total, 256 * 4);
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
@@ -567,10 +584,12 @@ int ssvb_rowdot_fwd(int kind, const float* o, const float* t, int64_t n, int64_t
   const int d4 = static_cast<int>(d / 4);
   const float sc = kind == 0 ? 1.f / (static_cast<float>(n) * d) : -1.f / static_cast<float>(n);
   const unsigned g = static_cast<unsigned>(grid);
-#define SSVB_RD(K, F) rowdot_fwd_kernel<K, F><<<g, 256, 0, s>>>(o, t, n, d4, ld_o, ld_t, ws.block_sums, ws.counter, sc, loss)
+#define SSVB_RD(K, F) rowdot_fwd_kernel<K, F><<<g, 256, 0, s>>>(o, t, n, d4, ld_o, ld_t, ws.block_sums, nullptr, sc, loss)
   if (kind == 0) { if (flat) SSVB_RD(0, true); else SSVB_RD(0, false); }
   else           { if (flat) SSVB_RD(1, true); else SSVB_RD(1, false); }
 #undef SSVB_RD
+  SSVB_LAUNCH_CHECK();
+  block_sums_finish_kernel<<<1, 256, 0, s>>>(ws.block_sums, static_cast<int>(grid), sc, loss);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
@@ -589,19 +608,22 @@ int ssvb_rowdot_norm_fwd(int kind, const float* o, const float* t, int64_t n, in
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   RowdotWs ws = rowdot_ws(workspace);
   RowdotNormSaved sv = rowdot_norm_saved(saved, n);
-  SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
   int64_t grid = ceil_div(n, 8);
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
   if (grid > cap) grid = cap;
   const int d4 = static_cast<int>(d / 4);
   if (kind == 0)
     rowdot_norm_fwd_kernel<0><<<static_cast<unsigned>(grid), 256, 0, s>>>(
-        o, t, n, d4, ld_o, ld_t, normalize_o, normalize_t, sv, ws.block_sums, ws.counter,
+        o, t, n, d4, ld_o, ld_t, normalize_o, normalize_t, sv, ws.block_sums, nullptr,
         1.f / (static_cast<float>(n) * d), loss);
   else
     rowdot_norm_fwd_kernel<1><<<static_cast<unsigned>(grid), 256, 0, s>>>(
-        o, t, n, d4, ld_o, ld_t, normalize_o, normalize_t, sv, ws.block_sums, ws.counter, -1.f / static_cast<float>(n),
+        o, t, n, d4, ld_o, ld_t, normalize_o, normalize_t, sv, ws.block_sums, nullptr, -1.f / static_cast<float>(n),
         loss);
+  SSVB_LAUNCH_CHECK();
+  block_sums_finish_kernel<<<1, 256, 0, s>>>(ws.block_sums, static_cast<int>(grid),
+                                             kind == 0 ? 1.f / (static_cast<float>(n) * d) : -1.f / static_cast<float>(n),
+                                             loss);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
@@ -767,6 +789,26 @@ int ssvb_relic_kl_fwd(const float* zi, const float* zj, const float* zo, int64_t
   return SSVB_OK;
 }
 
+// The whole RelicLoss.forward / backward in ONE call each (utils/losses.py:162-201): NT-Xent on (zi, zj), the KL term on
+// top, `loss` = contrastive + alpha * KL written by the last kernel (no host-side add, one library crossing).
+int ssvb_relic_fwd(const float* zi, const float* zj, const float* zo, int64_t n, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                   int64_t ld_zo, int normalize, float temperature, float alpha, float* loss, void* saved_ntxent,
+                   void* saved_kl, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!saved_kl) return SSVB_ERR_INVALID;
+  SSVB_TRY(check_rows(zo, ld_zo));
+  SSVB_TRY(ssvb_ntxent_fwd(zi, zj, n, d, ld_zi, ld_zj, normalize, temperature, loss, saved_ntxent, workspace,
+                           workspace_bytes, stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  RelicSaved sv = relic_saved(saved_kl, n);
+  relic_dots_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(zi, zj, zo, n, static_cast<int>(d), ld_zi,
+                                                                          ld_zj, ld_zo, normalize, 1.f / temperature,
+                                                                          sv);
+  SSVB_LAUNCH_CHECK();
+  relic_softmax_kernel<<<1, 1024, 0, s>>>(n, RelicVec{sv.a, sv.b, 0}, sv, alpha, loss, loss);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
 // ---- multi-GPU ReLIC-KL: the KL's two softmaxes run over the BATCH axis (utils/losses.py:196-200), so the
 // per-row logits a_n, b_n of all ranks are all-gathered (2 * n_local floats per rank) between two stages:
 //   dist_dots   : this rank's a, b (+ inverse norms) into `saved`, and into ab_local [2][n_local] for the all-gather
@@ -854,6 +896,16 @@ int ssvb_bank_gather(const float* bank, int64_t size, int64_t d, int64_t ld_bank
       bank, size, static_cast<int>(d), ld_bank, reinterpret_cast<const long long*>(indices), n, out, ld_out);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
+}
+
+int ssvb_relic_bwd(const float* zi, const float* zj, const float* zo, int64_t n, int64_t d, int64_t ld_zi, int64_t ld_zj,
+                   int64_t ld_zo, int normalize, float temperature, float alpha, const float* grad_out,
+                   const void* saved_ntxent, const void* saved_kl, float* dzi, float* dzj, float* dzo, int64_t ld_dzi,
+                   int64_t ld_dzj, int64_t ld_dzo, void* workspace, size_t workspace_bytes, void* stream) {
+  SSVB_TRY(ssvb_ntxent_bwd(zi, zj, n, d, ld_zi, ld_zj, normalize, temperature, grad_out, saved_ntxent, dzi, dzj, ld_dzi,
+                           ld_dzj, workspace, workspace_bytes, stream));
+  return ssvb_relic_kl_bwd(zi, zj, zo, n, d, ld_zi, ld_zj, ld_zo, normalize, temperature, alpha, grad_out, saved_kl, dzi,
+                           dzj, dzo, ld_dzi, ld_dzj, ld_dzo, stream);
 }
 
 }  // extern "C"

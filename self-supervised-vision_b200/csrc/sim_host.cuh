@@ -122,8 +122,18 @@ static __global__ void pair_prep_kernel(const float* __restrict__ xi, const floa
                                  float* __restrict__ inv_j, float* __restrict__ pos_i, float* __restrict__ pos_j,
                                  int norm_mask = -1 /* >= 0: bit 0 normalises xi, bit 1 xj (overrides `normalize`) */,
                                  float prescale = 1.f /* staged rows = x_hat * prescale (NT-Xent FIXED mode:
-                                 sqrt(log2(e)/tau), so the tensor-core accumulator is the log2-domain logit) */) {
+                                 sqrt(log2(e)/tau), so the tensor-core accumulator is the log2-domain logit) */,
+                                 unsigned int* zero_counter = nullptr /* 4 counters of the later last-block reductions:
+                                 zeroed HERE (first kernel of the call) instead of by a memset node, which costs a
+                                 2-4 us dependency gap in front of the first kernel of a CUDA graph */,
+                                 float* zero_rows = nullptr, int zero_ld = 0, int zero_nrows = 0 /* fp32 accumulator
+                                 rows [zero_nrows x zero_ld] that a later kernel adds into (red.global.add): warp w
+                                 zeroes row w; the grid must cover max(n, zero_nrows) warps */) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (zero_counter && blockIdx.x == 0 && threadIdx.x < 4) zero_counter[threadIdx.x] = 0u;
+  if (zero_rows && warp < zero_nrows)
+    for (int k = lane * 4; k < zero_ld; k += 128)
+      *reinterpret_cast<float4*>(zero_rows + static_cast<int64_t>(warp) * zero_ld + k) = make_float4(0.f, 0.f, 0.f, 0.f);
   if (warp >= n) return;
   const float* ri = xi + static_cast<int64_t>(warp) * ldi;
   const float* rj = xj + static_cast<int64_t>(warp) * ldj;
@@ -196,6 +206,10 @@ __device__ __forceinline__ float block_sum_256(float v) {
 __device__ __forceinline__ bool grid_sum_finish(float block_total, float* block_sums, unsigned int* counter,
                                                 float scale, float* out, bool accumulate) {
   __shared__ bool is_last;
+  if (counter == nullptr) {  // two-kernel form: the caller launches a one-block sum over block_sums afterwards
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = block_total;
+    return false;
+  }
   if (threadIdx.x == 0) {
     block_sums[blockIdx.x] = block_total;
     __threadfence();

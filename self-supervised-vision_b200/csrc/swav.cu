@@ -391,7 +391,10 @@ int ssvb_swav_bwd(const float* z1, const float* z2, const float* bank, const flo
     p.alpha = 1.f;
     p.out = ws.dz;
     p.ldc = m.dpad;
-    SSVB_TRY(launch_gemm({sv.ds, m.kp8, false}, {sv.c, m.dpad, true}, p, 128, EPI_STORE_F32, 0, s));
+    // 2B'/128 x 1 tiles (55 at the reference shape) for 148 SMs: split K over CTAs, partial products added by TMA
+    const bool split = gemm_will_split(p.M, p.N, p.K, 128, ws.dz, m.dpad);
+    if (split) SSVB_CUDA(cudaMemsetAsync(ws.dz, 0, static_cast<size_t>(p.M) * m.dpad * sizeof(float), s));
+    SSVB_TRY(launch_gemm({sv.ds, m.kp8, false}, {sv.c, m.dpad, true}, p, 128, EPI_STORE_F32, 0, s, split));
     if (dz1) {
       scale_rows_kernel<<<grid_for(nb * d, 256), 256, 0, s>>>(ws.dz, m.dpad, nb, di, grad_out, dz1, ld_dz1);
       SSVB_LAUNCH_CHECK();
@@ -410,7 +413,10 @@ int ssvb_swav_bwd(const float* z1, const float* z2, const float* bank, const flo
     p.alpha = 1.f;
     p.out = ws.dc;
     p.ldc = m.dpad;
-    SSVB_TRY(launch_gemm({sv.ds, m.kp8, true}, {sv.z, m.dpad, true}, p, 128, EPI_STORE_F32, 0, s));
+    // K/128 x 1 tiles (24 at K = 3000): split the contraction over the stacked rows across CTAs
+    const bool split = gemm_will_split(p.M, p.N, p.K, 128, ws.dc, m.dpad);
+    if (split) SSVB_CUDA(cudaMemsetAsync(ws.dc, 0, static_cast<size_t>(p.M) * m.dpad * sizeof(float), s));
+    SSVB_TRY(launch_gemm({sv.ds, m.kp8, true}, {sv.z, m.dpad, true}, p, 128, EPI_STORE_F32, 0, s, split));
     scale_rows_kernel<<<grid_for(k * d, 256), 256, 0, s>>>(ws.dc, m.dpad, k, di, grad_out, dproto, ld_dproto);
     SSVB_LAUNCH_CHECK();
   }

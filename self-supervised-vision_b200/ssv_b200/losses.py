@@ -240,17 +240,14 @@ class _RelicFn(torch.autograd.Function):
             saved_c = C.byte_buffer(C.cached_size("ssvb_ntxent_saved_bytes", n, d), dev)
             ws_bytes = C.cached_size("ssvb_ntxent_workspace_bytes", n, d)
             ws = C.workspace("ntxent", ws_bytes, dev)
-            out = torch.empty(2, dtype=torch.float32, device=dev)
-            C.check(L.ssvb_ntxent_fwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), norm, float(temperature),
-                                      C.ptr(out), C.ptr(saved_c), C.ptr(ws), ws_bytes, st), "ssvb_ntxent_fwd")
+            out = torch.empty((), dtype=torch.float32, device=dev)
             saved_k = C.byte_buffer(C.cached_size("ssvb_relic_kl_saved_bytes", n), dev)
-            kl = out[1:]
-            C.check(L.ssvb_relic_kl_fwd(C.ptr(xi), C.ptr(xj), C.ptr(xo), n, d, _ld(xi), _ld(xj), _ld(xo), norm,
-                                        float(temperature), float(alpha), C.ptr(kl), C.ptr(saved_k), None, 0, st),
-                    "ssvb_relic_kl_fwd")
+            C.check(L.ssvb_relic_fwd(C.ptr(xi), C.ptr(xj), C.ptr(xo), n, d, _ld(xi), _ld(xj), _ld(xo), norm,
+                                     float(temperature), float(alpha), C.ptr(out), C.ptr(saved_c), C.ptr(saved_k),
+                                     C.ptr(ws), ws_bytes, st), "ssvb_relic_fwd")
         ctx.save_for_backward(xi, xj, xo, saved_c, saved_k)
         ctx.cfg = (norm, float(temperature), float(alpha), zi.dtype, zj.dtype, zo.dtype)
-        return out.sum()  # contrastive + alpha * KL  (utils/losses.py:201)
+        return out  # contrastive + alpha * KL  (utils/losses.py:201), combined by the last kernel
 
     @staticmethod
     @once_differentiable
@@ -266,12 +263,9 @@ class _RelicFn(torch.autograd.Function):
             dzi, dzj, dzo = torch.empty_like(xi), torch.empty_like(xj), torch.empty_like(xo)
             ws_bytes = C.cached_size("ssvb_ntxent_workspace_bytes", n, d)
             ws = C.workspace("ntxent", ws_bytes, dev)
-            C.check(L.ssvb_ntxent_bwd(C.ptr(xi), C.ptr(xj), n, d, _ld(xi), _ld(xj), norm, temperature, C.ptr(go),
-                                      C.ptr(saved_c), C.ptr(dzi), C.ptr(dzj), _ld(dzi), _ld(dzj), C.ptr(ws), ws_bytes,
-                                      st), "ssvb_ntxent_bwd")
-            C.check(L.ssvb_relic_kl_bwd(C.ptr(xi), C.ptr(xj), C.ptr(xo), n, d, _ld(xi), _ld(xj), _ld(xo), norm,
-                                        temperature, alpha, C.ptr(go), C.ptr(saved_k), C.ptr(dzi), C.ptr(dzj),
-                                        C.ptr(dzo), _ld(dzi), _ld(dzj), _ld(dzo), st), "ssvb_relic_kl_bwd")
+            C.check(L.ssvb_relic_bwd(C.ptr(xi), C.ptr(xj), C.ptr(xo), n, d, _ld(xi), _ld(xj), _ld(xo), norm, temperature,
+                                     alpha, C.ptr(go), C.ptr(saved_c), C.ptr(saved_k), C.ptr(dzi), C.ptr(dzj), C.ptr(dzo),
+                                     _ld(dzi), _ld(dzj), _ld(dzo), C.ptr(ws), ws_bytes, st), "ssvb_relic_bwd")
         return dzi.to(dti), dzj.to(dtj), dzo.to(dto), None, None, None
 
 
@@ -510,13 +504,13 @@ class _PirlFn(torch.autograd.Function):
             saved = C.byte_buffer(C.cached_size("ssvb_pirl_saved_bytes", n, d), dev)
             ws_bytes = C.cached_size("ssvb_pirl_workspace_bytes", n, k, d)
             ws = C.workspace("moco", ws_bytes, dev)
-            out = torch.empty(2, dtype=torch.float32, device=dev)
+            out = torch.empty((), dtype=torch.float32, device=dev)
             C.check(L.ssvb_pirl_fwd(C.ptr(xi), C.ptr(xp), C.ptr(mp), C.ptr(mn), n, k, d, _ld(xi), _ld(xp), _ld(mp), _ld(mn),
                                     norm, float(temperature), float(loss_weight), C.ptr(out), C.ptr(saved), C.ptr(ws),
                                     ws_bytes, C.stream_ptr(dev)), "ssvb_pirl_fwd")
         ctx.save_for_backward(xi, xp, mp, saved)
         ctx.cfg = (norm, float(temperature), float(loss_weight), img.dtype, patch.dtype)
-        return out.sum()  # loss_weight * loss_1 + (1 - loss_weight) * loss_2  (utils/losses.py:117)
+        return out  # loss_weight * loss_1 + (1 - loss_weight) * loss_2  (utils/losses.py:117), summed in the kernel
 
     @staticmethod
     @once_differentiable
