@@ -244,6 +244,32 @@ __global__ void col_finalize_kernel(const float* __restrict__ part, int nsplit, 
   }
 }
 
+// MODE 1 finalize for MANY stripes (the GEMM epilogue's partials: one stripe per 32 rows): block (32 columns x 8 stripe
+// phases), fixed-order combine.  out0 = mean_0(dT), out1 = sum_0(dT x~) / (n - 1).
+__global__ void col_finalize_wide_kernel(const float* __restrict__ part, int nsplit, int64_t n, int d,
+                                         float* __restrict__ out0, float* __restrict__ out1) {
+  __shared__ float sh1[8][33], sh2[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float s1 = 0.f, s2 = 0.f;
+  if (col < d) {
+    for (int i = threadIdx.y; i < nsplit; i += 8) {
+      s1 += part[(static_cast<int64_t>(i) * 2 + 0) * d + col];
+      s2 += part[(static_cast<int64_t>(i) * 2 + 1) * d + col];
+    }
+  }
+  sh1[threadIdx.y][threadIdx.x] = s1;
+  sh2[threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < d) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += sh1[i][threadIdx.x]; b += sh2[i][threadIdx.x]; }
+    const float fn = static_cast<float>(n);
+    out0[col] = a / fn;
+    out1[col] = b / (fn - 1.f);
+  }
+}
+
 // x~ = (x * inv_row - mean) * rstd  -> bf16 [n x d]
 __global__ void standardize_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row,
                                    const float* __restrict__ mean, const float* __restrict__ rstd, int64_t n, int d4,
@@ -630,10 +656,11 @@ int ssvb_barlow_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
     col_partials_kernel<1><<<grid, block, 0, s>>>(zj, ld_zj, inv_j, ws.dtj, d, sv.mean_j, sv.rstd_j, n, static_cast<int>(d), part_j);
     SSVB_LAUNCH_CHECK();
   }
-  const unsigned fgrid = static_cast<unsigned>(ceil_div(d, 256));
-  col_finalize_kernel<1><<<fgrid, 256, 0, s>>>(part_i, nsplit, nullptr, nullptr, n, static_cast<int>(d), ws.colred, ws.colred + d);
+  const unsigned fgrid = static_cast<unsigned>(ceil_div(d, 32));
+  col_finalize_wide_kernel<<<fgrid, dim3(32, 8), 0, s>>>(part_i, nsplit, n, static_cast<int>(d), ws.colred, ws.colred + d);
   SSVB_LAUNCH_CHECK();
-  col_finalize_kernel<1><<<fgrid, 256, 0, s>>>(part_j, nsplit, nullptr, nullptr, n, static_cast<int>(d), ws.colred + 2 * d, ws.colred + 3 * d);
+  col_finalize_wide_kernel<<<fgrid, dim3(32, 8), 0, s>>>(part_j, nsplit, n, static_cast<int>(d), ws.colred + 2 * d,
+                                                         ws.colred + 3 * d);
   SSVB_LAUNCH_CHECK();
   barlow_finish_kernel<<<static_cast<unsigned>(n), 256, 0, s>>>(zi, ld_zi, inv_i, sv.mean_i, sv.rstd_i, ws.dti, d, ws.colred,
                                                               ws.colred + d, static_cast<int>(d), grad_out, dzi, ld_dzi);

@@ -86,9 +86,11 @@ __device__ __forceinline__ float block_reduce_f(float v, bool is_max, float* red
 // Every row (K floats) is loaded ONCE into registers (EPT values per thread, coalesced: column = tid + e * 256) and the
 // max / sum / dot / gradient passes run on the registers; one block reduction per statistic.  The 2 + nv rows of a
 // sample form one sequence and the loads of row r + 1 are issued BEFORE the reductions of row r (register double
-// buffer), so every CTA keeps a row of HBM traffic in flight through its barrier / exp phases.
+// buffer), so every CTA keeps a row of HBM traffic in flight through its barrier / exp phases.  Tsum lives in shared
+// memory (each thread only ever touches its own columns: no barrier needed), which keeps the kernel at <= 51 registers
+// = 5 CTAs per SM for K <= 4096 (5 x 16 KB of loads in flight per SM).
 template <bool BWD, int EPT>
-__global__ void __launch_bounds__(256, (EPT <= 16 ? 3 : 1))
+__global__ void __launch_bounds__(256, (EPT <= 16 ? 5 : (EPT <= 32 ? 2 : 1)))
 dino_kernel(const float* __restrict__ teacher, int64_t ld_tb, int64_t ld_tv, const float* __restrict__ student,
             int64_t ld_sb, int64_t ld_sv, int nv, int k, const float* __restrict__ center, float inv_ts, float inv_tt,
             float* __restrict__ loss_part /* [bs] */, const float* __restrict__ grad_out, float coef,
@@ -99,11 +101,11 @@ dino_kernel(const float* __restrict__ teacher, int64_t ld_tb, int64_t ld_tv, con
   auto row_ptr = [&](int r) -> const float* {
     return r < 2 ? teacher + b * ld_tb + r * ld_tv : student + b * ld_sb + static_cast<int64_t>(r - 2) * ld_sv;
   };
-  float tsum[EPT], nxt[EPT];
+  extern __shared__ float tsum[];  // [EPT * 256]: column c = threadIdx.x + e * 256 belongs to this thread
+  float nxt[EPT];
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
     const int c = threadIdx.x + e * 256;
-    tsum[e] = 0.f;
     nxt[e] = c < k ? row_ptr(0)[c] : 0.f;
   }
   float acc = 0.f;
@@ -131,7 +133,7 @@ dino_kernel(const float* __restrict__ teacher, int64_t ld_tb, int64_t ld_tv, con
     float z = 0.f, dot = 0.f;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-      if (!BWD && !is_teacher && threadIdx.x + e * 256 < k) dot = fmaf(tsum[e], x[e], dot);
+      if (!BWD && !is_teacher && threadIdx.x + e * 256 < k) dot = fmaf(tsum[threadIdx.x + e * 256], x[e], dot);
       x[e] = __expf(x[e] - m);  // exp(-inf) = 0 for the padding
       z += x[e];
     }
@@ -139,7 +141,8 @@ dino_kernel(const float* __restrict__ teacher, int64_t ld_tb, int64_t ld_tv, con
     if (is_teacher) {
       const float iz = 1.f / z;
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) tsum[e] = fmaf(x[e], iz, tsum[e]);
+      for (int e = 0; e < EPT; ++e)
+        tsum[threadIdx.x + e * 256] = r == 0 ? x[e] * iz : fmaf(x[e], iz, tsum[threadIdx.x + e * 256]);
     } else if (!BWD) {
       dot = block_reduce_f(dot, false, red);
       acc += dot - 2.f * (m + __logf(z));  // sum_k Tsum (x - lse) with sum_k Tsum = 2
@@ -149,7 +152,7 @@ dino_kernel(const float* __restrict__ teacher, int64_t ld_tb, int64_t ld_tv, con
 #pragma unroll
       for (int e = 0; e < EPT; ++e) {
         const int c = threadIdx.x + e * 256;
-        if (c < k) d[c] = (x[e] * iz - tsum[e]) * go;
+        if (c < k) d[c] = (x[e] * iz - tsum[c]) * go;
       }
     }
   }
@@ -164,7 +167,7 @@ int dino_launch(const float* teacher, const float* student, const float* center,
   const int ki = static_cast<int>(k), nvi = static_cast<int>(nv);
   const float its = 1.f / temp_s, itt = 1.f / temp_t;
 #define SSVB_DINO(E)                                                                                                   \
-  dino_kernel<BWD, E><<<grid, 256, 0, s>>>(teacher, 2 * k, k, student, nv * k, k, nvi, ki, center, its, itt, part, grad_out, \
+  dino_kernel<BWD, E><<<grid, 256, E * 256 * sizeof(float), s>>>(teacher, 2 * k, k, student, nv * k, k, nvi, ki, center, its, itt, part, grad_out, \
                                            coef, dstudent, nv * k, k)
   if (k <= 4 * 256) SSVB_DINO(4);
   else if (k <= 8 * 256) SSVB_DINO(8);
