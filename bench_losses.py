@@ -52,13 +52,33 @@ def unit(x):
     return torch.nn.functional.normalize(x, dim=-1)
 
 
+_FLUSH_READ = {}
+
+
+def l2_flush(flush):
+    """Evict the L2 between timed repetitions: write a 256 MiB buffer (> the 126 MB L2), then READ a second 256 MiB
+    buffer so that the cache is left cold AND clean.  After the write alone every L2 line is dirty, and the first
+    ~126 MB a kernel reads pay for the write-back of the flush buffer on top of their own traffic (measured: the
+    leading read-only kernel of a row ran at 3-3.5 TB/s after a write-only flush) - an artefact of the flush, not of
+    the kernel.  BENCH_FLUSH=write restores the write-only flush."""
+    flush.zero_()
+    if os.environ.get("BENCH_FLUSH", "clean") == "write":
+        return
+    key = flush.device.index
+    buf = _FLUSH_READ.get(key)
+    if buf is None:
+        buf = (torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=flush.device), torch.empty(1, dtype=torch.float32, device=flush.device))
+        _FLUSH_READ[key] = buf
+    torch.sum(buf[0], dim=(0,), keepdim=True, out=buf[1])
+
+
 def time_gpu(fn, reps, flush, warm=5):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
-        flush.zero_()
+        l2_flush(flush)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
@@ -86,7 +106,7 @@ def time_graph(fn, reps, flush):
         torch.cuda.synchronize()
         ts = []
         for _ in range(reps):
-            flush.zero_()
+            l2_flush(flush)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             g.replay()
@@ -122,13 +142,16 @@ def graph_timeline(fn, flush, title, out):
         torch.cuda.synchronize()
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             for _ in range(3):
-                flush.zero_()
+                l2_flush(flush)
                 g.replay()
                 torch.cuda.synchronize()
         evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
         evs.sort(key=lambda e: e.time_range.start)
-        # the last replay = everything after the last flush fill (a 256 MiB FillFunctor<unsigned char> launch)
+        # the last replay = everything after the last flush (256 MiB FillFunctor<unsigned char> launch [+ the read-back
+        # reduce_kernel of l2_flush])
         cut = max(i for i, e in enumerate(evs) if "FillFunctor<unsigned char>" in e.name)
+        while cut + 1 < len(evs) and "reduce_kernel" in evs[cut + 1].name and evs[cut + 1].time_range.end - evs[cut + 1].time_range.start > 20:
+            cut += 1
         step = evs[cut + 1:]
         if not step:
             return

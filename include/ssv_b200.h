@@ -459,11 +459,12 @@ int ssvb_sela_self_label(const float* logits, int64_t b, int64_t k, int64_t ld, 
  *     gradient to the student only (the teacher runs under no_grad, models/dino.py:151-152).
  *     ssvb_dino_center_update: models/dino.py:136-141 (first != 0: center = mean of the rows).
  * ------------------------------------------------------------------------------------- */
-size_t ssvb_dino_workspace_bytes(int64_t bs);
+size_t ssvb_dino_workspace_bytes(int64_t bs, int64_t nv, int64_t k);
 int ssvb_dino_fwd(const float* teacher, const float* student, const float* center, int64_t bs, int64_t nv, int64_t k,
                   float temp_s, float temp_t, float* loss, void* workspace, size_t workspace_bytes, void* stream);
 int ssvb_dino_bwd(const float* teacher, const float* student, const float* center, int64_t bs, int64_t nv, int64_t k,
-                  float temp_s, float temp_t, const float* grad_out, float* dstudent, void* stream);
+                  float temp_s, float temp_t, const float* grad_out, float* dstudent, void* workspace,
+                  size_t workspace_bytes, void* stream);
 int ssvb_dino_center_update(const float* teacher_rows, int64_t rows, int64_t k, int64_t ld, float momentum,
                             float one_minus_m, int first, float* center, void* stream);
 

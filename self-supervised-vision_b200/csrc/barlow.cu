@@ -169,7 +169,7 @@ __global__ void col_partials_kernel(const float* __restrict__ x, int64_t ldx, co
   }
 }
 
-// Forward statistics, float4 version of MODE 0: block (32, 8) covers 128 columns (one float4 per thread and row), four
+// Forward statistics, float4 version of MODE 0: block (32, 8) covers 128 columns (one float4 per thread and row), eight
 // rows in flight per thread; same shifted sums and the same partial layout [stripe][2][d].
 __global__ void __launch_bounds__(256)
 col_stats4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row, int64_t n, int d,
@@ -190,16 +190,16 @@ col_stats4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
       s2.x = fmaf(tx, tx, s2.x); s2.y = fmaf(ty, ty, s2.y); s2.z = fmaf(tz, tz, s2.z); s2.w = fmaf(tw, tw, s2.w);
     };
     int64_t r = r0 + threadIdx.y;
-    for (; r + 24 < r1; r += 32) {
-      float4 v[4];
-      float sc[4];
+    for (; r + 56 < r1; r += 64) {  // eight rows (128 bytes per thread) in flight
+      float4 v[8];
+      float sc[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         v[u] = __ldg(reinterpret_cast<const float4*>(x + (r + 8 * u) * ldx) + c4);
         sc[u] = inv_row ? inv_row[r + 8 * u] : 1.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc(v[u], sc[u]);
+      for (int u = 0; u < 8; ++u) acc(v[u], sc[u]);
     }
     for (; r < r1; r += 8) acc(__ldg(reinterpret_cast<const float4*>(x + r * ldx) + c4), inv_row ? inv_row[r] : 1.f);
   }

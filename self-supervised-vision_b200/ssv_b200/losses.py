@@ -435,7 +435,7 @@ class _DinoFn(torch.autograd.Function):
         L = C.lib()
         dev = s.device
         with C.on_device(dev):
-            ws_bytes = C.cached_size("ssvb_dino_workspace_bytes", bs)
+            ws_bytes = C.cached_size("ssvb_dino_workspace_bytes", bs, nv, k)
             ws = C.workspace("dino", ws_bytes, dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             C.check(L.ssvb_dino_fwd(C.ptr(t), C.ptr(s), C.ptr(c), bs, nv, k, float(temp_s), float(temp_t), C.ptr(loss),
@@ -454,8 +454,10 @@ class _DinoFn(torch.autograd.Function):
         with C.on_device(dev):
             go = C.f32_scalar(grad_out)
             ds = torch.empty_like(s)
+            ws_bytes = C.cached_size("ssvb_dino_workspace_bytes", bs, nv, k)
+            ws = C.workspace("dino", ws_bytes, dev)
             C.check(C.lib().ssvb_dino_bwd(C.ptr(t), C.ptr(s), C.ptr(c), bs, nv, k, temp_s, temp_t, C.ptr(go), C.ptr(ds),
-                                          C.stream_ptr(dev)), "ssvb_dino_bwd")
+                                          C.ptr(ws), ws_bytes, C.stream_ptr(dev)), "ssvb_dino_bwd")
         return None, ds.to(dts), None, None, None
 
 
