@@ -470,7 +470,9 @@ def run_ours(args):
                 "dtype_detail": "fp16 tensor-core operands (unit-norm rows scaled by sqrt(log2(e)/tau); bf16 for raw "
                                 "inputs), fp32 accumulation / statistics / loss / gradients",
                 "config": {"workload": WORKLOAD, "global_batch": N_GLOBAL, "dim": DIM, "rows_per_rank": 2 * n_local,
-                           "parallelism": f"row-sharded x{world}, all-gather zhat + lse", "l2": "flushed (256 MiB write) between timed iterations"},
+                           "parallelism": f"row-sharded x{world}, all-gather zhat + lse", "l2": "flushed (256 MiB write) between timed iterations",
+                           "per_config_l2": "flushed between repetitions by a 256 MiB write followed by a 256 MiB read "
+                                            "(cold and clean lines, bench_losses.l2_flush)"},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": 2 * n_local * DIM * 4 * world, "d2h_bytes_per_step": 4 * world,

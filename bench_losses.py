@@ -88,6 +88,21 @@ def time_gpu(fn, reps, flush, warm=5):
     return statistics.median(ts)
 
 
+def time_host(fn, n=50):
+    """Host (Python + driver) microseconds per step: n back-to-back calls with no synchronisation in between, timed
+    on the host clock - the issue cost a training loop pays per call when the GPU is not the bottleneck.  (n is small
+    enough that the launch queue never fills for the rows where the device time exceeds the host time.)"""
+    for _ in range(10):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    return (t1 - t0) / n * 1e6
+
+
 def time_graph(fn, reps, flush):
     """Same step captured once in a CUDA graph and replayed: device time without the per-launch Python / driver cost
     (what a graph-captured training step pays).  Returns None if capture is not possible."""
@@ -150,8 +165,9 @@ def graph_timeline(fn, flush, title, out):
         # the last replay = everything after the last flush (256 MiB FillFunctor<unsigned char> launch [+ the read-back
         # reduce_kernel of l2_flush])
         cut = max(i for i, e in enumerate(evs) if "FillFunctor<unsigned char>" in e.name)
-        while cut + 1 < len(evs) and "reduce_kernel" in evs[cut + 1].name and evs[cut + 1].time_range.end - evs[cut + 1].time_range.start > 20:
-            cut += 1
+        for i in range(cut + 1, min(cut + 4, len(evs))):   # [memset of the reduce output,] the 256 MiB read-back
+            if "reduce_kernel" in evs[i].name and evs[i].time_range.end - evs[i].time_range.start > 20:
+                cut = i
         step = evs[cut + 1:]
         if not step:
             return
@@ -209,7 +225,8 @@ def run_all(dev=None, reps=20, cpu=True, ref_gpu=True, only=None, emit=None):
     rows = []
     want = set(only) if only else None
 
-    def record(tag, name, cfg, ms, samples, flops=None, bytes_=None, graph_ms=None, cpu_res=None, ref_ms=None, note=""):
+    def record(tag, name, cfg, ms, samples, flops=None, bytes_=None, graph_ms=None, cpu_res=None, ref_ms=None, note="",
+               host_us=None, ref_host_us=None):
         t = graph_ms if graph_ms else ms   # roofline fraction from the device time (graph replay) when available
         if flops:
             ach = flops / (t * 1e-3) / 1e12
@@ -220,6 +237,7 @@ def run_all(dev=None, reps=20, cpu=True, ref_gpu=True, only=None, emit=None):
             roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "traffic": None, "algorithmic": bytes_, "peak_source": f"{src} copy bandwidth"}
         r = {"tag": tag, "loss": name, "config": cfg, "ms": ms, "graph_ms": graph_ms,
+             "host_us_per_step": host_us, "torch_eager_host_us_per_step": ref_host_us,
              "samples_per_s": samples / (t * 1e-3), "roofline": roof, "torch_eager_b200_ms": ref_ms,
              "speedup_vs_torch_eager_b200": (ref_ms / ms) if ref_ms else None, "cpu_baseline": None, "note": note}
         if cpu_res is not None:
@@ -237,6 +255,8 @@ def run_all(dev=None, reps=20, cpu=True, ref_gpu=True, only=None, emit=None):
         rp = reps_ or reps
         ms = time_gpu(ours, rp, flush)
         gms = time_graph(ours, rp, flush)
+        host_us = time_host(ours)
+        ref_host_us = None
         if TIMELINE is not None:
             legs.count = getattr(legs, "count", 0) + 1
             graph_timeline(ours, flush, f"row {legs.count} (eager {ms * 1e3:.1f} us, graph "
@@ -245,6 +265,8 @@ def run_all(dev=None, reps=20, cpu=True, ref_gpu=True, only=None, emit=None):
         if ref_gpu and R is not None and ref_cuda is not None:
             try:
                 ref_ms = time_gpu(ref_cuda, max(3, rp // 4), flush, warm=2)
+                if ref_ms < 5.0:
+                    ref_host_us = time_host(ref_cuda, n=20)
             except Exception as e:  # noqa: BLE001
                 print(f"[reference on cuda failed: {type(e).__name__}: {str(e)[:160]}]", file=sys.stderr)
                 torch.cuda.synchronize()
@@ -256,7 +278,8 @@ def run_all(dev=None, reps=20, cpu=True, ref_gpu=True, only=None, emit=None):
             elif port_cpu is not None and O is not None:
                 sec, nrep = time_cpu(port_cpu, budget_s=2.0, max_reps=2)
                 cpu_res = (sec, nrep, "port")
-        return dict(ms=ms, graph_ms=gms, ref_ms=ref_ms, cpu_res=cpu_res, samples=samples, **kw)
+        return dict(ms=ms, graph_ms=gms, ref_ms=ref_ms, cpu_res=cpu_res, samples=samples, host_us=host_us,
+                    ref_host_us=ref_host_us, **kw)
 
     def on(tag):
         return want is None or tag in want
@@ -512,9 +535,9 @@ def run_all(dev=None, reps=20, cpu=True, ref_gpu=True, only=None, emit=None):
 
 
 def table(rows, file=sys.stderr):
-    print("| loss | config | ours eager ms | ours graph ms | reference eager on B200 ms | speed-up (eager/eager) | "
-          "bound | achieved | frac of measured peak | CPU arm (kind, cores) s |", file=file)
-    print("|---|---|---|---|---|---|---|---|---|---|", file=file)
+    print("| loss | config | ours eager ms | ours graph ms | ours host us / step | reference eager on B200 ms | "
+          "speed-up (eager/eager) | bound | achieved | frac of measured peak | CPU arm (kind, cores) s |", file=file)
+    print("|---|---|---|---|---|---|---|---|---|---|---|", file=file)
     for r in rows:
         rf = r["roofline"]
         ach = f"{rf['achieved']:.1f} {rf['unit']}"
@@ -523,7 +546,8 @@ def table(rows, file=sys.stderr):
         sp = f"{r['speedup_vs_torch_eager_b200']:.1f}x" if r.get("speedup_vs_torch_eager_b200") else "-"
         cb = r.get("cpu_baseline")
         cs = f"{cb['seconds']:.4g} ({cb['kind']}, {cb['cores']})" if cb else "-"
-        print(f"| {r['loss']} | {r['config']} | {r['ms']:.4f} | {gm} | {rm} | {sp} | {rf['bound']} | {ach} | "
+        hu = f"{r['host_us_per_step']:.0f}" if r.get("host_us_per_step") else "-"
+        print(f"| {r['loss']} | {r['config']} | {r['ms']:.4f} | {gm} | {hu} | {rm} | {sp} | {rf['bound']} | {ach} | "
               f"{rf['frac']:.3f} | {cs} |", file=file)
 
 

@@ -37,7 +37,7 @@ enum {
   SSVB_OK = 0,
   SSVB_ERR_INVALID = -1,     /* null pointer / non-positive size / bad flag */
   SSVB_ERR_ALIGNMENT = -2,   /* pointer or leading dimension not 16-byte aligned */
-  SSVB_ERR_UNSUPPORTED = -3, /* shape outside what the sm_100a kernels cover (e.g. d > 128 for tensor-core losses) */
+  SSVB_ERR_UNSUPPORTED = -3, /* shape outside what the sm_100a kernels cover (e.g. d > 256 for tensor-core losses) */
   SSVB_ERR_WORKSPACE = -4,   /* workspace / saved buffer too small */
   SSVB_ERR_ARCH = -5,        /* current device is not compute capability 10.x */
   SSVB_ERR_DRIVER = -6       /* cuTensorMapEncodeTiled unavailable / failed */
@@ -53,7 +53,8 @@ int ssvb_device_check(void);
  *     call site models/simclr.py:90) and the contrastive term of RelicLoss (:163-194).
  *     zi, zj: [n x d].  loss = mean over 2n rows of (LSE_{b != a} s_ab - s_{a,partner(a)}),
  *     s = Zhat Zhat^T / temperature.  The 2n x 2n similarity matrix is never written to HBM.
- *     d <= 128 (zero-padded to a multiple of 64 internally).
+ *     d <= 256: zero-padded internally to 64 / 128 columns (d <= 128, the tuned path: whole rows per tile) or to 256
+ *     (128 < d <= 256: four 64-wide k-blocks per tile, two-stage ring, backward in two 128-column halves).
  * ------------------------------------------------------------------------------------- */
 size_t ssvb_ntxent_saved_bytes(int64_t n, int64_t d);
 size_t ssvb_ntxent_workspace_bytes(int64_t n, int64_t d);
@@ -474,7 +475,7 @@ int ssvb_dino_center_update(const float* teacher_rows, int64_t rows, int64_t k, 
  *     logits_h = [mem_pos . v_h / tau | mem_pos mem_neg^T / tau], v_0 = patch, v_1 = img (L2-normalised when
  *     `normalize`; the memory rows are used as stored), loss = w CE_0 + (1 - w) CE_1 (label 0).
  *     `loss` receives w CE_0 + (1 - w) CE_1 (one deterministic reduction over both heads).  The memory rows carry no
- *     gradient (models/pirl.py:131-133 reads them from the bank), so backward is one row-wise kernel.  d <= 128.
+ *     gradient (models/pirl.py:131-133 reads them from the bank), so backward is one row-wise kernel.  d <= 256.
  *     ssvb_bank_scatter / ssvb_bank_gather: the per-sample momentum bank of models/pirl.py:22-46
  *     (mode 0 initialize_vectors, mode 1 update_vectors; indices: DEVICE int64).
  * ------------------------------------------------------------------------------------- */

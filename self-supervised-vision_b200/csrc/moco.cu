@@ -65,7 +65,7 @@ MocoWs moco_ws(void* base, int64_t n, int64_t k, int64_t dpad) {
   MocoWs w;
   const int64_t npad = round_up(n, 128);
   SimParams p, pb;
-  moco_plan(p, n, k, 1.f, kFwdBN, 512 / kFwdBN);
+  moco_plan(p, n, k, 1.f, sim_fwd_bn(dpad), 512 / sim_fwd_bn(dpad));
   moco_plan(pb, n, k, 1.f, 128, 4);  // the fused single-pass form runs the backward-shaped kernel with its own chunk plan
   const int nch = p.nchunks > pb.nchunks ? p.nchunks : pb.nchunks;
   w.queue_bf16 = c.take<__nv_bfloat16>(k * dpad);
@@ -195,36 +195,51 @@ __global__ void moco_grad_finish_kernel(const float* __restrict__ q, const float
   const float scale = inv_n_tau * __ldg(grad_out);
   const float p0m1 = exp2f(sv.pos[row] * c - sv.lse2[row]) - 1.f;
   const float iq = normalize ? sv.inv_q[row] : 1.f, ik = normalize ? sv.inv_k[row] : 1.f;
-  const int k4 = lane * 4;
-  float gq[4] = {0.f, 0.f, 0.f, 0.f}, gk[4] = {0.f, 0.f, 0.f, 0.f}, qh[4] = {0.f, 0.f, 0.f, 0.f},
-        kh[4] = {0.f, 0.f, 0.f, 0.f};
-  if (k4 < d) {
-    const float4 acc = *reinterpret_cast<const float4*>(dacc + static_cast<int64_t>(row) * ld_dacc + k4);
-    const float4 vq = *reinterpret_cast<const float4*>(q + static_cast<int64_t>(row) * ldq + k4);
-    const float4 vk = *reinterpret_cast<const float4*>(kk + static_cast<int64_t>(row) * ldk + k4);
-    qh[0] = vq.x * iq; qh[1] = vq.y * iq; qh[2] = vq.z * iq; qh[3] = vq.w * iq;
-    kh[0] = vk.x * ik; kh[1] = vk.y * ik; kh[2] = vk.z * ik; kh[3] = vk.w * ik;
-    const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+  // d <= 256: up to two float4 per lane (columns lane * 4 and 128 + lane * 4)
+  float gq[2][4], gk[2][4], qh[2][4], kh[2][4];
+  float dq_dot = 0.f, dk_dot = 0.f;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int k4 = it * 128 + lane * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) gq[it][e] = gk[it][e] = qh[it][e] = kh[it][e] = 0.f;
+    if (k4 < d) {
+      const float4 acc = *reinterpret_cast<const float4*>(dacc + static_cast<int64_t>(row) * ld_dacc + k4);
+      const float4 vq = *reinterpret_cast<const float4*>(q + static_cast<int64_t>(row) * ldq + k4);
+      const float4 vk = *reinterpret_cast<const float4*>(kk + static_cast<int64_t>(row) * ldk + k4);
+      qh[it][0] = vq.x * iq; qh[it][1] = vq.y * iq; qh[it][2] = vq.z * iq; qh[it][3] = vq.w * iq;
+      kh[it][0] = vk.x * ik; kh[it][1] = vk.y * ik; kh[it][2] = vk.z * ik; kh[it][3] = vk.w * ik;
+      const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        gq[it][e] = (p0m1 * kh[it][e] + a[e]) * scale;
+        gk[it][e] = p0m1 * qh[it][e] * scale;
+      }
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      gq[e] = (p0m1 * kh[e] + a[e]) * scale;
-      gk[e] = p0m1 * qh[e] * scale;
+      dq_dot += gq[it][e] * qh[it][e];
+      dk_dot += gk[it][e] * kh[it][e];
     }
   }
   if (normalize) {
-    float dq_dot = gq[0] * qh[0] + gq[1] * qh[1] + gq[2] * qh[2] + gq[3] * qh[3];
-    float dk_dot = gk[0] * kh[0] + gk[1] * kh[1] + gk[2] * kh[2] + gk[3] * kh[3];
     dq_dot = warp_sum(dq_dot);
     dk_dot = warp_sum(dk_dot);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      gq[e] = (gq[e] - dq_dot * qh[e]) * iq;
-      gk[e] = (gk[e] - dk_dot * kh[e]) * ik;
-    }
+    for (int it = 0; it < 2; ++it)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        gq[it][e] = (gq[it][e] - dq_dot * qh[it][e]) * iq;
+        gk[it][e] = (gk[it][e] - dk_dot * kh[it][e]) * ik;
+      }
   }
-  if (k4 < d) {
-    if (dq) *reinterpret_cast<float4*>(dq + static_cast<int64_t>(row) * lddq + k4) = make_float4(gq[0], gq[1], gq[2], gq[3]);
-    if (dk) *reinterpret_cast<float4*>(dk + static_cast<int64_t>(row) * lddk + k4) = make_float4(gk[0], gk[1], gk[2], gk[3]);
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int k4 = it * 128 + lane * 4;
+    if (k4 < d) {
+      if (dq) *reinterpret_cast<float4*>(dq + static_cast<int64_t>(row) * lddq + k4) = make_float4(gq[it][0], gq[it][1], gq[it][2], gq[it][3]);
+      if (dk) *reinterpret_cast<float4*>(dk + static_cast<int64_t>(row) * lddk + k4) = make_float4(gk[it][0], gk[it][1], gk[it][2], gk[it][3]);
+    }
   }
 }
 
@@ -299,11 +314,15 @@ __global__ void pirl_grad_kernel(const float* __restrict__ img, const float* __r
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= n) return;
   const float scale = inv_n_tau * __ldg(grad_out);
-  const int k4 = lane * 4;
-  float q[4] = {0.f, 0.f, 0.f, 0.f};
-  if (k4 < d) {
-    const float4 v = *reinterpret_cast<const float4*>(mem_pos + static_cast<int64_t>(row) * ld_pos + k4);
-    q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+  // d <= 256: up to two float4 per lane (columns lane * 4 and 128 + lane * 4)
+  float q[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int k4 = it * 128 + lane * 4;
+    if (k4 < d) {
+      const float4 v = *reinterpret_cast<const float4*>(mem_pos + static_cast<int64_t>(row) * ld_pos + k4);
+      q[it][0] = v.x; q[it][1] = v.y; q[it][2] = v.z; q[it][3] = v.w;
+    }
   }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {  // head 0: patch (weight w), head 1: img (weight 1 - w)
@@ -315,20 +334,34 @@ __global__ void pirl_grad_kernel(const float* __restrict__ img, const float* __r
     const float lse2 = h ? sv.lse_img[row] : sv.lse_patch[row];
     const float iv = normalize ? (h ? sv.inv_img[row] : sv.inv_patch[row]) : 1.f;
     const float coef = (exp2f(pos * c - lse2) - 1.f) * scale * (h ? 1.f - w : w);
-    float g[4], xh[4] = {0.f, 0.f, 0.f, 0.f};
-    if (k4 < d) {
-      const float4 v = *reinterpret_cast<const float4*>(src + static_cast<int64_t>(row) * lds + k4);
-      xh[0] = v.x * iv; xh[1] = v.y * iv; xh[2] = v.z * iv; xh[3] = v.w * iv;
-    }
+    float g[2][4], xh[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float dot = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) g[e] = coef * q[e];
+    for (int it = 0; it < 2; ++it) {
+      const int k4 = it * 128 + lane * 4;
+      if (k4 < d) {
+        const float4 v = *reinterpret_cast<const float4*>(src + static_cast<int64_t>(row) * lds + k4);
+        xh[it][0] = v.x * iv; xh[it][1] = v.y * iv; xh[it][2] = v.z * iv; xh[it][3] = v.w * iv;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        g[it][e] = coef * q[it][e];
+        dot += g[it][e] * xh[it][e];
+      }
+    }
     if (normalize) {
-      float dot = g[0] * xh[0] + g[1] * xh[1] + g[2] * xh[2] + g[3] * xh[3];
       dot = warp_sum(dot);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) g[e] = (g[e] - dot * xh[e]) * iv;
+      for (int it = 0; it < 2; ++it)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) g[it][e] = (g[it][e] - dot * xh[it][e]) * iv;
     }
-    if (k4 < d) *reinterpret_cast<float4*>(dst + static_cast<int64_t>(row) * ldd + k4) = make_float4(g[0], g[1], g[2], g[3]);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int k4 = it * 128 + lane * 4;
+      if (k4 < d)
+        *reinterpret_cast<float4*>(dst + static_cast<int64_t>(row) * ldd + k4) = make_float4(g[it][0], g[it][1], g[it][2], g[it][3]);
+    }
   }
 }
 
@@ -340,7 +373,7 @@ int check_rows(const void* p, int64_t ld) {
 int check_shape(int64_t n, int64_t k, int64_t d, float temperature) {
   if (n <= 0 || k <= 0 || d <= 0 || !(temperature > 0.f)) return SSVB_ERR_INVALID;
   if (d % 4) return SSVB_ERR_ALIGNMENT;
-  if (d > 128 || k > (1 << 30) || n > (1 << 30)) return SSVB_ERR_UNSUPPORTED;
+  if (d > 256 || k > (1 << 30) || n > (1 << 30)) return SSVB_ERR_UNSUPPORTED;
   return SSVB_OK;
 }
 
@@ -421,7 +454,7 @@ int ssvb_moco_fwd(const float* query, const float* keys, const float* queue, con
     SSVB_LAUNCH_CHECK();
     return SSVB_OK;
   }
-  moco_plan(p, n, k, c, kFwdBN, 512 / kFwdBN);
+  moco_plan(p, n, k, c, sim_fwd_bn(dpad), 512 / sim_fwd_bn(dpad));
   p.part_m = ws.part_m;
   p.part_l = ws.part_l;
   p.part_stride = static_cast<int>(npad);
@@ -522,7 +555,7 @@ int ssvb_moco_dist_shard_fwd(const void* qhat_all, int64_t n_global, const float
   const __nv_bfloat16* qb = nullptr;
   SSVB_TRY(get_queue_bf16(queue_shard, queue_shard_bf16, k_local, d, ld_queue, dpad, ws, s, &qb));
   SimParams p;
-  moco_plan(p, n_global, k_local, c, kFwdBN, 512 / kFwdBN);
+  moco_plan(p, n_global, k_local, c, sim_fwd_bn(dpad), 512 / sim_fwd_bn(dpad));
   p.part_m = ws.part_m;
   p.part_l = ws.part_l;
   p.part_stride = static_cast<int>(npad);
@@ -653,7 +686,7 @@ int ssvb_pirl_fwd(const float* img, const float* patch, const float* mem_pos, co
   SSVB_TRY(get_queue_bf16(mem_neg, nullptr, k, d, ld_neg, dpad, ws, s, &qb));
   // the negatives' logits are shared by both heads (:109): one pass of the tensor-core kernel, one finalize for both
   SimParams p;
-  moco_plan(p, n, k, c, kFwdBN, 512 / kFwdBN);
+  moco_plan(p, n, k, c, sim_fwd_bn(dpad), 512 / sim_fwd_bn(dpad));
   p.part_m = ws.part_m;
   p.part_l = ws.part_l;
   p.part_stride = static_cast<int>(npad);

@@ -26,7 +26,7 @@ struct NtxPlan {
 int make_plan(NtxPlan& pl, int64_t n_glob, int64_t d, int normalize, float temperature) {
   if (n_glob <= 0 || d <= 0 || !(temperature > 0.f)) return SSVB_ERR_INVALID;
   if (d % 4) return SSVB_ERR_ALIGNMENT;
-  if (d > 128) return SSVB_ERR_UNSUPPORTED;
+  if (d > 256) return SSVB_ERR_UNSUPPORTED;  // 128 < d <= 256: KB = 4 kernels (sim_kernels.cuh FwdCfg / BwdCfg)
   if (2 * n_glob > (1 << 30)) return SSVB_ERR_UNSUPPORTED;
   pl.n_glob = n_glob;
   pl.m = 2 * n_glob;
@@ -97,7 +97,7 @@ WsLayout ws_layout(void* base, int64_t local_rows, int64_t row_blocks, int64_t c
   SimParams p{};
   p.row_blocks = static_cast<int>(row_blocks);
   p.cols = static_cast<int>(cols);
-  plan_chunks(p, kFwdBN, kFwdMinTiles);
+  plan_chunks(p, sim_fwd_bn(dpad), sim_fwd_min_tiles(dpad));
   size_t part_elems = static_cast<size_t>(4 * p.nchunks + 2) * lr;
   if (part_elems < static_cast<size_t>(sim_mpad(cols))) part_elems = sim_mpad(cols);
   w.pos = c.take<float>(lr);
@@ -130,27 +130,38 @@ __global__ void ntx_grad_finish_kernel(const float* __restrict__ zi, const float
   float* out = view ? dzj + static_cast<int64_t>(r) * ld_dzj : dzi + static_cast<int64_t>(r) * ld_dzi;
   const float scale = inv_m_tau * __ldg(grad_out);
   const float inv = normalize ? inv_norm[lrow] : 1.f;
-  const int k = lane * 4;
-  float g[4] = {0.f, 0.f, 0.f, 0.f}, zh[4] = {0.f, 0.f, 0.f, 0.f};
-  if (k < d) {
-    const float4 acc = *reinterpret_cast<const float4*>(dacc + static_cast<int64_t>(lrow) * ld_dacc + k);
-    const uint2 pz = *reinterpret_cast<const uint2*>(zhat + static_cast<int64_t>(partner) * dpad + k);
-    const float2 p01 = unpack_h2(pz.x, normalize != 0), p23 = unpack_h2(pz.y, normalize != 0);  // fp16 iff normalised
-    const float4 zz = *reinterpret_cast<const float4*>(z + k);
-    const float za = -2.f * zp_scale;
-    g[0] = fmaf(acc.x, acc_scale, za * p01.x) * scale;
-    g[1] = fmaf(acc.y, acc_scale, za * p01.y) * scale;
-    g[2] = fmaf(acc.z, acc_scale, za * p23.x) * scale;
-    g[3] = fmaf(acc.w, acc_scale, za * p23.y) * scale;
-    zh[0] = zz.x * inv; zh[1] = zz.y * inv; zh[2] = zz.z * inv; zh[3] = zz.w * inv;
+  // d <= 256: up to two float4 per lane (columns lane * 4 and 128 + lane * 4)
+  float g[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, zh[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float dot = 0.f;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int k = it * 128 + lane * 4;
+    if (k < d) {
+      const float4 acc = *reinterpret_cast<const float4*>(dacc + static_cast<int64_t>(lrow) * ld_dacc + k);
+      const uint2 pz = *reinterpret_cast<const uint2*>(zhat + static_cast<int64_t>(partner) * dpad + k);
+      const float2 p01 = unpack_h2(pz.x, normalize != 0), p23 = unpack_h2(pz.y, normalize != 0);  // fp16 iff normalised
+      const float4 zz = *reinterpret_cast<const float4*>(z + k);
+      const float za = -2.f * zp_scale;
+      g[it][0] = fmaf(acc.x, acc_scale, za * p01.x) * scale;
+      g[it][1] = fmaf(acc.y, acc_scale, za * p01.y) * scale;
+      g[it][2] = fmaf(acc.z, acc_scale, za * p23.x) * scale;
+      g[it][3] = fmaf(acc.w, acc_scale, za * p23.y) * scale;
+      zh[it][0] = zz.x * inv; zh[it][1] = zz.y * inv; zh[it][2] = zz.z * inv; zh[it][3] = zz.w * inv;
+    }
+    dot += g[it][0] * zh[it][0] + g[it][1] * zh[it][1] + g[it][2] * zh[it][2] + g[it][3] * zh[it][3];
   }
   if (normalize) {
-    float dot = g[0] * zh[0] + g[1] * zh[1] + g[2] * zh[2] + g[3] * zh[3];
     dot = warp_sum(dot);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) g[i] = (g[i] - dot * zh[i]) * inv;
+    for (int it = 0; it < 2; ++it)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) g[it][i] = (g[it][i] - dot * zh[it][i]) * inv;
   }
-  if (k < d) *reinterpret_cast<float4*>(out + k) = make_float4(g[0], g[1], g[2], g[3]);
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int k = it * 128 + lane * 4;
+    if (k < d) *reinterpret_cast<float4*>(out + k) = make_float4(g[it][0], g[it][1], g[it][2], g[it][3]);
+  }
 }
 
 int check_rows(const void* p, int64_t ld) {
@@ -216,7 +227,7 @@ int ssvb_ntxent_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   }
   SimParams p;
   fill_sim_params_rows(p, pl, 1, pl.m, 0, 0);
-  plan_chunks(p, kFwdBN, kFwdMinTiles);
+  plan_chunks(p, sim_fwd_bn(pl.dpad), sim_fwd_min_tiles(pl.dpad));
   p.part_m = ws.part_m;
   p.part_l = ws.part_l;
   p.part_stride = static_cast<int>(round_up(pl.m, 256));
@@ -370,7 +381,7 @@ int rows_fwd_impl(const void* zhat_all, int64_t world, int64_t rank, int64_t n_l
   const size_t peer_off = peer_stat_off / (gen ? sizeof(uint2) : sizeof(float)) + static_cast<size_t>(rank) * 2 * lr;
   SimParams p;
   fill_sim_params_rows(p, pl, 1, lr, rank * lr, 0);
-  plan_chunks(p, kFwdBN, kFwdMinTiles);
+  plan_chunks(p, sim_fwd_bn(pl.dpad), sim_fwd_min_tiles(pl.dpad));
   p.part_m = ws.part_m;
   p.part_l = ws.part_l;
   p.part_stride = static_cast<int>(round_up(lr, 256));
@@ -702,7 +713,7 @@ int ssvb_ntxent_p2p_prep_push(const float* zi, const float* zj, int64_t n_local,
                               float* inv_norm_local, float* pos_local, void* stream) {
   SSVB_TRY(check_device_sm100());
   SSVB_TRY(dist_check(world, rank, n_local));
-  if (world > 256) return SSVB_ERR_UNSUPPORTED;
+  if (world > 256 || d > 128) return SSVB_ERR_UNSUPPORTED;  // the push kernel moves one float4 per lane and row
   NtxPlan pl;
   SSVB_TRY(make_plan(pl, n_local * world, d, normalize, temperature));
   SSVB_TRY(check_rows(zi, ld_zi));

@@ -6,10 +6,13 @@
 
 namespace ssvb {
 
-inline int64_t sim_dpad(int64_t d) { return round_up(d, 64); }
+// staged row width: 64 or 128 columns for d <= 128, 256 for 128 < d <= 256 (KB = dpad / 64 = 1, 2 or 4 k-blocks)
+inline int64_t sim_dpad(int64_t d) { return d <= 128 ? round_up(d, 64) : 256; }
 inline int64_t sim_mpad(int64_t m) { return round_up(m, 256); }
-// forward chunk plan: tile width and the smallest number of tiles a column chunk may have (1024 columns)
-constexpr int kFwdMinTiles = 1024 / kFwdBN;
+// forward tile width for a staged row width (FwdCfg<KB>::BN) and the smallest number of tiles a column chunk may have
+// (1024 columns)
+inline int sim_fwd_bn(int64_t dpad) { return dpad > 128 ? 128 : kFwdBN; }
+inline int sim_fwd_min_tiles(int64_t dpad) { return 1024 / sim_fwd_bn(dpad); }
 
 // Choose the column chunking: (row block, chunk) units are statically strided over one CTA per SM, so the number
 // of units should fill whole waves of `num_sms()` CTAs (tail effect) while every chunk keeps >= min_tiles tiles
@@ -70,7 +73,7 @@ inline int launch_sim_fwd(int mode, const void* A, int64_t a_rows, const void* B
                           const SimParams& p, cudaStream_t s) {
   CUtensorMap tmA, tmB;
   SSVB_TRY(make_tmap_bf16(&tmA, A, a_rows, dpad, dpad, 128, p.opf16 != 0));
-  SSVB_TRY(make_tmap_bf16(&tmB, B, b_rows, dpad, dpad, kFwdBN, p.opf16 != 0));
+  SSVB_TRY(make_tmap_bf16(&tmB, B, b_rows, dpad, dpad, sim_fwd_bn(dpad), p.opf16 != 0));
   const int KB = static_cast<int>(dpad / 64);
 #define SSVB_DISPATCH(KBV)                                                      \
   switch (mode) {                                                               \
@@ -85,10 +88,24 @@ inline int launch_sim_fwd(int mode, const void* A, int64_t a_rows, const void* B
   }
   if (KB == 1) { SSVB_DISPATCH(1) }
   if (KB == 2) { SSVB_DISPATCH(2) }
+  if (KB == 4) { SSVB_DISPATCH(4) }
 #undef SSVB_DISPATCH
   return SSVB_ERR_UNSUPPORTED;
 }
+inline int launch_sim_bwd_half(int mode, const void* A, int64_t a_rows, const void* B, int64_t b_rows, int64_t dpad,
+                               const SimParams& p, cudaStream_t s);
+// dpad = 256: one launch per 128-column half of dZ (see BwdCfg::DP)
 inline int launch_sim_bwd(int mode, const void* A, int64_t a_rows, const void* B, int64_t b_rows, int64_t dpad,
+                          const SimParams& p, cudaStream_t s) {
+  if (dpad <= 128) return launch_sim_bwd_half(mode, A, a_rows, B, b_rows, dpad, p, s);
+  SimParams q = p;
+  for (int h = 0; h < 2; ++h) {
+    q.dhalf = h;
+    SSVB_TRY(launch_sim_bwd_half(mode, A, a_rows, B, b_rows, dpad, q, s));
+  }
+  return SSVB_OK;
+}
+inline int launch_sim_bwd_half(int mode, const void* A, int64_t a_rows, const void* B, int64_t b_rows, int64_t dpad,
                           const SimParams& p, cudaStream_t s) {
   CUtensorMap tmA, tmB;
   SSVB_TRY(make_tmap_bf16(&tmA, A, a_rows, dpad, dpad, 128, p.opf16 != 0));
@@ -107,6 +124,7 @@ inline int launch_sim_bwd(int mode, const void* A, int64_t a_rows, const void* B
   }
   if (KB == 1) { SSVB_DISPATCH(1) }
   if (KB == 2) { SSVB_DISPATCH(2) }
+  if (KB == 4) { SSVB_DISPATCH(4) }
 #undef SSVB_DISPATCH
   return SSVB_ERR_UNSUPPORTED;
 }

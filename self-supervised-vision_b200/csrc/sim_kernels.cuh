@@ -39,6 +39,7 @@ struct SimParams {
   int use_atomic;  // nchunks > 1: red.add into a zeroed dacc
   unsigned long long* dbg;  // SSVB_DBG_TIMING builds only
   int opf16;  // similarity operands staged as fp16 (normalised rows) instead of bf16
+  int dhalf;  // backward, dpad = 256 only: which 128-column half of dZ this launch produces
 };
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -150,11 +151,13 @@ __device__ __forceinline__ void lds_v4(uint32_t saddr, unsigned long long& lo, u
 constexpr int kFwdBN = SSVB_FWD_BN;
 template <int KB>
 struct FwdCfg {
-  static constexpr int BN = kFwdBN;
+  // d <= 128 (KB <= 2): BN = kFwdBN.  128 < d <= 256 (KB = 4, dpad = 256): 128-column tiles (four S buffers) and a
+  // 2-stage ring - a 64 KB A tile + 2 x 64 KB B tiles is what fits in 227 KB; functional coverage, not the tuned path.
+  static constexpr int BN = (KB > 2) ? 128 : kFwdBN;
   static constexpr int NBUF = 512 / BN;  // S buffers in TMEM
   static constexpr int A_BYTES = 128 * 128 * KB;
   static constexpr int B_BYTES = BN * 128 * KB;
-  static constexpr int NSTAGE = ((KB == 1) ? 6 : 3) * (256 / BN);  // deep enough to cover the TMA latency (192 KB ring)
+  static constexpr int NSTAGE = (KB > 2) ? 2 : ((KB == 1) ? 6 : 3) * (256 / BN);  // deep enough to cover the TMA latency
   static constexpr int NBARS = 4 + 2 * NSTAGE + 2 * NBUF;
   static constexpr int SMEM = 1024 + A_BYTES + NSTAGE * B_BYTES + NBARS * 8 + 16;
 };
@@ -429,11 +432,14 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int KB>
 struct BwdCfg {
   static constexpr int BN = 128;
-  static constexpr int DP = 64 * KB;
+  // output columns of one launch: the whole row for d <= 128; for KB = 4 (dpad = 256) the dZ accumulator holds ONE
+  // 128-column half (TMEM: S0 S1 dZ W0 W1 = 512 columns) and the host launches the kernel once per half (p.dhalf) -
+  // S and the weights are recomputed, the second GEMM reads k-blocks {2 dhalf, 2 dhalf + 1} of the same B tile
+  static constexpr int DP = (KB >= 2) ? 128 : 64;
   static constexpr int A_BYTES = 128 * 128 * KB;
   static constexpr int B_BYTES = BN * 128 * KB;
   static constexpr int CS_BYTES = BN * 4;  // per-stage column statistics (fp32)
-  static constexpr int NSTAGE = (KB == 1) ? 8 : 5;
+  static constexpr int NSTAGE = (KB == 1) ? 8 : (KB == 2 ? 5 : 2);
   static constexpr int NBARS = 2 + 2 * NSTAGE + 8 + 2;
   static constexpr int SMEM = 1024 + A_BYTES + NSTAGE * (B_BYTES + CS_BYTES) + NBARS * 8 + 16;
   static constexpr int T_S = 0;
@@ -655,8 +661,9 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifndef SSVB_DBG_NOD
 #pragma unroll
             for (int k = 0; k < BN / 16; ++k)
-              umma_ts(tmem + C::T_DZ, tmem + C::T_W + buf * 64 + k * 8, desc_mnmajor(bbase + k * (16 * 128), BN * 128),
-                      IDESC_D, (t > ui.t0 || k > 0) ? 1u : 0u);
+              umma_ts(tmem + C::T_DZ, tmem + C::T_W + buf * 64 + k * 8,
+                      desc_mnmajor(bbase + (KB > 2 ? p.dhalf * 2 * (BN * 128) : 0) + k * (16 * 128), BN * 128), IDESC_D,
+                      (t > ui.t0 || k > 0) ? 1u : 0u);
 #endif
             umma_commit(&b_empty[st]);
             umma_commit(&w_empty[buf]);
@@ -757,7 +764,7 @@ sim_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_x32(tmem + tlane + C::T_DZ + col0, v);
         tmem_ld_wait_regs(v);
         if (valid) {
-          float* dst = p.dacc + static_cast<size_t>(ui.lrow0 + row_l) * p.ld_dacc + col0;
+          float* dst = p.dacc + static_cast<size_t>(ui.lrow0 + row_l) * p.ld_dacc + col0 + (KB > 2 ? p.dhalf * 128 : 0);
           if (p.use_atomic) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)

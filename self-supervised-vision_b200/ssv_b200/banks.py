@@ -50,7 +50,7 @@ class _Ring:
         self._data = torch.zeros(rows, dim, dtype=torch.float32, device=self._device)
         self._shadow = None
         self._shadow_version = -1
-        if with_shadow and dim % 4 == 0 and dim <= 128:
+        if with_shadow and dim % 4 == 0 and dim <= 256:
             dpad = C.lib().ssvb_ntxent_dpad(dim)
             self._shadow = torch.zeros(rows, dpad, dtype=torch.bfloat16, device=self._device)
             self._shadow_version = self._data._version

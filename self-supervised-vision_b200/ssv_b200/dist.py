@@ -220,7 +220,8 @@ class _NtxentDistFn(torch.autograd.Function):
         norm = int(bool(normalize))
         use_p2p = False
         multicast = transport != "p2p-unicast"
-        if cuda and world > 1 and transport in ("auto", "p2p", "p2p-unicast"):
+        if cuda and world > 1 and transport in ("auto", "p2p", "p2p-unicast") and (d <= 128 or transport != "auto"):
+            # (the peer-push kernels cover d <= 128; "auto" takes the NCCL transport for 128 < d <= 256)
             use_p2p = _p2p_available(group, world, n, d, dev, multicast, required=transport != "auto")
         if use_p2p:
             arena = _PeerArena.get(group, world, n, d, dev, multicast)

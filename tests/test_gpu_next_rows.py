@@ -129,7 +129,8 @@ def test_pirl_golden(S, tag):
           grad_tol=2e-2 if tag == "pa" else 1e-2)
 
 
-@pytest.mark.parametrize("n,k,d,tau,w", [(256, 1000, 128, 0.07, 0.5), (100, 4100, 64, 0.2, 0.3), (300, 65536, 128, 0.07, 0.5)])
+@pytest.mark.parametrize("n,k,d,tau,w", [(256, 1000, 128, 0.07, 0.5), (100, 4100, 64, 0.2, 0.3), (300, 65536, 128, 0.07, 0.5),
+                                         (150, 3000, 256, 0.1, 0.4)])
 def test_pirl_oracle(S, n, k, d, tau, w):
     def unit(x):
         return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)

@@ -78,6 +78,9 @@ def test_ntxent_golden(S, tag):
     (640, 128, True, 0.02, True),      # tau below the fixed-shift bound -> online-max path
     (2048, 128, True, 0.5, False),     # several row blocks x column chunks (atomic accumulation path)
     (1024, 32, True, 0.1, False),
+    (300, 256, True, 0.5, False),      # 128 < d <= 256: four k-blocks, 128-column tiles, backward in two halves
+    (700, 192, True, 0.1, True),       # ... padded to 256, several row blocks, peaky
+    (384, 200, False, 1.0, False),     # ... raw inputs -> online-max path
 ])
 def test_ntxent_oracle(S, n, d, norm, tau, clu):
     zi, zj = clustered(3, n, d) if clu else (randn(0, n, d), randn(1, n, d))
@@ -158,7 +161,8 @@ def test_moco_golden(S, tag):
     check(loss.item(), [q.grad, k.grad], float(g[f"{tag}_loss"]), [g[f"{tag}_dq"], g[f"{tag}_dk"]], f"moco[{tag}]")
 
 
-@pytest.mark.parametrize("n,k,d,tau", [(256, 65536, 128, 0.07), (100, 1000, 128, 0.07), (300, 4100, 64, 0.2)])
+@pytest.mark.parametrize("n,k,d,tau", [(256, 65536, 128, 0.07), (100, 1000, 128, 0.07), (300, 4100, 64, 0.2),
+                                       (200, 5000, 256, 0.07), (64, 1000, 160, 0.2)])
 def test_moco_oracle(S, n, k, d, tau):
     q, kk = randn(0, n, d), randn(1, n, d)
     mem = randn(2, k, d)
@@ -365,7 +369,7 @@ def test_relic_golden(S, tag):
           [g[f"{tag}_dzi"], g[f"{tag}_dzj"], g[f"{tag}_dzo"]], f"relic[{tag}]")
 
 
-@pytest.mark.parametrize("n,d,tau", [(512, 128, 1.0), (4096, 128, 1.0), (300, 64, 0.2)])
+@pytest.mark.parametrize("n,d,tau", [(512, 128, 1.0), (4096, 128, 1.0), (300, 64, 0.2), (260, 256, 0.5)])
 def test_relic_oracle(S, n, d, tau):
     zi, zj, zo = randn(0, n, d), randn(1, n, d), randn(2, n, d)
     ref = O.relic(zi, zj, zo, True, tau, 0.5)
