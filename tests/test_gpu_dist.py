@@ -54,6 +54,16 @@ def _worker(rank, world, port, n_local, d, normalize, tau, out, transport="auto"
 @pytest.mark.parametrize("transport", ["p2p", "p2p-unicast", "nccl"])
 @pytest.mark.parametrize("n_local,d,normalize,tau", [(192, 128, True, 0.5), (1000, 64, True, 0.07), (256, 128, True, 0.02)])
 def test_dist_ntxent_vs_oracle(n_local, d, normalize, tau, transport):
+    _dist_ntxent_case(n_local, d, normalize, tau, transport)
+
+
+def test_dist_ntxent_wide_rows_take_nccl():
+    """128 < d <= 256: the four-k-block kernels behind the NCCL transport (the peer-push kernels cover d <= 128, so
+    transport="auto" must fall back without being asked)."""
+    _dist_ntxent_case(160, 200, True, 0.5, "auto")
+
+
+def _dist_ntxent_case(n_local, d, normalize, tau, transport):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     from oracle import ssl_oracle as O
@@ -178,6 +188,13 @@ def test_dist_swav_vs_oracle(nb, nbank, k, d):
         assert rl2(out[r]["codes"], ref_codes[r * nb:(r + 1) * nb]) < 1e-4
 
 
+def _max_ulp(a, b):
+    """largest distance in units of the last place between two fp32 arrays (same sign pattern assumed; zeros exact)"""
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    assert ((a == 0) == (b == 0)).all() and (np.signbit(a) == np.signbit(b)).all()
+    return int(np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64)).max())
+
+
 def _moco_worker(rank, world, port, n_local, k_total, d, tau, out):
     _init(rank, world, port)
     from ssv_b200.dist import DistributedMocoLoss, ShardedMemoryBank
@@ -217,7 +234,9 @@ def test_dist_moco_sharded_queue_vs_oracle(n_local, k_total, d, tau):
     queue = np.concatenate([out[r]["before"] for r in range(world)])
     # the sharded ring after the fill == single-process ring fed the same global batch
     ref_bank, ref_ptr = O.ring_enqueue(np.zeros((k_total, d), np.float32), 0, out[0]["fill"], True)
-    np.testing.assert_allclose(queue, ref_bank, rtol=2.4e-7, atol=0)  # <= 2 ulp of the fp64-rounded oracle (fp32 norm: 1 ulp + 1 ulp for the quotient)
+    # normalised rows vs the fp64-rounded oracle: fp32 sum of squares (shuffle-tree order) + sqrt + division against a
+    # correctly rounded reference -> 2 ulp typical, 3 ulp for ~1 element in 10^6 (measured on this test's 1 M elements)
+    assert _max_ulp(queue, ref_bank) <= 3
     assert all(out[r]["ptr_before"] == ref_ptr for r in range(world))
     ref_loss, ref_dq, ref_dk = O.moco(q, k, queue, True, tau)
     rl2 = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)  # noqa: E731
@@ -229,7 +248,7 @@ def test_dist_moco_sharded_queue_vs_oracle(n_local, k_total, d, tau):
     assert len({out[r]["loss"] for r in range(world)}) == 1
     ref_bank2, ref_ptr2 = O.ring_enqueue(queue.copy(), ref_ptr, k, True)
     after = np.concatenate([out[r]["after"] for r in range(world)])
-    np.testing.assert_allclose(after, ref_bank2, rtol=2.4e-7, atol=0)  # <= 2 ulp of the fp64-rounded oracle (fp32 norm: 1 ulp + 1 ulp for the quotient)
+    assert _max_ulp(after, ref_bank2) <= 3
     assert all(out[r]["ptr"] == ref_ptr2 for r in range(world))
 
 
