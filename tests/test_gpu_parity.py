@@ -12,6 +12,8 @@ from conftest import load_golden, rel_l2, rel_scalar, ulp_diff
 from oracle import ssl_oracle as O
 
 pytestmark = pytest.mark.gpu
+ROOT = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+PKG = __import__("os").path.join(ROOT, "self-supervised-vision_b200")
 
 LOSS_TOL = 1e-3
 GRAD_TOL = 1e-2
@@ -458,7 +460,8 @@ def test_swav_golden(S, tag):
           [g[f"sw_{tag}_dz1"], g[f"sw_{tag}_dz2"], g[f"sw_{tag}_dc"]], f"swav[{tag}]")
 
 
-@pytest.mark.parametrize("nb,nbank,k,d", [(512, 3000, 3000, 128), (300, 0, 100, 64), (64, 70, 1000, 32)])
+@pytest.mark.parametrize("nb,nbank,k,d", [(512, 3000, 3000, 128), (300, 0, 100, 64), (64, 70, 1000, 32),
+                                          (200, 1000, 1000, 96)])   # split-K gradient GEMMs with ragged K slices / N tails
 def test_swav_oracle(S, nb, nbank, k, d):
     def unit(x):
         return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
@@ -471,3 +474,39 @@ def test_swav_oracle(S, nb, nbank, k, d):
     loss = S.SwavLoss(0.1, 0.05, 3)(a, b, p, dev(bank, False) if nbank else None)
     loss.backward()
     check(loss.item(), [a.grad, b.grad, p.grad], ref[0], ref[1:], f"swav nb={nb} k={k}")
+
+
+# ------------------------------------------------------------------------------------------------ GEMM epilogue paths
+def test_gemm_row_store_fallback_matches_oracle():
+    """The staged TMA-store epilogue is the default; rows that are not 16-byte aligned take the per-thread row-store
+    epilogue.  `SSVB_GEMM_NO_TMA_STORE=1` forces that path (read once per process, hence the subprocess): Barlow (fused
+    loss epilogue + the un-fused backward column reduction) and SwAV (fp32 scores, no split-K) against the oracle."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np, torch
+sys.path[:0] = [%r, %r]
+import ssv_b200 as S
+from oracle import ssl_oracle as O
+g = torch.Generator().manual_seed(3)
+zi = (torch.randn(200, 264, generator=g) * 1.3 + 0.2).numpy(); zj = (0.7 * zi + 0.3 * torch.randn(200, 264, generator=g).numpy()).astype(np.float32)
+a, b = torch.from_numpy(zi).cuda().requires_grad_(True), torch.from_numpy(zj).cuda().requires_grad_(True)
+loss = S.BarlowLoss(False, 0.005)(a, b); loss.backward()
+ref = O.barlow(zi, zj, False, 0.005)
+rl2 = lambda x, y: np.linalg.norm(x - y) / np.linalg.norm(y)
+assert abs(loss.item() - ref[0]) / abs(ref[0]) <= 1e-3, (loss.item(), ref[0])
+assert rl2(a.grad.cpu().numpy(), ref[1]) <= 1e-2 and rl2(b.grad.cpu().numpy(), ref[2]) <= 1e-2
+unit = lambda x: (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+z1 = unit(torch.randn(200, 96, generator=g).numpy()); z2 = unit(0.6 * z1 + 0.4 * torch.randn(200, 96, generator=g).numpy())
+c = unit(torch.randn(1000, 96, generator=g).numpy())
+t1, t2, tc = (torch.from_numpy(x).cuda().requires_grad_(True) for x in (z1, z2, c))
+l2 = S.SwavLoss(0.1, 0.05, 3)(t1, t2, tc, None); l2.backward()
+r2 = O.swav(z1, z2, c, None, 0.1, 0.05, 3)
+assert abs(l2.item() - r2[0]) / abs(r2[0]) <= 1e-3
+assert rl2(t1.grad.cpu().numpy(), r2[1]) <= 1e-2 and rl2(tc.grad.cpu().numpy(), r2[3]) <= 1e-2
+print("fallback-ok")
+""" % (ROOT, PKG)
+    env = dict(os.environ, SSVB_GEMM_NO_TMA_STORE="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "fallback-ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
