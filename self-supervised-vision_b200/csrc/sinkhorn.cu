@@ -79,6 +79,7 @@ constexpr int kSkSlices = 32;  // row slices per column group in the alpha kerne
 // its column (coalesced 128-byte row segments), fixed-order combine through shared memory -> ~94 CTAs instead of 12.
 __global__ void sk_alpha_kernel(const float* __restrict__ upart, int grid, int kpad, int k, float* __restrict__ alpha,
                                 int raw = 0) {
+  pdl_launch_dependents();  // the next pass may start streaming score rows now; it waits before it reads alpha
   __shared__ float sh[kSkSlices][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float u = 0.f;
@@ -100,6 +101,7 @@ __global__ void sk_alpha_kernel(const float* __restrict__ upart, int grid, int k
 __global__ void sk_alpha0_kernel(const float* __restrict__ upart, const float* __restrict__ mpart, int grid, int kpad,
                                  int k, float inv_eps_log2e, float* __restrict__ alpha, float* __restrict__ smax,
                                  int raw = 0) {
+  pdl_launch_dependents();  // (see sk_alpha_kernel)
   __shared__ float sh[kSkSlices][33];
   __shared__ float msh[32];
   const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -404,11 +406,20 @@ sk_tma_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, float i
     // ---- producer: one elected lane streams this CTA's rows through the ring
     if (lane == 0) {
       const uint32_t bytes = static_cast<uint32_t>(k) * 4u;
+      // the score rows do not depend on the previous kernel (the alpha kernel): when this pass was launched with
+      // programmatic stream serialization the first ring-full of rows streams in while that kernel still runs
+      const int pre = (PHASE != 0) ? (n_my < nst ? n_my : nst) : 0;
+      for (int i = 0; i < pre; ++i) {
+        const int64_t r = blockIdx.x + static_cast<int64_t>(i) * gridDim.x;
+        mbar_expect_tx(&full[i], bytes);
+        bulk_load_1d(ring + static_cast<size_t>(i) * rowf, s + r * ld, bytes, &full[i]);
+      }
       if (PHASE != 0) {
+        pdl_wait();
         mbar_expect_tx(abar, bytes);
         bulk_load_1d(alpha_s, alpha, bytes, abar);
       }
-      for (int i = 0; i < n_my; ++i) {
+      for (int i = pre; i < n_my; ++i) {
         const int slot = i % nst;
         if (i >= nst) mbar_wait(&empty[slot], ((i / nst) - 1) & 1);
         const int64_t r = blockIdx.x + static_cast<int64_t>(i) * gridDim.x;
@@ -416,9 +427,11 @@ sk_tma_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, float i
         bulk_load_1d(ring + static_cast<size_t>(slot) * rowf, s + r * ld, bytes, &full[slot]);
       }
     }
+    if (PHASE != 0) pdl_wait();  // the whole producer warp takes part in the combine that overwrites upart
   } else {
     float shift = 0.f;
     if (PHASE != 0) {
+      pdl_wait();  // smax / alpha come from the previous kernel
       shift = smax[0] * inv_eps_log2e;
       mbar_wait(abar, 0);
     }
@@ -539,7 +552,7 @@ inline SkRing sk_ring(int kpad) {
 }
 template <int PHASE>
 int sk_launch_fast(int grid, size_t smem_unused, cudaStream_t s, const float* scores, int64_t b, int k, int64_t ld, float iel,
-                   const SkWs& ws, float* codes, int64_t ldc, float inv_b) {
+                   const SkWs& ws, float* codes, int64_t ldc, float inv_b, bool pdl = false) {
   (void)smem_unused;
 #ifdef SSVB_SK_ROWREG  // previous fast path (global loads straight into registers), kept for A/B timing
   const size_t smem = static_cast<size_t>(9) * ws.kpad * 4;
@@ -549,8 +562,27 @@ int sk_launch_fast(int grid, size_t smem_unused, cudaStream_t s, const float* sc
 #else
   const SkRing g = sk_ring(ws.kpad);
   SSVB_CUDA(cudaFuncSetAttribute(sk_tma_kernel<PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem)));
-  sk_tma_kernel<PHASE><<<grid, (kSkConsumers + 1) * 32, g.smem, s>>>(scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart,
-                                                                     ws.kpad, codes, ldc, ws.smax_part, inv_b, g.nst, g.rowf);
+  static const bool no_pdl = getenv("SSVB_NO_PDL") != nullptr;  // A/B switch
+  if (pdl && PHASE != 0 && !no_pdl) {
+    // programmatic dependent launch behind the alpha kernel: prologue + first ring-full of rows overlap it
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3((kSkConsumers + 1) * 32);
+    cfg.dynamicSmemBytes = g.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const float* smax_c = ws.smax;
+    const float* alpha_c = ws.alpha;
+    SSVB_CUDA(cudaLaunchKernelEx(&cfg, sk_tma_kernel<PHASE>, scores, b, k, ld, iel, smax_c, alpha_c, ws.upart, ws.kpad, codes,
+                                 ldc, ws.smax_part, inv_b, g.nst, g.rowf));
+  } else {
+    sk_tma_kernel<PHASE><<<grid, (kSkConsumers + 1) * 32, g.smem, s>>>(scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart,
+                                                                       ws.kpad, codes, ldc, ws.smax_part, inv_b, g.nst, g.rowf);
+  }
 #endif
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
@@ -615,13 +647,14 @@ int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, f
     }
     SSVB_LAUNCH_CHECK();
     for (int it = 1; it < n_iters; ++it) {
-      if (fast) SSVB_TRY(sk_launch_fast<1>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
+      if (fast) SSVB_TRY(sk_launch_fast<1>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b, true));
       else SSVB_TRY(sk_launch<1>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
       sk_alpha_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, kSkSlices), 0, s>>>(ws.upart, fast ? fgrid : ws.grid, ws.kpad, kk, ws.alpha);
       SSVB_LAUNCH_CHECK();
     }
   }
-  if (fast) SSVB_TRY(sk_launch_fast<2>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
+  // (n_iters == 0: the final pass follows a fill kernel without the launch_dependents trigger - plain launch)
+  if (fast) SSVB_TRY(sk_launch_fast<2>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b, n_iters > 0));
   else SSVB_TRY(sk_launch<2>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
   return SSVB_OK;
 }

@@ -36,6 +36,17 @@ for k in (300, 302, 3000):       # TMA-ring fast path (k % 4 == 0) and the gener
     run(f"DistributedSwavLoss k={k}", lambda: DistributedSwavLoss()(z1, z2, pc, bank))
     codes = S.SwavLoss(0.1, 0.05, 3).compute_codes_sinkhorn((z1.detach() @ pc.detach().t()).contiguous())
     torch.cuda.synchronize()
+# round 2: wide rows (KB = 4 kernels), split-K SwAV gradients, the split DinoLoss path, fused-normalise losses, SeLA
+aw, bw = rn(150, 200).requires_grad_(True), rn(150, 200).requires_grad_(True)
+run("SimclrLoss d=200", lambda: S.SimclrLoss(True, 0.5)(aw, bw))
+run("MocoLoss d=200", lambda: S.MocoLoss(True, 0.07)(aw, bw, F.normalize(rn(700, 200))))
+z1b, z2b = F.normalize(rn(200, 96)).requires_grad_(True), F.normalize(rn(200, 96)).requires_grad_(True)
+pcb = F.normalize(rn(1000, 96)).requires_grad_(True)
+run("SwavLoss split-K", lambda: S.SwavLoss()(z1b, z2b, pcb, F.normalize(rn(1000, 96))))
+tb, sb = rn(130, 2, 1000), rn(130, 5, 1000).requires_grad_(True)
+run("DinoLoss split path", lambda: S.DinoLoss()(tb, sb, 0.1, 0.04, 0.1 * rn(1000)))
+run("NormalizedMSELoss", lambda: S.NormalizedMSELoss()(a, b.detach()))
+S.SelaLabeler(30, 70, 25.0).step(rn(70, 30), 5)
 run("MSELoss", lambda: S.MSELoss()(a, b.detach()))
 run("SimSiamLoss", lambda: S.SimSiamLoss()(a, b))
 t, s = rn(9, 2, 1000), rn(9, 5, 1000).requires_grad_(True)
