@@ -135,6 +135,7 @@ def time_graph(fn, reps, flush):
         return None
 
 
+PROFILE_ONLY = False   # --profile: minimal launch count per row (for ncu)
 TIMELINE = None   # file object: when set, legs() also prints the kernel timeline of one graph replay of each row
 
 
@@ -253,6 +254,15 @@ def run_all(dev=None, reps=20, cpu=True, ref_gpu=True, only=None, emit=None):
 
     def legs(ours, samples, ref_cpu=None, port_cpu=None, ref_cuda=None, reps_=None, **kw):
         rp = reps_ or reps
+        if PROFILE_ONLY:   # under ncu: two eager steps per row and nothing else (every launch is replayed by the profiler)
+            ours()
+            l2_flush(flush)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ours()
+            e1.record()
+            e1.synchronize()
+            return dict(ms=e0.elapsed_time(e1), graph_ms=None, ref_ms=None, cpu_res=None, samples=samples, **kw)
         ms = time_gpu(ours, rp, flush)
         gms = time_graph(ours, rp, flush)
         host_us = time_host(ours)
@@ -558,8 +568,12 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--only", default=None, help="comma-separated row tags (cfg1,cfg2,cfg3,cfg4,swav,rowdot128,...)")
     ap.add_argument("--timeline", default=None, help="also write the per-kernel timeline of one graph replay per row here")
+    ap.add_argument("--profile", action="store_true", help="two eager steps per row and nothing else (run under ncu)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
+    if args.profile:
+        global PROFILE_ONLY
+        PROFILE_ONLY = True
     if args.timeline:
         global TIMELINE
         TIMELINE = open(args.timeline, "w")

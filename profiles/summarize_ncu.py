@@ -67,10 +67,11 @@ def report(path):
 
 
 def metrics(path):
-    """Per-kernel means of every metric in a `ncu --metrics a,b,c --csv` log (one line per launch and metric)."""
+    """Per-kernel means of every metric in a `ncu --metrics a,b,c --csv` log (one line per launch and metric).  Launches
+    of one kernel on very different problem sizes (durations more than 1.8x apart) are listed as separate groups."""
     rows = list(csv.reader(open(path, errors="ignore")))
     hdr = None
-    per = collections.OrderedDict()   # kernel -> metric -> [values]
+    per = collections.OrderedDict()   # (kernel, launch id) -> metric -> value
     for r in rows:
         if "Kernel Name" in r:
             hdr = r
@@ -83,8 +84,7 @@ def metrics(path):
                 continue
             u = d["Metric Unit"]
             scale = {"ns": 1e-3, "nsecond": 1e-3, "ms": 1e3, "msecond": 1e3, "Kbyte": 1e-3, "Gbyte": 1e3, "byte": 1e-6}.get(u, 1.0)
-            per.setdefault(d["Kernel Name"].split("(")[0][:60], collections.OrderedDict()).setdefault(
-                d["Metric Name"], []).append(v * scale)
+            per.setdefault((d["Kernel Name"].split("(")[0][:60], d["ID"]), collections.OrderedDict())[d["Metric Name"]] = v * scale
     names = []
     for m in per.values():
         for k in m:
@@ -94,11 +94,27 @@ def metrics(path):
              "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_%", "lts__t_sector_hit_rate.pct": "l2hit_%",
              "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_%", "launch__grid_size": "grid",
              "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_%"}
-    print(f"# ncu --metrics ... --clock-control none : {path}   (means over the launches of each kernel; time in us, bytes in MB)")
-    print(f"{'kernel':62s} {'n':>4s} " + " ".join(f"{short.get(k, k[:10]):>9s}" for k in names))
-    for kname, m in sorted(per.items(), key=lambda kv: -sum(kv[1].get("gpu__time_duration.sum", [0]))):
-        n = len(next(iter(m.values())))
-        print(f"{kname:62s} {n:4d} " + " ".join(f"{(sum(m[k]) / len(m[k]) if k in m else float('nan')):9.2f}" for k in names))
+    by_kernel = collections.OrderedDict()
+    for (kname, _), m in per.items():
+        by_kernel.setdefault(kname, []).append(m)
+    groups = []
+    for kname, launches_ in by_kernel.items():
+        launches_.sort(key=lambda m: m.get("gpu__time_duration.sum", 0.0))
+        cur = [launches_[0]]
+        for m in launches_[1:]:
+            if m.get("gpu__time_duration.sum", 0.0) > 1.8 * cur[-1].get("gpu__time_duration.sum", 1e-9):
+                groups.append((kname, cur))
+                cur = []
+            cur.append(m)
+        groups.append((kname, cur))
+    print(f"# ncu --metrics ... --clock-control none : {path}   (means over the launches of each kernel / size group; time in us, "
+          "bytes in MB, GB/s = (rd + wr) / time; cold cache and serialised launches: compare with the in-graph timelines)")
+    print(f"{'kernel':62s} {'n':>4s} " + " ".join(f"{short.get(k, k[:10]):>9s}" for k in names) + f" {'GB/s':>9s}")
+    mean = lambda g, k: sum(m.get(k, 0.0) for m in g) / len(g)  # noqa: E731
+    for kname, g in sorted(groups, key=lambda kg: -mean(kg[1], "gpu__time_duration.sum") * len(kg[1])):
+        t = mean(g, "gpu__time_duration.sum")
+        bw = (mean(g, "dram__bytes_read.sum") + mean(g, "dram__bytes_write.sum")) / t * 1e3 if t > 0 else float("nan")
+        print(f"{kname:62s} {len(g):4d} " + " ".join(f"{mean(g, k):9.2f}" for k in names) + f" {bw:9.0f}")
 
 
 if __name__ == "__main__":
