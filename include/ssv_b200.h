@@ -15,7 +15,9 @@
  *  - `saved` is an opaque blob written by `*_fwd` and read by the matching `*_bwd`
  *    (size from `*_saved_bytes`); `workspace` is scratch (size from `*_workspace_bytes`);
  *  - all work is enqueued asynchronously on `stream` (a `cudaStream_t`); no host sync, no
- *    global mutable state: entry points are re-entrant (autograd calls bwd from its own thread);
+ *    global mutable state that affects results: entry points are re-entrant (autograd calls bwd from its own thread;
+ *    the library only memoises - a per-thread cache of encoded TMA descriptors, per-kernel attribute bits - and
+ *    keeps the opt-in profiling counters of ssvb_profile_enable);
  *  - `loss` and `grad_out` are device scalars (fp32) so no device->host sync is ever needed;
  *  - return 0 on success, <0 for argument errors detected before launch (see codes),
  *    >0 = a `cudaError_t`.  No exceptions, no exit(), no CPU fallback: on a non-sm_100

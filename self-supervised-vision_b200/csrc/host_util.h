@@ -51,6 +51,39 @@ inline PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+// Small per-thread cache of encoded tensor maps keyed on everything that goes into the encoding.  A descriptor is a
+// pure function of (pointer, shape, stride, box, type): the losses are called with the same buffers step after step
+// (torch's caching allocator hands the same blocks back), and each cuTensorMapEncodeTiled costs 1-2 us of the
+// launch-bound small-shape path (four encodes per NT-Xent fwd+bwd).
+struct TmapKey {
+  const void* ptr;
+  int64_t rows, cols, ld;
+  int box_rows, kind;  // kind: 0 bf16 operand, 1 fp16 operand, 2 fp32 output, 3 bf16 output
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && kind == o.kind;
+  }
+};
+struct TmapCache {
+  static constexpr int N = 32;
+  TmapKey keys[N];
+  CUtensorMap maps[N];
+  int used = 0, next = 0;
+  const CUtensorMap* find(const TmapKey& k) const {
+    for (int i = 0; i < used; ++i)
+      if (keys[i] == k) return &maps[i];
+    return nullptr;
+  }
+  void put(const TmapKey& k, const CUtensorMap& m) {
+    const int i = used < N ? used++ : (next++ % N);
+    keys[i] = k;
+    maps[i] = m;
+  }
+};
+inline TmapCache& tmap_cache() {
+  static thread_local TmapCache c;
+  return c;
+}
+
 // bf16 row-major [rows x cols], leading dimension ld (elements, ld*2 % 16 == 0).
 // Box = 64 columns (128 B, SWIZZLE_128B) x box_rows rows; out-of-bounds reads are zero-filled.
 inline int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
@@ -58,6 +91,11 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return SSVB_ERR_DRIVER;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return SSVB_ERR_ALIGNMENT;
+  const TmapKey key{ptr, rows, cols, ld, box_rows, fp16 ? 1 : 0};
+  if (const CUtensorMap* hit = tmap_cache().find(key)) {
+    *out = *hit;
+    return SSVB_OK;
+  }
   // the driver call needs a context bound to THIS thread; autograd's backward thread may not have touched the runtime
   // yet.  cudaFree(0) binds the primary context of the current device (once per thread; the retry below stays as a net).
   static thread_local bool ctx_bound = false;
@@ -85,6 +123,7 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64
     fprintf(stderr, "[ssv_b200] cuTensorMapEncodeTiled -> %d (ptr=%p rows=%lld cols=%lld ld=%lld box_rows=%d)\n",
             static_cast<int>(r), ptr, static_cast<long long>(rows), static_cast<long long>(cols),
             static_cast<long long>(ld), box_rows);
+  if (r == CUDA_SUCCESS) tmap_cache().put(key, *out);
   return r == CUDA_SUCCESS ? SSVB_OK : SSVB_ERR_DRIVER;
 }
 
@@ -95,6 +134,11 @@ inline int make_tmap_out(CUtensorMap* out, const void* ptr, int64_t rows, int64_
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return SSVB_ERR_DRIVER;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * elem_bytes) & 15)) return SSVB_ERR_ALIGNMENT;
+  const TmapKey key{ptr, rows, cols, ld, 32, elem_bytes == 4 ? 2 : 3};
+  if (const CUtensorMap* hit = tmap_cache().find(key)) {
+    *out = *hit;
+    return SSVB_OK;
+  }
   static thread_local bool ctx_bound = false;
   if (!ctx_bound) {
     cudaFree(nullptr);
@@ -111,6 +155,7 @@ inline int make_tmap_out(CUtensorMap* out, const void* ptr, int64_t rows, int64_
     fprintf(stderr, "[ssv_b200] cuTensorMapEncodeTiled(out) -> %d (ptr=%p rows=%lld cols=%lld ld=%lld eb=%d)\n",
             static_cast<int>(r), ptr, static_cast<long long>(rows), static_cast<long long>(cols),
             static_cast<long long>(ld), elem_bytes);
+  if (r == CUDA_SUCCESS) tmap_cache().put(key, *out);
   return r == CUDA_SUCCESS ? SSVB_OK : SSVB_ERR_DRIVER;
 }
 
