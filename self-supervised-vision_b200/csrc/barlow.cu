@@ -171,9 +171,8 @@ __global__ void col_partials_kernel(const float* __restrict__ x, int64_t ldx, co
 
 // Forward statistics, float4 version of MODE 0: block (32, 8) covers 128 columns (one float4 per thread and row), eight
 // rows in flight per thread; same shifted sums and the same partial layout [stripe][2][d].
-__global__ void __launch_bounds__(256)
-col_stats4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row, int64_t n, int d,
-                  float* __restrict__ part) {
+__device__ __forceinline__ void col_stats4_body(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row,
+                                                int64_t n, int d, float* __restrict__ part) {
   const int c4 = blockIdx.x * 32 + threadIdx.x;
   const int stripe = blockIdx.y;
   const int64_t rows_per = (n + gridDim.y - 1) / gridDim.y;
@@ -220,6 +219,28 @@ col_stats4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
   }
 }
 
+__global__ void __launch_bounds__(256)
+col_stats4_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row, int64_t n, int d,
+                  float* __restrict__ part) {
+  col_stats4_body(x, ldx, inv_row, n, d, part);
+}
+// Both views of the Barlow forward in ONE launch (view = blockIdx.z / blockIdx.y of the kernels below): the launch ramp,
+// tail and dependency gap of three kernels are paid once instead of twice (profiles/r2_tuning_log.md §6).
+struct TwoViews {
+  const float *x0, *x1;      // [n x d] fp32 rows
+  int64_t ld0, ld1;
+  const float *inv0, *inv1;  // row 1/norm or nullptr
+};
+struct TwoStats {
+  float *mean0, *rstd0, *mean1, *rstd1;  // [d] each
+};
+__global__ void __launch_bounds__(256)
+col_stats4_x2_kernel(TwoViews v, int64_t n, int d, float* __restrict__ part, int64_t view_stride) {
+  const bool second = blockIdx.z != 0;
+  col_stats4_body(second ? v.x1 : v.x0, second ? v.ld1 : v.ld0, second ? v.inv1 : v.inv0, n, d,
+                  part + (second ? view_stride : 0));
+}
+
 // MODE 0: mean, 1/std (unbiased)   MODE 1: mean_0(dT), sum_0(dT x~)/(n-1)
 template <int MODE>
 __global__ void col_finalize_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ x,
@@ -244,10 +265,35 @@ __global__ void col_finalize_kernel(const float* __restrict__ part, int nsplit, 
   }
 }
 
+// forward statistics of both views: blockIdx.y = view
+__global__ void col_finalize_x2_kernel(const float* __restrict__ part, int64_t view_stride, int nsplit, TwoViews v, int64_t n,
+                                       int d, TwoStats st) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= d) return;
+  const bool second = blockIdx.y != 0;
+  part += second ? view_stride : 0;
+  const float* x = second ? v.x1 : v.x0;
+  const float* inv_row = second ? v.inv1 : v.inv0;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < nsplit; ++i) {
+    s1 += part[(static_cast<int64_t>(i) * 2 + 0) * d + col];
+    s2 += part[(static_cast<int64_t>(i) * 2 + 1) * d + col];
+  }
+  const float fn = static_cast<float>(n);
+  const float v0 = x[col] * (inv_row ? inv_row[0] : 1.f);
+  const float var = (s2 - s1 * s1 / fn) / (fn - 1.f);
+  (second ? st.mean1 : st.mean0)[col] = v0 + s1 / fn;
+  (second ? st.rstd1 : st.rstd0)[col] = rsqrtf(var);
+}
+
 // MODE 1 finalize for MANY stripes (the GEMM epilogue's partials: one stripe per 32 rows): block (32 columns x 8 stripe
 // phases), fixed-order combine.  out0 = mean_0(dT), out1 = sum_0(dT x~) / (n - 1).
 __global__ void col_finalize_wide_kernel(const float* __restrict__ part, int nsplit, int64_t n, int d,
-                                         float* __restrict__ out0, float* __restrict__ out1) {
+                                         float* __restrict__ out0, float* __restrict__ out1, int64_t part_view_stride = 0) {
+  // blockIdx.y = view (two-view launch): partials `part_view_stride` apart, outputs [out0 | out1] pairs 2 * d apart
+  part += blockIdx.y * part_view_stride;
+  out0 += blockIdx.y * 2 * static_cast<int64_t>(d);
+  out1 += blockIdx.y * 2 * static_cast<int64_t>(d);
   __shared__ float sh1[8][33], sh2[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   float s1 = 0.f, s2 = 0.f;
@@ -271,9 +317,9 @@ __global__ void col_finalize_wide_kernel(const float* __restrict__ part, int nsp
 }
 
 // x~ = (x * inv_row - mean) * rstd  -> bf16 [n x d]
-__global__ void standardize_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row,
-                                   const float* __restrict__ mean, const float* __restrict__ rstd, int64_t n, int d4,
-                                   __nv_bfloat16* __restrict__ out, int64_t ldo) {
+__device__ __forceinline__ void standardize_body(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row,
+                                                 const float* __restrict__ mean, const float* __restrict__ rstd, int64_t n,
+                                                 int d4, __nv_bfloat16* __restrict__ out, int64_t ldo) {
   const int64_t total = n * d4;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -292,6 +338,19 @@ __global__ void standardize_kernel(const float* __restrict__ x, int64_t ldx, con
   }
 }
 
+__global__ void standardize_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row,
+                                   const float* __restrict__ mean, const float* __restrict__ rstd, int64_t n, int d4,
+                                   __nv_bfloat16* __restrict__ out, int64_t ldo) {
+  standardize_body(x, ldx, inv_row, mean, rstd, n, d4, out, ldo);
+}
+// both views: blockIdx.y = view; outputs `out_view_stride` elements apart
+__global__ void standardize_x2_kernel(TwoViews v, TwoStats st, int64_t n, int d4, __nv_bfloat16* __restrict__ out,
+                                      int64_t out_view_stride, int64_t ldo) {
+  const bool second = blockIdx.y != 0;
+  standardize_body(second ? v.x1 : v.x0, second ? v.ld1 : v.ld0, second ? v.inv1 : v.inv0, second ? st.mean1 : st.mean0,
+                   second ? st.rstd1 : st.rstd0, n, d4, out + (second ? out_view_stride : 0), ldo);
+}
+
 // one block per row: dx^ = (dT - m1 - x~ m2) * rstd * grad_out, then (optionally) the row-normalise backward.
 // float4 traffic throughout (d % 8 == 0 and 16-byte aligned rows are checked by the entry points).
 __device__ __forceinline__ float4 barlow_g4(const float4 xv, const float4 dtv, const float4 mu, const float4 rs,
@@ -305,11 +364,11 @@ __device__ __forceinline__ float4 barlow_g4(const float4 xv, const float4 dtv, c
   g.w = (dtv.w - a1.w - (xh.w - mu.w) * rs.w * a2.w) * rs.w * go;
   return g;
 }
-__global__ void barlow_finish_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row,
-                                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                                     const float* __restrict__ dt, int64_t lddt, const float* __restrict__ m1,
-                                     const float* __restrict__ m2, int d, const float* __restrict__ grad_out,
-                                     float* __restrict__ dx, int64_t lddx) {
+__device__ __forceinline__ void barlow_finish_body(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row,
+                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                   const float* __restrict__ dt, int64_t lddt, const float* __restrict__ m1,
+                                                   const float* __restrict__ m2, int d, const float* __restrict__ grad_out,
+                                                   float* __restrict__ dx, int64_t lddx) {
   const int64_t r = blockIdx.x;
   const float go = __ldg(grad_out);
   const float sc = inv_row ? inv_row[r] : 1.f;
@@ -347,6 +406,29 @@ __global__ void barlow_finish_kernel(const float* __restrict__ x, int64_t ldx, c
     dx4[c] = g;
   }
 }
+
+__global__ void barlow_finish_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ inv_row,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const float* __restrict__ dt, int64_t lddt, const float* __restrict__ m1,
+                                     const float* __restrict__ m2, int d, const float* __restrict__ grad_out,
+                                     float* __restrict__ dx, int64_t lddx) {
+  barlow_finish_body(x, ldx, inv_row, mean, rstd, dt, lddt, m1, m2, d, grad_out, dx, lddx);
+}
+// both views in one launch: blockIdx.y = view; colred = [m1_i | m2_i | m1_j | m2_j]
+struct TwoGrads {
+  const float *dt0, *dt1;  // [n x d] fp32, leading dimension lddt
+  float *dx0, *dx1;
+  int64_t lddx0, lddx1;
+};
+__global__ void barlow_finish_x2_kernel(TwoViews v, TwoStats st, TwoGrads g, int64_t lddt, const float* __restrict__ colred,
+                                        int d, const float* __restrict__ grad_out) {
+  const bool second = blockIdx.y != 0;
+  const float* cr = colred + (second ? 2 * static_cast<int64_t>(d) : 0);
+  barlow_finish_body(second ? v.x1 : v.x0, second ? v.ld1 : v.ld0, second ? v.inv1 : v.inv0, second ? st.mean1 : st.mean0,
+                     second ? st.rstd1 : st.rstd0, second ? g.dt1 : g.dt0, lddt, cr, cr + d, d, grad_out,
+                     second ? g.dx1 : g.dx0, second ? g.lddx1 : g.lddx0);
+}
+
 
 // ---- distributed (batch rows sharded over ranks) -------------------------------------------------------------
 // local column statistics of one rank: out0 = local mean, out1 = local M2 = sum_r (x - mean_local)^2
@@ -558,6 +640,36 @@ int stats_and_standardize(const float* x, int64_t ld, int normalize, int64_t n, 
   return SSVB_OK;
 }
 
+// forward pre-pass of BOTH views in three launches (statistics, finalize, standardize); `xi` heads the two standardised
+// operands (`x_view_stride` elements apart)
+int stats_and_standardize_x2(const float* zi, int64_t ld_zi, const float* zj, int64_t ld_zj, int normalize, int64_t n,
+                             int64_t d, float* inv_i, float* inv_j, TwoStats st, __nv_bfloat16* xi, int64_t x_view_stride,
+                             float* colpart, int64_t part_view_stride, cudaStream_t s) {
+  TwoViews v{zi, zj, ld_zi, ld_zj, nullptr, nullptr};
+  if (normalize) {
+    row_invnorm_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(zi, n, static_cast<int>(d), ld_zi, inv_i);
+    SSVB_LAUNCH_CHECK();
+    row_invnorm_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, s>>>(zj, n, static_cast<int>(d), ld_zj, inv_j);
+    SSVB_LAUNCH_CHECK();
+    v.inv0 = inv_i;
+    v.inv1 = inv_j;
+  }
+  dim3 grid(static_cast<unsigned>(ceil_div(d, 128)), kStatSplit, 2), block(32, 8);
+  col_stats4_x2_kernel<<<grid, block, 0, s>>>(v, n, static_cast<int>(d), colpart, part_view_stride);
+  SSVB_LAUNCH_CHECK();
+  col_finalize_x2_kernel<<<dim3(static_cast<unsigned>(ceil_div(d, 256)), 2), 256, 0, s>>>(colpart, part_view_stride, kStatSplit, v,
+                                                                                          n, static_cast<int>(d), st);
+  SSVB_LAUNCH_CHECK();
+  const int64_t total = n * (d / 4);
+  int64_t g = ceil_div(total, 256 * 4);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;  // x 2 views = 16 resident-CTA waves' worth, as in the one-view form
+  if (g > cap) g = cap;
+  standardize_x2_kernel<<<dim3(static_cast<unsigned>(g), 2), 256, 0, s>>>(v, st, n, static_cast<int>(d / 4), xi, x_view_stride,
+                                                                        d);
+  SSVB_LAUNCH_CHECK();
+  return SSVB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -583,9 +695,16 @@ int ssvb_barlow_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   BarlowSaved sv = barlow_saved(saved, n, d);
   BarlowWs ws = barlow_ws(workspace, n, d);
-  SSVB_TRY(stats_and_standardize(zi, ld_zi, normalize, n, d, sv.inv_i, sv.mean_i, sv.rstd_i, sv.xi, ws.colpart, s));
-  SSVB_TRY(stats_and_standardize(zj, ld_zj, normalize, n, d, sv.inv_j, sv.mean_j, sv.rstd_j, sv.xj,
-                                 ws.colpart + ws.view_stride, s));
+  static const bool no_x2 = getenv("SSVB_BARLOW_NO_X2") != nullptr;  // A/B switch: one view per launch
+  if (no_x2) {
+    SSVB_TRY(stats_and_standardize(zi, ld_zi, normalize, n, d, sv.inv_i, sv.mean_i, sv.rstd_i, sv.xi, ws.colpart, s));
+    SSVB_TRY(stats_and_standardize(zj, ld_zj, normalize, n, d, sv.inv_j, sv.mean_j, sv.rstd_j, sv.xj,
+                                   ws.colpart + ws.view_stride, s));
+  } else {
+    SSVB_TRY(stats_and_standardize_x2(zi, ld_zi, zj, ld_zj, normalize, n, d, sv.inv_i, sv.inv_j,
+                                      TwoStats{sv.mean_i, sv.rstd_i, sv.mean_j, sv.rstd_j}, sv.xi, sv.xj - sv.xi, ws.colpart,
+                                      ws.view_stride, s));
+  }
   // C = Xi~^T Xj~ / n : contraction over the batch axis, both operands MN-major in place
   GemmParams p{};
   p.M = static_cast<int>(d);
@@ -657,17 +776,29 @@ int ssvb_barlow_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
     SSVB_LAUNCH_CHECK();
   }
   const unsigned fgrid = static_cast<unsigned>(ceil_div(d, 32));
-  col_finalize_wide_kernel<<<fgrid, dim3(32, 8), 0, s>>>(part_i, nsplit, n, static_cast<int>(d), ws.colred, ws.colred + d);
+  static const bool no_x2 = getenv("SSVB_BARLOW_NO_X2") != nullptr;  // A/B switch: one view per launch
+  if (no_x2) {
+    col_finalize_wide_kernel<<<fgrid, dim3(32, 8), 0, s>>>(part_i, nsplit, n, static_cast<int>(d), ws.colred, ws.colred + d);
+    SSVB_LAUNCH_CHECK();
+    col_finalize_wide_kernel<<<fgrid, dim3(32, 8), 0, s>>>(part_j, nsplit, n, static_cast<int>(d), ws.colred + 2 * d,
+                                                           ws.colred + 3 * d);
+    SSVB_LAUNCH_CHECK();
+    barlow_finish_kernel<<<static_cast<unsigned>(n), 256, 0, s>>>(zi, ld_zi, inv_i, sv.mean_i, sv.rstd_i, ws.dti, d, ws.colred,
+                                                                ws.colred + d, static_cast<int>(d), grad_out, dzi, ld_dzi);
+    SSVB_LAUNCH_CHECK();
+    barlow_finish_kernel<<<static_cast<unsigned>(n), 256, 0, s>>>(zj, ld_zj, inv_j, sv.mean_j, sv.rstd_j, ws.dtj, d,
+                                                                ws.colred + 2 * d, ws.colred + 3 * d, static_cast<int>(d),
+                                                                grad_out, dzj, ld_dzj);
+    SSVB_LAUNCH_CHECK();
+    return SSVB_OK;
+  }
+  // both views per launch (colred = [mean dTi | sum dTi x~i | mean dTj | sum dTj x~j])
+  col_finalize_wide_kernel<<<dim3(fgrid, 2), dim3(32, 8), 0, s>>>(part_i, nsplit, n, static_cast<int>(d), ws.colred,
+                                                                  ws.colred + d, ws.view_stride);
   SSVB_LAUNCH_CHECK();
-  col_finalize_wide_kernel<<<fgrid, dim3(32, 8), 0, s>>>(part_j, nsplit, n, static_cast<int>(d), ws.colred + 2 * d,
-                                                         ws.colred + 3 * d);
-  SSVB_LAUNCH_CHECK();
-  barlow_finish_kernel<<<static_cast<unsigned>(n), 256, 0, s>>>(zi, ld_zi, inv_i, sv.mean_i, sv.rstd_i, ws.dti, d, ws.colred,
-                                                              ws.colred + d, static_cast<int>(d), grad_out, dzi, ld_dzi);
-  SSVB_LAUNCH_CHECK();
-  barlow_finish_kernel<<<static_cast<unsigned>(n), 256, 0, s>>>(zj, ld_zj, inv_j, sv.mean_j, sv.rstd_j, ws.dtj, d,
-                                                              ws.colred + 2 * d, ws.colred + 3 * d, static_cast<int>(d),
-                                                              grad_out, dzj, ld_dzj);
+  barlow_finish_x2_kernel<<<dim3(static_cast<unsigned>(n), 2), 256, 0, s>>>(
+      TwoViews{zi, zj, ld_zi, ld_zj, inv_i, inv_j}, TwoStats{sv.mean_i, sv.rstd_i, sv.mean_j, sv.rstd_j},
+      TwoGrads{ws.dti, ws.dtj, dzi, dzj, ld_dzi, ld_dzj}, d, ws.colred, static_cast<int>(d), grad_out);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }

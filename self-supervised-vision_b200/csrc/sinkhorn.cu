@@ -18,13 +18,16 @@ struct SkWs {
   float* smax_part;  // [grid]
   float* smax;       // [1]
   float* upart;      // [grid x kpad]
-  float* alpha;      // [kpad]
+  float* alpha;      // [kSkMaxProb x kpad]  (one scaling vector per batched problem)
   unsigned int* counter;
   size_t bytes;
   int grid;
   int kpad;
 };
 inline int sk_grid() { return num_sms() * 2; }
+// Independent problems of one shape run in ONE launch per pass (SwAV: the two views' score matrices): problem p = blockIdx.y
+// takes its own rows / alpha / smax / partial rows; the CTAs of a launch are split evenly between the problems.
+constexpr int kSkMaxProb = 2;
 SkWs sk_ws(void* base, int64_t k) {
   Carver c(base);
   SkWs w;
@@ -33,7 +36,7 @@ SkWs sk_ws(void* base, int64_t k) {
   w.smax_part = c.take<float>(w.grid);
   w.smax = c.take<float>(4);
   w.upart = c.take<float>(static_cast<size_t>(w.grid) * w.kpad);
-  w.alpha = c.take<float>(w.kpad);
+  w.alpha = c.take<float>(static_cast<size_t>(kSkMaxProb) * w.kpad);
   w.counter = c.take<unsigned int>(4);
   w.bytes = c.used();
   return w;
@@ -80,6 +83,8 @@ constexpr int kSkSlices = 32;  // row slices per column group in the alpha kerne
 __global__ void sk_alpha_kernel(const float* __restrict__ upart, int grid, int kpad, int k, float* __restrict__ alpha,
                                 int raw = 0) {
   pdl_launch_dependents();  // the next pass may start streaming score rows now; it waits before it reads alpha
+  upart += static_cast<size_t>(blockIdx.y) * grid * kpad;  // batched problems: blockIdx.y (0 for a single problem)
+  alpha += static_cast<size_t>(blockIdx.y) * kpad;
   __shared__ float sh[kSkSlices][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float u = 0.f;
@@ -102,6 +107,10 @@ __global__ void sk_alpha0_kernel(const float* __restrict__ upart, const float* _
                                  int k, float inv_eps_log2e, float* __restrict__ alpha, float* __restrict__ smax,
                                  int raw = 0) {
   pdl_launch_dependents();  // (see sk_alpha_kernel)
+  upart += static_cast<size_t>(blockIdx.y) * grid * kpad;  // batched problems: blockIdx.y (0 for a single problem)
+  mpart += static_cast<size_t>(blockIdx.y) * grid;
+  alpha += static_cast<size_t>(blockIdx.y) * kpad;
+  smax += blockIdx.y;
   __shared__ float sh[kSkSlices][33];
   __shared__ float msh[32];
   const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -376,8 +385,18 @@ template <int PHASE>
 __global__ void __launch_bounds__((kSkConsumers + 1) * 32, 1)
 sk_tma_kernel(const float* __restrict__ s, int64_t b, int k, int64_t ld, float inv_eps_log2e,
               const float* __restrict__ smax, const float* __restrict__ alpha, float* __restrict__ upart, int kpad,
-              float* __restrict__ codes, int64_t ldc, float* __restrict__ mpart, float inv_b, int nst, int rowf) {
+              float* __restrict__ codes, int64_t ldc, float* __restrict__ mpart, float inv_b, int nst, int rowf,
+              int64_t pstride_s, int64_t pstride_c) {
   extern __shared__ __align__(128) float sk_smem[];  // [nst][rowf] ring | [kpad] alpha | 2*nst + 1 mbarriers
+  if (gridDim.y > 1) {  // batched independent problems (same b, k): problem blockIdx.y, gridDim.x CTAs each
+    const size_t pb = blockIdx.y;
+    s += pb * pstride_s;
+    codes += pb * pstride_c;
+    smax += pb;
+    alpha += pb * kpad;
+    upart += pb * gridDim.x * kpad;
+    mpart += pb * gridDim.x;
+  }
   float* ring = sk_smem;
   float* alpha_s = sk_smem + static_cast<size_t>(nst) * rowf;
   uint64_t* full = reinterpret_cast<uint64_t*>(alpha_s + kpad);
@@ -552,7 +571,8 @@ inline SkRing sk_ring(int kpad) {
 }
 template <int PHASE>
 int sk_launch_fast(int grid, size_t smem_unused, cudaStream_t s, const float* scores, int64_t b, int k, int64_t ld, float iel,
-                   const SkWs& ws, float* codes, int64_t ldc, float inv_b, bool pdl = false) {
+                   const SkWs& ws, float* codes, int64_t ldc, float inv_b, bool pdl = false, int nprob = 1,
+                   int64_t pstride_s = 0, int64_t pstride_c = 0) {
   (void)smem_unused;
 #ifdef SSVB_SK_ROWREG  // previous fast path (global loads straight into registers), kept for A/B timing
   const size_t smem = static_cast<size_t>(9) * ws.kpad * 4;
@@ -566,7 +586,7 @@ int sk_launch_fast(int grid, size_t smem_unused, cudaStream_t s, const float* sc
   if (pdl && PHASE != 0 && !no_pdl) {
     // programmatic dependent launch behind the alpha kernel: prologue + first ring-full of rows overlap it
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.gridDim = dim3(static_cast<unsigned>(grid), static_cast<unsigned>(nprob));
     cfg.blockDim = dim3((kSkConsumers + 1) * 32);
     cfg.dynamicSmemBytes = g.smem;
     cfg.stream = s;
@@ -578,10 +598,11 @@ int sk_launch_fast(int grid, size_t smem_unused, cudaStream_t s, const float* sc
     const float* smax_c = ws.smax;
     const float* alpha_c = ws.alpha;
     SSVB_CUDA(cudaLaunchKernelEx(&cfg, sk_tma_kernel<PHASE>, scores, b, k, ld, iel, smax_c, alpha_c, ws.upart, ws.kpad, codes,
-                                 ldc, ws.smax_part, inv_b, g.nst, g.rowf));
+                                 ldc, ws.smax_part, inv_b, g.nst, g.rowf, pstride_s, pstride_c));
   } else {
-    sk_tma_kernel<PHASE><<<grid, (kSkConsumers + 1) * 32, g.smem, s>>>(scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart,
-                                                                       ws.kpad, codes, ldc, ws.smax_part, inv_b, g.nst, g.rowf);
+    sk_tma_kernel<PHASE><<<dim3(static_cast<unsigned>(grid), static_cast<unsigned>(nprob)), (kSkConsumers + 1) * 32, g.smem, s>>>(
+        scores, b, k, ld, iel, ws.smax, ws.alpha, ws.upart, ws.kpad, codes, ldc, ws.smax_part, inv_b, g.nst, g.rowf, pstride_s,
+        pstride_c);
   }
 #endif
   SSVB_LAUNCH_CHECK();
@@ -609,9 +630,12 @@ int sk_launch(bool regacc, int grid, int threads, size_t smem, cudaStream_t s, c
 }  // namespace
 
 namespace ssvb {
-// shared with swav.cu: scores -> codes on `s`
+// shared with swav.cu: scores -> codes on `s`.  nprob > 1: that many independent problems of the same shape, problem p
+// at scores + p * pstride_s / codes + p * pstride_c (elements).  On the fast path two problems share every launch (each
+// pass and alpha kernel covers both: half of the CTAs per problem), which halves the number of dependent launches of
+// SwAV's two code assignments (utils/losses.py:232); otherwise they run one after the other.
 int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters, float* codes,
-                 int64_t ld_codes, void* workspace, cudaStream_t s) {
+                 int64_t ld_codes, void* workspace, cudaStream_t s, int nprob, int64_t pstride_s, int64_t pstride_c) {
   SkWs ws = sk_ws(workspace, k);
   const int kk = static_cast<int>(k);
   const float iel = SSVB_LOG2E / eps;
@@ -624,37 +648,55 @@ int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, f
   const bool regacc = (nwarp == 8) && (k <= static_cast<int64_t>(kSkJ) * threads);
   const bool fast = (k % 4 == 0) && (k <= 128 * kSkNV) && (ld_scores % 4 == 0) && (ld_codes % 4 == 0) &&
                     !(reinterpret_cast<uintptr_t>(scores) & 15) && !(reinterpret_cast<uintptr_t>(codes) & 15);
+  static const bool no_batch = getenv("SSVB_SK_NO_BATCH") != nullptr;  // A/B switch
+  bool batch = fast && n_iters > 0 && nprob == kSkMaxProb && (pstride_s % 4 == 0) && (pstride_c % 4 == 0) && !no_batch;
+#ifdef SSVB_SK_ROWREG
+  batch = false;
+#endif
+  if (nprob > 1 && !batch) {
+    for (int p = 0; p < nprob; ++p)
+      SSVB_TRY(sinkhorn_run(scores + p * pstride_s, b, k, ld_scores, eps, n_iters, codes + p * pstride_c, ld_codes, workspace,
+                            s, 1, 0, 0));
+    return SSVB_OK;
+  }
+  const int np = batch ? nprob : 1;
   const size_t smem_fast = static_cast<size_t>(9) * ws.kpad * 4;
-  const int fgrid = num_sms();  // one 8-warp CTA per SM; partial rows [fgrid x kpad]
+  // one 8-warp CTA per SM; partial rows [np x fgrid x kpad] (batched: the SMs are split between the problems)
+  const int fgrid = batch ? (num_sms() / np > 0 ? num_sms() / np : 1) : num_sms();
   if (!(fast && n_iters > 0)) {  // the fast path finds the max online inside its first pass
     SSVB_CUDA(cudaMemsetAsync(ws.counter, 0, 16, s));
     sk_max_kernel<<<ws.grid, 256, 0, s>>>(scores, b, kk, ld_scores, ws.smax_part, ws.counter, ws.smax);
     SSVB_LAUNCH_CHECK();
   }
-  const unsigned agrid = static_cast<unsigned>(ceil_div(k, 256));  // (alpha / fill kernels: 256 columns per CTA)
+  const unsigned agrid = static_cast<unsigned>(ceil_div(k, 256));  // (fill kernel: 256 columns per CTA)
+  const dim3 alpha_grid(static_cast<unsigned>(ceil_div(k, 32)), static_cast<unsigned>(np)), alpha_block(32, kSkSlices);
   if (n_iters <= 0) {
     // no iterations: codes = E / rowsum(E)  (alpha = 1)
     fill_kernel<<<agrid, 256, 0, s>>>(ws.alpha, k, 1.f);
     SSVB_LAUNCH_CHECK();
   } else {
     if (fast) {
-      SSVB_TRY(sk_launch_fast<0>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
-      sk_alpha0_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, kSkSlices), 0, s>>>(ws.upart, ws.smax_part, fgrid, ws.kpad,
-                                                                                      kk, iel, ws.alpha, ws.smax);
+      SSVB_TRY(sk_launch_fast<0>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b, false, np,
+                                 pstride_s, pstride_c));
+      sk_alpha0_kernel<<<alpha_grid, alpha_block, 0, s>>>(ws.upart, ws.smax_part, fgrid, ws.kpad, kk, iel, ws.alpha, ws.smax);
     } else {
       SSVB_TRY(sk_launch<0>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
-      sk_alpha_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, kSkSlices), 0, s>>>(ws.upart, ws.grid, ws.kpad, kk, ws.alpha);
+      sk_alpha_kernel<<<alpha_grid, alpha_block, 0, s>>>(ws.upart, ws.grid, ws.kpad, kk, ws.alpha);
     }
     SSVB_LAUNCH_CHECK();
     for (int it = 1; it < n_iters; ++it) {
-      if (fast) SSVB_TRY(sk_launch_fast<1>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b, true));
+      if (fast)
+        SSVB_TRY(sk_launch_fast<1>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b, true, np,
+                                   pstride_s, pstride_c));
       else SSVB_TRY(sk_launch<1>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
-      sk_alpha_kernel<<<static_cast<unsigned>(ceil_div(k, 32)), dim3(32, kSkSlices), 0, s>>>(ws.upart, fast ? fgrid : ws.grid, ws.kpad, kk, ws.alpha);
+      sk_alpha_kernel<<<alpha_grid, alpha_block, 0, s>>>(ws.upart, fast ? fgrid : ws.grid, ws.kpad, kk, ws.alpha);
       SSVB_LAUNCH_CHECK();
     }
   }
   // (n_iters == 0: the final pass follows a fill kernel without the launch_dependents trigger - plain launch)
-  if (fast) SSVB_TRY(sk_launch_fast<2>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b, n_iters > 0));
+  if (fast)
+    SSVB_TRY(sk_launch_fast<2>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b, n_iters > 0, np,
+                               pstride_s, pstride_c));
   else SSVB_TRY(sk_launch<2>(regacc, ws.grid, threads, smem, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b));
   return SSVB_OK;
 }
@@ -738,7 +780,7 @@ int ssvb_sinkhorn(const float* scores, int64_t b, int64_t k, int64_t ld_scores, 
     return SSVB_ERR_INVALID;
   if (workspace_bytes < sk_ws(nullptr, k).bytes) return SSVB_ERR_WORKSPACE;
   return sinkhorn_run(scores, b, k, ld_scores, eps, n_iters, codes, ld_codes, workspace,
-                      static_cast<cudaStream_t>(stream));
+                      static_cast<cudaStream_t>(stream), 1, 0, 0);
 }
 
 // ---- distributed (sample rows sharded over ranks): see include/ssv_b200.h

@@ -14,7 +14,7 @@
 
 namespace ssvb {
 int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters, float* codes,
-                 int64_t ld_codes, void* workspace, cudaStream_t s);
+                 int64_t ld_codes, void* workspace, cudaStream_t s, int nprob, int64_t pstride_s, int64_t pstride_c);
 size_t sinkhorn_ws_bytes(int64_t k);
 }  // namespace ssvb
 
@@ -210,6 +210,108 @@ swav_ce_reg_kernel(const float* __restrict__ scores, const float* __restrict__ c
   }
 }
 
+// float4 form of the register-cached kernel (16-byte aligned rows, ld % 4 == 0, ldds % 4 == 0, ldds <= 1024 * V): thread t
+// owns columns 4 * (t + 256 * e) .. + 3 - a quarter of the load / store instructions (16-byte loads, 8-byte bf16 stores).
+// The padding columns [k, ld) of the score / code rows are never written by their producers: masked per element.
+template <int V>
+__global__ void __launch_bounds__(256)
+swav_ce_reg4_kernel(const float* __restrict__ scores, const float* __restrict__ codes, int64_t bp, int k, int64_t ld,
+                    float inv_t, float coef /* 1/(2 B' T) */, float* __restrict__ loss_part, __nv_bfloat16* __restrict__ ds,
+                    int64_t ldds) {
+  __shared__ float red[8][6];
+  const int64_t r = blockIdx.x;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4* s1p = reinterpret_cast<const float4*>(scores + r * ld);
+  const float4* s2p = reinterpret_cast<const float4*>(scores + (bp + r) * ld);
+  const float4* q1p = reinterpret_cast<const float4*>(codes + r * ld);
+  const float4* q2p = reinterpret_cast<const float4*>(codes + (bp + r) * ld);
+  const int ld4 = static_cast<int>(ld >> 2);
+  float t1[4 * V], t2[4 * V], q1[4 * V], q2[4 * V];
+  float m1 = -INFINITY, m2 = -INFINITY;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    const int c4 = threadIdx.x + e * 256;
+    const bool in = c4 < ld4;
+    const float4 a = in ? __ldg(s1p + c4) : z4, b = in ? __ldg(s2p + c4) : z4;
+    const float4 x = in ? __ldg(q1p + c4) : z4, y = in ? __ldg(q2p + c4) : z4;
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    const float xv[4] = {x.x, x.y, x.z, x.w}, yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool ok = c4 * 4 + i < k;
+      t1[4 * e + i] = ok ? av[i] * inv_t : -INFINITY;
+      t2[4 * e + i] = ok ? bv[i] * inv_t : -INFINITY;
+      q1[4 * e + i] = ok ? xv[i] : 0.f;
+      q2[4 * e + i] = ok ? yv[i] : 0.f;
+      m1 = fmaxf(m1, t1[4 * e + i]);
+      m2 = fmaxf(m2, t2[4 * e + i]);
+    }
+  }
+  m1 = warp_max(m1);
+  m2 = warp_max(m2);
+  if (lane == 0) { red[w][0] = m1; red[w][1] = m2; }
+  __syncthreads();
+  m1 = red[0][0]; m2 = red[0][1];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) { m1 = fmaxf(m1, red[i][0]); m2 = fmaxf(m2, red[i][1]); }
+  __syncthreads();
+  float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // e1, e2, a12, a21, sq1, sq2
+#pragma unroll
+  for (int e = 0; e < 4 * V; ++e) {
+    if ((threadIdx.x + (e >> 2) * 256) * 4 + (e & 3) < k) {
+      v[2] = fmaf(q1[e], t2[e], v[2]);  // sum q1 * (s2/T)
+      v[3] = fmaf(q2[e], t1[e], v[3]);
+    }
+    t1[e] = __expf(t1[e] - m1);  // exp(-inf) = 0 on the padding
+    t2[e] = __expf(t2[e] - m2);
+    v[0] += t1[e];
+    v[1] += t2[e];
+    v[4] += q1[e];
+    v[5] += q2[e];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) red[w][i] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) t += red[ww][i];
+    v[i] = t;
+  }
+  const float lse1 = m1 + __logf(v[0]), lse2 = m2 + __logf(v[1]);
+  if (threadIdx.x == 0) loss_part[r] = -0.5f * ((v[2] - v[4] * lse2) + (v[3] - v[5] * lse1));
+  const float i1 = v[5] / v[0], i2 = v[4] / v[1];  // softmax(s/T) * sum(q of the other view)
+  uint2* d1 = reinterpret_cast<uint2*>(ds + r * ldds);
+  uint2* d2 = reinterpret_cast<uint2*>(ds + (bp + r) * ldds);
+  const int ldds4 = static_cast<int>(ldds >> 2);
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    const int c4 = threadIdx.x + e * 256;
+    if (c4 < ldds4) {
+      float g1[4], g2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = c4 * 4 + i < k;
+        g1[i] = ok ? -(q2[4 * e + i] - t1[4 * e + i] * i1) * coef : 0.f;  // d loss / d s1
+        g2[i] = ok ? -(q1[4 * e + i] - t2[4 * e + i] * i2) * coef : 0.f;  // d loss / d s2
+      }
+      __nv_bfloat162 a0 = __floats2bfloat162_rn(g1[0], g1[1]), a1 = __floats2bfloat162_rn(g1[2], g1[3]);
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(g2[0], g2[1]), b1 = __floats2bfloat162_rn(g2[2], g2[3]);
+      uint2 pa, pb;
+      pa.x = *reinterpret_cast<uint32_t*>(&a0); pa.y = *reinterpret_cast<uint32_t*>(&a1);
+      pb.x = *reinterpret_cast<uint32_t*>(&b0); pb.y = *reinterpret_cast<uint32_t*>(&b1);
+      d1[c4] = pa;
+      d2[c4] = pb;
+    }
+  }
+}
+
 // out[r, c] = go * in[r, c]  (+ optionally go * in2[r, c]) for c < d
 __global__ void scale_rows_kernel(const float* __restrict__ in, int64_t ldi, int64_t rows, int d,
                                   const float* __restrict__ grad_out, float* __restrict__ out, int64_t ldo) {
@@ -220,6 +322,29 @@ __global__ void scale_rows_kernel(const float* __restrict__ in, int64_t ldi, int
     const int64_t r = i / d;
     const int c = static_cast<int>(i - r * d);
     out[r * ldo + c] = in[r * ldi + c] * go;
+  }
+}
+
+// the three gradient outputs in one launch: segment g of (in, ldi, rows, out, ldo); out[r, c] = go * in[r, c], c < d
+struct ScaleSeg {
+  const float* in;
+  float* out;
+  int64_t ldi, ldo, rows;
+};
+struct ScaleSegs {
+  ScaleSeg seg[3];
+};
+__global__ void scale_rows3_kernel(ScaleSegs sg, int d4, const float* __restrict__ grad_out) {
+  const float go = __ldg(grad_out);
+  const ScaleSeg& g = sg.seg[blockIdx.y];
+  const int64_t total = g.rows * d4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / d4;
+    const int c = static_cast<int>(i - r * d4);
+    float4 v = __ldg(reinterpret_cast<const float4*>(g.in + r * g.ldi) + c);
+    v.x *= go; v.y *= go; v.z *= go; v.w *= go;
+    reinterpret_cast<float4*>(g.out + r * g.ldo)[c] = v;
   }
 }
 
@@ -243,25 +368,53 @@ unsigned grid_for(int64_t total, int per_block) {
 }
 
 
+// One launch for the four operand conversions of the scores GEMM (one warp per source row): z1 -> Z[0, nb), z2 ->
+// Z[bp, bp + nb), bank row j -> Z[nb + j] AND Z[bp + nb + j] (the bank closes both views, utils/losses.py:227-229),
+// prototypes -> C.  fp32 [rows x d] -> bf16 [rows x dpad], zero padded.
+__global__ void swav_stage_kernel(const float* __restrict__ z1, const float* __restrict__ z2, const float* __restrict__ bank,
+                                  const float* __restrict__ proto, int64_t nb, int64_t nbank, int64_t k, int64_t bp, int d,
+                                  int dpad, int64_t ld_z1, int64_t ld_z2, int64_t ld_bank, int64_t ld_proto,
+                                  __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ c) {
+  int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const float* src;
+  __nv_bfloat16 *dst, *dst2 = nullptr;
+  if (row < nb) {
+    src = z1 + row * ld_z1;
+    dst = z + row * dpad;
+  } else if ((row -= nb) < nb) {
+    src = z2 + row * ld_z2;
+    dst = z + (bp + row) * dpad;
+  } else if ((row -= nb) < nbank) {
+    src = bank + row * ld_bank;
+    dst = z + (nb + row) * dpad;
+    dst2 = z + (bp + nb + row) * dpad;
+  } else if ((row -= nbank) < k) {
+    src = proto + row * ld_proto;
+    dst = c + row * dpad;
+  } else {
+    return;
+  }
+  for (int col = lane * 4; col < dpad; col += 128) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < d) v = __ldg(reinterpret_cast<const float4*>(src + col));
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dst + col) = pk;
+    if (dst2) *reinterpret_cast<uint2*>(dst2 + col) = pk;
+  }
+}
+
 // stage [Z1; Z2] (each = live rows then bank rows) and the prototypes as bf16, then scores[2B' x K] = [Z1; Z2] C^T
 int stage_scores(const float* z1, const float* z2, const float* bank, const float* prototypes, const SwavDims& m,
                  int64_t ld_z1, int64_t ld_z2, int64_t ld_bank, int64_t ld_proto, const SwavSaved& sv, float* scores,
                  cudaStream_t s) {
   const int di = static_cast<int>(m.d), dp = static_cast<int>(m.dpad);
   const int64_t nb = m.nb, nbank = m.nbank, k = m.k;
-  rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(nb, 8)), 256, 0, s>>>(z1, nb, di, ld_z1, dp, nullptr, sv.z);
-  SSVB_LAUNCH_CHECK();
-  rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(nb, 8)), 256, 0, s>>>(z2, nb, di, ld_z2, dp, nullptr,
-                                                                             sv.z + m.bp * m.dpad);
-  SSVB_LAUNCH_CHECK();
-  if (nbank > 0) {
-    rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(nbank, 8)), 256, 0, s>>>(bank, nbank, di, ld_bank, dp, nullptr,
-                                                                                  sv.z + nb * m.dpad);
-    SSVB_LAUNCH_CHECK();
-    SSVB_CUDA(cudaMemcpyAsync(sv.z + (m.bp + nb) * m.dpad, sv.z + nb * m.dpad, nbank * m.dpad * sizeof(__nv_bfloat16),
-                              cudaMemcpyDeviceToDevice, s));
-  }
-  rows_to_bf16_kernel<<<static_cast<unsigned>(ceil_div(k, 8)), 256, 0, s>>>(prototypes, k, di, ld_proto, dp, nullptr, sv.c);
+  swav_stage_kernel<<<static_cast<unsigned>(ceil_div(2 * nb + nbank + k, 8)), 256, 0, s>>>(
+      z1, z2, bank, prototypes, nb, nbank, k, m.bp, di, dp, ld_z1, ld_z2, ld_bank, ld_proto, sv.z, sv.c);
   SSVB_LAUNCH_CHECK();
   GemmParams p{};
   p.M = static_cast<int>(2 * m.bp);
@@ -281,12 +434,21 @@ int stage_ce(const float* scores, const float* codes, const SwavDims& m, int64_t
   const int ki = static_cast<int>(m.k);
   const float it = 1.f / temperature, coef = 0.5f / (static_cast<float>(bp_total) * temperature);
 #define SSVB_CE(E) swav_ce_reg_kernel<E><<<grid, 256, 0, s>>>(scores, codes, m.bp, ki, m.kp4, it, coef, loss_part, sv.ds, m.kp8)
-  if (m.kp8 <= 4 * 256) SSVB_CE(4);
+#define SSVB_CE4(V) swav_ce_reg4_kernel<V><<<grid, 256, 0, s>>>(scores, codes, m.bp, ki, m.kp4, it, coef, loss_part, sv.ds, m.kp8)
+  static const bool no_ce4 = getenv("SSVB_SWAV_NO_CE4") != nullptr;  // A/B switch
+  const bool vec = !no_ce4 && !(reinterpret_cast<uintptr_t>(scores) & 15) && !(reinterpret_cast<uintptr_t>(codes) & 15) &&
+                   !(reinterpret_cast<uintptr_t>(sv.ds) & 7);  // (kp4 % 4 == 0 and kp8 % 8 == 0 by construction)
+  if (vec && m.kp8 <= 1 * 1024) SSVB_CE4(1);
+  else if (vec && m.kp8 <= 2 * 1024) SSVB_CE4(2);
+  else if (vec && m.kp8 <= 3 * 1024) SSVB_CE4(3);
+  else if (vec && m.kp8 <= 4 * 1024) SSVB_CE4(4);
+  else if (m.kp8 <= 4 * 256) SSVB_CE(4);
   else if (m.kp8 <= 8 * 256) SSVB_CE(8);
   else if (m.kp8 <= 12 * 256) SSVB_CE(12);
   else if (m.kp8 <= 16 * 256) SSVB_CE(16);
   else swav_ce_kernel<<<grid, 256, 0, s>>>(scores, codes, m.bp, ki, m.kp4, it, coef, loss_part, sv.ds, m.kp8);
 #undef SSVB_CE
+#undef SSVB_CE4
   SSVB_LAUNCH_CHECK();
   sum_partials_kernel<<<1, 1024, 0, s>>>(loss_part, static_cast<int>(m.bp), 1.f / static_cast<float>(bp_total), loss);
   SSVB_LAUNCH_CHECK();
@@ -324,8 +486,8 @@ int ssvb_swav_fwd(const float* z1, const float* z2, const float* bank, const flo
   SwavWs ws = swav_ws(workspace, m);
   SSVB_TRY(stage_scores(z1, z2, bank, prototypes, m, ld_z1, ld_z2, ld_bank, ld_proto, sv, ws.scores, s));
   // codes per view (Sinkhorn normalises over the B' rows of ONE view)
-  SSVB_TRY(sinkhorn_run(ws.scores, m.bp, k, m.kp4, eps, n_iters, ws.codes, m.kp4, ws.sk, s));
-  SSVB_TRY(sinkhorn_run(ws.scores + m.bp * m.kp4, m.bp, k, m.kp4, eps, n_iters, ws.codes + m.bp * m.kp4, m.kp4, ws.sk, s));
+  // the two views' code assignments (utils/losses.py:232) are independent problems of one shape: batched launches
+  SSVB_TRY(sinkhorn_run(ws.scores, m.bp, k, m.kp4, eps, n_iters, ws.codes, m.kp4, ws.sk, s, 2, m.bp * m.kp4, m.bp * m.kp4));
   return stage_ce(ws.scores, ws.codes, m, m.bp, temperature, sv, ws.loss_part, loss, s);
 }
 
@@ -382,42 +544,55 @@ int ssvb_swav_bwd(const float* z1, const float* z2, const float* bank, const flo
   SwavWs ws = swav_ws(workspace, m);
   const int di = static_cast<int>(d);
 
+  GemmParams pz{}, pc{};
+  bool split_z = false, split_c = false;
   if (dz1 || dz2) {
     // dz[2B' x d] = ds[2B' x K] C[K x d]        (A K-major, B = prototypes consumed MN-major)
-    GemmParams p{};
-    p.M = static_cast<int>(2 * m.bp);
-    p.N = static_cast<int>(m.dpad);
-    p.K = static_cast<int>(k);
-    p.alpha = 1.f;
-    p.out = ws.dz;
-    p.ldc = m.dpad;
+    pz.M = static_cast<int>(2 * m.bp);
+    pz.N = static_cast<int>(m.dpad);
+    pz.K = static_cast<int>(k);
+    pz.alpha = 1.f;
+    pz.out = ws.dz;
+    pz.ldc = m.dpad;
     // 2B'/128 x 1 tiles (55 at the reference shape) for 148 SMs: split K over CTAs, partial products added by TMA
-    const bool split = gemm_will_split(p.M, p.N, p.K, 128, ws.dz, m.dpad);
-    if (split) SSVB_CUDA(cudaMemsetAsync(ws.dz, 0, static_cast<size_t>(p.M) * m.dpad * sizeof(float), s));
-    SSVB_TRY(launch_gemm({sv.ds, m.kp8, false}, {sv.c, m.dpad, true}, p, 128, EPI_STORE_F32, 0, s, split));
-    if (dz1) {
-      scale_rows_kernel<<<grid_for(nb * d, 256), 256, 0, s>>>(ws.dz, m.dpad, nb, di, grad_out, dz1, ld_dz1);
-      SSVB_LAUNCH_CHECK();
-    }
-    if (dz2) {
-      scale_rows_kernel<<<grid_for(nb * d, 256), 256, 0, s>>>(ws.dz + m.bp * m.dpad, m.dpad, nb, di, grad_out, dz2, ld_dz2);
-      SSVB_LAUNCH_CHECK();
-    }
+    split_z = gemm_will_split(pz.M, pz.N, pz.K, 128, ws.dz, m.dpad);
   }
   if (dproto) {
     // dC[K x d] = ds^T [K x 2B'] [Z1; Z2] [2B' x d]   (both operands MN-major, contraction over the stacked rows)
-    GemmParams p{};
-    p.M = static_cast<int>(k);
-    p.N = static_cast<int>(m.dpad);
-    p.K = static_cast<int>(2 * m.bp);
-    p.alpha = 1.f;
-    p.out = ws.dc;
-    p.ldc = m.dpad;
+    pc.M = static_cast<int>(k);
+    pc.N = static_cast<int>(m.dpad);
+    pc.K = static_cast<int>(2 * m.bp);
+    pc.alpha = 1.f;
+    pc.out = ws.dc;
+    pc.ldc = m.dpad;
     // K/128 x 1 tiles (24 at K = 3000): split the contraction over the stacked rows across CTAs
-    const bool split = gemm_will_split(p.M, p.N, p.K, 128, ws.dc, m.dpad);
-    if (split) SSVB_CUDA(cudaMemsetAsync(ws.dc, 0, static_cast<size_t>(p.M) * m.dpad * sizeof(float), s));
-    SSVB_TRY(launch_gemm({sv.ds, m.kp8, true}, {sv.z, m.dpad, true}, p, 128, EPI_STORE_F32, 0, s, split));
-    scale_rows_kernel<<<grid_for(k * d, 256), 256, 0, s>>>(ws.dc, m.dpad, k, di, grad_out, dproto, ld_dproto);
+    split_c = gemm_will_split(pc.M, pc.N, pc.K, 128, ws.dc, m.dpad);
+  }
+  // split-K accumulators are zeroed up front; ws.dz and ws.dc are adjacent in the workspace: one memset node when both split
+  const size_t zbytes = static_cast<size_t>(2 * m.bp) * m.dpad * sizeof(float), cbytes = static_cast<size_t>(k) * m.dpad * sizeof(float);
+  if (split_z && split_c) {
+    const size_t span = static_cast<size_t>(reinterpret_cast<uint8_t*>(ws.dc) - reinterpret_cast<uint8_t*>(ws.dz)) + cbytes;
+    SSVB_CUDA(cudaMemsetAsync(ws.dz, 0, span, s));
+  } else if (split_z) {
+    SSVB_CUDA(cudaMemsetAsync(ws.dz, 0, zbytes, s));
+  } else if (split_c) {
+    SSVB_CUDA(cudaMemsetAsync(ws.dc, 0, cbytes, s));
+  }
+  if (dz1 || dz2) SSVB_TRY(launch_gemm({sv.ds, m.kp8, false}, {sv.c, m.dpad, true}, pz, 128, EPI_STORE_F32, 0, s, split_z));
+  if (dproto) SSVB_TRY(launch_gemm({sv.ds, m.kp8, true}, {sv.z, m.dpad, true}, pc, 128, EPI_STORE_F32, 0, s, split_c));
+  // grad_out scaling of every requested output in one launch
+  ScaleSegs sg{};
+  int nseg = 0;
+  int64_t max_rows = 0;
+  auto add = [&](const float* in, float* out, int64_t ldo, int64_t rows) {
+    sg.seg[nseg++] = ScaleSeg{in, out, m.dpad, ldo, rows};
+    if (rows > max_rows) max_rows = rows;
+  };
+  if (dz1) add(ws.dz, dz1, ld_dz1, nb);
+  if (dz2) add(ws.dz + m.bp * m.dpad, dz2, ld_dz2, nb);
+  if (dproto) add(ws.dc, dproto, ld_dproto, k);
+  if (nseg) {
+    scale_rows3_kernel<<<dim3(grid_for(max_rows * (d / 4), 256), static_cast<unsigned>(nseg)), 256, 0, s>>>(sg, di / 4, grad_out);
     SSVB_LAUNCH_CHECK();
   }
   return SSVB_OK;

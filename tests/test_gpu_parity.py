@@ -477,10 +477,17 @@ def test_swav_oracle(S, nb, nbank, k, d):
 
 
 # ------------------------------------------------------------------------------------------------ GEMM epilogue paths
-def test_gemm_row_store_fallback_matches_oracle():
-    """The staged TMA-store epilogue is the default; rows that are not 16-byte aligned take the per-thread row-store
-    epilogue.  `SSVB_GEMM_NO_TMA_STORE=1` forces that path (read once per process, hence the subprocess): Barlow (fused
-    loss epilogue + the un-fused backward column reduction) and SwAV (fp32 scores, no split-K) against the oracle."""
+@pytest.mark.parametrize("switches", [
+    {"SSVB_GEMM_NO_TMA_STORE": "1"},
+    {"SSVB_SK_NO_BATCH": "1", "SSVB_BARLOW_NO_X2": "1", "SSVB_SWAV_NO_CE4": "1"},
+], ids=["row-store-epilogue", "one-view-per-launch"])
+def test_alternative_paths_match_oracle(switches):
+    """The library's A/B switches select code paths that the default configuration does not take; they are read once per
+    process, hence the subprocess.  (1) `SSVB_GEMM_NO_TMA_STORE=1`: the per-thread row-store GEMM epilogue that rows
+    without 16-byte alignment take instead of the staged TMA store - Barlow (fused loss epilogue + the un-fused backward
+    column reduction) and SwAV (fp32 scores, no split-K).  (2) one view per launch: Sinkhorn without the two-problem
+    batching, Barlow's one-view statistics / standardize / finish kernels, the scalar SwAV cross-entropy kernel (the
+    forms the distributed stages and odd shapes still use).  Both against the oracle."""
     import os
     import subprocess
     import sys
@@ -507,6 +514,6 @@ assert abs(l2.item() - r2[0]) / abs(r2[0]) <= 1e-3
 assert rl2(t1.grad.cpu().numpy(), r2[1]) <= 1e-2 and rl2(tc.grad.cpu().numpy(), r2[3]) <= 1e-2
 print("fallback-ok")
 """ % (ROOT, PKG)
-    env = dict(os.environ, SSVB_GEMM_NO_TMA_STORE="1")
+    env = dict(os.environ, **switches)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "fallback-ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
