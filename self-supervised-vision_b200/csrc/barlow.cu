@@ -32,6 +32,7 @@ struct BarlowSaved {
   __nv_bfloat16* dC;       // [d x d]
   float *mean_i, *rstd_i, *mean_j, *rstd_j;  // [d]
   float *inv_i, *inv_j;                      // [n] row 1/norm (normalize=1)
+  float *q_i, *q_j;  // [d] rstd * sum_n(dT x~)/(n-1), from the forward's dC .* C sums (closed-form backward, see below)
   size_t bytes;
 };
 BarlowSaved barlow_saved(void* base, int64_t n, int64_t d) {
@@ -46,6 +47,8 @@ BarlowSaved barlow_saved(void* base, int64_t n, int64_t d) {
   s.rstd_j = c.take<float>(d);
   s.inv_i = c.take<float>(n);
   s.inv_j = c.take<float>(n);
+  s.q_i = c.take<float>(d);
+  s.q_j = c.take<float>(d);
   s.bytes = c.used();
   return s;
 }
@@ -55,6 +58,8 @@ struct BarlowWs {
   float* loss_partials;  // [kMaxGemmCtas]
   float *dti, *dtj;      // backward: [n x d] fp32 each
   float* colred;         // [2 views][2][d]  (mean of dT, sum(dT x~)/(n-1))
+  float* xrow;           // forward: [ceil(d/256)][d] row sums of dC .* C per column tile (GEMM epilogue)
+  float* xcol;           // forward: [ceil(d/128) * 4][d] column sums of dC .* C per (row tile, epilogue warp)
   size_t bytes;
 };
 BarlowWs barlow_ws(void* base, int64_t n, int64_t d) {
@@ -68,6 +73,8 @@ BarlowWs barlow_ws(void* base, int64_t n, int64_t d) {
   w.dti = c.take<float>(n * d);
   w.dtj = c.take<float>(n * d);
   w.colred = c.take<float>(4 * d);
+  w.xrow = c.take<float>(ceil_div(d, 256) * d);
+  w.xcol = c.take<float>(ceil_div(d, 128) * 4 * d);
   w.bytes = c.used();
   return w;
 }
@@ -640,6 +647,53 @@ int stats_and_standardize(const float* x, int64_t ld, int normalize, int64_t n, 
   return SSVB_OK;
 }
 
+// Closed-form backward of the batch standardisation.  With x~ = (x - mean) / std (unbiased) and dT = dL/dx~:
+//   dx = (dT - mean_n(dT) - x~ * sum_n(dT x~) / (n - 1)) / std.
+// Here dTi[n, a] = sum_b x~j[n, b] dC[a, b] / n, so mean_n(dTi[., a]) = sum_b dC[a, b] mean_n(x~j[., b]) = 0 (standardised
+// columns have zero mean) and sum_n(dTi[n, a] x~i[n, a]) = sum_b dC[a, b] C[a, b]: both column statistics of the backward
+// are known after the FORWARD GEMM - row sums (view i) / column sums (view j) of dC .* C, taken in its epilogue.  The
+// backward GEMM epilogue can then turn each dT tile into the input gradient on its way out of TMEM: no fp32 dT round trip
+// (2 x 67 MB written + read at 2048 x 8192), no column reduction, no finish pass.
+// This kernel: blocks [0, ceil(d/32)) combine the partial sums in fixed order into q_i = rstd_i * m2_i, q_j = rstd_j * m2_j;
+// the last block sums the loss partials (was sum_partials_kernel).
+__global__ void barlow_fwd_finish_kernel(const float* __restrict__ xrow, int nrow, const float* __restrict__ xcol, int ncol,
+                                         int d, float inv_nm1, const float* __restrict__ rstd_i,
+                                         const float* __restrict__ rstd_j, float* __restrict__ q_i, float* __restrict__ q_j,
+                                         const float* __restrict__ loss_part, int nloss, float* __restrict__ loss) {
+  __shared__ float sh1[8][33], sh2[8][33];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (blockIdx.x == gridDim.x - 1) {
+    float v = 0.f;
+    for (int i = tid; i < nloss; i += 256) v += loss_part[i];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) sh1[threadIdx.y][0] = v;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += sh1[i][0];
+      loss[0] = t;
+    }
+    return;
+  }
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float s1 = 0.f, s2 = 0.f;
+  if (col < d) {
+    for (int i = threadIdx.y; i < nrow; i += 8) s1 += xrow[static_cast<int64_t>(i) * d + col];
+    for (int i = threadIdx.y; i < ncol; i += 8) s2 += xcol[static_cast<int64_t>(i) * d + col];
+  }
+  sh1[threadIdx.y][threadIdx.x] = s1;
+  sh2[threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < d) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += sh1[i][threadIdx.x]; b += sh2[i][threadIdx.x]; }
+    q_i[col] = a * inv_nm1 * rstd_i[col];
+    q_j[col] = b * inv_nm1 * rstd_j[col];
+  }
+}
+
 // forward pre-pass of BOTH views in three launches (statistics, finalize, standardize); `xi` heads the two standardised
 // operands (`x_view_stride` elements apart)
 int stats_and_standardize_x2(const float* zi, int64_t ld_zi, const float* zj, int64_t ld_zj, int normalize, int64_t n,
@@ -715,10 +769,14 @@ int ssvb_barlow_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   p.dC = sv.dC;
   p.ld_dc = d;
   p.loss_partials = ws.loss_partials;
+  p.bl_rowpart = ws.xrow;  // dC .* C sums for the closed-form backward (barlow_fwd_finish_kernel)
+  p.bl_colpart = ws.xcol;
   SSVB_TRY(launch_gemm({sv.xi, d, true}, {sv.xj, d, true}, p, 256, EPI_BARLOW, kMaxGemmCtas, s));
   // every launched CTA wrote its partial (persistent kernel, grid = min(tiles, SMs)): sum exactly those, no memset
-  sum_partials_kernel<<<1, 256, 0, s>>>(ws.loss_partials, gemm_grid(ceil_div(d, 128) * ceil_div(d, 256), kMaxGemmCtas),
-                                        1.f, loss);
+  barlow_fwd_finish_kernel<<<static_cast<unsigned>(ceil_div(d, 32) + 1), dim3(32, 8), 0, s>>>(
+      ws.xrow, static_cast<int>(ceil_div(d, 256)), ws.xcol, static_cast<int>(ceil_div(d, 128) * 4), static_cast<int>(d),
+      1.f / static_cast<float>(n - 1), sv.rstd_i, sv.rstd_j, sv.q_i, sv.q_j, ws.loss_partials,
+      gemm_grid(ceil_div(d, 128) * ceil_div(d, 256), kMaxGemmCtas), loss);
   SSVB_LAUNCH_CHECK();
   return SSVB_OK;
 }
@@ -751,6 +809,29 @@ int ssvb_barlow_bwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   // and the epilogue leaves the column partials sum_n dT, sum_n dT x~ per (row tile, warp) beside the output
   const float* inv_i = normalize ? sv.inv_i : nullptr;
   const float* inv_j = normalize ? sv.inv_j : nullptr;
+  static const bool no_fused = getenv("SSVB_BARLOW_NO_FUSED_BWD") != nullptr;  // A/B switch: dT round trip + finish kernels
+  if (!normalize && !no_fused && gemm_tma_store_allowed()) {
+    // closed-form standardisation backward inside the GEMM epilogue (see barlow_fwd_finish_kernel): the two GEMMs write
+    // dzi / dzj directly (rows are 16-byte aligned: check_rows above).  normalize = 1 also needs a per-row dot with the
+    // finished gradient and keeps the dT + finish-kernel path below.
+    p.out = dzi;
+    p.ldc = ld_dzi;
+    p.out2 = dzj;
+    p.ldc2 = ld_dzj;
+    p.xf = zi;  // x~ is rebuilt from the fp32 inputs: the bf16 operand copy would add 2^-9 to a term that largely cancels dT
+    p.ldxf = ld_zi;
+    p.xf2 = zj;
+    p.ldxf2 = ld_zj;
+    p.vm = sv.mean_i;
+    p.vr = sv.rstd_i;
+    p.vq = sv.q_i;
+    p.vm2 = sv.mean_j;
+    p.vr2 = sv.rstd_j;
+    p.vq2 = sv.q_j;
+    p.go = grad_out;
+    const GemmOperand a2f{sv.xi, d, false}, b2f{sv.dC, d, true};
+    return launch_gemm({sv.xj, d, false}, {sv.dC, d, false}, p, 256, EPI_BARLOW_BWD, 0, s, false, &a2f, &b2f);
+  }
   float* part_i = ws.colpart;
   float* part_j = ws.colpart + ws.view_stride;
   int nsplit = fused_stripes(n);

@@ -61,8 +61,14 @@ inline int launch_gemm(const GemmOperand& A, const GemmOperand& B, GemmParams p,
                        const GemmOperand* B2 = nullptr) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return SSVB_ERR_INVALID;
   const bool dual = A2 != nullptr;
-  if (dual && (!B2 || A.mn_major || A2->mn_major || B.mn_major || !B2->mn_major || bn != 256 || epi != EPI_STORE_F32 || !p.out2))
+  if (dual && (!B2 || A.mn_major || A2->mn_major || B.mn_major || !B2->mn_major || bn != 256 ||
+               (epi != EPI_STORE_F32 && epi != EPI_BARLOW_BWD) || !p.out2))
     return SSVB_ERR_UNSUPPORTED;
+  if (epi == EPI_BARLOW_BWD && (!dual || !p.vm || !p.vr || !p.vq || !p.vm2 || !p.vr2 || !p.vq2 || !p.xf || !p.xf2 || !p.go ||
+                                (p.ldxf & 3) || (p.ldxf2 & 3) || (reinterpret_cast<uintptr_t>(p.xf) & 15) ||
+                                (reinterpret_cast<uintptr_t>(p.xf2) & 15)))
+    return SSVB_ERR_INVALID;
+  const int64_t ldc2 = p.ldc2 > 0 ? p.ldc2 : p.ldc;
   CUtensorMap tm[6];
   auto operand_maps = [&](const GemmOperand& a, const GemmOperand& b, CUtensorMap* ta, CUtensorMap* tb) -> int {
     if (a.mn_major)
@@ -87,15 +93,15 @@ inline int launch_gemm(const GemmOperand& A, const GemmOperand& B, GemmParams p,
     if (p.tma_store) SSVB_TRY(make_tmap_out(&tm[2], p.dC, p.M, p.N, p.ld_dc, 2));
   } else {
     p.tma_store = gemm_tma_store_allowed() && !(reinterpret_cast<uintptr_t>(p.out) & 15) && (p.ldc % 4 == 0) &&
-                  (!dual || !(reinterpret_cast<uintptr_t>(p.out2) & 15));
+                  (!dual || (!(reinterpret_cast<uintptr_t>(p.out2) & 15) && (ldc2 % 4 == 0)));
     if (p.tma_store) SSVB_TRY(make_tmap_out(&tm[2], p.out, p.M, p.N, p.ldc, 4));
   }
   if (!p.tma_store) {
     tm[2] = tm[0];  // never dereferenced
-    if (p.colpart) return SSVB_ERR_ALIGNMENT;  // the fused column partials live in the staged epilogue
+    if (p.colpart || epi == EPI_BARLOW_BWD) return SSVB_ERR_ALIGNMENT;  // these live in the staged epilogue only
   }
   tm[5] = tm[2];
-  if (dual && p.tma_store) SSVB_TRY(make_tmap_out(&tm[5], p.out2, p.M, p.N, p.ldc, 4));
+  if (dual && p.tma_store) SSVB_TRY(make_tmap_out(&tm[5], p.out2, p.M, p.N, ldc2, 4));
   gemm_plan_splits(p, static_cast<int64_t>(p.tiles_m) * p.tiles_n,
                    split_k && p.tma_store && epi == EPI_STORE_F32 && !dual && !p.colpart);
 #define SSVB_G(BNV, AM, BM_, E, D) return launch_gemm_t<BNV, AM, BM_, E, D>(tm, p, max_ctas, s)
@@ -103,6 +109,8 @@ inline int launch_gemm(const GemmOperand& A, const GemmOperand& B, GemmParams p,
     if (bn == 256 && A.mn_major && B.mn_major) SSVB_G(256, true, true, EPI_BARLOW, false);
     return SSVB_ERR_UNSUPPORTED;
   }
+  if (dual && epi == EPI_BARLOW_BWD) SSVB_G(256, false, false, EPI_BARLOW_BWD, true);
+  if (epi == EPI_BARLOW_BWD) return SSVB_ERR_UNSUPPORTED;
   if (dual) SSVB_G(256, false, false, EPI_STORE_F32, true);
   if (bn == 256) {
     if (!A.mn_major && !B.mn_major) SSVB_G(256, false, false, EPI_STORE_F32, false);

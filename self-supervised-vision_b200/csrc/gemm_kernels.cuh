@@ -27,7 +27,7 @@
 
 namespace ssvb {
 
-enum GemmEpiMode { EPI_STORE_F32 = 0, EPI_BARLOW = 1 };
+enum GemmEpiMode { EPI_STORE_F32 = 0, EPI_BARLOW = 1, EPI_BARLOW_BWD = 2 };
 
 struct GemmParams {
   int M, N, K;  // logical sizes (tails are zero-filled by TMA and predicated / clipped in the epilogue)
@@ -52,6 +52,19 @@ struct GemmParams {
   int64_t ld_dc;
   float* loss_partials;  // [gridDim.x]
   int diag_off;          // the output is a column slab of the full matrix: global column = n + diag_off
+  // EPI_BARLOW, optional (nullptr = off): partial sums of dC .* C for the closed-form backward of the standardisation
+  // (csrc/barlow.cu): bl_rowpart[tile_n * M + m] = sum over the tile's columns, bl_colpart[(tile_m * 4 + q) * N + n] = sum
+  // over the 32 rows of epilogue warp q
+  float* bl_rowpart;
+  float* bl_colpart;
+  // EPI_BARLOW_BWD (staged TMA-store epilogue only): out[m, n] = (acc * alpha - (xf[m, n] - vm[n]) * vq[n]) * vr[n] * go[0],
+  // i.e. the standardisation backward applied to the dT tile while it leaves TMEM (xf = the fp32 input rows, vm / vr =
+  // column mean / 1/std, vq = rstd * sum_n(dT x~)/(n-1)); second problem: xf2 / ldxf2 / vm2 / vr2 / vq2 / out2 / ldc2
+  const float *xf, *xf2;
+  int64_t ldxf, ldxf2;
+  const float *vm, *vr, *vq, *vm2, *vr2, *vq2;
+  const float* go;
+  int64_t ldc2;
 };
 
 template <int BN>
@@ -321,9 +334,65 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
+      } else if (EPI == EPI_BARLOW_BWD) {
+        // dz tile = (dT - x~ * q) * rstd * grad_out with x~ = (x - mean) * rstd from the fp32 input rows, straight from the
+        // accumulator to the caller's gradient (TMA store)
+        const float* xf = second ? p.xf2 : p.xf;
+        const int64_t ldxf = second ? p.ldxf2 : p.ldxf;
+        const float* vm = second ? p.vm2 : p.vm;
+        const float* vr = second ? p.vr2 : p.vr;
+        const float* vq = second ? p.vq2 : p.vq;
+        const float go = __ldg(p.go);
+        const float ago = p.alpha * go;
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          const int col0 = tn * BN + cc * 32;
+          uint32_t v[32];
+          tmem_ld_x32(tmem + tlane + ab * BN + cc * 32, v);
+          // this thread's 32 input values (128 contiguous bytes) while the TMEM load is in flight
+          float4 xv[8];
+          const bool full = col0 + 32 <= p.N;  // warp-uniform
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_ok && (full || col0 + 4 * i < p.N))  // (N % 4 == 0: whole 16-byte pieces)
+              xv[i] = __ldg(reinterpret_cast<const float4*>(xf + static_cast<int64_t>(row) * ldxf + col0) + i);
+          }
+          tmem_ld_wait_regs32(v);
+          if (col0 >= p.N) continue;  // warp-uniform
+          const uint32_t buf = my_row + static_cast<uint32_t>(nstore & 1) * 4096u;
+          if (nstore >= 2) {
+            if (lane == 0) bulk_wait_group_read<1>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), r4 = m4, q4 = m4;
+            if (full || col0 + 4 * i < p.N) {
+              m4 = __ldg(reinterpret_cast<const float4*>(vm + col0) + i);
+              r4 = __ldg(reinterpret_cast<const float4*>(vr + col0) + i);
+              q4 = __ldg(reinterpret_cast<const float4*>(vq + col0) + i);
+            }
+            // (acc * alpha - (x - mean) * q) * rstd * go   [q already carries one rstd: x~ * m2 = (x - mean) * rstd * m2]
+            const float o0 = fmaf(__uint_as_float(v[4 * i]) * ago, r4.x, -((xv[i].x - m4.x) * q4.x) * (r4.x * go));
+            const float o1 = fmaf(__uint_as_float(v[4 * i + 1]) * ago, r4.y, -((xv[i].y - m4.y) * q4.y) * (r4.y * go));
+            const float o2 = fmaf(__uint_as_float(v[4 * i + 2]) * ago, r4.z, -((xv[i].z - m4.z) * q4.z) * (r4.z * go));
+            const float o3 = fmaf(__uint_as_float(v[4 * i + 3]) * ago, r4.w, -((xv[i].w - m4.w) * q4.w) * (r4.w * go));
+            sts_v4(buf + ((static_cast<uint32_t>(i) ^ swz) << 4), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2),
+                   __float_as_uint(o3));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(mc, stage0 + static_cast<uint32_t>(nstore & 1) * 4096u, col0, tm * C::BM + q * 32);
+            bulk_commit_group();
+          }
+          ++nstore;
+        }
       } else {
         // EPI_BARLOW: loss terms + dC (bf16); 64 columns (128 bytes of bf16 per row) per staged block
 #pragma unroll 1
+        float rs_acc = 0.f;  // sum over this tile's columns of dC .* C (row = this thread)
         for (int cc = 0; cc < BN / 64; ++cc) {
           const int col0 = tn * BN + cc * 64;
           uint32_t pk[32];
@@ -332,6 +401,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t v[32];
             tmem_ld_x32(tmem + tlane + ab * BN + cc * 64 + h * 32, v);
             tmem_ld_wait_regs32(v);
+            float gc[32];  // dC .* C of this thread's row, 32 columns
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               float g[2];
@@ -342,10 +412,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const bool diag = (col + p.diag_off == row);
                 const float r = diag ? (c - 1.f) : c;
                 const float w = diag ? 1.f : p.lambda;
-                if (row_ok && col < p.N) loss_acc = fmaf(w * r, r, loss_acc);
+                const bool ok = row_ok && col < p.N;
+                if (ok) loss_acc = fmaf(w * r, r, loss_acc);
                 g[e] = 2.f * w * r;
+                gc[2 * i + e] = ok ? c : 0.f;
               }
-              pk[h * 16 + i] = pack_bf16x2(g[0], g[1]);
+              const uint32_t pkv = pack_bf16x2(g[0], g[1]);
+              pk[h * 16 + i] = pkv;
+              // dC .* C with dC AS STORED (bf16): the backward GEMM multiplies by the rounded dC, and sum_n(dT x~) must carry
+              // the same rounding - dT and x~ * sum_n(dT x~)/(n-1) largely cancel, an inconsistent dC would be amplified
+              gc[2 * i] *= __uint_as_float(pkv << 16);
+              gc[2 * i + 1] *= __uint_as_float(pkv & 0xffff0000u);
+            }
+            if (p.bl_rowpart != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) rs_acc += gc[i];
+            }
+            if (p.bl_colpart != nullptr) {
+              // transpose-reduce over the warp's 32 rows: 31 shuffles leave the sum of column `lane` in gc[0]
+#pragma unroll
+              for (int sft = 16; sft >= 1; sft >>= 1) {
+                const bool upper = (lane & sft) != 0;
+#pragma unroll
+                for (int j = 0; j < sft; ++j) {
+                  const float keep = upper ? gc[j + sft] : gc[j];
+                  const float send = upper ? gc[j] : gc[j + sft];
+                  gc[j] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                }
+              }
+              const int col = col0 + h * 32 + lane;
+              if (col < p.N) p.bl_colpart[(static_cast<int64_t>(tm) * 4 + q) * p.N + col] = gc[0];
             }
           }
           if (col0 >= p.N) continue;  // warp-uniform
@@ -378,6 +474,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
+        if (p.bl_rowpart != nullptr && row_ok) p.bl_rowpart[static_cast<int64_t>(tn) * p.M + row] = rs_acc;
       }
       tc_fence_before();
       __syncwarp();

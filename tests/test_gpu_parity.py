@@ -479,15 +479,18 @@ def test_swav_oracle(S, nb, nbank, k, d):
 # ------------------------------------------------------------------------------------------------ GEMM epilogue paths
 @pytest.mark.parametrize("switches", [
     {"SSVB_GEMM_NO_TMA_STORE": "1"},
-    {"SSVB_SK_NO_BATCH": "1", "SSVB_BARLOW_NO_X2": "1", "SSVB_SWAV_NO_CE4": "1"},
-], ids=["row-store-epilogue", "one-view-per-launch"])
+    {"SSVB_SK_NO_BATCH": "1", "SSVB_BARLOW_NO_X2": "1", "SSVB_SWAV_NO_CE4": "1", "SSVB_BARLOW_NO_FUSED_BWD": "1"},
+    {"SSVB_BARLOW_NO_FUSED_BWD": "1"},
+], ids=["row-store-epilogue", "one-view-per-launch", "barlow-dT-round-trip"])
 def test_alternative_paths_match_oracle(switches):
     """The library's A/B switches select code paths that the default configuration does not take; they are read once per
     process, hence the subprocess.  (1) `SSVB_GEMM_NO_TMA_STORE=1`: the per-thread row-store GEMM epilogue that rows
     without 16-byte alignment take instead of the staged TMA store - Barlow (fused loss epilogue + the un-fused backward
     column reduction) and SwAV (fp32 scores, no split-K).  (2) one view per launch: Sinkhorn without the two-problem
     batching, Barlow's one-view statistics / standardize / finish kernels, the scalar SwAV cross-entropy kernel (the
-    forms the distributed stages and odd shapes still use).  Both against the oracle."""
+    forms the distributed stages and odd shapes still use).  (3) Barlow backward through the fp32 dT buffers, the
+    fused column partials and the two-view finish kernel instead of the closed-form GEMM epilogue (the path
+    normalize=True takes).  All against the oracle."""
     import os
     import subprocess
     import sys
