@@ -634,8 +634,34 @@ namespace ssvb {
 // at scores + p * pstride_s / codes + p * pstride_c (elements).  On the fast path two problems share every launch (each
 // pass and alpha kernel covers both: half of the CTAs per problem), which halves the number of dependent launches of
 // SwAV's two code assignments (utils/losses.py:232); otherwise they run one after the other.
+static int sinkhorn_run_impl(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters, float* codes,
+                             int64_t ld_codes, void* workspace, cudaStream_t s, int nprob, int64_t pstride_s,
+                             int64_t pstride_c, bool scaling_only, bool* batched);
 int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters, float* codes,
                  int64_t ld_codes, void* workspace, cudaStream_t s, int nprob, int64_t pstride_s, int64_t pstride_c) {
+  return sinkhorn_run_impl(scores, b, k, ld_scores, eps, n_iters, codes, ld_codes, workspace, s, nprob, pstride_s, pstride_c,
+                           false, nullptr);
+}
+// Two batched problems WITHOUT the final pass: runs the iterations (passes 0 .. n_iters - 1 and their alpha kernels) and
+// hands back the last scaling vectors alpha [2][kpad] and the maxima smax [2] (both live in `workspace`), from which
+// codes_bk = alpha_k E_bk / sum_k alpha_k E_bk can be rebuilt row by row (swav.cu: swav_ce_sk4_kernel).  Returns false -
+// and launches nothing - when the batched fast path does not apply (the caller then uses sinkhorn_run).
+bool sinkhorn_scaling_only(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters, void* workspace,
+                           cudaStream_t s, int64_t pstride_s, const float** alpha, const float** smax, int* kpad, int* rc) {
+  bool batched = false;
+  // (codes = scores: only its alignment is looked at on this path - nothing is written)
+  *rc = sinkhorn_run_impl(scores, b, k, ld_scores, eps, n_iters, const_cast<float*>(scores), ld_scores, workspace, s, kSkMaxProb,
+                          pstride_s, pstride_s, true, &batched);
+  if (!batched) return false;
+  const SkWs ws = sk_ws(workspace, k);
+  *alpha = ws.alpha;
+  *smax = ws.smax;
+  *kpad = ws.kpad;
+  return true;
+}
+static int sinkhorn_run_impl(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters, float* codes,
+                             int64_t ld_codes, void* workspace, cudaStream_t s, int nprob, int64_t pstride_s,
+                             int64_t pstride_c, bool scaling_only, bool* batched) {
   SkWs ws = sk_ws(workspace, k);
   const int kk = static_cast<int>(k);
   const float iel = SSVB_LOG2E / eps;
@@ -653,6 +679,8 @@ int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, f
 #ifdef SSVB_SK_ROWREG
   batch = false;
 #endif
+  if (batched) *batched = batch;
+  if (scaling_only && !batch) return SSVB_OK;  // nothing launched: the caller falls back to sinkhorn_run
   if (nprob > 1 && !batch) {
     for (int p = 0; p < nprob; ++p)
       SSVB_TRY(sinkhorn_run(scores + p * pstride_s, b, k, ld_scores, eps, n_iters, codes + p * pstride_c, ld_codes, workspace,
@@ -693,6 +721,7 @@ int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, f
       SSVB_LAUNCH_CHECK();
     }
   }
+  if (scaling_only) return SSVB_OK;
   // (n_iters == 0: the final pass follows a fill kernel without the launch_dependents trigger - plain launch)
   if (fast)
     SSVB_TRY(sk_launch_fast<2>(fgrid, smem_fast, s, scores, b, kk, ld_scores, iel, ws, codes, ld_codes, inv_b, n_iters > 0, np,

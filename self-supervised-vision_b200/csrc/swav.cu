@@ -16,6 +16,8 @@ namespace ssvb {
 int sinkhorn_run(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters, float* codes,
                  int64_t ld_codes, void* workspace, cudaStream_t s, int nprob, int64_t pstride_s, int64_t pstride_c);
 size_t sinkhorn_ws_bytes(int64_t k);
+bool sinkhorn_scaling_only(const float* scores, int64_t b, int64_t k, int64_t ld_scores, float eps, int n_iters, void* workspace,
+                           cudaStream_t s, int64_t pstride_s, const float** alpha, const float** smax, int* kpad, int* rc);
 }  // namespace ssvb
 
 using namespace ssvb;
@@ -312,6 +314,121 @@ swav_ce_reg4_kernel(const float* __restrict__ scores, const float* __restrict__ 
   }
 }
 
+// Cross-entropy with the codes rebuilt on the fly: q_v[r, c] = alpha_v[c] E_v[r, c] / sum_c alpha_v[c] E_v[r, c] with
+// E_v = exp((s_v - smax_v) / eps) is exactly what the final Sinkhorn pass writes (sinkhorn.cu PHASE 2), so with the last
+// scaling vectors in hand that pass and the fp32 code matrix (written, then read back here: 2 x 84 MB at 3512 x 3000) are
+// not needed - the row sum of alpha E joins the first block reduction next to the softmax maxima.  Same layout / masks as
+// swav_ce_reg4_kernel.  alpha = [2][kpad] (view 1, view 2), smax = [2].
+template <int V>
+__global__ void __launch_bounds__(256)
+swav_ce_sk4_kernel(const float* __restrict__ scores, const float* __restrict__ alpha, const float* __restrict__ smax, int kpad,
+                   float inv_eps_log2e, int64_t bp, int k, int64_t ld, float inv_t, float coef /* 1/(2 B' T) */,
+                   float* __restrict__ loss_part, __nv_bfloat16* __restrict__ ds, int64_t ldds) {
+  __shared__ float red[8][6];
+  const int64_t r = blockIdx.x;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4* s1p = reinterpret_cast<const float4*>(scores + r * ld);
+  const float4* s2p = reinterpret_cast<const float4*>(scores + (bp + r) * ld);
+  const float4* a1p = reinterpret_cast<const float4*>(alpha);
+  const float4* a2p = reinterpret_cast<const float4*>(alpha + kpad);
+  const int ld4 = static_cast<int>(ld >> 2), kp4 = kpad >> 2;
+  const float sh1 = __ldg(smax) * inv_eps_log2e, sh2 = __ldg(smax + 1) * inv_eps_log2e;
+  float t1[4 * V], t2[4 * V], q1[4 * V], q2[4 * V];
+  float m1 = -INFINITY, m2 = -INFINITY, v1 = 0.f, v2 = 0.f;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    const int c4 = threadIdx.x + e * 256;
+    const bool in = c4 < ld4 && c4 < kp4;
+    const float4 a = in ? __ldg(s1p + c4) : z4, b = in ? __ldg(s2p + c4) : z4;
+    const float4 x = in ? __ldg(a1p + c4) : z4, y = in ? __ldg(a2p + c4) : z4;
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    const float xv[4] = {x.x, x.y, x.z, x.w}, yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool ok = in && c4 * 4 + i < k;
+      t1[4 * e + i] = ok ? av[i] * inv_t : -INFINITY;
+      t2[4 * e + i] = ok ? bv[i] * inv_t : -INFINITY;
+      q1[4 * e + i] = ok ? xv[i] * ex2f(fmaf(av[i], inv_eps_log2e, -sh1)) : 0.f;  // alpha E (un-normalised code)
+      q2[4 * e + i] = ok ? yv[i] * ex2f(fmaf(bv[i], inv_eps_log2e, -sh2)) : 0.f;
+      m1 = fmaxf(m1, t1[4 * e + i]);
+      m2 = fmaxf(m2, t2[4 * e + i]);
+      v1 += q1[4 * e + i];
+      v2 += q2[4 * e + i];
+    }
+  }
+  m1 = warp_max(m1);
+  m2 = warp_max(m2);
+  v1 = warp_sum(v1);
+  v2 = warp_sum(v2);
+  if (lane == 0) { red[w][0] = m1; red[w][1] = m2; red[w][2] = v1; red[w][3] = v2; }
+  __syncthreads();
+  m1 = red[0][0]; m2 = red[0][1]; v1 = red[0][2]; v2 = red[0][3];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) {
+    m1 = fmaxf(m1, red[i][0]); m2 = fmaxf(m2, red[i][1]);
+    v1 += red[i][2]; v2 += red[i][3];
+  }
+  __syncthreads();
+  const float iv1 = 1.f / v1, iv2 = 1.f / v2;
+  float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // e1, e2, a12, a21, sq1, sq2
+#pragma unroll
+  for (int e = 0; e < 4 * V; ++e) {
+    q1[e] *= iv1;  // codes_bk = alpha_k E_bk / v_b  (sinkhorn.cu PHASE 2)
+    q2[e] *= iv2;
+    if ((threadIdx.x + (e >> 2) * 256) * 4 + (e & 3) < k) {
+      v[2] = fmaf(q1[e], t2[e], v[2]);  // sum q1 * (s2/T)
+      v[3] = fmaf(q2[e], t1[e], v[3]);
+    }
+    t1[e] = __expf(t1[e] - m1);  // exp(-inf) = 0 on the padding
+    t2[e] = __expf(t2[e] - m2);
+    v[0] += t1[e];
+    v[1] += t2[e];
+    v[4] += q1[e];
+    v[5] += q2[e];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) red[w][i] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) t += red[ww][i];
+    v[i] = t;
+  }
+  const float lse1 = m1 + __logf(v[0]), lse2 = m2 + __logf(v[1]);
+  if (threadIdx.x == 0) loss_part[r] = -0.5f * ((v[2] - v[4] * lse2) + (v[3] - v[5] * lse1));
+  const float i1 = v[5] / v[0], i2 = v[4] / v[1];  // softmax(s/T) * sum(q of the other view)
+  uint2* d1 = reinterpret_cast<uint2*>(ds + r * ldds);
+  uint2* d2 = reinterpret_cast<uint2*>(ds + (bp + r) * ldds);
+  const int ldds4 = static_cast<int>(ldds >> 2);
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    const int c4 = threadIdx.x + e * 256;
+    if (c4 < ldds4) {
+      float g1[4], g2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool ok = c4 * 4 + i < k;
+        g1[i] = ok ? -(q2[4 * e + i] - t1[4 * e + i] * i1) * coef : 0.f;  // d loss / d s1
+        g2[i] = ok ? -(q1[4 * e + i] - t2[4 * e + i] * i2) * coef : 0.f;  // d loss / d s2
+      }
+      __nv_bfloat162 a0 = __floats2bfloat162_rn(g1[0], g1[1]), a1 = __floats2bfloat162_rn(g1[2], g1[3]);
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(g2[0], g2[1]), b1 = __floats2bfloat162_rn(g2[2], g2[3]);
+      uint2 pa, pb;
+      pa.x = *reinterpret_cast<uint32_t*>(&a0); pa.y = *reinterpret_cast<uint32_t*>(&a1);
+      pb.x = *reinterpret_cast<uint32_t*>(&b0); pb.y = *reinterpret_cast<uint32_t*>(&b1);
+      d1[c4] = pa;
+      d2[c4] = pb;
+    }
+  }
+}
+
 // out[r, c] = go * in[r, c]  (+ optionally go * in2[r, c]) for c < d
 __global__ void scale_rows_kernel(const float* __restrict__ in, int64_t ldi, int64_t rows, int d,
                                   const float* __restrict__ grad_out, float* __restrict__ out, int64_t ldo) {
@@ -487,6 +604,28 @@ int ssvb_swav_fwd(const float* z1, const float* z2, const float* bank, const flo
   SSVB_TRY(stage_scores(z1, z2, bank, prototypes, m, ld_z1, ld_z2, ld_bank, ld_proto, sv, ws.scores, s));
   // codes per view (Sinkhorn normalises over the B' rows of ONE view)
   // the two views' code assignments (utils/losses.py:232) are independent problems of one shape: batched launches
+  static const bool no_fuse = getenv("SSVB_SWAV_NO_FUSED_CODES") != nullptr;  // A/B switch: final pass + code matrix
+  const float *alpha = nullptr, *smax = nullptr;
+  int kpad = 0, rc = SSVB_OK;
+  if (!no_fuse && m.kp8 <= 4 * 1024 && !(reinterpret_cast<uintptr_t>(sv.ds) & 7) &&
+      sinkhorn_scaling_only(ws.scores, m.bp, k, m.kp4, eps, n_iters, ws.sk, s, m.bp * m.kp4, &alpha, &smax, &kpad, &rc)) {
+    // the iteration ran without its final pass: the cross-entropy kernel rebuilds each code row from the scaling vectors
+    SSVB_TRY(rc);
+    const unsigned grid = static_cast<unsigned>(m.bp);
+    const float iel = SSVB_LOG2E / eps, it = 1.f / temperature, coef = 0.5f / (static_cast<float>(m.bp) * temperature);
+#define SSVB_CESK(V)                                                                                                       \
+  swav_ce_sk4_kernel<V><<<grid, 256, 0, s>>>(ws.scores, alpha, smax, kpad, iel, m.bp, static_cast<int>(k), m.kp4, it, coef, \
+                                             ws.loss_part, sv.ds, m.kp8)
+    if (m.kp8 <= 1 * 1024) SSVB_CESK(1);
+    else if (m.kp8 <= 2 * 1024) SSVB_CESK(2);
+    else if (m.kp8 <= 3 * 1024) SSVB_CESK(3);
+    else SSVB_CESK(4);
+#undef SSVB_CESK
+    SSVB_LAUNCH_CHECK();
+    sum_partials_kernel<<<1, 1024, 0, s>>>(ws.loss_part, static_cast<int>(m.bp), 1.f / static_cast<float>(m.bp), loss);
+    SSVB_LAUNCH_CHECK();
+    return SSVB_OK;
+  }
   SSVB_TRY(sinkhorn_run(ws.scores, m.bp, k, m.kp4, eps, n_iters, ws.codes, m.kp4, ws.sk, s, 2, m.bp * m.kp4, m.bp * m.kp4));
   return stage_ce(ws.scores, ws.codes, m, m.bp, temperature, sv, ws.loss_part, loss, s);
 }

@@ -480,8 +480,8 @@ def test_swav_oracle(S, nb, nbank, k, d):
 @pytest.mark.parametrize("switches", [
     {"SSVB_GEMM_NO_TMA_STORE": "1"},
     {"SSVB_SK_NO_BATCH": "1", "SSVB_BARLOW_NO_X2": "1", "SSVB_SWAV_NO_CE4": "1", "SSVB_BARLOW_NO_FUSED_BWD": "1"},
-    {"SSVB_BARLOW_NO_FUSED_BWD": "1"},
-], ids=["row-store-epilogue", "one-view-per-launch", "barlow-dT-round-trip"])
+    {"SSVB_BARLOW_NO_FUSED_BWD": "1", "SSVB_SWAV_NO_FUSED_CODES": "1"},
+], ids=["row-store-epilogue", "one-view-per-launch", "unfused-epilogues"])
 def test_alternative_paths_match_oracle(switches):
     """The library's A/B switches select code paths that the default configuration does not take; they are read once per
     process, hence the subprocess.  (1) `SSVB_GEMM_NO_TMA_STORE=1`: the per-thread row-store GEMM epilogue that rows
@@ -490,7 +490,8 @@ def test_alternative_paths_match_oracle(switches):
     batching, Barlow's one-view statistics / standardize / finish kernels, the scalar SwAV cross-entropy kernel (the
     forms the distributed stages and odd shapes still use).  (3) Barlow backward through the fp32 dT buffers, the
     fused column partials and the two-view finish kernel instead of the closed-form GEMM epilogue (the path
-    normalize=True takes).  All against the oracle."""
+    normalize=True takes), and SwAV with the final Sinkhorn pass + fp32 code matrix instead of the codes rebuilt inside
+    the cross-entropy kernel.  All against the oracle."""
     import os
     import subprocess
     import sys
