@@ -679,7 +679,9 @@ __global__ void barlow_fwd_finish_kernel(const float* __restrict__ xrow, int nro
   const int col = blockIdx.x * 32 + threadIdx.x;
   float s1 = 0.f, s2 = 0.f;
   if (col < d) {
+#pragma unroll 4
     for (int i = threadIdx.y; i < nrow; i += 8) s1 += xrow[static_cast<int64_t>(i) * d + col];
+#pragma unroll 8
     for (int i = threadIdx.y; i < ncol; i += 8) s2 += xcol[static_cast<int64_t>(i) * d + col];
   }
   sh1[threadIdx.y][threadIdx.x] = s1;
