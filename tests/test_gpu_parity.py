@@ -425,7 +425,8 @@ def barlow_inputs(n, d, corr=0.7):
     return zi.astype(np.float32), zj.astype(np.float32)
 
 
-@pytest.mark.parametrize("n,d,norm", [(512, 4096, False), (256, 1000, False), (200, 264, True), (2048, 8192, False)])
+@pytest.mark.parametrize("n,d,norm", [(512, 4096, False), (256, 1000, False), (200, 264, True), (200, 264, False),
+                                      (2048, 8192, False)])   # norm False: closed-form backward in the GEMM epilogue (ragged M / N tails)
 def test_barlow_oracle(S, n, d, norm):
     zi, zj = barlow_inputs(n, d)
     a, b = dev(zi), dev(zj)
@@ -474,6 +475,24 @@ def test_swav_oracle(S, nb, nbank, k, d):
     loss = S.SwavLoss(0.1, 0.05, 3)(a, b, p, dev(bank, False) if nbank else None)
     loss.backward()
     check(loss.item(), [a.grad, b.grad, p.grad], ref[0], ref[1:], f"swav nb={nb} k={k}")
+
+
+@pytest.mark.parametrize("iters,temp,eps", [(0, 0.1, 0.05), (1, 0.1, 0.05), (5, 0.2, 0.03)])
+def test_swav_iteration_counts(S, iters, temp, eps):
+    """sinkhorn_iters = 0 (no iteration: the final-pass + code-matrix path), 1 (the scaling vectors come from the first
+    alpha kernel alone) and 5, with other temperatures / eps: the codes rebuilt inside the cross-entropy kernel must
+    match the reference's dense iteration (utils/losses.py:213-235) for any count."""
+    def unit(x):
+        return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+    z1 = unit(randn(0, 160, 64))
+    z2 = unit(0.6 * z1 + 0.4 * randn(1, 160, 64))
+    c = unit(randn(2, 500, 64))
+    bank = unit(randn(3, 90, 64))
+    ref = O.swav(z1, z2, c, bank, temp, eps, iters)
+    a, b, p = dev(z1), dev(z2), dev(c)
+    loss = S.SwavLoss(temp, eps, iters)(a, b, p, dev(bank, False))
+    loss.backward()
+    check(loss.item(), [a.grad, b.grad, p.grad], ref[0], ref[1:], f"swav iters={iters}")
 
 
 # ------------------------------------------------------------------------------------------------ GEMM epilogue paths
