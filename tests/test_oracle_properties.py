@@ -88,3 +88,51 @@ def test_dino_gradient_rows_sum_to_zero_and_fd(bs, nv, k, seed):
     e[0, 0, 0] = 1e-6
     num = (O.dino(t, s + e, 0.1, 0.04, c)[0] - O.dino(t, s - e, 0.1, 0.04, c)[0]) / 2e-6
     assert abs(num - ds[0, 0, 0]) <= 1e-5 * max(1.0, abs(num))
+
+
+@settings(max_examples=20, deadline=None)
+@given(n=st.integers(4, 40), d=st.integers(2, 12), seed=st.integers(0, 10_000), lm=st.sampled_from([0.005, 0.05]))
+def test_barlow_closed_form_standardisation_backward(n, d, seed, lm):
+    """The identity the fused Barlow backward relies on (csrc/barlow.cu, `barlow_fwd_finish_kernel` / `EPI_BARLOW_BWD`):
+    with x~ standardised and dT = dL/dx~, mean_n(dT) = 0 and sum_n(dT x~) = row / column sums of dC .* C, so
+    dx = (dT - x~ * rowsum(dC .* C) / (n - 1)) / std needs no pass over dT.  Checked against the oracle's gradient, which
+    follows the reference's autograd form (utils/losses.py:136-142)."""
+    zi = _rand(seed, n, d) * 1.3 + 0.2
+    zj = 0.7 * zi + 0.3 * _rand(seed + 1, n, d)
+    _, dzi, dzj = O.barlow(zi, zj, False, lm)
+    sdi, sdj = zi.std(0, ddof=1), zj.std(0, ddof=1)
+    ti, tj = (zi - zi.mean(0)) / sdi, (zj - zj.mean(0)) / sdj
+    c = ti.T @ tj / n
+    w = np.full((d, d), lm)
+    np.fill_diagonal(w, 1.0)
+    dc = 2.0 * (c - np.eye(d)) * w
+    dti, dtj = tj @ dc.T / n, ti @ dc / n
+    assert np.abs(dti.mean(0)).max() < 1e-12 and np.abs(dtj.mean(0)).max() < 1e-12
+    m2_i, m2_j = (dc * c).sum(1) / (n - 1), (dc * c).sum(0) / (n - 1)
+    np.testing.assert_allclose((dti * ti).sum(0) / (n - 1), m2_i, rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose((dtj * tj).sum(0) / (n - 1), m2_j, rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose((dti - ti * m2_i) / sdi, dzi, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose((dtj - tj * m2_j) / sdj, dzj, rtol=1e-8, atol=1e-12)
+
+
+@settings(max_examples=20, deadline=None)
+@given(b=st.integers(2, 30), k=st.integers(2, 20), iters=st.integers(1, 5), seed=st.integers(0, 10_000))
+def test_sinkhorn_codes_from_scaling_vectors(b, k, iters, seed):
+    """The identity the fused SwAV cross-entropy relies on (csrc/swav.cu `swav_ce_sk4_kernel`, csrc/sinkhorn.cu): in
+    scaling-vector form E = exp((s - max)/eps), alpha_k <- (1/K) / sum_b E_bk beta_b, beta_b <- (1/B) / sum_k alpha_k E_bk,
+    the reference's codes (utils/losses.py:213-224) are alpha_k E_bk / sum_k alpha_k E_bk with the LAST alpha - no final
+    pass over a stored Q is needed."""
+    z = _rand(seed, b, 8)
+    c = _rand(seed + 1, k, 8)
+    z /= np.linalg.norm(z, axis=1, keepdims=True)
+    c /= np.linalg.norm(c, axis=1, keepdims=True)
+    s = z @ c.T
+    eps = 0.05
+    e = np.exp((s - s.max()) / eps)
+    beta = np.ones(b)
+    for _ in range(iters):
+        alpha = (1.0 / k) / (e * beta[:, None]).sum(0)
+        beta = (1.0 / b) / (e * alpha[None, :]).sum(1)
+    codes = e * alpha[None, :]
+    codes /= codes.sum(1, keepdims=True)
+    np.testing.assert_allclose(codes, O.sinkhorn(s, eps, iters), rtol=1e-9, atol=1e-15)
