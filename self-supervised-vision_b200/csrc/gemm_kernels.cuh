@@ -391,8 +391,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else {
         // EPI_BARLOW: loss terms + dC (bf16); 64 columns (128 bytes of bf16 per row) per staged block
-#pragma unroll 1
         float rs_acc = 0.f;  // sum over this tile's columns of dC .* C (row = this thread)
+        // (no `unroll 1` here: the compiler's own unrolling of these BN / 64 = 4 blocks measured 193 vs 202 us at cfg3)
         for (int cc = 0; cc < BN / 64; ++cc) {
           const int col0 = tn * BN + cc * 64;
           uint32_t pk[32];

@@ -429,19 +429,6 @@ swav_ce_sk4_kernel(const float* __restrict__ scores, const float* __restrict__ a
   }
 }
 
-// out[r, c] = go * in[r, c]  (+ optionally go * in2[r, c]) for c < d
-__global__ void scale_rows_kernel(const float* __restrict__ in, int64_t ldi, int64_t rows, int d,
-                                  const float* __restrict__ grad_out, float* __restrict__ out, int64_t ldo) {
-  const float go = __ldg(grad_out);
-  const int64_t total = rows * d;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / d;
-    const int c = static_cast<int>(i - r * d);
-    out[r * ldo + c] = in[r * ldi + c] * go;
-  }
-}
-
 // the three gradient outputs in one launch: segment g of (in, ldi, rows, out, ldo); out[r, c] = go * in[r, c], c < d
 struct ScaleSeg {
   const float* in;
