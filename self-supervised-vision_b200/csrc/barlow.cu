@@ -275,17 +275,29 @@ __global__ void col_finalize_kernel(const float* __restrict__ part, int nsplit, 
 // forward statistics of both views: blockIdx.y = view
 __global__ void col_finalize_x2_kernel(const float* __restrict__ part, int64_t view_stride, int nsplit, TwoViews v, int64_t n,
                                        int d, TwoStats st) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= d) return;
+  // block (32 columns x 8 stripe phases), fixed-order combine: 2 x d/32 CTAs instead of 2 x d/256 serial column loops
+  __shared__ float sh1[8][33], sh2[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
   const bool second = blockIdx.y != 0;
   part += second ? view_stride : 0;
+  float s1 = 0.f, s2 = 0.f;
+  if (col < d) {
+#pragma unroll 4
+    for (int i = threadIdx.y; i < nsplit; i += 8) {
+      s1 += part[(static_cast<int64_t>(i) * 2 + 0) * d + col];
+      s2 += part[(static_cast<int64_t>(i) * 2 + 1) * d + col];
+    }
+  }
+  sh1[threadIdx.y][threadIdx.x] = s1;
+  sh2[threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y != 0 || col >= d) return;
+  s1 = 0.f;
+  s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1 += sh1[i][threadIdx.x]; s2 += sh2[i][threadIdx.x]; }
   const float* x = second ? v.x1 : v.x0;
   const float* inv_row = second ? v.inv1 : v.inv0;
-  float s1 = 0.f, s2 = 0.f;
-  for (int i = 0; i < nsplit; ++i) {
-    s1 += part[(static_cast<int64_t>(i) * 2 + 0) * d + col];
-    s2 += part[(static_cast<int64_t>(i) * 2 + 1) * d + col];
-  }
   const float fn = static_cast<float>(n);
   const float v0 = x[col] * (inv_row ? inv_row[0] : 1.f);
   const float var = (s2 - s1 * s1 / fn) / (fn - 1.f);
@@ -660,18 +672,19 @@ __global__ void barlow_fwd_finish_kernel(const float* __restrict__ xrow, int nro
                                          int d, float inv_nm1, const float* __restrict__ rstd_i,
                                          const float* __restrict__ rstd_j, float* __restrict__ q_i, float* __restrict__ q_j,
                                          const float* __restrict__ loss_part, int nloss, float* __restrict__ loss) {
-  __shared__ float sh1[8][33], sh2[8][33];
+  constexpr int kPh = 32;  // block (32 columns x 32 partial-row phases)
+  __shared__ float sh1[kPh][33], sh2[kPh][33];
   const int tid = threadIdx.y * 32 + threadIdx.x;
   if (blockIdx.x == gridDim.x - 1) {
     float v = 0.f;
-    for (int i = tid; i < nloss; i += 256) v += loss_part[i];
+    for (int i = tid; i < nloss; i += 32 * kPh) v += loss_part[i];
     v = warp_sum(v);
     if (threadIdx.x == 0) sh1[threadIdx.y][0] = v;
     __syncthreads();
     if (tid == 0) {
       float t = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t += sh1[i][0];
+      for (int i = 0; i < kPh; ++i) t += sh1[i][0];
       loss[0] = t;
     }
     return;
@@ -679,10 +692,9 @@ __global__ void barlow_fwd_finish_kernel(const float* __restrict__ xrow, int nro
   const int col = blockIdx.x * 32 + threadIdx.x;
   float s1 = 0.f, s2 = 0.f;
   if (col < d) {
-#pragma unroll 4
-    for (int i = threadIdx.y; i < nrow; i += 8) s1 += xrow[static_cast<int64_t>(i) * d + col];
+    for (int i = threadIdx.y; i < nrow; i += kPh) s1 += xrow[static_cast<int64_t>(i) * d + col];
 #pragma unroll 8
-    for (int i = threadIdx.y; i < ncol; i += 8) s2 += xcol[static_cast<int64_t>(i) * d + col];
+    for (int i = threadIdx.y; i < ncol; i += kPh) s2 += xcol[static_cast<int64_t>(i) * d + col];
   }
   sh1[threadIdx.y][threadIdx.x] = s1;
   sh2[threadIdx.y][threadIdx.x] = s2;
@@ -690,7 +702,7 @@ __global__ void barlow_fwd_finish_kernel(const float* __restrict__ xrow, int nro
   if (threadIdx.y == 0 && col < d) {
     float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a += sh1[i][threadIdx.x]; b += sh2[i][threadIdx.x]; }
+    for (int i = 0; i < kPh; ++i) { a += sh1[i][threadIdx.x]; b += sh2[i][threadIdx.x]; }
     q_i[col] = a * inv_nm1 * rstd_i[col];
     q_j[col] = b * inv_nm1 * rstd_j[col];
   }
@@ -713,8 +725,9 @@ int stats_and_standardize_x2(const float* zi, int64_t ld_zi, const float* zj, in
   dim3 grid(static_cast<unsigned>(ceil_div(d, 128)), kStatSplit, 2), block(32, 8);
   col_stats4_x2_kernel<<<grid, block, 0, s>>>(v, n, static_cast<int>(d), colpart, part_view_stride);
   SSVB_LAUNCH_CHECK();
-  col_finalize_x2_kernel<<<dim3(static_cast<unsigned>(ceil_div(d, 256)), 2), 256, 0, s>>>(colpart, part_view_stride, kStatSplit, v,
-                                                                                          n, static_cast<int>(d), st);
+  col_finalize_x2_kernel<<<dim3(static_cast<unsigned>(ceil_div(d, 32)), 2), dim3(32, 8), 0, s>>>(colpart, part_view_stride,
+                                                                                                 kStatSplit, v, n,
+                                                                                                 static_cast<int>(d), st);
   SSVB_LAUNCH_CHECK();
   const int64_t total = n * (d / 4);
   int64_t g = ceil_div(total, 256 * 4);
@@ -775,7 +788,7 @@ int ssvb_barlow_fwd(const float* zi, const float* zj, int64_t n, int64_t d, int6
   p.bl_colpart = ws.xcol;
   SSVB_TRY(launch_gemm({sv.xi, d, true}, {sv.xj, d, true}, p, 256, EPI_BARLOW, kMaxGemmCtas, s));
   // every launched CTA wrote its partial (persistent kernel, grid = min(tiles, SMs)): sum exactly those, no memset
-  barlow_fwd_finish_kernel<<<static_cast<unsigned>(ceil_div(d, 32) + 1), dim3(32, 8), 0, s>>>(
+  barlow_fwd_finish_kernel<<<static_cast<unsigned>(ceil_div(d, 32) + 1), dim3(32, 32), 0, s>>>(
       ws.xrow, static_cast<int>(ceil_div(d, 256)), ws.xcol, static_cast<int>(ceil_div(d, 128) * 4), static_cast<int>(d),
       1.f / static_cast<float>(n - 1), sv.rstd_i, sv.rstd_j, sv.q_i, sv.q_j, ws.loss_partials,
       gemm_grid(ceil_div(d, 128) * ceil_div(d, 256), kMaxGemmCtas), loss);
